@@ -1,0 +1,121 @@
+"""ctypes binding of libbioseqdb_gpu.so (include/bioseqdb_gpu.h). The library is built in-tree by
+``bioseqdb_b200/csrc/Makefile``; there is no CPU fallback -- if it is missing or no GPU is present the
+calls fail loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbioseqdb_gpu.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+ROW_DTYPE = np.dtype([
+    ("rb", "<i8"), ("re", "<i8"), ("pos", "<i8"), ("hash", "<u8"),
+    ("qb", "<i4"), ("qe", "<i4"), ("rid", "<i4"), ("score", "<i4"), ("truesc", "<i4"), ("sub", "<i4"),
+    ("csub", "<i4"), ("sub_n", "<i4"), ("w", "<i4"), ("seedcov", "<i4"), ("secondary", "<i4"),
+    ("seedlen0", "<i4"), ("n_comp", "<i4"), ("frac_rep", "<f4"),
+    ("is_rev", "<i4"), ("mapq", "<i4"), ("NM", "<i4"), ("flag", "<i4"),
+    ("cigar_off", "<u4"), ("n_cigar", "<u4"), ("ref_id", "<i8"),
+])
+assert ROW_DTYPE.itemsize == 120
+HOLE_DTYPE = np.dtype([("offset", "<i8"), ("len", "<i4"), ("amb", "S1"), ("_pad", "V3")])
+
+ARR_PAC, ARR_OCC, ARR_SA, ARR_ANN_OFFSET, ARR_ANN_LEN, ARR_ANN_ID, ARR_COUNT = range(7)
+
+
+class BsqOpts(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "min_seed_len", "max_occ", "a", "b", "pen_clip3", "pen_clip5", "zdrop", "w", "o_del", "e_del", "o_ins", "e_ins")]
+
+
+class BsqResult(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("row_off", C.POINTER(C.c_uint64)), ("rows", C.c_void_p),
+                ("cigar", C.POINTER(C.c_uint32)), ("n_cigar_words", C.c_uint64)]
+
+
+class BsqTiming(C.Structure):
+    _fields_ = [("h2d", C.c_float), ("seed", C.c_float), ("chain", C.c_float), ("extend", C.c_float), ("finalize", C.c_float),
+                ("d2h", C.c_float), ("total", C.c_float), ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+class BsqMeta(C.Structure):
+    _fields_ = [("l_pac", C.c_int64), ("seq_len", C.c_uint64), ("primary", C.c_uint64), ("L2", C.c_uint64 * 5), ("n_anns", C.c_uint64),
+                ("sa_bytes", C.c_uint32), ("built", C.c_uint32), ("arr_bytes", C.c_uint64 * ARR_COUNT), ("build_ms", C.c_double),
+                ("build_launches", C.c_uint64), ("sort_pass_bytes", C.c_uint64)]
+
+
+def build_library(force: bool = False) -> str:
+    """Compile libbioseqdb_gpu.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.check_call(["make", "-s", "-C", CSRC, "clean"])
+    subprocess.check_call(["make", "-s", "-j8", "-C", CSRC])
+    return LIB_PATH
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libbioseqdb_gpu.so is not built (run __graft_entry__.build() or make -C bioseqdb_b200/csrc); "
+                           "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, i64, u32, i32 = C.c_void_p, C.c_uint64, C.c_int64, C.c_uint32, C.c_int32
+    L.bsq_last_error.restype = C.c_char_p
+    L.bsq_device_count.restype = C.c_int
+    L.bsq_opts_init.argtypes = [C.POINTER(BsqOpts)]
+    L.bsq_index_new.restype = vp
+    L.bsq_index_new.argtypes = [C.POINTER(BsqOpts), C.c_int]
+    L.bsq_index_set_opts.argtypes = [vp, C.POINTER(BsqOpts)]
+    L.bsq_index_add_ref.argtypes = [vp, i64, vp, u32, vp, u32]
+    L.bsq_index_build.argtypes = [vp]
+    L.bsq_index_free.argtypes = [vp]
+    L.bsq_align_batch.argtypes = [vp, vp, vp, vp, u64, C.POINTER(C.POINTER(BsqResult))]
+    L.bsq_result_free.argtypes = [C.POINTER(BsqResult)]
+    L.bsq_last_timing.argtypes = [vp, C.POINTER(BsqTiming)]
+    L.bsq_reads_upload.argtypes = [vp, vp, vp, vp, u64]
+    L.bsq_align_resident.argtypes = [vp]
+    L.bsq_result_download.argtypes = [vp, C.POINTER(C.POINTER(BsqResult))]
+    L.bsq_index_get_meta.argtypes = [vp, C.POINTER(BsqMeta)]
+    L.bsq_index_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.bsq_index_download.argtypes = [vp, C.c_int, vp, u64]
+    L.bsq_index_alloc_replica.argtypes = [vp, C.POINTER(BsqMeta)]
+    L.bsq_index_bwt_plain.argtypes = [vp, vp]
+    L.bsq_index_sa_sampled.argtypes = [vp, vp, u64]
+    L.bsq_debug_seed.argtypes = [vp, vp, vp, u64, vp, u32, vp]
+    L.bsq_debug_ksw_extend.argtypes = [C.POINTER(BsqOpts), C.c_int, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.bsq_debug_ksw_global.argtypes = [C.POINTER(BsqOpts), C.c_int, u64, vp, vp, vp, vp, vp, vp, vp, u32, vp]
+    L.bsq_bench_gather.argtypes = [vp, u64, C.c_int, C.POINTER(C.c_double)]
+    L.bsq_bench_dpx.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.bsq_set_counters.argtypes = [vp, C.c_int]
+    L.bsq_get_counters.argtypes = [vp, vp]
+    _LIB = L
+    return L
+
+
+ABI_SYMBOLS = [
+    "bsq_last_error", "bsq_device_count", "bsq_opts_init", "bsq_index_new", "bsq_index_set_opts", "bsq_index_add_ref", "bsq_index_build",
+    "bsq_index_free", "bsq_align_batch", "bsq_result_free", "bsq_last_timing", "bsq_reads_upload", "bsq_align_resident", "bsq_result_download",
+    "bsq_index_get_meta", "bsq_index_device_ptr", "bsq_index_download", "bsq_index_alloc_replica", "bsq_index_bwt_plain", "bsq_index_sa_sampled",
+    "bsq_debug_seed", "bsq_debug_ksw_extend", "bsq_debug_ksw_global", "bsq_bench_gather", "bsq_bench_dpx", "bsq_set_counters", "bsq_get_counters",
+]
+
+
+class BsqError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise BsqError(lib().bsq_last_error().decode(errors="replace"))
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,283 @@
+"""Python mirror of the reference's bwa adapter interface (bioseqdb/bwa.h:15-48): ``BwaIndex`` with
+``add_ref_sequence`` / ``build`` / ``align_sequence`` and ``BwaMatch`` rows, plus the batched entry point
+that replaces the per-read loop of ``nuclseq_multi_search_bwa`` (bioseqdb/extension.cpp:362-370).
+Everything below the class runs on the GPU through the C ABI (include/bioseqdb_gpu.h)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import BsqMeta, BsqOpts, BsqResult, BsqTiming, ROW_DTYPE, check, ptr
+from .sequence import NucleotideSequence, nuclseq_from_text, nuclseq_to_text
+
+_CIGAR_CHR = "MIDNSHP=XB"  # htslib's table applied to bwa op codes (bwa.cpp:70-77): soft clip prints as 'N'
+
+
+@dataclass
+class BwaMatch:  # bwa.h:15-30
+    ref_id: int
+    ref_subseq: bytes
+    ref_match_begin: int
+    ref_match_end: int
+    ref_match_len: int
+    query_subseq: bytes
+    query_match_begin: int
+    query_match_end: int
+    query_match_len: int
+    is_primary: bool
+    is_secondary: bool
+    is_reverse: bool
+    cigar: str
+    score: int
+
+
+def bwa_opts(min_seed_len=19, max_occ=None, match_score=1, mismatch_penalty=4, pen_clip3=5, pen_clip5=5, zdrop=100,
+             bandwidth=100, o_del=6, o_ins=6, e_del=1, e_ins=1):
+    """The SQL function bwa_opts() (bioseqdb--0.0.0.sql:175-194) INCLUDING its positional mix-up: the ROW is
+    built as (..., o_del, o_ins, e_del, e_ins) but the composite's fields are (..., o_del, e_del, o_ins, e_ins),
+    so a caller's o_ins lands in e_del and e_del in o_ins. Returns the composite as a dict
+    keyed by the field names the C side reads (extension.cpp:220-231); None = SQL NULL."""
+    row = (min_seed_len, max_occ, match_score, mismatch_penalty, pen_clip3, pen_clip5, zdrop, bandwidth, o_del, o_ins, e_del, e_ins)
+    names = ("min_seed_len", "max_occ", "match_score", "mismatch_penalty", "pen_clip3", "pen_clip5", "zdrop", "bandwidth",
+             "o_del", "e_del", "o_ins", "e_ins")
+    return dict(zip(names, row))
+
+
+def cigar_to_string(words) -> str:
+    return "".join("%d%s" % (int(w) >> 4, _CIGAR_CHR[int(w) & 0xF]) for w in words)
+
+
+class AlignResult:
+    """Rows of one batch: ``row_off`` (n+1), ``rows`` (ROW_DTYPE), ``cigar`` (u32 words)."""
+
+    def __init__(self, row_off, rows, cigar):
+        self.row_off, self.rows, self.cigar = row_off, rows, cigar
+
+    def rows_of(self, i):
+        return self.rows[int(self.row_off[i]):int(self.row_off[i + 1])]
+
+    def cigar_of(self, row) -> str:
+        return cigar_to_string(self.cigar[int(row["cigar_off"]):int(row["cigar_off"]) + int(row["n_cigar"])])
+
+
+class BwaIndex:
+    """BwaIndex of bioseqdb/bwa.h:32-48 over libbioseqdb_gpu.so."""
+
+    def __init__(self, device: int = 0, opts: BsqOpts | None = None):
+        self.L = _lib.lib()
+        if opts is None:
+            opts = BsqOpts()
+            self.L.bsq_opts_init(C.byref(opts))
+        self.options = opts
+        self.h = self.L.bsq_index_new(C.byref(opts), device)
+        if not self.h:
+            raise _lib.BsqError(self.L.bsq_last_error().decode())
+        self.device = device
+        self.n_rows = 0
+        self._refs = []  # (id, NucleotideSequence) kept for ref_subseq extraction (extract_reference_subseq, bwa.cpp:55-68)
+        self._lrand_state = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.bsq_index_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    # ---- options: bwa_index_from_query's writes (extension.cpp:220-231)
+    def set_options_from_composite(self, opts: dict | None):
+        o = opts or {}
+
+        def get(name, default):
+            v = o.get(name)
+            if v is None:
+                return default
+            if v < 0:
+                raise ValueError("bwa_opt %s must be nonnegative" % name)
+            return int(v)
+        b = BsqOpts(get("min_seed_len", 19), get("max_occ", max(500, self.n_rows * 2)), get("match_score", 1), get("mismatch_penalty", 4),
+                    get("pen_clip3", 5), get("pen_clip5", 5), get("zdrop", 100), get("bandwidth", 100),
+                    get("o_del", 6), get("e_del", 1), get("o_ins", 6), get("e_ins", 1))
+        self.set_options(b)
+
+    def set_options(self, b: BsqOpts):
+        check(self.L.bsq_index_set_opts(self.h, C.byref(b)))
+        self.options = b
+
+    # ---- reference rows
+    def add_ref_sequence(self, ref_id: int, seq):
+        if not isinstance(seq, NucleotideSequence):
+            seq = nuclseq_from_text(seq)
+        holes = np.ascontiguousarray(seq.holes)
+        pac = np.ascontiguousarray(seq.pac)
+        check(self.L.bsq_index_add_ref(self.h, int(ref_id), ptr(pac), seq.len, ptr(holes) if len(holes) else None, len(holes)))
+        self._refs.append((int(ref_id), seq))
+        self.n_rows += 1
+
+    def build(self):
+        check(self.L.bsq_index_build(self.h))
+
+    def meta(self) -> BsqMeta:
+        m = BsqMeta()
+        check(self.L.bsq_index_get_meta(self.h, C.byref(m)))
+        return m
+
+    def download(self, what: int) -> np.ndarray:
+        m = self.meta()
+        n = int(m.arr_bytes[what])
+        out = np.empty(n, dtype=np.uint8)
+        check(self.L.bsq_index_download(self.h, what, ptr(out), n))
+        return out
+
+    def bwt_plain(self) -> np.ndarray:
+        m = self.meta()
+        out = np.zeros((int(m.seq_len) + 15) // 16, dtype=np.uint32)
+        check(self.L.bsq_index_bwt_plain(self.h, ptr(out)))
+        return out
+
+    def sa_sampled(self) -> np.ndarray:
+        m = self.meta()
+        n_sa = (int(m.seq_len) + 32) // 32
+        out = np.zeros(n_sa, dtype=np.uint64)
+        check(self.L.bsq_index_sa_sampled(self.h, ptr(out), n_sa))
+        return out
+
+    # ---- lrand48 ids: mem_align1 draws one per read; the host keeps the generator
+    def next_ids(self, n: int) -> np.ndarray:
+        from .synth import lrand48_ids
+        ids, self._lrand_state = lrand48_ids(n, self._lrand_state) if n <= 4096 else self._ids_big(n)
+        return ids
+
+    def _ids_big(self, n):
+        from .synth import lrand48_ids_fast
+        if self._lrand_state == 0:
+            ids = lrand48_ids_fast(n)
+            # recover the state after n draws: one more scalar pass over the last block is cheap
+            a, c, m = 0x5DEECE66D, 0xB, (1 << 48) - 1
+            x = 0
+            # jump: x_n = A^n x_0 + C (A^n - 1)/(A - 1); computed by square-and-multiply on the affine map
+            A, Cc, k = 1, 0, n
+            ba, bc = a, c
+            while k:
+                if k & 1:
+                    A, Cc = (A * ba) & m, (Cc * ba + bc) & m
+                ba, bc = (ba * ba) & m, (bc * ba + bc) & m
+                k >>= 1
+            x = (A * x + Cc) & m
+            return ids, x
+        from .synth import lrand48_ids
+        return lrand48_ids(n, self._lrand_state)
+
+    # ---- alignment
+    def _collect(self, res_p) -> AlignResult:
+        r = res_p.contents
+        n = int(r.n_reads)
+        row_off = np.ctypeslib.as_array(r.row_off, shape=(n + 1,)).copy()
+        total = int(row_off[n])
+        rows = np.zeros(total, dtype=ROW_DTYPE)
+        if total:
+            C.memmove(ptr(rows), r.rows, total * ROW_DTYPE.itemsize)
+        ncw = int(r.n_cigar_words)
+        cigar = np.ctypeslib.as_array(r.cigar, shape=(max(ncw, 1),))[:ncw].copy()
+        self.L.bsq_result_free(res_p)
+        return AlignResult(row_off, rows, cigar)
+
+    def align_batch(self, seqs: np.ndarray, offs: np.ndarray, ids: np.ndarray | None = None) -> AlignResult:
+        """reads: concatenated ASCII bytes, offs (n+1). One call = the whole per-read loop of extension.cpp:362-370."""
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        n = len(offs) - 1
+        ids = self.next_ids(n) if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+        res = C.POINTER(BsqResult)()
+        check(self.L.bsq_align_batch(self.h, ptr(seqs), ptr(offs), ptr(ids), n, C.byref(res)))
+        return self._collect(res)
+
+    def upload(self, seqs, offs, ids):
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        check(self.L.bsq_reads_upload(self.h, ptr(seqs), ptr(offs), ptr(ids), len(offs) - 1))
+
+    def align_resident(self):
+        check(self.L.bsq_align_resident(self.h))
+
+    def download_result(self) -> AlignResult:
+        res = C.POINTER(BsqResult)()
+        check(self.L.bsq_result_download(self.h, C.byref(res)))
+        return self._collect(res)
+
+    def timing(self) -> BsqTiming:
+        t = BsqTiming()
+        check(self.L.bsq_last_timing(self.h, C.byref(t)))
+        return t
+
+    def set_counters(self, on: bool):
+        check(self.L.bsq_set_counters(self.h, int(on)))
+
+    def counters(self) -> dict:
+        v = np.zeros(8, dtype=np.uint64)
+        check(self.L.bsq_get_counters(self.h, ptr(v)))
+        names = ["n_extend", "n_sa", "dup_chain_pos", "ext_cells", "ext_calls", "ext_rows", "glb_cells", "glb_calls"]
+        return {k: int(x) for k, x in zip(names, v)}
+
+    def align_sequence(self, seq) -> list[BwaMatch]:
+        """BwaIndex::align_sequence (bwa.cpp:141-181) for one read."""
+        if not self._refs:
+            return []
+        text = nuclseq_to_text(seq) if isinstance(seq, NucleotideSequence) else bytes(seq)
+        q = np.frombuffer(text, dtype=np.uint8)
+        res = self.align_batch(q, np.array([0, len(q)], dtype=np.uint64))
+        return self.matches(res, 0, text)
+
+    def matches(self, res: AlignResult, i: int, text: bytes) -> list[BwaMatch]:
+        out = []
+        m = self.meta()
+        offsets = np.cumsum([0] + [((s.len + 3) // 4) * 4 for _, s in self._refs])
+        for row in res.rows_of(i):
+            rid = int(row["rid"])
+            ref_offset = int(offsets[rid])
+            rb, re_ = int(row["rb"]), int(row["re"])
+            out.append(BwaMatch(
+                ref_id=int(row["ref_id"]),
+                ref_subseq=self._ref_subseq(rb, re_, int(m.l_pac), offsets),
+                ref_match_begin=_i32(rb - ref_offset), ref_match_end=_i32(re_ - ref_offset), ref_match_len=_i32(re_ - rb),
+                query_subseq=text[int(row["qb"]):int(row["qe"])],
+                query_match_begin=int(row["qb"]), query_match_end=int(row["qe"]), query_match_len=int(row["qe"] - row["qb"]),
+                is_primary=(int(row["flag"]) & 0x100) == 0, is_secondary=(int(row["flag"]) & 0x100) != 0, is_reverse=bool(row["is_rev"]),
+                cigar=res.cigar_of(row), score=int(row["score"])))
+        return out
+
+    def _ref_subseq(self, rb, re_, l_pac, offsets) -> bytes:
+        """extract_reference_subseq (bwa.cpp:55-68). Forward hits: the reference's own arithmetic, holes
+        overlaid with their un-rebased offsets. Reverse hits index past the reference's
+        vector (UB, B#3): defined here as the reverse-strand text."""
+        comp = bytes.maketrans(b"ACGT", b"TGCA")
+        cat = getattr(self, "_cat", None)
+        if cat is None:
+            parts = []
+            for _, s in self._refs:
+                p = s.pac
+                v = np.empty((len(p), 4), dtype=np.uint8)
+                v[:, 0] = p >> 6; v[:, 1] = (p >> 4) & 3; v[:, 2] = (p >> 2) & 3; v[:, 3] = p & 3
+                parts.append(np.frombuffer(b"ACGT", dtype=np.uint8)[v.reshape(-1)])
+            cat = self._cat = np.concatenate(parts)
+        if rb >= l_pac:
+            fwd = cat[2 * l_pac - re_:2 * l_pac - rb].tobytes()
+            out = bytearray(fwd.translate(comp)[::-1])
+        else:
+            out = bytearray(cat[rb:re_].tobytes())
+        for _, s in self._refs:
+            for h in s.holes:
+                lo, hi = max(int(h["offset"]), rb), min(int(h["offset"]) + int(h["len"]), re_)
+                for k in range(lo, hi):
+                    out[k - rb] = ord(h["amb"])
+        return bytes(out)
+
+
+def _i32(v: int) -> int:
+    v &= 0xFFFFFFFF
+    return v - (1 << 32) if v & 0x80000000 else v

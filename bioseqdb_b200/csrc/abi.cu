@@ -1,0 +1,705 @@
+// abi.cu -- the extern "C" boundary (include/bioseqdb_gpu.h) and the host-side orchestration of the
+// per-batch kernel pipeline: upload -> seed_smem -> chain_build -> sw_extend -> regs_finalize -> compact
+// -> download (+ MAPQ, which needs libm's log).  Pools are bump-allocated on the device
+// and grown by re-running the batch when a kernel raises the overflow flag; there is no CPU fallback for
+// any stage.
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include "../../include/bioseqdb_gpu.h"
+#include "common.cuh"
+#include "index_build.cuh"
+#include "seed.cuh"
+#include "pipeline.cuh"
+#include "primitives.cuh"
+#include "debug_kernels.cuh"
+
+static thread_local char g_err[1024] = "";
+void bsq_set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+
+static_assert(sizeof(bsq_row) == sizeof(RowDev), "bsq_row / RowDev mismatch");
+static_assert(sizeof(bsq_hole) == 16, "bsq_hole must match bntamb1_t");
+
+namespace {
+
+template <class T> struct DevBuf {
+    T* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 16;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Batch {
+    uint64_t n = 0; uint32_t max_len = 0; uint64_t total_bases = 0;
+    DevBuf<uint8_t> seqs; DevBuf<uint64_t> offs; DevBuf<int64_t> ids;
+    DevBuf<Intv> intv; DevBuf<uint32_t> intv_cnt; uint32_t intv_cap = 0;
+    DevBuf<Intv> seed_scratch; uint32_t list_cap = 0;
+    DevBuf<SeedRec> raw, seeds; DevBuf<ChainTmp> ctmp; DevBuf<uint32_t> ord; DevBuf<ChainRec> chains; DevBuf<uint64_t> srt;
+    DevBuf<RegRec> regs; DevBuf<RowDev> rows, rows_compact; DevBuf<uint32_t> reg_cnt, row_cnt, row_off, scan_tmp;
+    DevBuf<ReadBlock> blocks; uint32_t pool_cap = 0;
+    DevBuf<uint32_t> cigar; uint32_t cigar_cap = 0;
+    DevBuf<uint8_t> ext_scratch, fin_scratch;
+    DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..] counters (u64 x 8)
+    bool resident = false, aligned = false;
+    void release() {
+        seqs.release(); offs.release(); ids.release(); intv.release(); intv_cnt.release(); seed_scratch.release(); raw.release(); seeds.release();
+        ctmp.release(); ord.release(); chains.release(); srt.release(); regs.release(); rows.release(); rows_compact.release(); reg_cnt.release();
+        row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release(); ctl.release();
+    }
+};
+
+}  // namespace
+
+struct bsq_index {
+    int device = 0;
+    bsq_opts opts; DevOpts dopts;
+    float mapQ_coef_len = 50.f, mapQ_coef_fac = 0.f;
+    std::vector<uint8_t> pac; std::vector<int64_t> ann_offset, ann_id; std::vector<int32_t> ann_len; std::vector<bsq_hole> holes;
+    uint8_t* d_pac = nullptr; uint32_t* d_occ = nullptr; void* d_sa = nullptr; int64_t* d_ann_offset = nullptr; int32_t* d_ann_len = nullptr; int64_t* d_ann_id = nullptr;
+    bsq_index_meta meta;
+    cudaStream_t stream = nullptr;
+    Batch batch;
+    bsq_timing timing;
+    bool collect_counters = false;
+    uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+static void fill_dev_opts(bsq_index* h) {
+    const bsq_opts& p = h->opts; DevOpts& o = h->dopts;
+    o.a = p.a; o.b = p.b; o.o_del = p.o_del; o.e_del = p.e_del; o.o_ins = p.o_ins; o.e_ins = p.e_ins;
+    o.pen_clip5 = p.pen_clip5; o.pen_clip3 = p.pen_clip3; o.w = p.w; o.zdrop = p.zdrop; o.min_seed_len = p.min_seed_len; o.max_occ = p.max_occ;
+    o.max_mem_intv = 20; o.split_width = 10;
+    o.split_len = (int)(p.min_seed_len * 1.5f + .499);   // (int)(min_seed_len * split_factor + .499), split_factor is a float 1.5
+    o.max_chain_gap = 10000; o.max_chain_extend = 1 << 30; o.min_chain_weight = 0;
+    o.mask_level = 0.50f; o.drop_ratio = 0.50f; o.mask_level_redun = 0.95f;
+    // bwa_fill_scmat(1, 4): filled once by mem_opt_init and never refreshed
+    for (int i = 0; i < 4; ++i) { for (int j = 0; j < 4; ++j) o.mat[i * 5 + j] = i == j ? 1 : -4; o.mat[i * 5 + 4] = -1; }
+    for (int j = 0; j < 5; ++j) o.mat[20 + j] = -1;
+    o.mat_max = 1;
+    h->mapQ_coef_len = 50.f; h->mapQ_coef_fac = (float)log((double)h->mapQ_coef_len);
+}
+
+static int check_opts(const bsq_opts* o) {
+    const int32_t* v = &o->min_seed_len;
+    static const char* names[12] = {"min_seed_len", "max_occ", "match_score", "mismatch_penalty", "pen_clip3", "pen_clip5", "zdrop", "bandwidth", "o_del", "e_del", "o_ins", "e_ins"};
+    for (int i = 0; i < 12; ++i) if (v[i] < 0) { bsq_set_error("bwa_opt %s must be nonnegative", names[i]); return BSQ_ERR; }   // extension.cpp:205-206
+    if (o->e_del == 0 || o->e_ins == 0) { bsq_set_error("bwa_opt e_del / e_ins must be positive (libbwa divides by them)"); return BSQ_ERR; }
+    if (o->max_occ == 0) { bsq_set_error("bwa_opt max_occ must be positive (libbwa divides by it)"); return BSQ_ERR; }
+    return BSQ_OK;
+}
+
+extern "C" {
+
+const char* bsq_last_error(void) { return g_err; }
+
+int bsq_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+void bsq_opts_init(bsq_opts* o) {
+    o->min_seed_len = 19; o->max_occ = 500; o->a = 1; o->b = 4; o->pen_clip3 = 5; o->pen_clip5 = 5; o->zdrop = 100; o->w = 100;
+    o->o_del = 6; o->e_del = 1; o->o_ins = 6; o->e_ins = 1;
+}
+
+bsq_index* bsq_index_new(const bsq_opts* o, int device) {
+    bsq_opts d;
+    if (!o) { bsq_opts_init(&d); o = &d; }
+    if (check_opts(o) != BSQ_OK) return nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { bsq_set_error("no CUDA device: libbioseqdb_gpu has no CPU fallback"); return nullptr; }
+    if (device < 0 || device >= n) { bsq_set_error("device %d out of range (%d devices)", device, n); return nullptr; }
+    CUDA_CHECK_NULL(cudaSetDevice(device));
+    bsq_index* h = new bsq_index;
+    h->device = device; h->opts = *o;
+    memset(&h->meta, 0, sizeof(h->meta)); memset(&h->timing, 0, sizeof(h->timing));
+    fill_dev_opts(h);
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { bsq_set_error("cudaStreamCreate failed"); delete h; return nullptr; }
+    return h;
+}
+
+int bsq_index_set_opts(bsq_index* h, const bsq_opts* o) {
+    if (!h || !o) { bsq_set_error("null argument"); return BSQ_ERR; }
+    if (check_opts(o) != BSQ_OK) return BSQ_ERR;
+    h->opts = *o; fill_dev_opts(h);
+    return BSQ_OK;
+}
+
+int bsq_index_add_ref(bsq_index* h, int64_t id, const uint8_t* pac, uint32_t len, const bsq_hole* holes, uint32_t n_holes) {
+    if (!h) { bsq_set_error("null index"); return BSQ_ERR; }
+    if (h->meta.built) { bsq_set_error("index already built"); return BSQ_ERR; }
+    // BwaIndex::add_ref_sequence (bwa.cpp:82-105): offset = 4 * bytes so far, byte-rounded append, holes not rebased
+    h->ann_offset.push_back((int64_t)h->pac.size() * 4);
+    h->ann_len.push_back((int32_t)len);
+    h->ann_id.push_back(id);
+    size_t nb = (size_t)len / 4 + (len % 4 != 0);
+    h->pac.insert(h->pac.end(), pac, pac + nb);
+    for (uint32_t i = 0; i < n_holes; ++i) h->holes.push_back(holes[i]);
+    return BSQ_OK;
+}
+
+static void free_index_arrays(bsq_index* h) {
+    if (h->d_pac) cudaFree(h->d_pac); if (h->d_occ) cudaFree(h->d_occ); if (h->d_sa) cudaFree(h->d_sa);
+    if (h->d_ann_offset) cudaFree(h->d_ann_offset); if (h->d_ann_len) cudaFree(h->d_ann_len); if (h->d_ann_id) cudaFree(h->d_ann_id);
+    h->d_pac = nullptr; h->d_occ = nullptr; h->d_sa = nullptr; h->d_ann_offset = nullptr; h->d_ann_len = nullptr; h->d_ann_id = nullptr;
+}
+
+static int upload_anns(bsq_index* h) {
+    size_t na = h->ann_offset.size();
+    CUDA_CHECK(cudaMalloc(&h->d_ann_offset, na * 8 + 8)); CUDA_CHECK(cudaMalloc(&h->d_ann_len, na * 4 + 8)); CUDA_CHECK(cudaMalloc(&h->d_ann_id, na * 8 + 8));
+    CUDA_CHECK(cudaMemcpyAsync(h->d_ann_offset, h->ann_offset.data(), na * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(h->d_ann_len, h->ann_len.data(), na * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(h->d_ann_id, h->ann_id.data(), na * 8, cudaMemcpyHostToDevice, h->stream));
+    return BSQ_OK;
+}
+
+int bsq_index_build(bsq_index* h) {
+    if (!h) { bsq_set_error("null index"); return BSQ_ERR; }
+    if (h->pac.empty()) return BSQ_OK;   // bwa.cpp:108-109: empty reference => no index, alignments return nothing
+    CUDA_CHECK(cudaSetDevice(h->device));
+    free_index_arrays(h);
+    CUDA_CHECK(cudaMalloc(&h->d_pac, h->pac.size() + 64));
+    CUDA_CHECK(cudaMemcpyAsync(h->d_pac, h->pac.data(), h->pac.size(), cudaMemcpyHostToDevice, h->stream));
+    if (upload_anns(h) != BSQ_OK) return BSQ_ERR;
+    IndexBuild B;
+    B.d_pac = h->d_pac; B.l_pac = (int64_t)h->pac.size() * 4;
+    if (build_index_device(B, h->stream) != BSQ_OK) return BSQ_ERR;
+    h->d_occ = B.d_occ; h->d_sa = B.d_sa;
+    bsq_index_meta& m = h->meta;
+    m.l_pac = B.l_pac; m.seq_len = B.seq_len; m.primary = B.primary; memcpy(m.L2, B.L2, sizeof(m.L2));
+    m.n_anns = h->ann_offset.size(); m.sa_bytes = (uint32_t)B.sa_bytes; m.built = 1;
+    m.arr_bytes[BSQ_ARR_PAC] = h->pac.size(); m.arr_bytes[BSQ_ARR_OCC] = B.occ_bytes; m.arr_bytes[BSQ_ARR_SA] = (B.seq_len + 1) * B.sa_bytes;
+    m.arr_bytes[BSQ_ARR_ANN_OFFSET] = m.n_anns * 8; m.arr_bytes[BSQ_ARR_ANN_LEN] = m.n_anns * 4; m.arr_bytes[BSQ_ARR_ANN_ID] = m.n_anns * 8;
+    m.build_ms = B.build_ms; m.build_launches = B.launches; m.sort_pass_bytes = B.sort_pass_bytes;
+    return BSQ_OK;
+}
+
+void bsq_index_free(bsq_index* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    h->batch.release();
+    free_index_arrays(h);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int bsq_index_get_meta(const bsq_index* h, bsq_index_meta* m) {
+    if (!h || !m) { bsq_set_error("null argument"); return BSQ_ERR; }
+    *m = h->meta;
+    return BSQ_OK;
+}
+
+static void* index_array(const bsq_index* h, int what) {
+    switch (what) {
+        case BSQ_ARR_PAC: return h->d_pac; case BSQ_ARR_OCC: return h->d_occ; case BSQ_ARR_SA: return h->d_sa;
+        case BSQ_ARR_ANN_OFFSET: return h->d_ann_offset; case BSQ_ARR_ANN_LEN: return h->d_ann_len; case BSQ_ARR_ANN_ID: return h->d_ann_id;
+        default: return nullptr;
+    }
+}
+
+int bsq_index_device_ptr(const bsq_index* h, int what, void** dptr) {
+    if (!h || !dptr || what < 0 || what >= BSQ_ARR_COUNT) { bsq_set_error("bad argument"); return BSQ_ERR; }
+    *dptr = index_array(h, what);
+    return BSQ_OK;
+}
+
+int bsq_index_download(const bsq_index* h, int what, void* dst, uint64_t bytes) {
+    if (!h || !h->meta.built || what < 0 || what >= BSQ_ARR_COUNT) { bsq_set_error("index not built / bad array"); return BSQ_ERR; }
+    if (bytes > h->meta.arr_bytes[what]) { bsq_set_error("download of %llu bytes exceeds array size %llu", (unsigned long long)bytes, (unsigned long long)h->meta.arr_bytes[what]); return BSQ_ERR; }
+    CUDA_CHECK(cudaSetDevice(h->device));
+    CUDA_CHECK(cudaMemcpy(dst, index_array(h, what), bytes, cudaMemcpyDeviceToHost));
+    return BSQ_OK;
+}
+
+int bsq_index_alloc_replica(bsq_index* h, const bsq_index_meta* m) {
+    if (!h || !m || !m->built) { bsq_set_error("bad argument"); return BSQ_ERR; }
+    CUDA_CHECK(cudaSetDevice(h->device));
+    free_index_arrays(h);
+    h->meta = *m;
+    CUDA_CHECK(cudaMalloc(&h->d_pac, m->arr_bytes[BSQ_ARR_PAC] + 64));
+    CUDA_CHECK(cudaMalloc(&h->d_occ, m->arr_bytes[BSQ_ARR_OCC] + 64));
+    CUDA_CHECK(cudaMalloc(&h->d_sa, m->arr_bytes[BSQ_ARR_SA] + 64));
+    CUDA_CHECK(cudaMalloc(&h->d_ann_offset, m->arr_bytes[BSQ_ARR_ANN_OFFSET] + 8));
+    CUDA_CHECK(cudaMalloc(&h->d_ann_len, m->arr_bytes[BSQ_ARR_ANN_LEN] + 8));
+    CUDA_CHECK(cudaMalloc(&h->d_ann_id, m->arr_bytes[BSQ_ARR_ANN_ID] + 8));
+    return BSQ_OK;
+}
+
+int bsq_index_bwt_plain(const bsq_index* h, uint32_t* out) {
+    if (!h || !h->meta.built) { bsq_set_error("index not built"); return BSQ_ERR; }
+    std::vector<uint32_t> occ(h->meta.arr_bytes[BSQ_ARR_OCC] / 4);
+    if (bsq_index_download(h, BSQ_ARR_OCC, occ.data(), h->meta.arr_bytes[BSQ_ARR_OCC]) != BSQ_OK) return BSQ_ERR;
+    uint64_t nw = (h->meta.seq_len + 15) / 16;
+    for (uint64_t i = 0; i < nw; ++i) out[i] = occ[(i >> 3 << 4) + 8 + (i & 7)];
+    return BSQ_OK;
+}
+
+int bsq_index_sa_sampled(const bsq_index* h, uint64_t* out, uint64_t n_sa) {
+    if (!h || !h->meta.built) { bsq_set_error("index not built"); return BSQ_ERR; }
+    uint64_t n = h->meta.seq_len;
+    if (n_sa != (n + 32) / 32) { bsq_set_error("n_sa must be (seq_len + 32) / 32"); return BSQ_ERR; }
+    std::vector<uint8_t> sa(h->meta.arr_bytes[BSQ_ARR_SA]);
+    if (bsq_index_download(h, BSQ_ARR_SA, sa.data(), sa.size()) != BSQ_OK) return BSQ_ERR;
+    for (uint64_t k = 0; k < n_sa; ++k) {
+        uint64_t row = k * 32;
+        out[k] = h->meta.sa_bytes == 4 ? (uint64_t)((uint32_t*)sa.data())[row] : ((uint64_t*)sa.data())[row];
+    }
+    out[0] = (uint64_t)-1;   // bwt_cal_sa: sa[0] = -1
+    return BSQ_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ batch
+namespace {
+
+__global__ void k_to_nt4(uint8_t* s, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint8_t c = s[i], v;
+        // mem_align1_core: seq[i] < 4 ? seq[i] : nst_nt4_table[seq[i]]
+        if (c < 4) v = c;
+        else switch (c) {
+            case 'A': case 'a': v = 0; break; case 'C': case 'c': v = 1; break; case 'G': case 'g': v = 2; break; case 'T': case 't': v = 3; break;
+            case '-': v = 5; break; default: v = 4;
+        }
+        s[i] = v;
+    }
+}
+
+__global__ void k_compact_rows(const ReadBlock* blocks, const RowDev* rows, const uint32_t* row_cnt, const uint32_t* row_off, uint32_t n_reads, RowDev* out) {
+    // one warp per read; a row is 120 bytes = 30 words
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t r = gw; r < n_reads; r += nw) {
+        uint32_t c = row_cnt[r];
+        if (!c) continue;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(rows + blocks[r].base);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + row_off[r]);
+        for (uint32_t w = lane; w < c * 30; w += 32) dst[w] = src[w];
+    }
+}
+
+DevIndex make_dev_index(const bsq_index* h) {
+    DevIndex ix;
+    ix.pac = h->d_pac; ix.occ = h->d_occ; ix.sa = h->d_sa; ix.ann_offset = h->d_ann_offset; ix.ann_len = h->d_ann_len;
+    ix.l_pac = h->meta.l_pac; ix.seq_len = h->meta.seq_len; ix.primary = h->meta.primary;
+    for (int i = 0; i < 5; ++i) ix.L2[i] = h->meta.L2[i];
+    ix.n_anns = (int)h->meta.n_anns; ix.sa_bytes = (int)h->meta.sa_bytes;
+    return ix;
+}
+
+uint32_t rseq_cap_for(const bsq_index* h, uint32_t max_len) { return max_len + 4u * (uint32_t)h->opts.w + 16u; }
+
+// reads longer than this would need mem_flt_chained_seeds' local SW (runs when 5.5 ln L <= 0.05 L)
+bool needs_seed_sw(uint32_t len) { return len > 0 && 5.5f * log((double)len) <= 0.05f * (double)len; }
+
+int upload_reads(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n) {
+    Batch& b = h->batch;
+    b.resident = false; b.aligned = false;
+    if (n >= 0x7fffffffull) { bsq_set_error("batch too large"); return BSQ_ERR; }
+    uint32_t max_len = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (offs[i + 1] < offs[i]) { bsq_set_error("read offsets must be non-decreasing"); return BSQ_ERR; }
+        uint64_t l = offs[i + 1] - offs[i];
+        if (l > 0x3fffffffull) { bsq_set_error("read too long"); return BSQ_ERR; }
+        max_len = std::max<uint32_t>(max_len, (uint32_t)l);
+    }
+    if (needs_seed_sw(max_len)) {
+        bsq_set_error("reads of %u bases need the per-seed local-SW filter (mem_flt_chained_seeds), which this build does not implement yet; "
+                      "reads must be shorter than ~730 bases", max_len);
+        return BSQ_ERR;
+    }
+    const uint64_t total = n ? offs[n] - offs[0] : 0;
+    b.n = n; b.max_len = max_len; b.total_bases = total;
+    CUDA_CHECK(b.seqs.ensure(total + 64)); CUDA_CHECK(b.offs.ensure(n + 1)); CUDA_CHECK(b.ids.ensure(n + 1));
+    std::vector<uint64_t> rel(n + 1);
+    for (uint64_t i = 0; i <= n; ++i) rel[i] = offs[i] - (n ? offs[0] : 0);
+    if (total) CUDA_CHECK(cudaMemcpyAsync(b.seqs.p, seqs + offs[0], total, cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(b.offs.p, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    if (n) CUDA_CHECK(cudaMemcpyAsync(b.ids.p, ids, n * 8, cudaMemcpyHostToDevice, h->stream));
+    if (total) { k_to_nt4<<<(unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 16), 256, 0, h->stream>>>(b.seqs.p, total); ++h->timing.launches; }
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));   // rel[] is a stack-lifetime staging buffer
+    h->timing.h2d_bytes = total + (n + 1) * 8 + n * 8;
+    b.resident = true;
+    return BSQ_OK;
+}
+
+int run_pipeline(bsq_index* h) {
+    Batch& b = h->batch;
+    if (!b.resident) { bsq_set_error("no reads uploaded"); return BSQ_ERR; }
+    const uint32_t n = (uint32_t)b.n;
+    bsq_timing& T = h->timing;
+    T.seed = T.chain = T.extend = T.finalize = 0;
+    if (n == 0 || !h->meta.built) { b.aligned = true; return BSQ_OK; }
+    const DevIndex ix = make_dev_index(h);
+    const DevOpts& o = h->dopts;
+    const uint32_t max_len = std::max<uint32_t>(b.max_len, 1);
+    const uint32_t rseq_cap = rseq_cap_for(h, max_len);
+    if (b.intv_cap == 0) b.intv_cap = 48 + max_len / 4;
+    if (b.pool_cap == 0) b.pool_cap = (uint32_t)std::min<uint64_t>((uint64_t)n * 24 + 4096, 0x7fffffffull);
+    if (b.cigar_cap == 0) b.cigar_cap = (uint32_t)std::min<uint64_t>((uint64_t)n * 8 + 4096, 0x7fffffffull);
+    cudaEvent_t ev[5];
+    for (auto& e : ev) cudaEventCreate(&e);
+    int rc = BSQ_OK;
+    for (int attempt = 0; attempt < 12; ++attempt) {
+        // ---- (re)size pools
+        const int seed_warps = seed_resident_warps();
+        b.list_cap = std::max<uint32_t>(max_len + 1, b.intv_cap);
+        const int ext_warps = extend_resident_warps();
+        const size_t ext_per_warp = extend_scratch_per_warp(max_len, rseq_cap);
+        uint32_t z_cap = 0;
+        const size_t fin_per_warp = finalize_scratch_per_warp(max_len, rseq_cap, &z_cap);
+        int fin_warps = finalize_resident_warps();
+        {   // bound the traceback scratch to ~8 GB
+            size_t budget = (size_t)8 << 30;
+            int fit = (int)std::max<size_t>(budget / fin_per_warp, 4 * 148);
+            fin_warps = std::min(fin_warps, fit) / 4 * 4;
+        }
+#define ENS(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { bsq_set_error("allocating batch pools: %s", cudaGetErrorString(e_)); rc = BSQ_ERR; goto done; } } while (0)
+        ENS(b.intv.ensure((size_t)n * b.intv_cap)); ENS(b.intv_cnt.ensure(n));
+        ENS(b.seed_scratch.ensure((size_t)seed_warps * 3 * b.list_cap));
+        ENS(b.raw.ensure(b.pool_cap)); ENS(b.seeds.ensure(b.pool_cap)); ENS(b.ctmp.ensure(b.pool_cap)); ENS(b.ord.ensure(b.pool_cap));
+        ENS(b.chains.ensure(b.pool_cap)); ENS(b.srt.ensure(b.pool_cap)); ENS(b.regs.ensure(b.pool_cap)); ENS(b.rows.ensure(b.pool_cap));
+        ENS(b.reg_cnt.ensure(n)); ENS(b.row_cnt.ensure(n)); ENS(b.row_off.ensure(n + 1)); ENS(b.blocks.ensure(n));
+        ENS(b.scan_tmp.ensure(prim::scan_tmp_elems(n + 1) + 16));
+        ENS(b.cigar.ensure(b.cigar_cap));
+        ENS(b.ext_scratch.ensure((size_t)ext_warps * ext_per_warp)); ENS(b.fin_scratch.ensure((size_t)fin_warps * fin_per_warp));
+        ENS(b.ctl.ensure(64));
+        ENS(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, h->stream));
+        unsigned long long* ctr = h->collect_counters ? reinterpret_cast<unsigned long long*>(b.ctl.p + 8) : nullptr;
+        cudaEventRecord(ev[0], h->stream);
+        {
+            SeedParams P;
+            P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = b.intv_cap;
+            P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.ticket = b.ctl.p + 0; P.overflow = b.ctl.p + 4; P.n_extend = ctr ? ctr + 0 : nullptr;
+            launch_seed(P, ix, o, h->stream, nullptr); ++T.launches;
+        }
+        cudaEventRecord(ev[1], h->stream);
+        {
+            ChainParams P;
+            P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.intv = b.intv.p; P.intv_cnt = b.intv_cnt.p; P.intv_cap = b.intv_cap;
+            P.raw = b.raw.p; P.ctmp = b.ctmp.p; P.ord = b.ord.p; P.chains = b.chains.p; P.seeds = b.seeds.p; P.pool_cap = b.pool_cap; P.pool_top = b.ctl.p + 5;
+            P.blocks = b.blocks.p; P.ticket = b.ctl.p + 1; P.overflow = b.ctl.p + 4; P.counters = ctr ? ctr + 1 : nullptr;
+            launch_chain(P, ix, o, h->stream); ++T.launches;
+        }
+        cudaEventRecord(ev[2], h->stream);
+        {
+            ExtendParams P;
+            P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.blocks = b.blocks.p; P.chains = b.chains.p; P.seeds = b.seeds.p; P.srt = b.srt.p;
+            P.regs = b.regs.p; P.reg_cnt = b.reg_cnt.p; P.scratch = b.ext_scratch.p; P.scratch_per_warp = ext_per_warp; P.max_len = max_len; P.rseq_cap = rseq_cap;
+            P.ticket = b.ctl.p + 2; P.overflow = b.ctl.p + 4; P.counters = ctr ? ctr + 3 : nullptr;
+            launch_extend(P, ix, o, h->stream); ++T.launches;
+        }
+        cudaEventRecord(ev[3], h->stream);
+        {
+            FinalizeParams P;
+            P.seqs = b.seqs.p; P.offs = b.offs.p; P.ids = b.ids.p; P.n_reads = n; P.blocks = b.blocks.p; P.regs = b.regs.p; P.reg_cnt = b.reg_cnt.p;
+            P.rows = b.rows.p; P.row_cnt = b.row_cnt.p; P.cigar_pool = b.cigar.p; P.cigar_cap = b.cigar_cap; P.cigar_top = b.ctl.p + 6;
+            P.scratch = b.fin_scratch.p; P.scratch_per_warp = fin_per_warp; P.max_len = max_len; P.z_cap = z_cap; P.ann_id = h->d_ann_id;
+            P.ticket = b.ctl.p + 3; P.overflow = b.ctl.p + 4; P.counters = ctr ? ctr + 6 : nullptr;
+            launch_finalize(P, ix, o, h->stream, rseq_cap, fin_warps); ++T.launches;
+        }
+        // compact rows: exclusive scan of row_cnt (n + 1 entries, the last one is a zero pad) -> row_off
+        prim::device_scan<uint32_t, prim::OpSum, false>(b.row_cnt.p, b.row_off.p, n, b.scan_tmp.p, prim::OpSum(), h->stream, &T.launches);
+        cudaEventRecord(ev[4], h->stream);
+        uint32_t ctl[8];
+        ENS(cudaMemcpyAsync(ctl, b.ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
+        ENS(cudaStreamSynchronize(h->stream));
+        { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { bsq_set_error("kernel failure: %s", cudaGetErrorString(e_)); rc = BSQ_ERR; goto done; } }
+        float ms;
+        cudaEventElapsedTime(&ms, ev[0], ev[1]); T.seed += ms;
+        cudaEventElapsedTime(&ms, ev[1], ev[2]); T.chain += ms;
+        cudaEventElapsedTime(&ms, ev[2], ev[3]); T.extend += ms;
+        cudaEventElapsedTime(&ms, ev[3], ev[4]); T.finalize += ms;
+        if (ctl[4] == 0) {
+            if (ctr) { ENS(cudaMemcpy(h->counters, ctr, sizeof(h->counters), cudaMemcpyDeviceToHost)); }
+            b.aligned = true;
+            goto done;
+        }
+        if (ctl[4] == 2) { bsq_set_error("alignment scratch capacity exceeded (reference window / traceback larger than planned)"); rc = BSQ_ERR; goto done; }
+        // a pool was too small: grow everything that can overflow and run the batch again
+        if (ctl[5] > b.pool_cap) b.pool_cap = (uint32_t)std::min<uint64_t>((uint64_t)ctl[5] + ctl[5] / 8 + 4096, 0x7fffffffull);
+        else if (ctl[6] > b.cigar_cap) b.cigar_cap = (uint32_t)std::min<uint64_t>((uint64_t)ctl[6] + ctl[6] / 8 + 4096, 0x7fffffffull);
+        else b.intv_cap *= 2;
+    }
+    if (!b.aligned && rc == BSQ_OK) { bsq_set_error("batch pools kept overflowing"); rc = BSQ_ERR; }
+done:
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
+#undef ENS
+}
+
+// mem_approx_mapq_se on the host: double math with libm log
+int approx_mapq(const bsq_index* h, const bsq_row& a) {
+    const bsq_opts& o = h->opts;
+    int mapq, l, sub = a.sub ? a.sub : o.min_seed_len * o.a;
+    double identity;
+    sub = a.csub > sub ? a.csub : sub;
+    if (sub >= a.score) return 0;
+    l = a.qe - a.qb > a.re - a.rb ? a.qe - a.qb : (int)(a.re - a.rb);
+    identity = 1. - (double)(l * o.a - a.score) / (o.a + o.b) / l;
+    if (a.score == 0) mapq = 0;
+    else {   // mapQ_coef_len = 50 > 0
+        double tmp;
+        tmp = l < h->mapQ_coef_len ? 1. : h->mapQ_coef_fac / log(l);
+        tmp *= identity * identity;
+        mapq = (int)(6.02 * (a.score - sub) / o.a * tmp * tmp + .499);
+    }
+    if (a.sub_n > 0) mapq -= (int)(4.343 * log(a.sub_n + 1) + .499);
+    if (mapq > 60) mapq = 60;
+    if (mapq < 0) mapq = 0;
+    mapq = (int)(mapq * (1. - a.frac_rep) + .499);
+    return mapq;
+}
+
+int download_result(bsq_index* h, bsq_result** out) {
+    Batch& b = h->batch;
+    if (!b.aligned) { bsq_set_error("no aligned batch to download"); return BSQ_ERR; }
+    const uint64_t n = b.n;
+    bsq_result* R = new bsq_result;
+    R->n_reads = n; R->row_off = new uint64_t[n + 1]; R->rows = nullptr; R->cigar = nullptr; R->n_cigar_words = 0;
+    for (uint64_t i = 0; i <= n; ++i) R->row_off[i] = 0;
+    *out = R;
+    h->timing.d2h_bytes = 0;
+    if (n == 0 || !h->meta.built) { R->rows = new bsq_row[1]; R->cigar = new uint32_t[1]; return BSQ_OK; }
+    std::vector<uint32_t> off32(n), cnt_last(1);
+    CUDA_CHECK(cudaMemcpyAsync(off32.data(), b.row_off.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(cnt_last.data(), b.row_cnt.p + (n - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+    uint32_t cig_top = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&cig_top, b.ctl.p + 6, 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    const uint64_t total_rows = (uint64_t)off32[n - 1] + cnt_last[0];
+    for (uint64_t i = 0; i < n; ++i) R->row_off[i] = off32[i];
+    R->row_off[n] = total_rows;
+    R->rows = new bsq_row[total_rows + 1];
+    R->cigar = new uint32_t[(size_t)cig_top + 1];
+    R->n_cigar_words = cig_top;
+    if (total_rows) {
+        CUDA_CHECK(b.rows_compact.ensure(total_rows));
+        k_compact_rows<<<148 * 8, 256, 0, h->stream>>>(b.blocks.p, b.rows.p, b.row_cnt.p, b.row_off.p, (uint32_t)n, b.rows_compact.p); ++h->timing.launches;
+        CUDA_CHECK(cudaMemcpyAsync(R->rows, b.rows_compact.p, total_rows * sizeof(bsq_row), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (cig_top) CUDA_CHECK(cudaMemcpyAsync(R->cigar, b.cigar.p, (size_t)cig_top * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->timing.d2h_bytes = n * 4 + 8 + total_rows * sizeof(bsq_row) + (uint64_t)cig_top * 4;
+    for (uint64_t i = 0; i < total_rows; ++i) R->rows[i].mapq = R->rows[i].secondary < 0 ? approx_mapq(h, R->rows[i]) : 0;
+    return BSQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bsq_reads_upload(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n) {
+    if (!h || (n && (!seqs || !offs || !ids))) { bsq_set_error("null argument"); return BSQ_ERR; }
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->timing.launches = 0;
+    return upload_reads(h, seqs, offs, ids, n);
+}
+
+int bsq_align_resident(bsq_index* h) {
+    if (!h) { bsq_set_error("null index"); return BSQ_ERR; }
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->timing.launches = 0;
+    return run_pipeline(h);
+}
+
+int bsq_result_download(bsq_index* h, bsq_result** out) {
+    if (!h || !out) { bsq_set_error("null argument"); return BSQ_ERR; }
+    CUDA_CHECK(cudaSetDevice(h->device));
+    return download_result(h, out);
+}
+
+int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, bsq_result** out) {
+    if (!h || !out || (n && (!seqs || !offs || !ids))) { bsq_set_error("null argument"); return BSQ_ERR; }
+    CUDA_CHECK(cudaSetDevice(h->device));
+    cudaEvent_t e0, e1, e2, e3;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    h->timing.launches = 0;
+    cudaEventRecord(e0, h->stream);
+    int rc = upload_reads(h, seqs, offs, ids, n);
+    cudaEventRecord(e1, h->stream);
+    uint64_t l0 = h->timing.launches;
+    if (rc == BSQ_OK) rc = run_pipeline(h);
+    cudaEventRecord(e2, h->stream);
+    if (rc == BSQ_OK) rc = download_result(h, out);
+    cudaEventRecord(e3, h->stream);
+    cudaEventSynchronize(e3);
+    (void)l0;
+    cudaEventElapsedTime(&h->timing.h2d, e0, e1); cudaEventElapsedTime(&h->timing.d2h, e2, e3); cudaEventElapsedTime(&h->timing.total, e0, e3);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    return rc;
+}
+
+void bsq_result_free(bsq_result* r) {
+    if (!r) return;
+    delete[] r->row_off; delete[] r->rows; delete[] r->cigar; delete r;
+}
+
+int bsq_last_timing(const bsq_index* h, bsq_timing* t) {
+    if (!h || !t) { bsq_set_error("null argument"); return BSQ_ERR; }
+    *t = h->timing;
+    return BSQ_OK;
+}
+
+int bsq_set_counters(bsq_index* h, int on) { if (!h) return BSQ_ERR; h->collect_counters = on != 0; return BSQ_OK; }
+int bsq_get_counters(const bsq_index* h, uint64_t* out8) { if (!h || !out8) return BSQ_ERR; memcpy(out8, h->counters, sizeof(h->counters)); return BSQ_OK; }
+
+int bsq_debug_seed(bsq_index* h, const char* seqs, const uint64_t* offs, uint64_t n, uint64_t* out, uint32_t cap, uint32_t* cnt) {
+    if (!h || !h->meta.built) { bsq_set_error("index not built"); return BSQ_ERR; }
+    CUDA_CHECK(cudaSetDevice(h->device));
+    std::vector<int64_t> ids(n, 0);
+    if (upload_reads(h, seqs, offs, ids.data(), n) != BSQ_OK) return BSQ_ERR;
+    Batch& b = h->batch;
+    const DevIndex ix = make_dev_index(h);
+    b.intv_cap = cap;
+    b.list_cap = std::max<uint32_t>(b.max_len + 1, cap);
+    const int seed_warps = seed_resident_warps();
+    CUDA_CHECK(b.intv.ensure((size_t)n * cap)); CUDA_CHECK(b.intv_cnt.ensure(n)); CUDA_CHECK(b.seed_scratch.ensure((size_t)seed_warps * 3 * b.list_cap));
+    CUDA_CHECK(b.ctl.ensure(64));
+    CUDA_CHECK(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, h->stream));
+    SeedParams P;
+    P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = (uint32_t)n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = cap;
+    P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.ticket = b.ctl.p; P.overflow = b.ctl.p + 4; P.n_extend = reinterpret_cast<unsigned long long*>(b.ctl.p + 8);
+    launch_seed(P, ix, h->dopts, h->stream, nullptr);
+    uint32_t ctl[8];
+    CUDA_CHECK(cudaMemcpyAsync(ctl, b.ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(out, b.intv.p, (size_t)n * cap * sizeof(Intv), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(cnt, b.intv_cnt.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(h->counters, b.ctl.p + 8, 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    CUDA_CHECK(cudaGetLastError());
+    b.intv_cap = 0; b.resident = false;
+    if (ctl[4]) { bsq_set_error("interval capacity %u too small", cap); return BSQ_ERR; }
+    return BSQ_OK;
+}
+
+static int dbg_common(const bsq_opts* o, int device, bsq_index** tmp) {
+    *tmp = bsq_index_new(o, device);
+    return *tmp ? BSQ_OK : BSQ_ERR;
+}
+
+int bsq_debug_ksw_extend(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
+                         const uint64_t* t_off, const int32_t* w, const int32_t* end_bonus, const int32_t* h0, int32_t* out) {
+    bsq_index* h;
+    if (dbg_common(o, device, &h) != BSQ_OK) return BSQ_ERR;
+    int rc = BSQ_ERR;
+    uint8_t *dq = nullptr, *dt = nullptr; uint64_t *dqo = nullptr, *dto = nullptr; int *dw = nullptr, *deb = nullptr, *dh0 = nullptr, *dout = nullptr, *deh = nullptr;
+    uint32_t* dtk = nullptr;
+    uint32_t max_q = 0;
+    for (uint64_t i = 0; i < n_jobs; ++i) max_q = std::max<uint32_t>(max_q, (uint32_t)(q_off[i + 1] - q_off[i]));
+    const int blocks = 148 * 4, warps = blocks * 4;
+    do {
+#define DC(x) if ((x) != cudaSuccess) { bsq_set_error("debug extend: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        DC(cudaMalloc(&dq, q_off[n_jobs] + 16)); DC(cudaMalloc(&dt, t_off[n_jobs] + 16));
+        DC(cudaMalloc(&dqo, (n_jobs + 1) * 8)); DC(cudaMalloc(&dto, (n_jobs + 1) * 8));
+        DC(cudaMalloc(&dw, n_jobs * 4 + 4)); DC(cudaMalloc(&deb, n_jobs * 4 + 4)); DC(cudaMalloc(&dh0, n_jobs * 4 + 4)); DC(cudaMalloc(&dout, n_jobs * 24 + 4));
+        DC(cudaMalloc(&deh, (size_t)warps * 2 * (max_q + 2) * 4)); DC(cudaMalloc(&dtk, 64));
+        DC(cudaMemset(dtk, 0, 64));
+        DC(cudaMemcpy(dq, q, q_off[n_jobs], cudaMemcpyHostToDevice)); DC(cudaMemcpy(dt, t, t_off[n_jobs], cudaMemcpyHostToDevice));
+        DC(cudaMemcpy(dqo, q_off, (n_jobs + 1) * 8, cudaMemcpyHostToDevice)); DC(cudaMemcpy(dto, t_off, (n_jobs + 1) * 8, cudaMemcpyHostToDevice));
+        DC(cudaMemcpy(dw, w, n_jobs * 4, cudaMemcpyHostToDevice)); DC(cudaMemcpy(deb, end_bonus, n_jobs * 4, cudaMemcpyHostToDevice));
+        DC(cudaMemcpy(dh0, h0, n_jobs * 4, cudaMemcpyHostToDevice));
+        launch_dbg_extend(h->dopts, (uint32_t)n_jobs, dq, dqo, dt, dto, dw, deb, dh0, dout, deh, max_q, dtk, nullptr, blocks, h->stream);
+        DC(cudaStreamSynchronize(h->stream)); DC(cudaGetLastError());
+        DC(cudaMemcpy(out, dout, n_jobs * 24, cudaMemcpyDeviceToHost));
+        rc = BSQ_OK;
+    } while (0);
+    cudaFree(dq); cudaFree(dt); cudaFree(dqo); cudaFree(dto); cudaFree(dw); cudaFree(deb); cudaFree(dh0); cudaFree(dout); cudaFree(deh); cudaFree(dtk);
+    bsq_index_free(h);
+    return rc;
+}
+
+int bsq_debug_ksw_global(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
+                         const uint64_t* t_off, const int32_t* w, int32_t* out_score, uint32_t* cigar, uint32_t cig_cap, int32_t* n_cigar) {
+    bsq_index* h;
+    if (dbg_common(o, device, &h) != BSQ_OK) return BSQ_ERR;
+    int rc = BSQ_ERR;
+    uint8_t *dq = nullptr, *dt = nullptr, *dz = nullptr; uint64_t *dqo = nullptr, *dto = nullptr; int *dw = nullptr, *dsc = nullptr, *dnc = nullptr, *deh = nullptr;
+    uint32_t *dtk = nullptr, *dcg = nullptr;
+    uint32_t max_q = 0; size_t z_per_warp = 16;
+    for (uint64_t i = 0; i < n_jobs; ++i) {
+        uint32_t ql = (uint32_t)(q_off[i + 1] - q_off[i]), tl = (uint32_t)(t_off[i + 1] - t_off[i]);
+        max_q = std::max<uint32_t>(max_q, ql);
+        size_t ncol = std::min<size_t>(ql, 2 * (size_t)w[i] + 1);
+        z_per_warp = std::max<size_t>(z_per_warp, ncol * tl + 16);
+    }
+    const int blocks = 148 * 2, warps = blocks * 4;
+    do {
+        DC(cudaMalloc(&dq, q_off[n_jobs] + 16)); DC(cudaMalloc(&dt, t_off[n_jobs] + 16));
+        DC(cudaMalloc(&dqo, (n_jobs + 1) * 8)); DC(cudaMalloc(&dto, (n_jobs + 1) * 8));
+        DC(cudaMalloc(&dw, n_jobs * 4 + 4)); DC(cudaMalloc(&dsc, n_jobs * 4 + 4)); DC(cudaMalloc(&dnc, n_jobs * 4 + 4));
+        DC(cudaMalloc(&dcg, (size_t)n_jobs * cig_cap * 4 + 4));
+        DC(cudaMalloc(&deh, (size_t)warps * 2 * (max_q + 2) * 4)); DC(cudaMalloc(&dtk, 64)); DC(cudaMalloc(&dz, (size_t)warps * z_per_warp));
+        DC(cudaMemset(dtk, 0, 64));
+        DC(cudaMemcpy(dq, q, q_off[n_jobs], cudaMemcpyHostToDevice)); DC(cudaMemcpy(dt, t, t_off[n_jobs], cudaMemcpyHostToDevice));
+        DC(cudaMemcpy(dqo, q_off, (n_jobs + 1) * 8, cudaMemcpyHostToDevice)); DC(cudaMemcpy(dto, t_off, (n_jobs + 1) * 8, cudaMemcpyHostToDevice));
+        DC(cudaMemcpy(dw, w, n_jobs * 4, cudaMemcpyHostToDevice));
+        launch_dbg_global(h->dopts, (uint32_t)n_jobs, dq, dqo, dt, dto, dw, dsc, cigar ? dcg : nullptr, cig_cap, dnc, deh, max_q, dz, z_per_warp, dtk, blocks, h->stream);
+        DC(cudaStreamSynchronize(h->stream)); DC(cudaGetLastError());
+        DC(cudaMemcpy(out_score, dsc, n_jobs * 4, cudaMemcpyDeviceToHost));
+        if (cigar) { DC(cudaMemcpy(cigar, dcg, (size_t)n_jobs * cig_cap * 4, cudaMemcpyDeviceToHost)); DC(cudaMemcpy(n_cigar, dnc, n_jobs * 4, cudaMemcpyDeviceToHost)); }
+        rc = BSQ_OK;
+    } while (0);
+#undef DC
+    cudaFree(dq); cudaFree(dt); cudaFree(dz); cudaFree(dqo); cudaFree(dto); cudaFree(dw); cudaFree(dsc); cudaFree(dnc); cudaFree(dcg); cudaFree(deh); cudaFree(dtk);
+    bsq_index_free(h);
+    return rc;
+}
+
+int bsq_bench_gather(bsq_index* h, uint64_t n_loads, int reps, double* gbs) {
+    if (!h || !h->meta.built || !gbs) { bsq_set_error("index not built"); return BSQ_ERR; }
+    CUDA_CHECK(cudaSetDevice(h->device));
+    const uint64_t n_blocks = h->meta.arr_bytes[BSQ_ARR_OCC] / 64;
+    const int blocks = 148 * 8;                       // 8 CTAs of 256 threads per SM
+    const uint64_t groups = (uint64_t)blocks * 256 / 16;
+    uint64_t per_group = std::max<uint64_t>(8, (n_loads / groups) / 8 * 8);
+    uint32_t* sink = nullptr;
+    CUDA_CHECK(cudaMalloc(&sink, 64));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    launch_gather(h->d_occ, n_blocks, per_group, blocks, sink, h->stream);   // warm-up
+    float best = 1e30f;
+    for (int r = 0; r < reps; ++r) {
+        cudaEventRecord(e0, h->stream);
+        launch_gather(h->d_occ, n_blocks, per_group, blocks, sink, h->stream);
+        cudaEventRecord(e1, h->stream);
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *gbs = (double)(per_group * groups) * 64.0 / (best * 1e-3) / 1e9;
+    return BSQ_OK;
+}
+
+int bsq_bench_dpx(int device, int reps, double* gops) {
+    if (!gops) { bsq_set_error("null argument"); return BSQ_ERR; }
+    CUDA_CHECK(cudaSetDevice(device));
+    int* sink = nullptr;
+    CUDA_CHECK(cudaMalloc(&sink, 64));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int blocks = 148 * 8, iters = 4096;
+    launch_dpx(iters, blocks, sink, 0);
+    float best = 1e30f;
+    for (int r = 0; r < reps; ++r) {
+        cudaEventRecord(e0, 0);
+        launch_dpx(iters, blocks, sink, 0);
+        cudaEventRecord(e1, 0);
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *gops = (double)blocks * 256 * (double)iters * 8.0 / (best * 1e-3) / 1e9;   // DPX instructions (per thread) per second, in G
+    return BSQ_OK;
+}
+
+}  // extern "C"

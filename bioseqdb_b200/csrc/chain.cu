@@ -1,0 +1,215 @@
+// chain.cu -- kernel `chain_build`: SA lookup of every seed occurrence, seed chaining and chain filtering
+// (replaces libbwa mem_chain / test_and_merge / mem_chain_weight / mem_chain_flt
+// reached from reference bioseqdb/bwa.cpp:149).  One warp per read.  The SA lookups (the only HBM
+// random reads here: one 4- or 8-byte load per occurrence because the full SA is resident) are issued by
+// all lanes in parallel; the ordered-insert chaining itself is sequential bookkeeping on a few records.
+#include "pipeline.cuh"
+#include "ksort_dev.cuh"
+
+namespace {
+
+constexpr int CHAIN_THREADS = 128;
+
+// libbwa keeps chains in a B-tree keyed by pos; here: `ord` holds chain indices sorted by pos, the
+// newcomer goes after its equals and lookups return the last chain with pos <= key (SURVEY A.5 corner,
+// same definition as the oracle).
+__device__ __forceinline__ int find_lower(const ChainTmp* ct, const uint32_t* ord, int n, int64_t key) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int md = (lo + hi) >> 1; if (ct[ord[md]].pos <= key) lo = md + 1; else hi = md; }
+    return lo;  // lower = ord[lo - 1] when lo > 0; insertion point = lo
+}
+
+__device__ __forceinline__ int chain_weight(const SeedRec* raw, const ChainTmp& c) {
+    int64_t end = 0; int w = 0, tmp;
+    for (int s = c.head; s >= 0; s = raw[s].next) {
+        const SeedRec& q = raw[s];
+        if (q.qbeg >= end) w += q.len;
+        else if (q.qbeg + q.len > end) w += (int)(q.qbeg + q.len - end);
+        end = end > q.qbeg + q.len ? end : q.qbeg + q.len;
+    }
+    tmp = w; w = 0; end = 0;
+    for (int s = c.head; s >= 0; s = raw[s].next) {
+        const SeedRec& q = raw[s];
+        if (q.rbeg >= end) w += q.len;
+        else if (q.rbeg + q.len > end) w += (int)(q.rbeg + q.len - end);
+        end = end > q.rbeg + q.len ? end : q.rbeg + q.len;
+    }
+    w = w < tmp ? w : tmp;
+    return w < 1 << 30 ? w : (1 << 30) - 1;
+}
+
+__global__ void __launch_bounds__(CHAIN_THREADS) chain_build(ChainParams P, DevIndex ix, DevOpts o) {
+    const int lane = lane_id();
+    unsigned long long n_sa = 0, n_dup = 0;
+    for (;;) {
+        uint32_t r = next_ticket(P.ticket);
+        if (r >= P.n_reads) break;
+        const int len = (int)(P.offs[r + 1] - P.offs[r]);
+        const Intv* iv = P.intv + (size_t)r * P.intv_cap;
+        const int n_iv = (int)P.intv_cnt[r];
+        // ---- occurrences per interval (count rule of the k/step loop), frac_rep sweep
+        uint32_t total = 0;
+        int l_rep = 0;
+        {
+            int b = 0, e = 0;
+            for (int i = 0; i < n_iv; ++i) {   // uniform across lanes (broadcast loads)
+                uint64_t x2 = iv[i].x2;
+                uint64_t step = x2 > (uint64_t)o.max_occ ? x2 / (uint64_t)o.max_occ : 1;
+                uint64_t cnt = (x2 + step - 1) / step;
+                if (cnt > (uint64_t)o.max_occ) cnt = (uint64_t)o.max_occ;
+                total += (uint32_t)cnt;
+                if (x2 > (uint64_t)o.max_occ) {
+                    int sb = (int)(iv[i].info >> 32), se = (int)(uint32_t)iv[i].info;
+                    if (sb > e) { l_rep += e - b; b = sb; e = se; }
+                    else e = e > se ? e : se;
+                }
+            }
+            l_rep += e - b;
+        }
+        uint32_t base = 0;
+        if (lane == 0 && total) base = atomicAdd(P.pool_top, total);
+        base = __shfl_sync(FULL, base, 0);
+        ReadBlock blk; blk.base = base; blk.n_alloc = total; blk.n_chains = 0; blk.n_seeds = 0;
+        if (total == 0 || (uint64_t)base + total > (uint64_t)P.pool_cap) {
+            if (total && lane == 0) atomicExch(P.overflow, 1u);
+            blk.n_alloc = 0;
+            if (lane == 0) P.blocks[r] = blk;
+            continue;
+        }
+        SeedRec* raw = P.raw + base; ChainTmp* ct = P.ctmp + base; uint32_t* ord = P.ord + base;
+        // ---- SA lookups, all lanes (one HBM read each)
+        {
+            uint32_t t0 = 0;
+            for (int i = 0; i < n_iv; ++i) {
+                Intv p = iv[i];
+                uint64_t step = p.x2 > (uint64_t)o.max_occ ? p.x2 / (uint64_t)o.max_occ : 1;
+                uint64_t cnt = (p.x2 + step - 1) / step;
+                if (cnt > (uint64_t)o.max_occ) cnt = (uint64_t)o.max_occ;
+                int qbeg = (int)(p.info >> 32), slen = (int)((uint32_t)p.info - (uint32_t)(p.info >> 32));
+                for (uint64_t c = lane; c < cnt; c += 32) {
+                    int64_t rbeg = (int64_t)sa_at(ix, p.x0 + c * step);
+                    SeedRec s; s.rbeg = rbeg; s.qbeg = qbeg; s.len = slen; s.next = -1;
+                    s.score = bns_intv2rid(ix, rbeg, rbeg + slen);   // rid parked in `score` until chaining
+                    raw[t0 + c] = s;
+                }
+                t0 += (uint32_t)cnt;
+                n_sa += cnt;
+            }
+        }
+        __syncwarp();
+        // ---- ordered-insert chaining (lane 0)
+        int n_ch = 0;
+        if (lane == 0) {
+            for (uint32_t t = 0; t < total; ++t) {
+                SeedRec s = raw[t];
+                int rid = s.score;
+                if (rid < 0) continue;
+                raw[t].score = s.len;
+                bool to_add = true;
+                int lo = 0;
+                if (n_ch) {
+                    lo = find_lower(ct, ord, n_ch, s.rbeg);
+                    if (lo > 0) {
+                        ChainTmp& c = ct[ord[lo - 1]];
+                        // test_and_merge
+                        int64_t qend = c.l_qbeg + c.l_len, rend = c.l_rbeg + c.l_len;
+                        int res = 0;
+                        if (rid != c.rid) res = 0;
+                        else if (s.qbeg >= c.f_qbeg && s.qbeg + s.len <= qend && s.rbeg >= c.f_rbeg && s.rbeg + s.len <= rend) res = 1;
+                        else if ((c.l_rbeg < ix.l_pac || c.f_rbeg < ix.l_pac) && s.rbeg >= ix.l_pac) res = 0;
+                        else {
+                            int64_t x = s.qbeg - c.l_qbeg, y = s.rbeg - c.l_rbeg;
+                            if (y >= 0 && x - y <= o.w && y - x <= o.w && x - c.l_len < o.max_chain_gap && y - c.l_len < o.max_chain_gap) {
+                                raw[c.tail].next = (int32_t)t; c.tail = (int32_t)t; ++c.n;
+                                c.l_rbeg = s.rbeg; c.l_qbeg = s.qbeg; c.l_len = s.len;
+                                res = 1;
+                            }
+                        }
+                        if (res) to_add = false;
+                        else if (c.pos == s.rbeg) ++n_dup;
+                    }
+                }
+                if (to_add) {
+                    ChainTmp c;
+                    c.pos = s.rbeg; c.f_rbeg = c.l_rbeg = s.rbeg; c.f_qbeg = c.l_qbeg = s.qbeg; c.f_len = c.l_len = s.len;
+                    c.head = c.tail = (int32_t)t; c.n = 1; c.rid = rid; c.first = -1; c.kept = 0; c.w = 0; c.pad = 0;
+                    ct[n_ch] = c;
+                    for (int k = n_ch; k > lo; --k) ord[k] = ord[k - 1];
+                    ord[lo] = (uint32_t)n_ch;
+                    ++n_ch;
+                }
+            }
+        }
+        n_ch = __shfl_sync(FULL, n_ch, 0);
+        __syncwarp();
+        // ---- weights (lanes over chains), min_chain_weight drop
+        for (int k = lane; k < n_ch; k += 32) ct[k].w = (uint32_t)chain_weight(raw, ct[k]);
+        __syncwarp();
+        int n_out = 0; uint32_t seed_out = 0;
+        if (lane == 0 && n_ch) {
+            // mem_chain_flt: ord[] is the chain array `a` in pos order
+            int n = 0;
+            for (int i = 0; i < n_ch; ++i) { uint32_t c = ord[i]; if ((int)ct[c].w >= o.min_chain_weight) ord[n++] = c; }
+            if (n) {
+                const ChainTmp* ctc = ct;
+                ks_introsort_dev(n, ord, [ctc](uint32_t x, uint32_t y) { return ctc[x].w > ctc[y].w; });
+                // `kept_idx` list lives in the tail of ord (n_alloc >= n_ch >= n ... use a second region: P.ord is
+                // n_alloc wide, chains <= seeds, so [n, 2n) may not exist; keep the list in ChainTmp.pad instead)
+                int n_kept = 0;
+                ct[ord[0]].kept = 3; ct[n_kept++].pad = 0;
+                for (int i = 1; i < n; ++i) {
+                    ChainTmp& ci = ct[ord[i]];
+                    int large_ovlp = 0, k;
+                    int bi = ci.f_qbeg, ei = ci.l_qbeg + ci.l_len;
+                    for (k = 0; k < n_kept; ++k) {
+                        int j = (int)ct[k].pad;
+                        ChainTmp& cj = ct[ord[j]];
+                        int bj = cj.f_qbeg, ej = cj.l_qbeg + cj.l_len;
+                        int b_max = bj > bi ? bj : bi, e_min = ej < ei ? ej : ei;
+                        if (e_min > b_max) {   // is_alt is always 0 on this path (reference bwa.cpp:84-91)
+                            int li = ei - bi, lj = ej - bj, min_l = li < lj ? li : lj;
+                            if ((float)(e_min - b_max) >= __fmul_rn((float)min_l, o.mask_level) && min_l < o.max_chain_gap) {
+                                large_ovlp = 1;
+                                if (cj.first < 0) cj.first = i;
+                                if ((float)(int)ci.w < __fmul_rn((float)(int)cj.w, o.drop_ratio) && (int)cj.w - (int)ci.w >= o.min_seed_len << 1) break;
+                            }
+                        }
+                    }
+                    if (k == n_kept) { ct[n_kept++].pad = (uint32_t)i; ci.kept = large_ovlp ? 2 : 3; }
+                }
+                for (int k = 0; k < n_kept; ++k) { ChainTmp& c = ct[ord[ct[k].pad]]; if (c.first >= 0) ct[ord[c.first]].kept = 1; }
+                int i, k;
+                for (i = k = 0; i < n; ++i) {
+                    int kp = ct[ord[i]].kept;
+                    if (kp == 0 || kp == 3) continue;
+                    if (++k >= o.max_chain_extend) break;
+                }
+                for (; i < n; ++i) if (ct[ord[i]].kept < 3) ct[ord[i]].kept = 0;
+                // ---- emit kept chains in order with contiguous seeds
+                ChainRec* co = P.chains + base; SeedRec* so = P.seeds + base;
+                float frac_rep = (float)l_rep / len;
+                for (i = 0; i < n; ++i) {
+                    const ChainTmp& c = ct[ord[i]];
+                    if (c.kept == 0) continue;
+                    ChainRec rec; rec.pos = c.pos; rec.rid = c.rid; rec.n_seeds = c.n; rec.seed_off = (int32_t)seed_out; rec.kept = c.kept;
+                    rec.w = c.w; rec.frac_rep = frac_rep;
+                    for (int s = c.head; s >= 0; s = raw[s].next) { SeedRec q = raw[s]; q.next = -1; so[seed_out++] = q; }
+                    co[n_out++] = rec;
+                }
+            }
+        }
+        if (lane == 0) { blk.n_chains = (uint32_t)n_out; blk.n_seeds = seed_out; P.blocks[r] = blk; }
+    }
+    if (P.counters && lane == 0) { if (n_sa) atomicAdd(&P.counters[0], n_sa); if (n_dup) atomicAdd(&P.counters[1], n_dup); }
+}
+
+}  // namespace
+
+void launch_chain(const ChainParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st) {
+    int nb = 0, dev = 0, sms = 148;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_build, CHAIN_THREADS, 0);
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (nb < 1) nb = 1;
+    chain_build<<<nb * sms, CHAIN_THREADS, 0, st>>>(p, ix, o);
+}

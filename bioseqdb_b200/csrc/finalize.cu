@@ -1,0 +1,383 @@
+// finalize.cu -- kernel `regs_finalize`: mem_sort_dedup_patch + mem_mark_primary_se and,
+// for every surviving region, mem_reg2aln: banded global alignment with traceback (ksw_global2, A.11),
+// CIGAR, NM, pos / is_rev (A.12).  Replaces the libbwa calls at reference bioseqdb/bwa.cpp:149 (tail of
+// mem_align1) and :158 (mem_reg2aln per region).  One warp per read.  Control flow is evaluated by all
+// lanes on the same data (loads broadcast); stores are issued by lane 0 and followed by __syncwarp().
+// The DP rows run on the whole warp (ksw_global_warp).  MAPQ needs libm's log() and is finished on the
+// host from the fields written here (A.12).
+#include "pipeline.cuh"
+#include "ksw_warp.cuh"
+#include "ksort_dev.cuh"
+
+namespace {
+
+constexpr int FIN_THREADS = 128;
+constexpr int FIN_WARPS = FIN_THREADS / 32;
+
+struct FScratch { int* ehh; int* ehe; uint8_t* rseq; uint8_t* query; uint8_t* z; uint32_t* cig; };
+
+__device__ __forceinline__ uint64_t hash_64(uint64_t key) {
+    key += ~(key << 32); key ^= (key >> 22); key += ~(key << 13); key ^= (key >> 8);
+    key += (key << 3); key ^= (key >> 15); key += ~(key << 27); key ^= (key >> 31);
+    return key;
+}
+
+__device__ __forceinline__ int infer_bw(int l1, int l2, int score, int a, int q, int r) {
+    int w;
+    if (l1 == l2 && l1 * a - score < (q + r - a) << 1) return 0;
+    w = (int)((double)((l1 < l2 ? l1 : l2) * a - score - q) / r + 2.);
+    int d = l1 - l2; d = d < 0 ? -d : d;
+    if (w < d) w = d;
+    return w;
+}
+
+struct GenOut { int ok, score, n_cigar, NM; };
+
+// bwa_gen_cigar2.  Query segment q[0..l_query) (forward orientation in scratch), reference
+// [rb, re).  WANT_CIGAR: traceback into S.cig (forward order) and NM.
+template <bool WANT_CIGAR>
+__device__ GenOut gen_cigar2(const DevIndex& ix, const DevOpts& o, const int* smat, int w_, int l_query, const uint8_t* q, int64_t rb, int64_t re,
+                             const FScratch& S, uint32_t rseq_cap, uint32_t z_cap, uint32_t cig_cap, uint32_t* overflow,
+                             unsigned long long& cells, unsigned long long& calls) {
+    const int lane = lane_id();
+    const int64_t l_pac = ix.l_pac;
+    GenOut g; g.ok = 0; g.score = 0; g.n_cigar = 0; g.NM = -1;
+    if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) return g;
+    // bns_get_seq clamps to [0, 2 l_pac); a clamped fetch makes libbwa bail out (re - rb != rlen)
+    if (rb < 0 || re > (l_pac << 1)) return g;
+    const int64_t rlen64 = re - rb;
+    if (rlen64 > (int64_t)rseq_cap) { if (lane == 0) atomicExch(overflow, 2u); return g; }
+    const int rlen = (int)rlen64;
+    for (int i = lane; i < rlen; i += 32) S.rseq[i] = (uint8_t)ref_base(ix, rb + i);
+    __syncwarp();
+    // reverse strand: libbwa reverses both sequences so that gaps are left-aligned on the forward strand
+    const bool rev = rb >= l_pac;
+    const uint8_t* qp = rev ? q + l_query - 1 : q; const int qs = rev ? -1 : 1;
+    const uint8_t* tp = rev ? S.rseq + rlen - 1 : S.rseq; const int ts = rev ? -1 : 1;
+    g.ok = 1;
+    if (l_query == rlen && w_ == 0) {   // no gap: no DP
+        int sc = 0;
+        for (int i = lane; i < l_query; i += 32) sc += smat[(int)tp[(long)i * ts] * 5 + qp[(long)i * qs]];
+        sc = __reduce_add_sync(FULL, sc);
+        g.score = sc;
+        if (WANT_CIGAR) { if (lane == 0) S.cig[0] = (uint32_t)l_query << 4; g.n_cigar = 1; __syncwarp(); }
+    } else {
+        int w, max_gap, max_ins, max_del, min_w;
+        max_ins = (int)((double)(((l_query + 1) >> 1) * o.mat[0] - o.o_ins) / o.e_ins + 1.);
+        max_del = (int)((double)(((l_query + 1) >> 1) * o.mat[0] - o.o_del) / o.e_del + 1.);
+        max_gap = max_ins > max_del ? max_ins : max_del;
+        max_gap = max_gap > 1 ? max_gap : 1;
+        int dl = rlen - l_query; dl = dl < 0 ? -dl : dl;
+        w = (max_gap + dl + 1) >> 1;
+        w = w < w_ ? w : w_;
+        min_w = dl + 3;
+        w = w > min_w ? w : min_w;
+        const int n_col = l_query < 2 * w + 1 ? l_query : 2 * w + 1;
+        uint8_t* z = nullptr;
+        if (WANT_CIGAR) {
+            if ((uint64_t)n_col * (uint64_t)rlen > (uint64_t)z_cap) { if (lane == 0) atomicExch(overflow, 2u); g.ok = 0; return g; }
+            z = S.z;
+        }
+        ++calls;
+        g.score = ksw_global_warp(o, l_query, qp, qs, rlen, tp, ts, w, S.ehh, S.ehe, smat, z, n_col, cells);
+        if (WANT_CIGAR) {
+            int n_cigar = 0;
+            if (lane == 0) {   // traceback: a dependent walk over one byte per step
+                int which = 0, i = rlen - 1, k = (i + w + 1 < l_query ? i + w + 1 : l_query) - 1;
+                uint32_t* cg = S.cig;   // built backwards, then reversed
+                auto push = [&](uint32_t op, uint32_t len) {
+                    if (n_cigar == 0 || op != (cg[n_cigar - 1] & 0xf)) { if ((uint32_t)n_cigar < cig_cap) cg[n_cigar] = len << 4 | op; ++n_cigar; }
+                    else cg[n_cigar - 1] += len << 4;
+                };
+                while (i >= 0 && k >= 0) {
+                    which = z[(size_t)i * n_col + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
+                    if (which == 0) { push(0, 1); --i; --k; }
+                    else if (which == 1) { push(2, 1); --i; }
+                    else { push(1, 1); --k; }
+                }
+                if (i >= 0) push(2, (uint32_t)(i + 1));
+                if (k >= 0) push(1, (uint32_t)(k + 1));
+                if ((uint32_t)n_cigar > cig_cap) { atomicExch(overflow, 2u); n_cigar = 0; }
+                for (int a = 0; a < n_cigar >> 1; ++a) { uint32_t t = cg[a]; cg[a] = cg[n_cigar - 1 - a]; cg[n_cigar - 1 - a] = t; }
+            }
+            g.n_cigar = __shfl_sync(FULL, n_cigar, 0);
+            __syncwarp();
+        }
+    }
+    if (WANT_CIGAR) {   // NM (MD is not exported by the reference adapter)
+        int x = 0, y = 0, n_mm = 0, n_gap = 0;
+        for (int k = 0; k < g.n_cigar; ++k) {
+            const uint32_t cw = S.cig[k];
+            const int op = (int)(cw & 0xf), len = (int)(cw >> 4);
+            if (op == 0) {
+                for (int i = lane; i < len; i += 32) n_mm += qp[(long)(x + i) * qs] != tp[(long)(y + i) * ts];
+                x += len; y += len;
+            } else if (op == 2) {
+                if (k > 0 && k < g.n_cigar - 1) n_gap += len;
+                y += len;
+            } else if (op == 1) { x += len; n_gap += len; }
+        }
+        n_mm = __reduce_add_sync(FULL, n_mm);
+        g.NM = n_mm + n_gap;
+    }
+    return g;
+}
+
+// mem_patch_reg; a = earlier region, b = later region
+__device__ int patch_reg(const DevIndex& ix, const DevOpts& o, const int* smat, const uint8_t* query, const RegRec& a, const RegRec& b, int* _w,
+                         const FScratch& S, uint32_t rseq_cap, uint32_t* overflow, unsigned long long& cells, unsigned long long& calls) {
+    int w, score, q_s, r_s;
+    double r;
+    if (a.rb < ix.l_pac && b.rb >= ix.l_pac) return 0;
+    if (a.qb >= b.qb || a.qe >= b.qe || a.re >= b.re) return 0;
+    w = (int)((a.re - b.rb) - (a.qe - b.qb));
+    w = w > 0 ? w : -w;
+    r = (double)(a.re - b.rb) / (double)(b.re - a.rb) - (double)(a.qe - b.qb) / (double)(b.qe - a.qb);
+    r = r > 0. ? r : -r;
+    if (a.re < b.rb || a.qe < b.qb) {
+        if (w > o.w << 1 || r >= (double)0.05f) return 0;
+    } else if (w > o.w << 2 || r >= (double)(0.05f * 2)) return 0;
+    w += a.w + b.w;
+    w = w < o.w << 2 ? w : o.w << 2;
+    GenOut g = gen_cigar2<false>(ix, o, smat, w, b.qe - a.qb, query + a.qb, a.rb, b.re, S, rseq_cap, 0, 0, overflow, cells, calls);
+    score = g.score;
+    q_s = (int)((double)(b.qe - a.qb) / (double)((b.qe - b.qb) + (a.qe - a.qb)) * (double)(b.score + a.score) + .499);
+    r_s = (int)((double)(b.re - a.rb) / (double)((b.re - b.rb) + (a.re - a.rb)) * (double)(b.score + a.score) + .499);
+    if ((double)score / (double)(q_s > r_s ? q_s : r_s) < (double)0.90f) return 0;
+    *_w = w;
+    return score;
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(FIN_THREADS) regs_finalize(FinalizeParams P, DevIndex ix, DevOpts o, uint32_t cig_cap, uint32_t rseq_cap) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    __shared__ int smat[25];
+    if (threadIdx.x < 25) smat[threadIdx.x] = o.mat[threadIdx.x];
+    __syncthreads();
+    const int lane = lane_id();
+    const uint32_t gwarp = (blockIdx.x * FIN_THREADS + threadIdx.x) >> 5;
+    FScratch S;
+    {
+        // fast part (DP rows, sequences) optionally in shared memory; z and the cigar buffer stay in global scratch
+        const size_t fast = ((size_t)(P.max_len + 2) * 8 + rseq_cap + P.max_len + 15) & ~(size_t)15;
+        uint8_t* gbase = P.scratch + (size_t)gwarp * P.scratch_per_warp;
+        uint8_t* fbase = SMEM ? dyn_smem + (size_t)(threadIdx.x >> 5) * fast : gbase;
+        S.ehh = reinterpret_cast<int*>(fbase);
+        S.ehe = S.ehh + (P.max_len + 2);
+        S.rseq = reinterpret_cast<uint8_t*>(S.ehe + (P.max_len + 2));
+        S.query = S.rseq + rseq_cap;
+        S.cig = reinterpret_cast<uint32_t*>(gbase + fast);
+        S.z = reinterpret_cast<uint8_t*>(S.cig + cig_cap);
+    }
+    unsigned long long cells = 0, calls = 0;
+    for (;;) {
+        uint32_t r = next_ticket(P.ticket);
+        if (r >= P.n_reads) break;
+        const ReadBlock blk = P.blocks[r];
+        int n = blk.n_alloc ? (int)P.reg_cnt[r] : 0;
+        if (n == 0) { if (lane == 0) P.row_cnt[r] = 0; continue; }
+        const int l_query = (int)(P.offs[r + 1] - P.offs[r]);
+        {
+            const uint8_t* qg = P.seqs + P.offs[r];
+            for (int i = lane; i < l_query; i += 32) S.query[i] = qg[i];
+        }
+        RegRec* a = P.regs + blk.base;
+        __syncwarp();
+        // ---------------- mem_sort_dedup_patch
+        if (n > 1) {
+            if (lane == 0) {
+                ks_introsort_dev(n, a, [](const RegRec& x, const RegRec& y) { return x.re < y.re; });
+                for (int i = 0; i < n; ++i) a[i].n_comp = 1;
+            }
+            __syncwarp();
+            for (int i = 1; i < n; ++i) {
+                if (a[i].rid != a[i - 1].rid || a[i].rb >= a[i - 1].re + o.max_chain_gap) continue;
+                for (int j = i - 1; j >= 0 && a[i].rid == a[j].rid && a[i].rb < a[j].re + o.max_chain_gap; --j) {
+                    const RegRec p = a[i], q = a[j];
+                    int64_t orr, oq, mr, mq;
+                    int score, w;
+                    if (q.qe == q.qb) continue;
+                    orr = q.re - p.rb;
+                    oq = q.qb < p.qb ? q.qe - p.qb : p.qe - q.qb;
+                    mr = q.re - q.rb < p.re - p.rb ? q.re - q.rb : p.re - p.rb;
+                    mq = q.qe - q.qb < p.qe - p.qb ? q.qe - q.qb : p.qe - p.qb;
+                    if ((float)orr > __fmul_rn(o.mask_level_redun, (float)mr) && (float)oq > __fmul_rn(o.mask_level_redun, (float)mq)) {
+                        if (p.score < q.score) {
+                            if (lane == 0) a[i].qe = p.qb;
+                            __syncwarp();
+                            break;
+                        } else {
+                            if (lane == 0) a[j].qe = q.qb;
+                            __syncwarp();
+                        }
+                    } else if (q.rb < p.rb && (score = patch_reg(ix, o, smat, S.query, q, p, &w, S, rseq_cap, P.overflow, cells, calls)) > 0) {
+                        if (lane == 0) {
+                            RegRec& pp = a[i];
+                            pp.n_comp += q.n_comp + 1;
+                            pp.seedcov = p.seedcov > q.seedcov ? p.seedcov : q.seedcov;
+                            pp.sub = p.sub > q.sub ? p.sub : q.sub;
+                            pp.csub = p.csub > q.csub ? p.csub : q.csub;
+                            pp.qb = q.qb; pp.rb = q.rb;
+                            pp.truesc = pp.score = score;
+                            pp.w = w;
+                            a[j].qb = q.qe;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            int m = 0;
+            if (lane == 0) {
+                for (int i = 0; i < n; ++i)
+                    if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
+                n = m;
+                ks_introsort_dev(n, a, [](const RegRec& x, const RegRec& y) {
+                    return x.score > y.score || (x.score == y.score && (x.rb < y.rb || (x.rb == y.rb && x.qb < y.qb)));
+                });
+                for (int i = 1; i < n; ++i)
+                    if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
+                m = n < 1 ? 0 : 1;
+                for (int i = 1; i < n; ++i)
+                    if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
+            }
+            n = __shfl_sync(FULL, m, 0);
+            __syncwarp();
+        }
+        // ---------------- mem_mark_primary_se
+        if (lane == 0 && n > 0) {
+            const int64_t id = P.ids[r];
+            for (int i = 0; i < n; ++i) { a[i].sub = 0; a[i].secondary = -1; a[i].hash = hash_64((uint64_t)(id + i)); }
+            ks_introsort_dev(n, a, [](const RegRec& x, const RegRec& y) { return x.score > y.score || (x.score == y.score && x.hash < y.hash); });
+            int tmp = o.a + o.b;
+            tmp = o.o_del + o.e_del > tmp ? o.o_del + o.e_del : tmp;
+            tmp = o.o_ins + o.e_ins > tmp ? o.o_ins + o.e_ins : tmp;
+            // z list: indices of non-secondary regions, kept in the (not yet used) n_comp-free field `secondary` of ...
+            // simple: the list is a prefix-ordered subset; store it in the csub field of slot k (csub is 0 on this path
+            // except after a patch merge, so keep a copy and restore)
+            int nz = 0;
+            // use the cigar scratch as the z list (free at this point)
+            uint32_t* zl = S.cig;
+            zl[nz++] = 0;
+            for (int i = 1; i < n; ++i) {
+                int k;
+                for (k = 0; k < nz; ++k) {
+                    const int j = (int)zl[k];
+                    const int b_max = a[j].qb > a[i].qb ? a[j].qb : a[i].qb;
+                    const int e_min = a[j].qe < a[i].qe ? a[j].qe : a[i].qe;
+                    if (e_min > b_max) {
+                        const int li = a[i].qe - a[i].qb, lj = a[j].qe - a[j].qb;
+                        const int min_l = li < lj ? li : lj;
+                        if ((float)(e_min - b_max) >= __fmul_rn((float)min_l, o.mask_level)) {
+                            if (a[j].sub == 0) a[j].sub = a[i].score;
+                            if (a[j].score - a[i].score <= tmp) ++a[j].sub_n;
+                            break;
+                        }
+                    }
+                }
+                if (k == nz) { if ((uint32_t)nz < cig_cap) zl[nz] = (uint32_t)i; ++nz; }
+                else a[i].secondary = (int)zl[k];
+            }
+            if ((uint32_t)nz > cig_cap) atomicExch(P.overflow, 2u);
+        }
+        __syncwarp();
+        // ---------------- mem_reg2aln per region (reference bwa.cpp:151-177 calls it for every region)
+        RowDev* rows = P.rows + blk.base;
+        for (int i = 0; i < n; ++i) {
+            const RegRec ar = a[i];
+            RowDev row;
+            row.rb = ar.rb; row.re = ar.re; row.hash = ar.hash; row.qb = ar.qb; row.qe = ar.qe; row.rid = ar.rid; row.score = ar.score;
+            row.truesc = ar.truesc; row.sub = ar.sub; row.csub = ar.csub; row.sub_n = ar.sub_n; row.w = ar.w; row.seedcov = ar.seedcov;
+            row.secondary = ar.secondary; row.seedlen0 = ar.seedlen0; row.n_comp = ar.n_comp; row.frac_rep = ar.frac_rep;
+            row.mapq = 0;   // filled on the host (mem_approx_mapq_se needs libm log)
+            row.flag = ar.secondary >= 0 ? 0x100 : 0;
+            const int qb = ar.qb, qe = ar.qe; const int64_t rb = ar.rb, re = ar.re;
+            int tmpw = infer_bw(qe - qb, (int)(re - rb), ar.truesc, o.a, o.o_del, o.e_del);
+            int w2 = infer_bw(qe - qb, (int)(re - rb), ar.truesc, o.a, o.o_ins, o.e_ins);
+            w2 = w2 > tmpw ? w2 : tmpw;
+            if (w2 > o.w) w2 = w2 < ar.w ? w2 : ar.w;
+            int it = 0, score = 0, last_sc = -(1 << 30);
+            GenOut g;
+            do {
+                w2 = w2 < o.w << 2 ? w2 : o.w << 2;
+                g = gen_cigar2<true>(ix, o, smat, w2, qe - qb, S.query + qb, rb, re, S, rseq_cap, P.z_cap, cig_cap - 2, P.overflow, cells, calls);
+                if (g.ok) score = g.score;
+                if (score == last_sc || w2 == o.w << 2) break;
+                last_sc = score;
+                w2 <<= 1;
+            } while (++it < 3 && score < ar.truesc - o.a);
+            row.NM = g.NM;
+            int is_rev;
+            int64_t pos = bns_depos(ix, rb < ix.l_pac ? rb : re - 1, &is_rev);
+            row.is_rev = is_rev;
+            // squeeze out a leading or trailing deletion, add soft clips, publish the CIGAR
+            int n_cigar = g.n_cigar, first = 0;
+            if (n_cigar > 0) {
+                if ((S.cig[0] & 0xf) == 2) { pos += S.cig[0] >> 4; first = 1; --n_cigar; }
+                else if ((S.cig[g.n_cigar - 1] & 0xf) == 2) --n_cigar;
+            }
+            int clip5 = 0, clip3 = 0;
+            if (qb != 0 || qe != l_query) { clip5 = is_rev ? l_query - qe : qb; clip3 = is_rev ? qb : l_query - qe; }
+            const int n_out = n_cigar + (clip5 ? 1 : 0) + (clip3 ? 1 : 0);
+            uint32_t coff = 0;
+            if (lane == 0 && n_out) coff = atomicAdd(P.cigar_top, (uint32_t)n_out);
+            coff = __shfl_sync(FULL, coff, 0);
+            if ((uint64_t)coff + (uint64_t)n_out > (uint64_t)P.cigar_cap) { if (lane == 0) atomicExch(P.overflow, 1u); row.cigar_off = 0; row.n_cigar = 0; }
+            else {
+                row.cigar_off = coff; row.n_cigar = (uint32_t)n_out;
+                if (lane == 0) {
+                    uint32_t* dst = P.cigar_pool + coff;
+                    int k = 0;
+                    if (clip5) dst[k++] = (uint32_t)clip5 << 4 | 3;
+                    for (int c = 0; c < n_cigar; ++c) dst[k++] = S.cig[first + c];
+                    if (clip3) dst[k++] = (uint32_t)clip3 << 4 | 3;
+                }
+            }
+            const int rid = bns_pos2rid(ix, pos);
+            row.pos = pos - ix.ann_offset[rid < 0 ? 0 : rid];
+            row.ref_id = P.ann_id[ar.rid];
+            if (lane == 0) rows[i] = row;
+            __syncwarp();
+        }
+        if (lane == 0) P.row_cnt[r] = (uint32_t)n;
+    }
+    if (P.counters && lane == 0) { atomicAdd(&P.counters[0], cells); atomicAdd(&P.counters[1], calls); }
+}
+
+}  // namespace
+
+static size_t fin_fast_bytes(uint32_t max_len, uint32_t rseq_cap) { return ((size_t)(max_len + 2) * 8 + rseq_cap + max_len + 15) & ~(size_t)15; }
+static uint32_t fin_cig_cap(uint32_t max_len, uint32_t rseq_cap) { return max_len + rseq_cap + 8; }
+
+size_t finalize_scratch_per_warp(uint32_t max_len, uint32_t rseq_cap, uint32_t* z_cap_out) {
+    // traceback matrix: n_col <= min(qlen, 2w+1) with w <= 4 * opt.w handled by the caller through rseq_cap;
+    // worst case qlen x tlen for short reads, band-limited for long ones
+    uint64_t z = (uint64_t)max_len * (uint64_t)rseq_cap;
+    const uint64_t z_band = (uint64_t)rseq_cap * 1024;   // 2w+1 <= 801 columns when w = 4 * 100
+    if (z > z_band) z = z_band;
+    if (z_cap_out) *z_cap_out = (uint32_t)z;
+    size_t b = fin_fast_bytes(max_len, rseq_cap) + (size_t)fin_cig_cap(max_len, rseq_cap) * 4 + (size_t)z;
+    return (b + 255) & ~(size_t)255;
+}
+
+static bool fin_use_smem(uint32_t max_len, uint32_t rseq_cap) { return fin_fast_bytes(max_len, rseq_cap) * FIN_WARPS <= 40 * 1024; }
+
+int finalize_resident_warps() {
+    int nb = 0, dev = 0, sms = 148;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, regs_finalize<false>, FIN_THREADS, 0);
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (nb < 1) nb = 1;
+    return nb * sms * FIN_WARPS;
+}
+
+void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint32_t rseq_cap, int n_warps) {
+    const uint32_t cig_cap = fin_cig_cap(p.max_len, rseq_cap);
+    int blocks = n_warps / FIN_WARPS;
+    if (blocks < 1) blocks = 1;
+    if (fin_use_smem(p.max_len, rseq_cap)) {
+        size_t smem = fin_fast_bytes(p.max_len, rseq_cap) * FIN_WARPS;
+        regs_finalize<true><<<blocks, FIN_THREADS, smem, st>>>(p, ix, o, cig_cap, rseq_cap);
+    } else {
+        regs_finalize<false><<<blocks, FIN_THREADS, 0, st>>>(p, ix, o, cig_cap, rseq_cap);
+    }
+}

@@ -1,0 +1,173 @@
+// ksw_warp.cuh -- warp-cooperative banded DP kernels with libbwa ksw.c semantics.
+//
+// Both ksw_extend2 and ksw_global2 open gaps from M only, so within one target row M and E depend on the
+// previous row alone and F is a max-plus prefix scan along the row.  A warp therefore sweeps the row in
+// 32-column chunks: lanes compute M/E in parallel, F comes from a 5-step shuffle scan, H = max3(M,E,F)
+// (DPX __vimax3_s32 / __viaddmax_s32*), and the per-row band trimming, z-drop and tie rules of the scalar
+// code are applied between rows on warp-uniform registers -- bit-exact, including the right-hand trim
+// that a static anti-diagonal wavefront cannot reproduce ("hard parts").
+#pragma once
+#include "common.cuh"
+
+#define KSW_NEG_INF (-0x40000000)
+
+struct ExtOut { int score, qle, tle, gtle, gscore, max_off; };
+
+// ksw_extend2.  q[j*qs], t[i*ts]; ehh/ehe: qlen+1 ints each (warp-private scratch); smat: 25 ints.
+static __device__ __noinline__ ExtOut ksw_extend_warp(const DevOpts& o, int qlen, const uint8_t* q, int qs, int tlen, const uint8_t* t, int ts,
+                                               int w, int end_bonus, int h0, int* ehh, int* ehe, const int* smat,
+                                               unsigned long long& cells, unsigned long long& rows) {
+    const int lane = lane_id();
+    const int o_del = o.o_del, e_del = o.e_del, o_ins = o.o_ins, e_ins = o.e_ins;
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    // first row (closed form of the scalar fill loop): eh[0].h = h0, eh[j].h = max(h0 - o_ins - j e_ins, 0)
+    for (int j = lane; j <= qlen; j += 32) {
+        int v = j == 0 ? h0 : h0 - o_ins - j * e_ins;
+        ehh[j] = v > 0 ? v : 0;
+        ehe[j] = 0;
+    }
+    {
+        int max_ins = (int)((double)(qlen * o.mat_max + end_bonus - o_ins) / e_ins + 1.);
+        max_ins = max_ins > 1 ? max_ins : 1;
+        w = w < max_ins ? w : max_ins;
+        int max_del = (int)((double)(qlen * o.mat_max + end_bonus - o_del) / e_del + 1.);
+        max_del = max_del > 1 ? max_del : 1;
+        w = w < max_del ? w : max_del;
+    }
+    int max = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;
+    int beg = 0, end = qlen;
+    __syncwarp();
+    for (int i = 0; i < tlen; ++i) {
+        if (beg < i - w) beg = i - w;
+        if (end > i + w + 1) end = i + w + 1;
+        if (end > qlen) end = qlen;
+        int h1_init = 0;
+        if (beg == 0) { h1_init = h0 - (o_del + e_del * (i + 1)); if (h1_init < 0) h1_init = 0; }
+        const int* mrow = smat + (int)t[(long)i * ts] * 5;
+        int carryU = (beg - 1) * e_ins, carryH = h1_init;
+        int best_h = -1, best_j = -1, first_nz = -1, last_nz = -1;
+        cells += (unsigned long long)(end > beg ? end - beg : 0); ++rows;
+        for (int j0 = beg; j0 < end; j0 += 32) {
+            const int j = j0 + lane;
+            const bool act = j < end;
+            int M = 0, e = 0;
+            if (act) { M = ehh[j]; e = ehe[j]; int s = mrow[q[(long)j * qs]]; M = M ? M + s : 0; }
+            int u = act ? __viaddmax_s32(M, -oe_ins, 0) + j * e_ins : KSW_NEG_INF;
+            int inc = u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int ov = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc = ::max(inc, ov); }
+            int ex = __shfl_up_sync(FULL, inc, 1);
+            ex = lane == 0 ? carryU : ::max(ex, carryU);
+            const int f = ex - (j - 1) * e_ins;
+            const int h = __vimax3_s32(M, e, f);
+            int hl = __shfl_up_sync(FULL, h, 1);
+            if (lane == 0) hl = carryH;
+            bool nz = false;
+            if (act) {
+                ehh[j] = hl;
+                const int e2 = __viaddmax_s32_relu(e, -e_del, M - oe_del);
+                ehe[j] = e2;
+                if (h >= best_h) { best_h = h; best_j = j; }
+                nz = (hl | e2) != 0;
+            }
+            const unsigned bal = __ballot_sync(FULL, nz);
+            if (bal) { if (first_nz < 0) first_nz = j0 + __ffs(bal) - 1; last_nz = j0 + 31 - __clz(bal); }
+            const int last = (end - j0 < 32 ? end - j0 : 32) - 1;
+            carryU = ::max(carryU, __shfl_sync(FULL, inc, 31));
+            carryH = __shfl_sync(FULL, h, last);
+        }
+        const int h1 = carryH;  // H(i, end-1), or the first-column value when the row is empty
+        if (lane == 0) { ehh[end] = h1; ehe[end] = 0; }
+        __syncwarp();
+        const int jfin = beg < end ? end : beg;
+        if (jfin == qlen) {
+            max_ie = gscore > h1 ? max_ie : i;
+            gscore = gscore > h1 ? gscore : h1;
+        }
+        int m = __reduce_max_sync(FULL, best_h);
+        int mj = __reduce_max_sync(FULL, best_h == m ? best_j : -1);
+        if (m < 0) { m = 0; mj = -1; }
+        if (m == 0) break;
+        if (m > max) {
+            max = m; max_i = i; max_j = mj;
+            int off = mj - i; off = off < 0 ? -off : off;
+            max_off = max_off > off ? max_off : off;
+        } else if (o.zdrop > 0) {
+            if (i - max_i > mj - max_j) {
+                if (max - m - ((i - max_i) - (mj - max_j)) * e_del > o.zdrop) break;
+            } else {
+                if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > o.zdrop) break;
+            }
+        }
+        // band trimming for the next row (literal: eh[end] takes part in the downward scan only)
+        int nbeg = first_nz >= 0 ? first_nz : end;
+        int jj;
+        if (h1 != 0) jj = end;
+        else if (last_nz >= 0) jj = last_nz;
+        else jj = nbeg - 1;
+        beg = nbeg;
+        end = jj + 2 < qlen ? jj + 2 : qlen;
+    }
+    ExtOut r;
+    r.score = max; r.qle = max_j + 1; r.tle = max_i + 1; r.gtle = max_ie + 1; r.gscore = gscore; r.max_off = max_off;
+    return r;
+}
+
+// ksw_global2.  z: traceback bytes, n_col per row (nullptr => score only).
+static __device__ __noinline__ int ksw_global_warp(const DevOpts& o, int qlen, const uint8_t* q, int qs, int tlen, const uint8_t* t, int ts,
+                                            int w, int* ehh, int* ehe, const int* smat, uint8_t* z, int n_col, unsigned long long& cells) {
+    const int lane = lane_id();
+    const int o_del = o.o_del, e_del = o.e_del, o_ins = o.o_ins, e_ins = o.e_ins;
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    for (int j = lane; j <= qlen; j += 32) {
+        int hv = j == 0 ? 0 : (j <= w ? -(o_ins + e_ins * j) : KSW_NEG_INF);
+        ehh[j] = hv; ehe[j] = KSW_NEG_INF;
+    }
+    __syncwarp();
+    for (int i = 0; i < tlen; ++i) {
+        const int beg = i > w ? i - w : 0;
+        const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
+        const int h1_init = beg == 0 ? -(o_del + e_del * (i + 1)) : KSW_NEG_INF;
+        const int* mrow = smat + (int)t[(long)i * ts] * 5;
+        uint8_t* zi = z ? z + (size_t)i * n_col : nullptr;
+        // F(i, beg) = -inf: carry in "u-space" so that f_j = U_{j-1} - (j-1) e_ins reproduces it exactly
+        int carryU = KSW_NEG_INF + (beg - 1) * e_ins, carryH = h1_init;
+        cells += (unsigned long long)(end > beg ? end - beg : 0);
+        for (int j0 = beg; j0 < end; j0 += 32) {
+            const int j = j0 + lane;
+            const bool act = j < end;
+            int m = KSW_NEG_INF, e = KSW_NEG_INF;
+            if (act) { m = ehh[j] + mrow[q[(long)j * qs]]; e = ehe[j]; }
+            int u = act ? (m - oe_ins) + j * e_ins : 2 * KSW_NEG_INF + 1;
+            int inc = u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int ov = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc = ::max(inc, ov); }
+            int ex = __shfl_up_sync(FULL, inc, 1);
+            ex = lane == 0 ? carryU : ::max(ex, carryU);
+            const int f = ex - (j - 1) * e_ins;        // F(i, j)
+            int d = m >= e ? 0 : 1;
+            int h = m >= e ? m : e;
+            d = h >= f ? d : 2;
+            h = h >= f ? h : f;
+            int hl = __shfl_up_sync(FULL, h, 1);
+            if (lane == 0) hl = carryH;
+            if (act) {
+                ehh[j] = hl;
+                int tt = m - oe_del, e2 = e - e_del;
+                d |= e2 > tt ? 1 << 2 : 0;
+                ehe[j] = e2 > tt ? e2 : tt;
+                tt = m - oe_ins;
+                d |= (f - e_ins) > tt ? 2 << 4 : 0;
+                if (zi) zi[j - beg] = (uint8_t)d;
+            }
+            const int last = (end - j0 < 32 ? end - j0 : 32) - 1;
+            carryU = ::max(carryU, __shfl_sync(FULL, inc, 31));
+            carryH = __shfl_sync(FULL, h, last);
+        }
+        if (lane == 0) { ehh[end] = carryH; ehe[end] = KSW_NEG_INF; }
+        __syncwarp();
+    }
+    int score = ehh[qlen];
+    __syncwarp();
+    return score;
+}

@@ -1,0 +1,68 @@
+// pipeline.cuh -- records passed between the per-read kernels (seed -> chain -> extend -> finalize).
+// Names follow libbwa's structs: mem_seed_t, mem_chain_t, mem_alnreg_t.
+#pragma once
+#include "common.cuh"
+
+struct SeedRec { int64_t rbeg; int32_t qbeg, len, score, next; };              // 24 B; `next` links a chain's seeds while chaining
+struct ChainRec { int64_t pos; int32_t rid, n_seeds, seed_off, kept; uint32_t w; float frac_rep; };  // 32 B; seed_off is relative to the read's seed block
+struct ChainTmp {                                                             // working record while chaining
+    int64_t pos, f_rbeg, l_rbeg;
+    int32_t f_qbeg, f_len, l_qbeg, l_len, head, tail, n, rid, first, kept;
+    uint32_t w, pad;
+};
+struct RegRec {                                                               // mem_alnreg_t
+    int64_t rb, re; uint64_t hash;
+    int32_t qb, qe, rid, score, truesc, sub, csub, sub_n, w, seedcov, secondary, seedlen0, n_comp;
+    float frac_rep;
+};
+// per read: where its block lives in the bump-allocated pools
+struct ReadBlock { uint32_t base, n_alloc, n_chains, n_seeds; };
+
+struct ChainParams {
+    const uint8_t* seqs; const uint64_t* offs; uint32_t n_reads;
+    const Intv* intv; const uint32_t* intv_cnt; uint32_t intv_cap;
+    // pools (pool_cap records each); a read's block is [base, base + n_alloc) in every pool
+    SeedRec* raw; ChainTmp* ctmp; uint32_t* ord; ChainRec* chains; SeedRec* seeds;
+    uint32_t pool_cap; uint32_t* pool_top;
+    ReadBlock* blocks;
+    uint32_t* ticket; uint32_t* overflow;
+    unsigned long long* counters;  // optional: [0] = SA lookups, [1] = equal-pos chain events (SURVEY A.5 corner)
+};
+void launch_chain(const ChainParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st);
+
+struct ExtendParams {
+    const uint8_t* seqs; const uint64_t* offs; uint32_t n_reads;
+    const ReadBlock* blocks; const ChainRec* chains; const SeedRec* seeds; uint64_t* srt;  // srt: one u64 per pooled seed
+    RegRec* regs; uint32_t* reg_cnt;       // a read's regions live at regs[blocks[r].base ...], at most n_seeds of them
+    uint8_t* scratch; size_t scratch_per_warp; uint32_t max_len, rseq_cap;
+    uint32_t* ticket; uint32_t* overflow;
+    unsigned long long* counters;  // optional: [0] = ksw_extend2 cells, [1] = calls, [2] = rows
+};
+void launch_extend(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st);
+size_t extend_scratch_per_warp(uint32_t max_len, uint32_t rseq_cap);
+int extend_resident_warps();
+
+struct RowDev {  // device image of bsq_row (include/bioseqdb_gpu.h)
+    int64_t rb, re, pos; uint64_t hash;
+    int32_t qb, qe, rid, score, truesc, sub, csub, sub_n, w, seedcov, secondary, seedlen0, n_comp;
+    float frac_rep;
+    int32_t is_rev, mapq, NM, flag;
+    uint32_t cigar_off, n_cigar;
+    int64_t ref_id;
+};
+static_assert(sizeof(RowDev) == 120, "RowDev must match bsq_row");
+
+struct FinalizeParams {
+    const uint8_t* seqs; const uint64_t* offs; const int64_t* ids; uint32_t n_reads;
+    const ReadBlock* blocks; RegRec* regs; const uint32_t* reg_cnt;
+    RowDev* rows;                 // same indexing as regs (block base); row_cnt[r] rows valid
+    uint32_t* row_cnt;
+    uint32_t* cigar_pool; uint32_t cigar_cap; uint32_t* cigar_top;
+    uint8_t* scratch; size_t scratch_per_warp; uint32_t max_len, z_cap;
+    const int64_t* ann_id;
+    uint32_t* ticket; uint32_t* overflow;
+    unsigned long long* counters;  // optional: [0] = ksw_global2 cells, [1] = calls
+};
+void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint32_t rseq_cap, int n_warps);
+size_t finalize_scratch_per_warp(uint32_t max_len, uint32_t rseq_cap, uint32_t* z_cap_out);
+int finalize_resident_warps();

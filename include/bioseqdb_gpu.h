@@ -1,0 +1,127 @@
+/* include/bioseqdb_gpu.h -- C ABI of libbioseqdb_gpu.so, the B200 (sm_100a) replacement for the
+ * libbwa calls that bioseqdb's bwa adapter makes.  Plain pointers and sizes only; no exceptions, no
+ * longjmp; every entry point returns 0 / a handle on success and BSQ_ERR / NULL on failure with the
+ * message available from bsq_last_error().
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference repo):
+ *   bsq_opts_init        mem_opt_init()                        bioseqdb/bwa.cpp:80
+ *   bsq_index_new        BwaIndex::BwaIndex()                  bioseqdb/bwa.cpp:80, bwa.h:34
+ *   bsq_index_set_opts   writes to BwaIndex::options           bioseqdb/extension.cpp:220-231
+ *   bsq_index_add_ref    BwaIndex::add_ref_sequence            bioseqdb/bwa.cpp:82-105
+ *   bsq_index_build      BwaIndex::build (pac2bwt, is_bwt, bwt_bwtupdate_core, bwt_cal_sa)
+ *                                                              bioseqdb/bwa.cpp:20-53,107-128
+ *   bsq_align_batch      the loop over BwaIndex::align_sequence (mem_align1 + mem_reg2aln per region)
+ *                                                              bioseqdb/bwa.cpp:141-181, extension.cpp:362-370
+ *   bsq_result_free / bsq_index_free   BwaIndex::~BwaIndex     bioseqdb/bwa.cpp:131-139
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef BIOSEQDB_GPU_H
+#define BIOSEQDB_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSQ_OK 0
+#define BSQ_ERR (-1)
+
+/* The 12 fields of the SQL composite bwa_options (bioseqdb--0.0.0.sql:160-173), read by name at
+ * extension.cpp:220-231.  Everything else keeps mem_opt_init() defaults; the scoring matrix is NOT
+ * refreshed when a/b change (reference behaviour). */
+typedef struct bsq_opts {
+    int32_t min_seed_len, max_occ, a, b, pen_clip3, pen_clip5, zdrop, w, o_del, e_del, o_ins, e_ins;
+} bsq_opts;
+
+/* == bntamb1_t (16 bytes), the hole record inside a NUCLSEQ datum (bioseqdb/sequence.h:13-14) */
+typedef struct bsq_hole { int64_t offset; int32_t len; char amb; } bsq_hole;
+
+/* One output row = one mem_alnreg_t plus the mem_aln_t fields of its mem_reg2aln (bwa.cpp:151-177).
+ * rb/re are positions in the doubled (forward+reverse) coordinate; pos is row-relative forward. */
+typedef struct bsq_row {
+    int64_t rb, re, pos; uint64_t hash;
+    int32_t qb, qe, rid, score, truesc, sub, csub, sub_n, w, seedcov, secondary, seedlen0, n_comp;
+    float frac_rep;
+    int32_t is_rev, mapq, NM, flag;
+    uint32_t cigar_off, n_cigar; /* bwa cigar words (len<<4|op, op: M0 I1 D2 S3) in bsq_result.cigar */
+    int64_t ref_id;              /* the id column of the reference row (bwa.cpp:160) */
+} bsq_row;
+
+typedef struct bsq_result {
+    uint64_t n_reads;
+    uint64_t* row_off; /* n_reads + 1 */
+    bsq_row* rows;     /* row_off[n_reads] rows, per read in reference order (score desc, hash) */
+    uint32_t* cigar;
+    uint64_t n_cigar_words;
+} bsq_result;
+
+/* per-stage device timings of the last bsq_align_batch / bsq_align_resident call, milliseconds */
+typedef struct bsq_timing {
+    float h2d, seed, chain, extend, finalize, d2h, total;
+    uint64_t launches; /* kernels launched by the call */
+    uint64_t h2d_bytes, d2h_bytes;
+} bsq_timing;
+
+typedef struct bsq_index bsq_index;
+
+const char* bsq_last_error(void);
+int bsq_device_count(void);
+
+void bsq_opts_init(bsq_opts* o);
+bsq_index* bsq_index_new(const bsq_opts* o, int device);
+int bsq_index_set_opts(bsq_index* h, const bsq_opts* o);
+int bsq_index_add_ref(bsq_index* h, int64_t id, const uint8_t* pac, uint32_t len, const bsq_hole* holes, uint32_t n_holes);
+int bsq_index_build(bsq_index* h);
+void bsq_index_free(bsq_index* h);
+
+/* reads: concatenated ASCII (what BwaIndex::align_sequence hands to mem_align1 after to_text_palloc,
+ * bwa.cpp:146-149), offs[n+1], ids[n] = the values lrand48() would have returned. */
+int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, bsq_result** out);
+void bsq_result_free(bsq_result* r);
+int bsq_last_timing(const bsq_index* h, bsq_timing* t);
+
+/* Resident-input variant used by bench.py's `value` leg: upload once, run the kernels with inputs and
+ * outputs resident in HBM, download on request. */
+int bsq_reads_upload(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n);
+int bsq_align_resident(bsq_index* h);
+int bsq_result_download(bsq_index* h, bsq_result** out);
+
+/* Index inspection (parity tests for SURVEY.md 8a rows a5-a7) and replication (8e: the built index is
+ * broadcast to the other GPUs of the box).  what: see BSQ_ARR_*.  Sizes in bytes. */
+enum { BSQ_ARR_PAC = 0, BSQ_ARR_OCC = 1, BSQ_ARR_SA = 2, BSQ_ARR_ANN_OFFSET = 3, BSQ_ARR_ANN_LEN = 4, BSQ_ARR_ANN_ID = 5, BSQ_ARR_COUNT = 6 };
+typedef struct bsq_index_meta {
+    int64_t l_pac; uint64_t seq_len, primary, L2[5]; uint64_t n_anns; uint32_t sa_bytes; /* 4 or 8 per SA entry */
+    uint32_t built; uint64_t arr_bytes[BSQ_ARR_COUNT]; double build_ms; uint64_t build_launches;
+    uint64_t sort_pass_bytes; /* algorithmic bytes moved by the radix passes of the build */
+} bsq_index_meta;
+int bsq_index_get_meta(const bsq_index* h, bsq_index_meta* m);
+int bsq_index_device_ptr(const bsq_index* h, int what, void** dptr);       /* device pointer of an index array */
+int bsq_index_download(const bsq_index* h, int what, void* host_dst, uint64_t bytes);
+int bsq_index_alloc_replica(bsq_index* h, const bsq_index_meta* m);        /* allocate arrays to receive a broadcast */
+int bsq_index_bwt_plain(const bsq_index* h, uint32_t* out);               /* the u32 stream of bwa.cpp:48-50 */
+int bsq_index_sa_sampled(const bsq_index* h, uint64_t* out, uint64_t n_sa); /* bwt_cal_sa(bwt, 32) view */
+
+/* Stage dumps for parity tests (device results copied to host): SMEM intervals after mem_collect_intv,
+ * one record = 4 x u64 {x0,x1,x2,info}; cnt[n] = intervals per read, cap = records per read in `out`. */
+int bsq_debug_seed(bsq_index* h, const char* seqs, const uint64_t* offs, uint64_t n, uint64_t* out, uint32_t cap, uint32_t* cnt);
+/* Kernel-level entry points for parity tests of the DP kernels on explicit job lists.
+ * ext jobs: query/target are nt4 bytes; out = 6 x int32 per job {score,qle,tle,gtle,gscore,max_off}. */
+int bsq_debug_ksw_extend(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
+                         const uint64_t* t_off, const int32_t* w, const int32_t* end_bonus, const int32_t* h0, int32_t* out);
+/* global jobs: out_score[n]; cigar words written at cigar + cig_cap*i with counts in n_cigar[i] */
+int bsq_debug_ksw_global(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
+                         const uint64_t* t_off, const int32_t* w, int32_t* out_score, uint32_t* cigar, uint32_t cig_cap, int32_t* n_cigar);
+/* random 64-byte gather microbenchmark over the Occ array (the seeding roofline denominator): GB/s */
+int bsq_bench_gather(bsq_index* h, uint64_t n_loads, int reps, double* gbs);
+/* DPX issue microbenchmark (independent __vimax3_s32 / __viaddmax_s32_relu): G instructions per second */
+int bsq_bench_dpx(int device, int reps, double* gops);
+/* Optional work counters of the last batch (the roofline's algorithmic units):
+ * out8 = {bwt_extend calls, SA lookups, equal-pos chain events, ksw_extend2 cells, calls, rows, ksw_global2 cells, calls} */
+int bsq_set_counters(bsq_index* h, int on);
+int bsq_get_counters(const bsq_index* h, uint64_t* out8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,79 @@
+"""End-to-end parity through the C ABI (bsq_align_batch) vs the oracle: identical ordered rows --
+rid, rb, re, qb, qe, strand, score, truesc, secondary, sub, sub_n, CIGAR, NM, MAPQ, hash order."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from bioseqdb_b200 import synth
+from helpers import build_pair, compare_results, read_arrays
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("opts_fn", [O.sql_default_opts, O.canonical_opts])
+def test_align_simulated(gpu_lib, opts_fn):
+    rows = synth.reference_rows([400_003, 300_001, 250_002, 49_999], seed=21)
+    orc, gpu = build_pair(rows, opts_fn(len(rows)))
+    seqs, offs, _ = synth.simulate_reads(rows, 6000, 150, seed=22)
+    ids = synth.lrand48_ids_fast(6000)
+    g = gpu.align_batch(seqs, offs, ids)
+    o = orc.align_batch(seqs, offs, ids, 4)
+    bad = compare_results(g, o)
+    assert not bad, "\n".join(bad)
+    assert int(g.row_off[-1]) >= 6000 * 0.99
+
+
+def test_align_repeats_and_noise(gpu_lib):
+    """repeat families => multiple chains, secondaries, sub/sub_n, dedup; higher error => clipping, band retries"""
+    rows = synth.reference_rows([300_000, 200_001], seed=31)
+    rows = synth.plant_repeats(rows, n_families=12, copies=10, unit=(150, 1200), divergence=0.03)
+    orc, gpu = build_pair(rows, O.sql_default_opts(2))
+    seqs, offs, _ = synth.simulate_reads(rows, 4000, 150, sub=0.03, ins=0.006, dele=0.006, seed=32, n_frac=0.002)
+    ids = synth.lrand48_ids_fast(4000)
+    g = gpu.align_batch(seqs, offs, ids)
+    o = orc.align_batch(seqs, offs, ids, 4)
+    bad = compare_results(g, o)
+    assert not bad, "\n".join(bad)
+    assert (g.rows["secondary"] >= 0).sum() > 0
+
+
+def test_align_edge_cases(gpu_lib):
+    rows = synth.reference_rows([60_001, 1_003, 501], seed=41)
+    orc, gpu = build_pair(rows, O.canonical_opts(3))
+    r0, r1, r2 = [r.tobytes() for r in rows]
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    reads = [
+        r0[1000:1150],                       # perfect forward
+        r0[2000:2150].translate(comp)[::-1],  # perfect reverse
+        r0[0:150], r0[60_001 - 150:],        # flush with the row ends
+        r1[1_003 - 150:], r2[:150], r2[501 - 100:],
+        r0[5:23], r0[5:24], b"", b"A", b"N" * 150,   # shorter than min_seed_len / exactly 19 / empty / all N
+        r0[3000:3070] + b"N" * 10 + r0[3080:3150],
+        r0[4000:4075] + r0[4090:4165],       # 15-base deletion
+        r0[5000:5075] + b"ACGTACGTACGT" + r0[5075:5138],  # 12-base insertion
+        r0[6000:6100] + r1[100:150],         # chimera across rows
+        r0[7000:7100] + r0[9000:9050],       # split within a row
+        b"ACGT" * 37,
+    ]
+    seqs, offs = read_arrays(reads)
+    ids = synth.lrand48_ids_fast(len(reads))
+    g = gpu.align_batch(seqs, offs, ids)
+    o = orc.align_batch(seqs, offs, ids, 1)
+    bad = compare_results(g, o)
+    assert not bad, "\n".join(bad)
+    assert g.cigar_of(g.rows_of(0)[0]) == "150M" and g.rows_of(0)[0]["mapq"] == 60
+    assert len(g.rows_of(7)) == 0 and len(g.rows_of(9)) == 0 and len(g.rows_of(11)) == 0
+
+
+def test_align_single_read_entry(gpu_lib):
+    """nuclseq_search_bwa shape: one read per call, ids continue across calls."""
+    rows = synth.reference_rows([80_000], seed=51)
+    orc, gpu = build_pair(rows, O.sql_default_opts(1))
+    seqs, offs, _ = synth.simulate_reads(rows, 5, 150, seed=52)
+    ids = synth.lrand48_ids(5)[0]
+    for i in range(5):
+        read = seqs[int(offs[i]):int(offs[i + 1])]
+        g = gpu.align_batch(read, np.array([0, 150], dtype=np.uint64))   # the index object draws its own ids
+        o = orc.align_batch(read, np.array([0, 150], dtype=np.uint64), ids[i:i + 1], 1)
+        bad = compare_results(g, o)
+        assert not bad, "\n".join(bad)

@@ -1,0 +1,65 @@
+"""the GPU-built FM-index (text, L2, BWT, primary, Occ checkpoints, SA) must
+equal the oracle's, which is pinned by brute-force suffix sorting (test_oracle.py)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from bioseqdb_b200 import synth
+from bioseqdb_b200 import _lib
+from helpers import build_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_index(orc, gpu):
+    oi, m = orc.info(), gpu.meta()
+    assert m.built == 1
+    assert (m.l_pac, m.seq_len, m.primary) == (oi["l_pac"], oi["seq_len"], oi["primary"])
+    assert list(m.L2) == oi["L2"]
+    assert np.array_equal(gpu.bwt_plain(), orc.bwt_plain())
+    assert np.array_equal(gpu.sa_sampled(), orc.sa())
+    assert np.array_equal(gpu.download(_lib.ARR_PAC), orc.pac())
+    # Occ checkpoints: GPU keeps 64-byte blocks {4 x u64 counts, 8 x u32}; the oracle has bwa's layout,
+    # identical for every full block
+    g = gpu.download(_lib.ARR_OCC).view(np.uint32)
+    o = orc.bwt_interleaved()
+    n_full = oi["seq_len"] // 128
+    assert np.array_equal(g[:n_full * 16], o[:n_full * 16])
+    # trailing count record = L2 differences
+    n_blocks = (oi["seq_len"] + 127) // 128
+    tail = g[n_blocks * 16:n_blocks * 16 + 8].view(np.uint64)
+    assert tail.tolist() == [oi["L2"][c + 1] - oi["L2"][c] for c in range(4)]
+    # full SA against the oracle's bwt_sa on a sample of rows
+    sa = gpu.download(_lib.ARR_SA).view(np.uint32 if m.sa_bytes == 4 else np.uint64)
+    assert int(sa[0]) == oi["seq_len"]
+    rng = np.random.default_rng(5)
+    for k in rng.integers(1, oi["seq_len"] + 1, size=300):
+        assert int(sa[int(k)]) == orc.bwt_sa(int(k))
+
+
+@pytest.mark.parametrize("lens", [[1000], [997, 1503, 64], [200_003, 150_001, 99_999]])
+def test_index_random(gpu_lib, lens):
+    rows = synth.reference_rows(lens, seed=synth.SEED_REF + len(lens))
+    orc, gpu = build_pair(rows, O.sql_default_opts(len(rows)))
+    _check_index(orc, gpu)
+
+
+@pytest.mark.parametrize("text", [b"A" * 300, b"ACGT" * 100, b"AC" * 257 + b"G", b"ACGTTGCA" * 40 + b"A" * 100, b"T", b"ACG"])
+def test_index_repetitive(gpu_lib, text):
+    """Low-complexity texts need many prefix-doubling rounds (the initial 28-mer keys tie)."""
+    orc, gpu = build_pair([text], O.sql_default_opts(1))
+    _check_index(orc, gpu)
+
+
+def test_index_with_holes(gpu_lib):
+    rows = [b"ACGTNNNNACGTRYACGT" * 30 + b"AC", b"N" * 50 + b"ACGT" * 50]
+    orc, gpu = build_pair(rows, O.sql_default_opts(2))
+    _check_index(orc, gpu)
+
+
+def test_empty_reference(gpu_lib):
+    """bwa.cpp:108-109,142-143: no rows => build is a no-op and alignment returns nothing."""
+    from bioseqdb_b200 import BwaIndex
+    ix = BwaIndex()
+    ix.build()
+    assert ix.align_sequence(b"ACGTACGTACGTACGTACGTACGT") == []

@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- 150 bp reads aligned per second through the bwa hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads R] [--ref-mbp M]
+
+A step = one pass of the hot path (seed_smem -> chain_build -> sw_extend -> regs_finalize) over one batch
+of simulated reads against the resident FM-index.  Default workload = BASELINE.json configs[1]:
+1 M simulated 150 bp reads (1 % error) vs a 100 Mbp synthetic reference (10 rows x 10 Mbp) on one B200,
+"SQL default" options (what bwa_opts() really delivers).
+
+  value   whole-job reads/s with the reads already resident in HBM (device time, CUDA events on the
+          library's launching stream, max over ranks)
+  e2e     the same metric through the C-ABI call bsq_align_batch with HOST buffers: pinned host reads in,
+          host rows out, H2D and D2H inside the timed region
+  roofline  for the dominant kernel; cpu_baseline = the CPU oracle on this box's host cores (bounded sample)
+
+--impl reference times the CPU path only (the reference cannot be compiled here -- no PostgreSQL / libbwa
+sources -- so this is the oracle port, all host threads, bounded sample per step).
+N > 1 (torchrun): the index is built on rank 0 and broadcast over NCCL, reads are sharded per rank
+(weak scaling: every rank aligns its own batch), no collective in the per-read path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+from bioseqdb_b200 import synth  # noqa: E402
+
+METRIC = "150bp_reads_aligned_per_sec"
+UNIT = "reads/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=1_000_000)
+    ap.add_argument("--ref-mbp", type=int, default=100)
+    ap.add_argument("--opts", default="sql", choices=["sql", "canonical"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU seconds of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def workload(args, rank):
+    rows_n = 10
+    per = args.ref_mbp * 1_000_000 // rows_n
+    rows = synth.reference_rows([per] * rows_n)
+    seqs, offs, truth = synth.simulate_reads(rows, args.reads, 150, seed=synth.SEED_READS + rank)
+    ids = synth.lrand48_ids_fast(args.reads)
+    return rows, seqs, offs, ids
+
+
+def opts_tuple(args, n_rows):
+    # (min_seed_len, max_occ, a, b, clip3, clip5, zdrop, w, o_del, e_del, o_ins, e_ins)
+    if args.opts == "sql":
+        return (19, max(500, 2 * n_rows), 1, 4, 5, 5, 100, 100, 6, 6, 1, 1)
+    return (19, max(500, 2 * n_rows), 1, 4, 5, 5, 100, 100, 6, 1, 6, 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.stop = threading.Event()
+        self.idx = gpu_index
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = max(int(r[1]) for r in self.rows if r[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import oracle_lib as O
+    rows, seqs, offs, ids = workload(args, 0)
+    cores = os.cpu_count() or 1
+    ot = opts_tuple(args, len(rows))
+    orc = O.OracleIndex(O.Opts(*ot))
+    for i, r in enumerate(rows):
+        orc.add_ref_text(i + 1, r.tobytes())
+    build_s = orc.build()
+    # bounded sample per step: size it from a short probe so that K + W steps end within a few minutes
+    probe = min(20_000, args.reads)
+    r = orc.align_batch(seqs[:int(offs[probe])], offs[:probe + 1], ids[:probe], cores)
+    rate = probe / max(r["seconds"], 1e-9)
+    sample = int(min(args.reads, max(probe, rate * args.cpu_seconds)))
+    times = []
+    for s in range(args.warmup + args.steps):
+        r = orc.align_batch(seqs[:int(offs[sample])], offs[:sample + 1], ids[:sample], cores)
+        if s >= args.warmup:
+            times.append(r["seconds"])
+    total = sum(times)
+    value = sample * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic", "config": config_dict(args, 1, sample_reads=sample),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d of %d reads per step, all %d host threads; index built once by the oracle's SA-IS in %.1f s (not in the step)" % (sample, args.reads, cores, build_s)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference cannot be compiled in this image (no PostgreSQL, libbwa, htslib sources): this arm is the CPU oracle port of the same path",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, n_gpus, **extra):
+    d = {"workload": "BASELINE configs[1]: %d simulated 150bp reads (1%% error: 0.8 sub / 0.1 ins / 0.1 del) per GPU vs %d Mbp synthetic reference (10 rows), index resident" % (args.reads, args.ref_mbp),
+         "options": "SQL default (o_del 6, e_del 6, o_ins 1, e_ins 1)" if args.opts == "sql" else "canonical bwa (6/1/6/1)",
+         "reads_per_gpu": args.reads, "read_len": 150, "ref_mbp": args.ref_mbp,
+         "l2_policy": "per-step working set (index %d MB + batch pools > 1 GB) exceeds the 126 MB L2; no explicit flush" % (args.ref_mbp * 2 + args.ref_mbp * 8 + args.ref_mbp // 4),
+         "parallelism": "reads sharded over %d GPU(s), index replicated" % n_gpus}
+    d.update(extra)
+    return d
+
+
+# ------------------------------------------------------------------------------------------ our arm
+class _CudaArray:
+    """Expose a raw device pointer through __cuda_array_interface__ so torch can wrap it (NCCL broadcast)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def broadcast_index(ix, rank, world, dist, torch):
+    """Rank 0 built the index; everybody else allocates and receives it."""
+    import ctypes as C
+    from bioseqdb_b200 import _lib
+    from bioseqdb_b200._lib import BsqMeta
+    meta_bytes = torch.zeros(C.sizeof(BsqMeta), dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        m = ix.meta()
+        meta_bytes.copy_(torch.frombuffer(bytearray(bytes(m)), dtype=torch.uint8))
+    dist.broadcast(meta_bytes, 0)
+    m = BsqMeta.from_buffer_copy(bytes(meta_bytes.cpu().numpy().tobytes()))
+    if rank != 0:
+        _lib.check(ix.L.bsq_index_alloc_replica(ix.h, C.byref(m)))
+    nbytes = 0
+    for what in range(_lib.ARR_COUNT):
+        p = C.c_void_p()
+        _lib.check(ix.L.bsq_index_device_ptr(ix.h, what, C.byref(p)))
+        n = int(m.arr_bytes[what])
+        if n == 0:
+            continue
+        t = torch.as_tensor(_CudaArray(p.value, n), device="cuda")
+        dist.broadcast(t, 0)
+        nbytes += n
+    torch.cuda.synchronize()
+    return nbytes
+
+
+def run_ours(args, rank, world, local_rank):
+    import ctypes as C
+    import torch
+    from bioseqdb_b200 import BwaIndex, BsqOpts, _lib
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev = local_rank if world > 1 else 0
+    rows, seqs, offs, ids = workload(args, rank)
+    ot = opts_tuple(args, len(rows))
+    ix = BwaIndex(dev, BsqOpts(*ot))
+    bcast_bytes = 0
+    t0 = time.time()
+    if world == 1 or rank == 0:
+        for i, r in enumerate(rows):
+            ix.add_ref_sequence(i + 1, r)
+        ix.build()
+    else:
+        for i, r in enumerate(rows):
+            ix._refs.append((i + 1, None))
+            ix.n_rows += 1
+    if world > 1:
+        bcast_bytes = broadcast_index(ix, rank, world, dist, torch)
+    meta = ix.meta()
+    build_wall = time.time() - t0
+    n = args.reads
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # pinned host staging for the e2e leg
+    seqs_pin = torch.from_numpy(seqs).pin_memory()
+    offs_pin = torch.from_numpy(offs.view(np.int64)).pin_memory()
+    ids_pin = torch.from_numpy(ids).pin_memory()
+
+    # ---------------- value: inputs resident in HBM
+    ix.upload(seqs, offs, ids)
+    ix.set_counters(True)
+    ix.align_resident()          # also sizes the pools (first run may re-run on overflow)
+    ctr = ix.counters()
+    ix.set_counters(False)
+    for _ in range(max(args.warmup, 3)):
+        ix.align_resident()
+    stage = {"seed": 0.0, "chain": 0.0, "extend": 0.0, "finalize": 0.0}
+    dev_ms = 0.0
+    launches = 0
+    barrier()
+    with ClockSampler(dev) as clk:
+        w0 = time.time()
+        for _ in range(args.steps):
+            ix.align_resident()
+            t = ix.timing()
+            dev_ms += t.total
+            launches += t.launches
+            for k in stage:
+                stage[k] += getattr(t, k)
+        barrier()
+        wall = time.time() - w0
+    clocks = clk.summary()
+    res = ix.download_result()
+    total_rows = int(res.row_off[-1])
+
+    # ---------------- e2e: host buffers through bsq_align_batch
+    resp = C.POINTER(_lib.BsqResult)()
+    def one_e2e():
+        _lib.check(ix.L.bsq_align_batch(ix.h, C.c_void_p(seqs_pin.data_ptr()), C.c_void_p(offs_pin.data_ptr()), C.c_void_p(ids_pin.data_ptr()), n, C.byref(resp)))
+        ix.L.bsq_result_free(resp)
+    for _ in range(2):
+        one_e2e()
+    barrier()
+    e0 = time.time()
+    e2e_dev_ms = 0.0
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        one_e2e()
+        t = ix.timing()
+        e2e_dev_ms += t.total
+        h2d, d2h = int(t.h2d_bytes), int(t.d2h_bytes)
+    barrier()
+    e2e_wall = time.time() - e0
+
+    # ---------------- max over ranks
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    dev_ms_max = allmax(dev_ms)
+    e2e_ms_max = allmax(e2e_dev_ms)
+    wall_max = allmax(wall)
+    e2e_wall_max = allmax(e2e_wall)
+    if dist is not None:
+        tot = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot)
+        launches_all = int(tot.item())
+    else:
+        launches_all = launches
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        value = n * world * args.steps / (dev_ms_max * 1e-3)
+        e2e_value = n * world * args.steps / max(e2e_ms_max * 1e-3, 1e-9)
+        # roofline of the dominant kernel (by device time share)
+        dom = max(stage, key=stage.get)
+        seed_bytes = 64.0 * 2.0 * ctr["n_extend"]                 # per launch: two 64-byte Occ blocks per bwt_extend
+        seed_s = stage["seed"] / args.steps * 1e-3
+        gather = C.c_double(0)
+        _lib.check(ix.L.bsq_bench_gather(ix.h, 1 << 28, 3, C.byref(gather)))
+        dpx = C.c_double(0)
+        _lib.check(ix.L.bsq_bench_dpx(dev, 3, C.byref(dpx)))
+        roof = {"kernel": "seed_smem", "bound": "hbm", "achieved": seed_bytes / seed_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": seed_bytes / seed_s / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": seed_bytes, "random_gather_peak_gbs": gather.value,
+                "frac_of_random_gather": seed_bytes / seed_s / 1e9 / max(gather.value, 1e-9),
+                "dominant_kernel_by_time": dom}
+        ext_s = stage["extend"] / args.steps * 1e-3
+        fin_s = stage["finalize"] / args.steps * 1e-3
+        sw = {"ksw_extend2_gcups": ctr["ext_cells"] / ext_s / 1e9, "ksw_global2_gcups_incl_finalize": ctr["glb_cells"] / fin_s / 1e9,
+              "ext_cells_per_launch": ctr["ext_cells"], "glb_cells_per_launch": ctr["glb_cells"], "dpx_peak_ginstr_s": dpx.value}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "config": config_dict(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms_max / args.steps, "wall_ms_per_step": 1e3 * e2e_wall_max / args.steps},
+            "gpu_launches": launches_all,
+            "clocks": clocks,
+            "roofline": roof, "sw": sw,
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+            "wall_ms_per_step": 1e3 * wall_max / args.steps,
+            "rows_per_step_rank0": total_rows,
+            "index": {"build_ms_device": meta.build_ms, "build_wall_s": build_wall, "build_launches": int(meta.build_launches),
+                      "sort_pass_gbs": (meta.sort_pass_bytes / (meta.build_ms * 1e-3) / 1e9) if meta.build_ms else None,
+                      "seq_len": int(meta.seq_len), "broadcast_bytes": bcast_bytes},
+            "counters_per_launch": ctr,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, rows, seqs, offs, ids, ix, ot)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, rows, seqs, offs, ids, ix, ot):
+    """The oracle port on this box's host cores, bounded sample; the index arrays are adopted from the GPU
+    build (they are mathematically unique) so that the sample budget goes to alignment."""
+    import oracle_lib as O
+    cores = os.cpu_count() or 1
+    orc = O.OracleIndex(O.Opts(*ot))
+    for i, r in enumerate(rows):
+        orc.add_ref_text(i + 1, r.tobytes())
+    orc.adopt(ix.bwt_plain(), int(ix.meta().primary), ix.sa_sampled())
+    probe = min(20_000, args.reads)
+    r = orc.align_batch(seqs[:int(offs[probe])], offs[:probe + 1], ids[:probe], cores)
+    rate = probe / max(r["seconds"], 1e-9)
+    sample = int(min(args.reads, max(probe, rate * args.cpu_seconds)))
+    r = orc.align_batch(seqs[:int(offs[sample])], offs[:sample + 1], ids[:sample], cores)
+    r1 = orc.align_batch(seqs[:int(offs[probe])], offs[:probe + 1], ids[:probe], 1)
+    # index build on a bounded 8 Mbp sample, 1 core
+    small = O.OracleIndex(O.Opts(*ot))
+    small.add_ref_text(1, rows[0][:8_000_000].tobytes())
+    bs = small.build()
+    return {"value": sample / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of %d reads, %d threads, FM-index arrays adopted from the GPU build" % (sample, args.reads, cores),
+            "one_core_reads_per_s": probe / r1["seconds"], "index_build_s_8Mbp_1core": bs,
+            "oracle_counters_per_read": {k: v / sample for k, v in r["counters"].items()}}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

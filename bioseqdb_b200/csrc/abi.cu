@@ -337,7 +337,7 @@ int run_pipeline(bsq_index* h) {
     if (!b.resident) { bsq_set_error("no reads uploaded"); return BSQ_ERR; }
     const uint32_t n = (uint32_t)b.n;
     bsq_timing& T = h->timing;
-    T.seed = T.chain = T.extend = T.finalize = 0;
+    T.seed = T.chain = T.extend = T.finalize = T.total = 0;
     if (n == 0 || !h->meta.built) { b.aligned = true; return BSQ_OK; }
     const DevIndex ix = make_dev_index(h);
     const DevOpts& o = h->dopts;
@@ -379,7 +379,7 @@ int run_pipeline(bsq_index* h) {
         {
             SeedParams P;
             P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = b.intv_cap;
-            P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.ticket = b.ctl.p + 0; P.overflow = b.ctl.p + 4; P.n_extend = ctr ? ctr + 0 : nullptr;
+            P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.lists_in_smem = seed_lists_fit_smem(b.list_cap); P.ticket = b.ctl.p + 0; P.overflow = b.ctl.p + 4; P.n_extend = ctr ? ctr + 0 : nullptr;
             launch_seed(P, ix, o, h->stream, nullptr); ++T.launches;
         }
         cudaEventRecord(ev[1], h->stream);
@@ -419,6 +419,7 @@ int run_pipeline(bsq_index* h) {
         cudaEventElapsedTime(&ms, ev[1], ev[2]); T.chain += ms;
         cudaEventElapsedTime(&ms, ev[2], ev[3]); T.extend += ms;
         cudaEventElapsedTime(&ms, ev[3], ev[4]); T.finalize += ms;
+        cudaEventElapsedTime(&ms, ev[0], ev[4]); T.total += ms;
         if (ctl[4] == 0) {
             if (ctr) { ENS(cudaMemcpy(h->counters, ctr, sizeof(h->counters), cudaMemcpyDeviceToHost)); }
             b.aligned = true;
@@ -568,7 +569,7 @@ int bsq_debug_seed(bsq_index* h, const char* seqs, const uint64_t* offs, uint64_
     CUDA_CHECK(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, h->stream));
     SeedParams P;
     P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = (uint32_t)n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = cap;
-    P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.ticket = b.ctl.p; P.overflow = b.ctl.p + 4; P.n_extend = reinterpret_cast<unsigned long long*>(b.ctl.p + 8);
+    P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.lists_in_smem = seed_lists_fit_smem(b.list_cap); P.ticket = b.ctl.p; P.overflow = b.ctl.p + 4; P.n_extend = reinterpret_cast<unsigned long long*>(b.ctl.p + 8);
     launch_seed(P, ix, h->dopts, h->stream, nullptr);
     uint32_t ctl[8];
     CUDA_CHECK(cudaMemcpyAsync(ctl, b.ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));

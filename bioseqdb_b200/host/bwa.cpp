@@ -1,0 +1,100 @@
+// bwa.cpp -- see bwa.h.  Mirrors reference bioseqdb/bwa.cpp:55-181 with libbwa replaced by the C ABI.
+#include "bwa.h"
+#include <algorithm>
+#include <stdexcept>
+
+namespace bioseqdb {
+
+static void fail() { throw std::runtime_error(bsq_last_error()); }
+
+std::string cigar_compressed_to_string(const uint32_t* raw, int len) {
+    std::string cigar;
+    for (int i = 0; i < len; ++i) {
+        cigar += std::to_string(raw[i] >> 4);     // bam_cigar_oplen
+        cigar += "MIDNSHP=XB"[raw[i] & 0xf];      // bam_cigar_opchr: bwa's soft clip (3) prints as 'N' 
+    }
+    return cigar;
+}
+
+BwaIndex::BwaIndex(int device) : index(nullptr), lrand_state(0) {
+    bsq_opts_init(&options);
+    index = bsq_index_new(&options, device);
+    if (!index) fail();
+}
+
+BwaIndex::~BwaIndex() { bsq_index_free(index); }
+
+void BwaIndex::add_ref_sequence(int64_t id, const NucleotideSequence& seq) {
+    offsets.push_back((int64_t)pac_forward.size() * 4);
+    pac_forward.insert(pac_forward.end(), seq.pac(), seq.pac() + pac_byte_size(seq.len));
+    holes.insert(holes.end(), seq.holes(), seq.holes() + seq.holes_num());
+    if (bsq_index_add_ref(index, id, seq.pac(), seq.len, seq.holes(), seq.holes_num()) != BSQ_OK) fail();
+}
+
+void BwaIndex::build() {
+    if (pac_forward.empty()) return;
+    if (bsq_index_set_opts(index, &options) != BSQ_OK) fail();
+    if (bsq_index_build(index) != BSQ_OK) fail();
+}
+
+std::string BwaIndex::extract_reference_subseq(int64_t rb, int64_t re) const {
+    // Forward hits: the reference's arithmetic incl. the un-rebased hole overlay.  Reverse hits
+    // index past pac_forward in the reference (UB, B#3): defined here as the reverse-strand text.
+    const int64_t l_pac = (int64_t)pac_forward.size() * 4;
+    std::string subseq((size_t)(re - rb), '?');
+    for (int64_t i = 0; i < re - rb; ++i) {
+        const int64_t p = rb + i;
+        const int c = p < l_pac ? pac_raw_get(pac_forward.data(), (size_t)p) : 3 - pac_raw_get(pac_forward.data(), (size_t)((l_pac << 1) - 1 - p));
+        subseq[(size_t)i] = "ACGT"[c];
+    }
+    for (const bsq_hole& h : holes) {
+        const int64_t l = std::max<int64_t>(h.offset, rb), r = std::min<int64_t>(h.offset + h.len, re);
+        for (int64_t i = l; i < r; ++i) subseq[(size_t)(i - rb)] = h.amb;
+    }
+    return subseq;
+}
+
+std::vector<std::vector<BwaMatch>> BwaIndex::align_sequences(const std::vector<const NucleotideSequence*>& seqs) {
+    std::vector<std::vector<BwaMatch>> out(seqs.size());
+    if (pac_forward.empty() || seqs.empty()) return out;
+    std::string cat;
+    std::vector<uint64_t> offs(seqs.size() + 1, 0);
+    std::vector<int64_t> ids(seqs.size());
+    std::vector<std::string> texts(seqs.size());
+    for (size_t i = 0; i < seqs.size(); ++i) {
+        texts[i] = seqs[i]->to_text();
+        cat += texts[i];
+        offs[i + 1] = cat.size();
+        lrand_state = (lrand_state * 0x5DEECE66DULL + 0xBULL) & 0xFFFFFFFFFFFFULL;   // id = lrand48()
+        ids[i] = (int64_t)(lrand_state >> 17);
+    }
+    bsq_result* res = nullptr;
+    if (bsq_align_batch(index, cat.data(), offs.data(), ids.data(), seqs.size(), &res) != BSQ_OK) fail();
+    for (size_t i = 0; i < seqs.size(); ++i) {
+        for (uint64_t k = res->row_off[i]; k < res->row_off[i + 1]; ++k) {
+            const bsq_row& a = res->rows[k];
+            const int64_t ref_offset = offsets[(size_t)a.rid];
+            BwaMatch m;
+            m.ref_id = a.ref_id;
+            m.ref_subseq = extract_reference_subseq(a.rb, a.re);
+            m.ref_match_begin = (int32_t)(a.rb - ref_offset);
+            m.ref_match_end = (int32_t)(a.re - ref_offset);
+            m.ref_match_len = (int32_t)(a.re - a.rb);
+            m.query_subseq = texts[i].substr((size_t)a.qb, (size_t)(a.qe - a.qb));
+            m.query_match_begin = a.qb; m.query_match_end = a.qe; m.query_match_len = a.qe - a.qb;
+            m.is_primary = (a.flag & 0x100) == 0; m.is_secondary = (a.flag & 0x100) != 0; m.is_reverse = a.is_rev != 0;
+            m.cigar = cigar_compressed_to_string(res->cigar + a.cigar_off, (int)a.n_cigar);
+            m.score = a.score; m.mapq = a.mapq; m.nm = a.NM;
+            out[i].push_back(std::move(m));
+        }
+    }
+    bsq_result_free(res);
+    return out;
+}
+
+std::vector<BwaMatch> BwaIndex::align_sequence(const NucleotideSequence& seq) {
+    if (pac_forward.empty()) return {};
+    return std::move(align_sequences({&seq})[0]);
+}
+
+}  // namespace bioseqdb

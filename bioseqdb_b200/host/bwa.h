@@ -1,0 +1,55 @@
+// bwa.h -- host C++ mirror of the reference adapter interface (bioseqdb/bwa.h:15-48): BwaMatch and
+// BwaIndex{add_ref_sequence, build, align_sequence}, same names and argument meaning, implemented over the
+// C ABI of libbioseqdb_gpu.so instead of libbwa.  `options` is the POD the PG glue writes by field
+// (extension.cpp:220-231).  Errors surface as std::runtime_error carrying bsq_last_error(); the PG glue
+// turns them into ereport(ERROR).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "sequence.h"
+#include "../../include/bioseqdb_gpu.h"
+
+namespace bioseqdb {
+
+struct BwaMatch {
+    int64_t ref_id;
+    std::string ref_subseq;
+    int32_t ref_match_begin, ref_match_end, ref_match_len;
+    std::string query_subseq;
+    int32_t query_match_begin, query_match_end, query_match_len;
+    bool is_primary, is_secondary, is_reverse;
+    std::string cigar;
+    int score;
+    // computed by the path but not exported by the reference's SQL row
+    int mapq, nm;
+};
+
+class BwaIndex {
+public:
+    explicit BwaIndex(int device = 0);
+    ~BwaIndex();
+    BwaIndex(const BwaIndex&) = delete;
+    BwaIndex& operator=(const BwaIndex&) = delete;
+
+    std::vector<BwaMatch> align_sequence(const NucleotideSequence& seq);
+    // batched form of the per-read loop at extension.cpp:362-370: one GPU pass for all reads
+    std::vector<std::vector<BwaMatch>> align_sequences(const std::vector<const NucleotideSequence*>& seqs);
+    void build();
+    void add_ref_sequence(int64_t id, const NucleotideSequence& seq);
+
+    bsq_opts options;            // written by bwa_index_from_query before build()
+    size_t ref_count() const { return offsets.size(); }
+
+private:
+    std::vector<uint8_t> pac_forward;      // kept on the host for extract_reference_subseq (bwa.cpp:55-68)
+    std::vector<bsq_hole> holes;           // not rebased, as in the reference (bwa.cpp:100-104)
+    std::vector<int64_t> offsets;
+    bsq_index* index;
+    uint64_t lrand_state;                  // glibc lrand48 state: one draw per aligned read
+    std::string extract_reference_subseq(int64_t ref_begin, int64_t ref_end) const;
+};
+
+std::string cigar_compressed_to_string(const uint32_t* raw, int len);   // htslib letters on bwa op codes (bwa.cpp:70-77)
+
+}  // namespace bioseqdb

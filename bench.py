@@ -166,40 +166,6 @@ def config_dict(args, n_gpus, **extra):
 
 
 # ------------------------------------------------------------------------------------------ our arm
-class _CudaArray:
-    """Expose a raw device pointer through __cuda_array_interface__ so torch can wrap it (NCCL broadcast)."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
-def broadcast_index(ix, rank, world, dist, torch):
-    """Rank 0 built the index; everybody else allocates and receives it."""
-    import ctypes as C
-    from bioseqdb_b200 import _lib
-    from bioseqdb_b200._lib import BsqMeta
-    meta_bytes = torch.zeros(C.sizeof(BsqMeta), dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        m = ix.meta()
-        meta_bytes.copy_(torch.frombuffer(bytearray(bytes(m)), dtype=torch.uint8))
-    dist.broadcast(meta_bytes, 0)
-    m = BsqMeta.from_buffer_copy(bytes(meta_bytes.cpu().numpy().tobytes()))
-    if rank != 0:
-        _lib.check(ix.L.bsq_index_alloc_replica(ix.h, C.byref(m)))
-    nbytes = 0
-    for what in range(_lib.ARR_COUNT):
-        p = C.c_void_p()
-        _lib.check(ix.L.bsq_index_device_ptr(ix.h, what, C.byref(p)))
-        n = int(m.arr_bytes[what])
-        if n == 0:
-            continue
-        t = torch.as_tensor(_CudaArray(p.value, n), device="cuda")
-        dist.broadcast(t, 0)
-        nbytes += n
-    torch.cuda.synchronize()
-    return nbytes
-
-
 def run_ours(args, rank, world, local_rank):
     import ctypes as C
     import torch
@@ -226,7 +192,8 @@ def run_ours(args, rank, world, local_rank):
             ix._refs.append((i + 1, None))
             ix.n_rows += 1
     if world > 1:
-        bcast_bytes = broadcast_index(ix, rank, world, dist, torch)
+        from bioseqdb_b200.dist import broadcast_index
+        bcast_bytes = broadcast_index(ix, rank, dist)
     meta = ix.meta()
     build_wall = time.time() - t0
     n = args.reads

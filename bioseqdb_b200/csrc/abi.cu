@@ -49,13 +49,13 @@ struct Batch {
     DevBuf<RegRec> regs; DevBuf<RowDev> rows, rows_compact; DevBuf<uint32_t> reg_cnt, row_cnt, row_off, scan_tmp;
     DevBuf<ReadBlock> blocks; uint32_t pool_cap = 0;
     DevBuf<uint32_t> cigar; uint32_t cigar_cap = 0;
-    DevBuf<uint8_t> ext_scratch, fin_scratch;
-    DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..] counters (u64 x 8)
+    DevBuf<uint8_t> ext_scratch, fin_scratch, narrow_z; DevBuf<uint64_t> narrow_jobs, wide_jobs;
+    DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..23] counters (u64 x 8), [24] narrow_cnt, [25] wide_cnt, [26..27] tickets
     bool resident = false, aligned = false;
     void release() {
         seqs.release(); offs.release(); ids.release(); intv.release(); intv_cnt.release(); seed_scratch.release(); raw.release(); seeds.release();
         ctmp.release(); ord.release(); chains.release(); srt.release(); regs.release(); rows.release(); rows_compact.release(); reg_cnt.release();
-        row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release(); ctl.release();
+        row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release(); ctl.release(); narrow_z.release(); narrow_jobs.release(); wide_jobs.release();
     }
 };
 
@@ -372,6 +372,9 @@ int run_pipeline(bsq_index* h) {
         ENS(b.scan_tmp.ensure(prim::scan_tmp_elems(n + 1) + 16));
         ENS(b.cigar.ensure(b.cigar_cap));
         ENS(b.ext_scratch.ensure((size_t)ext_warps * ext_per_warp)); ENS(b.fin_scratch.ensure((size_t)fin_warps * fin_per_warp));
+        int narrow_warps = 0;
+        const size_t narrow_bytes = narrow_zbuf_bytes(&narrow_warps);
+        ENS(b.narrow_z.ensure(narrow_bytes)); ENS(b.narrow_jobs.ensure(b.pool_cap)); ENS(b.wide_jobs.ensure(b.pool_cap));
         ENS(b.ctl.ensure(64));
         ENS(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, h->stream));
         unsigned long long* ctr = h->collect_counters ? reinterpret_cast<unsigned long long*>(b.ctl.p + 8) : nullptr;
@@ -404,8 +407,9 @@ int run_pipeline(bsq_index* h) {
             P.seqs = b.seqs.p; P.offs = b.offs.p; P.ids = b.ids.p; P.n_reads = n; P.blocks = b.blocks.p; P.regs = b.regs.p; P.reg_cnt = b.reg_cnt.p;
             P.rows = b.rows.p; P.row_cnt = b.row_cnt.p; P.cigar_pool = b.cigar.p; P.cigar_cap = b.cigar_cap; P.cigar_top = b.ctl.p + 6;
             P.scratch = b.fin_scratch.p; P.scratch_per_warp = fin_per_warp; P.max_len = max_len; P.z_cap = z_cap; P.ann_id = h->d_ann_id;
-            P.ticket = b.ctl.p + 3; P.overflow = b.ctl.p + 4; P.counters = ctr ? ctr + 6 : nullptr;
-            launch_finalize(P, ix, o, h->stream, rseq_cap, fin_warps); ++T.launches;
+            P.narrow_jobs = b.narrow_jobs.p; P.narrow_cnt = b.ctl.p + 24; P.wide_jobs = b.wide_jobs.p; P.wide_cnt = b.ctl.p + 25; P.narrow_z = b.narrow_z.p; P.narrow_warps = narrow_warps;
+            P.ticket = b.ctl.p + 26; P.overflow = b.ctl.p + 4; P.counters = ctr ? ctr + 6 : nullptr;
+            launch_finalize(P, ix, o, h->stream, rseq_cap, fin_warps, &T.launches);
         }
         // compact rows: exclusive scan of row_cnt (n + 1 entries, the last one is a zero pad) -> row_off
         prim::device_scan<uint32_t, prim::OpSum, false>(b.row_cnt.p, b.row_off.p, n, b.scan_tmp.p, prim::OpSum(), h->stream, &T.launches);

@@ -13,6 +13,12 @@ namespace {
 
 constexpr int FIN_THREADS = 128;
 constexpr int FIN_WARPS = FIN_THREADS / 32;
+// thread-per-region kernel limits: band columns (circular row buffer), target rows, query length
+constexpr int NARROW_NC = 64;
+constexpr int NARROW_TMAX = 192;
+constexpr int NARROW_QMAX = 160;
+constexpr int NARROW_THREADS = 128;
+constexpr int NARROW_CIG = 48;
 
 struct FScratch { int* ehh; int* ehe; uint8_t* rseq; uint8_t* query; uint8_t* z; uint32_t* cig; };
 
@@ -148,6 +154,98 @@ __device__ int patch_reg(const DevIndex& ix, const DevOpts& o, const int* smat, 
     return score;
 }
 
+__device__ __forceinline__ RowDev row_from_reg(const RegRec& ar, const int64_t* ann_id) {
+    RowDev row;
+    row.rb = ar.rb; row.re = ar.re; row.pos = 0; row.hash = ar.hash; row.qb = ar.qb; row.qe = ar.qe; row.rid = ar.rid; row.score = ar.score;
+    row.truesc = ar.truesc; row.sub = ar.sub; row.csub = ar.csub; row.sub_n = ar.sub_n; row.w = ar.w; row.seedcov = ar.seedcov;
+    row.secondary = ar.secondary; row.seedlen0 = ar.seedlen0; row.n_comp = ar.n_comp; row.frac_rep = ar.frac_rep;
+    row.is_rev = 0; row.mapq = 0;   // mapq is filled on the host (mem_approx_mapq_se needs libm log)
+    row.NM = -1; row.flag = ar.secondary >= 0 ? 0x100 : 0; row.cigar_off = 0; row.n_cigar = 0;
+    row.ref_id = ann_id[ar.rid];
+    return row;
+}
+
+__device__ __forceinline__ int reg2aln_w2(const DevOpts& o, const RegRec& ar) {
+    const int qb = ar.qb, qe = ar.qe; const int64_t rb = ar.rb, re = ar.re;
+    int tmpw = infer_bw(qe - qb, (int)(re - rb), ar.truesc, o.a, o.o_del, o.e_del);
+    int w2 = infer_bw(qe - qb, (int)(re - rb), ar.truesc, o.a, o.o_ins, o.e_ins);
+    w2 = w2 > tmpw ? w2 : tmpw;
+    if (w2 > o.w) w2 = w2 < ar.w ? w2 : ar.w;
+    return w2;
+}
+
+// effective band of bwa_gen_cigar2 for a requested w_
+__device__ __forceinline__ int gen_cigar_band(const DevOpts& o, int l_query, int rlen, int w_) {
+    int max_ins = (int)((double)(((l_query + 1) >> 1) * o.mat[0] - o.o_ins) / o.e_ins + 1.);
+    int max_del = (int)((double)(((l_query + 1) >> 1) * o.mat[0] - o.o_del) / o.e_del + 1.);
+    int max_gap = max_ins > max_del ? max_ins : max_del;
+    max_gap = max_gap > 1 ? max_gap : 1;
+    int dl = rlen - l_query; dl = dl < 0 ? -dl : dl;
+    int w = (max_gap + dl + 1) >> 1;
+    w = w < w_ ? w : w_;
+    const int min_w = dl + 3;
+    return w > min_w ? w : min_w;
+}
+
+__device__ __forceinline__ bool is_narrow_first_try(const DevOpts& o, const RegRec& ar, uint32_t max_len) {
+    const int lq = ar.qe - ar.qb; const int64_t rl = ar.re - ar.rb;
+    if (max_len > NARROW_QMAX || lq <= 0 || rl <= 0 || rl > NARROW_TMAX) return false;
+    int w2 = reg2aln_w2(o, ar);
+    w2 = w2 < o.w << 2 ? w2 : o.w << 2;
+    if (lq == rl && w2 == 0) return true;
+    return 2 * gen_cigar_band(o, lq, (int)rl, w2) + 1 <= NARROW_NC;
+}
+
+// mem_reg2aln for one region on the whole warp; completes *out (NM, pos, is_rev, CIGAR)
+__device__ void reg2aln_warp(const FinalizeParams& P, const DevIndex& ix, const DevOpts& o, const int* smat, const FScratch& S, uint32_t cig_cap,
+                             uint32_t rseq_cap, int l_query, const RegRec& ar, RowDev* out, unsigned long long& cells, unsigned long long& calls) {
+    const int lane = lane_id();
+    const int qb = ar.qb, qe = ar.qe; const int64_t rb = ar.rb, re = ar.re;
+    int w2 = reg2aln_w2(o, ar);
+    int it = 0, score = 0, last_sc = -(1 << 30);
+    GenOut g;
+    do {
+        w2 = w2 < o.w << 2 ? w2 : o.w << 2;
+        g = gen_cigar2<true>(ix, o, smat, w2, qe - qb, S.query + qb, rb, re, S, rseq_cap, P.z_cap, cig_cap - 2, P.overflow, cells, calls);
+        if (g.ok) score = g.score;
+        if (score == last_sc || w2 == o.w << 2) break;
+        last_sc = score;
+        w2 <<= 1;
+    } while (++it < 3 && score < ar.truesc - o.a);
+    int is_rev;
+    int64_t pos = bns_depos(ix, rb < ix.l_pac ? rb : re - 1, &is_rev);
+    // squeeze out a leading or trailing deletion, add soft clips, publish the CIGAR
+    int n_cigar = g.n_cigar, first = 0;
+    if (n_cigar > 0) {
+        if ((S.cig[0] & 0xf) == 2) { pos += S.cig[0] >> 4; first = 1; --n_cigar; }
+        else if ((S.cig[g.n_cigar - 1] & 0xf) == 2) --n_cigar;
+    }
+    int clip5 = 0, clip3 = 0;
+    if (qb != 0 || qe != l_query) { clip5 = is_rev ? l_query - qe : qb; clip3 = is_rev ? qb : l_query - qe; }
+    const int n_out = n_cigar + (clip5 ? 1 : 0) + (clip3 ? 1 : 0);
+    uint32_t coff = 0;
+    if (lane == 0 && n_out) coff = atomicAdd(P.cigar_top, (uint32_t)n_out);
+    coff = __shfl_sync(FULL, coff, 0);
+    uint32_t r_off = 0, r_n = 0;
+    if ((uint64_t)coff + (uint64_t)n_out > (uint64_t)P.cigar_cap) { if (lane == 0) atomicExch(P.overflow, 1u); }
+    else {
+        r_off = coff; r_n = (uint32_t)n_out;
+        if (lane == 0) {
+            uint32_t* dst = P.cigar_pool + coff;
+            int k = 0;
+            if (clip5) dst[k++] = (uint32_t)clip5 << 4 | 3;
+            for (int c = 0; c < n_cigar; ++c) dst[k++] = S.cig[first + c];
+            if (clip3) dst[k++] = (uint32_t)clip3 << 4 | 3;
+        }
+    }
+    const int rid = bns_pos2rid(ix, pos);
+    if (lane == 0) {
+        out->NM = g.NM; out->is_rev = is_rev; out->cigar_off = r_off; out->n_cigar = r_n;
+        out->pos = pos - ix.ann_offset[rid < 0 ? 0 : rid];
+    }
+    __syncwarp();
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(FIN_THREADS) regs_finalize(FinalizeParams P, DevIndex ix, DevOpts o, uint32_t cig_cap, uint32_t rseq_cap) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -280,65 +378,244 @@ __global__ void __launch_bounds__(FIN_THREADS) regs_finalize(FinalizeParams P, D
             if ((uint32_t)nz > cig_cap) atomicExch(P.overflow, 2u);
         }
         __syncwarp();
-        // ---------------- mem_reg2aln per region (reference bwa.cpp:151-177 calls it for every region)
+        // ---------------- mem_reg2aln per region (reference bwa.cpp:151-177 calls it for every region):
+        // narrow-band regions are queued for the thread-per-region kernel, the rest run here on the warp
         RowDev* rows = P.rows + blk.base;
         for (int i = 0; i < n; ++i) {
             const RegRec ar = a[i];
-            RowDev row;
-            row.rb = ar.rb; row.re = ar.re; row.hash = ar.hash; row.qb = ar.qb; row.qe = ar.qe; row.rid = ar.rid; row.score = ar.score;
-            row.truesc = ar.truesc; row.sub = ar.sub; row.csub = ar.csub; row.sub_n = ar.sub_n; row.w = ar.w; row.seedcov = ar.seedcov;
-            row.secondary = ar.secondary; row.seedlen0 = ar.seedlen0; row.n_comp = ar.n_comp; row.frac_rep = ar.frac_rep;
-            row.mapq = 0;   // filled on the host (mem_approx_mapq_se needs libm log)
-            row.flag = ar.secondary >= 0 ? 0x100 : 0;
-            const int qb = ar.qb, qe = ar.qe; const int64_t rb = ar.rb, re = ar.re;
-            int tmpw = infer_bw(qe - qb, (int)(re - rb), ar.truesc, o.a, o.o_del, o.e_del);
-            int w2 = infer_bw(qe - qb, (int)(re - rb), ar.truesc, o.a, o.o_ins, o.e_ins);
-            w2 = w2 > tmpw ? w2 : tmpw;
-            if (w2 > o.w) w2 = w2 < ar.w ? w2 : ar.w;
-            int it = 0, score = 0, last_sc = -(1 << 30);
-            GenOut g;
+            RowDev row = row_from_reg(ar, P.ann_id);
+            const bool narrow = P.narrow_jobs != nullptr && is_narrow_first_try(o, ar, P.max_len);
+            if (lane == 0) {
+                rows[i] = row;
+                if (narrow) { uint32_t k = atomicAdd(P.narrow_cnt, 1u); P.narrow_jobs[k] = (uint64_t)r << 32 | (uint64_t)(blk.base + i); }
+            }
+            __syncwarp();
+            if (!narrow) reg2aln_warp(P, ix, o, smat, S, cig_cap, rseq_cap, l_query, ar, rows + i, cells, calls);
+        }
+        if (lane == 0) P.row_cnt[r] = (uint32_t)n;
+    }
+    if (P.counters && lane == 0) { atomicAdd(&P.counters[0], cells); atomicAdd(&P.counters[1], calls); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Thread-per-region mem_reg2aln for narrow bands (the common case for 150 bp reads: w = 6..31).
+// One thread runs the scalar ksw_global2 recurrence; the row buffer is a 64-entry circular window in
+// shared memory laid out [column][thread] (bank = thread, conflict-free for any column), the query is
+// staged in shared memory the same way, reference bases are decoded from pac once per row, traceback
+// bytes go to a per-warp global buffer laid out [cell][lane] (coalesced while lanes run in step).
+// A region whose retry needs a wider band is handed to regs_cigar_wide (warp-cooperative rows).
+struct NarrowParams {
+    const uint8_t* seqs; const uint64_t* offs; const RegRec* regs; RowDev* rows;
+    const uint64_t* jobs; const uint32_t* n_jobs; uint64_t* wide_jobs; uint32_t* wide_cnt;
+    uint32_t* cigar_pool; uint32_t cigar_cap; uint32_t* cigar_top;
+    uint8_t* zbuf; uint32_t* ticket; uint32_t* overflow; unsigned long long* counters;
+};
+
+__global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams P, DevIndex ix, DevOpts o) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    __shared__ int smat[25];
+    if (threadIdx.x < 25) smat[threadIdx.x] = o.mat[threadIdx.x];
+    __syncthreads();
+    const int tid = threadIdx.x, lane = tid & 31;
+    int* H = reinterpret_cast<int*>(dyn_smem) + tid;                                 // H[c * NARROW_THREADS]
+    int* E = reinterpret_cast<int*>(dyn_smem) + NARROW_NC * NARROW_THREADS + tid;
+    uint8_t* Q = dyn_smem + 2 * NARROW_NC * NARROW_THREADS * 4 + tid;               // Q[j * NARROW_THREADS]
+    const uint32_t gwarp = (blockIdx.x * NARROW_THREADS + tid) >> 5;
+    uint8_t* Z = P.zbuf + (size_t)gwarp * ((size_t)NARROW_TMAX * NARROW_NC * 32) + lane;  // Z[(i * NC + jj) * 32]
+    const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins, e_del = o.e_del, e_ins = o.e_ins;
+    const int64_t l_pac = ix.l_pac;
+    const uint32_t n_jobs = *P.n_jobs;
+    unsigned long long cells = 0, calls = 0;
+    for (;;) {
+        uint32_t t = next_ticket(P.ticket);
+        if ((uint64_t)t * 32 >= n_jobs) break;
+        const uint32_t j_id = t * 32 + lane;
+        if (j_id < n_jobs) {
+            const uint64_t job = P.jobs[j_id];
+            const uint32_t r = (uint32_t)(job >> 32), slot = (uint32_t)job;
+            const RegRec ar = P.regs[slot];
+            const int l_read = (int)(P.offs[r + 1] - P.offs[r]);
+            const int qb = ar.qb, qe = ar.qe, lq = qe - qb;
+            const int64_t rb = ar.rb, re = ar.re;
+            const int rlen = (int)(re - rb);
+            const bool rev = rb >= l_pac;
+            const bool reject = lq <= 0 || rb >= re || (rb < l_pac && re > l_pac) || rb < 0 || re > (l_pac << 1);
+            // libbwa reverses query and reference on the reverse strand; both then read pac ascending
+            const int64_t tbase = rev ? (l_pac << 1) - re : rb;
+            {
+                const uint8_t* qg = P.seqs + P.offs[r] + qb;
+                for (int j = 0; j < lq; ++j) Q[j * NARROW_THREADS] = rev ? qg[lq - 1 - j] : qg[j];
+            }
+            uint32_t cg[NARROW_CIG];
+            int n_cigar = 0, NM = -1, score = 0, last_sc = -(1 << 30), it = 0;
+            int w2 = reg2aln_w2(o, ar);
+            bool go_wide = false;
             do {
                 w2 = w2 < o.w << 2 ? w2 : o.w << 2;
-                g = gen_cigar2<true>(ix, o, smat, w2, qe - qb, S.query + qb, rb, re, S, rseq_cap, P.z_cap, cig_cap - 2, P.overflow, cells, calls);
-                if (g.ok) score = g.score;
+                n_cigar = 0; NM = -1;
+                if (!reject) {
+                    if (lq == rlen && w2 == 0) {
+                        int sc = 0;
+                        for (int i = 0; i < lq; ++i) {
+                            const int tb = rev ? 3 - (int)pac_get(ix.pac, tbase + i) : (int)pac_get(ix.pac, tbase + i);
+                            sc += smat[tb * 5 + Q[i * NARROW_THREADS]];
+                        }
+                        score = sc; cg[0] = (uint32_t)lq << 4; n_cigar = 1;
+                    } else {
+                        const int w = gen_cigar_band(o, lq, rlen, w2);
+                        const int n_col = lq < 2 * w + 1 ? lq : 2 * w + 1;
+                        if (2 * w + 1 > NARROW_NC || rlen > NARROW_TMAX) { go_wide = true; break; }
+                        ++calls;
+                        // first row of the band
+                        H[0] = 0; E[0] = KSW_NEG_INF;
+                        for (int j = 1; j <= lq && j <= w; ++j) { H[(j & (NARROW_NC - 1)) * NARROW_THREADS] = -(o.o_ins + e_ins * j); E[(j & (NARROW_NC - 1)) * NARROW_THREADS] = KSW_NEG_INF; }
+                        if (w + 1 <= lq) { H[((w + 1) & (NARROW_NC - 1)) * NARROW_THREADS] = KSW_NEG_INF; E[((w + 1) & (NARROW_NC - 1)) * NARROW_THREADS] = KSW_NEG_INF; }
+                        for (int i = 0; i < rlen; ++i) {
+                            const int beg = i > w ? i - w : 0;
+                            const int end = i + w + 1 < lq ? i + w + 1 : lq;
+                            int h1 = beg == 0 ? -(o.o_del + e_del * (i + 1)) : KSW_NEG_INF;
+                            int f = KSW_NEG_INF;
+                            const int tb = rev ? 3 - (int)pac_get(ix.pac, tbase + i) : (int)pac_get(ix.pac, tbase + i);
+                            const int* mrow = smat + tb * 5;
+                            uint8_t* zi = Z + (size_t)i * NARROW_NC * 32;
+                            cells += (unsigned long long)(end - beg);
+                            for (int j = beg; j < end; ++j) {
+                                const int c = (j & (NARROW_NC - 1)) * NARROW_THREADS;
+                                int m = H[c], e = E[c];
+                                H[c] = h1;
+                                m += mrow[Q[j * NARROW_THREADS]];
+                                int d = m >= e ? 0 : 1;
+                                int h = m >= e ? m : e;
+                                d = h >= f ? d : 2;
+                                h = h >= f ? h : f;
+                                h1 = h;
+                                int tt = m - oe_del;
+                                e -= e_del;
+                                d |= e > tt ? 1 << 2 : 0;
+                                e = e > tt ? e : tt;
+                                E[c] = e;
+                                tt = m - oe_ins;
+                                f -= e_ins;
+                                d |= f > tt ? 2 << 4 : 0;
+                                f = f > tt ? f : tt;
+                                zi[(j - beg) * 32] = (uint8_t)d;
+                            }
+                            const int ce = (end & (NARROW_NC - 1)) * NARROW_THREADS;
+                            H[ce] = h1; E[ce] = KSW_NEG_INF;
+                        }
+                        score = H[(lq & (NARROW_NC - 1)) * NARROW_THREADS];
+                        // traceback
+                        {
+                            int which = 0, i = rlen - 1, k = (i + w + 1 < lq ? i + w + 1 : lq) - 1;
+                            bool full = false;
+                            auto push = [&](uint32_t op, uint32_t len) {
+                                if (n_cigar == 0 || op != (cg[n_cigar - 1] & 0xf)) { if (n_cigar < NARROW_CIG) cg[n_cigar++] = len << 4 | op; else full = true; }
+                                else cg[n_cigar - 1] += len << 4;
+                            };
+                            while (i >= 0 && k >= 0) {
+                                which = Z[((size_t)i * NARROW_NC + (k - (i > w ? i - w : 0))) * 32] >> (which << 1) & 3;
+                                if (which == 0) { push(0, 1); --i; --k; }
+                                else if (which == 1) { push(2, 1); --i; }
+                                else { push(1, 1); --k; }
+                            }
+                            if (i >= 0) push(2, (uint32_t)(i + 1));
+                            if (k >= 0) push(1, (uint32_t)(k + 1));
+                            if (full) { go_wide = true; break; }
+                            for (int a = 0; a < n_cigar >> 1; ++a) { uint32_t x = cg[a]; cg[a] = cg[n_cigar - 1 - a]; cg[n_cigar - 1 - a] = x; }
+                        }
+                        (void)n_col;
+                    }
+                    // NM
+                    int x = 0, y = 0, n_mm = 0, n_gap = 0;
+                    for (int k = 0; k < n_cigar; ++k) {
+                        const int op = (int)(cg[k] & 0xf), len = (int)(cg[k] >> 4);
+                        if (op == 0) {
+                            for (int i = 0; i < len; ++i) {
+                                const int tb = rev ? 3 - (int)pac_get(ix.pac, tbase + y + i) : (int)pac_get(ix.pac, tbase + y + i);
+                                n_mm += (int)Q[(x + i) * NARROW_THREADS] != tb;
+                            }
+                            x += len; y += len;
+                        } else if (op == 2) { if (k > 0 && k < n_cigar - 1) n_gap += len; y += len; }
+                        else if (op == 1) { x += len; n_gap += len; }
+                    }
+                    NM = n_mm + n_gap;
+                }
                 if (score == last_sc || w2 == o.w << 2) break;
                 last_sc = score;
                 w2 <<= 1;
             } while (++it < 3 && score < ar.truesc - o.a);
-            row.NM = g.NM;
-            int is_rev;
-            int64_t pos = bns_depos(ix, rb < ix.l_pac ? rb : re - 1, &is_rev);
-            row.is_rev = is_rev;
-            // squeeze out a leading or trailing deletion, add soft clips, publish the CIGAR
-            int n_cigar = g.n_cigar, first = 0;
-            if (n_cigar > 0) {
-                if ((S.cig[0] & 0xf) == 2) { pos += S.cig[0] >> 4; first = 1; --n_cigar; }
-                else if ((S.cig[g.n_cigar - 1] & 0xf) == 2) --n_cigar;
-            }
-            int clip5 = 0, clip3 = 0;
-            if (qb != 0 || qe != l_query) { clip5 = is_rev ? l_query - qe : qb; clip3 = is_rev ? qb : l_query - qe; }
-            const int n_out = n_cigar + (clip5 ? 1 : 0) + (clip3 ? 1 : 0);
-            uint32_t coff = 0;
-            if (lane == 0 && n_out) coff = atomicAdd(P.cigar_top, (uint32_t)n_out);
-            coff = __shfl_sync(FULL, coff, 0);
-            if ((uint64_t)coff + (uint64_t)n_out > (uint64_t)P.cigar_cap) { if (lane == 0) atomicExch(P.overflow, 1u); row.cigar_off = 0; row.n_cigar = 0; }
-            else {
-                row.cigar_off = coff; row.n_cigar = (uint32_t)n_out;
-                if (lane == 0) {
+            if (go_wide) {
+                uint32_t k = atomicAdd(P.wide_cnt, 1u);
+                P.wide_jobs[k] = job;
+            } else {
+                int is_rev;
+                int64_t pos = bns_depos(ix, rb < l_pac ? rb : re - 1, &is_rev);
+                int nc = n_cigar, first = 0;
+                if (nc > 0) {
+                    if ((cg[0] & 0xf) == 2) { pos += cg[0] >> 4; first = 1; --nc; }
+                    else if ((cg[n_cigar - 1] & 0xf) == 2) --nc;
+                }
+                int clip5 = 0, clip3 = 0;
+                if (qb != 0 || qe != l_read) { clip5 = is_rev ? l_read - qe : qb; clip3 = is_rev ? qb : l_read - qe; }
+                const int n_out = nc + (clip5 ? 1 : 0) + (clip3 ? 1 : 0);
+                uint32_t coff = n_out ? atomicAdd(P.cigar_top, (uint32_t)n_out) : 0u;
+                RowDev* out = P.rows + slot;
+                if ((uint64_t)coff + (uint64_t)n_out > (uint64_t)P.cigar_cap) { atomicExch(P.overflow, 1u); }
+                else {
                     uint32_t* dst = P.cigar_pool + coff;
                     int k = 0;
                     if (clip5) dst[k++] = (uint32_t)clip5 << 4 | 3;
-                    for (int c = 0; c < n_cigar; ++c) dst[k++] = S.cig[first + c];
+                    for (int c = 0; c < nc; ++c) dst[k++] = cg[first + c];
                     if (clip3) dst[k++] = (uint32_t)clip3 << 4 | 3;
+                    out->cigar_off = coff; out->n_cigar = (uint32_t)n_out;
                 }
+                const int rid = bns_pos2rid(ix, pos);
+                out->NM = NM; out->is_rev = is_rev; out->pos = pos - ix.ann_offset[rid < 0 ? 0 : rid];
             }
-            const int rid = bns_pos2rid(ix, pos);
-            row.pos = pos - ix.ann_offset[rid < 0 ? 0 : rid];
-            row.ref_id = P.ann_id[ar.rid];
-            if (lane == 0) rows[i] = row;
-            __syncwarp();
         }
-        if (lane == 0) P.row_cnt[r] = (uint32_t)n;
+        __syncwarp();
+    }
+    if (P.counters) {
+        cells = __reduce_add_sync(FULL, (unsigned)(cells & 0xffffffffu)) + ((unsigned long long)__reduce_add_sync(FULL, (unsigned)(cells >> 32)) << 32);
+        calls = __reduce_add_sync(FULL, (unsigned)calls);
+        if (lane == 0) { atomicAdd(&P.counters[0], cells); atomicAdd(&P.counters[1], calls); }
+    }
+}
+
+// regions handed over by the narrow kernel: warp-cooperative mem_reg2aln, one warp per job
+template <bool SMEM>
+__global__ void __launch_bounds__(FIN_THREADS) regs_cigar_wide(FinalizeParams P, DevIndex ix, DevOpts o, uint32_t cig_cap, uint32_t rseq_cap) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    __shared__ int smat[25];
+    if (threadIdx.x < 25) smat[threadIdx.x] = o.mat[threadIdx.x];
+    __syncthreads();
+    const int lane = lane_id();
+    const uint32_t gwarp = (blockIdx.x * FIN_THREADS + threadIdx.x) >> 5;
+    FScratch S;
+    {
+        const size_t fast = ((size_t)(P.max_len + 2) * 8 + rseq_cap + P.max_len + 15) & ~(size_t)15;
+        uint8_t* gbase = P.scratch + (size_t)gwarp * P.scratch_per_warp;
+        uint8_t* fbase = SMEM ? dyn_smem + (size_t)(threadIdx.x >> 5) * fast : gbase;
+        S.ehh = reinterpret_cast<int*>(fbase);
+        S.ehe = S.ehh + (P.max_len + 2);
+        S.rseq = reinterpret_cast<uint8_t*>(S.ehe + (P.max_len + 2));
+        S.query = S.rseq + rseq_cap;
+        S.cig = reinterpret_cast<uint32_t*>(gbase + fast);
+        S.z = reinterpret_cast<uint8_t*>(S.cig + cig_cap);
+    }
+    unsigned long long cells = 0, calls = 0;
+    const uint32_t n_jobs = *P.wide_cnt;
+    for (;;) {
+        uint32_t t = next_ticket(P.ticket);
+        if (t >= n_jobs) break;
+        const uint64_t job = P.wide_jobs[t];
+        const uint32_t r = (uint32_t)(job >> 32), slot = (uint32_t)job;
+        const int l_query = (int)(P.offs[r + 1] - P.offs[r]);
+        const uint8_t* qg = P.seqs + P.offs[r];
+        for (int i = lane; i < l_query; i += 32) S.query[i] = qg[i];
+        __syncwarp();
+        const RegRec ar = P.regs[slot];
+        reg2aln_warp(P, ix, o, smat, S, cig_cap, rseq_cap, l_query, ar, P.rows + slot, cells, calls);
     }
     if (P.counters && lane == 0) { atomicAdd(&P.counters[0], cells); atomicAdd(&P.counters[1], calls); }
 }
@@ -370,14 +647,49 @@ int finalize_resident_warps() {
     return nb * sms * FIN_WARPS;
 }
 
-void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint32_t rseq_cap, int n_warps) {
+size_t narrow_zbuf_bytes(int* n_warps_out) {
+    int nb = 0, dev = 0, sms = 148;
+    const size_t smem = (size_t)NARROW_THREADS * (2 * NARROW_NC * 4 + NARROW_QMAX);
+    cudaFuncSetAttribute(regs_cigar_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, regs_cigar_narrow, NARROW_THREADS, smem);
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (nb < 1) nb = 1;
+    const int warps = nb * sms * (NARROW_THREADS / 32);
+    if (n_warps_out) *n_warps_out = warps;
+    return (size_t)warps * NARROW_TMAX * NARROW_NC * 32;
+}
+
+void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint32_t rseq_cap, int n_warps, uint64_t* launches) {
     const uint32_t cig_cap = fin_cig_cap(p.max_len, rseq_cap);
     int blocks = n_warps / FIN_WARPS;
     if (blocks < 1) blocks = 1;
-    if (fin_use_smem(p.max_len, rseq_cap)) {
-        size_t smem = fin_fast_bytes(p.max_len, rseq_cap) * FIN_WARPS;
-        regs_finalize<true><<<blocks, FIN_THREADS, smem, st>>>(p, ix, o, cig_cap, rseq_cap);
-    } else {
-        regs_finalize<false><<<blocks, FIN_THREADS, 0, st>>>(p, ix, o, cig_cap, rseq_cap);
+    const bool smem_ok = fin_use_smem(p.max_len, rseq_cap);
+    const size_t smem = smem_ok ? fin_fast_bytes(p.max_len, rseq_cap) * FIN_WARPS : 0;
+    // phase 1: dedup / patch / primary marking; wide regions aligned inline, narrow ones queued
+    if (smem_ok) regs_finalize<true><<<blocks, FIN_THREADS, smem, st>>>(p, ix, o, cig_cap, rseq_cap);
+    else regs_finalize<false><<<blocks, FIN_THREADS, 0, st>>>(p, ix, o, cig_cap, rseq_cap);
+    if (launches) ++*launches;
+    if (!p.narrow_jobs) return;
+    // phase 2: thread-per-region narrow-band mem_reg2aln
+    {
+        int warps = 0;
+        narrow_zbuf_bytes(&warps);
+        if (warps > p.narrow_warps) warps = p.narrow_warps;
+        NarrowParams q;
+        q.seqs = p.seqs; q.offs = p.offs; q.regs = p.regs; q.rows = p.rows; q.jobs = p.narrow_jobs; q.n_jobs = p.narrow_cnt;
+        q.wide_jobs = p.wide_jobs; q.wide_cnt = p.wide_cnt; q.cigar_pool = p.cigar_pool; q.cigar_cap = p.cigar_cap; q.cigar_top = p.cigar_top;
+        q.zbuf = p.narrow_z; q.ticket = p.ticket + 1; q.overflow = p.overflow; q.counters = p.counters;
+        const size_t nsmem = (size_t)NARROW_THREADS * (2 * NARROW_NC * 4 + NARROW_QMAX);
+        regs_cigar_narrow<<<warps / (NARROW_THREADS / 32), NARROW_THREADS, nsmem, st>>>(q, ix, o);
+        if (launches) ++*launches;
+    }
+    // phase 3: whatever needed a wider band on a retry
+    {
+        FinalizeParams w = p;
+        w.ticket = p.ticket + 2;
+        if (smem_ok) regs_cigar_wide<true><<<blocks, FIN_THREADS, smem, st>>>(w, ix, o, cig_cap, rseq_cap);
+        else regs_cigar_wide<false><<<blocks, FIN_THREADS, 0, st>>>(w, ix, o, cig_cap, rseq_cap);
+        if (launches) ++*launches;
     }
 }

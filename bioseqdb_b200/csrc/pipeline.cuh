@@ -60,9 +60,14 @@ struct FinalizeParams {
     uint32_t* cigar_pool; uint32_t cigar_cap; uint32_t* cigar_top;
     uint8_t* scratch; size_t scratch_per_warp; uint32_t max_len, z_cap;
     const int64_t* ann_id;
-    uint32_t* ticket; uint32_t* overflow;
+    // narrow-band regions are queued (read << 32 | row slot) for the thread-per-region kernel; regions that
+    // need a wider band on a retry come back through wide_jobs.  narrow_jobs == nullptr disables the split.
+    uint64_t* narrow_jobs; uint32_t* narrow_cnt; uint64_t* wide_jobs; uint32_t* wide_cnt; uint8_t* narrow_z; int narrow_warps;
+    uint32_t* ticket;              // three consecutive tickets: finalize, narrow, wide
+    uint32_t* overflow;
     unsigned long long* counters;  // optional: [0] = ksw_global2 cells, [1] = calls
 };
-void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint32_t rseq_cap, int n_warps);
+void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint32_t rseq_cap, int n_warps, uint64_t* launches);
+size_t narrow_zbuf_bytes(int* n_warps_out);
 size_t finalize_scratch_per_warp(uint32_t max_len, uint32_t rseq_cap, uint32_t* z_cap_out);
 int finalize_resident_warps();

@@ -17,62 +17,50 @@ namespace {
 constexpr int SEED_THREADS = 256;
 constexpr int SEED_WARPS = SEED_THREADS / 32;
 
-struct Iv32 { uint32_t x0, x1, x2, info; };   // info = end (forward list) ; start<<16|end packing is NOT used: lists keep end only
+struct __align__(16) Iv32 { uint32_t x0, x1, x2, info; };   // info = end of the match on the query
 
-__device__ __forceinline__ uint32_t occ_word(const DevIndex& ix, uint32_t pos_k, uint32_t pos_l, uint32_t& pos_adj) {
-    const int lane = lane_id();
-    uint32_t pos = (lane & 16) ? pos_l : pos_k;
-    pos -= (pos >= (uint32_t)ix.primary);
-    pos_adj = pos;
-    return __ldg(ix.occ + ((size_t)(pos >> 7) << 4) + (lane & 15));
-}
+// warp-private context of the narrow path: everything the extend needs without touching the kernel
+// parameter block dynamically (a dynamically indexed parameter array is spilled to local memory)
+struct Ctx32 {
+    const uint32_t* occ;
+    const uint32_t* sL2;     // shared memory: L2[0..4] as u32
+    uint32_t primary;
+    // per-lane constants
+    uint32_t sym_base;       // first symbol covered by this lane's word (symbol lanes), 1 << 20 for count lanes
+    int cnt_sym;             // symbol whose checkpoint low word this lane holds, -1 otherwise
+    bool lhalf;              // lanes 16-31 read the block of row l
+};
 
-// child interval for base c of the parent (xo = x[!is_back], xb = x[is_back], x2): see file header
-__device__ __forceinline__ void occ_reduce(const DevIndex& ix, uint32_t word, uint32_t pos, int c, uint32_t xo, uint32_t xb, uint32_t x2,
-                                           uint32_t& no, uint32_t& nb, uint32_t& nsz) {
-    const int lane = lane_id();
-    const int idx = lane & 15;
-    int eq, gt;
-    if (idx < 8) {
-        const bool low = !(idx & 1);
-        const int cc = idx >> 1;
-        eq = (low && cc == c) ? (int)word : 0;
-        gt = (low && cc > c) ? (int)word : 0;
-    } else {
-        int nsym = (int)(pos & 127) + 1 - ((idx - 8) << 4);
-        nsym = nsym < 0 ? 0 : (nsym > 16 ? 16 : nsym);
-        const uint32_t keep = nsym ? (0x55555555u & (0xffffffffu << (32 - 2 * nsym))) : 0u;
-        const uint32_t lo = word & keep, hi = (word >> 1) & keep;      // keep is on the 0x5555 lattice
-        const uint32_t nlo = ~word & keep, nhi = ~(word >> 1) & keep;
-        const uint32_t mh = (c & 2) ? hi : nhi, ml = (c & 1) ? lo : nlo;
-        eq = __popc(mh & ml);
-        const uint32_t g = c == 0 ? (hi | lo) : (c == 1 ? hi : (c == 2 ? (hi & lo) : 0u));
-        gt = __popc(g);
-    }
-    const bool lhalf = (lane & 16) != 0;
-    const int sz = __reduce_add_sync(FULL, lhalf ? eq : -eq);
-    const int S = __reduce_add_sync(FULL, lhalf ? gt : -gt);
-    const int tk = __reduce_add_sync(FULL, lhalf ? 0 : eq);
-    no = (uint32_t)ix.L2[c] + 1u + (uint32_t)tk;
-    nsz = (uint32_t)sz;
-    nb = xb + (uint32_t)(xo <= (uint32_t)ix.primary && xo + x2 - 1 >= (uint32_t)ix.primary) + (uint32_t)S;
-}
-
+// child interval of `ik` for base c (see file header).  IS_BACK selects which of x0/x1 plays "k".
 template <int IS_BACK>
-__device__ __forceinline__ Iv32 extend32(const DevIndex& ix, const Iv32& ik, int c) {
+__device__ __forceinline__ Iv32 extend32(const Ctx32& C, const Iv32& ik, int c) {
     const uint32_t xo = IS_BACK ? ik.x0 : ik.x1, xb = IS_BACK ? ik.x1 : ik.x0;
-    uint32_t pos;
-    const uint32_t word = occ_word(ix, xo - 1, xo - 1 + ik.x2, pos);
-    uint32_t no, nb, nsz;
-    occ_reduce(ix, word, pos, c, xo, xb, ik.x2, no, nb, nsz);
+    uint32_t pos = xo - 1 + (C.lhalf ? ik.x2 : 0u);
+    pos -= (pos >= C.primary);
+    const uint32_t word = __ldg(C.occ + ((size_t)(pos >> 7) << 4) + (lane_id() & 15));
+    // symbol lanes: count symbols == c and > c among the first nsym symbols of the word (branch-free)
+    int nsym = (int)(pos & 127) + 1 - (int)C.sym_base;
+    nsym = nsym < 0 ? 0 : (nsym > 16 ? 16 : nsym);
+    const uint32_t keep = __funnelshift_rc(0u, 0x55555555u, 2 * nsym);   // low bit of each of the top nsym symbols
+    const uint32_t C1 = 0u - (uint32_t)(c >> 1), C0 = 0u - (uint32_t)(c & 1);
+    const uint32_t hx = ~((word >> 1) ^ C1);          // hi bit equals c's hi bit
+    const uint32_t eqm = hx & ~(word ^ C0) & keep;
+    const uint32_t gtm = (((word >> 1) & ~C1) | (hx & word & ~C0)) & keep;
+    int eq = __popc(eqm), gt = __popc(gtm);
+    if (C.cnt_sym >= 0) { eq = C.cnt_sym == c ? (int)word : 0; gt = C.cnt_sym > c ? (int)word : 0; }
+    const int sz = __reduce_add_sync(FULL, C.lhalf ? eq : -eq);
+    const int S = __reduce_add_sync(FULL, C.lhalf ? gt : -gt);
+    const int tk = __reduce_add_sync(FULL, C.lhalf ? 0 : eq);
+    const uint32_t no = C.sL2[c] + 1u + (uint32_t)tk;
+    const uint32_t nb = xb + (uint32_t)(xo <= C.primary && xo + ik.x2 - 1 >= C.primary) + (uint32_t)S;
     Iv32 ok;
-    ok.x0 = IS_BACK ? no : nb; ok.x1 = IS_BACK ? nb : no; ok.x2 = nsz; ok.info = ik.info;
+    ok.x0 = IS_BACK ? no : nb; ok.x1 = IS_BACK ? nb : no; ok.x2 = (uint32_t)sz; ok.info = ik.info;
     return ok;
 }
 
-__device__ __forceinline__ Iv32 set_intv32(const DevIndex& ix, int c) {
+__device__ __forceinline__ Iv32 set_intv32(const Ctx32& C, int c) {
     Iv32 ik;
-    ik.x0 = (uint32_t)ix.L2[c] + 1; ik.x1 = (uint32_t)ix.L2[3 - c] + 1; ik.x2 = (uint32_t)(ix.L2[c + 1] - ix.L2[c]); ik.info = 0;
+    ik.x0 = C.sL2[c] + 1; ik.x1 = C.sL2[3 - c] + 1; ik.x2 = C.sL2[c + 1] - C.sL2[c]; ik.info = 0;
     return ik;
 }
 
@@ -85,13 +73,13 @@ __device__ __forceinline__ void emit(Out& O, const Iv32& p, uint32_t start, uint
     ++O.n;
 }
 
-// bwt_smem1a with max_intv == 0.  la/lb: two interval lists of list_cap entries (shared memory).
-__device__ int smem1_32(const DevIndex& ix, const DevOpts& o, int len, const uint8_t* q, int x, uint32_t min_intv, Iv32* la, Iv32* lb,
-                        uint32_t list_cap, Out& O, unsigned long long& n_ext) {
+// bwt_smem1a with max_intv == 0.  la/lb: two interval lists of list_cap entries; q: the read (nt4).
+__device__ __forceinline__ int smem1_32(const Ctx32& C, const DevOpts& o, int len, const uint8_t* q, int x, uint32_t min_intv, Iv32* la, Iv32* lb,
+                                        uint32_t list_cap, Out& O, unsigned long long& n_ext) {
     if (q[x] > 3) return x + 1;
     if (min_intv < 1) min_intv = 1;
     const int lane = lane_id();
-    Iv32 ik = set_intv32(ix, q[x]);
+    Iv32 ik = set_intv32(C, q[x]);
     ik.info = (uint32_t)(x + 1);
     Iv32* curr = la; Iv32* prev = lb;
     uint32_t n_curr = 0;
@@ -99,7 +87,7 @@ __device__ int smem1_32(const DevIndex& ix, const DevOpts& o, int len, const uin
     for (i = x + 1; i < len; ++i) {
         const int b = q[i];
         if (b < 4) {
-            Iv32 ok = extend32<0>(ix, ik, 3 - b); ++n_ext;
+            Iv32 ok = extend32<0>(C, ik, 3 - b); ++n_ext;
             if (ok.x2 != ik.x2) {
                 if (n_curr < list_cap) { if (lane == 0) curr[n_curr] = ik; } else O.ovf = true;
                 ++n_curr;
@@ -127,7 +115,7 @@ __device__ int smem1_32(const DevIndex& ix, const DevOpts& o, int len, const uin
         for (uint32_t j = 0; j < n_prev; ++j) {
             const Iv32 p = prev[reversed ? n_prev - 1 - j : j];
             Iv32 ok; ok.x2 = 0;
-            if (c >= 0) { ok = extend32<1>(ix, p, c); ++n_ext; }
+            if (c >= 0) { ok = extend32<1>(C, p, c); ++n_ext; }
             if (c < 0 || ok.x2 < min_intv) {
                 if (n_curr == 0) {
                     if (!have_mem || (uint32_t)(i + 1) < last_mem_start) {
@@ -162,13 +150,13 @@ __device__ int smem1_32(const DevIndex& ix, const DevOpts& o, int len, const uin
     return ret;
 }
 
-__device__ int seed_strategy1_32(const DevIndex& ix, int len, const uint8_t* q, int x, int min_len, uint32_t max_intv, Out& O, unsigned long long& n_ext) {
+__device__ __forceinline__ int seed_strategy1_32(const Ctx32& C, int len, const uint8_t* q, int x, int min_len, uint32_t max_intv, Out& O, unsigned long long& n_ext) {
     if (q[x] > 3) return x + 1;
-    Iv32 ik = set_intv32(ix, q[x]);
+    Iv32 ik = set_intv32(C, q[x]);
     for (int i = x + 1; i < len; ++i) {
         const int b = q[i];
         if (b < 4) {
-            Iv32 ok = extend32<0>(ix, ik, 3 - b); ++n_ext;
+            Iv32 ok = extend32<0>(C, ik, 3 - b); ++n_ext;
             if (ok.x2 < max_intv && i - x >= min_len) {
                 if (ok.x2 > 0) emit(O, ok, (uint32_t)x, (uint32_t)(i + 1));
                 return i + 1;
@@ -177,6 +165,30 @@ __device__ int seed_strategy1_32(const DevIndex& ix, int len, const uint8_t* q, 
         } else return i + 1;
     }
     return len;
+}
+
+// the three passes of mem_collect_intv for one read on the narrow path
+__device__ __forceinline__ void collect_intv_32(const Ctx32& C, const DevOpts& o, int len, const uint8_t* q, Iv32* la, Iv32* lb, uint32_t list_cap,
+                                                Out& O, unsigned long long& n_ext) {
+    int x = 0;
+    while (x < len) {      // pass 1: all SMEMs
+        if (q[x] < 4) x = smem1_32(C, o, len, q, x, 1, la, lb, list_cap, O, n_ext);
+        else ++x;
+    }
+    const uint32_t old_n = O.n < O.cap ? O.n : O.cap;
+    for (uint32_t k = 0; k < old_n; ++k) {   // pass 2: re-seeding inside long, rare SMEMs
+        const Intv p = O.out[k];
+        const int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
+        if (end - start < o.split_len || p.x2 > (uint64_t)o.split_width) continue;
+        smem1_32(C, o, len, q, (start + end) >> 1, (uint32_t)p.x2 + 1, la, lb, list_cap, O, n_ext);
+    }
+    if (o.max_mem_intv > 0) {                // pass 3: LAST-like
+        x = 0;
+        while (x < len) {
+            if (q[x] < 4) x = seed_strategy1_32(C, len, q, x, o.min_seed_len, (uint32_t)o.max_mem_intv, O, n_ext);
+            else ++x;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- wide path (>= 2^32 rows): 64-bit records
@@ -313,18 +325,32 @@ __device__ void sort_by_info(Intv* out, uint32_t n_out, Intv* tmp, uint32_t tmp_
     __syncwarp();
 }
 
-template <bool WIDE>
+// MODE 0: narrow path, lists and the read staged in shared memory; 1: narrow path, lists in global scratch
+// (reads too long for shared memory); 2: wide path (>= 2^32 rows)
+template <int MODE>
 __global__ void __launch_bounds__(SEED_THREADS) seed_smem(SeedParams P, DevIndex ix, DevOpts o) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
+    __shared__ uint32_t sL2[8];
+    if (threadIdx.x < 5) sL2[threadIdx.x] = (uint32_t)ix.L2[threadIdx.x];
+    __syncthreads();
     const int lane = lane_id();
     const uint32_t gwarp = (blockIdx.x * SEED_THREADS + threadIdx.x) >> 5;
     Intv* gl = P.scratch + (size_t)gwarp * 3 * P.list_cap;     // global scratch: wide-path lists, big-sort buffer
     unsigned long long n_ext = 0;
-    Iv32* la = nullptr; Iv32* lb = nullptr;
-    if (!WIDE) {
-        if (P.lists_in_smem) { la = reinterpret_cast<Iv32*>(dyn_smem) + (size_t)(threadIdx.x >> 5) * 2 * P.list_cap; lb = la + P.list_cap; }
-        else { la = reinterpret_cast<Iv32*>(gl); lb = la + P.list_cap; }
+    Ctx32 C;
+    C.occ = ix.occ; C.sL2 = sL2; C.primary = (uint32_t)ix.primary;
+    {
+        const int idx = lane & 15;
+        C.sym_base = idx >= 8 ? (uint32_t)((idx - 8) << 4) : (1u << 20);
+        C.cnt_sym = (idx < 8 && !(idx & 1)) ? (idx >> 1) : -1;
+        C.lhalf = (lane & 16) != 0;
+        // lanes holding the high half of a checkpoint act as symbol lanes with zero symbols: they contribute 0
     }
+    Iv32* la = nullptr; Iv32* lb = nullptr; uint8_t* sq = nullptr;
+    if (MODE == 0) {
+        la = reinterpret_cast<Iv32*>(dyn_smem) + (size_t)(threadIdx.x >> 5) * 2 * P.list_cap; lb = la + P.list_cap;
+        sq = dyn_smem + (size_t)SEED_WARPS * 2 * P.list_cap * sizeof(Iv32) + (size_t)(threadIdx.x >> 5) * P.read_cap;
+    } else if (MODE == 1) { la = reinterpret_cast<Iv32*>(gl); lb = la + P.list_cap; }
     for (;;) {
         uint32_t r = next_ticket(P.ticket);
         if (r >= P.n_reads) break;
@@ -333,27 +359,14 @@ __global__ void __launch_bounds__(SEED_THREADS) seed_smem(SeedParams P, DevIndex
         Intv* out = P.out + (size_t)r * P.cap;
         uint32_t n_out = 0; bool ovf = false;
         if (len >= o.min_seed_len) {   // mem_chain returns before seeding otherwise
-            if (!WIDE) {
+            if (MODE != 2) {
                 Out O; O.out = out; O.n = 0; O.cap = P.cap; O.ovf = false;
-                int x = 0;
-                while (x < len) {      // pass 1: all SMEMs
-                    if (q[x] < 4) x = smem1_32(ix, o, len, q, x, 1, la, lb, P.list_cap, O, n_ext);
-                    else ++x;
-                }
-                const uint32_t old_n = O.n < O.cap ? O.n : O.cap;
-                for (uint32_t k = 0; k < old_n; ++k) {   // pass 2: re-seeding inside long, rare SMEMs
-                    const Intv p = out[k];
-                    const int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
-                    if (end - start < o.split_len || p.x2 > (uint64_t)o.split_width) continue;
-                    smem1_32(ix, o, len, q, (start + end) >> 1, (uint32_t)p.x2 + 1, la, lb, P.list_cap, O, n_ext);
-                }
-                if (o.max_mem_intv > 0) {                // pass 3: LAST-like
-                    x = 0;
-                    while (x < len) {
-                        if (q[x] < 4) x = seed_strategy1_32(ix, len, q, x, o.min_seed_len, (uint32_t)o.max_mem_intv, O, n_ext);
-                        else ++x;
-                    }
-                }
+                if (MODE == 0) {
+                    __syncwarp();
+                    for (int i = lane; i < len; i += 32) sq[i] = q[i];
+                    __syncwarp();
+                    collect_intv_32(C, o, len, sq, la, lb, P.list_cap, O, n_ext);
+                } else collect_intv_32(C, o, len, q, la, lb, P.list_cap, O, n_ext);
                 n_out = O.n; ovf = O.ovf;
             } else {
                 WarpLists L; L.a = gl; L.b = gl + P.list_cap; L.m = L.b + P.list_cap;
@@ -391,7 +404,9 @@ __global__ void __launch_bounds__(SEED_THREADS) seed_smem(SeedParams P, DevIndex
 
 }  // namespace
 
-static size_t seed_smem_bytes(const SeedParams& p) { return p.lists_in_smem ? (size_t)SEED_WARPS * 2 * p.list_cap * sizeof(Iv32) : 0; }
+static size_t seed_smem_bytes(const SeedParams& p) {
+    return p.lists_in_smem ? (size_t)SEED_WARPS * (2 * p.list_cap * sizeof(Iv32) + p.read_cap) : 0;
+}
 
 int seed_resident_warps() {
     // upper bound used to size the per-warp global scratch: 64 warps per SM
@@ -401,19 +416,24 @@ int seed_resident_warps() {
     return 64 * sms;
 }
 
-bool seed_lists_fit_smem(uint32_t list_cap) { return (size_t)SEED_WARPS * 2 * list_cap * sizeof(Iv32) <= 48 * 1024; }
+bool seed_lists_fit_smem(uint32_t list_cap, uint32_t read_cap) {
+    return (size_t)SEED_WARPS * (2 * list_cap * sizeof(Iv32) + read_cap) <= 48 * 1024;
+}
 
-void launch_seed(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, int* n_warps_out) {
+template <int MODE> static void launch_mode(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, size_t smem, int* n_warps_out) {
     int dev = 0, sms = 148, nb = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const bool wide = ix.seq_len + 1 >= 0xffffffffull;
-    const size_t smem = wide ? 0 : seed_smem_bytes(p);
-    if (wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seed_smem<true>, SEED_THREADS, smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seed_smem<false>, SEED_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seed_smem<MODE>, SEED_THREADS, smem);
     if (nb < 1) nb = 1;
     if (nb * SEED_WARPS > 64) nb = 64 / SEED_WARPS;
     if (n_warps_out) *n_warps_out = nb * sms * SEED_WARPS;
-    if (wide) seed_smem<true><<<nb * sms, SEED_THREADS, smem, st>>>(p, ix, o);
-    else seed_smem<false><<<nb * sms, SEED_THREADS, smem, st>>>(p, ix, o);
+    seed_smem<MODE><<<nb * sms, SEED_THREADS, smem, st>>>(p, ix, o);
+}
+
+void launch_seed(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, int* n_warps_out) {
+    const bool wide = ix.seq_len + 1 >= 0xffffffffull;
+    if (wide) launch_mode<2>(p, ix, o, st, 0, n_warps_out);
+    else if (p.lists_in_smem) launch_mode<0>(p, ix, o, st, seed_smem_bytes(p), n_warps_out);
+    else launch_mode<1>(p, ix, o, st, 0, n_warps_out);
 }

@@ -71,11 +71,12 @@ struct SeedParams {
     uint32_t cap;
     Intv* scratch;            // per resident warp: 3 lists of list_cap entries
     uint32_t list_cap;
-    int lists_in_smem;        // narrow path: the two interval lists of a warp live in shared memory
+    int lists_in_smem;        // narrow path: the two interval lists of a warp and the read live in shared memory
+    uint32_t read_cap;        // bytes reserved per warp for the staged read (>= longest read, multiple of 16)
     uint32_t* ticket;
     uint32_t* overflow;       // set to 1 when a read needs more than cap intervals
     unsigned long long* n_extend;  // optional counter (roofline units); nullptr in production
 };
 void launch_seed(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, int* n_warps_out);
 int seed_resident_warps();
-bool seed_lists_fit_smem(uint32_t list_cap);
+bool seed_lists_fit_smem(uint32_t list_cap, uint32_t read_cap);

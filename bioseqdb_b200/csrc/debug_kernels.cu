@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t* __restrict__ occ
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {
             s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
-            uint64_t b = (s * 0x2545F4914F6CDD1Dull) % n_blocks;
+            uint64_t b = __umul64hi(s * 0x2545F4914F6CDD1Dull, n_blocks);   // uniform in [0, n_blocks) without a division
             v[u] = __ldg(occ + (b << 4) + idx);
         }
 #pragma unroll

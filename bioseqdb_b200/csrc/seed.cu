@@ -328,7 +328,7 @@ __device__ void sort_by_info(Intv* out, uint32_t n_out, Intv* tmp, uint32_t tmp_
 // MODE 0: narrow path, lists and the read staged in shared memory; 1: narrow path, lists in global scratch
 // (reads too long for shared memory); 2: wide path (>= 2^32 rows)
 template <int MODE>
-__global__ void __launch_bounds__(SEED_THREADS) seed_smem(SeedParams P, DevIndex ix, DevOpts o) {
+__global__ void __launch_bounds__(SEED_THREADS, MODE == 0 ? 5 : 1) seed_smem(SeedParams P, DevIndex ix, DevOpts o) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ uint32_t sL2[8];
     if (threadIdx.x < 5) sL2[threadIdx.x] = (uint32_t)ix.L2[threadIdx.x];

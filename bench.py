@@ -245,11 +245,13 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e0 = time.time()
     e2e_dev_ms = 0.0
+    e2e_h2d_ms = e2e_d2h_ms = 0.0
     h2d = d2h = 0
     for _ in range(args.steps):
         one_e2e()
         t = ix.timing()
         e2e_dev_ms += t.total
+        e2e_h2d_ms += t.h2d; e2e_d2h_ms += t.d2h
         h2d, d2h = int(t.h2d_bytes), int(t.d2h_bytes)
     barrier()
     e2e_wall = time.time() - e0
@@ -298,7 +300,8 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "config": config_dict(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms_max / args.steps, "wall_ms_per_step": 1e3 * e2e_wall_max / args.steps},
+                    "ms_per_step": e2e_ms_max / args.steps, "wall_ms_per_step": 1e3 * e2e_wall_max / args.steps,
+                    "h2d_ms_per_step": e2e_h2d_ms / args.steps, "d2h_ms_per_step": e2e_d2h_ms / args.steps},
             "gpu_launches": launches_all,
             "clocks": clocks,
             "roofline": roof, "sw": sw,

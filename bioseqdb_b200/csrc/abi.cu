@@ -8,6 +8,7 @@
 #include <cstring>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 #include "../../include/bioseqdb_gpu.h"
 #include "common.cuh"
 #include "index_build.cuh"
@@ -71,6 +72,7 @@ struct bsq_index {
     cudaStream_t stream = nullptr;
     Batch batch;
     bsq_timing timing;
+    double* d_logtab = nullptr;
     bool collect_counters = false;
     uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -187,6 +189,7 @@ void bsq_index_free(bsq_index* h) {
     cudaSetDevice(h->device);
     h->batch.release();
     free_index_arrays(h);
+    if (h->d_logtab) cudaFree(h->d_logtab);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -274,16 +277,48 @@ __global__ void k_to_nt4(uint8_t* s, uint64_t n) {
     }
 }
 
-__global__ void k_compact_rows(const ReadBlock* blocks, const RowDev* rows, const uint32_t* row_cnt, const uint32_t* row_off, uint32_t n_reads, RowDev* out) {
+// mem_approx_mapq_se on the device.  The only transcendental is log() of small integers
+// (alignment length l and sub_n + 1): both come from a table filled by the HOST libm, so every double
+// operation here is an IEEE +,-,*,/ evaluated in the reference's order (the library is compiled with
+// --fmad=false).  Rows whose l or sub_n fall outside the table get mapq = -1 and are finished on the host.
+constexpr int LOGTAB_N = 4096;
+struct MapqParams { int a, b, min_seed_len; float coef_len; double coef_fac; const double* logtab; };
+
+__device__ __forceinline__ int approx_mapq_dev(const MapqParams& M, const RowDev& r) {
+    int mapq, l, sub = r.sub ? r.sub : M.min_seed_len * M.a;
+    sub = r.csub > sub ? r.csub : sub;
+    if (sub >= r.score) return 0;
+    l = r.qe - r.qb > r.re - r.rb ? r.qe - r.qb : (int)(r.re - r.rb);
+    if (l >= LOGTAB_N || r.sub_n + 1 >= LOGTAB_N || l <= 0) return -1;
+    const double identity = 1. - (double)(l * M.a - r.score) / (M.a + M.b) / l;
+    if (r.score == 0) mapq = 0;
+    else {
+        double tmp = l < M.coef_len ? 1. : M.coef_fac / M.logtab[l];
+        tmp *= identity * identity;
+        mapq = (int)(6.02 * (r.score - sub) / M.a * tmp * tmp + .499);
+    }
+    if (r.sub_n > 0) mapq -= (int)(4.343 * M.logtab[r.sub_n + 1] + .499);
+    if (mapq > 60) mapq = 60;
+    if (mapq < 0) mapq = 0;
+    mapq = (int)(mapq * (1. - r.frac_rep) + .499);
+    return mapq;
+}
+
+__global__ void k_compact_rows(const ReadBlock* blocks, const RowDev* rows, const uint32_t* row_cnt, const uint32_t* row_off, uint32_t n_reads,
+                               RowDev* out, MapqParams M) {
     // one warp per read; a row is 120 bytes = 30 words
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     for (uint32_t r = gw; r < n_reads; r += nw) {
         uint32_t c = row_cnt[r];
         if (!c) continue;
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(rows + blocks[r].base);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(out + row_off[r]);
+        const RowDev* srow = rows + blocks[r].base;
+        RowDev* drow = out + row_off[r];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(srow);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(drow);
         for (uint32_t w = lane; w < c * 30; w += 32) dst[w] = src[w];
+        __syncwarp();
+        for (uint32_t k = lane; k < c; k += 32) drow[k].mapq = srow[k].secondary < 0 ? approx_mapq_dev(M, srow[k]) : 0;
     }
 }
 
@@ -465,37 +500,90 @@ int approx_mapq(const bsq_index* h, const bsq_row& a) {
     return mapq;
 }
 
+// A result lives in ONE pinned host block {row_off, rows, cigar}; freed blocks are cached process-wide
+// so that steady-state calls do not pay cudaHostAlloc.
+struct ResultImpl { bsq_result pub; void* block; size_t bytes; };
+struct PinnedCache { void* ptr[4]; size_t bytes[4]; };
+PinnedCache g_pinned = {{nullptr, nullptr, nullptr, nullptr}, {0, 0, 0, 0}};
+std::mutex g_pinned_mu;
+
+void* pinned_get(size_t need, size_t* got) {
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        for (int i = 0; i < 4; ++i)
+            if (g_pinned.ptr[i] && g_pinned.bytes[i] >= need && g_pinned.bytes[i] <= 2 * need + (1 << 20)) {
+                void* p = g_pinned.ptr[i]; *got = g_pinned.bytes[i]; g_pinned.ptr[i] = nullptr; g_pinned.bytes[i] = 0; return p;
+            }
+    }
+    void* p = nullptr;
+    size_t want = need + need / 8 + 4096;
+    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *got = want;
+    return p;
+}
+void pinned_put(void* p, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        for (int i = 0; i < 4; ++i) if (!g_pinned.ptr[i]) { g_pinned.ptr[i] = p; g_pinned.bytes[i] = bytes; return; }
+    }
+    cudaFreeHost(p);
+}
+
 int download_result(bsq_index* h, bsq_result** out) {
     Batch& b = h->batch;
     if (!b.aligned) { bsq_set_error("no aligned batch to download"); return BSQ_ERR; }
     const uint64_t n = b.n;
-    bsq_result* R = new bsq_result;
-    R->n_reads = n; R->row_off = new uint64_t[n + 1]; R->rows = nullptr; R->cigar = nullptr; R->n_cigar_words = 0;
-    for (uint64_t i = 0; i <= n; ++i) R->row_off[i] = 0;
-    *out = R;
     h->timing.d2h_bytes = 0;
-    if (n == 0 || !h->meta.built) { R->rows = new bsq_row[1]; R->cigar = new uint32_t[1]; return BSQ_OK; }
-    std::vector<uint32_t> off32(n), cnt_last(1);
-    CUDA_CHECK(cudaMemcpyAsync(off32.data(), b.row_off.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_CHECK(cudaMemcpyAsync(cnt_last.data(), b.row_cnt.p + (n - 1), 4, cudaMemcpyDeviceToHost, h->stream));
-    uint32_t cig_top = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&cig_top, b.ctl.p + 6, 4, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    const uint64_t total_rows = (uint64_t)off32[n - 1] + cnt_last[0];
-    for (uint64_t i = 0; i < n; ++i) R->row_off[i] = off32[i];
-    R->row_off[n] = total_rows;
-    R->rows = new bsq_row[total_rows + 1];
-    R->cigar = new uint32_t[(size_t)cig_top + 1];
-    R->n_cigar_words = cig_top;
+    uint32_t tail[2] = {0, 0}, cig_top = 0;
+    const bool have = n != 0 && h->meta.built;
+    if (have) {
+        CUDA_CHECK(cudaMemcpyAsync(&tail[0], b.row_off.p + (n - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaMemcpyAsync(&tail[1], b.row_cnt.p + (n - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaMemcpyAsync(&cig_top, b.ctl.p + 6, 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    }
+    const uint64_t total_rows = (uint64_t)tail[0] + tail[1];
+    // block layout: row_off (u64 x (n+1)) | rows | cigar | staging for the device's u32 offsets
+    const size_t off_rows = ((n + 1) * 8 + 63) & ~(size_t)63;
+    const size_t off_cig = (off_rows + (total_rows + 1) * sizeof(bsq_row) + 63) & ~(size_t)63;
+    const size_t off_o32 = (off_cig + ((size_t)cig_top + 1) * 4 + 63) & ~(size_t)63;
+    const size_t need = off_o32 + (n + 1) * 4;
+    size_t got = 0;
+    void* block = pinned_get(need, &got);
+    if (!block) { bsq_set_error("cannot allocate %zu bytes of pinned host memory for the result", need); return BSQ_ERR; }
+    ResultImpl* R = new ResultImpl;
+    R->block = block; R->bytes = got;
+    R->pub.n_reads = n;
+    R->pub.row_off = reinterpret_cast<uint64_t*>(block);
+    R->pub.rows = reinterpret_cast<bsq_row*>(static_cast<char*>(block) + off_rows);
+    R->pub.cigar = reinterpret_cast<uint32_t*>(static_cast<char*>(block) + off_cig);
+    R->pub.n_cigar_words = cig_top;
+    *out = &R->pub;
+    if (!have) { for (uint64_t i = 0; i <= n; ++i) R->pub.row_off[i] = 0; return BSQ_OK; }
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(static_cast<char*>(block) + off_o32);
+    CUDA_CHECK(cudaMemcpyAsync(o32, b.row_off.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
     if (total_rows) {
         CUDA_CHECK(b.rows_compact.ensure(total_rows));
-        k_compact_rows<<<148 * 8, 256, 0, h->stream>>>(b.blocks.p, b.rows.p, b.row_cnt.p, b.row_off.p, (uint32_t)n, b.rows_compact.p); ++h->timing.launches;
-        CUDA_CHECK(cudaMemcpyAsync(R->rows, b.rows_compact.p, total_rows * sizeof(bsq_row), cudaMemcpyDeviceToHost, h->stream));
+        if (!h->d_logtab) {
+            std::vector<double> tab(LOGTAB_N);
+            tab[0] = 0.;
+            for (int i = 1; i < LOGTAB_N; ++i) tab[i] = log((double)i);   // host libm: the values the reference's log() returns
+            CUDA_CHECK(cudaMalloc(&h->d_logtab, LOGTAB_N * sizeof(double)));
+            CUDA_CHECK(cudaMemcpy(h->d_logtab, tab.data(), LOGTAB_N * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        MapqParams M; M.a = h->opts.a; M.b = h->opts.b; M.min_seed_len = h->opts.min_seed_len; M.coef_len = h->mapQ_coef_len;
+        M.coef_fac = (double)h->mapQ_coef_fac; M.logtab = h->d_logtab;
+        k_compact_rows<<<148 * 8, 256, 0, h->stream>>>(b.blocks.p, b.rows.p, b.row_cnt.p, b.row_off.p, (uint32_t)n, b.rows_compact.p, M); ++h->timing.launches;
+        CUDA_CHECK(cudaMemcpyAsync(R->pub.rows, b.rows_compact.p, total_rows * sizeof(bsq_row), cudaMemcpyDeviceToHost, h->stream));
     }
-    if (cig_top) CUDA_CHECK(cudaMemcpyAsync(R->cigar, b.cigar.p, (size_t)cig_top * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (cig_top) CUDA_CHECK(cudaMemcpyAsync(R->pub.cigar, b.cigar.p, (size_t)cig_top * 4, cudaMemcpyDeviceToHost, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    h->timing.d2h_bytes = n * 4 + 8 + total_rows * sizeof(bsq_row) + (uint64_t)cig_top * 4;
-    for (uint64_t i = 0; i < total_rows; ++i) R->rows[i].mapq = R->rows[i].secondary < 0 ? approx_mapq(h, R->rows[i]) : 0;
+    for (uint64_t i = 0; i < n; ++i) R->pub.row_off[i] = o32[i];
+    R->pub.row_off[n] = total_rows;
+    h->timing.d2h_bytes = n * 4 + 12 + total_rows * sizeof(bsq_row) + (uint64_t)cig_top * 4;
+    // rows outside the device log table (very long alignments): finish MAPQ on the host
+    for (uint64_t i = 0; i < total_rows; ++i)
+        if (R->pub.rows[i].mapq < 0) R->pub.rows[i].mapq = approx_mapq(h, R->pub.rows[i]);
     return BSQ_OK;
 }
 
@@ -546,7 +634,9 @@ int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const 
 
 void bsq_result_free(bsq_result* r) {
     if (!r) return;
-    delete[] r->row_off; delete[] r->rows; delete[] r->cigar; delete r;
+    ResultImpl* R = reinterpret_cast<ResultImpl*>(r);   // pub is the first member
+    pinned_put(R->block, R->bytes);
+    delete R;
 }
 
 int bsq_last_timing(const bsq_index* h, bsq_timing* t) {

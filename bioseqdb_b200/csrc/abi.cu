@@ -50,13 +50,14 @@ struct Batch {
     DevBuf<RegRec> regs; DevBuf<RowDev> rows, rows_compact; DevBuf<uint32_t> reg_cnt, row_cnt, row_off, scan_tmp;
     DevBuf<ReadBlock> blocks; uint32_t pool_cap = 0;
     DevBuf<uint32_t> cigar; uint32_t cigar_cap = 0;
+    DevBuf<double> read_logtab; uint32_t read_logtab_n = 0; uint32_t rseq_cap = 0;
     DevBuf<uint8_t> ext_scratch, fin_scratch, narrow_z; DevBuf<uint64_t> narrow_jobs, wide_jobs;
     DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..23] counters (u64 x 8), [24] narrow_cnt, [25] wide_cnt, [26..27] tickets
     bool resident = false, aligned = false;
     void release() {
         seqs.release(); offs.release(); ids.release(); intv.release(); intv_cnt.release(); seed_scratch.release(); raw.release(); seeds.release();
         ctmp.release(); ord.release(); chains.release(); srt.release(); regs.release(); rows.release(); rows_compact.release(); reg_cnt.release();
-        row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release(); ctl.release(); narrow_z.release(); narrow_jobs.release(); wide_jobs.release();
+        row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release(); ctl.release(); narrow_z.release(); narrow_jobs.release(); wide_jobs.release(); read_logtab.release();
     }
 };
 
@@ -347,13 +348,17 @@ int upload_reads(bsq_index* h, const char* seqs, const uint64_t* offs, const int
         if (l > 0x3fffffffull) { bsq_set_error("read too long"); return BSQ_ERR; }
         max_len = std::max<uint32_t>(max_len, (uint32_t)l);
     }
-    if (needs_seed_sw(max_len)) {
-        bsq_set_error("reads of %u bases need the per-seed local-SW filter (mem_flt_chained_seeds), which this build does not implement yet; "
-                      "reads must be shorter than ~730 bases", max_len);
-        return BSQ_ERR;
-    }
     const uint64_t total = n ? offs[n] - offs[0] : 0;
     b.n = n; b.max_len = max_len; b.total_bases = total;
+    if (needs_seed_sw(max_len) && b.read_logtab_n < max_len + 1) {
+        // log(l_query) for mem_flt_chained_seeds' thresholds: host libm values
+        std::vector<double> tab(max_len + 1);
+        tab[0] = 0.;
+        for (uint32_t i = 1; i <= max_len; ++i) tab[i] = log((double)i);
+        CUDA_CHECK(b.read_logtab.ensure(max_len + 1));
+        CUDA_CHECK(cudaMemcpy(b.read_logtab.p, tab.data(), (max_len + 1) * sizeof(double), cudaMemcpyHostToDevice));
+        b.read_logtab_n = max_len + 1;
+    }
     CUDA_CHECK(b.seqs.ensure(total + 64)); CUDA_CHECK(b.offs.ensure(n + 1)); CUDA_CHECK(b.ids.ensure(n + 1));
     std::vector<uint64_t> rel(n + 1);
     for (uint64_t i = 0; i <= n; ++i) rel[i] = offs[i] - (n ? offs[0] : 0);
@@ -377,7 +382,7 @@ int run_pipeline(bsq_index* h) {
     const DevIndex ix = make_dev_index(h);
     const DevOpts& o = h->dopts;
     const uint32_t max_len = std::max<uint32_t>(b.max_len, 1);
-    const uint32_t rseq_cap = rseq_cap_for(h, max_len);
+    uint32_t rseq_cap = std::max(rseq_cap_for(h, max_len), b.rseq_cap);
     if (b.intv_cap == 0) b.intv_cap = 48 + max_len / 4;
     if (b.pool_cap == 0) b.pool_cap = (uint32_t)std::min<uint64_t>((uint64_t)n * 24 + 4096, 0x7fffffffull);
     if (b.cigar_cap == 0) b.cigar_cap = (uint32_t)std::min<uint64_t>((uint64_t)n * 8 + 4096, 0x7fffffffull);
@@ -426,6 +431,7 @@ int run_pipeline(bsq_index* h) {
             P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.intv = b.intv.p; P.intv_cnt = b.intv_cnt.p; P.intv_cap = b.intv_cap;
             P.raw = b.raw.p; P.ctmp = b.ctmp.p; P.ord = b.ord.p; P.chains = b.chains.p; P.seeds = b.seeds.p; P.pool_cap = b.pool_cap; P.pool_top = b.ctl.p + 5;
             P.blocks = b.blocks.p; P.ticket = b.ctl.p + 1; P.overflow = b.ctl.p + 4; P.counters = ctr ? ctr + 1 : nullptr;
+            P.logtab = needs_seed_sw(b.max_len) ? b.read_logtab.p : nullptr; P.sw_cells = nullptr;
             launch_chain(P, ix, o, h->stream); ++T.launches;
         }
         cudaEventRecord(ev[2], h->stream);
@@ -433,7 +439,7 @@ int run_pipeline(bsq_index* h) {
             ExtendParams P;
             P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.blocks = b.blocks.p; P.chains = b.chains.p; P.seeds = b.seeds.p; P.srt = b.srt.p;
             P.regs = b.regs.p; P.reg_cnt = b.reg_cnt.p; P.scratch = b.ext_scratch.p; P.scratch_per_warp = ext_per_warp; P.max_len = max_len; P.rseq_cap = rseq_cap;
-            P.ticket = b.ctl.p + 2; P.overflow = b.ctl.p + 4; P.counters = ctr ? ctr + 3 : nullptr;
+            P.ticket = b.ctl.p + 2; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 3 : nullptr;
             launch_extend(P, ix, o, h->stream); ++T.launches;
         }
         cudaEventRecord(ev[3], h->stream);
@@ -443,7 +449,7 @@ int run_pipeline(bsq_index* h) {
             P.rows = b.rows.p; P.row_cnt = b.row_cnt.p; P.cigar_pool = b.cigar.p; P.cigar_cap = b.cigar_cap; P.cigar_top = b.ctl.p + 6;
             P.scratch = b.fin_scratch.p; P.scratch_per_warp = fin_per_warp; P.max_len = max_len; P.z_cap = z_cap; P.ann_id = h->d_ann_id;
             P.narrow_jobs = b.narrow_jobs.p; P.narrow_cnt = b.ctl.p + 24; P.wide_jobs = b.wide_jobs.p; P.wide_cnt = b.ctl.p + 25; P.narrow_z = b.narrow_z.p; P.narrow_warps = narrow_warps;
-            P.ticket = b.ctl.p + 26; P.overflow = b.ctl.p + 4; P.counters = ctr ? ctr + 6 : nullptr;
+            P.ticket = b.ctl.p + 26; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 6 : nullptr;
             launch_finalize(P, ix, o, h->stream, rseq_cap, fin_warps, &T.launches);
         }
         // compact rows: exclusive scan of row_cnt (n + 1 entries, the last one is a zero pad) -> row_off
@@ -459,6 +465,10 @@ int run_pipeline(bsq_index* h) {
         cudaEventElapsedTime(&ms, ev[2], ev[3]); T.extend += ms;
         cudaEventElapsedTime(&ms, ev[3], ev[4]); T.finalize += ms;
         cudaEventElapsedTime(&ms, ev[0], ev[4]); T.total += ms;
+        if (ctl[7] > rseq_cap && ctl[4] != 2) {   // a reference window was larger than planned: grow the per-warp scratch and run again
+            rseq_cap = b.rseq_cap = ctl[7] + ctl[7] / 8 + 64;
+            continue;
+        }
         if (ctl[4] == 0) {
             if (ctr) { ENS(cudaMemcpy(h->counters, ctr, sizeof(h->counters), cudaMemcpyDeviceToHost)); }
             b.aligned = true;

@@ -38,9 +38,100 @@ __device__ __forceinline__ int chain_weight(const SeedRec* raw, const ChainTmp& 
     return w < 1 << 30 ? w : (1 << 30) - 1;
 }
 
-__global__ void __launch_bounds__(CHAIN_THREADS) chain_build(ChainParams P, DevIndex ix, DevOpts o) {
+constexpr int MEM_SHORT_EXT = 50;
+constexpr int MEM_SHORT_LEN = 200;
+constexpr int SW_BUF_INTS = 2 * MEM_SHORT_LEN + MEM_SHORT_LEN / 4 + 8;   // boundary H, boundary F, reference window bytes
+
+// Score of ksw_align2 (local SW, affine gaps opening from H, 16-bit kernel => no saturation at these sizes).
+// Anti-diagonal wavefront: lane l owns query column 32 b + l of column block b and processes target row
+// s - l at step s; H(i,j-1), F(i,j) and H(i-1,j-1) come from the left lane by shuffle, the block's last
+// column is parked in shared memory for the next block.  qlen, tlen < 200.
+__device__ int ksw_local_warp(const DevOpts& o, const int* smat, int qlen, const uint8_t* q, int tlen, const uint8_t* t, int* bH, int* bF) {
     const int lane = lane_id();
-    unsigned long long n_sa = 0, n_dup = 0;
+    const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins, e_del = o.e_del, e_ins = o.e_ins;
+    for (int i = lane; i < tlen; i += 32) { bH[i] = 0; bF[i] = 0; }
+    __syncwarp();
+    int best = 0;
+    for (int j0 = 0; j0 < qlen; j0 += 32) {
+        const int j = j0 + lane;
+        const bool col_ok = j < qlen;
+        const int qb = col_ok ? (int)q[j] : 4;
+        int h_up = 0, e = 0;          // H(i-1, j), E(i, j) of this lane's column
+        int h_cur = 0, h_prev = 0;    // this lane's H at the previous two steps (H(i,j) and H(i-1,j) seen from the right)
+        int f_out = 0;                // F(i, j+1) produced by this lane at the previous step
+        for (int s = 0; s < tlen + 31; ++s) {
+            const int i = s - lane;
+            // values from the left neighbour (its state after step s-1): H(i, j-1) = its h_cur, H(i-1, j-1) = its h_prev, F(i, j) = its f_out
+            int h_left = __shfl_up_sync(FULL, h_cur, 1), h_diag = __shfl_up_sync(FULL, h_prev, 1), f_in = __shfl_up_sync(FULL, f_out, 1);
+            if (lane == 0) {
+                const bool in = i >= 0 && i < tlen;
+                h_left = in ? bH[i] : 0;
+                h_diag = (in && i > 0) ? bH[i - 1] : 0;   // H(i-1, j0-1); the block boundary column still holds the previous block's values
+                f_in = in ? bF[i] : 0;
+            }
+            (void)h_left;
+            if (i >= 0 && i < tlen && col_ok) {
+                int h = h_diag + smat[(int)t[i] * 5 + qb];
+                h = h > e ? h : e;
+                h = h > f_in ? h : f_in;
+                h = h > 0 ? h : 0;
+                best = best > h ? best : h;
+                int tt = h - oe_del; tt = tt > 0 ? tt : 0;
+                e -= e_del; e = e > tt ? e : tt;
+                tt = h - oe_ins; tt = tt > 0 ? tt : 0;
+                int f2 = f_in - e_ins; f2 = f2 > tt ? f2 : tt;
+                h_prev = h_cur; h_cur = h; f_out = f2; h_up = h;
+            } else { h_prev = h_cur; h_cur = 0; f_out = 0; }
+            // the last column of the block becomes the next block's left boundary
+            if (lane == 31 && i >= 0 && i < tlen) { bH[i] = h_cur; bF[i] = f_out; }
+        }
+        (void)h_up;
+        __syncwarp();
+    }
+    return __reduce_max_sync(FULL, best);
+}
+
+// mem_seed_sw: -1 when the seed or its +-50 bp window is long enough to be trusted
+__device__ int mem_seed_sw(const DevIndex& ix, const DevOpts& o, const int* smat, int l_query, const uint8_t* query, const SeedRec& s, int* swbuf,
+                           unsigned long long& cells) {
+    const int64_t l_pac = ix.l_pac;
+    if (s.len >= MEM_SHORT_LEN) return -1;
+    int qb = s.qbeg, qe = s.qbeg + s.len;
+    int64_t rb = s.rbeg, re = s.rbeg + s.len;
+    const int64_t mid = (rb + re) >> 1;
+    qb -= MEM_SHORT_EXT; qb = qb > 0 ? qb : 0;
+    qe += MEM_SHORT_EXT; qe = qe < l_query ? qe : l_query;
+    rb -= MEM_SHORT_EXT; rb = rb > 0 ? rb : 0;
+    re += MEM_SHORT_EXT; re = re < (l_pac << 1) ? re : (l_pac << 1);
+    if (rb < l_pac && l_pac < re) { if (mid < l_pac) re = l_pac; else rb = l_pac; }
+    if (qe - qb >= MEM_SHORT_LEN || re - rb >= MEM_SHORT_LEN) return -1;
+    {   // bns_fetch_seq: clamp to the row that holds mid
+        int is_rev;
+        const int rid = bns_pos2rid(ix, bns_depos(ix, mid, &is_rev));
+        int64_t far_beg = ix.ann_offset[rid], far_end = far_beg + ix.ann_len[rid];
+        if (is_rev) { const int64_t tmp = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - tmp; }
+        rb = rb > far_beg ? rb : far_beg;
+        re = re < far_end ? re : far_end;
+        if (re < rb) re = rb;
+    }
+    const int tlen = (int)(re - rb), qlen = qe - qb;
+    int* bH = swbuf; int* bF = swbuf + MEM_SHORT_LEN;
+    uint8_t* tw = reinterpret_cast<uint8_t*>(swbuf + 2 * MEM_SHORT_LEN);
+    __syncwarp();
+    for (int i = lane_id(); i < tlen; i += 32) tw[i] = (uint8_t)ref_base(ix, rb + i);
+    __syncwarp();
+    cells += (unsigned long long)qlen * (unsigned long long)tlen;
+    return ksw_local_warp(o, smat, qlen, query + qb, tlen, tw, bH, bF);
+}
+
+__global__ void __launch_bounds__(CHAIN_THREADS) chain_build(ChainParams P, DevIndex ix, DevOpts o) {
+    __shared__ int smat[25];
+    __shared__ int sw_smem[CHAIN_THREADS / 32][SW_BUF_INTS];
+    if (threadIdx.x < 25) smat[threadIdx.x] = o.mat[threadIdx.x];
+    __syncthreads();
+    const int lane = lane_id();
+    int* swbuf = sw_smem[threadIdx.x >> 5];
+    unsigned long long n_sa = 0, n_dup = 0, n_swcells = 0;
     for (;;) {
         uint32_t r = next_ticket(P.ticket);
         if (r >= P.n_reads) break;
@@ -145,7 +236,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) chain_build(ChainParams P, DevI
         // ---- weights (lanes over chains), min_chain_weight drop
         for (int k = lane; k < n_ch; k += 32) ct[k].w = (uint32_t)chain_weight(raw, ct[k]);
         __syncwarp();
-        int n_out = 0; uint32_t seed_out = 0;
+        int n_out = 0, n_flt = 0; uint32_t seed_out = 0;
         if (lane == 0 && n_ch) {
             // mem_chain_flt: ord[] is the chain array `a` in pos order
             int n = 0;
@@ -185,22 +276,48 @@ __global__ void __launch_bounds__(CHAIN_THREADS) chain_build(ChainParams P, DevI
                     if (++k >= o.max_chain_extend) break;
                 }
                 for (; i < n; ++i) if (ct[ord[i]].kept < 3) ct[ord[i]].kept = 0;
-                // ---- emit kept chains in order with contiguous seeds
-                ChainRec* co = P.chains + base; SeedRec* so = P.seeds + base;
-                float frac_rep = (float)l_rep / len;
-                for (i = 0; i < n; ++i) {
-                    const ChainTmp& c = ct[ord[i]];
-                    if (c.kept == 0) continue;
-                    ChainRec rec; rec.pos = c.pos; rec.rid = c.rid; rec.n_seeds = c.n; rec.seed_off = (int32_t)seed_out; rec.kept = c.kept;
-                    rec.w = c.w; rec.frac_rep = frac_rep;
-                    for (int s = c.head; s >= 0; s = raw[s].next) { SeedRec q = raw[s]; q.next = -1; so[seed_out++] = q; }
-                    co[n_out++] = rec;
+                n_flt = n;
+            }
+        }
+        n_flt = __shfl_sync(FULL, n_flt, 0);
+        __syncwarp();
+        // ---- emit kept chains in order with contiguous seeds; long reads first pass every short seed through
+        // mem_seed_sw (local SW of the seed +-50 bp, SURVEY A.6 mem_flt_chained_seeds) on the whole warp
+        if (n_flt) {
+            ChainRec* co = P.chains + base; SeedRec* so = P.seeds + base;
+            const float frac_rep = (float)l_rep / len;
+            bool seed_sw = false; int min_HSP = 0;
+            if (P.logtab) {
+                const double min_l = (double)5.5f * P.logtab[len];            // MEM_MINSC_COEF * log(l_query), min_chain_weight == 0
+                seed_sw = !(min_l > (double)__fmul_rn(0.05f, (float)len));   // MEM_SEEDSW_COEF * l_query is a float product
+                min_HSP = (int)(o.a * min_l + .499);
+            }
+            const uint8_t* query = P.seqs + P.offs[r];
+            for (int i = 0; i < n_flt; ++i) {
+                const ChainTmp c = ct[ord[i]];
+                if (c.kept == 0) continue;
+                ChainRec rec; rec.pos = c.pos; rec.rid = c.rid; rec.seed_off = (int32_t)seed_out; rec.kept = c.kept;
+                rec.w = c.w; rec.frac_rep = frac_rep;
+                int kept_seeds = 0;
+                for (int s = c.head; s >= 0; s = raw[s].next) {
+                    SeedRec q = raw[s]; q.next = -1;
+                    bool keep = true;
+                    if (seed_sw) {
+                        const int sc = mem_seed_sw(ix, o, smat, len, query, q, swbuf, n_swcells);
+                        if (sc < 0 || sc >= min_HSP) q.score = sc < 0 ? q.len * o.a : sc;
+                        else keep = false;
+                    }
+                    if (keep) { if (lane == 0) so[seed_out] = q; ++seed_out; ++kept_seeds; }
                 }
+                rec.n_seeds = kept_seeds;
+                if (lane == 0) co[n_out] = rec;
+                ++n_out;
             }
         }
         if (lane == 0) { blk.n_chains = (uint32_t)n_out; blk.n_seeds = seed_out; P.blocks[r] = blk; }
     }
     if (P.counters && lane == 0) { if (n_sa) atomicAdd(&P.counters[0], n_sa); if (n_dup) atomicAdd(&P.counters[1], n_dup); }
+    if (P.sw_cells && lane == 0 && n_swcells) atomicAdd(P.sw_cells, n_swcells);
 }
 
 }  // namespace

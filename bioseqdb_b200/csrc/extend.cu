@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(EXT_THREADS) sw_extend(ExtendParams P, DevInde
                 if (rmax1 < rmax0) rmax1 = rmax0;   // seed lying wholly in inter-row filler: empty fetch
             }
             const int64_t rlen = rmax1 - rmax0;
-            if (rlen > (int64_t)P.rseq_cap) { if (lane == 0) atomicExch(P.overflow, 2u); continue; }
+            if (rlen > (int64_t)P.rseq_cap) { if (lane == 0) atomicMax(P.need_rseq, (uint32_t)(rlen < 0x7fffffff ? rlen : 0x7fffffff)); continue; }
             for (int64_t i = lane; i < rlen; i += 32) S.rseq[i] = (uint8_t)ref_base(ix, rmax0 + i);
             // ---- seed order: by (score, index) ascending, processed from the top (keys are unique)
             if (lane == 0) {

@@ -43,7 +43,7 @@ struct GenOut { int ok, score, n_cigar, NM; };
 // [rb, re).  WANT_CIGAR: traceback into S.cig (forward order) and NM.
 template <bool WANT_CIGAR>
 __device__ GenOut gen_cigar2(const DevIndex& ix, const DevOpts& o, const int* smat, int w_, int l_query, const uint8_t* q, int64_t rb, int64_t re,
-                             const FScratch& S, uint32_t rseq_cap, uint32_t z_cap, uint32_t cig_cap, uint32_t* overflow,
+                             const FScratch& S, uint32_t rseq_cap, uint32_t z_cap, uint32_t cig_cap, uint32_t* overflow, uint32_t* need_rseq,
                              unsigned long long& cells, unsigned long long& calls) {
     const int lane = lane_id();
     const int64_t l_pac = ix.l_pac;
@@ -52,7 +52,7 @@ __device__ GenOut gen_cigar2(const DevIndex& ix, const DevOpts& o, const int* sm
     // bns_get_seq clamps to [0, 2 l_pac); a clamped fetch makes libbwa bail out (re - rb != rlen)
     if (rb < 0 || re > (l_pac << 1)) return g;
     const int64_t rlen64 = re - rb;
-    if (rlen64 > (int64_t)rseq_cap) { if (lane == 0) atomicExch(overflow, 2u); return g; }
+    if (rlen64 > (int64_t)rseq_cap) { if (lane == 0) atomicMax(need_rseq, (uint32_t)(rlen64 < 0x7fffffff ? rlen64 : 0x7fffffff)); return g; }
     const int rlen = (int)rlen64;
     for (int i = lane; i < rlen; i += 32) S.rseq[i] = (uint8_t)ref_base(ix, rb + i);
     __syncwarp();
@@ -131,7 +131,7 @@ __device__ GenOut gen_cigar2(const DevIndex& ix, const DevOpts& o, const int* sm
 
 // mem_patch_reg; a = earlier region, b = later region
 __device__ int patch_reg(const DevIndex& ix, const DevOpts& o, const int* smat, const uint8_t* query, const RegRec& a, const RegRec& b, int* _w,
-                         const FScratch& S, uint32_t rseq_cap, uint32_t* overflow, unsigned long long& cells, unsigned long long& calls) {
+                         const FScratch& S, uint32_t rseq_cap, uint32_t* overflow, uint32_t* need_rseq, unsigned long long& cells, unsigned long long& calls) {
     int w, score, q_s, r_s;
     double r;
     if (a.rb < ix.l_pac && b.rb >= ix.l_pac) return 0;
@@ -145,7 +145,7 @@ __device__ int patch_reg(const DevIndex& ix, const DevOpts& o, const int* smat, 
     } else if (w > o.w << 2 || r >= (double)(0.05f * 2)) return 0;
     w += a.w + b.w;
     w = w < o.w << 2 ? w : o.w << 2;
-    GenOut g = gen_cigar2<false>(ix, o, smat, w, b.qe - a.qb, query + a.qb, a.rb, b.re, S, rseq_cap, 0, 0, overflow, cells, calls);
+    GenOut g = gen_cigar2<false>(ix, o, smat, w, b.qe - a.qb, query + a.qb, a.rb, b.re, S, rseq_cap, 0, 0, overflow, need_rseq, cells, calls);
     score = g.score;
     q_s = (int)((double)(b.qe - a.qb) / (double)((b.qe - b.qb) + (a.qe - a.qb)) * (double)(b.score + a.score) + .499);
     r_s = (int)((double)(b.re - a.rb) / (double)((b.re - b.rb) + (a.re - a.rb)) * (double)(b.score + a.score) + .499);
@@ -206,7 +206,7 @@ __device__ void reg2aln_warp(const FinalizeParams& P, const DevIndex& ix, const 
     GenOut g;
     do {
         w2 = w2 < o.w << 2 ? w2 : o.w << 2;
-        g = gen_cigar2<true>(ix, o, smat, w2, qe - qb, S.query + qb, rb, re, S, rseq_cap, P.z_cap, cig_cap - 2, P.overflow, cells, calls);
+        g = gen_cigar2<true>(ix, o, smat, w2, qe - qb, S.query + qb, rb, re, S, rseq_cap, P.z_cap, cig_cap - 2, P.overflow, P.need_rseq, cells, calls);
         if (g.ok) score = g.score;
         if (score == last_sc || w2 == o.w << 2) break;
         last_sc = score;
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(FIN_THREADS) regs_finalize(FinalizeParams P, D
                             if (lane == 0) a[j].qe = q.qb;
                             __syncwarp();
                         }
-                    } else if (q.rb < p.rb && (score = patch_reg(ix, o, smat, S.query, q, p, &w, S, rseq_cap, P.overflow, cells, calls)) > 0) {
+                    } else if (q.rb < p.rb && (score = patch_reg(ix, o, smat, S.query, q, p, &w, S, rseq_cap, P.overflow, P.need_rseq, cells, calls)) > 0) {
                         if (lane == 0) {
                             RegRec& pp = a[i];
                             pp.n_comp += q.n_comp + 1;

@@ -27,6 +27,8 @@ struct ChainParams {
     ReadBlock* blocks;
     uint32_t* ticket; uint32_t* overflow;
     unsigned long long* counters;  // optional: [0] = SA lookups, [1] = equal-pos chain events (SURVEY A.5 corner)
+    const double* logtab;          // host-libm log(l) for l <= longest read; nullptr when no read is long enough for mem_flt_chained_seeds
+    unsigned long long* sw_cells;  // optional: cells of the seed-filter local SW
 };
 void launch_chain(const ChainParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st);
 
@@ -36,6 +38,7 @@ struct ExtendParams {
     RegRec* regs; uint32_t* reg_cnt;       // a read's regions live at regs[blocks[r].base ...], at most n_seeds of them
     uint8_t* scratch; size_t scratch_per_warp; uint32_t max_len, rseq_cap;
     uint32_t* ticket; uint32_t* overflow;
+    uint32_t* need_rseq;           // atomicMax of the reference window a read needed when it exceeded rseq_cap (host grows and re-runs)
     unsigned long long* counters;  // optional: [0] = ksw_extend2 cells, [1] = calls, [2] = rows
 };
 void launch_extend(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st);
@@ -65,6 +68,7 @@ struct FinalizeParams {
     uint64_t* narrow_jobs; uint32_t* narrow_cnt; uint64_t* wide_jobs; uint32_t* wide_cnt; uint8_t* narrow_z; int narrow_warps;
     uint32_t* ticket;              // three consecutive tickets: finalize, narrow, wide
     uint32_t* overflow;
+    uint32_t* need_rseq;           // see ExtendParams
     unsigned long long* counters;  // optional: [0] = ksw_global2 cells, [1] = calls
 };
 void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint32_t rseq_cap, int n_warps, uint64_t* launches);

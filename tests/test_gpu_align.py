@@ -77,3 +77,81 @@ def test_align_single_read_entry(gpu_lib):
         o = orc.align_batch(read, np.array([0, 150], dtype=np.uint64), ids[i:i + 1], 1)
         bad = compare_results(g, o)
         assert not bad, "\n".join(bad)
+
+
+def test_align_many_short_contigs(gpu_lib):
+    """C5-like: thousands of short rows whose lengths are not multiples of 4 (inter-row filler bases in the
+    text), max_occ = max(500, 2 * rows) by the reference's rule; reads flush with contig ends."""
+    rng = np.random.default_rng(61)
+    lens = rng.integers(500, 1501, size=3000)
+    lens = (lens + (lens % 4 == 0)).tolist()
+    rows = synth.reference_rows(lens, seed=62)
+    orc, gpu = build_pair(rows, O.sql_default_opts(len(rows)))
+    assert orc.opts.max_occ == 6000
+    seqs, offs, _ = synth.simulate_reads(rows, 3000, 150, seed=63)
+    extra = [rows[i].tobytes()[-150:] for i in range(0, 3000, 97)] + [rows[i].tobytes()[:150] for i in range(5, 3000, 101)]
+    s2, o2 = read_arrays(extra)
+    seqs = np.concatenate([seqs, s2]); offs = np.concatenate([offs, o2[1:] + offs[-1]])
+    n = len(offs) - 1
+    ids = synth.lrand48_ids_fast(n)
+    g = gpu.align_batch(seqs, offs, ids)
+    o = orc.align_batch(seqs, offs, ids, 4)
+    bad = compare_results(g, o)
+    assert not bad, "\n".join(bad)
+
+
+def test_align_small_max_occ_and_options(gpu_lib):
+    """max_occ below the repeat copy number => the k/step sampling rule, frac_rep > 0 and MAPQ scaling;
+    non-default match score / penalties / band / zdrop / clip penalties flow through every kernel."""
+    rows = synth.reference_rows([200_000], seed=71)
+    rows = synth.plant_repeats(rows, n_families=4, copies=40, unit=(300, 500), divergence=0.0, seed=72)
+    opts = O.Opts(17, 8, 2, 5, 7, 3, 60, 40, 5, 2, 4, 1)
+    orc, gpu = build_pair(rows, opts)
+    seqs, offs, _ = synth.simulate_reads(rows, 3000, 150, sub=0.02, ins=0.004, dele=0.004, seed=73)
+    ids = synth.lrand48_ids_fast(3000)
+    g = gpu.align_batch(seqs, offs, ids)
+    o = orc.align_batch(seqs, offs, ids, 4)
+    bad = compare_results(g, o)
+    assert not bad, "\n".join(bad)
+    assert (g.rows["frac_rep"] > 0).sum() > 0
+
+
+def test_align_read_lengths_ragged(gpu_lib):
+    """ragged batch: read lengths 19..700 in one call (the batch's max length sizes every per-warp scratch)"""
+    rows = synth.reference_rows([150_000, 90_001], seed=81)
+    orc, gpu = build_pair(rows, O.canonical_opts(2))
+    rng = np.random.default_rng(82)
+    reads = []
+    cat = [r.tobytes() for r in rows]
+    for i in range(600):
+        ln = int(rng.choice([19, 20, 35, 76, 100, 151, 250, 400, 700]))
+        r = int(rng.integers(0, 2)); p = int(rng.integers(0, len(cat[r]) - ln))
+        t = bytearray(cat[r][p:p + ln])
+        for k in range(len(t)):
+            if rng.random() < 0.02:
+                t[k] = b"ACGT"[int(rng.integers(0, 4))]
+        reads.append(bytes(t))
+    seqs, offs = read_arrays(reads)
+    ids = synth.lrand48_ids_fast(len(reads))
+    g = gpu.align_batch(seqs, offs, ids)
+    o = orc.align_batch(seqs, offs, ids, 4)
+    bad = compare_results(g, o)
+    assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("opts_fn,rlen,err", [(O.canonical_opts, 1000, (0.02, 0.005, 0.005)), (O.sql_default_opts, 2500, (0.04, 0.03, 0.03)),
+                                              (O.canonical_opts, 6000, (0.04, 0.03, 0.03))])
+def test_align_long_reads(gpu_lib, opts_fn, rlen, err):
+    """C4-like: reads long enough (> ~730 bp) for mem_flt_chained_seeds' per-seed local SW, many seeds per
+    chain, wide-band ksw_extend2 with band retries, wide ksw_global2 tracebacks."""
+    rows = synth.reference_rows([400_000, 250_003], seed=101)
+    orc, gpu = build_pair(rows, opts_fn(2))
+    n = 120 if rlen <= 2500 else 40
+    seqs, offs, _ = synth.simulate_reads(rows, n, rlen, sub=err[0], ins=err[1], dele=err[2], seed=102 + rlen)
+    ids = synth.lrand48_ids_fast(n)
+    g = gpu.align_batch(seqs, offs, ids)
+    o = orc.align_batch(seqs, offs, ids, 4)
+    bad = compare_results(g, o)
+    assert not bad, "\n".join(bad)
+    assert o["counters"]["sw_calls"] > 0
+    assert int(g.row_off[-1]) >= n

@@ -309,3 +309,28 @@ def test_options_mixup_and_row_text(oracle):
     txt = ix.rows_text(b"TTTTTTTT" + ref[100:200], 0)
     f = txt.strip().split("\t")
     assert f[0] == "42" and f[12] == "8N100M" and f[13] == "100" and f[1] == ref[100:200].decode() and f[2:5] == ["100", "200", "100"]
+
+
+def test_ksw_local_vs_naive(L):
+    """ksw_align2's score (mem_seed_sw) = plain Gotoh local SW, gaps opening from H."""
+    rng = np.random.default_rng(12)
+    for opts_fn in (O.sql_default_opts, O.canonical_opts):
+        opts = opts_fn(1)
+        S = _mat()
+        for _ in range(60):
+            ql, tl = int(rng.integers(1, 50)), int(rng.integers(1, 50))
+            q = rng.integers(0, 4, size=ql).astype(np.uint8)
+            t = rng.integers(0, 4, size=tl).astype(np.uint8)
+            k = int(rng.integers(0, min(ql, tl)))
+            t[:k] = q[:k]
+            sc = L.orc_ksw_local(ql, O._ptr(q), tl, O._ptr(t), C.byref(opts))
+            NEG = -10**9
+            H = [[0] * (ql + 1) for _ in range(tl + 1)]; E = [[NEG] * (ql + 1) for _ in range(tl + 1)]; F = [[NEG] * (ql + 1) for _ in range(tl + 1)]
+            best = 0
+            for i in range(1, tl + 1):
+                for j in range(1, ql + 1):
+                    E[i][j] = max(E[i - 1][j] - opts.e_del, H[i - 1][j] - opts.o_del - opts.e_del)
+                    F[i][j] = max(F[i][j - 1] - opts.e_ins, H[i][j - 1] - opts.o_ins - opts.e_ins)
+                    H[i][j] = max(0, H[i - 1][j - 1] + S[t[i - 1]][q[j - 1]], E[i][j], F[i][j])
+                    best = max(best, H[i][j])
+            assert sc == best

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
 #include <mutex>
@@ -174,6 +175,7 @@ int bsq_index_build(bsq_index* h) {
     if (upload_anns(h) != BSQ_OK) return BSQ_ERR;
     IndexBuild B;
     B.d_pac = h->d_pac; B.l_pac = (int64_t)h->pac.size() * 4;
+    { const char* fw = getenv("BSQ_FORCE_WIDE"); B.force_wide = fw && fw[0] == '1'; }   // test hook: 64-bit index path on small inputs
     if (build_index_device(B, h->stream) != BSQ_OK) return BSQ_ERR;
     h->d_occ = B.d_occ; h->d_sa = B.d_sa;
     bsq_index_meta& m = h->meta;

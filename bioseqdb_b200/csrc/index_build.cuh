@@ -6,6 +6,7 @@ struct IndexBuild {
     // in
     const uint8_t* d_pac = nullptr;  // device, l_pac / 4 bytes
     int64_t l_pac = 0;
+    bool force_wide = false;         // take the 64-bit-id path regardless of size (tests)
     // out (device allocations owned by the caller after success)
     uint32_t* d_occ = nullptr; uint64_t occ_bytes = 0;
     void* d_sa = nullptr; int sa_bytes = 4;

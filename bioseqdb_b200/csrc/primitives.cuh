@@ -104,8 +104,16 @@ constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 elements per CTA tile
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_BINS = 256;
 
-// histogram: hist[bin * n_tiles + tile]
-template <class K> __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K* keys, size_t n, int shift, uint32_t* hist, uint32_t n_tiles) {
+// Element source of a radix pass: plain (key, value) arrays, or keys/values computed from the element index
+// (used by the wide index build to bucket 64-bit suffix ids by their leading symbols without materialising them).
+template <class K, class V> struct SrcArrays {
+    const K* k; const V* v;
+    __device__ __forceinline__ K key(size_t i) const { return k[i]; }
+    __device__ __forceinline__ V val(size_t i) const { return v[i]; }
+};
+
+// histogram: hist[bin * n_tiles + tile]; H = uint32_t while n < 2^32, unsigned long long beyond
+template <class Src, class H> __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(Src src, size_t n, int shift, H* hist, uint32_t n_tiles) {
     __shared__ uint32_t h[RS_BINS];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -113,21 +121,24 @@ template <class K> __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         size_t idx = base + (size_t)i * RS_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&h[(uint32_t)(keys[idx] >> shift) & 0xff], 1u);
+        if (idx < n) atomicAdd(&h[(uint32_t)(src.key(idx) >> shift) & 0xff], 1u);
     }
     __syncthreads();
-    hist[(size_t)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
+    hist[(size_t)threadIdx.x * n_tiles + blockIdx.x] = (H)h[threadIdx.x];
 }
 
-template <class K, class V> __global__ void __launch_bounds__(RS_THREADS)
-k_rs_scatter(const K* __restrict__ keys_in, const V* __restrict__ vals_in, K* __restrict__ keys_out, V* __restrict__ vals_out,
-             size_t n, int shift, const uint32_t* __restrict__ hist_scanned, uint32_t n_tiles) {
+template <class K, class V, class H> constexpr size_t rs_scatter_smem() {
+    return sizeof(uint32_t) * (RS_WARPS * RS_BINS + RS_BINS + 32) + sizeof(H) * RS_BINS + (sizeof(K) + sizeof(V)) * RS_TILE;
+}
+
+template <class K, class V, class Src, class H> __global__ void __launch_bounds__(RS_THREADS)
+k_rs_scatter(Src src, K* __restrict__ keys_out, V* __restrict__ vals_out, size_t n, int shift, const H* __restrict__ hist_scanned, uint32_t n_tiles) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     uint32_t (*wcount)[RS_BINS] = reinterpret_cast<uint32_t (*)[RS_BINS]>(rs_smem);  // per-warp digit counts, then bases
     uint32_t* tile_base = reinterpret_cast<uint32_t*>(rs_smem + sizeof(uint32_t) * RS_WARPS * RS_BINS);  // excl. scan over digits
-    uint32_t* glob_base = tile_base + RS_BINS;
-    uint32_t* shs = glob_base + RS_BINS;
-    K* skey = reinterpret_cast<K*>(shs + 32);
+    uint32_t* shs = tile_base + RS_BINS;
+    H* glob_base = reinterpret_cast<H*>(shs + 32);
+    K* skey = reinterpret_cast<K*>(glob_base + RS_BINS);
     V* sval = reinterpret_cast<V*>(skey + RS_TILE);
     const int w = threadIdx.x >> 5, lane = lane_id();
     for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&wcount[0][0])[i] = 0;
@@ -141,8 +152,8 @@ k_rs_scatter(const K* __restrict__ keys_in, const V* __restrict__ vals_in, K* __
     for (int r = 0; r < RS_ITEMS; ++r) {
         size_t idx = wbase + (size_t)r * 32 + lane;
         bool ok = idx < n;
-        k[r] = ok ? keys_in[idx] : K(0);
-        v[r] = ok ? vals_in[idx] : V(0);
+        k[r] = ok ? src.key(idx) : K(0);
+        v[r] = ok ? src.val(idx) : V(0);
         uint32_t d = ok ? ((uint32_t)(k[r] >> shift) & 0xff) : 0x100u;  // invalid lanes form their own class
         uint32_t peers = __match_any_sync(FULL, d);
         uint32_t before = __popc(peers & ((1u << lane) - 1));
@@ -179,15 +190,13 @@ k_rs_scatter(const K* __restrict__ keys_in, const V* __restrict__ vals_in, K* __
         K kk = skey[p];
         uint32_t d = (uint32_t)(kk >> shift) & 0xff;
         size_t g = (size_t)glob_base[d] + (p - tile_base[d]);
-        keys_out[g] = kk; vals_out[g] = sval[p];
+        if (keys_out) keys_out[g] = kk;
+        vals_out[g] = sval[p];
     }
 }
 
-template <class K, class V> constexpr size_t rs_scatter_smem() {
-    return sizeof(uint32_t) * (RS_WARPS * RS_BINS + 2 * RS_BINS + 32) + (sizeof(K) + sizeof(V)) * RS_TILE;
-}
-template <class K, class V> cudaError_t rs_prepare() {  // opt in to > 48 KB dynamic shared memory
-    return cudaFuncSetAttribute(k_rs_scatter<K, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_scatter_smem<K, V>());
+template <class K, class V, class Src, class H> cudaError_t rs_prepare() {  // opt in to > 48 KB dynamic shared memory
+    return cudaFuncSetAttribute(k_rs_scatter<K, V, Src, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_scatter_smem<K, V, H>());
 }
 struct RadixWorkspace {
     uint32_t* hist = nullptr; uint32_t* scan_tmp = nullptr; size_t hist_elems = 0, tmp_elems = 0;
@@ -202,12 +211,14 @@ int radix_sort_pairs(K* k0, V* v0, K* k1, V* v1, size_t n, int begin_bit, int en
     int cur = 0;
     if (n == 0) return 0;
     uint32_t tiles = (uint32_t)rs_tiles(n);
+    using Src = SrcArrays<K, V>;
     for (int shift = begin_bit; shift < end_bit; shift += 8) {
         K* ki = cur ? k1 : k0; V* vi = cur ? v1 : v0; K* ko = cur ? k0 : k1; V* vo = cur ? v0 : v1;
-        k_rs_hist<K><<<tiles, RS_THREADS, 0, st>>>(ki, n, shift, ws.hist, tiles);
+        Src src{ki, vi};
+        k_rs_hist<Src, uint32_t><<<tiles, RS_THREADS, 0, st>>>(src, n, shift, ws.hist, tiles);
         if (launches) ++*launches;
         device_scan<uint32_t, OpSum, false>(ws.hist, ws.hist, (size_t)tiles * RS_BINS, ws.scan_tmp, OpSum(), st, launches);
-        k_rs_scatter<K, V><<<tiles, RS_THREADS, rs_scatter_smem<K, V>(), st>>>(ki, vi, ko, vo, n, shift, ws.hist, tiles);
+        k_rs_scatter<K, V, Src, uint32_t><<<tiles, RS_THREADS, rs_scatter_smem<K, V, uint32_t>(), st>>>(src, ko, vo, n, shift, ws.hist, tiles);
         if (launches) ++*launches;
         if (pass_bytes) *pass_bytes += (uint64_t)n * (2 * sizeof(K) + sizeof(V) + sizeof(K) + sizeof(V));
         cur ^= 1;

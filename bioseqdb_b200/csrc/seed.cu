@@ -432,7 +432,7 @@ template <int MODE> static void launch_mode(const SeedParams& p, const DevIndex&
 }
 
 void launch_seed(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, int* n_warps_out) {
-    const bool wide = ix.seq_len + 1 >= 0xffffffffull;
+    const bool wide = ix.sa_bytes == 8;   // 64-bit row indices
     if (wide) launch_mode<2>(p, ix, o, st, 0, n_warps_out);
     else if (p.lists_in_smem) launch_mode<0>(p, ix, o, st, seed_smem_bytes(p), n_warps_out);
     else launch_mode<1>(p, ix, o, st, 0, n_warps_out);

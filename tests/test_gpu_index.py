@@ -63,3 +63,20 @@ def test_empty_reference(gpu_lib):
     ix = BwaIndex()
     ix.build()
     assert ix.align_sequence(b"ACGTACGTACGTACGTACGTACGT") == []
+
+
+@pytest.mark.parametrize("text", [None, b"A" * 300, b"ACGTTGCA" * 40 + b"A" * 100, b"AC" * 257 + b"G"])
+def test_index_wide_path_small(gpu_lib, monkeypatch, text):
+    """The 64-bit-id build (bucketed counting sort + per-bucket radix sort + compacted prefix doubling) and the
+    64-bit seeding path, forced on small inputs so that the oracle can check them (at >= 2^32 rows it cannot)."""
+    monkeypatch.setenv("BSQ_FORCE_WIDE", "1")
+    rows = [text] if text is not None else synth.reference_rows([120_001, 80_003, 997], seed=55)
+    orc, gpu = build_pair(rows, O.sql_default_opts(len(rows)))
+    assert gpu.meta().sa_bytes == 8
+    _check_index(orc, gpu)
+    if text is None:
+        from helpers import compare_results
+        seqs, offs, _ = synth.simulate_reads(rows, 800, 150, seed=56)
+        ids = synth.lrand48_ids_fast(800)
+        bad = compare_results(gpu.align_batch(seqs, offs, ids), orc.align_batch(seqs, offs, ids, 2))
+        assert not bad, "\n".join(bad)

@@ -421,7 +421,9 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
     int* E = reinterpret_cast<int*>(dyn_smem) + NARROW_NC * NARROW_THREADS + tid;
     uint8_t* Q = dyn_smem + 2 * NARROW_NC * NARROW_THREADS * 4 + tid;               // Q[j * NARROW_THREADS]
     const uint32_t gwarp = (blockIdx.x * NARROW_THREADS + tid) >> 5;
-    uint8_t* Z = P.zbuf + (size_t)gwarp * ((size_t)NARROW_TMAX * NARROW_NC * 32) + lane;  // Z[(i * NC + jj) * 32]
+    // traceback bytes: thread-major rows of NARROW_NC bytes, written 8 cells at a time (a byte-per-store layout costs a
+    // 32-byte L2 sector per cell)
+    uint8_t* Z = P.zbuf + ((size_t)gwarp * 32 + lane) * ((size_t)NARROW_TMAX * NARROW_NC);   // Z[i * NC + jj]
     const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins, e_del = o.e_del, e_ins = o.e_ins;
     const int64_t l_pac = ix.l_pac;
     const uint32_t n_jobs = *P.n_jobs;
@@ -477,13 +479,19 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                             int f = KSW_NEG_INF;
                             const int tb = rev ? 3 - (int)pac_get(ix.pac, tbase + i) : (int)pac_get(ix.pac, tbase + i);
                             const int* mrow = smat + tb * 5;
-                            uint8_t* zi = Z + (size_t)i * NARROW_NC * 32;
+                            unsigned long long* zi = reinterpret_cast<unsigned long long*>(Z + (size_t)i * NARROW_NC);
                             cells += (unsigned long long)(end - beg);
+                            unsigned long long zpack = 0;
+                            // software pipeline: the loads of column j + 1 are issued before the dependent chain of column j
+                            int c = (beg & (NARROW_NC - 1)) * NARROW_THREADS;
+                            int m = 0, e = 0, sc = 0;
+                            if (beg < end) { m = H[c]; e = E[c]; sc = mrow[Q[beg * NARROW_THREADS]]; }
                             for (int j = beg; j < end; ++j) {
-                                const int c = (j & (NARROW_NC - 1)) * NARROW_THREADS;
-                                int m = H[c], e = E[c];
+                                const int cn = ((j + 1) & (NARROW_NC - 1)) * NARROW_THREADS;
+                                int mn = 0, en = 0, scn = 0;
+                                if (j + 1 < end) { mn = H[cn]; en = E[cn]; scn = mrow[Q[(j + 1) * NARROW_THREADS]]; }
                                 H[c] = h1;
-                                m += mrow[Q[j * NARROW_THREADS]];
+                                m += sc;
                                 int d = m >= e ? 0 : 1;
                                 int h = m >= e ? m : e;
                                 d = h >= f ? d : 2;
@@ -498,8 +506,12 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                                 f -= e_ins;
                                 d |= f > tt ? 2 << 4 : 0;
                                 f = f > tt ? f : tt;
-                                zi[(j - beg) * 32] = (uint8_t)d;
+                                const int jj = j - beg;
+                                zpack |= (unsigned long long)d << ((jj & 7) << 3);
+                                if ((jj & 7) == 7) { zi[jj >> 3] = zpack; zpack = 0; }
+                                c = cn; m = mn; e = en; sc = scn;
                             }
+                            if (((end - beg) & 7) != 0) zi[(end - beg) >> 3] = zpack;
                             const int ce = (end & (NARROW_NC - 1)) * NARROW_THREADS;
                             H[ce] = h1; E[ce] = KSW_NEG_INF;
                         }
@@ -513,7 +525,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                                 else cg[n_cigar - 1] += len << 4;
                             };
                             while (i >= 0 && k >= 0) {
-                                which = Z[((size_t)i * NARROW_NC + (k - (i > w ? i - w : 0))) * 32] >> (which << 1) & 3;
+                                which = Z[(size_t)i * NARROW_NC + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
                                 if (which == 0) { push(0, 1); --i; --k; }
                                 else if (which == 1) { push(2, 1); --i; }
                                 else { push(1, 1); --k; }

@@ -62,7 +62,7 @@ def workload(args, rank):
     rows = synth.reference_rows([per] * rows_n)
     seqs, offs, truth = synth.simulate_reads(rows, args.reads, 150, seed=synth.SEED_READS + rank)
     ids = synth.lrand48_ids_fast(args.reads)
-    return rows, seqs, offs, ids
+    return rows, seqs, offs, ids, truth
 
 
 def opts_tuple(args, n_rows):
@@ -124,7 +124,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import oracle_lib as O
-    rows, seqs, offs, ids = workload(args, 0)
+    rows, seqs, offs, ids, _truth = workload(args, 0)
     cores = os.cpu_count() or 1
     ot = opts_tuple(args, len(rows))
     orc = O.OracleIndex(O.Opts(*ot))
@@ -178,7 +178,7 @@ def run_ours(args, rank, world, local_rank):
     else:
         torch.cuda.set_device(0)
     dev = local_rank if world > 1 else 0
-    rows, seqs, offs, ids = workload(args, rank)
+    rows, seqs, offs, ids, truth = workload(args, rank)
     ot = opts_tuple(args, len(rows))
     ix = BwaIndex(dev, BsqOpts(*ot))
     bcast_bytes = 0
@@ -234,6 +234,13 @@ def run_ours(args, rank, world, local_rank):
     clocks = clk.summary()
     res = ix.download_result()
     total_rows = int(res.row_off[-1])
+    # sanity against the simulator's truth (parity is GPU vs oracle in tests/; this is a scale check): the first row of a
+    # read is its best hit -- same reference row, same strand, position within the indel slack
+    first = res.row_off[:-1].astype(np.int64)
+    has = np.diff(res.row_off.astype(np.int64)) > 0
+    pr = res.rows[np.minimum(first, max(total_rows - 1, 0))]
+    okk = has & (pr["rid"] == truth[0]) & (pr["is_rev"] == truth[2].astype(np.int32)) & (np.abs(pr["pos"] - truth[1]) <= 16)
+    truth_frac = float(okk.mean())
 
     # ---------------- e2e: host buffers through bsq_align_batch
     resp = C.POINTER(_lib.BsqResult)()
@@ -307,7 +314,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roof, "sw": sw,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "wall_ms_per_step": 1e3 * wall_max / args.steps,
-            "rows_per_step_rank0": total_rows,
+            "rows_per_step_rank0": total_rows, "truth_match_frac_rank0": truth_frac,
             "index": {"build_ms_device": meta.build_ms, "build_wall_s": build_wall, "build_launches": int(meta.build_launches),
                       "sort_pass_gbs": (meta.sort_pass_bytes / (meta.build_ms * 1e-3) / 1e9) if meta.build_ms else None,
                       "seq_len": int(meta.seq_len), "broadcast_bytes": bcast_bytes},

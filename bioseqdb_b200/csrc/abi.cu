@@ -52,7 +52,7 @@ struct Batch {
     DevBuf<ReadBlock> blocks; uint32_t pool_cap = 0;
     DevBuf<uint32_t> cigar; uint32_t cigar_cap = 0;
     DevBuf<double> read_logtab; uint32_t read_logtab_n = 0; uint32_t rseq_cap = 0;
-    DevBuf<uint8_t> ext_scratch, fin_scratch, narrow_z; DevBuf<uint64_t> narrow_jobs, wide_jobs;
+    DevBuf<uint8_t> ext_scratch, fin_scratch, narrow_z, narrow_jobs; DevBuf<uint64_t> wide_jobs;
     DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..23] counters (u64 x 8), [24] narrow_cnt, [25] wide_cnt, [26..27] tickets
     bool resident = false, aligned = false;
     void release() {
@@ -416,7 +416,7 @@ int run_pipeline(bsq_index* h) {
         ENS(b.ext_scratch.ensure((size_t)ext_warps * ext_per_warp)); ENS(b.fin_scratch.ensure((size_t)fin_warps * fin_per_warp));
         int narrow_warps = 0;
         const size_t narrow_bytes = narrow_zbuf_bytes(&narrow_warps);
-        ENS(b.narrow_z.ensure(narrow_bytes)); ENS(b.narrow_jobs.ensure(b.pool_cap)); ENS(b.wide_jobs.ensure(b.pool_cap));
+        ENS(b.narrow_z.ensure(narrow_bytes)); ENS(b.narrow_jobs.ensure((size_t)b.pool_cap * 2 * 24)); ENS(b.wide_jobs.ensure(b.pool_cap));
         ENS(b.ctl.ensure(64));
         ENS(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, h->stream));
         unsigned long long* ctr = h->collect_counters ? reinterpret_cast<unsigned long long*>(b.ctl.p + 8) : nullptr;
@@ -424,7 +424,7 @@ int run_pipeline(bsq_index* h) {
         {
             SeedParams P;
             P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = b.intv_cap;
-            P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = (b.max_len + 16) & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap); P.ticket = b.ctl.p + 0; P.overflow = b.ctl.p + 4; P.n_extend = ctr ? ctr + 0 : nullptr;
+            P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = (b.max_len + 16) & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p + 0; P.overflow = b.ctl.p + 4; P.n_extend = ctr ? ctr + 0 : nullptr;
             launch_seed(P, ix, o, h->stream, nullptr); ++T.launches;
         }
         cudaEventRecord(ev[1], h->stream);
@@ -450,8 +450,8 @@ int run_pipeline(bsq_index* h) {
             P.seqs = b.seqs.p; P.offs = b.offs.p; P.ids = b.ids.p; P.n_reads = n; P.blocks = b.blocks.p; P.regs = b.regs.p; P.reg_cnt = b.reg_cnt.p;
             P.rows = b.rows.p; P.row_cnt = b.row_cnt.p; P.cigar_pool = b.cigar.p; P.cigar_cap = b.cigar_cap; P.cigar_top = b.ctl.p + 6;
             P.scratch = b.fin_scratch.p; P.scratch_per_warp = fin_per_warp; P.max_len = max_len; P.z_cap = z_cap; P.ann_id = h->d_ann_id;
-            P.narrow_jobs = b.narrow_jobs.p; P.narrow_cnt = b.ctl.p + 24; P.wide_jobs = b.wide_jobs.p; P.wide_cnt = b.ctl.p + 25; P.narrow_z = b.narrow_z.p; P.narrow_warps = narrow_warps;
-            P.ticket = b.ctl.p + 26; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 6 : nullptr;
+            P.narrow_jobs = b.narrow_jobs.p; P.narrow_cap = b.pool_cap; P.narrow_cnt = b.ctl.p + 32; P.wide_jobs = b.wide_jobs.p; P.wide_cnt = b.ctl.p + 25; P.narrow_z = b.narrow_z.p; P.narrow_warps = narrow_warps;
+            P.ticket = b.ctl.p + 40; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 6 : nullptr;
             launch_finalize(P, ix, o, h->stream, rseq_cap, fin_warps, &T.launches);
         }
         // compact rows: exclusive scan of row_cnt (n + 1 entries, the last one is a zero pad) -> row_off
@@ -675,7 +675,7 @@ int bsq_debug_seed(bsq_index* h, const char* seqs, const uint64_t* offs, uint64_
     CUDA_CHECK(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, h->stream));
     SeedParams P;
     P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = (uint32_t)n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = cap;
-    P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = (b.max_len + 16) & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap); P.ticket = b.ctl.p; P.overflow = b.ctl.p + 4; P.n_extend = reinterpret_cast<unsigned long long*>(b.ctl.p + 8);
+    P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = (b.max_len + 16) & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p; P.overflow = b.ctl.p + 4; P.n_extend = reinterpret_cast<unsigned long long*>(b.ctl.p + 8);
     launch_seed(P, ix, h->dopts, h->stream, nullptr);
     uint32_t ctl[8];
     CUDA_CHECK(cudaMemcpyAsync(ctl, b.ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));

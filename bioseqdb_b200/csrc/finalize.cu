@@ -20,6 +20,8 @@ constexpr int NARROW_QMAX = 160;
 constexpr int NARROW_THREADS = 128;
 constexpr int NARROW_CIG = 48;
 
+struct NarrowJob { uint32_t r, slot; int32_t w2, last_sc, it, score; };   // one pending try of mem_reg2aln's band-doubling loop
+
 struct FScratch { int* ehh; int* ehe; uint8_t* rseq; uint8_t* query; uint8_t* z; uint32_t* cig; };
 
 __device__ __forceinline__ uint64_t hash_64(uint64_t key) {
@@ -192,7 +194,7 @@ __device__ __forceinline__ bool is_narrow_first_try(const DevOpts& o, const RegR
     if (max_len > NARROW_QMAX || lq <= 0 || rl <= 0 || rl > NARROW_TMAX) return false;
     int w2 = reg2aln_w2(o, ar);
     w2 = w2 < o.w << 2 ? w2 : o.w << 2;
-    if (lq == rl && w2 == 0) return true;
+    if (lq == rl && w2 == 0) return false;   // no DP at all: the warp does the 150-base score sum inline
     return 2 * gen_cigar_band(o, lq, (int)rl, w2) + 1 <= NARROW_NC;
 }
 
@@ -387,7 +389,11 @@ __global__ void __launch_bounds__(FIN_THREADS) regs_finalize(FinalizeParams P, D
             const bool narrow = P.narrow_jobs != nullptr && is_narrow_first_try(o, ar, P.max_len);
             if (lane == 0) {
                 rows[i] = row;
-                if (narrow) { uint32_t k = atomicAdd(P.narrow_cnt, 1u); P.narrow_jobs[k] = (uint64_t)r << 32 | (uint64_t)(blk.base + i); }
+                if (narrow) {
+                    const uint32_t k = atomicAdd(P.narrow_cnt, 1u);
+                    NarrowJob jb; jb.r = r; jb.slot = blk.base + i; jb.w2 = reg2aln_w2(o, ar); jb.last_sc = -(1 << 30); jb.it = 0; jb.score = 0;
+                    reinterpret_cast<NarrowJob*>(P.narrow_jobs)[k] = jb;
+                }
             }
             __syncwarp();
             if (!narrow) reg2aln_warp(P, ix, o, smat, S, cig_cap, rseq_cap, l_query, ar, rows + i, cells, calls);
@@ -406,7 +412,7 @@ __global__ void __launch_bounds__(FIN_THREADS) regs_finalize(FinalizeParams P, D
 // A region whose retry needs a wider band is handed to regs_cigar_wide (warp-cooperative rows).
 struct NarrowParams {
     const uint8_t* seqs; const uint64_t* offs; const RegRec* regs; RowDev* rows;
-    const uint64_t* jobs; const uint32_t* n_jobs; uint64_t* wide_jobs; uint32_t* wide_cnt;
+    const NarrowJob* jobs; const uint32_t* n_jobs; NarrowJob* requeue; uint32_t* requeue_cnt; uint64_t* wide_jobs; uint32_t* wide_cnt;
     uint32_t* cigar_pool; uint32_t cigar_cap; uint32_t* cigar_top;
     uint8_t* zbuf; uint32_t* ticket; uint32_t* overflow; unsigned long long* counters;
 };
@@ -421,9 +427,8 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
     int* E = reinterpret_cast<int*>(dyn_smem) + NARROW_NC * NARROW_THREADS + tid;
     uint8_t* Q = dyn_smem + 2 * NARROW_NC * NARROW_THREADS * 4 + tid;               // Q[j * NARROW_THREADS]
     const uint32_t gwarp = (blockIdx.x * NARROW_THREADS + tid) >> 5;
-    // traceback bytes: thread-major rows of NARROW_NC bytes, written 8 cells at a time (a byte-per-store layout costs a
-    // 32-byte L2 sector per cell)
-    uint8_t* Z = P.zbuf + ((size_t)gwarp * 32 + lane) * ((size_t)NARROW_TMAX * NARROW_NC);   // Z[i * NC + jj]
+    // traceback bytes, 8 cells per 64-bit store, laid out [row][8-cell group][lane]: a warp store is 256 contiguous bytes
+    unsigned long long* Z = reinterpret_cast<unsigned long long*>(P.zbuf + (size_t)gwarp * ((size_t)NARROW_TMAX * NARROW_NC * 32)) + lane;
     const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins, e_del = o.e_del, e_ins = o.e_ins;
     const int64_t l_pac = ix.l_pac;
     const uint32_t n_jobs = *P.n_jobs;
@@ -433,8 +438,9 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
         if ((uint64_t)t * 32 >= n_jobs) break;
         const uint32_t j_id = t * 32 + lane;
         if (j_id < n_jobs) {
-            const uint64_t job = P.jobs[j_id];
-            const uint32_t r = (uint32_t)(job >> 32), slot = (uint32_t)job;
+            const NarrowJob jb = P.jobs[j_id];
+            const uint32_t r = jb.r, slot = jb.slot;
+            const uint64_t job = (uint64_t)r << 32 | slot;
             const RegRec ar = P.regs[slot];
             const int l_read = (int)(P.offs[r + 1] - P.offs[r]);
             const int qb = ar.qb, qe = ar.qe, lq = qe - qb;
@@ -449,11 +455,12 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                 for (int j = 0; j < lq; ++j) Q[j * NARROW_THREADS] = rev ? qg[lq - 1 - j] : qg[j];
             }
             uint32_t cg[NARROW_CIG];
-            int n_cigar = 0, NM = -1, score = 0, last_sc = -(1 << 30), it = 0;
-            int w2 = reg2aln_w2(o, ar);
-            bool go_wide = false;
+            // ONE try of the band-doubling loop per pass; a region that needs another try is re-queued so that the
+            // lanes of a warp stay balanced (the loop state travels in the job record)
+            int n_cigar = 0, NM = -1, score = jb.score;
+            int w2 = jb.w2 < o.w << 2 ? jb.w2 : o.w << 2;
+            bool go_wide = false, again = false;
             do {
-                w2 = w2 < o.w << 2 ? w2 : o.w << 2;
                 n_cigar = 0; NM = -1;
                 if (!reject) {
                     if (lq == rlen && w2 == 0) {
@@ -479,19 +486,14 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                             int f = KSW_NEG_INF;
                             const int tb = rev ? 3 - (int)pac_get(ix.pac, tbase + i) : (int)pac_get(ix.pac, tbase + i);
                             const int* mrow = smat + tb * 5;
-                            unsigned long long* zi = reinterpret_cast<unsigned long long*>(Z + (size_t)i * NARROW_NC);
+                            unsigned long long* zi = Z + (size_t)i * (NARROW_NC / 8) * 32;
                             cells += (unsigned long long)(end - beg);
                             unsigned long long zpack = 0;
-                            // software pipeline: the loads of column j + 1 are issued before the dependent chain of column j
-                            int c = (beg & (NARROW_NC - 1)) * NARROW_THREADS;
-                            int m = 0, e = 0, sc = 0;
-                            if (beg < end) { m = H[c]; e = E[c]; sc = mrow[Q[beg * NARROW_THREADS]]; }
                             for (int j = beg; j < end; ++j) {
-                                const int cn = ((j + 1) & (NARROW_NC - 1)) * NARROW_THREADS;
-                                int mn = 0, en = 0, scn = 0;
-                                if (j + 1 < end) { mn = H[cn]; en = E[cn]; scn = mrow[Q[(j + 1) * NARROW_THREADS]]; }
+                                const int c = (j & (NARROW_NC - 1)) * NARROW_THREADS;
+                                int m = H[c], e = E[c];
                                 H[c] = h1;
-                                m += sc;
+                                m += mrow[Q[j * NARROW_THREADS]];
                                 int d = m >= e ? 0 : 1;
                                 int h = m >= e ? m : e;
                                 d = h >= f ? d : 2;
@@ -508,10 +510,9 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                                 f = f > tt ? f : tt;
                                 const int jj = j - beg;
                                 zpack |= (unsigned long long)d << ((jj & 7) << 3);
-                                if ((jj & 7) == 7) { zi[jj >> 3] = zpack; zpack = 0; }
-                                c = cn; m = mn; e = en; sc = scn;
+                                if ((jj & 7) == 7) { zi[(jj >> 3) * 32] = zpack; zpack = 0; }
                             }
-                            if (((end - beg) & 7) != 0) zi[(end - beg) >> 3] = zpack;
+                            if (((end - beg) & 7) != 0) zi[((end - beg) >> 3) * 32] = zpack;
                             const int ce = (end & (NARROW_NC - 1)) * NARROW_THREADS;
                             H[ce] = h1; E[ce] = KSW_NEG_INF;
                         }
@@ -525,7 +526,8 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                                 else cg[n_cigar - 1] += len << 4;
                             };
                             while (i >= 0 && k >= 0) {
-                                which = Z[(size_t)i * NARROW_NC + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
+                                const int jj = k - (i > w ? i - w : 0);
+                                which = (int)(Z[((size_t)i * (NARROW_NC / 8) + (jj >> 3)) * 32] >> ((jj & 7) << 3) & 0xff) >> (which << 1) & 3;
                                 if (which == 0) { push(0, 1); --i; --k; }
                                 else if (which == 1) { push(2, 1); --i; }
                                 else { push(1, 1); --k; }
@@ -552,14 +554,17 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                     }
                     NM = n_mm + n_gap;
                 }
-                if (score == last_sc || w2 == o.w << 2) break;
-                last_sc = score;
-                w2 <<= 1;
-            } while (++it < 3 && score < ar.truesc - o.a);
+                if (score == jb.last_sc || w2 == o.w << 2) break;
+                if (jb.it + 1 < 3 && score < ar.truesc - o.a) {
+                    again = true;
+                    NarrowJob nx; nx.r = r; nx.slot = slot; nx.w2 = w2 << 1; nx.last_sc = score; nx.it = jb.it + 1; nx.score = score;
+                    P.requeue[atomicAdd(P.requeue_cnt, 1u)] = nx;
+                }
+            } while (false);
             if (go_wide) {
                 uint32_t k = atomicAdd(P.wide_cnt, 1u);
                 P.wide_jobs[k] = job;
-            } else {
+            } else if (!again) {
                 int is_rev;
                 int64_t pos = bns_depos(ix, rb < l_pac ? rb : re - 1, &is_rev);
                 int nc = n_cigar, first = 0;
@@ -683,23 +688,29 @@ void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts&
     else regs_finalize<false><<<blocks, FIN_THREADS, 0, st>>>(p, ix, o, cig_cap, rseq_cap);
     if (launches) ++*launches;
     if (!p.narrow_jobs) return;
-    // phase 2: thread-per-region narrow-band mem_reg2aln
+    // phase 2: thread-per-region narrow-band mem_reg2aln, one try of the band-doubling loop per pass (<= 3 tries)
     {
         int warps = 0;
         narrow_zbuf_bytes(&warps);
         if (warps > p.narrow_warps) warps = p.narrow_warps;
-        NarrowParams q;
-        q.seqs = p.seqs; q.offs = p.offs; q.regs = p.regs; q.rows = p.rows; q.jobs = p.narrow_jobs; q.n_jobs = p.narrow_cnt;
-        q.wide_jobs = p.wide_jobs; q.wide_cnt = p.wide_cnt; q.cigar_pool = p.cigar_pool; q.cigar_cap = p.cigar_cap; q.cigar_top = p.cigar_top;
-        q.zbuf = p.narrow_z; q.ticket = p.ticket + 1; q.overflow = p.overflow; q.counters = p.counters;
+        NarrowJob* listA = reinterpret_cast<NarrowJob*>(p.narrow_jobs);
+        NarrowJob* listB = listA + p.narrow_cap;
         const size_t nsmem = (size_t)NARROW_THREADS * (2 * NARROW_NC * 4 + NARROW_QMAX);
-        regs_cigar_narrow<<<warps / (NARROW_THREADS / 32), NARROW_THREADS, nsmem, st>>>(q, ix, o);
-        if (launches) ++*launches;
+        for (int pass = 0; pass < 3; ++pass) {
+            NarrowParams q;
+            q.seqs = p.seqs; q.offs = p.offs; q.regs = p.regs; q.rows = p.rows;
+            q.jobs = (pass & 1) ? listB : listA; q.n_jobs = p.narrow_cnt + pass;
+            q.requeue = (pass & 1) ? listA : listB; q.requeue_cnt = p.narrow_cnt + pass + 1;   // pass 2 never re-queues (it + 1 == 3)
+            q.wide_jobs = p.wide_jobs; q.wide_cnt = p.wide_cnt; q.cigar_pool = p.cigar_pool; q.cigar_cap = p.cigar_cap; q.cigar_top = p.cigar_top;
+            q.zbuf = p.narrow_z; q.ticket = p.ticket + 1 + pass; q.overflow = p.overflow; q.counters = p.counters;
+            regs_cigar_narrow<<<warps / (NARROW_THREADS / 32), NARROW_THREADS, nsmem, st>>>(q, ix, o);
+            if (launches) ++*launches;
+        }
     }
     // phase 3: whatever needed a wider band on a retry
     {
         FinalizeParams w = p;
-        w.ticket = p.ticket + 2;
+        w.ticket = p.ticket + 4;
         if (smem_ok) regs_cigar_wide<true><<<blocks, FIN_THREADS, smem, st>>>(w, ix, o, cig_cap, rseq_cap);
         else regs_cigar_wide<false><<<blocks, FIN_THREADS, 0, st>>>(w, ix, o, cig_cap, rseq_cap);
         if (launches) ++*launches;

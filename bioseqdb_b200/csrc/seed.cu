@@ -3,13 +3,14 @@
 // the same interval registers; the lanes split the two 64-byte Occ blocks of a bwt_extend (one coalesced
 // warp load: lanes 0-15 -> block of row k, lanes 16-31 -> block of row l).
 //
-// Fast path (text shorter than 2^32 rows): only the child interval of the ONE base being extended is ever
-// needed, and it is three sums over the 32 lanes --
-//     x2' = sum_l contrib_c - sum_k contrib_c,   S = sum over symbols > c of the same,   tk[c] = sum_k contrib_c
-// where a lane's contribution is its count word (lanes holding the checkpoint of symbol c) or the popcount
-// of its masked symbol word.  Each sum is ONE redux.sync (warp vote/reduce hardware), so a bwt_extend costs
-// one load, two popcounts and three reductions per lane.  Interval lists live in shared memory.
-// The wide path (>= 2^32 rows) keeps the shuffle-based occ4_pair of seed.cuh.
+// Only the child interval of the ONE base being extended is ever needed, and it is a few sums over the 32
+// lanes --
+//     x2' = sum_l eq - sum_k eq,   S = sum_l gt - sum_k gt (symbols > c, for the cumulative side),   tk[c] = sum_k eq
+// where a lane contributes its checkpoint word (lanes holding the checkpoint of symbol c) or the popcount of
+// its masked symbol word.  Each sum is ONE redux.sync (warp reduce hardware): a bwt_extend costs one load,
+// two popcounts and three reductions per lane.  Texts of 2^32 rows or more keep row indices in 64 bits; x2'
+// and S still fit 32 bits (they are bounded by the parent interval), only tk[c] needs its checkpoint's two
+// halves, i.e. two more single-contributor reductions.  Interval lists and the read live in shared memory.
 #include "seed.cuh"
 
 namespace {
@@ -17,25 +18,26 @@ namespace {
 constexpr int SEED_THREADS = 256;
 constexpr int SEED_WARPS = SEED_THREADS / 32;
 
-struct __align__(16) Iv32 { uint32_t x0, x1, x2, info; };   // info = end of the match on the query
+template <class IdxT> struct IvT { IdxT x0, x1; uint32_t x2, info; };   // info = end of the match on the query
+template <> struct __align__(16) IvT<uint32_t> { uint32_t x0, x1, x2, info; };
 
-// warp-private context of the narrow path: everything the extend needs without touching the kernel
-// parameter block dynamically (a dynamically indexed parameter array is spilled to local memory)
-struct Ctx32 {
+// warp-private context: everything the extend needs without indexing the kernel parameter block dynamically
+// (a dynamically indexed parameter array is spilled to local memory)
+template <class IdxT> struct Ctx {
     const uint32_t* occ;
-    const uint32_t* sL2;     // shared memory: L2[0..4] as u32
-    uint32_t primary;
-    // per-lane constants
-    uint32_t sym_base;       // first symbol covered by this lane's word (symbol lanes), 1 << 20 for count lanes
-    int cnt_sym;             // symbol whose checkpoint low word this lane holds, -1 otherwise
+    const IdxT* sL2;         // shared memory: L2[0..4]
+    IdxT primary;
+    uint32_t sym_base;       // first symbol covered by this lane's word (symbol lanes), 1 << 20 for checkpoint lanes
+    int cnt_sym;             // symbol whose checkpoint LOW word this lane holds, -1 otherwise
+    int cnt_hi;              // symbol whose checkpoint HIGH word this lane holds, -1 otherwise
     bool lhalf;              // lanes 16-31 read the block of row l
 };
 
-// child interval of `ik` for base c (see file header).  IS_BACK selects which of x0/x1 plays "k".
-template <int IS_BACK>
-__device__ __forceinline__ Iv32 extend32(const Ctx32& C, const Iv32& ik, int c) {
-    const uint32_t xo = IS_BACK ? ik.x0 : ik.x1, xb = IS_BACK ? ik.x1 : ik.x0;
-    uint32_t pos = xo - 1 + (C.lhalf ? ik.x2 : 0u);
+// child interval of `ik` for base c.  IS_BACK selects which of x0/x1 plays "k" (SURVEY A.2 bwt_extend).
+template <class IdxT, int IS_BACK>
+__device__ __forceinline__ IvT<IdxT> extend1(const Ctx<IdxT>& C, const IvT<IdxT>& ik, int c) {
+    const IdxT xo = IS_BACK ? ik.x0 : ik.x1, xb = IS_BACK ? ik.x1 : ik.x0;
+    IdxT pos = xo - 1 + (C.lhalf ? (IdxT)ik.x2 : (IdxT)0);
     pos -= (pos >= C.primary);
     const uint32_t word = __ldg(C.occ + ((size_t)(pos >> 7) << 4) + (lane_id() & 15));
     // symbol lanes: count symbols == c and > c among the first nsym symbols of the word (branch-free)
@@ -46,48 +48,57 @@ __device__ __forceinline__ Iv32 extend32(const Ctx32& C, const Iv32& ik, int c) 
     const uint32_t hx = ~((word >> 1) ^ C1);          // hi bit equals c's hi bit
     const uint32_t eqm = hx & ~(word ^ C0) & keep;
     const uint32_t gtm = (((word >> 1) & ~C1) | (hx & word & ~C0)) & keep;
-    int eq = __popc(eqm), gt = __popc(gtm);
+    const int pop_eq = __popc(eqm);
+    int eq = pop_eq, gt = __popc(gtm);
     if (C.cnt_sym >= 0) { eq = C.cnt_sym == c ? (int)word : 0; gt = C.cnt_sym > c ? (int)word : 0; }
     const int sz = __reduce_add_sync(FULL, C.lhalf ? eq : -eq);
     const int S = __reduce_add_sync(FULL, C.lhalf ? gt : -gt);
-    const int tk = __reduce_add_sync(FULL, C.lhalf ? 0 : eq);
-    const uint32_t no = C.sL2[c] + 1u + (uint32_t)tk;
-    const uint32_t nb = xb + (uint32_t)(xo <= C.primary && xo + ik.x2 - 1 >= C.primary) + (uint32_t)S;
-    Iv32 ok;
+    IdxT tk;
+    if (sizeof(IdxT) == 4) tk = (IdxT)(uint32_t)__reduce_add_sync(FULL, C.lhalf ? 0 : eq);
+    else {   // exactly one lane contributes to each of the two halves of the 64-bit checkpoint
+        const uint32_t lo = __reduce_add_sync(FULL, (!C.lhalf && C.cnt_sym == c) ? word : 0u);
+        const uint32_t hi = __reduce_add_sync(FULL, (!C.lhalf && C.cnt_hi == c) ? word : 0u);
+        const uint32_t pp = __reduce_add_sync(FULL, (!C.lhalf && C.cnt_sym < 0) ? (uint32_t)pop_eq : 0u);
+        tk = (IdxT)(((unsigned long long)hi << 32 | lo) + pp);
+    }
+    const IdxT no = C.sL2[c] + 1 + tk;
+    const IdxT nb = xb + (IdxT)(xo <= C.primary && xo + ik.x2 - 1 >= C.primary) + (IdxT)(uint32_t)S;
+    IvT<IdxT> ok;
     ok.x0 = IS_BACK ? no : nb; ok.x1 = IS_BACK ? nb : no; ok.x2 = (uint32_t)sz; ok.info = ik.info;
     return ok;
 }
 
-__device__ __forceinline__ Iv32 set_intv32(const Ctx32& C, int c) {
-    Iv32 ik;
-    ik.x0 = C.sL2[c] + 1; ik.x1 = C.sL2[3 - c] + 1; ik.x2 = C.sL2[c + 1] - C.sL2[c]; ik.info = 0;
+template <class IdxT> __device__ __forceinline__ IvT<IdxT> set_intv(const Ctx<IdxT>& C, int c) {
+    IvT<IdxT> ik;
+    ik.x0 = C.sL2[c] + 1; ik.x1 = C.sL2[3 - c] + 1; ik.x2 = (uint32_t)(C.sL2[c + 1] - C.sL2[c]); ik.info = 0;
     return ik;
 }
 
 struct Out { Intv* out; uint32_t n, cap; bool ovf; };
 
-__device__ __forceinline__ void emit(Out& O, const Iv32& p, uint32_t start, uint32_t end) {
+template <class IdxT> __device__ __forceinline__ void emit(Out& O, const IvT<IdxT>& p, uint32_t start, uint32_t end) {
     if (O.n < O.cap) {
         if (lane_id() == 0) { Intv v; v.x0 = p.x0; v.x1 = p.x1; v.x2 = p.x2; v.info = (uint64_t)start << 32 | end; O.out[O.n] = v; }
     } else O.ovf = true;
     ++O.n;
 }
 
-// bwt_smem1a with max_intv == 0.  la/lb: two interval lists of list_cap entries; q: the read (nt4).
-__device__ __forceinline__ int smem1_32(const Ctx32& C, const DevOpts& o, int len, const uint8_t* q, int x, uint32_t min_intv, Iv32* la, Iv32* lb,
-                                        uint32_t list_cap, Out& O, unsigned long long& n_ext) {
+// bwt_smem1a with max_intv == 0 (the only way this path calls it).  la/lb: two interval lists of list_cap entries.
+template <class IdxT>
+__device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int len, const uint8_t* q, int x, uint32_t min_intv, IvT<IdxT>* la,
+                                     IvT<IdxT>* lb, uint32_t list_cap, Out& O, unsigned long long& n_ext) {
     if (q[x] > 3) return x + 1;
     if (min_intv < 1) min_intv = 1;
     const int lane = lane_id();
-    Iv32 ik = set_intv32(C, q[x]);
+    IvT<IdxT> ik = set_intv(C, q[x]);
     ik.info = (uint32_t)(x + 1);
-    Iv32* curr = la; Iv32* prev = lb;
+    IvT<IdxT>* curr = la; IvT<IdxT>* prev = lb;
     uint32_t n_curr = 0;
     int i;
     for (i = x + 1; i < len; ++i) {
         const int b = q[i];
         if (b < 4) {
-            Iv32 ok = extend32<0>(C, ik, 3 - b); ++n_ext;
+            IvT<IdxT> ok = extend1<IdxT, 0>(C, ik, 3 - b); ++n_ext;
             if (ok.x2 != ik.x2) {
                 if (n_curr < list_cap) { if (lane == 0) curr[n_curr] = ik; } else O.ovf = true;
                 ++n_curr;
@@ -104,7 +115,7 @@ __device__ __forceinline__ int smem1_32(const Ctx32& C, const DevOpts& o, int le
     if (n_curr > list_cap) n_curr = list_cap;
     __syncwarp();
     const int ret = (int)curr[n_curr - 1].info;     // the list is consumed backwards (longest match first)
-    { Iv32* t = curr; curr = prev; prev = t; }
+    { IvT<IdxT>* t = curr; curr = prev; prev = t; }
     uint32_t n_prev = n_curr; bool reversed = true;
     const uint32_t out_first = O.n;
     bool have_mem = false; uint32_t last_mem_start = 0;
@@ -113,9 +124,9 @@ __device__ __forceinline__ int smem1_32(const Ctx32& C, const DevOpts& o, int le
         n_curr = 0;
         uint32_t last_x2 = 0;
         for (uint32_t j = 0; j < n_prev; ++j) {
-            const Iv32 p = prev[reversed ? n_prev - 1 - j : j];
-            Iv32 ok; ok.x2 = 0;
-            if (c >= 0) { ok = extend32<1>(C, p, c); ++n_ext; }
+            const IvT<IdxT> p = prev[reversed ? n_prev - 1 - j : j];
+            IvT<IdxT> ok; ok.x2 = 0;
+            if (c >= 0) { ok = extend1<IdxT, 1>(C, p, c); ++n_ext; }
             if (c < 0 || ok.x2 < min_intv) {
                 if (n_curr == 0) {
                     if (!have_mem || (uint32_t)(i + 1) < last_mem_start) {
@@ -131,7 +142,7 @@ __device__ __forceinline__ int smem1_32(const Ctx32& C, const DevOpts& o, int le
         }
         if (n_curr == 0) break;
         __syncwarp();
-        { Iv32* t = curr; curr = prev; prev = t; }
+        { IvT<IdxT>* t = curr; curr = prev; prev = t; }
         n_prev = n_curr; reversed = false;
     }
     // emitted in decreasing start order: reverse the appended segment
@@ -150,13 +161,15 @@ __device__ __forceinline__ int smem1_32(const Ctx32& C, const DevOpts& o, int le
     return ret;
 }
 
-__device__ __forceinline__ int seed_strategy1_32(const Ctx32& C, int len, const uint8_t* q, int x, int min_len, uint32_t max_intv, Out& O, unsigned long long& n_ext) {
+template <class IdxT>
+__device__ __forceinline__ int seed_strategy1(const Ctx<IdxT>& C, int len, const uint8_t* q, int x, int min_len, uint32_t max_intv, Out& O,
+                                              unsigned long long& n_ext) {
     if (q[x] > 3) return x + 1;
-    Iv32 ik = set_intv32(C, q[x]);
+    IvT<IdxT> ik = set_intv(C, q[x]);
     for (int i = x + 1; i < len; ++i) {
         const int b = q[i];
         if (b < 4) {
-            Iv32 ok = extend32<0>(C, ik, 3 - b); ++n_ext;
+            IvT<IdxT> ok = extend1<IdxT, 0>(C, ik, 3 - b); ++n_ext;
             if (ok.x2 < max_intv && i - x >= min_len) {
                 if (ok.x2 > 0) emit(O, ok, (uint32_t)x, (uint32_t)(i + 1));
                 return i + 1;
@@ -167,12 +180,13 @@ __device__ __forceinline__ int seed_strategy1_32(const Ctx32& C, int len, const 
     return len;
 }
 
-// the three passes of mem_collect_intv for one read on the narrow path
-__device__ __forceinline__ void collect_intv_32(const Ctx32& C, const DevOpts& o, int len, const uint8_t* q, Iv32* la, Iv32* lb, uint32_t list_cap,
-                                                Out& O, unsigned long long& n_ext) {
+// the three passes of mem_collect_intv for one read
+template <class IdxT>
+__device__ __forceinline__ void collect_intv(const Ctx<IdxT>& C, const DevOpts& o, int len, const uint8_t* q, IvT<IdxT>* la, IvT<IdxT>* lb,
+                                             uint32_t list_cap, Out& O, unsigned long long& n_ext) {
     int x = 0;
     while (x < len) {      // pass 1: all SMEMs
-        if (q[x] < 4) x = smem1_32(C, o, len, q, x, 1, la, lb, list_cap, O, n_ext);
+        if (q[x] < 4) x = smem1(C, o, len, q, x, 1, la, lb, list_cap, O, n_ext);
         else ++x;
     }
     const uint32_t old_n = O.n < O.cap ? O.n : O.cap;
@@ -180,114 +194,15 @@ __device__ __forceinline__ void collect_intv_32(const Ctx32& C, const DevOpts& o
         const Intv p = O.out[k];
         const int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
         if (end - start < o.split_len || p.x2 > (uint64_t)o.split_width) continue;
-        smem1_32(C, o, len, q, (start + end) >> 1, (uint32_t)p.x2 + 1, la, lb, list_cap, O, n_ext);
+        smem1(C, o, len, q, (start + end) >> 1, (uint32_t)p.x2 + 1, la, lb, list_cap, O, n_ext);
     }
     if (o.max_mem_intv > 0) {                // pass 3: LAST-like
         x = 0;
         while (x < len) {
-            if (q[x] < 4) x = seed_strategy1_32(C, len, q, x, o.min_seed_len, (uint32_t)o.max_mem_intv, O, n_ext);
+            if (q[x] < 4) x = seed_strategy1(C, len, q, x, o.min_seed_len, (uint32_t)o.max_mem_intv, O, n_ext);
             else ++x;
         }
     }
-}
-
-// ---------------------------------------------------------------- wide path (>= 2^32 rows): 64-bit records
-struct WarpLists { Intv* a; Intv* b; Intv* m; };
-__device__ __forceinline__ void put(Intv* dst, const Intv& v) { if (lane_id() == 0) *dst = v; }
-
-__device__ int smem1_64(const DevIndex& ix, const DevOpts& o, int len, const uint8_t* q, int x, uint64_t min_intv, const WarpLists& L,
-                        uint32_t list_cap, Intv* out, uint32_t& n_out, uint32_t cap, bool& ovf, unsigned long long& n_ext) {
-    if (q[x] > 3) return x + 1;
-    if (min_intv < 1) min_intv = 1;
-    Intv ik, ok[4];
-    bwt_set_intv(ix, q[x], ik);
-    ik.info = (uint64_t)(x + 1);
-    Intv* curr = L.a; Intv* prev = L.b;
-    uint32_t n_curr = 0;
-    int i;
-    for (i = x + 1; i < len; ++i) {
-        int b = q[i];
-        if (b < 4) {
-            int c = 3 - b;
-            bwt_extend<0>(ix, ik, ok); ++n_ext;
-            if (ok[c].x2 != ik.x2) {
-                if (n_curr < list_cap) put(curr + n_curr, ik); else ovf = true;
-                ++n_curr;
-                if (ok[c].x2 < min_intv) break;
-            }
-            ik = ok[c]; ik.info = (uint64_t)(i + 1);
-        } else {
-            if (n_curr < list_cap) put(curr + n_curr, ik); else ovf = true;
-            ++n_curr;
-            break;
-        }
-    }
-    if (i == len) { if (n_curr < list_cap) put(curr + n_curr, ik); else ovf = true; ++n_curr; }
-    if (n_curr > list_cap) n_curr = list_cap;
-    __syncwarp();
-    int ret = (int)(uint32_t)curr[n_curr - 1].info;
-    { Intv* t = curr; curr = prev; prev = t; }
-    uint32_t n_prev = n_curr; bool prev_reversed = true;
-    uint32_t n_mem = 0; uint64_t last_mem_start = 0;
-    for (i = x - 1; i >= -1; --i) {
-        int c = i < 0 ? -1 : (q[i] < 4 ? q[i] : -1);
-        n_curr = 0;
-        uint64_t last_x2 = 0;
-        for (uint32_t j = 0; j < n_prev; ++j) {
-            Intv p = prev[prev_reversed ? n_prev - 1 - j : j];
-            if (c >= 0) { bwt_extend<1>(ix, p, ok); ++n_ext; }
-            if (c < 0 || ok[c].x2 < min_intv) {
-                if (n_curr == 0) {
-                    if (n_mem == 0 || (uint64_t)(i + 1) < last_mem_start) {
-                        p.info |= (uint64_t)(i + 1) << 32;
-                        if (n_mem < list_cap) put(L.m + n_mem, p); else ovf = true;
-                        ++n_mem; last_mem_start = (uint64_t)(i + 1);
-                    }
-                }
-            } else if (n_curr == 0 || ok[c].x2 != last_x2) {
-                ok[c].info = p.info;
-                put(curr + n_curr, ok[c]);
-                ++n_curr; last_x2 = ok[c].x2;
-            }
-        }
-        if (n_curr == 0) break;
-        __syncwarp();
-        { Intv* t = curr; curr = prev; prev = t; }
-        n_prev = n_curr; prev_reversed = false;
-    }
-    if (n_mem > list_cap) n_mem = list_cap;
-    __syncwarp();
-    for (uint32_t k = 0; k < n_mem; ++k) {
-        Intv p = L.m[n_mem - 1 - k];
-        int slen = (int)((uint32_t)p.info - (uint32_t)(p.info >> 32));
-        if (slen >= o.min_seed_len) {
-            if (n_out < cap) put(out + n_out, p); else ovf = true;
-            ++n_out;
-        }
-    }
-    __syncwarp();
-    return ret;
-}
-
-__device__ int seed_strategy1_64(const DevIndex& ix, int len, const uint8_t* q, int x, int min_len, uint64_t max_intv, Intv& mem, unsigned long long& n_ext) {
-    mem.x0 = mem.x1 = mem.x2 = mem.info = 0;
-    if (q[x] > 3) return x + 1;
-    Intv ik, ok[4];
-    bwt_set_intv(ix, q[x], ik);
-    for (int i = x + 1; i < len; ++i) {
-        int b = q[i];
-        if (b < 4) {
-            int c = 3 - b;
-            bwt_extend<0>(ix, ik, ok); ++n_ext;
-            if (ok[c].x2 < max_intv && i - x >= min_len) {
-                mem = ok[c];
-                mem.info = (uint64_t)x << 32 | (uint64_t)(i + 1);
-                return i + 1;
-            }
-            ik = ok[c];
-        } else return i + 1;
-    }
-    return len;
 }
 
 // sort a read's intervals by info (ties are bit-identical records, so any correct sort equals ks_introsort's result)
@@ -325,88 +240,74 @@ __device__ void sort_by_info(Intv* out, uint32_t n_out, Intv* tmp, uint32_t tmp_
     __syncwarp();
 }
 
-// MODE 0: narrow path, lists and the read staged in shared memory; 1: narrow path, lists in global scratch
-// (reads too long for shared memory); 2: wide path (>= 2^32 rows)
-template <int MODE>
-__global__ void __launch_bounds__(SEED_THREADS, MODE == 0 ? 5 : 1) seed_smem(SeedParams P, DevIndex ix, DevOpts o) {
+// IdxT = uint32_t while the text has fewer than 2^32 rows; SMEM: interval lists and the read staged in shared
+// memory (otherwise in the per-warp global scratch: reads too long for shared memory)
+template <class IdxT, bool SMEM>
+__global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 5 : 1) seed_smem(SeedParams P, DevIndex ix, DevOpts o) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
-    __shared__ uint32_t sL2[8];
-    if (threadIdx.x < 5) sL2[threadIdx.x] = (uint32_t)ix.L2[threadIdx.x];
+    __shared__ IdxT sL2[8];
+    if (threadIdx.x < 5) sL2[threadIdx.x] = (IdxT)ix.L2[threadIdx.x];
     __syncthreads();
+    using Iv = IvT<IdxT>;
     const int lane = lane_id();
     const uint32_t gwarp = (blockIdx.x * SEED_THREADS + threadIdx.x) >> 5;
-    Intv* gl = P.scratch + (size_t)gwarp * 3 * P.list_cap;     // global scratch: wide-path lists, big-sort buffer
+    Intv* gl = P.scratch + (size_t)gwarp * 3 * P.list_cap;     // global scratch: lists of long reads, big-sort buffer
     unsigned long long n_ext = 0;
-    Ctx32 C;
-    C.occ = ix.occ; C.sL2 = sL2; C.primary = (uint32_t)ix.primary;
+    Ctx<IdxT> C;
+    C.occ = ix.occ; C.sL2 = sL2; C.primary = (IdxT)ix.primary;
     {
         const int idx = lane & 15;
         C.sym_base = idx >= 8 ? (uint32_t)((idx - 8) << 4) : (1u << 20);
         C.cnt_sym = (idx < 8 && !(idx & 1)) ? (idx >> 1) : -1;
+        C.cnt_hi = (idx < 8 && (idx & 1)) ? (idx >> 1) : -1;
         C.lhalf = (lane & 16) != 0;
-        // lanes holding the high half of a checkpoint act as symbol lanes with zero symbols: they contribute 0
+        // lanes holding the high half of a checkpoint act as symbol lanes with zero symbols: they contribute 0 to eq / gt
     }
-    Iv32* la = nullptr; Iv32* lb = nullptr; uint8_t* sq = nullptr;
-    if (MODE == 0) {
-        la = reinterpret_cast<Iv32*>(dyn_smem) + (size_t)(threadIdx.x >> 5) * 2 * P.list_cap; lb = la + P.list_cap;
-        sq = dyn_smem + (size_t)SEED_WARPS * 2 * P.list_cap * sizeof(Iv32) + (size_t)(threadIdx.x >> 5) * P.read_cap;
-    } else if (MODE == 1) { la = reinterpret_cast<Iv32*>(gl); lb = la + P.list_cap; }
+    Iv* la; Iv* lb; uint8_t* sq = nullptr;
+    if (SMEM) {
+        la = reinterpret_cast<Iv*>(dyn_smem) + (size_t)(threadIdx.x >> 5) * 2 * P.list_cap; lb = la + P.list_cap;
+        sq = dyn_smem + (size_t)SEED_WARPS * 2 * P.list_cap * sizeof(Iv) + (size_t)(threadIdx.x >> 5) * P.read_cap;
+    } else { la = reinterpret_cast<Iv*>(gl); lb = la + P.list_cap; }
     for (;;) {
         uint32_t r = next_ticket(P.ticket);
         if (r >= P.n_reads) break;
         const uint8_t* q = P.seqs + P.offs[r];
         const int len = (int)(P.offs[r + 1] - P.offs[r]);
-        Intv* out = P.out + (size_t)r * P.cap;
-        uint32_t n_out = 0; bool ovf = false;
+        Out O; O.out = P.out + (size_t)r * P.cap; O.n = 0; O.cap = P.cap; O.ovf = false;
         if (len >= o.min_seed_len) {   // mem_chain returns before seeding otherwise
-            if (MODE != 2) {
-                Out O; O.out = out; O.n = 0; O.cap = P.cap; O.ovf = false;
-                if (MODE == 0) {
-                    __syncwarp();
-                    for (int i = lane; i < len; i += 32) sq[i] = q[i];
-                    __syncwarp();
-                    collect_intv_32(C, o, len, sq, la, lb, P.list_cap, O, n_ext);
-                } else collect_intv_32(C, o, len, q, la, lb, P.list_cap, O, n_ext);
-                n_out = O.n; ovf = O.ovf;
-            } else {
-                WarpLists L; L.a = gl; L.b = gl + P.list_cap; L.m = L.b + P.list_cap;
-                int x = 0;
-                while (x < len) {
-                    if (q[x] < 4) x = smem1_64(ix, o, len, q, x, 1, L, P.list_cap, out, n_out, P.cap, ovf, n_ext);
-                    else ++x;
-                }
-                uint32_t old_n = n_out < P.cap ? n_out : P.cap;
-                for (uint32_t k = 0; k < old_n; ++k) {
-                    Intv p = out[k];
-                    int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
-                    if (end - start < o.split_len || p.x2 > (uint64_t)o.split_width) continue;
-                    smem1_64(ix, o, len, q, (start + end) >> 1, p.x2 + 1, L, P.list_cap, out, n_out, P.cap, ovf, n_ext);
-                }
-                if (o.max_mem_intv > 0) {
-                    x = 0;
-                    while (x < len) {
-                        if (q[x] < 4) {
-                            Intv m;
-                            x = seed_strategy1_64(ix, len, q, x, o.min_seed_len, (uint64_t)o.max_mem_intv, m, n_ext);
-                            if (m.x2 > 0) { if (n_out < P.cap) put(out + n_out, m); else ovf = true; ++n_out; }
-                        } else ++x;
-                    }
-                }
-            }
+            if (SMEM) {
+                __syncwarp();
+                for (int i = lane; i < len; i += 32) sq[i] = q[i];
+                __syncwarp();
+                collect_intv(C, o, len, sq, la, lb, P.list_cap, O, n_ext);
+            } else collect_intv(C, o, len, q, la, lb, P.list_cap, O, n_ext);
             __syncwarp();
         }
-        if (ovf || n_out > P.cap) { if (lane == 0) atomicExch(P.overflow, 1u); n_out = n_out < P.cap ? n_out : P.cap; }
-        sort_by_info(out, n_out, gl, 3 * P.list_cap, P.overflow);
+        uint32_t n_out = O.n;
+        if (O.ovf || n_out > P.cap) { if (lane == 0) atomicExch(P.overflow, 1u); n_out = n_out < P.cap ? n_out : P.cap; }
+        sort_by_info(O.out, n_out, gl, 3 * P.list_cap, P.overflow);
         if (lane == 0) P.out_cnt[r] = n_out;
     }
     if (P.n_extend && lane == 0 && n_ext) atomicAdd(P.n_extend, n_ext);
 }
 
-}  // namespace
-
-static size_t seed_smem_bytes(const SeedParams& p) {
-    return p.lists_in_smem ? (size_t)SEED_WARPS * (2 * p.list_cap * sizeof(Iv32) + p.read_cap) : 0;
+template <class IdxT> size_t lists_bytes(uint32_t list_cap, uint32_t read_cap) {
+    return (size_t)SEED_WARPS * (2 * (size_t)list_cap * sizeof(IvT<IdxT>) + read_cap);
 }
+
+template <class IdxT, bool SMEM> void launch_mode(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, size_t smem, int* n_warps_out) {
+    int dev = 0, sms = 148, nb = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(seed_smem<IdxT, SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seed_smem<IdxT, SMEM>, SEED_THREADS, smem);
+    if (nb < 1) nb = 1;
+    if (nb * SEED_WARPS > 64) nb = 64 / SEED_WARPS;
+    if (n_warps_out) *n_warps_out = nb * sms * SEED_WARPS;
+    seed_smem<IdxT, SMEM><<<nb * sms, SEED_THREADS, smem, st>>>(p, ix, o);
+}
+
+}  // namespace
 
 int seed_resident_warps() {
     // upper bound used to size the per-warp global scratch: 64 warps per SM
@@ -416,24 +317,18 @@ int seed_resident_warps() {
     return 64 * sms;
 }
 
-bool seed_lists_fit_smem(uint32_t list_cap, uint32_t read_cap) {
-    return (size_t)SEED_WARPS * (2 * list_cap * sizeof(Iv32) + read_cap) <= 48 * 1024;
-}
-
-template <int MODE> static void launch_mode(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, size_t smem, int* n_warps_out) {
-    int dev = 0, sms = 148, nb = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seed_smem<MODE>, SEED_THREADS, smem);
-    if (nb < 1) nb = 1;
-    if (nb * SEED_WARPS > 64) nb = 64 / SEED_WARPS;
-    if (n_warps_out) *n_warps_out = nb * sms * SEED_WARPS;
-    seed_smem<MODE><<<nb * sms, SEED_THREADS, smem, st>>>(p, ix, o);
+bool seed_lists_fit_smem(uint32_t list_cap, uint32_t read_cap, int sa_bytes) {
+    const size_t b = sa_bytes == 8 ? lists_bytes<uint64_t>(list_cap, read_cap) : lists_bytes<uint32_t>(list_cap, read_cap);
+    return b <= 72 * 1024;
 }
 
 void launch_seed(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, int* n_warps_out) {
     const bool wide = ix.sa_bytes == 8;   // 64-bit row indices
-    if (wide) launch_mode<2>(p, ix, o, st, 0, n_warps_out);
-    else if (p.lists_in_smem) launch_mode<0>(p, ix, o, st, seed_smem_bytes(p), n_warps_out);
-    else launch_mode<1>(p, ix, o, st, 0, n_warps_out);
+    if (wide) {
+        if (p.lists_in_smem) launch_mode<uint64_t, true>(p, ix, o, st, lists_bytes<uint64_t>(p.list_cap, p.read_cap), n_warps_out);
+        else launch_mode<uint64_t, false>(p, ix, o, st, 0, n_warps_out);
+    } else {
+        if (p.lists_in_smem) launch_mode<uint32_t, true>(p, ix, o, st, lists_bytes<uint32_t>(p.list_cap, p.read_cap), n_warps_out);
+        else launch_mode<uint32_t, false>(p, ix, o, st, 0, n_warps_out);
+    }
 }

@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--reads", type=int, default=1_000_000)
     ap.add_argument("--ref-mbp", type=int, default=100)
     ap.add_argument("--opts", default="sql", choices=["sql", "canonical"])
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--err", default="0.008,0.001,0.001", help="substitution,insertion,deletion rates per base")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU seconds of the cpu_baseline sample")
     return ap.parse_args()
@@ -60,7 +62,9 @@ def workload(args, rank):
     rows_n = 10
     per = args.ref_mbp * 1_000_000 // rows_n
     rows = synth.reference_rows([per] * rows_n)
-    seqs, offs, truth = synth.simulate_reads(rows, args.reads, 150, seed=synth.SEED_READS + rank)
+    sub, ins, dele = [float(x) for x in args.err.split(",")]
+    seqs, offs, truth = synth.simulate_reads(rows, args.reads, args.read_len, sub=sub, ins=ins, dele=dele, seed=synth.SEED_READS + rank,
+                                             chunk=max(1, min(200_000, 40_000_000 // max(args.read_len, 1))))
     ids = synth.lrand48_ids_fast(args.reads)
     return rows, seqs, offs, ids, truth
 
@@ -132,7 +136,7 @@ def run_reference(args, rank, world):
         orc.add_ref_text(i + 1, r.tobytes())
     build_s = orc.build()
     # bounded sample per step: size it from a short probe so that K + W steps end within a few minutes
-    probe = min(20_000, args.reads)
+    probe = max(16, min(20_000, args.reads, 3_000_000 // max(args.read_len, 1)))
     r = orc.align_batch(seqs[:int(offs[probe])], offs[:probe + 1], ids[:probe], cores)
     rate = probe / max(r["seconds"], 1e-9)
     sample = int(min(args.reads, max(probe, rate * args.cpu_seconds)))
@@ -156,9 +160,9 @@ def run_reference(args, rank, world):
 
 
 def config_dict(args, n_gpus, **extra):
-    d = {"workload": "BASELINE configs[1]: %d simulated 150bp reads (1%% error: 0.8 sub / 0.1 ins / 0.1 del) per GPU vs %d Mbp synthetic reference (10 rows), index resident" % (args.reads, args.ref_mbp),
+    d = {"workload": ("BASELINE configs[1]: " if (args.read_len == 150 and args.ref_mbp == 100) else "") + "%d simulated %dbp reads (error sub/ins/del %s) per GPU vs %d Mbp synthetic reference (10 rows), index resident" % (args.reads, args.read_len, args.err, args.ref_mbp),
          "options": "SQL default (o_del 6, e_del 6, o_ins 1, e_ins 1)" if args.opts == "sql" else "canonical bwa (6/1/6/1)",
-         "reads_per_gpu": args.reads, "read_len": 150, "ref_mbp": args.ref_mbp,
+         "reads_per_gpu": args.reads, "read_len": args.read_len, "ref_mbp": args.ref_mbp,
          "l2_policy": "per-step working set (index %d MB + batch pools > 1 GB) exceeds the 126 MB L2; no explicit flush" % (args.ref_mbp * 2 + args.ref_mbp * 8 + args.ref_mbp // 4),
          "parallelism": "reads sharded over %d GPU(s), index replicated" % n_gpus}
     d.update(extra)
@@ -239,7 +243,7 @@ def run_ours(args, rank, world, local_rank):
     first = res.row_off[:-1].astype(np.int64)
     has = np.diff(res.row_off.astype(np.int64)) > 0
     pr = res.rows[np.minimum(first, max(total_rows - 1, 0))]
-    okk = has & (pr["rid"] == truth[0]) & (pr["is_rev"] == truth[2].astype(np.int32)) & (np.abs(pr["pos"] - truth[1]) <= 16)
+    okk = has & (pr["rid"] == truth[0]) & (pr["is_rev"] == truth[2].astype(np.int32)) & (np.abs(pr["pos"] - truth[1]) <= 16 + args.read_len // 8)
     truth_frac = float(okk.mean())
 
     # ---------------- e2e: host buffers through bsq_align_batch
@@ -337,19 +341,20 @@ def cpu_baseline(args, rows, seqs, offs, ids, ix, ot):
     for i, r in enumerate(rows):
         orc.add_ref_text(i + 1, r.tobytes())
     orc.adopt(ix.bwt_plain(), int(ix.meta().primary), ix.sa_sampled())
-    probe = min(20_000, args.reads)
+    probe = max(16, min(20_000, args.reads, 3_000_000 // max(args.read_len, 1)))
     r = orc.align_batch(seqs[:int(offs[probe])], offs[:probe + 1], ids[:probe], cores)
     rate = probe / max(r["seconds"], 1e-9)
     sample = int(min(args.reads, max(probe, rate * args.cpu_seconds)))
     r = orc.align_batch(seqs[:int(offs[sample])], offs[:sample + 1], ids[:sample], cores)
-    r1 = orc.align_batch(seqs[:int(offs[probe])], offs[:probe + 1], ids[:probe], 1)
+    probe1 = max(8, min(probe, int(rate / cores * 3.0)))   # ~3 s of single-core work
+    r1 = orc.align_batch(seqs[:int(offs[probe1])], offs[:probe1 + 1], ids[:probe1], 1)
     # index build on a bounded 8 Mbp sample, 1 core
     small = O.OracleIndex(O.Opts(*ot))
     small.add_ref_text(1, rows[0][:8_000_000].tobytes())
     bs = small.build()
     return {"value": sample / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d of %d reads, %d threads, FM-index arrays adopted from the GPU build" % (sample, args.reads, cores),
-            "one_core_reads_per_s": probe / r1["seconds"], "index_build_s_8Mbp_1core": bs,
+            "one_core_reads_per_s": probe1 / r1["seconds"], "index_build_s_8Mbp_1core": bs,
             "oracle_counters_per_read": {k: v / sample for k, v in r["counters"].items()}}
 
 

@@ -25,7 +25,7 @@ __device__ __forceinline__ Scratch carve(uint8_t* base, uint32_t max_len, uint32
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(EXT_THREADS) sw_extend(ExtendParams P, DevIndex ix, DevOpts o) {
+__global__ void __launch_bounds__(EXT_THREADS, SMEM ? 8 : 4) sw_extend(ExtendParams P, DevIndex ix, DevOpts o) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ int smat[25];
     if (threadIdx.x < 25) smat[threadIdx.x] = o.mat[threadIdx.x];

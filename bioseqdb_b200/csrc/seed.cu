@@ -68,6 +68,59 @@ __device__ __forceinline__ IvT<IdxT> extend1(const Ctx<IdxT>& C, const IvT<IdxT>
     return ok;
 }
 
+// Four backward extensions per warp step: lane group g = lane / 8 extends its own list entry with the same base c
+// (the entries of a backward step are independent).  Inside a group lanes 0-3 read the block of row k and lanes
+// 4-7 the block of row l, 16 bytes each (lane 0: checkpoints A,C; lane 1: G,T; lanes 2,3: 64 symbols each), so a
+// warp load touches 8 cache lines for 4 extensions; the three sums are 3-step xor-shuffle reductions confined to
+// the group.  Every lane of a group returns the group's child interval.
+template <class IdxT>
+__device__ __forceinline__ IvT<IdxT> extend4_back(const Ctx<IdxT>& C, const IvT<IdxT>& ik, int c, bool valid) {
+    const int t = lane_id() & 7;
+    const bool lside = (t & 4) != 0;
+    const IdxT xo = ik.x0, xb = ik.x1;
+    IdxT pos = xo - 1 + (lside ? (IdxT)ik.x2 : (IdxT)0);
+    pos -= (pos >= C.primary);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (valid) v = __ldg(reinterpret_cast<const uint4*>(C.occ + ((size_t)(pos >> 7) << 4)) + (t & 3));
+    // symbol lanes (t & 2): 4 words = 64 symbols starting at 64 (t & 1); checkpoint lanes get rem = 0 => nothing counted
+    const uint32_t C1 = 0u - (uint32_t)(c >> 1), C0 = 0u - (uint32_t)(c & 1);
+    const int rem = (t & 2) ? (int)(pos & 127) + 1 - ((t & 1) << 6) : 0;
+    int eq = 0, gt = 0;
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int nsym = rem - (k << 4);
+        nsym = nsym < 0 ? 0 : (nsym > 16 ? 16 : nsym);
+        const uint32_t keep = __funnelshift_rc(0u, 0x55555555u, 2 * nsym);
+        const uint32_t word = w4[k];
+        const uint32_t hx = ~((word >> 1) ^ C1);
+        eq += __popc(hx & ~(word ^ C0) & keep);
+        gt += __popc((((word >> 1) & ~C1) | (hx & word & ~C0)) & keep);
+    }
+    uint32_t tk_hi = 0;
+    if ((t & 2) == 0) {   // checkpoint lanes: symbols a = 2 (t & 1) and a + 1; u64 checkpoints = (.x,.y) and (.z,.w)
+        const int a = (t & 1) << 1;
+        eq = c == a ? (int)v.x : (c == a + 1 ? (int)v.z : 0);
+        gt = (a > c ? (int)v.x : 0) + (a + 1 > c ? (int)v.z : 0);
+        if (sizeof(IdxT) == 8 && !lside) tk_hi = c == a ? v.y : (c == a + 1 ? v.w : 0u);
+    }
+    int sz = lside ? eq : -eq, S = lside ? gt : -gt;
+    // tk: the checkpoint's low word and the popcounts are summed separately so that a 64-bit checkpoint cannot lose a carry
+    uint32_t tk_lo = (!lside && (t & 2) == 0) ? (uint32_t)eq : 0u, tk_pop = (!lside && (t & 2) != 0) ? (uint32_t)eq : 0u;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        sz += __shfl_xor_sync(FULL, sz, d); S += __shfl_xor_sync(FULL, S, d);
+        tk_lo += __shfl_xor_sync(FULL, tk_lo, d); tk_pop += __shfl_xor_sync(FULL, tk_pop, d);
+        if (sizeof(IdxT) == 8) tk_hi += __shfl_xor_sync(FULL, tk_hi, d);
+    }
+    const IdxT tk = sizeof(IdxT) == 8 ? (IdxT)(((unsigned long long)tk_hi << 32 | tk_lo) + tk_pop) : (IdxT)(tk_lo + tk_pop);
+    IvT<IdxT> ok;
+    ok.x0 = C.sL2[c] + 1 + tk;
+    ok.x1 = xb + (IdxT)(xo <= C.primary && xo + ik.x2 - 1 >= C.primary) + (IdxT)(uint32_t)S;
+    ok.x2 = (uint32_t)sz; ok.info = ik.info;
+    return ok;
+}
+
 template <class IdxT> __device__ __forceinline__ IvT<IdxT> set_intv(const Ctx<IdxT>& C, int c) {
     IvT<IdxT> ik;
     ik.x0 = C.sL2[c] + 1; ik.x1 = C.sL2[3 - c] + 1; ik.x2 = (uint32_t)(C.sL2[c + 1] - C.sL2[c]); ik.info = 0;
@@ -123,6 +176,52 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
         const int c = i < 0 ? -1 : (q[i] < 4 ? q[i] : -1);
         n_curr = 0;
         uint32_t last_x2 = 0;
+        if (c >= 0 && n_prev >= 2) {
+            // several entries: lane group g extends entry j0 + g, then the sequential bookkeeping of bwt_smem1a is evaluated
+            // for all entries at once.  In list order: (1) only the FIRST dying entry can emit a MEM, and only if no
+            // survivor precedes it (curr empty at its turn); (2) a survivor is pushed iff it is the first survivor or
+            // its size differs from the PREVIOUS survivor's (a skipped survivor has the size of the last pushed one).
+            bool any_push = false;
+            const int grp = lane >> 3;
+            const bool leader = (lane & 7) == 0;
+            for (uint32_t j0 = 0; j0 < n_prev; j0 += 4) {
+                const uint32_t j = j0 + (uint32_t)grp;
+                const bool valid = j < n_prev;
+                IvT<IdxT> p; p.x0 = 1; p.x1 = 1; p.x2 = 0; p.info = 0;
+                if (valid) p = prev[reversed ? n_prev - 1 - j : j];
+                const IvT<IdxT> ok = extend4_back(C, p, c, valid);
+                const bool surv = valid && ok.x2 >= min_intv;
+                // one bit per entry: the leader lane of each group votes
+                const uint32_t surv_mask = __ballot_sync(FULL, surv && leader);
+                const uint32_t die_mask = __ballot_sync(FULL, valid && !surv && leader);
+                n_ext += (unsigned long long)__popc(surv_mask | die_mask);
+                if (die_mask && !any_push) {
+                    const int fd = __ffs(die_mask) - 1;          // leader lane of the first dying entry
+                    if ((surv_mask & ((1u << fd) - 1u)) == 0 && (!have_mem || (uint32_t)(i + 1) < last_mem_start)) {
+                        const uint32_t pinfo = __shfl_sync(FULL, p.info, fd);
+                        const int slen = (int)pinfo - (i + 1);
+                        if (slen >= o.min_seed_len) {
+                            if (O.n < O.cap) {
+                                if (lane == fd) { Intv v; v.x0 = p.x0; v.x1 = p.x1; v.x2 = p.x2; v.info = (uint64_t)(uint32_t)(i + 1) << 32 | p.info; O.out[O.n] = v; }
+                            } else O.ovf = true;
+                            ++O.n;
+                        }
+                        have_mem = true; last_mem_start = (uint32_t)(i + 1);
+                    }
+                }
+                if (surv_mask) {
+                    const uint32_t before = surv_mask & ((1u << (grp << 3)) - 1u);   // surviving entries before mine
+                    const int pl = before ? 31 - __clz(before) : 0;
+                    const uint32_t prev_sz = __shfl_sync(FULL, ok.x2, pl);
+                    const bool push = surv && leader && (before ? ok.x2 != prev_sz : (!any_push || ok.x2 != last_x2));
+                    const uint32_t push_mask = __ballot_sync(FULL, push);
+                    if (push) curr[n_curr + __popc(push_mask & ((1u << lane) - 1u))] = ok;   // n_curr + pushes <= n_prev <= list_cap
+                    n_curr += __popc(push_mask);
+                    last_x2 = __shfl_sync(FULL, ok.x2, 31 - __clz(surv_mask));   // size of the last survivor so far
+                    any_push = true;   // a survivor exists => the first survivor was pushed
+                }
+            }
+        } else
         for (uint32_t j = 0; j < n_prev; ++j) {
             const IvT<IdxT> p = prev[reversed ? n_prev - 1 - j : j];
             IvT<IdxT> ok; ok.x2 = 0;

@@ -12,11 +12,13 @@
 // and S still fit 32 bits (they are bounded by the parent interval), only tk[c] needs its checkpoint's two
 // halves, i.e. two more single-contributor reductions.  Interval lists and the read live in shared memory.
 #include "seed.cuh"
+#include <algorithm>
 
 namespace {
 
 constexpr int SEED_THREADS = 256;
 constexpr int SEED_WARPS = SEED_THREADS / 32;
+constexpr int KMER_K = 12;   // k-mer table of the LAST-like pass: 4^12 entries x 16 B = 268 MB
 
 template <class IdxT> struct IvT { IdxT x0, x1; uint32_t x2, info; };   // info = end of the match on the query
 template <> struct __align__(16) IvT<uint32_t> { uint32_t x0, x1, x2, info; };
@@ -26,6 +28,7 @@ template <> struct __align__(16) IvT<uint32_t> { uint32_t x0, x1, x2, info; };
 template <class IdxT> struct Ctx {
     const uint32_t* occ;
     const IdxT* sL2;         // shared memory: L2[0..4]
+    const uint4* kmer_tab;   // bi-intervals of all KMER_K-mers (x0, x1, x2, -), nullptr when absent
     IdxT primary;
     uint32_t sym_base;       // first symbol covered by this lane's word (symbol lanes), 1 << 20 for checkpoint lanes
     int cnt_sym;             // symbol whose checkpoint LOW word this lane holds, -1 otherwise
@@ -265,7 +268,20 @@ __device__ __forceinline__ int seed_strategy1(const Ctx<IdxT>& C, int len, const
                                               unsigned long long& n_ext) {
     if (q[x] > 3) return x + 1;
     IvT<IdxT> ik = set_intv(C, q[x]);
-    for (int i = x + 1; i < len; ++i) {
+    int i = x + 1;
+    // The first KMER_K - 1 extensions can neither emit (i - x < min_len) nor be observed: take their result from the
+    // k-mer table when the next KMER_K bases are all ACGT (an ambiguous base ends the walk, which the plain loop handles)
+    if (sizeof(IdxT) == 4 && C.kmer_tab && min_len >= KMER_K && x + KMER_K <= len) {
+        uint32_t idx = 0; bool acgt = true;
+#pragma unroll
+        for (int t = 0; t < KMER_K; ++t) { const uint32_t b = q[x + t]; acgt = acgt && b < 4; idx = idx << 2 | (b & 3); }
+        if (acgt) {
+            const uint4 e = __ldg(C.kmer_tab + idx);
+            ik.x0 = (IdxT)e.x; ik.x1 = (IdxT)e.y; ik.x2 = e.z;
+            i = x + KMER_K; n_ext += KMER_K - 1;   // the roofline unit stays the reference's count of bwt_extend calls
+        }
+    }
+    for (; i < len; ++i) {
         const int b = q[i];
         if (b < 4) {
             IvT<IdxT> ok = extend1<IdxT, 0>(C, ik, 3 - b); ++n_ext;
@@ -302,6 +318,52 @@ __device__ __forceinline__ void collect_intv(const Ctx<IdxT>& C, const DevOpts& 
             else ++x;
         }
     }
+}
+
+// ---------------------------------------------------------------- k-mer table of the LAST-like pass
+// Level-by-level: the 4^t intervals of level t come from one forward bwt_extend of each level t-1 interval
+// (all four children at once, scalar Occ4 per thread).  Entry of k-mer b0 b1 .. b_{K-1} sits at index sum b_t 4^{K-1-t}.
+__device__ __forceinline__ void occ4_scalar(const uint32_t* occ, uint32_t primary, uint32_t k, uint32_t cnt[4]) {
+    k -= (k >= primary);
+    const uint4* blk = reinterpret_cast<const uint4*>(occ + ((size_t)(k >> 7) << 4));
+    const uint4 ca = __ldg(blk), cb = __ldg(blk + 1), s0 = __ldg(blk + 2), s1 = __ldg(blk + 3);
+    cnt[0] = ca.x; cnt[1] = ca.z; cnt[2] = cb.x; cnt[3] = cb.z;
+    const int within = (int)(k & 127) + 1;
+    const uint32_t w8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        int nsym = within - (w << 4);
+        nsym = nsym < 0 ? 0 : (nsym > 16 ? 16 : nsym);
+        const uint32_t keep = __funnelshift_rc(0u, 0x55555555u, 2 * nsym);
+        const uint32_t lo = w8[w] & keep, hi = (w8[w] >> 1) & keep, nlo = ~w8[w] & keep, nhi = ~(w8[w] >> 1) & keep;
+        cnt[0] += __popc(nhi & nlo); cnt[1] += __popc(nhi & lo); cnt[2] += __popc(hi & nlo); cnt[3] += __popc(hi & lo);
+    }
+}
+
+__global__ void k_kmer_level(const uint4* __restrict__ parent, uint4* __restrict__ child, uint32_t n_parent, const uint32_t* __restrict__ occ,
+                             uint32_t primary, uint32_t L2a, uint32_t L2c, uint32_t L2g, uint32_t L2t) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_parent; p += gridDim.x * blockDim.x) {
+        const uint4 ik = parent[p];   // x0, x1, x2
+        uint32_t tk[4], tl[4];
+        occ4_scalar(occ, primary, ik.y - 1, tk);
+        occ4_scalar(occ, primary, ik.y - 1 + ik.z, tl);
+        const uint32_t L2[4] = {L2a, L2c, L2g, L2t};
+        uint32_t x1[4], sz[4], x0[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { x1[c] = L2[c] + 1 + tk[c]; sz[c] = tl[c] - tk[c]; }
+        x0[3] = ik.x + (uint32_t)(ik.y <= primary && ik.y + ik.z - 1 >= primary);
+        x0[2] = x0[3] + sz[3]; x0[1] = x0[2] + sz[2]; x0[0] = x0[1] + sz[1];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {   // appending base b = taking ok[3 - b] of a forward extension
+            const int c = 3 - b;
+            child[(size_t)p * 4 + b] = make_uint4(x0[c], x1[c], ik.z ? sz[c] : 0u, 0u);
+        }
+    }
+}
+__global__ void k_kmer_level0(uint4* out, uint32_t L2a, uint32_t L2c, uint32_t L2g, uint32_t L2t, uint32_t L2n) {
+    const uint32_t L2[5] = {L2a, L2c, L2g, L2t, L2n};
+    const int c = threadIdx.x;
+    if (c < 4) out[c] = make_uint4(L2[c] + 1, L2[3 - c] + 1, L2[c + 1] - L2[c], 0u);
 }
 
 // sort a read's intervals by info (ties are bit-identical records, so any correct sort equals ks_introsort's result)
@@ -353,7 +415,7 @@ __global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 5 
     Intv* gl = P.scratch + (size_t)gwarp * 3 * P.list_cap;     // global scratch: lists of long reads, big-sort buffer
     unsigned long long n_ext = 0;
     Ctx<IdxT> C;
-    C.occ = ix.occ; C.sL2 = sL2; C.primary = (IdxT)ix.primary;
+    C.occ = ix.occ; C.sL2 = sL2; C.primary = (IdxT)ix.primary; C.kmer_tab = P.kmer_tab;
     {
         const int idx = lane & 15;
         C.sym_base = idx >= 8 ? (uint32_t)((idx - 8) << 4) : (1u << 20);
@@ -407,6 +469,26 @@ template <class IdxT, bool SMEM> void launch_mode(const SeedParams& p, const Dev
 }
 
 }  // namespace
+
+size_t kmer_table_bytes() { return ((size_t)1 << (2 * KMER_K)) * sizeof(uint4); }
+
+// builds the table into `tab` (kmer_table_bytes()); `tmp` must hold a quarter of it.  32-bit indices only.
+void build_kmer_table(const DevIndex& ix, void* tab, void* tmp, cudaStream_t st, uint64_t* launches) {
+    uint4* a = reinterpret_cast<uint4*>(tab); uint4* b = reinterpret_cast<uint4*>(tmp);
+    // levels alternate between the two buffers so that the last level (KMER_K) lands in `tab`
+    uint4* cur = (KMER_K & 1) ? a : b;
+    const uint32_t L2a = (uint32_t)ix.L2[0], L2c = (uint32_t)ix.L2[1], L2g = (uint32_t)ix.L2[2], L2t = (uint32_t)ix.L2[3], L2n = (uint32_t)ix.L2[4];
+    k_kmer_level0<<<1, 32, 0, st>>>(cur, L2a, L2c, L2g, L2t, L2n);
+    if (launches) ++*launches;
+    uint32_t n = 4;
+    for (int t = 2; t <= KMER_K; ++t) {
+        uint4* nxt = cur == a ? b : a;
+        const unsigned blocks = (unsigned)std::min<uint32_t>((n + 255) / 256, 148u * 16u);
+        k_kmer_level<<<blocks ? blocks : 1, 256, 0, st>>>(cur, nxt, n, ix.occ, (uint32_t)ix.primary, L2a, L2c, L2g, L2t);
+        if (launches) ++*launches;
+        cur = nxt; n *= 4;
+    }
+}
 
 int seed_resident_warps() {
     // upper bound used to size the per-warp global scratch: 64 warps per SM

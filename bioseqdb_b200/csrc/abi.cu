@@ -432,7 +432,7 @@ int run_pipeline(bsq_index* h) {
         ENS(b.ext_scratch.ensure((size_t)ext_warps * ext_per_warp)); ENS(b.fin_scratch.ensure((size_t)fin_warps * fin_per_warp));
         int narrow_warps = 0;
         const size_t narrow_bytes = narrow_zbuf_bytes(&narrow_warps);
-        ENS(b.narrow_z.ensure(narrow_bytes)); ENS(b.narrow_jobs.ensure((size_t)b.pool_cap * 2 * 24)); ENS(b.wide_jobs.ensure(b.pool_cap));
+        ENS(b.narrow_z.ensure(narrow_bytes)); ENS(b.narrow_jobs.ensure((size_t)b.pool_cap * 3 * 24)); ENS(b.wide_jobs.ensure(b.pool_cap));
         ENS(b.ctl.ensure(64));
         ENS(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, h->stream));
         unsigned long long* ctr = h->collect_counters ? reinterpret_cast<unsigned long long*>(b.ctl.p + 8) : nullptr;

@@ -189,13 +189,14 @@ __device__ __forceinline__ int gen_cigar_band(const DevOpts& o, int l_query, int
     return w > min_w ? w : min_w;
 }
 
-__device__ __forceinline__ bool is_narrow_first_try(const DevOpts& o, const RegRec& ar, uint32_t max_len) {
+// 0: align on the warp here; 1: thread-per-region narrow-band DP; 2: thread-per-region, no DP (equal lengths, zero band)
+__device__ __forceinline__ int narrow_class(const DevOpts& o, const RegRec& ar, uint32_t max_len) {
     const int lq = ar.qe - ar.qb; const int64_t rl = ar.re - ar.rb;
-    if (max_len > NARROW_QMAX || lq <= 0 || rl <= 0 || rl > NARROW_TMAX) return false;
+    if (max_len > NARROW_QMAX || lq <= 0 || rl <= 0 || rl > NARROW_TMAX) return 0;
     int w2 = reg2aln_w2(o, ar);
     w2 = w2 < o.w << 2 ? w2 : o.w << 2;
-    if (lq == rl && w2 == 0) return false;   // no DP at all: the warp does the 150-base score sum inline
-    return 2 * gen_cigar_band(o, lq, (int)rl, w2) + 1 <= NARROW_NC;
+    if (lq == rl) return 2;   // equal lengths: first a thread checks whether the gap-free diagonal is provably the unique optimum
+    return 2 * gen_cigar_band(o, lq, (int)rl, w2) + 1 <= NARROW_NC ? 1 : 0;
 }
 
 // mem_reg2aln for one region on the whole warp; completes *out (NM, pos, is_rev, CIGAR)
@@ -386,11 +387,13 @@ __global__ void __launch_bounds__(FIN_THREADS) regs_finalize(FinalizeParams P, D
         for (int i = 0; i < n; ++i) {
             const RegRec ar = a[i];
             RowDev row = row_from_reg(ar, P.ann_id);
-            const bool narrow = P.narrow_jobs != nullptr && is_narrow_first_try(o, ar, P.max_len);
+            const int ncls = P.narrow_jobs != nullptr ? narrow_class(o, ar, P.max_len) : 0;
+            const bool narrow = ncls != 0;
             if (lane == 0) {
                 rows[i] = row;
                 if (narrow) {
-                    const uint32_t k = atomicAdd(P.narrow_cnt, 1u);
+                    // DP regions and no-DP regions go to separate lists so that the lanes of a warp do similar work
+                    const uint32_t k = ncls == 1 ? atomicAdd(P.narrow_cnt, 1u) : 2u * P.narrow_cap + atomicAdd(P.narrow_cnt + 3, 1u);
                     NarrowJob jb; jb.r = r; jb.slot = blk.base + i; jb.w2 = reg2aln_w2(o, ar); jb.last_sc = -(1 << 30); jb.it = 0; jb.score = 0;
                     reinterpret_cast<NarrowJob*>(P.narrow_jobs)[k] = jb;
                 }
@@ -415,6 +418,7 @@ struct NarrowParams {
     const NarrowJob* jobs; const uint32_t* n_jobs; NarrowJob* requeue; uint32_t* requeue_cnt; uint64_t* wide_jobs; uint32_t* wide_cnt;
     uint32_t* cigar_pool; uint32_t cigar_cap; uint32_t* cigar_top;
     uint8_t* zbuf; uint32_t* ticket; uint32_t* overflow; unsigned long long* counters;
+    int diag_pass;   // 1: equal-length regions -- finish the ones whose diagonal is provably optimal, hand the rest to the DP list
 };
 
 __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams P, DevIndex ix, DevOpts o) {
@@ -427,9 +431,11 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
     int* E = reinterpret_cast<int*>(dyn_smem) + NARROW_NC * NARROW_THREADS + tid;
     uint8_t* Q = dyn_smem + 2 * NARROW_NC * NARROW_THREADS * 4 + tid;               // Q[j * NARROW_THREADS]
     const uint32_t gwarp = (blockIdx.x * NARROW_THREADS + tid) >> 5;
-    // traceback bytes, 8 cells per 64-bit store, laid out [row][8-cell group][lane]: a warp store is 256 contiguous bytes
-    unsigned long long* Z = reinterpret_cast<unsigned long long*>(P.zbuf + (size_t)gwarp * ((size_t)NARROW_TMAX * NARROW_NC * 32)) + lane;
-    const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins, e_del = o.e_del, e_ins = o.e_ins;
+    // traceback bytes, 4 cells per 32-bit store, laid out [row][4-cell group][lane]: a warp store is 128 contiguous bytes
+    uint32_t* Z = reinterpret_cast<uint32_t*>(P.zbuf + (size_t)gwarp * ((size_t)NARROW_TMAX * NARROW_NC * 32)) + lane;
+    int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins, e_del = o.e_del, e_ins = o.e_ins;
+    // keep the four gap constants in registers: left to itself the compiler re-reads them from the constant bank per cell
+    asm volatile("" : "+r"(oe_del), "+r"(oe_ins), "+r"(e_del), "+r"(e_ins));
     const int64_t l_pac = ix.l_pac;
     const uint32_t n_jobs = *P.n_jobs;
     unsigned long long cells = 0, calls = 0;
@@ -463,14 +469,28 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
             do {
                 n_cigar = 0; NM = -1;
                 if (!reject) {
-                    if (lq == rlen && w2 == 0) {
+                    bool diagonal = lq == rlen && w2 == 0;   // bwa_gen_cigar2's own no-DP case
+                    if (P.diag_pass && lq == rlen) {
+                        // Equal lengths: any alignment other than the gap-free diagonal has >= 1 insertion and >= 1 deletion and at
+                        // most lq - 1 aligned pairs, so it scores <= (lq - 1) max(mat) - oe_ins - oe_del.  If the diagonal beats that
+                        // bound it is the UNIQUE optimum of ksw_global2 for every band (the diagonal lies inside any band), so the
+                        // traceback is lq M and the score is band-independent: the DP and the band-doubling retries are skipped.
+                        int sc = 0;
+                        for (int i = 0; i < lq; ++i) {
+                            const int tb = rev ? 3 - (int)pac_get(ix.pac, tbase + i) : (int)pac_get(ix.pac, tbase + i);
+                            sc += smat[tb * 5 + Q[i * NARROW_THREADS]];
+                        }
+                        if (diagonal || sc > (lq - 1) * o.mat_max - oe_ins - oe_del) { score = sc; cg[0] = (uint32_t)lq << 4; n_cigar = 1; diagonal = true; }
+                        else { P.requeue[atomicAdd(P.requeue_cnt, 1u)] = jb; again = true; break; }   // needs the DP: over to the DP list, same try
+                    } else if (diagonal) {
                         int sc = 0;
                         for (int i = 0; i < lq; ++i) {
                             const int tb = rev ? 3 - (int)pac_get(ix.pac, tbase + i) : (int)pac_get(ix.pac, tbase + i);
                             sc += smat[tb * 5 + Q[i * NARROW_THREADS]];
                         }
                         score = sc; cg[0] = (uint32_t)lq << 4; n_cigar = 1;
-                    } else {
+                    }
+                    if (!diagonal) {
                         const int w = gen_cigar_band(o, lq, rlen, w2);
                         const int n_col = lq < 2 * w + 1 ? lq : 2 * w + 1;
                         if (2 * w + 1 > NARROW_NC || rlen > NARROW_TMAX) { go_wide = true; break; }
@@ -486,14 +506,17 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                             int f = KSW_NEG_INF;
                             const int tb = rev ? 3 - (int)pac_get(ix.pac, tbase + i) : (int)pac_get(ix.pac, tbase + i);
                             const int* mrow = smat + tb * 5;
-                            unsigned long long* zi = Z + (size_t)i * (NARROW_NC / 8) * 32;
+                            uint32_t* zi = Z + (size_t)i * (NARROW_NC / 4) * 32;
                             cells += (unsigned long long)(end - beg);
-                            unsigned long long zpack = 0;
+                            uint32_t zpack = 0; int zsh = 0;
+                            // walking pointers: circular row window (wraps after NARROW_NC columns), staged query column
+                            int* hp = H + (beg & (NARROW_NC - 1)) * NARROW_THREADS;
+                            int* const hwrap = H + NARROW_NC * NARROW_THREADS;
+                            const uint8_t* qp = Q + beg * NARROW_THREADS;
                             for (int j = beg; j < end; ++j) {
-                                const int c = (j & (NARROW_NC - 1)) * NARROW_THREADS;
-                                int m = H[c], e = E[c];
-                                H[c] = h1;
-                                m += mrow[Q[j * NARROW_THREADS]];
+                                int m = hp[0], e = hp[NARROW_NC * NARROW_THREADS];
+                                hp[0] = h1;
+                                m += mrow[*qp];
                                 int d = m >= e ? 0 : 1;
                                 int h = m >= e ? m : e;
                                 d = h >= f ? d : 2;
@@ -503,16 +526,18 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                                 e -= e_del;
                                 d |= e > tt ? 1 << 2 : 0;
                                 e = e > tt ? e : tt;
-                                E[c] = e;
+                                hp[NARROW_NC * NARROW_THREADS] = e;
                                 tt = m - oe_ins;
                                 f -= e_ins;
                                 d |= f > tt ? 2 << 4 : 0;
                                 f = f > tt ? f : tt;
-                                const int jj = j - beg;
-                                zpack |= (unsigned long long)d << ((jj & 7) << 3);
-                                if ((jj & 7) == 7) { zi[(jj >> 3) * 32] = zpack; zpack = 0; }
+                                zpack |= (uint32_t)d << zsh;
+                                zsh += 8;
+                                if (zsh == 32) { *zi = zpack; zi += 32; zpack = 0; zsh = 0; }
+                                hp += NARROW_THREADS; if (hp == hwrap) hp = H;
+                                qp += NARROW_THREADS;
                             }
-                            if (((end - beg) & 7) != 0) zi[((end - beg) >> 3) * 32] = zpack;
+                            if (zsh) *zi = zpack;
                             const int ce = (end & (NARROW_NC - 1)) * NARROW_THREADS;
                             H[ce] = h1; E[ce] = KSW_NEG_INF;
                         }
@@ -527,7 +552,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                             };
                             while (i >= 0 && k >= 0) {
                                 const int jj = k - (i > w ? i - w : 0);
-                                which = (int)(Z[((size_t)i * (NARROW_NC / 8) + (jj >> 3)) * 32] >> ((jj & 7) << 3) & 0xff) >> (which << 1) & 3;
+                                which = (int)(Z[((size_t)i * (NARROW_NC / 4) + (jj >> 2)) * 32] >> ((jj & 3) << 3) & 0xff) >> (which << 1) & 3;
                                 if (which == 0) { push(0, 1); --i; --k; }
                                 else if (which == 1) { push(2, 1); --i; }
                                 else { push(1, 1); --k; }
@@ -555,6 +580,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                     NM = n_mm + n_gap;
                 }
                 if (score == jb.last_sc || w2 == o.w << 2) break;
+                if (P.diag_pass && !reject && lq == rlen && !(lq == rlen && w2 == 0)) break;   // band-independent result (see above)
                 if (jb.it + 1 < 3 && score < ar.truesc - o.a) {
                     again = true;
                     NarrowJob nx; nx.r = r; nx.slot = slot; nx.w2 = w2 << 1; nx.last_sc = score; nx.it = jb.it + 1; nx.score = score;
@@ -696,13 +722,17 @@ void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts&
         NarrowJob* listA = reinterpret_cast<NarrowJob*>(p.narrow_jobs);
         NarrowJob* listB = listA + p.narrow_cap;
         const size_t nsmem = (size_t)NARROW_THREADS * (2 * NARROW_NC * 4 + NARROW_QMAX);
-        for (int pass = 0; pass < 3; ++pass) {
+        for (int pass = 0; pass < 4; ++pass) {
+            // pass 0: equal-length regions (list S): diagonal proof, the rest joins list A; pass 1: DP regions (A -> re-queue B);
+            // pass 2: second tries (B -> A); pass 3: third tries (A)
             NarrowParams q;
             q.seqs = p.seqs; q.offs = p.offs; q.regs = p.regs; q.rows = p.rows;
-            q.jobs = (pass & 1) ? listB : listA; q.n_jobs = p.narrow_cnt + pass;
-            q.requeue = (pass & 1) ? listA : listB; q.requeue_cnt = p.narrow_cnt + pass + 1;   // pass 2 never re-queues (it + 1 == 3)
+            q.jobs = pass == 0 ? listA + 2 * (size_t)p.narrow_cap : (pass == 2 ? listB : listA);
+            q.n_jobs = p.narrow_cnt + (pass == 0 ? 3 : (pass == 1 ? 0 : (pass == 2 ? 1 : 2)));
+            q.requeue = (pass == 0 || pass == 2) ? listA : listB;
+            q.requeue_cnt = p.narrow_cnt + (pass == 0 ? 0 : (pass == 1 ? 1 : (pass == 2 ? 2 : 4)));   // pass 3 never re-queues
             q.wide_jobs = p.wide_jobs; q.wide_cnt = p.wide_cnt; q.cigar_pool = p.cigar_pool; q.cigar_cap = p.cigar_cap; q.cigar_top = p.cigar_top;
-            q.zbuf = p.narrow_z; q.ticket = p.ticket + 1 + pass; q.overflow = p.overflow; q.counters = p.counters;
+            q.zbuf = p.narrow_z; q.ticket = p.ticket + 1 + pass; q.overflow = p.overflow; q.counters = p.counters; q.diag_pass = pass == 0;
             regs_cigar_narrow<<<warps / (NARROW_THREADS / 32), NARROW_THREADS, nsmem, st>>>(q, ix, o);
             if (launches) ++*launches;
         }
@@ -710,7 +740,7 @@ void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts&
     // phase 3: whatever needed a wider band on a retry
     {
         FinalizeParams w = p;
-        w.ticket = p.ticket + 4;
+        w.ticket = p.ticket + 5;
         if (smem_ok) regs_cigar_wide<true><<<blocks, FIN_THREADS, smem, st>>>(w, ix, o, cig_cap, rseq_cap);
         else regs_cigar_wide<false><<<blocks, FIN_THREADS, 0, st>>>(w, ix, o, cig_cap, rseq_cap);
         if (launches) ++*launches;

@@ -380,12 +380,9 @@ int upload_reads(bsq_index* h, const char* seqs, const uint64_t* offs, const int
 // k-mer table of the LAST-like seeding pass: built once per device index (also after a broadcast replica)
 int ensure_kmer_table(bsq_index* h, const DevIndex& ix) {
     if (h->d_kmer || ix.sa_bytes != 4 || ix.seq_len < (1u << 16)) return BSQ_OK;
-    void* tmp = nullptr;
     CUDA_CHECK(cudaMalloc(&h->d_kmer, kmer_table_bytes()));
-    CUDA_CHECK(cudaMalloc(&tmp, kmer_table_bytes() / 4 + 64));
-    build_kmer_table(ix, h->d_kmer, tmp, h->stream, &h->timing.launches);
+    build_kmer_table(ix, h->d_kmer, nullptr, h->stream, &h->timing.launches);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    cudaFree(tmp);
     return BSQ_OK;
 }
 

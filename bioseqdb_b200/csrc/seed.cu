@@ -18,7 +18,8 @@ namespace {
 
 constexpr int SEED_THREADS = 256;
 constexpr int SEED_WARPS = SEED_THREADS / 32;
-constexpr int KMER_K = 12;   // k-mer table of the LAST-like pass: 4^12 entries x 16 B = 268 MB
+constexpr int KMER_K = 12;   // prefix table: bi-intervals of every t-mer, t = 1..12 (levels back to back, 22.4 M entries x 16 B = 358 MB)
+__host__ __device__ constexpr uint32_t kmer_level_off(int t) { return ((1u << (2 * t)) - 4u) / 3u; }   // first entry of level t
 
 template <class IdxT> struct IvT { IdxT x0, x1; uint32_t x2, info; };   // info = end of the match on the query
 template <> struct __align__(16) IvT<uint32_t> { uint32_t x0, x1, x2, info; };
@@ -28,7 +29,7 @@ template <> struct __align__(16) IvT<uint32_t> { uint32_t x0, x1, x2, info; };
 template <class IdxT> struct Ctx {
     const uint32_t* occ;
     const IdxT* sL2;         // shared memory: L2[0..4]
-    const uint4* kmer_tab;   // bi-intervals of all KMER_K-mers (x0, x1, x2, -), nullptr when absent
+    const uint4* kmer_tab;   // prefix table (x0, x1, x2, -) of all t-mers, t <= KMER_K; nullptr when absent
     IdxT primary;
     uint32_t sym_base;       // first symbol covered by this lane's word (symbol lanes), 1 << 20 for checkpoint lanes
     int cnt_sym;             // symbol whose checkpoint LOW word this lane holds, -1 otherwise
@@ -150,8 +151,37 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
     ik.info = (uint32_t)(x + 1);
     IvT<IdxT>* curr = la; IvT<IdxT>* prev = lb;
     uint32_t n_curr = 0;
-    int i;
-    for (i = x + 1; i < len; ++i) {
+    int i = x + 1;
+    bool fwd_done = false;
+    if (sizeof(IdxT) == 4 && C.kmer_tab && x + KMER_K <= len) {
+        // The first KMER_K - 1 forward steps from the prefix table: lane t fetches the interval of q[x .. x+t]; the step
+        // that appends base t+1 records lane t's interval when the size changes and stops the walk when it falls below
+        // min_intv -- the same decisions the scalar loop takes, evaluated for all steps at once.
+        uint32_t idx = 0; bool acgt = true;
+#pragma unroll
+        for (int t = 0; t < KMER_K; ++t) { const uint32_t b = q[x + t]; acgt = acgt && b < 4; idx = idx << 2 | (b & 3); }
+        if (acgt) {
+            uint4 e = make_uint4(0, 0, 0, 0);
+            if (lane < KMER_K) e = __ldg(C.kmer_tab + kmer_level_off(lane + 1) + (idx >> (2 * (KMER_K - 1 - lane))));
+            const uint32_t x2n = __shfl_down_sync(FULL, e.z, 1);
+            const bool change = lane < KMER_K - 1 && x2n != e.z;
+            const uint32_t brk = __ballot_sync(FULL, change && x2n < min_intv);
+            const int steps = brk ? __ffs(brk) : KMER_K - 1;
+            const bool push = change && lane < steps;
+            const uint32_t pmask = __ballot_sync(FULL, push);
+            if (push) { IvT<IdxT> pv; pv.x0 = (IdxT)e.x; pv.x1 = (IdxT)e.y; pv.x2 = e.z; pv.info = (uint32_t)(x + lane + 1); curr[__popc(pmask & ((1u << lane) - 1u))] = pv; }
+            n_curr = (uint32_t)__popc(pmask);
+            n_ext += (unsigned long long)steps;
+            if (brk) { fwd_done = true; i = x + steps; }
+            else {
+                ik.x0 = (IdxT)__shfl_sync(FULL, e.x, KMER_K - 1); ik.x1 = (IdxT)__shfl_sync(FULL, e.y, KMER_K - 1);
+                ik.x2 = __shfl_sync(FULL, e.z, KMER_K - 1); ik.info = (uint32_t)(x + KMER_K);
+                i = x + KMER_K;
+            }
+        }
+    }
+    if (!fwd_done)
+    for (; i < len; ++i) {
         const int b = q[i];
         if (b < 4) {
             IvT<IdxT> ok = extend1<IdxT, 0>(C, ik, 3 - b); ++n_ext;
@@ -276,7 +306,7 @@ __device__ __forceinline__ int seed_strategy1(const Ctx<IdxT>& C, int len, const
 #pragma unroll
         for (int t = 0; t < KMER_K; ++t) { const uint32_t b = q[x + t]; acgt = acgt && b < 4; idx = idx << 2 | (b & 3); }
         if (acgt) {
-            const uint4 e = __ldg(C.kmer_tab + idx);
+            const uint4 e = __ldg(C.kmer_tab + kmer_level_off(KMER_K) + idx);
             ik.x0 = (IdxT)e.x; ik.x1 = (IdxT)e.y; ik.x2 = e.z;
             i = x + KMER_K; n_ext += KMER_K - 1;   // the roofline unit stays the reference's count of bwt_extend calls
         }
@@ -470,23 +500,20 @@ template <class IdxT, bool SMEM> void launch_mode(const SeedParams& p, const Dev
 
 }  // namespace
 
-size_t kmer_table_bytes() { return ((size_t)1 << (2 * KMER_K)) * sizeof(uint4); }
+size_t kmer_table_bytes() { return (size_t)kmer_level_off(KMER_K + 1) * sizeof(uint4); }
 
-// builds the table into `tab` (kmer_table_bytes()); `tmp` must hold a quarter of it.  32-bit indices only.
-void build_kmer_table(const DevIndex& ix, void* tab, void* tmp, cudaStream_t st, uint64_t* launches) {
-    uint4* a = reinterpret_cast<uint4*>(tab); uint4* b = reinterpret_cast<uint4*>(tmp);
-    // levels alternate between the two buffers so that the last level (KMER_K) lands in `tab`
-    uint4* cur = (KMER_K & 1) ? a : b;
+// builds every level of the prefix table into `tab` (kmer_table_bytes()).  32-bit indices only.
+void build_kmer_table(const DevIndex& ix, void* tab, void* /*unused*/, cudaStream_t st, uint64_t* launches) {
+    uint4* base = reinterpret_cast<uint4*>(tab);
     const uint32_t L2a = (uint32_t)ix.L2[0], L2c = (uint32_t)ix.L2[1], L2g = (uint32_t)ix.L2[2], L2t = (uint32_t)ix.L2[3], L2n = (uint32_t)ix.L2[4];
-    k_kmer_level0<<<1, 32, 0, st>>>(cur, L2a, L2c, L2g, L2t, L2n);
+    k_kmer_level0<<<1, 32, 0, st>>>(base + kmer_level_off(1), L2a, L2c, L2g, L2t, L2n);
     if (launches) ++*launches;
     uint32_t n = 4;
     for (int t = 2; t <= KMER_K; ++t) {
-        uint4* nxt = cur == a ? b : a;
         const unsigned blocks = (unsigned)std::min<uint32_t>((n + 255) / 256, 148u * 16u);
-        k_kmer_level<<<blocks ? blocks : 1, 256, 0, st>>>(cur, nxt, n, ix.occ, (uint32_t)ix.primary, L2a, L2c, L2g, L2t);
+        k_kmer_level<<<blocks ? blocks : 1, 256, 0, st>>>(base + kmer_level_off(t - 1), base + kmer_level_off(t), n, ix.occ, (uint32_t)ix.primary, L2a, L2c, L2g, L2t);
         if (launches) ++*launches;
-        cur = nxt; n *= 4;
+        n *= 4;
     }
 }
 

@@ -437,7 +437,7 @@ int run_pipeline(bsq_index* h) {
         {
             SeedParams P;
             P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = b.intv_cap;
-            P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = (b.max_len + 16) & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p + 0; P.overflow = b.ctl.p + 4; P.n_extend = ctr ? ctr + 0 : nullptr;
+            P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p + 0; P.overflow = b.ctl.p + 4; P.n_extend = ctr ? ctr + 0 : nullptr;
             launch_seed(P, ix, o, h->stream, nullptr); ++T.launches;
         }
         cudaEventRecord(ev[1], h->stream);
@@ -689,7 +689,7 @@ int bsq_debug_seed(bsq_index* h, const char* seqs, const uint64_t* offs, uint64_
     CUDA_CHECK(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, h->stream));
     SeedParams P;
     P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = (uint32_t)n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = cap;
-    P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = (b.max_len + 16) & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p; P.overflow = b.ctl.p + 4; P.n_extend = reinterpret_cast<unsigned long long*>(b.ctl.p + 8);
+    P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p; P.overflow = b.ctl.p + 4; P.n_extend = reinterpret_cast<unsigned long long*>(b.ctl.p + 8);
     launch_seed(P, ix, h->dopts, h->stream, nullptr);
     uint32_t ctl[8];
     CUDA_CHECK(cudaMemcpyAsync(ctl, b.ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));

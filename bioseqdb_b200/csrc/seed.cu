@@ -143,7 +143,7 @@ template <class IdxT> __device__ __forceinline__ void emit(Out& O, const IvT<Idx
 // bwt_smem1a with max_intv == 0 (the only way this path calls it).  la/lb: two interval lists of list_cap entries.
 template <class IdxT>
 __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int len, const uint8_t* q, int x, uint32_t min_intv, IvT<IdxT>* la,
-                                     IvT<IdxT>* lb, uint32_t list_cap, Out& O, unsigned long long& n_ext) {
+                                     IvT<IdxT>* lb, uint32_t list_cap, Out& O, unsigned long long& n_ext, const uint32_t* pk) {
     if (q[x] > 3) return x + 1;
     if (min_intv < 1) min_intv = 1;
     const int lane = lane_id();
@@ -214,22 +214,51 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
             // for all entries at once.  In list order: (1) only the FIRST dying entry can emit a MEM, and only if no
             // survivor precedes it (curr empty at its turn); (2) a survivor is pushed iff it is the first survivor or
             // its size differs from the PREVIOUS survivor's (a skipped survivor has the size of the last pushed one).
+            // Lane j owns entry j.  An entry whose match, once extended to q[i], is at most KMER_K long needs no Occ
+            // access at all: the bi-interval of a string does not depend on how it was reached, so it is read from the
+            // prefix table (all such entries of the step in ONE load instruction).  The remaining (long) entries are
+            // extended four at a time by 8-lane groups.
             bool any_push = false;
-            const int grp = lane >> 3;
-            const bool leader = (lane & 7) == 0;
-            for (uint32_t j0 = 0; j0 < n_prev; j0 += 4) {
-                const uint32_t j = j0 + (uint32_t)grp;
+            for (uint32_t j0 = 0; j0 < n_prev; j0 += 32) {
+                const uint32_t j = j0 + (uint32_t)lane;
                 const bool valid = j < n_prev;
                 IvT<IdxT> p; p.x0 = 1; p.x1 = 1; p.x2 = 0; p.info = 0;
                 if (valid) p = prev[reversed ? n_prev - 1 - j : j];
-                const IvT<IdxT> ok = extend4_back(C, p, c, valid);
+                IvT<IdxT> ok; ok.x0 = 0; ok.x1 = 0; ok.x2 = 0; ok.info = p.info;
+                const int lq = (int)p.info - i;                      // length of the match after prepending q[i]
+                const bool by_table = valid && sizeof(IdxT) == 4 && pk != nullptr && lq <= KMER_K;
+                if (by_table) {
+                    const uint32_t hi = pk[i >> 4], lo = pk[(i >> 4) + 1];
+                    const uint32_t kidx = __funnelshift_l(lo, hi, (i & 15) << 1) >> (32 - 2 * lq);
+                    const uint4 e = __ldg(C.kmer_tab + kmer_level_off(lq) + kidx);
+                    ok.x0 = (IdxT)e.x; ok.x1 = (IdxT)e.y; ok.x2 = e.z;
+                }
+                uint32_t todo = __ballot_sync(FULL, valid && !by_table);
+                n_ext += (unsigned long long)__popc(__ballot_sync(FULL, valid));
+                while (todo) {
+                    // the four lowest pending entries: group g (lanes 8g..8g+7) fetches entry s_g's interval, extends it, hands it back
+                    int s0 = __ffs(todo) - 1; uint32_t m = todo & (todo - 1);
+                    int s1 = m ? __ffs(m) - 1 : -1; m = m ? m & (m - 1) : 0;
+                    int s2 = m ? __ffs(m) - 1 : -1; m = m ? m & (m - 1) : 0;
+                    int s3 = m ? __ffs(m) - 1 : -1; m = m ? m & (m - 1) : 0;
+                    const int g = lane >> 3;
+                    const int src = g == 0 ? s0 : (g == 1 ? s1 : (g == 2 ? s2 : s3));
+                    IvT<IdxT> pg;
+                    pg.x0 = __shfl_sync(FULL, p.x0, src < 0 ? 0 : src); pg.x1 = __shfl_sync(FULL, p.x1, src < 0 ? 0 : src);
+                    pg.x2 = __shfl_sync(FULL, p.x2, src < 0 ? 0 : src); pg.info = 0;
+                    const IvT<IdxT> og = extend4_back(C, pg, c, src >= 0);
+                    // entry lane s_g pulls the result from the leader of group g
+                    const int mine = lane == s0 ? 0 : (lane == s1 ? 1 : (lane == s2 ? 2 : (lane == s3 ? 3 : -1)));
+                    const IdxT r0 = __shfl_sync(FULL, og.x0, mine < 0 ? 0 : mine << 3), r1 = __shfl_sync(FULL, og.x1, mine < 0 ? 0 : mine << 3);
+                    const uint32_t r2 = __shfl_sync(FULL, og.x2, mine < 0 ? 0 : mine << 3);
+                    if (mine >= 0) { ok.x0 = r0; ok.x1 = r1; ok.x2 = r2; }
+                    todo = m;
+                }
                 const bool surv = valid && ok.x2 >= min_intv;
-                // one bit per entry: the leader lane of each group votes
-                const uint32_t surv_mask = __ballot_sync(FULL, surv && leader);
-                const uint32_t die_mask = __ballot_sync(FULL, valid && !surv && leader);
-                n_ext += (unsigned long long)__popc(surv_mask | die_mask);
+                const uint32_t surv_mask = __ballot_sync(FULL, surv);
+                const uint32_t die_mask = __ballot_sync(FULL, valid && !surv);
                 if (die_mask && !any_push) {
-                    const int fd = __ffs(die_mask) - 1;          // leader lane of the first dying entry
+                    const int fd = __ffs(die_mask) - 1;          // first dying entry
                     if ((surv_mask & ((1u << fd) - 1u)) == 0 && (!have_mem || (uint32_t)(i + 1) < last_mem_start)) {
                         const uint32_t pinfo = __shfl_sync(FULL, p.info, fd);
                         const int slen = (int)pinfo - (i + 1);
@@ -243,10 +272,10 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
                     }
                 }
                 if (surv_mask) {
-                    const uint32_t before = surv_mask & ((1u << (grp << 3)) - 1u);   // surviving entries before mine
+                    const uint32_t before = surv_mask & ((1u << lane) - 1u);   // surviving entries before mine
                     const int pl = before ? 31 - __clz(before) : 0;
                     const uint32_t prev_sz = __shfl_sync(FULL, ok.x2, pl);
-                    const bool push = surv && leader && (before ? ok.x2 != prev_sz : (!any_push || ok.x2 != last_x2));
+                    const bool push = surv && (before ? ok.x2 != prev_sz : (!any_push || ok.x2 != last_x2));
                     const uint32_t push_mask = __ballot_sync(FULL, push);
                     if (push) curr[n_curr + __popc(push_mask & ((1u << lane) - 1u))] = ok;   // n_curr + pushes <= n_prev <= list_cap
                     n_curr += __popc(push_mask);
@@ -328,10 +357,10 @@ __device__ __forceinline__ int seed_strategy1(const Ctx<IdxT>& C, int len, const
 // the three passes of mem_collect_intv for one read
 template <class IdxT>
 __device__ __forceinline__ void collect_intv(const Ctx<IdxT>& C, const DevOpts& o, int len, const uint8_t* q, IvT<IdxT>* la, IvT<IdxT>* lb,
-                                             uint32_t list_cap, Out& O, unsigned long long& n_ext) {
+                                             uint32_t list_cap, Out& O, unsigned long long& n_ext, const uint32_t* pk) {
     int x = 0;
     while (x < len) {      // pass 1: all SMEMs
-        if (q[x] < 4) x = smem1(C, o, len, q, x, 1, la, lb, list_cap, O, n_ext);
+        if (q[x] < 4) x = smem1(C, o, len, q, x, 1, la, lb, list_cap, O, n_ext, pk);
         else ++x;
     }
     const uint32_t old_n = O.n < O.cap ? O.n : O.cap;
@@ -339,7 +368,7 @@ __device__ __forceinline__ void collect_intv(const Ctx<IdxT>& C, const DevOpts& 
         const Intv p = O.out[k];
         const int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
         if (end - start < o.split_len || p.x2 > (uint64_t)o.split_width) continue;
-        smem1(C, o, len, q, (start + end) >> 1, (uint32_t)p.x2 + 1, la, lb, list_cap, O, n_ext);
+        smem1(C, o, len, q, (start + end) >> 1, (uint32_t)p.x2 + 1, la, lb, list_cap, O, n_ext, pk);
     }
     if (o.max_mem_intv > 0) {                // pass 3: LAST-like
         x = 0;
@@ -434,7 +463,7 @@ __device__ void sort_by_info(Intv* out, uint32_t n_out, Intv* tmp, uint32_t tmp_
 // IdxT = uint32_t while the text has fewer than 2^32 rows; SMEM: interval lists and the read staged in shared
 // memory (otherwise in the per-warp global scratch: reads too long for shared memory)
 template <class IdxT, bool SMEM>
-__global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 5 : 1) seed_smem(SeedParams P, DevIndex ix, DevOpts o) {
+__global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 4 : 1) seed_smem(SeedParams P, DevIndex ix, DevOpts o) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ IdxT sL2[8];
     if (threadIdx.x < 5) sL2[threadIdx.x] = (IdxT)ix.L2[threadIdx.x];
@@ -470,8 +499,19 @@ __global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 5 
                 __syncwarp();
                 for (int i = lane; i < len; i += 32) sq[i] = q[i];
                 __syncwarp();
-                collect_intv(C, o, len, sq, la, lb, P.list_cap, O, n_ext);
-            } else collect_intv(C, o, len, q, la, lb, P.list_cap, O, n_ext);
+                // 2-bit packed copy of the read (16 bases per word, MSB first) for k-mer indices of arbitrary substrings
+                uint32_t* pk = nullptr;
+                if (sizeof(IdxT) == 4 && C.kmer_tab) {
+                    pk = reinterpret_cast<uint32_t*>(sq + ((len + 15) & ~15));
+                    for (int w = lane; w <= (len >> 4) + 1; w += 32) {
+                        uint32_t v = 0;
+                        for (int k = 0; k < 16; ++k) { const int pos = (w << 4) + k; v = v << 2 | (pos < len ? (sq[pos] & 3u) : 0u); }
+                        pk[w] = v;
+                    }
+                    __syncwarp();
+                }
+                collect_intv(C, o, len, sq, la, lb, P.list_cap, O, n_ext, pk);
+            } else collect_intv(C, o, len, q, la, lb, P.list_cap, O, n_ext, (const uint32_t*)nullptr);
             __syncwarp();
         }
         uint32_t n_out = O.n;

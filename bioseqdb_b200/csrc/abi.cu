@@ -75,6 +75,7 @@ struct bsq_index {
     Batch batch;
     bsq_timing timing;
     double* d_logtab = nullptr;
+    uint32_t* d_isa = nullptr;       // inverse SA for the unique-match shortcut of the seeding kernel (built lazily, 32-bit rows)
     void* d_kmer = nullptr;          // k-mer table of the LAST-like seeding pass (built lazily per device index)
     bool collect_counters = false;
     uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -153,6 +154,7 @@ int bsq_index_add_ref(bsq_index* h, int64_t id, const uint8_t* pac, uint32_t len
 
 static void free_index_arrays(bsq_index* h) {
     if (h->d_kmer) { cudaFree(h->d_kmer); h->d_kmer = nullptr; }
+    if (h->d_isa) { cudaFree(h->d_isa); h->d_isa = nullptr; }
     if (h->d_pac) cudaFree(h->d_pac); if (h->d_occ) cudaFree(h->d_occ); if (h->d_sa) cudaFree(h->d_sa);
     if (h->d_ann_offset) cudaFree(h->d_ann_offset); if (h->d_ann_len) cudaFree(h->d_ann_len); if (h->d_ann_id) cudaFree(h->d_ann_id);
     h->d_pac = nullptr; h->d_occ = nullptr; h->d_sa = nullptr; h->d_ann_offset = nullptr; h->d_ann_len = nullptr; h->d_ann_id = nullptr;
@@ -379,7 +381,13 @@ int upload_reads(bsq_index* h, const char* seqs, const uint64_t* offs, const int
 
 // k-mer table of the LAST-like seeding pass: built once per device index (also after a broadcast replica)
 int ensure_kmer_table(bsq_index* h, const DevIndex& ix) {
-    if (h->d_kmer || ix.sa_bytes != 4 || ix.seq_len < (1u << 16)) return BSQ_OK;
+    if (ix.sa_bytes != 4) return BSQ_OK;
+    if (!h->d_isa && !getenv("BSQ_NO_ISA")) {
+        CUDA_CHECK(cudaMalloc(&h->d_isa, (ix.seq_len + 1) * 4 + 64));
+        build_isa(ix, h->d_isa, h->stream, &h->timing.launches);
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    }
+    if (h->d_kmer || ix.seq_len < (1u << 16)) return BSQ_OK;
     CUDA_CHECK(cudaMalloc(&h->d_kmer, kmer_table_bytes()));
     build_kmer_table(ix, h->d_kmer, nullptr, h->stream, &h->timing.launches);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
@@ -437,7 +445,7 @@ int run_pipeline(bsq_index* h) {
         {
             SeedParams P;
             P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = b.intv_cap;
-            P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p + 0; P.overflow = b.ctl.p + 4; P.n_extend = ctr ? ctr + 0 : nullptr;
+            P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.isa = h->d_isa; P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p + 0; P.overflow = b.ctl.p + 4; P.n_extend = ctr ? ctr + 0 : nullptr;
             launch_seed(P, ix, o, h->stream, nullptr); ++T.launches;
         }
         cudaEventRecord(ev[1], h->stream);
@@ -689,7 +697,7 @@ int bsq_debug_seed(bsq_index* h, const char* seqs, const uint64_t* offs, uint64_
     CUDA_CHECK(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, h->stream));
     SeedParams P;
     P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = (uint32_t)n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = cap;
-    P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p; P.overflow = b.ctl.p + 4; P.n_extend = reinterpret_cast<unsigned long long*>(b.ctl.p + 8);
+    P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.isa = h->d_isa; P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p; P.overflow = b.ctl.p + 4; P.n_extend = reinterpret_cast<unsigned long long*>(b.ctl.p + 8);
     launch_seed(P, ix, h->dopts, h->stream, nullptr);
     uint32_t ctl[8];
     CUDA_CHECK(cudaMemcpyAsync(ctl, b.ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));

@@ -30,6 +30,8 @@ template <class IdxT> struct Ctx {
     const uint32_t* occ;
     const IdxT* sL2;         // shared memory: L2[0..4]
     const uint4* kmer_tab;   // prefix table (x0, x1, x2, -) of all t-mers, t <= KMER_K; nullptr when absent
+    // unique-match shortcut (32-bit rows): full SA, inverse SA and the 2-bit text; isa == nullptr disables it
+    const uint32_t* sa; const uint32_t* isa; const uint8_t* pac; uint32_t l_pac, n;
     IdxT primary;
     uint32_t sym_base;       // first symbol covered by this lane's word (symbol lanes), 1 << 20 for checkpoint lanes
     int cnt_sym;             // symbol whose checkpoint LOW word this lane holds, -1 otherwise
@@ -125,6 +127,40 @@ __device__ __forceinline__ IvT<IdxT> extend4_back(const Ctx<IdxT>& C, const IvT<
     return ok;
 }
 
+// ---- unique-match shortcut --------------------------------------------------------------------------
+// An interval of size 1 is ONE occurrence of the match at text position pos = SA[x0].  Extending it can only keep
+// it (the next text base equals the read base) or kill it, so the FM-index need not be consulted: the warp
+// compares read and text directly, 32 bases per step, and the rows of the extended match come from the inverse
+// suffix array -- x0 = ISA[start], x1 = ISA[n - start - length] (T is its own reverse complement).  The result
+// is the bi-interval bwt_extend would have produced, because the bi-interval of a string is unique.
+template <class IdxT> __device__ __forceinline__ uint32_t text_base(const Ctx<IdxT>& C, uint32_t p) {
+    return p < C.l_pac ? pac_get(C.pac, p) : 3u - pac_get(C.pac, (int64_t)2 * C.l_pac - 1 - p);
+}
+// number of consecutive k in [0, maxlen) with q[qpos + k] an ACGT base equal to T[tpos + k]
+template <class IdxT> __device__ __forceinline__ int match_run_fwd(const Ctx<IdxT>& C, uint32_t tpos, const uint8_t* q, int qpos, int maxlen) {
+    const int lane = lane_id();
+    for (int base = 0; base < maxlen; base += 32) {
+        const int k = base + lane;
+        bool ok = k < maxlen;
+        if (ok) { const uint32_t p = tpos + (uint32_t)k; const uint32_t b = q[qpos + k]; ok = p < C.n && b < 4 && text_base(C, p) == b; }
+        const uint32_t bad = __ballot_sync(FULL, !ok);
+        if (bad) { const int r = base + __ffs(bad) - 1; return r < maxlen ? r : maxlen; }
+    }
+    return maxlen;
+}
+// backwards: number of consecutive k in [0, maxlen) with q[qpos - k] == T[tpos - 1 - k]
+template <class IdxT> __device__ __forceinline__ int match_run_bwd(const Ctx<IdxT>& C, uint32_t tpos, const uint8_t* q, int qpos, int maxlen) {
+    const int lane = lane_id();
+    for (int base = 0; base < maxlen; base += 32) {
+        const int k = base + lane;
+        bool ok = k < maxlen;
+        if (ok) { const uint32_t b = q[qpos - k]; ok = (uint32_t)k < tpos && b < 4 && text_base(C, tpos - 1 - (uint32_t)k) == b; }
+        const uint32_t bad = __ballot_sync(FULL, !ok);
+        if (bad) { const int r = base + __ffs(bad) - 1; return r < maxlen ? r : maxlen; }
+    }
+    return maxlen;
+}
+
 template <class IdxT> __device__ __forceinline__ IvT<IdxT> set_intv(const Ctx<IdxT>& C, int c) {
     IvT<IdxT> ik;
     ik.x0 = C.sL2[c] + 1; ik.x1 = C.sL2[3 - c] + 1; ik.x2 = (uint32_t)(C.sL2[c + 1] - C.sL2[c]); ik.info = 0;
@@ -182,6 +218,17 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
     }
     if (!fwd_done)
     for (; i < len; ++i) {
+        if (sizeof(IdxT) == 4 && C.isa && ik.x2 == 1 && min_intv == 1) {
+            // unique match q[x .. i): walk to the first base that does not match (or the end of the read) in one go
+            const uint32_t pos = C.sa[ik.x0];
+            const int run = match_run_fwd(C, pos + (uint32_t)(i - x), q, i, len - i);
+            if (run > 0) { i += run; ik.x1 = (IdxT)C.isa[C.n - pos - (uint32_t)(i - x)]; ik.info = (uint32_t)i; n_ext += (unsigned long long)run; }
+            if (i == len) break;                               // matched to the end: recorded after the loop
+            if (q[i] < 4) ++n_ext;                             // the extension the scalar code tries next: it empties the interval
+            if (n_curr < list_cap) { if (lane == 0) curr[n_curr] = ik; } else O.ovf = true;
+            ++n_curr;
+            break;
+        }
         const int b = q[i];
         if (b < 4) {
             IvT<IdxT> ok = extend1<IdxT, 0>(C, ik, 3 - b); ++n_ext;
@@ -205,36 +252,49 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
     uint32_t n_prev = n_curr; bool reversed = true;
     const uint32_t out_first = O.n;
     bool have_mem = false; uint32_t last_mem_start = 0;
-    for (i = x - 1; i >= -1; --i) {
-        const int c = i < 0 ? -1 : (q[i] < 4 ? q[i] : -1);
-        n_curr = 0;
-        uint32_t last_x2 = 0;
-        if (c >= 0 && n_prev >= 2) {
-            // several entries: lane group g extends entry j0 + g, then the sequential bookkeeping of bwt_smem1a is evaluated
-            // for all entries at once.  In list order: (1) only the FIRST dying entry can emit a MEM, and only if no
-            // survivor precedes it (curr empty at its turn); (2) a survivor is pushed iff it is the first survivor or
-            // its size differs from the PREVIOUS survivor's (a skipped survivor has the size of the last pushed one).
-            // Lane j owns entry j.  An entry whose match, once extended to q[i], is at most KMER_K long needs no Occ
-            // access at all: the bi-interval of a string does not depend on how it was reached, so it is read from the
-            // prefix table (all such entries of the step in ONE load instruction).  The remaining (long) entries are
-            // extended four at a time by 8-lane groups.
-            bool any_push = false;
-            for (uint32_t j0 = 0; j0 < n_prev; j0 += 32) {
-                const uint32_t j = j0 + (uint32_t)lane;
-                const bool valid = j < n_prev;
-                IvT<IdxT> p; p.x0 = 1; p.x1 = 1; p.x2 = 0; p.info = 0;
-                if (valid) p = prev[reversed ? n_prev - 1 - j : j];
-                IvT<IdxT> ok; ok.x0 = 0; ok.x1 = 0; ok.x2 = 0; ok.info = p.info;
+    if (n_prev <= 32) {
+        // Lane k keeps entry k of the list (longest match first) in registers for the whole backward walk.  Every
+        // entry walks on its own -- the interval of q[i .. e_k) does not depend on the other entries -- and the list
+        // logic of bwt_smem1a reduces to two masks per step: an entry stays in the list iff it survives
+        // (size >= min_intv) and its size differs from the nearest surviving longer entry's (an entry with the size
+        // of a longer one IS that longer one's occurrence set from here on); a MEM is emitted exactly when the
+        // first entry of the list dies (longer matches die first, so nothing survives ahead of it, and its start
+        // i + 1 is below every start emitted before).
+        const bool own = (uint32_t)lane < n_prev;
+        IvT<IdxT> p; p.x0 = 1; p.x1 = 1; p.x2 = 0; p.info = 0;
+        if (own) p = prev[n_prev - 1 - (uint32_t)lane];
+        uint32_t present = __ballot_sync(FULL, own);
+        // unique first entry: its walk is one text comparison (uq_stop = the index i at which it dies, uq_x0 = its row then)
+        bool uq = false; int uq_stop = 0; IdxT uq_x0 = 0;
+        for (i = x - 1; i >= -1; --i) {
+            const int first = __ffs(present) - 1;
+            if (sizeof(IdxT) == 4 && C.isa && min_intv == 1 && !uq) {
+                const uint32_t fx2 = __shfl_sync(FULL, p.x2, first);
+                if (fx2 == 1) {
+                    const uint32_t fx0 = (uint32_t)__shfl_sync(FULL, p.x0, first);
+                    const uint32_t pos = C.sa[fx0];
+                    const int run = match_run_bwd(C, pos, q, i, i + 1);
+                    uq = true; uq_stop = i - run; uq_x0 = run > 0 ? (IdxT)C.isa[pos - (uint32_t)run] : (IdxT)fx0;
+                }
+            }
+            if (uq && present == (1u << first) && i > uq_stop) { n_ext += (unsigned long long)(i - uq_stop); i = uq_stop; }   // alone: jump
+            const int c = i < 0 ? -1 : (q[i] < 4 ? q[i] : -1);
+            const bool act = (present >> lane) & 1u;
+            IvT<IdxT> ok; ok.x0 = p.x0; ok.x1 = p.x1; ok.x2 = 0; ok.info = p.info;
+            if (c >= 0) {
+                const bool is_uq = uq && lane == first;
+                if (is_uq) ok.x2 = i > uq_stop ? 1u : 0u;
                 const int lq = (int)p.info - i;                      // length of the match after prepending q[i]
-                const bool by_table = valid && sizeof(IdxT) == 4 && pk != nullptr && lq <= KMER_K;
+                // a match of at most KMER_K bases needs no Occ access: its bi-interval is in the prefix table
+                const bool by_table = act && !is_uq && sizeof(IdxT) == 4 && pk != nullptr && lq <= KMER_K;
                 if (by_table) {
                     const uint32_t hi = pk[i >> 4], lo = pk[(i >> 4) + 1];
                     const uint32_t kidx = __funnelshift_l(lo, hi, (i & 15) << 1) >> (32 - 2 * lq);
                     const uint4 e = __ldg(C.kmer_tab + kmer_level_off(lq) + kidx);
                     ok.x0 = (IdxT)e.x; ok.x1 = (IdxT)e.y; ok.x2 = e.z;
                 }
-                uint32_t todo = __ballot_sync(FULL, valid && !by_table);
-                n_ext += (unsigned long long)__popc(__ballot_sync(FULL, valid));
+                uint32_t todo = __ballot_sync(FULL, act && !is_uq && !by_table);
+                n_ext += (unsigned long long)__popc(present);
                 while (todo) {
                     // the four lowest pending entries: group g (lanes 8g..8g+7) fetches entry s_g's interval, extends it, hands it back
                     int s0 = __ffs(todo) - 1; uint32_t m = todo & (todo - 1);
@@ -247,43 +307,38 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
                     pg.x0 = __shfl_sync(FULL, p.x0, src < 0 ? 0 : src); pg.x1 = __shfl_sync(FULL, p.x1, src < 0 ? 0 : src);
                     pg.x2 = __shfl_sync(FULL, p.x2, src < 0 ? 0 : src); pg.info = 0;
                     const IvT<IdxT> og = extend4_back(C, pg, c, src >= 0);
-                    // entry lane s_g pulls the result from the leader of group g
                     const int mine = lane == s0 ? 0 : (lane == s1 ? 1 : (lane == s2 ? 2 : (lane == s3 ? 3 : -1)));
                     const IdxT r0 = __shfl_sync(FULL, og.x0, mine < 0 ? 0 : mine << 3), r1 = __shfl_sync(FULL, og.x1, mine < 0 ? 0 : mine << 3);
                     const uint32_t r2 = __shfl_sync(FULL, og.x2, mine < 0 ? 0 : mine << 3);
                     if (mine >= 0) { ok.x0 = r0; ok.x1 = r1; ok.x2 = r2; }
                     todo = m;
                 }
-                const bool surv = valid && ok.x2 >= min_intv;
-                const uint32_t surv_mask = __ballot_sync(FULL, surv);
-                const uint32_t die_mask = __ballot_sync(FULL, valid && !surv);
-                if (die_mask && !any_push) {
-                    const int fd = __ffs(die_mask) - 1;          // first dying entry
-                    if ((surv_mask & ((1u << fd) - 1u)) == 0 && (!have_mem || (uint32_t)(i + 1) < last_mem_start)) {
-                        const uint32_t pinfo = __shfl_sync(FULL, p.info, fd);
-                        const int slen = (int)pinfo - (i + 1);
-                        if (slen >= o.min_seed_len) {
-                            if (O.n < O.cap) {
-                                if (lane == fd) { Intv v; v.x0 = p.x0; v.x1 = p.x1; v.x2 = p.x2; v.info = (uint64_t)(uint32_t)(i + 1) << 32 | p.info; O.out[O.n] = v; }
-                            } else O.ovf = true;
-                            ++O.n;
-                        }
-                        have_mem = true; last_mem_start = (uint32_t)(i + 1);
-                    }
-                }
-                if (surv_mask) {
-                    const uint32_t before = surv_mask & ((1u << lane) - 1u);   // surviving entries before mine
-                    const int pl = before ? 31 - __clz(before) : 0;
-                    const uint32_t prev_sz = __shfl_sync(FULL, ok.x2, pl);
-                    const bool push = surv && (before ? ok.x2 != prev_sz : (!any_push || ok.x2 != last_x2));
-                    const uint32_t push_mask = __ballot_sync(FULL, push);
-                    if (push) curr[n_curr + __popc(push_mask & ((1u << lane) - 1u))] = ok;   // n_curr + pushes <= n_prev <= list_cap
-                    n_curr += __popc(push_mask);
-                    last_x2 = __shfl_sync(FULL, ok.x2, 31 - __clz(surv_mask));   // size of the last survivor so far
-                    any_push = true;   // a survivor exists => the first survivor was pushed
-                }
             }
-        } else
+            const bool alive = act && ok.x2 >= min_intv;
+            const uint32_t alive_mask = __ballot_sync(FULL, alive);
+            if (!((alive_mask >> first) & 1u)) {
+                const uint32_t pinfo = __shfl_sync(FULL, p.info, first);
+                if ((int)pinfo - (i + 1) >= o.min_seed_len) {
+                    if (O.n < O.cap) {
+                        if (lane == first) { Intv v; v.x0 = uq ? uq_x0 : p.x0; v.x1 = p.x1; v.x2 = p.x2; v.info = (uint64_t)(uint32_t)(i + 1) << 32 | p.info; O.out[O.n] = v; }
+                    } else O.ovf = true;
+                    ++O.n;
+                }
+                uq = false;
+            }
+            const uint32_t before = alive_mask & ((1u << lane) - 1u);          // surviving entries ahead of mine
+            const uint32_t prev_sz = __shfl_sync(FULL, ok.x2, before ? 31 - __clz(before) : 0);
+            const bool keep = alive && (before == 0 || ok.x2 != prev_sz);
+            present = __ballot_sync(FULL, keep);
+            if (keep) { p.x0 = ok.x0; p.x1 = ok.x1; p.x2 = ok.x2; }
+            if (!present) break;
+        }
+    } else
+    for (i = x - 1; i >= -1; --i) {
+        // more entries than lanes (highly repetitive reads): the list logic of bwt_smem1a, one entry at a time
+        const int c = i < 0 ? -1 : (q[i] < 4 ? q[i] : -1);
+        n_curr = 0;
+        uint32_t last_x2 = 0;
         for (uint32_t j = 0; j < n_prev; ++j) {
             const IvT<IdxT> p = prev[reversed ? n_prev - 1 - j : j];
             IvT<IdxT> ok; ok.x2 = 0;
@@ -341,6 +396,27 @@ __device__ __forceinline__ int seed_strategy1(const Ctx<IdxT>& C, int len, const
         }
     }
     for (; i < len; ++i) {
+        if (sizeof(IdxT) == 4 && C.isa && ik.x2 == 1 && max_intv > 1 && i - x <= min_len) {
+            // unique match q[x .. i): the walk ends at j = x + min_len (emit iff still matching), at an ambiguous base
+            // (nothing emitted), or at the end of the read
+            const int stop = x + min_len;                       // index of the base whose extension triggers the emission test
+            const int lim = (stop < len ? stop + 1 : len) - i;  // bases q[i .. i + lim) are looked at
+            const int lane = lane_id();
+            bool isn = false;
+            if (lane < lim) isn = q[i + lane] > 3;              // lim <= min_len + 1 - (i - x) <= 32 for min_seed_len <= 31
+            const uint32_t nmask = __ballot_sync(FULL, isn);
+            const uint32_t pos = C.sa[ik.x0];
+            const int run = match_run_fwd(C, pos + (uint32_t)(i - x), q, i, lim);
+            if (nmask) { const int jn = i + __ffs(nmask) - 1; n_ext += (unsigned long long)(jn - i); return jn + 1; }
+            n_ext += (unsigned long long)lim;
+            if (stop >= len) return len;
+            if (run == lim) {
+                IvT<IdxT> ok = ik;
+                ok.x1 = (IdxT)C.isa[C.n - pos - (uint32_t)(stop + 1 - x)]; ok.x2 = 1;
+                emit(O, ok, (uint32_t)x, (uint32_t)(stop + 1));
+            }
+            return stop + 1;
+        }
         const int b = q[i];
         if (b < 4) {
             IvT<IdxT> ok = extend1<IdxT, 0>(C, ik, 3 - b); ++n_ext;
@@ -425,6 +501,10 @@ __global__ void k_kmer_level0(uint4* out, uint32_t L2a, uint32_t L2c, uint32_t L
     if (c < 4) out[c] = make_uint4(L2[c] + 1, L2[3 - c] + 1, L2[c + 1] - L2[c], 0u);
 }
 
+__global__ void k_build_isa(const uint32_t* __restrict__ sa, uint64_t rows, uint32_t* __restrict__ isa) {
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (uint64_t)gridDim.x * blockDim.x) isa[sa[r]] = (uint32_t)r;
+}
+
 // sort a read's intervals by info (ties are bit-identical records, so any correct sort equals ks_introsort's result)
 __device__ void sort_by_info(Intv* out, uint32_t n_out, Intv* tmp, uint32_t tmp_cap, uint32_t* overflow) {
     const int lane = lane_id();
@@ -475,6 +555,7 @@ __global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 4 
     unsigned long long n_ext = 0;
     Ctx<IdxT> C;
     C.occ = ix.occ; C.sL2 = sL2; C.primary = (IdxT)ix.primary; C.kmer_tab = P.kmer_tab;
+    C.sa = reinterpret_cast<const uint32_t*>(ix.sa); C.isa = sizeof(IdxT) == 4 ? P.isa : nullptr; C.pac = ix.pac; C.l_pac = (uint32_t)ix.l_pac; C.n = (uint32_t)ix.seq_len;
     {
         const int idx = lane & 15;
         C.sym_base = idx >= 8 ? (uint32_t)((idx - 8) << 4) : (1u << 20);
@@ -555,6 +636,14 @@ void build_kmer_table(const DevIndex& ix, void* tab, void* /*unused*/, cudaStrea
         if (launches) ++*launches;
         n *= 4;
     }
+}
+
+// inverse suffix array (32-bit rows): isa[SA[r]] = r for the n + 1 rows; `isa` holds n + 1 entries
+void build_isa(const DevIndex& ix, uint32_t* isa, cudaStream_t st, uint64_t* launches) {
+    const uint64_t rows = ix.seq_len + 1;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((rows + 255) / 256, 148ull * 16);
+    k_build_isa<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(ix.sa), rows, isa);
+    if (launches) ++*launches;
 }
 
 int seed_resident_warps() {

@@ -18,6 +18,7 @@ struct SeedParams {
     int lists_in_smem;        // narrow path: the two interval lists of a warp and the read live in shared memory
     uint32_t read_cap;        // bytes reserved per warp for the staged read (>= longest read, multiple of 16)
     const uint4* kmer_tab;    // bi-intervals of all 12-mers for the LAST-like pass (32-bit indices only), or nullptr
+    const uint32_t* isa;      // inverse suffix array for the unique-match shortcut (32-bit rows), or nullptr
     uint32_t* ticket;
     uint32_t* overflow;       // set to 1 when a read needs more than cap intervals
     unsigned long long* n_extend;  // optional counter (roofline units); nullptr in production
@@ -25,5 +26,6 @@ struct SeedParams {
 void launch_seed(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, int* n_warps_out);
 int seed_resident_warps();
 size_t kmer_table_bytes();
+void build_isa(const DevIndex& ix, uint32_t* isa, cudaStream_t st, uint64_t* launches);
 void build_kmer_table(const DevIndex& ix, void* tab, void* tmp, cudaStream_t st, uint64_t* launches);
 bool seed_lists_fit_smem(uint32_t list_cap, uint32_t read_cap, int sa_bytes);

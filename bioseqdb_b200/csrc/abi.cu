@@ -76,7 +76,7 @@ struct bsq_index {
     bsq_timing timing;
     double* d_logtab = nullptr;
     uint32_t* d_isa = nullptr;       // inverse SA for the unique-match shortcut of the seeding kernel (built lazily, 32-bit rows)
-    void* d_kmer = nullptr;          // k-mer table of the LAST-like seeding pass (built lazily per device index)
+    void* d_kmer = nullptr; int kmer_k = 0;          // k-mer table of the LAST-like seeding pass (built lazily per device index)
     bool collect_counters = false;
     uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -388,8 +388,10 @@ int ensure_kmer_table(bsq_index* h, const DevIndex& ix) {
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
     }
     if (h->d_kmer || ix.seq_len < (1u << 16)) return BSQ_OK;
-    CUDA_CHECK(cudaMalloc(&h->d_kmer, kmer_table_bytes()));
-    build_kmer_table(ix, h->d_kmer, nullptr, h->stream, &h->timing.launches);
+    h->kmer_k = kmer_table_depth(ix.seq_len);
+    if (const char* e = getenv("BSQ_KMER_K")) { const int k = atoi(e); if (k >= 8 && k <= 14) h->kmer_k = k; }
+    CUDA_CHECK(cudaMalloc(&h->d_kmer, kmer_table_bytes(h->kmer_k)));
+    build_kmer_table(ix, h->d_kmer, h->kmer_k, h->stream, &h->timing.launches);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
     return BSQ_OK;
 }
@@ -445,7 +447,7 @@ int run_pipeline(bsq_index* h) {
         {
             SeedParams P;
             P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = b.intv_cap;
-            P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.isa = h->d_isa; P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p + 0; P.overflow = b.ctl.p + 4; P.n_extend = ctr ? ctr + 0 : nullptr;
+            P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.kmer_k = h->kmer_k; P.isa = h->d_isa; P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p + 0; P.overflow = b.ctl.p + 4; P.n_extend = ctr ? ctr + 0 : nullptr;
             launch_seed(P, ix, o, h->stream, nullptr); ++T.launches;
         }
         cudaEventRecord(ev[1], h->stream);
@@ -697,7 +699,7 @@ int bsq_debug_seed(bsq_index* h, const char* seqs, const uint64_t* offs, uint64_
     CUDA_CHECK(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, h->stream));
     SeedParams P;
     P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = (uint32_t)n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = cap;
-    P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.isa = h->d_isa; P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p; P.overflow = b.ctl.p + 4; P.n_extend = reinterpret_cast<unsigned long long*>(b.ctl.p + 8);
+    P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.kmer_k = h->kmer_k; P.isa = h->d_isa; P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p; P.overflow = b.ctl.p + 4; P.n_extend = reinterpret_cast<unsigned long long*>(b.ctl.p + 8);
     launch_seed(P, ix, h->dopts, h->stream, nullptr);
     uint32_t ctl[8];
     CUDA_CHECK(cudaMemcpyAsync(ctl, b.ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));

@@ -18,7 +18,9 @@ namespace {
 
 constexpr int SEED_THREADS = 256;
 constexpr int SEED_WARPS = SEED_THREADS / 32;
-constexpr int KMER_K = 12;   // prefix table: bi-intervals of every t-mer, t = 1..12 (levels back to back, 22.4 M entries x 16 B = 358 MB)
+// prefix table: bi-intervals of every t-mer, t = 1..K, levels back to back.  K is chosen per index, about log4 of the text
+// length, so that a K-mer has a handful of occurrences at most: 12 -> 358 MB, 13 -> 1.4 GB, 14 -> 5.7 GB (of 180 GB HBM)
+constexpr int KMER_K_MAX = 14;
 __host__ __device__ constexpr uint32_t kmer_level_off(int t) { return ((1u << (2 * t)) - 4u) / 3u; }   // first entry of level t
 
 template <class IdxT> struct IvT { IdxT x0, x1; uint32_t x2, info; };   // info = end of the match on the query
@@ -29,7 +31,8 @@ template <> struct __align__(16) IvT<uint32_t> { uint32_t x0, x1, x2, info; };
 template <class IdxT> struct Ctx {
     const uint32_t* occ;
     const IdxT* sL2;         // shared memory: L2[0..4]
-    const uint4* kmer_tab;   // prefix table (x0, x1, x2, -) of all t-mers, t <= KMER_K; nullptr when absent
+    const uint4* kmer_tab;   // prefix table (x0, x1, x2, -) of all t-mers, t <= kk; nullptr when absent
+    int kk;                  // depth of the prefix table
     // unique-match shortcut (32-bit rows): full SA, inverse SA and the 2-bit text; isa == nullptr disables it
     const uint32_t* sa; const uint32_t* isa; const uint8_t* pac; uint32_t l_pac, n;
     IdxT primary;
@@ -161,6 +164,16 @@ template <class IdxT> __device__ __forceinline__ int match_run_bwd(const Ctx<Idx
     return maxlen;
 }
 
+// 16 bases of the read starting at x, 2 bits each, first base in the top bits; false when one of the first K is ambiguous.
+// pk = 2-bit packed copy of the read (shared-memory mode), has_n = the read holds an ambiguous base somewhere.
+__device__ __forceinline__ bool kmer_word(const uint8_t* q, const uint32_t* pk, bool has_n, int x, int K, uint32_t& w) {
+    if (pk != nullptr && !has_n) { w = __funnelshift_l(pk[(x >> 4) + 1], pk[x >> 4], (x & 15) << 1); return true; }
+    uint32_t idx = 0; bool acgt = true;
+    for (int t = 0; t < K; ++t) { const uint32_t b = q[x + t]; acgt = acgt && b < 4; idx = idx << 2 | (b & 3); }
+    w = idx << (32 - 2 * K);
+    return acgt;
+}
+
 template <class IdxT> __device__ __forceinline__ IvT<IdxT> set_intv(const Ctx<IdxT>& C, int c) {
     IvT<IdxT> ik;
     ik.x0 = C.sL2[c] + 1; ik.x1 = C.sL2[3 - c] + 1; ik.x2 = (uint32_t)(C.sL2[c + 1] - C.sL2[c]); ik.info = 0;
@@ -179,9 +192,10 @@ template <class IdxT> __device__ __forceinline__ void emit(Out& O, const IvT<Idx
 // bwt_smem1a with max_intv == 0 (the only way this path calls it).  la/lb: two interval lists of list_cap entries.
 template <class IdxT>
 __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int len, const uint8_t* q, int x, uint32_t min_intv, IvT<IdxT>* la,
-                                     IvT<IdxT>* lb, uint32_t list_cap, Out& O, unsigned long long& n_ext, const uint32_t* pk) {
+                                     IvT<IdxT>* lb, uint32_t list_cap, Out& O, unsigned long long& n_ext, const uint32_t* pk, bool has_n) {
     if (q[x] > 3) return x + 1;
     if (min_intv < 1) min_intv = 1;
+    const int KK = C.kk;
     const int lane = lane_id();
     IvT<IdxT> ik = set_intv(C, q[x]);
     ik.info = (uint32_t)(x + 1);
@@ -189,20 +203,18 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
     uint32_t n_curr = 0;
     int i = x + 1;
     bool fwd_done = false;
-    if (sizeof(IdxT) == 4 && C.kmer_tab && x + KMER_K <= len) {
-        // The first KMER_K - 1 forward steps from the prefix table: lane t fetches the interval of q[x .. x+t]; the step
+    if (sizeof(IdxT) == 4 && C.kmer_tab && x + KK <= len) {
+        // The first KK - 1 forward steps from the prefix table: lane t fetches the interval of q[x .. x+t]; the step
         // that appends base t+1 records lane t's interval when the size changes and stops the walk when it falls below
         // min_intv -- the same decisions the scalar loop takes, evaluated for all steps at once.
-        uint32_t idx = 0; bool acgt = true;
-#pragma unroll
-        for (int t = 0; t < KMER_K; ++t) { const uint32_t b = q[x + t]; acgt = acgt && b < 4; idx = idx << 2 | (b & 3); }
-        if (acgt) {
+        uint32_t w;
+        if (kmer_word(q, pk, has_n, x, KK, w)) {
             uint4 e = make_uint4(0, 0, 0, 0);
-            if (lane < KMER_K) e = __ldg(C.kmer_tab + kmer_level_off(lane + 1) + (idx >> (2 * (KMER_K - 1 - lane))));
+            if (lane < KK) e = __ldg(C.kmer_tab + kmer_level_off(lane + 1) + (w >> (30 - 2 * lane)));
             const uint32_t x2n = __shfl_down_sync(FULL, e.z, 1);
-            const bool change = lane < KMER_K - 1 && x2n != e.z;
+            const bool change = lane < KK - 1 && x2n != e.z;
             const uint32_t brk = __ballot_sync(FULL, change && x2n < min_intv);
-            const int steps = brk ? __ffs(brk) : KMER_K - 1;
+            const int steps = brk ? __ffs(brk) : KK - 1;
             const bool push = change && lane < steps;
             const uint32_t pmask = __ballot_sync(FULL, push);
             if (push) { IvT<IdxT> pv; pv.x0 = (IdxT)e.x; pv.x1 = (IdxT)e.y; pv.x2 = e.z; pv.info = (uint32_t)(x + lane + 1); curr[__popc(pmask & ((1u << lane) - 1u))] = pv; }
@@ -210,9 +222,9 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
             n_ext += (unsigned long long)steps;
             if (brk) { fwd_done = true; i = x + steps; }
             else {
-                ik.x0 = (IdxT)__shfl_sync(FULL, e.x, KMER_K - 1); ik.x1 = (IdxT)__shfl_sync(FULL, e.y, KMER_K - 1);
-                ik.x2 = __shfl_sync(FULL, e.z, KMER_K - 1); ik.info = (uint32_t)(x + KMER_K);
-                i = x + KMER_K;
+                ik.x0 = (IdxT)__shfl_sync(FULL, e.x, KK - 1); ik.x1 = (IdxT)__shfl_sync(FULL, e.y, KK - 1);
+                ik.x2 = __shfl_sync(FULL, e.z, KK - 1); ik.info = (uint32_t)(x + KK);
+                i = x + KK;
             }
         }
     }
@@ -285,8 +297,8 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
                 const bool is_uq = uq && lane == first;
                 if (is_uq) ok.x2 = i > uq_stop ? 1u : 0u;
                 const int lq = (int)p.info - i;                      // length of the match after prepending q[i]
-                // a match of at most KMER_K bases needs no Occ access: its bi-interval is in the prefix table
-                const bool by_table = act && !is_uq && sizeof(IdxT) == 4 && pk != nullptr && lq <= KMER_K;
+                // a match of at most KK bases needs no Occ access: its bi-interval is in the prefix table
+                const bool by_table = act && !is_uq && sizeof(IdxT) == 4 && pk != nullptr && lq <= KK;
                 if (by_table) {
                     const uint32_t hi = pk[i >> 4], lo = pk[(i >> 4) + 1];
                     const uint32_t kidx = __funnelshift_l(lo, hi, (i & 15) << 1) >> (32 - 2 * lq);
@@ -379,20 +391,18 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
 
 template <class IdxT>
 __device__ __forceinline__ int seed_strategy1(const Ctx<IdxT>& C, int len, const uint8_t* q, int x, int min_len, uint32_t max_intv, Out& O,
-                                              unsigned long long& n_ext) {
+                                              unsigned long long& n_ext, const uint32_t* pk, bool has_n) {
     if (q[x] > 3) return x + 1;
     IvT<IdxT> ik = set_intv(C, q[x]);
     int i = x + 1;
-    // The first KMER_K - 1 extensions can neither emit (i - x < min_len) nor be observed: take their result from the
-    // k-mer table when the next KMER_K bases are all ACGT (an ambiguous base ends the walk, which the plain loop handles)
-    if (sizeof(IdxT) == 4 && C.kmer_tab && min_len >= KMER_K && x + KMER_K <= len) {
-        uint32_t idx = 0; bool acgt = true;
-#pragma unroll
-        for (int t = 0; t < KMER_K; ++t) { const uint32_t b = q[x + t]; acgt = acgt && b < 4; idx = idx << 2 | (b & 3); }
-        if (acgt) {
-            const uint4 e = __ldg(C.kmer_tab + kmer_level_off(KMER_K) + idx);
+    // The first kk - 1 extensions can neither emit (i - x < min_len) nor be observed: take their result from the
+    // k-mer table when the next kk bases are all ACGT (an ambiguous base ends the walk, which the plain loop handles)
+    if (sizeof(IdxT) == 4 && C.kmer_tab && min_len >= C.kk && x + C.kk <= len) {
+        uint32_t w;
+        if (kmer_word(q, pk, has_n, x, C.kk, w)) {
+            const uint4 e = __ldg(C.kmer_tab + kmer_level_off(C.kk) + (w >> (32 - 2 * C.kk)));
             ik.x0 = (IdxT)e.x; ik.x1 = (IdxT)e.y; ik.x2 = e.z;
-            i = x + KMER_K; n_ext += KMER_K - 1;   // the roofline unit stays the reference's count of bwt_extend calls
+            i = x + C.kk; n_ext += C.kk - 1;   // the roofline unit stays the reference's count of bwt_extend calls
         }
     }
     for (; i < len; ++i) {
@@ -433,10 +443,10 @@ __device__ __forceinline__ int seed_strategy1(const Ctx<IdxT>& C, int len, const
 // the three passes of mem_collect_intv for one read
 template <class IdxT>
 __device__ __forceinline__ void collect_intv(const Ctx<IdxT>& C, const DevOpts& o, int len, const uint8_t* q, IvT<IdxT>* la, IvT<IdxT>* lb,
-                                             uint32_t list_cap, Out& O, unsigned long long& n_ext, const uint32_t* pk) {
+                                             uint32_t list_cap, Out& O, unsigned long long& n_ext, const uint32_t* pk, bool has_n) {
     int x = 0;
     while (x < len) {      // pass 1: all SMEMs
-        if (q[x] < 4) x = smem1(C, o, len, q, x, 1, la, lb, list_cap, O, n_ext, pk);
+        if (q[x] < 4) x = smem1(C, o, len, q, x, 1, la, lb, list_cap, O, n_ext, pk, has_n);
         else ++x;
     }
     const uint32_t old_n = O.n < O.cap ? O.n : O.cap;
@@ -444,12 +454,12 @@ __device__ __forceinline__ void collect_intv(const Ctx<IdxT>& C, const DevOpts& 
         const Intv p = O.out[k];
         const int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
         if (end - start < o.split_len || p.x2 > (uint64_t)o.split_width) continue;
-        smem1(C, o, len, q, (start + end) >> 1, (uint32_t)p.x2 + 1, la, lb, list_cap, O, n_ext, pk);
+        smem1(C, o, len, q, (start + end) >> 1, (uint32_t)p.x2 + 1, la, lb, list_cap, O, n_ext, pk, has_n);
     }
     if (o.max_mem_intv > 0) {                // pass 3: LAST-like
         x = 0;
         while (x < len) {
-            if (q[x] < 4) x = seed_strategy1(C, len, q, x, o.min_seed_len, (uint32_t)o.max_mem_intv, O, n_ext);
+            if (q[x] < 4) x = seed_strategy1(C, len, q, x, o.min_seed_len, (uint32_t)o.max_mem_intv, O, n_ext, pk, has_n);
             else ++x;
         }
     }
@@ -554,7 +564,7 @@ __global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 4 
     Intv* gl = P.scratch + (size_t)gwarp * 3 * P.list_cap;     // global scratch: lists of long reads, big-sort buffer
     unsigned long long n_ext = 0;
     Ctx<IdxT> C;
-    C.occ = ix.occ; C.sL2 = sL2; C.primary = (IdxT)ix.primary; C.kmer_tab = P.kmer_tab;
+    C.occ = ix.occ; C.sL2 = sL2; C.primary = (IdxT)ix.primary; C.kmer_tab = P.kmer_tab; C.kk = P.kmer_k;
     C.sa = reinterpret_cast<const uint32_t*>(ix.sa); C.isa = sizeof(IdxT) == 4 ? P.isa : nullptr; C.pac = ix.pac; C.l_pac = (uint32_t)ix.l_pac; C.n = (uint32_t)ix.seq_len;
     {
         const int idx = lane & 15;
@@ -578,7 +588,9 @@ __global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 4 
         if (len >= o.min_seed_len) {   // mem_chain returns before seeding otherwise
             if (SMEM) {
                 __syncwarp();
-                for (int i = lane; i < len; i += 32) sq[i] = q[i];
+                bool amb = false;
+                for (int i = lane; i < len; i += 32) { const uint8_t b = q[i]; sq[i] = b; amb = amb || b > 3; }
+                const bool has_n = __any_sync(FULL, amb);
                 __syncwarp();
                 // 2-bit packed copy of the read (16 bases per word, MSB first) for k-mer indices of arbitrary substrings
                 uint32_t* pk = nullptr;
@@ -591,8 +603,8 @@ __global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 4 
                     }
                     __syncwarp();
                 }
-                collect_intv(C, o, len, sq, la, lb, P.list_cap, O, n_ext, pk);
-            } else collect_intv(C, o, len, q, la, lb, P.list_cap, O, n_ext, (const uint32_t*)nullptr);
+                collect_intv(C, o, len, sq, la, lb, P.list_cap, O, n_ext, pk, has_n);
+            } else collect_intv(C, o, len, q, la, lb, P.list_cap, O, n_ext, (const uint32_t*)nullptr, true);
             __syncwarp();
         }
         uint32_t n_out = O.n;
@@ -621,16 +633,23 @@ template <class IdxT, bool SMEM> void launch_mode(const SeedParams& p, const Dev
 
 }  // namespace
 
-size_t kmer_table_bytes() { return (size_t)kmer_level_off(KMER_K + 1) * sizeof(uint4); }
+size_t kmer_table_bytes(int k) { return (size_t)kmer_level_off(k + 1) * sizeof(uint4); }
 
-// builds every level of the prefix table into `tab` (kmer_table_bytes()).  32-bit indices only.
-void build_kmer_table(const DevIndex& ix, void* tab, void* /*unused*/, cudaStream_t st, uint64_t* launches) {
+// depth of the prefix table for a text of n symbols: ceil(log4 n), within [8, KMER_K_MAX]
+int kmer_table_depth(uint64_t n) {
+    int k = 8;
+    while (k < KMER_K_MAX && (1ull << (2 * k)) < n) ++k;
+    return k;
+}
+
+// builds levels 1..k of the prefix table into `tab` (kmer_table_bytes(k)).  32-bit indices only.
+void build_kmer_table(const DevIndex& ix, void* tab, int k, cudaStream_t st, uint64_t* launches) {
     uint4* base = reinterpret_cast<uint4*>(tab);
     const uint32_t L2a = (uint32_t)ix.L2[0], L2c = (uint32_t)ix.L2[1], L2g = (uint32_t)ix.L2[2], L2t = (uint32_t)ix.L2[3], L2n = (uint32_t)ix.L2[4];
     k_kmer_level0<<<1, 32, 0, st>>>(base + kmer_level_off(1), L2a, L2c, L2g, L2t, L2n);
     if (launches) ++*launches;
     uint32_t n = 4;
-    for (int t = 2; t <= KMER_K; ++t) {
+    for (int t = 2; t <= k; ++t) {
         const unsigned blocks = (unsigned)std::min<uint32_t>((n + 255) / 256, 148u * 16u);
         k_kmer_level<<<blocks ? blocks : 1, 256, 0, st>>>(base + kmer_level_off(t - 1), base + kmer_level_off(t), n, ix.occ, (uint32_t)ix.primary, L2a, L2c, L2g, L2t);
         if (launches) ++*launches;

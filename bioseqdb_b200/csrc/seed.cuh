@@ -17,7 +17,8 @@ struct SeedParams {
     uint32_t list_cap;
     int lists_in_smem;        // narrow path: the two interval lists of a warp and the read live in shared memory
     uint32_t read_cap;        // bytes reserved per warp for the staged read (>= longest read, multiple of 16)
-    const uint4* kmer_tab;    // bi-intervals of all 12-mers for the LAST-like pass (32-bit indices only), or nullptr
+    const uint4* kmer_tab;    // prefix table: bi-intervals of all t-mers, t <= kmer_k (32-bit indices only), or nullptr
+    int kmer_k;
     const uint32_t* isa;      // inverse suffix array for the unique-match shortcut (32-bit rows), or nullptr
     uint32_t* ticket;
     uint32_t* overflow;       // set to 1 when a read needs more than cap intervals
@@ -25,7 +26,8 @@ struct SeedParams {
 };
 void launch_seed(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, int* n_warps_out);
 int seed_resident_warps();
-size_t kmer_table_bytes();
+size_t kmer_table_bytes(int k);
+int kmer_table_depth(uint64_t n);
 void build_isa(const DevIndex& ix, uint32_t* isa, cudaStream_t st, uint64_t* launches);
-void build_kmer_table(const DevIndex& ix, void* tab, void* tmp, cudaStream_t st, uint64_t* launches);
+void build_kmer_table(const DevIndex& ix, void* tab, int k, cudaStream_t st, uint64_t* launches);
 bool seed_lists_fit_smem(uint32_t list_cap, uint32_t read_cap, int sa_bytes);

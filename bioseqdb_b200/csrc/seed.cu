@@ -192,7 +192,7 @@ template <class IdxT> __device__ __forceinline__ void emit(Out& O, const IvT<Idx
 // bwt_smem1a with max_intv == 0 (the only way this path calls it).  la/lb: two interval lists of list_cap entries.
 template <class IdxT>
 __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int len, const uint8_t* q, int x, uint32_t min_intv, IvT<IdxT>* la,
-                                     IvT<IdxT>* lb, uint32_t list_cap, Out& O, unsigned long long& n_ext, const uint32_t* pk, bool has_n) {
+                                     IvT<IdxT>* lb, uint32_t list_cap, Out& O, unsigned long long& n_ext, const uint32_t* pk, bool has_n, IvT<IdxT>* hand) {
     if (q[x] > 3) return x + 1;
     if (min_intv < 1) min_intv = 1;
     const int KK = C.kk;
@@ -276,11 +276,15 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
         IvT<IdxT> p; p.x0 = 1; p.x1 = 1; p.x2 = 0; p.info = 0;
         if (own) p = prev[n_prev - 1 - (uint32_t)lane];
         uint32_t present = __ballot_sync(FULL, own);
+        const uint32_t lt = (1u << lane) - 1u;
+        const bool can_uq = sizeof(IdxT) == 4 && C.isa != nullptr && min_intv == 1;
+        const bool tab_ok = sizeof(IdxT) == 4 && pk != nullptr;
         // unique first entry: its walk is one text comparison (uq_stop = the index i at which it dies, uq_x0 = its row then)
         bool uq = false; int uq_stop = 0; IdxT uq_x0 = 0;
+        uint32_t ne = 0;
         for (i = x - 1; i >= -1; --i) {
             const int first = __ffs(present) - 1;
-            if (sizeof(IdxT) == 4 && C.isa && min_intv == 1 && !uq) {
+            if (can_uq && !uq) {
                 const uint32_t fx2 = __shfl_sync(FULL, p.x2, first);
                 if (fx2 == 1) {
                     const uint32_t fx0 = (uint32_t)__shfl_sync(FULL, p.x0, first);
@@ -289,44 +293,44 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
                     uq = true; uq_stop = i - run; uq_x0 = run > 0 ? (IdxT)C.isa[pos - (uint32_t)run] : (IdxT)fx0;
                 }
             }
-            if (uq && present == (1u << first) && i > uq_stop) { n_ext += (unsigned long long)(i - uq_stop); i = uq_stop; }   // alone: jump
-            const int c = i < 0 ? -1 : (q[i] < 4 ? q[i] : -1);
+            if (uq && (present & (present - 1)) == 0 && i > uq_stop) { ne += (uint32_t)(i - uq_stop); i = uq_stop; }   // alone: jump
+            int c = -1;
+            if (i >= 0) { c = q[i]; if (c > 3) c = -1; }
             const bool act = (present >> lane) & 1u;
-            IvT<IdxT> ok; ok.x0 = p.x0; ok.x1 = p.x1; ok.x2 = 0; ok.info = p.info;
+            IdxT nx0 = p.x0, nx1 = p.x1; uint32_t sz = 0;
             if (c >= 0) {
                 const bool is_uq = uq && lane == first;
-                if (is_uq) ok.x2 = i > uq_stop ? 1u : 0u;
+                if (is_uq) sz = i > uq_stop ? 1u : 0u;
                 const int lq = (int)p.info - i;                      // length of the match after prepending q[i]
                 // a match of at most KK bases needs no Occ access: its bi-interval is in the prefix table
-                const bool by_table = act && !is_uq && sizeof(IdxT) == 4 && pk != nullptr && lq <= KK;
+                const bool by_table = act && !is_uq && tab_ok && lq <= KK;
                 if (by_table) {
-                    const uint32_t hi = pk[i >> 4], lo = pk[(i >> 4) + 1];
-                    const uint32_t kidx = __funnelshift_l(lo, hi, (i & 15) << 1) >> (32 - 2 * lq);
-                    const uint4 e = __ldg(C.kmer_tab + kmer_level_off(lq) + kidx);
-                    ok.x0 = (IdxT)e.x; ok.x1 = (IdxT)e.y; ok.x2 = e.z;
+                    const uint32_t w = __funnelshift_l(pk[(i >> 4) + 1], pk[i >> 4], (i & 15) << 1);
+                    const uint4 e = __ldg(C.kmer_tab + kmer_level_off(lq) + (w >> (32 - 2 * lq)));
+                    nx0 = (IdxT)e.x; nx1 = (IdxT)e.y; sz = e.z;
                 }
                 uint32_t todo = __ballot_sync(FULL, act && !is_uq && !by_table);
-                n_ext += (unsigned long long)__popc(present);
+                ne += (uint32_t)__popc(present);
                 while (todo) {
-                    // the four lowest pending entries: group g (lanes 8g..8g+7) fetches entry s_g's interval, extends it, hands it back
-                    int s0 = __ffs(todo) - 1; uint32_t m = todo & (todo - 1);
-                    int s1 = m ? __ffs(m) - 1 : -1; m = m ? m & (m - 1) : 0;
-                    int s2 = m ? __ffs(m) - 1 : -1; m = m ? m & (m - 1) : 0;
-                    int s3 = m ? __ffs(m) - 1 : -1; m = m ? m & (m - 1) : 0;
+                    // the four lowest pending entries go through the warp's hand-off slots: group g (lanes 8g..8g+7)
+                    // extends the entry in slot g and its leader writes the result back
+                    const int rank = __popc(todo & lt);
+                    const bool mine = ((todo >> lane) & 1u) && rank < 4;
+                    if (mine) hand[rank] = p;
+                    __syncwarp();
                     const int g = lane >> 3;
-                    const int src = g == 0 ? s0 : (g == 1 ? s1 : (g == 2 ? s2 : s3));
-                    IvT<IdxT> pg;
-                    pg.x0 = __shfl_sync(FULL, p.x0, src < 0 ? 0 : src); pg.x1 = __shfl_sync(FULL, p.x1, src < 0 ? 0 : src);
-                    pg.x2 = __shfl_sync(FULL, p.x2, src < 0 ? 0 : src); pg.info = 0;
-                    const IvT<IdxT> og = extend4_back(C, pg, c, src >= 0);
-                    const int mine = lane == s0 ? 0 : (lane == s1 ? 1 : (lane == s2 ? 2 : (lane == s3 ? 3 : -1)));
-                    const IdxT r0 = __shfl_sync(FULL, og.x0, mine < 0 ? 0 : mine << 3), r1 = __shfl_sync(FULL, og.x1, mine < 0 ? 0 : mine << 3);
-                    const uint32_t r2 = __shfl_sync(FULL, og.x2, mine < 0 ? 0 : mine << 3);
-                    if (mine >= 0) { ok.x0 = r0; ok.x1 = r1; ok.x2 = r2; }
-                    todo = m;
+                    const bool gv = g < __popc(todo);
+                    IvT<IdxT> pg = hand[g];
+                    const IvT<IdxT> og = extend4_back(C, pg, c, gv);
+                    __syncwarp();
+                    if ((lane & 7) == 0) hand[g] = og;
+                    __syncwarp();
+                    if (mine) { const IvT<IdxT> r = hand[rank]; nx0 = r.x0; nx1 = r.x1; sz = r.x2; }
+                    __syncwarp();
+                    todo &= todo - 1; todo &= todo - 1; todo &= todo - 1; todo &= todo - 1;
                 }
             }
-            const bool alive = act && ok.x2 >= min_intv;
+            const bool alive = act && sz >= min_intv;
             const uint32_t alive_mask = __ballot_sync(FULL, alive);
             if (!((alive_mask >> first) & 1u)) {
                 const uint32_t pinfo = __shfl_sync(FULL, p.info, first);
@@ -338,13 +342,14 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
                 }
                 uq = false;
             }
-            const uint32_t before = alive_mask & ((1u << lane) - 1u);          // surviving entries ahead of mine
-            const uint32_t prev_sz = __shfl_sync(FULL, ok.x2, before ? 31 - __clz(before) : 0);
-            const bool keep = alive && (before == 0 || ok.x2 != prev_sz);
+            const uint32_t before = alive_mask & lt;                         // surviving entries ahead of mine
+            const uint32_t prev_sz = __shfl_sync(FULL, sz, 31 - __clz(before));   // (lane 31 when there is none: unused)
+            const bool keep = alive && (before == 0 || sz != prev_sz);
             present = __ballot_sync(FULL, keep);
-            if (keep) { p.x0 = ok.x0; p.x1 = ok.x1; p.x2 = ok.x2; }
+            if (keep) { p.x0 = nx0; p.x1 = nx1; p.x2 = sz; }
             if (!present) break;
         }
+        n_ext += ne;
     } else
     for (i = x - 1; i >= -1; --i) {
         // more entries than lanes (highly repetitive reads): the list logic of bwt_smem1a, one entry at a time
@@ -443,10 +448,10 @@ __device__ __forceinline__ int seed_strategy1(const Ctx<IdxT>& C, int len, const
 // the three passes of mem_collect_intv for one read
 template <class IdxT>
 __device__ __forceinline__ void collect_intv(const Ctx<IdxT>& C, const DevOpts& o, int len, const uint8_t* q, IvT<IdxT>* la, IvT<IdxT>* lb,
-                                             uint32_t list_cap, Out& O, unsigned long long& n_ext, const uint32_t* pk, bool has_n) {
+                                             uint32_t list_cap, Out& O, unsigned long long& n_ext, const uint32_t* pk, bool has_n, IvT<IdxT>* hand) {
     int x = 0;
     while (x < len) {      // pass 1: all SMEMs
-        if (q[x] < 4) x = smem1(C, o, len, q, x, 1, la, lb, list_cap, O, n_ext, pk, has_n);
+        if (q[x] < 4) x = smem1(C, o, len, q, x, 1, la, lb, list_cap, O, n_ext, pk, has_n, hand);
         else ++x;
     }
     const uint32_t old_n = O.n < O.cap ? O.n : O.cap;
@@ -454,7 +459,7 @@ __device__ __forceinline__ void collect_intv(const Ctx<IdxT>& C, const DevOpts& 
         const Intv p = O.out[k];
         const int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
         if (end - start < o.split_len || p.x2 > (uint64_t)o.split_width) continue;
-        smem1(C, o, len, q, (start + end) >> 1, (uint32_t)p.x2 + 1, la, lb, list_cap, O, n_ext, pk, has_n);
+        smem1(C, o, len, q, (start + end) >> 1, (uint32_t)p.x2 + 1, la, lb, list_cap, O, n_ext, pk, has_n, hand);
     }
     if (o.max_mem_intv > 0) {                // pass 3: LAST-like
         x = 0;
@@ -556,6 +561,8 @@ template <class IdxT, bool SMEM>
 __global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 4 : 1) seed_smem(SeedParams P, DevIndex ix, DevOpts o) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ IdxT sL2[8];
+    __shared__ IvT<IdxT> s_hand[SEED_WARPS][4];   // hand-off slots of the grouped backward extensions
+    IvT<IdxT>* hand = s_hand[threadIdx.x >> 5];
     if (threadIdx.x < 5) sL2[threadIdx.x] = (IdxT)ix.L2[threadIdx.x];
     __syncthreads();
     using Iv = IvT<IdxT>;
@@ -603,8 +610,8 @@ __global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 4 
                     }
                     __syncwarp();
                 }
-                collect_intv(C, o, len, sq, la, lb, P.list_cap, O, n_ext, pk, has_n);
-            } else collect_intv(C, o, len, q, la, lb, P.list_cap, O, n_ext, (const uint32_t*)nullptr, true);
+                collect_intv(C, o, len, sq, la, lb, P.list_cap, O, n_ext, pk, has_n, hand);
+            } else collect_intv(C, o, len, q, la, lb, P.list_cap, O, n_ext, (const uint32_t*)nullptr, true, hand);
             __syncwarp();
         }
         uint32_t n_out = O.n;

@@ -55,7 +55,19 @@ struct Batch {
     DevBuf<uint8_t> ext_scratch, fin_scratch, narrow_z, narrow_jobs; DevBuf<uint64_t> wide_jobs;
     DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..23] counters (u64 x 8), [24] narrow_cnt, [25] wide_cnt, [26..27] tickets
     bool resident = false, aligned = false;
+    // one batch = one lane of the host pipeline: its stream, the host staging that must outlive the async copies,
+    // and the state of the attempt in flight (pipeline_enqueue -> pipeline_check)
+    cudaStream_t st = nullptr;
+    std::vector<uint64_t> rel;
+    uint32_t* ctl_host = nullptr;       // pinned, 16 words: ctl[0..7], total rows (2 words), host-MAPQ flag
+    cudaEvent_t ev[5]; bool ev_ok = false;
+    cudaEvent_t ev_x[4]; bool evx_ok = false;   // chunked mode: upload begin/end, download begin/end
+    uint32_t att_rseq_cap = 0; bool idle = true;
+    uint64_t out_rows = 0; uint32_t out_cig = 0;
     void release() {
+        if (ctl_host) { cudaFreeHost(ctl_host); ctl_host = nullptr; }
+        if (ev_ok) { for (auto& e : ev) cudaEventDestroy(e); ev_ok = false; }
+        if (evx_ok) { for (auto& e : ev_x) cudaEventDestroy(e); evx_ok = false; }
         seqs.release(); offs.release(); ids.release(); intv.release(); intv_cnt.release(); seed_scratch.release(); raw.release(); seeds.release();
         ctmp.release(); ord.release(); chains.release(); srt.release(); regs.release(); rows.release(); rows_compact.release(); reg_cnt.release();
         row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release(); ctl.release(); narrow_z.release(); narrow_jobs.release(); wide_jobs.release(); read_logtab.release();
@@ -72,7 +84,8 @@ struct bsq_index {
     uint8_t* d_pac = nullptr; uint32_t* d_occ = nullptr; void* d_sa = nullptr; int64_t* d_ann_offset = nullptr; int32_t* d_ann_len = nullptr; int64_t* d_ann_id = nullptr;
     bsq_index_meta meta;
     cudaStream_t stream = nullptr;
-    Batch batch;
+    Batch batch, batch2;             // batch2 + stream2: second lane of bsq_align_batch's chunk pipeline
+    cudaStream_t stream2 = nullptr;
     bsq_timing timing;
     double* d_logtab = nullptr;
     uint32_t* d_isa = nullptr;       // inverse SA for the unique-match shortcut of the seeding kernel (built lazily, 32-bit rows)
@@ -129,6 +142,7 @@ bsq_index* bsq_index_new(const bsq_opts* o, int device) {
     memset(&h->meta, 0, sizeof(h->meta)); memset(&h->timing, 0, sizeof(h->timing));
     fill_dev_opts(h);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { bsq_set_error("cudaStreamCreate failed"); delete h; return nullptr; }
+    h->batch.st = h->stream;
     return h;
 }
 
@@ -194,11 +208,12 @@ int bsq_index_build(bsq_index* h) {
 void bsq_index_free(bsq_index* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    h->batch.release();
+    h->batch.release(); h->batch2.release();
     free_index_arrays(h);
     if (h->d_logtab) cudaFree(h->d_logtab);
     if (h->d_kmer) cudaFree(h->d_kmer);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     delete h;
 }
 
@@ -313,8 +328,9 @@ __device__ __forceinline__ int approx_mapq_dev(const MapqParams& M, const RowDev
 }
 
 __global__ void k_compact_rows(const ReadBlock* blocks, const RowDev* rows, const uint32_t* row_cnt, const uint32_t* row_off, uint32_t n_reads,
-                               RowDev* out, MapqParams M) {
-    // one warp per read; a row is 120 bytes = 30 words
+                               RowDev* out, MapqParams M, uint32_t cig_base, uint32_t* host_mapq) {
+    // one warp per read; a row is 120 bytes = 30 words.  cig_base rebases the rows' CIGAR offsets when the batch is one
+    // chunk of a larger result; *host_mapq is raised when a row's MAPQ has to be finished on the host.
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     for (uint32_t r = gw; r < n_reads; r += nw) {
@@ -326,7 +342,12 @@ __global__ void k_compact_rows(const ReadBlock* blocks, const RowDev* rows, cons
         uint32_t* dst = reinterpret_cast<uint32_t*>(drow);
         for (uint32_t w = lane; w < c * 30; w += 32) dst[w] = src[w];
         __syncwarp();
-        for (uint32_t k = lane; k < c; k += 32) drow[k].mapq = srow[k].secondary < 0 ? approx_mapq_dev(M, srow[k]) : 0;
+        for (uint32_t k = lane; k < c; k += 32) {
+            const int mq = srow[k].secondary < 0 ? approx_mapq_dev(M, srow[k]) : 0;
+            drow[k].mapq = mq;
+            if (mq < 0) atomicExch(host_mapq, 1u);
+            if (cig_base && srow[k].n_cigar) drow[k].cigar_off = srow[k].cigar_off + cig_base;
+        }
     }
 }
 
@@ -344,8 +365,7 @@ uint32_t rseq_cap_for(const bsq_index* h, uint32_t max_len) { return max_len + 4
 // reads longer than this would need mem_flt_chained_seeds' local SW (runs when 5.5 ln L <= 0.05 L)
 bool needs_seed_sw(uint32_t len) { return len > 0 && 5.5f * log((double)len) <= 0.05f * (double)len; }
 
-int upload_reads(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n) {
-    Batch& b = h->batch;
+int upload_reads(bsq_index* h, Batch& b, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n) {
     b.resident = false; b.aligned = false;
     if (n >= 0x7fffffffull) { bsq_set_error("batch too large"); return BSQ_ERR; }
     uint32_t max_len = 0;
@@ -367,14 +387,13 @@ int upload_reads(bsq_index* h, const char* seqs, const uint64_t* offs, const int
         b.read_logtab_n = max_len + 1;
     }
     CUDA_CHECK(b.seqs.ensure(total + 64)); CUDA_CHECK(b.offs.ensure(n + 1)); CUDA_CHECK(b.ids.ensure(n + 1));
-    std::vector<uint64_t> rel(n + 1);
-    for (uint64_t i = 0; i <= n; ++i) rel[i] = offs[i] - (n ? offs[0] : 0);
-    if (total) CUDA_CHECK(cudaMemcpyAsync(b.seqs.p, seqs + offs[0], total, cudaMemcpyHostToDevice, h->stream));
-    CUDA_CHECK(cudaMemcpyAsync(b.offs.p, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-    if (n) CUDA_CHECK(cudaMemcpyAsync(b.ids.p, ids, n * 8, cudaMemcpyHostToDevice, h->stream));
-    if (total) { k_to_nt4<<<(unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 16), 256, 0, h->stream>>>(b.seqs.p, total); ++h->timing.launches; }
-    CUDA_CHECK(cudaStreamSynchronize(h->stream));   // rel[] is a stack-lifetime staging buffer
-    h->timing.h2d_bytes = total + (n + 1) * 8 + n * 8;
+    b.rel.resize(n + 1);                    // staging owned by the batch: it outlives the asynchronous copy
+    for (uint64_t i = 0; i <= n; ++i) b.rel[i] = offs[i] - (n ? offs[0] : 0);
+    if (total) CUDA_CHECK(cudaMemcpyAsync(b.seqs.p, seqs + offs[0], total, cudaMemcpyHostToDevice, b.st));
+    CUDA_CHECK(cudaMemcpyAsync(b.offs.p, b.rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, b.st));
+    if (n) CUDA_CHECK(cudaMemcpyAsync(b.ids.p, ids, n * 8, cudaMemcpyHostToDevice, b.st));
+    if (total) { k_to_nt4<<<(unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 16), 256, 0, b.st>>>(b.seqs.p, total); ++h->timing.launches; }
+    h->timing.h2d_bytes += total + (n + 1) * 8 + n * 8;
     b.resident = true;
     return BSQ_OK;
 }
@@ -396,120 +415,158 @@ int ensure_kmer_table(bsq_index* h, const DevIndex& ix) {
     return BSQ_OK;
 }
 
-int run_pipeline(bsq_index* h) {
-    Batch& b = h->batch;
+// One attempt of the kernel pipeline on the batch's stream: size the pools, launch every stage, read the control
+// words back asynchronously.  Nothing here waits for the device.
+int pipeline_enqueue(bsq_index* h, Batch& b) {
     if (!b.resident) { bsq_set_error("no reads uploaded"); return BSQ_ERR; }
     const uint32_t n = (uint32_t)b.n;
     bsq_timing& T = h->timing;
-    T.seed = T.chain = T.extend = T.finalize = T.total = 0;
+    b.idle = true; b.out_rows = 0; b.out_cig = 0;
     if (n == 0 || !h->meta.built) { b.aligned = true; return BSQ_OK; }
     const DevIndex ix = make_dev_index(h);
     const DevOpts& o = h->dopts;
+    cudaStream_t st = b.st;
     if (ensure_kmer_table(h, ix) != BSQ_OK) return BSQ_ERR;
     const uint32_t max_len = std::max<uint32_t>(b.max_len, 1);
-    uint32_t rseq_cap = std::max(rseq_cap_for(h, max_len), b.rseq_cap);
+    const uint32_t rseq_cap = b.att_rseq_cap = std::max(rseq_cap_for(h, max_len), b.rseq_cap);
     if (b.intv_cap == 0) b.intv_cap = 48 + max_len / 4;
-    if (b.pool_cap == 0) b.pool_cap = (uint32_t)std::min<uint64_t>((uint64_t)n * 24 + 4096, 0x7fffffffull);
-    if (b.cigar_cap == 0) b.cigar_cap = (uint32_t)std::min<uint64_t>((uint64_t)n * 8 + 4096, 0x7fffffffull);
-    cudaEvent_t ev[5];
-    for (auto& e : ev) cudaEventCreate(&e);
-    int rc = BSQ_OK;
-    for (int attempt = 0; attempt < 12; ++attempt) {
-        // ---- (re)size pools
-        const int seed_warps = seed_resident_warps();
-        b.list_cap = std::max<uint32_t>(max_len + 1, b.intv_cap);
-        const int ext_warps = extend_resident_warps();
-        const size_t ext_per_warp = extend_scratch_per_warp(max_len, rseq_cap);
-        uint32_t z_cap = 0;
-        const size_t fin_per_warp = finalize_scratch_per_warp(max_len, rseq_cap, &z_cap);
-        int fin_warps = finalize_resident_warps();
-        {   // bound the traceback scratch to ~8 GB
-            size_t budget = (size_t)8 << 30;
-            int fit = (int)std::max<size_t>(budget / fin_per_warp, 4 * 148);
-            fin_warps = std::min(fin_warps, fit) / 4 * 4;
-        }
-#define ENS(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { bsq_set_error("allocating batch pools: %s", cudaGetErrorString(e_)); rc = BSQ_ERR; goto done; } } while (0)
-        ENS(b.intv.ensure((size_t)n * b.intv_cap)); ENS(b.intv_cnt.ensure(n));
-        ENS(b.seed_scratch.ensure((size_t)seed_warps * 3 * b.list_cap));
-        ENS(b.raw.ensure(b.pool_cap)); ENS(b.seeds.ensure(b.pool_cap)); ENS(b.ctmp.ensure(b.pool_cap)); ENS(b.ord.ensure(b.pool_cap));
-        ENS(b.chains.ensure(b.pool_cap)); ENS(b.srt.ensure(b.pool_cap)); ENS(b.regs.ensure(b.pool_cap)); ENS(b.rows.ensure(b.pool_cap));
-        ENS(b.reg_cnt.ensure(n)); ENS(b.row_cnt.ensure(n)); ENS(b.row_off.ensure(n + 1)); ENS(b.blocks.ensure(n));
-        ENS(b.scan_tmp.ensure(prim::scan_tmp_elems(n + 1) + 16));
-        ENS(b.cigar.ensure(b.cigar_cap));
-        ENS(b.ext_scratch.ensure((size_t)ext_warps * ext_per_warp)); ENS(b.fin_scratch.ensure((size_t)fin_warps * fin_per_warp));
-        int narrow_warps = 0;
-        const size_t narrow_bytes = narrow_zbuf_bytes(&narrow_warps);
-        ENS(b.narrow_z.ensure(narrow_bytes)); ENS(b.narrow_jobs.ensure((size_t)b.pool_cap * 3 * 24)); ENS(b.wide_jobs.ensure(b.pool_cap));
-        ENS(b.ctl.ensure(64));
-        ENS(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, h->stream));
-        unsigned long long* ctr = h->collect_counters ? reinterpret_cast<unsigned long long*>(b.ctl.p + 8) : nullptr;
-        cudaEventRecord(ev[0], h->stream);
-        {
-            SeedParams P;
-            P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = b.intv_cap;
-            P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.kmer_k = h->kmer_k; P.isa = h->d_isa; P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p + 0; P.overflow = b.ctl.p + 4; P.n_extend = ctr ? ctr + 0 : nullptr;
-            launch_seed(P, ix, o, h->stream, nullptr); ++T.launches;
-        }
-        cudaEventRecord(ev[1], h->stream);
-        {
-            ChainParams P;
-            P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.intv = b.intv.p; P.intv_cnt = b.intv_cnt.p; P.intv_cap = b.intv_cap;
-            P.raw = b.raw.p; P.ctmp = b.ctmp.p; P.ord = b.ord.p; P.chains = b.chains.p; P.seeds = b.seeds.p; P.pool_cap = b.pool_cap; P.pool_top = b.ctl.p + 5;
-            P.blocks = b.blocks.p; P.ticket = b.ctl.p + 1; P.overflow = b.ctl.p + 4; P.counters = ctr ? ctr + 1 : nullptr;
-            P.logtab = needs_seed_sw(b.max_len) ? b.read_logtab.p : nullptr; P.sw_cells = nullptr;
-            launch_chain(P, ix, o, h->stream); ++T.launches;
-        }
-        cudaEventRecord(ev[2], h->stream);
-        {
-            ExtendParams P;
-            P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.blocks = b.blocks.p; P.chains = b.chains.p; P.seeds = b.seeds.p; P.srt = b.srt.p;
-            P.regs = b.regs.p; P.reg_cnt = b.reg_cnt.p; P.scratch = b.ext_scratch.p; P.scratch_per_warp = ext_per_warp; P.max_len = max_len; P.rseq_cap = rseq_cap;
-            P.ticket = b.ctl.p + 2; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 3 : nullptr;
-            launch_extend(P, ix, o, h->stream); ++T.launches;
-        }
-        cudaEventRecord(ev[3], h->stream);
-        {
-            FinalizeParams P;
-            P.seqs = b.seqs.p; P.offs = b.offs.p; P.ids = b.ids.p; P.n_reads = n; P.blocks = b.blocks.p; P.regs = b.regs.p; P.reg_cnt = b.reg_cnt.p;
-            P.rows = b.rows.p; P.row_cnt = b.row_cnt.p; P.cigar_pool = b.cigar.p; P.cigar_cap = b.cigar_cap; P.cigar_top = b.ctl.p + 6;
-            P.scratch = b.fin_scratch.p; P.scratch_per_warp = fin_per_warp; P.max_len = max_len; P.z_cap = z_cap; P.ann_id = h->d_ann_id;
-            P.narrow_jobs = b.narrow_jobs.p; P.narrow_cap = b.pool_cap; P.narrow_cnt = b.ctl.p + 32; P.wide_jobs = b.wide_jobs.p; P.wide_cnt = b.ctl.p + 25; P.narrow_z = b.narrow_z.p; P.narrow_warps = narrow_warps;
-            P.ticket = b.ctl.p + 40; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 6 : nullptr;
-            launch_finalize(P, ix, o, h->stream, rseq_cap, fin_warps, &T.launches);
-        }
-        // compact rows: exclusive scan of row_cnt (n + 1 entries, the last one is a zero pad) -> row_off
-        prim::device_scan<uint32_t, prim::OpSum, false>(b.row_cnt.p, b.row_off.p, n, b.scan_tmp.p, prim::OpSum(), h->stream, &T.launches);
-        cudaEventRecord(ev[4], h->stream);
-        uint32_t ctl[8];
-        ENS(cudaMemcpyAsync(ctl, b.ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
-        ENS(cudaStreamSynchronize(h->stream));
-        { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { bsq_set_error("kernel failure: %s", cudaGetErrorString(e_)); rc = BSQ_ERR; goto done; } }
-        float ms;
-        cudaEventElapsedTime(&ms, ev[0], ev[1]); T.seed += ms;
-        cudaEventElapsedTime(&ms, ev[1], ev[2]); T.chain += ms;
-        cudaEventElapsedTime(&ms, ev[2], ev[3]); T.extend += ms;
-        cudaEventElapsedTime(&ms, ev[3], ev[4]); T.finalize += ms;
-        cudaEventElapsedTime(&ms, ev[0], ev[4]); T.total += ms;
-        if (ctl[7] > rseq_cap && ctl[4] != 2) {   // a reference window was larger than planned: grow the per-warp scratch and run again
-            rseq_cap = b.rseq_cap = ctl[7] + ctl[7] / 8 + 64;
-            continue;
-        }
-        if (ctl[4] == 0) {
-            if (ctr) { ENS(cudaMemcpy(h->counters, ctr, sizeof(h->counters), cudaMemcpyDeviceToHost)); }
-            b.aligned = true;
-            goto done;
-        }
-        if (ctl[4] == 2) { bsq_set_error("alignment scratch capacity exceeded (reference window / traceback larger than planned)"); rc = BSQ_ERR; goto done; }
-        // a pool was too small: grow everything that can overflow and run the batch again
-        if (ctl[5] > b.pool_cap) b.pool_cap = (uint32_t)std::min<uint64_t>((uint64_t)ctl[5] + ctl[5] / 8 + 4096, 0x7fffffffull);
-        else if (ctl[6] > b.cigar_cap) b.cigar_cap = (uint32_t)std::min<uint64_t>((uint64_t)ctl[6] + ctl[6] / 8 + 4096, 0x7fffffffull);
-        else b.intv_cap *= 2;
+    b.pool_cap = std::max<uint32_t>(b.pool_cap, (uint32_t)std::min<uint64_t>((uint64_t)n * 24 + 4096, 0x7fffffffull));
+    b.cigar_cap = std::max<uint32_t>(b.cigar_cap, (uint32_t)std::min<uint64_t>((uint64_t)n * 8 + 4096, 0x7fffffffull));
+    if (!b.ev_ok) { for (auto& e : b.ev) cudaEventCreate(&e); b.ev_ok = true; }
+    if (!b.ctl_host) CUDA_CHECK(cudaHostAlloc(&b.ctl_host, 16 * 4, cudaHostAllocDefault));
+    cudaEvent_t* ev = b.ev;
+    // ---- (re)size pools
+    const int seed_warps = seed_resident_warps();
+    b.list_cap = std::max<uint32_t>(max_len + 1, b.intv_cap);
+    const int ext_warps = extend_resident_warps();
+    const size_t ext_per_warp = extend_scratch_per_warp(max_len, rseq_cap);
+    uint32_t z_cap = 0;
+    const size_t fin_per_warp = finalize_scratch_per_warp(max_len, rseq_cap, &z_cap);
+    int fin_warps = finalize_resident_warps();
+    {   // bound the traceback scratch to ~8 GB
+        size_t budget = (size_t)8 << 30;
+        int fit = (int)std::max<size_t>(budget / fin_per_warp, 4 * 148);
+        fin_warps = std::min(fin_warps, fit) / 4 * 4;
     }
-    if (!b.aligned && rc == BSQ_OK) { bsq_set_error("batch pools kept overflowing"); rc = BSQ_ERR; }
-done:
-    for (auto& e : ev) cudaEventDestroy(e);
-    return rc;
+#define ENS(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { bsq_set_error("allocating batch pools: %s", cudaGetErrorString(e_)); return BSQ_ERR; } } while (0)
+    ENS(b.intv.ensure((size_t)n * b.intv_cap)); ENS(b.intv_cnt.ensure(n));
+    ENS(b.seed_scratch.ensure((size_t)seed_warps * 3 * b.list_cap));
+    ENS(b.raw.ensure(b.pool_cap)); ENS(b.seeds.ensure(b.pool_cap)); ENS(b.ctmp.ensure(b.pool_cap)); ENS(b.ord.ensure(b.pool_cap));
+    ENS(b.chains.ensure(b.pool_cap)); ENS(b.srt.ensure(b.pool_cap)); ENS(b.regs.ensure(b.pool_cap)); ENS(b.rows.ensure(b.pool_cap));
+    ENS(b.reg_cnt.ensure(n)); ENS(b.row_cnt.ensure(n)); ENS(b.row_off.ensure(n + 1)); ENS(b.blocks.ensure(n));
+    ENS(b.scan_tmp.ensure(prim::scan_tmp_elems(n + 1) + 16));
+    ENS(b.cigar.ensure(b.cigar_cap));
+    ENS(b.ext_scratch.ensure((size_t)ext_warps * ext_per_warp)); ENS(b.fin_scratch.ensure((size_t)fin_warps * fin_per_warp));
+    int narrow_warps = 0;
+    const size_t narrow_bytes = narrow_zbuf_bytes(&narrow_warps);
+    ENS(b.narrow_z.ensure(narrow_bytes)); ENS(b.narrow_jobs.ensure((size_t)b.pool_cap * 3 * 24)); ENS(b.wide_jobs.ensure(b.pool_cap));
+    ENS(b.ctl.ensure(64));
+    ENS(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, st));
+    unsigned long long* ctr = h->collect_counters ? reinterpret_cast<unsigned long long*>(b.ctl.p + 8) : nullptr;
+    cudaEventRecord(ev[0], st);
+    {
+        SeedParams P;
+        P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = b.intv_cap;
+        P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.kmer_k = h->kmer_k; P.isa = h->d_isa; P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p + 0; P.overflow = b.ctl.p + 4; P.n_extend = ctr ? ctr + 0 : nullptr;
+        launch_seed(P, ix, o, st, nullptr); ++T.launches;
+    }
+    cudaEventRecord(ev[1], st);
+    {
+        ChainParams P;
+        P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.intv = b.intv.p; P.intv_cnt = b.intv_cnt.p; P.intv_cap = b.intv_cap;
+        P.raw = b.raw.p; P.ctmp = b.ctmp.p; P.ord = b.ord.p; P.chains = b.chains.p; P.seeds = b.seeds.p; P.pool_cap = b.pool_cap; P.pool_top = b.ctl.p + 5;
+        P.blocks = b.blocks.p; P.ticket = b.ctl.p + 1; P.overflow = b.ctl.p + 4; P.counters = ctr ? ctr + 1 : nullptr;
+        P.logtab = needs_seed_sw(b.max_len) ? b.read_logtab.p : nullptr; P.sw_cells = nullptr;
+        launch_chain(P, ix, o, st); ++T.launches;
+    }
+    cudaEventRecord(ev[2], st);
+    {
+        ExtendParams P;
+        P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.blocks = b.blocks.p; P.chains = b.chains.p; P.seeds = b.seeds.p; P.srt = b.srt.p;
+        P.regs = b.regs.p; P.reg_cnt = b.reg_cnt.p; P.scratch = b.ext_scratch.p; P.scratch_per_warp = ext_per_warp; P.max_len = max_len; P.rseq_cap = rseq_cap;
+        P.ticket = b.ctl.p + 2; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 3 : nullptr;
+        launch_extend(P, ix, o, st); ++T.launches;
+    }
+    cudaEventRecord(ev[3], st);
+    {
+        FinalizeParams P;
+        P.seqs = b.seqs.p; P.offs = b.offs.p; P.ids = b.ids.p; P.n_reads = n; P.blocks = b.blocks.p; P.regs = b.regs.p; P.reg_cnt = b.reg_cnt.p;
+        P.rows = b.rows.p; P.row_cnt = b.row_cnt.p; P.cigar_pool = b.cigar.p; P.cigar_cap = b.cigar_cap; P.cigar_top = b.ctl.p + 6;
+        P.scratch = b.fin_scratch.p; P.scratch_per_warp = fin_per_warp; P.max_len = max_len; P.z_cap = z_cap; P.ann_id = h->d_ann_id;
+        P.narrow_jobs = b.narrow_jobs.p; P.narrow_cap = b.pool_cap; P.narrow_cnt = b.ctl.p + 32; P.wide_jobs = b.wide_jobs.p; P.wide_cnt = b.ctl.p + 25; P.narrow_z = b.narrow_z.p; P.narrow_warps = narrow_warps;
+        P.ticket = b.ctl.p + 40; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 6 : nullptr;
+        launch_finalize(P, ix, o, st, rseq_cap, fin_warps, &T.launches);
+    }
+    // compact rows: exclusive scan of row_cnt (n + 1 entries, the last one is a zero pad) -> row_off
+    prim::device_scan<uint32_t, prim::OpSum, false>(b.row_cnt.p, b.row_off.p, n, b.scan_tmp.p, prim::OpSum(), st, &T.launches);
+    cudaEventRecord(ev[4], st);
+    ENS(cudaMemcpyAsync(b.ctl_host, b.ctl.p, 8 * 4, cudaMemcpyDeviceToHost, st));
+    ENS(cudaMemcpyAsync(b.ctl_host + 8, b.row_off.p + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    ENS(cudaMemcpyAsync(b.ctl_host + 9, b.row_cnt.p + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    b.idle = false;
+    return BSQ_OK;
 #undef ENS
+}
+
+// Waits for the attempt in flight and looks at its control words: *again = a pool or a scratch area was too small;
+// the capacities have been raised and pipeline_enqueue must run once more.
+int pipeline_check(bsq_index* h, Batch& b, bool* again) {
+    *again = false;
+    if (b.idle) return BSQ_OK;
+    bsq_timing& T = h->timing;
+    CUDA_CHECK(cudaStreamSynchronize(b.st));
+    b.idle = true;
+    { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { bsq_set_error("kernel failure: %s", cudaGetErrorString(e_)); return BSQ_ERR; } }
+    const uint32_t* ctl = b.ctl_host;
+    cudaEvent_t* ev = b.ev;
+    float ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); T.seed += ms;
+    cudaEventElapsedTime(&ms, ev[1], ev[2]); T.chain += ms;
+    cudaEventElapsedTime(&ms, ev[2], ev[3]); T.extend += ms;
+    cudaEventElapsedTime(&ms, ev[3], ev[4]); T.finalize += ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[4]); T.total += ms;
+    if (ctl[7] > b.att_rseq_cap && ctl[4] != 2) {   // a reference window was larger than planned: grow the per-warp scratch and run again
+        b.rseq_cap = ctl[7] + ctl[7] / 8 + 64;
+        *again = true;
+        return BSQ_OK;
+    }
+    if (ctl[4] == 0) {
+        if (h->collect_counters) {
+            uint64_t c8[8];
+            CUDA_CHECK(cudaMemcpy(c8, b.ctl.p + 8, sizeof(c8), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < 8; ++i) h->counters[i] += c8[i];
+        }
+        b.out_rows = (uint64_t)ctl[8] + ctl[9]; b.out_cig = ctl[6];
+        b.aligned = true;
+        return BSQ_OK;
+    }
+    if (ctl[4] == 2) { bsq_set_error("alignment scratch capacity exceeded (reference window / traceback larger than planned)"); return BSQ_ERR; }
+    // a pool was too small: grow everything that can overflow and run the batch again
+    if (ctl[5] > b.pool_cap) b.pool_cap = (uint32_t)std::min<uint64_t>((uint64_t)ctl[5] + ctl[5] / 8 + 4096, 0x7fffffffull);
+    else if (ctl[6] > b.cigar_cap) b.cigar_cap = (uint32_t)std::min<uint64_t>((uint64_t)ctl[6] + ctl[6] / 8 + 4096, 0x7fffffffull);
+    else b.intv_cap *= 2;
+    *again = true;
+    return BSQ_OK;
+}
+
+// finishes the batch: checks the attempt in flight (if any) and re-runs it while capacities have to grow
+int pipeline_finish(bsq_index* h, Batch& b) {
+    for (int attempt = 0; attempt < 12; ++attempt) {
+        bool again = false;
+        if (pipeline_check(h, b, &again) != BSQ_OK) return BSQ_ERR;
+        if (!again) { if (!b.aligned) break; return BSQ_OK; }
+        if (pipeline_enqueue(h, b) != BSQ_OK) return BSQ_ERR;
+    }
+    bsq_set_error("batch pools kept overflowing");
+    return BSQ_ERR;
+}
+
+int run_pipeline(bsq_index* h, Batch& b) {
+    bsq_timing& T = h->timing;
+    T.seed = T.chain = T.extend = T.finalize = T.total = 0;
+    memset(h->counters, 0, sizeof(h->counters));
+    if (pipeline_enqueue(h, b) != BSQ_OK) return BSQ_ERR;
+    return pipeline_finish(h, b);
 }
 
 // mem_approx_mapq_se on the host: double math with libm log
@@ -535,9 +592,10 @@ int approx_mapq(const bsq_index* h, const bsq_row& a) {
     return mapq;
 }
 
-// A result lives in ONE pinned host block {row_off, rows, cigar}; freed blocks are cached process-wide
-// so that steady-state calls do not pay cudaHostAlloc.
-struct ResultImpl { bsq_result pub; void* block; size_t bytes; };
+// A result lives in ONE pinned host block, laid out by capacity: row_off (u64 x (n+1)) | rows (row_cap + 1) |
+// cigar (cig_cap + 1) | the device's u32 row offsets (n + 1).  Freed blocks are cached process-wide so that
+// steady-state calls do not pay cudaHostAlloc.
+struct ResultImpl { bsq_result pub; void* block; size_t bytes; uint64_t row_cap, cig_cap; uint32_t* o32; };
 struct PinnedCache { void* ptr[4]; size_t bytes[4]; };
 PinnedCache g_pinned = {{nullptr, nullptr, nullptr, nullptr}, {0, 0, 0, 0}};
 std::mutex g_pinned_mu;
@@ -564,39 +622,37 @@ void pinned_put(void* p, size_t bytes) {
     cudaFreeHost(p);
 }
 
-int download_result(bsq_index* h, bsq_result** out) {
-    Batch& b = h->batch;
-    if (!b.aligned) { bsq_set_error("no aligned batch to download"); return BSQ_ERR; }
-    const uint64_t n = b.n;
-    h->timing.d2h_bytes = 0;
-    uint32_t tail[2] = {0, 0}, cig_top = 0;
-    const bool have = n != 0 && h->meta.built;
-    if (have) {
-        CUDA_CHECK(cudaMemcpyAsync(&tail[0], b.row_off.p + (n - 1), 4, cudaMemcpyDeviceToHost, h->stream));
-        CUDA_CHECK(cudaMemcpyAsync(&tail[1], b.row_cnt.p + (n - 1), 4, cudaMemcpyDeviceToHost, h->stream));
-        CUDA_CHECK(cudaMemcpyAsync(&cig_top, b.ctl.p + 6, 4, cudaMemcpyDeviceToHost, h->stream));
-        CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    }
-    const uint64_t total_rows = (uint64_t)tail[0] + tail[1];
-    // block layout: row_off (u64 x (n+1)) | rows | cigar | staging for the device's u32 offsets
+ResultImpl* result_new(uint64_t n, uint64_t row_cap, uint64_t cig_cap) {
     const size_t off_rows = ((n + 1) * 8 + 63) & ~(size_t)63;
-    const size_t off_cig = (off_rows + (total_rows + 1) * sizeof(bsq_row) + 63) & ~(size_t)63;
-    const size_t off_o32 = (off_cig + ((size_t)cig_top + 1) * 4 + 63) & ~(size_t)63;
+    const size_t off_cig = (off_rows + (row_cap + 1) * sizeof(bsq_row) + 63) & ~(size_t)63;
+    const size_t off_o32 = (off_cig + (cig_cap + 1) * 4 + 63) & ~(size_t)63;
     const size_t need = off_o32 + (n + 1) * 4;
     size_t got = 0;
     void* block = pinned_get(need, &got);
-    if (!block) { bsq_set_error("cannot allocate %zu bytes of pinned host memory for the result", need); return BSQ_ERR; }
+    if (!block) { bsq_set_error("cannot allocate %zu bytes of pinned host memory for the result", need); return nullptr; }
     ResultImpl* R = new ResultImpl;
-    R->block = block; R->bytes = got;
+    R->block = block; R->bytes = got; R->row_cap = row_cap; R->cig_cap = cig_cap;
     R->pub.n_reads = n;
     R->pub.row_off = reinterpret_cast<uint64_t*>(block);
     R->pub.rows = reinterpret_cast<bsq_row*>(static_cast<char*>(block) + off_rows);
     R->pub.cigar = reinterpret_cast<uint32_t*>(static_cast<char*>(block) + off_cig);
-    R->pub.n_cigar_words = cig_top;
-    *out = &R->pub;
-    if (!have) { for (uint64_t i = 0; i <= n; ++i) R->pub.row_off[i] = 0; return BSQ_OK; }
-    uint32_t* o32 = reinterpret_cast<uint32_t*>(static_cast<char*>(block) + off_o32);
-    CUDA_CHECK(cudaMemcpyAsync(o32, b.row_off.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    R->pub.n_cigar_words = 0;
+    R->o32 = reinterpret_cast<uint32_t*>(static_cast<char*>(block) + off_o32);
+    return R;
+}
+
+void result_delete(ResultImpl* R) { if (R) { pinned_put(R->block, R->bytes); delete R; } }
+
+// Compacts the aligned batch's rows on the device (+ MAPQ) and starts the copies into the result: the batch's reads are
+// reads [read_base, read_base + b.n) of the result, its rows go to row_base, its CIGAR words to cig_base.
+int download_enqueue(bsq_index* h, Batch& b, ResultImpl* R, uint64_t read_base, uint64_t row_base, uint64_t cig_base) {
+    const uint64_t n = b.n;
+    if (n == 0 || !h->meta.built || !b.aligned) return BSQ_OK;
+    const uint64_t total_rows = b.out_rows; const uint32_t cig_top = b.out_cig;
+    if (row_base + total_rows > R->row_cap || cig_base + cig_top > R->cig_cap || cig_base + cig_top > 0xffffffffull) { bsq_set_error("result block too small"); return BSQ_ERR; }
+    cudaStream_t st = b.st;
+    b.ctl_host[10] = 0;
+    CUDA_CHECK(cudaMemcpyAsync(R->o32 + read_base, b.row_off.p, n * 4, cudaMemcpyDeviceToHost, st));
     if (total_rows) {
         CUDA_CHECK(b.rows_compact.ensure(total_rows));
         if (!h->d_logtab) {
@@ -608,17 +664,110 @@ int download_result(bsq_index* h, bsq_result** out) {
         }
         MapqParams M; M.a = h->opts.a; M.b = h->opts.b; M.min_seed_len = h->opts.min_seed_len; M.coef_len = h->mapQ_coef_len;
         M.coef_fac = (double)h->mapQ_coef_fac; M.logtab = h->d_logtab;
-        k_compact_rows<<<148 * 8, 256, 0, h->stream>>>(b.blocks.p, b.rows.p, b.row_cnt.p, b.row_off.p, (uint32_t)n, b.rows_compact.p, M); ++h->timing.launches;
-        CUDA_CHECK(cudaMemcpyAsync(R->pub.rows, b.rows_compact.p, total_rows * sizeof(bsq_row), cudaMemcpyDeviceToHost, h->stream));
+        k_compact_rows<<<148 * 8, 256, 0, st>>>(b.blocks.p, b.rows.p, b.row_cnt.p, b.row_off.p, (uint32_t)n, b.rows_compact.p, M, (uint32_t)cig_base, b.ctl.p + 30); ++h->timing.launches;
+        CUDA_CHECK(cudaMemcpyAsync(R->pub.rows + row_base, b.rows_compact.p, total_rows * sizeof(bsq_row), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(b.ctl_host + 10, b.ctl.p + 30, 4, cudaMemcpyDeviceToHost, st));
     }
-    if (cig_top) CUDA_CHECK(cudaMemcpyAsync(R->pub.cigar, b.cigar.p, (size_t)cig_top * 4, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    for (uint64_t i = 0; i < n; ++i) R->pub.row_off[i] = o32[i];
-    R->pub.row_off[n] = total_rows;
-    h->timing.d2h_bytes = n * 4 + 12 + total_rows * sizeof(bsq_row) + (uint64_t)cig_top * 4;
-    // rows outside the device log table (very long alignments): finish MAPQ on the host
-    for (uint64_t i = 0; i < total_rows; ++i)
-        if (R->pub.rows[i].mapq < 0) R->pub.rows[i].mapq = approx_mapq(h, R->pub.rows[i]);
+    if (cig_top) CUDA_CHECK(cudaMemcpyAsync(R->pub.cigar + cig_base, b.cigar.p, (size_t)cig_top * 4, cudaMemcpyDeviceToHost, st));
+    h->timing.d2h_bytes += n * 4 + 12 + total_rows * sizeof(bsq_row) + (uint64_t)cig_top * 4;
+    return BSQ_OK;
+}
+
+// after the copies have landed: 64-bit row offsets, and MAPQ of the rows outside the device log table (very long
+// alignments).  n reads starting at read_base, n_rows rows starting at row_base.
+void download_finish(bsq_index* h, ResultImpl* R, uint64_t n, uint64_t read_base, uint64_t n_rows, uint64_t row_base, bool host_mapq) {
+    if (!h->meta.built) { for (uint64_t i = 0; i < n; ++i) R->pub.row_off[read_base + i] = row_base; return; }
+    for (uint64_t i = 0; i < n; ++i) R->pub.row_off[read_base + i] = row_base + R->o32[read_base + i];
+    if (n_rows && host_mapq)
+        for (uint64_t i = row_base; i < row_base + n_rows; ++i)
+            if (R->pub.rows[i].mapq < 0) R->pub.rows[i].mapq = approx_mapq(h, R->pub.rows[i]);
+}
+
+int download_result(bsq_index* h, Batch& b, bsq_result** out) {
+    if (!b.aligned) { bsq_set_error("no aligned batch to download"); return BSQ_ERR; }
+    h->timing.d2h_bytes = 0;
+    ResultImpl* R = result_new(b.n, b.out_rows, b.out_cig);
+    if (!R) return BSQ_ERR;
+    if (download_enqueue(h, b, R, 0, 0, 0) != BSQ_OK || cudaStreamSynchronize(b.st) != cudaSuccess) { result_delete(R); if (!*bsq_last_error()) bsq_set_error("download failed"); return BSQ_ERR; }
+    download_finish(h, R, b.n, 0, b.out_rows, 0, b.ctl_host && b.ctl_host[10]);
+    R->pub.row_off[b.n] = b.out_rows;
+    R->pub.n_cigar_words = b.out_cig;
+    *out = &R->pub;
+    return BSQ_OK;
+}
+
+// bsq_align_batch on a large batch: the reads are cut into chunks that alternate between two lanes (batch + stream
+// each), so that a chunk's host->device copy and its result's device->host copy run while the other lane computes.
+// Chunk c's rows follow chunk c-1's in the result, so downloads are issued in chunk order; a lane takes chunk c+2 as
+// soon as chunk c's download has been queued (stream order protects the device buffers), and the host-side completion
+// of a download is deferred until the next chunk's work is in the queue.
+constexpr uint64_t CHUNK_READS = 1u << 17;
+
+int align_chunked(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, bsq_result** out, bool* fell_back) {
+    *fell_back = false;
+    if (!h->stream2) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        h->batch2.st = h->stream2;
+    }
+    Batch* lane[2] = {&h->batch, &h->batch2};
+    for (Batch* b : lane) if (!b->evx_ok) { for (auto& e : b->ev_x) cudaEventCreate(&e); b->evx_ok = true; }
+    const uint64_t n_chunks = (n + CHUNK_READS - 1) / CHUNK_READS;
+    auto start_of = [&](uint64_t c) { return std::min<uint64_t>(c * CHUNK_READS, n); };
+    auto launch = [&](uint64_t c) -> int {
+        Batch& b = *lane[c & 1];
+        const uint64_t s0 = start_of(c), cnt = start_of(c + 1) - s0;
+        b.intv_cap = std::max(b.intv_cap, lane[(c & 1) ^ 1]->intv_cap);      // capacities learnt by one lane serve the other
+        cudaEventRecord(b.ev_x[0], b.st);
+        if (upload_reads(h, b, seqs, offs + s0, ids + s0, cnt) != BSQ_OK) return BSQ_ERR;
+        cudaEventRecord(b.ev_x[1], b.st);
+        return pipeline_enqueue(h, b);
+    };
+    struct Pending { bool on = false; uint64_t c = 0, n = 0, n_rows = 0, row_base = 0; } pend;
+    ResultImpl* R = nullptr;
+    auto complete = [&](const Pending& q) -> int {       // host side of chunk q.c's download
+        Batch& b = *lane[q.c & 1];
+        if (cudaEventSynchronize(b.ev_x[3]) != cudaSuccess) { bsq_set_error("result download failed: %s", cudaGetErrorString(cudaGetLastError())); return BSQ_ERR; }
+        float ms;
+        if (cudaEventElapsedTime(&ms, b.ev_x[2], b.ev_x[3]) == cudaSuccess) h->timing.d2h += ms;
+        download_finish(h, R, q.n, start_of(q.c), q.n_rows, q.row_base, b.ctl_host[10] != 0);
+        return BSQ_OK;
+    };
+    uint64_t row_base = 0, cig_base = 0;
+    int rc = launch(0);
+    if (rc == BSQ_OK && n_chunks > 1) rc = launch(1);
+    for (uint64_t c = 0; c < n_chunks && rc == BSQ_OK; ++c) {
+        Batch& b = *lane[c & 1];
+        if ((rc = pipeline_finish(h, b)) != BSQ_OK) break;
+        { float ms; if (cudaEventElapsedTime(&ms, b.ev_x[0], b.ev_x[1]) == cudaSuccess) h->timing.h2d += ms; }
+        if (!R) {
+            // capacity of the result from the first chunk's yield
+            const double scale = (double)n / (double)b.n * 1.2;
+            R = result_new(n, (uint64_t)(b.out_rows * scale) + 65536, (uint64_t)(b.out_cig * scale) + 65536);
+            if (!R) { rc = BSQ_ERR; break; }
+        }
+        if (row_base + b.out_rows > R->row_cap || cig_base + b.out_cig > R->cig_cap) { *fell_back = true; break; }
+        cudaEventRecord(b.ev_x[2], b.st);
+        if ((rc = download_enqueue(h, b, R, start_of(c), row_base, cig_base)) != BSQ_OK) break;
+        cudaEventRecord(b.ev_x[3], b.st);
+        Pending mine; mine.on = true; mine.c = c; mine.n = b.n; mine.n_rows = b.out_rows; mine.row_base = row_base;
+        row_base += b.out_rows; cig_base += b.out_cig;
+        if (pend.on) { if ((rc = complete(pend)) != BSQ_OK) break; pend.on = false; }
+        // chunk c-1's lane is free on the host side now (its download completed): it already runs chunk c+1.
+        // This lane takes chunk c+2 behind its download.
+        if (c + 2 < n_chunks) { if ((rc = launch(c + 2)) != BSQ_OK) break; }
+        pend = mine;
+    }
+    if (rc == BSQ_OK && !*fell_back && pend.on) rc = complete(pend);
+    if (rc != BSQ_OK || *fell_back) {
+        cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->stream2);
+        cudaGetLastError();
+        h->batch.idle = h->batch2.idle = true; h->batch.aligned = h->batch2.aligned = false;
+        result_delete(R);
+        return rc;
+    }
+    R->pub.row_off[n] = row_base;
+    R->pub.n_cigar_words = cig_base;
+    *out = &R->pub;
     return BSQ_OK;
 }
 
@@ -630,20 +779,23 @@ int bsq_reads_upload(bsq_index* h, const char* seqs, const uint64_t* offs, const
     if (!h || (n && (!seqs || !offs || !ids))) { bsq_set_error("null argument"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
     h->timing.launches = 0;
-    return upload_reads(h, seqs, offs, ids, n);
+    h->timing.h2d_bytes = 0;
+    if (upload_reads(h, h->batch, seqs, offs, ids, n) != BSQ_OK) return BSQ_ERR;
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return BSQ_OK;
 }
 
 int bsq_align_resident(bsq_index* h) {
     if (!h) { bsq_set_error("null index"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
     h->timing.launches = 0;
-    return run_pipeline(h);
+    return run_pipeline(h, h->batch);
 }
 
 int bsq_result_download(bsq_index* h, bsq_result** out) {
     if (!h || !out) { bsq_set_error("null argument"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
-    return download_result(h, out);
+    return download_result(h, h->batch, out);
 }
 
 int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, bsq_result** out) {
@@ -651,18 +803,30 @@ int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const 
     CUDA_CHECK(cudaSetDevice(h->device));
     cudaEvent_t e0, e1, e2, e3;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
-    h->timing.launches = 0;
+    bsq_timing& T = h->timing;
+    T.launches = 0; T.h2d_bytes = T.d2h_bytes = 0; T.h2d = T.d2h = 0;
+    int rc = BSQ_OK;
+    bool chunked = n >= 2 * CHUNK_READS && h->meta.built && !getenv("BSQ_NO_CHUNKS");
     cudaEventRecord(e0, h->stream);
-    int rc = upload_reads(h, seqs, offs, ids, n);
-    cudaEventRecord(e1, h->stream);
-    uint64_t l0 = h->timing.launches;
-    if (rc == BSQ_OK) rc = run_pipeline(h);
-    cudaEventRecord(e2, h->stream);
-    if (rc == BSQ_OK) rc = download_result(h, out);
-    cudaEventRecord(e3, h->stream);
-    cudaEventSynchronize(e3);
-    (void)l0;
-    cudaEventElapsedTime(&h->timing.h2d, e0, e1); cudaEventElapsedTime(&h->timing.d2h, e2, e3); cudaEventElapsedTime(&h->timing.total, e0, e3);
+    if (chunked) {
+        // two lanes, copies overlapped with compute; the stage times are sums over chunks of each lane's stream time
+        T.seed = T.chain = T.extend = T.finalize = T.total = 0;
+        memset(h->counters, 0, sizeof(h->counters));
+        bool fell_back = false;
+        rc = align_chunked(h, seqs, offs, ids, n, out, &fell_back);
+        if (fell_back) { chunked = false; T.h2d_bytes = T.d2h_bytes = 0; T.h2d = T.d2h = 0; }   // the result outgrew the estimate: one plain pass
+        else { cudaEventRecord(e3, h->stream); cudaEventSynchronize(e3); cudaEventElapsedTime(&T.total, e0, e3); }
+    }
+    if (!chunked) {
+        rc = upload_reads(h, h->batch, seqs, offs, ids, n);
+        cudaEventRecord(e1, h->stream);
+        if (rc == BSQ_OK) rc = run_pipeline(h, h->batch);
+        cudaEventRecord(e2, h->stream);
+        if (rc == BSQ_OK) rc = download_result(h, h->batch, out);
+        cudaEventRecord(e3, h->stream);
+        cudaEventSynchronize(e3);
+        cudaEventElapsedTime(&T.h2d, e0, e1); cudaEventElapsedTime(&T.d2h, e2, e3); cudaEventElapsedTime(&T.total, e0, e3);
+    }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
     return rc;
 }
@@ -687,7 +851,7 @@ int bsq_debug_seed(bsq_index* h, const char* seqs, const uint64_t* offs, uint64_
     if (!h || !h->meta.built) { bsq_set_error("index not built"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
     std::vector<int64_t> ids(n, 0);
-    if (upload_reads(h, seqs, offs, ids.data(), n) != BSQ_OK) return BSQ_ERR;
+    if (upload_reads(h, h->batch, seqs, offs, ids.data(), n) != BSQ_OK) return BSQ_ERR;
     Batch& b = h->batch;
     const DevIndex ix = make_dev_index(h);
     if (ensure_kmer_table(h, ix) != BSQ_OK) return BSQ_ERR;

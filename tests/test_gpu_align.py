@@ -155,3 +155,47 @@ def test_align_long_reads(gpu_lib, opts_fn, rlen, err):
     assert not bad, "\n".join(bad)
     assert o["counters"]["sw_calls"] > 0
     assert int(g.row_off[-1]) >= n
+
+
+def _flat_cigars(res):
+    """per-row CIGAR words concatenated in row order (independent of where the pool put them)"""
+    off, n = res.rows["cigar_off"].astype(np.int64), res.rows["n_cigar"].astype(np.int64)
+    if len(n) == 0 or n.sum() == 0:
+        return np.zeros(0, dtype=np.uint32)
+    idx = np.repeat(off - np.concatenate(([0], np.cumsum(n)[:-1])), n) + np.arange(n.sum())
+    return res.cigar[idx]
+
+
+def test_align_batch_chunked_pipeline(gpu_lib):
+    """bsq_align_batch cuts a large batch into chunks on two lanes (copies overlapped with compute): rows, their order
+    and the rebased CIGAR offsets must equal the single-lane resident path's, and the oracle's on a sample."""
+    from helpers import PARITY_FIELDS
+    rows = synth.reference_rows([600_001, 400_003], seed=71)
+    rows = synth.plant_repeats(rows, n_families=6, copies=6, unit=(200, 800), divergence=0.02)
+    orc, gpu = build_pair(rows, O.sql_default_opts(2))
+    n = 2 * (1 << 17) + 12_345                      # two full chunks and a ragged third
+    seqs, offs, _ = synth.simulate_reads(rows, n, 100, sub=0.015, ins=0.002, dele=0.002, seed=72, n_frac=0.001)
+    ids = synth.lrand48_ids_fast(n)
+    g = gpu.align_batch(seqs, offs, ids)             # chunked
+    assert gpu.timing().launches > 40                # more launches than one pass of the pipeline: the chunks really ran
+    gpu.upload(seqs, offs, ids); gpu.align_resident(); r = gpu.download_result()
+    assert np.array_equal(g.row_off, r.row_off)
+    for f in PARITY_FIELDS:
+        assert np.array_equal(g.rows[f], r.rows[f]), f
+    assert np.array_equal(_flat_cigars(g), _flat_cigars(r))
+    # the oracle on reads that straddle the chunk boundaries and the tail
+    pick = np.concatenate([np.arange((1 << 17) - 600, (1 << 17) + 600), np.arange(2 * (1 << 17) - 600, 2 * (1 << 17) + 600), np.arange(n - 800, n)])
+    s_offs = np.zeros(len(pick) + 1, dtype=np.uint64)
+    lens = (offs[pick + 1] - offs[pick]).astype(np.int64)
+    s_offs[1:] = np.cumsum(lens)
+    s_seqs = np.concatenate([seqs[int(offs[i]):int(offs[i + 1])] for i in pick])
+    o = orc.align_batch(s_seqs, s_offs, ids[pick], 4)
+    cnt_g = np.diff(g.row_off.astype(np.int64))[pick]
+    assert np.array_equal(cnt_g, np.diff(o["row_off"].astype(np.int64)))
+    sel = np.concatenate([np.arange(int(g.row_off[i]), int(g.row_off[i + 1])) for i in pick]).astype(np.int64)
+    for f in PARITY_FIELDS:
+        assert np.array_equal(g.rows[f][sel], o["rows"][f]), f
+    gc = _flat_cigars(type(g)(g.row_off, g.rows[sel], g.cigar))
+    oo, on = o["rows"]["cigar_off"].astype(np.int64), o["rows"]["n_cigar"].astype(np.int64)
+    oc = np.concatenate([o["cigar"][int(a):int(a + b)] for a, b in zip(oo, on)]) if on.sum() else np.zeros(0, dtype=np.uint32)
+    assert np.array_equal(gc, oc)

@@ -701,7 +701,15 @@ int download_result(bsq_index* h, Batch& b, bsq_result** out) {
 // Chunk c's rows follow chunk c-1's in the result, so downloads are issued in chunk order; a lane takes chunk c+2 as
 // soon as chunk c's download has been queued (stream order protects the device buffers), and the host-side completion
 // of a download is deferred until the next chunk's work is in the queue.
-constexpr uint64_t CHUNK_READS = 1u << 17;
+// chunk size: a quarter of the batch, within [64 K, 256 K] reads (measured on B200, 1 M x 150 bp: 64 K 66.7 ms,
+// 128 K 65.7, 256 K 64.5, 512 K 68.2, 32 K 78.8 per step).  BSQ_CHUNK_READS overrides it.
+constexpr uint64_t CHUNK_MIN = 1u << 16, CHUNK_MAX = 1u << 18;
+uint64_t chunk_reads(uint64_t n) {
+    static long long env = -1;
+    if (env < 0) { env = 0; if (const char* e = getenv("BSQ_CHUNK_READS")) { const long long x = atoll(e); if (x >= 1024) env = x; } }
+    if (env > 0) return (uint64_t)env;
+    return std::min(std::max((n + 3) / 4, CHUNK_MIN), CHUNK_MAX);
+}
 
 int align_chunked(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, bsq_result** out, bool* fell_back) {
     *fell_back = false;
@@ -711,6 +719,7 @@ int align_chunked(bsq_index* h, const char* seqs, const uint64_t* offs, const in
     }
     Batch* lane[2] = {&h->batch, &h->batch2};
     for (Batch* b : lane) if (!b->evx_ok) { for (auto& e : b->ev_x) cudaEventCreate(&e); b->evx_ok = true; }
+    const uint64_t CHUNK_READS = chunk_reads(n);
     const uint64_t n_chunks = (n + CHUNK_READS - 1) / CHUNK_READS;
     auto start_of = [&](uint64_t c) { return std::min<uint64_t>(c * CHUNK_READS, n); };
     auto launch = [&](uint64_t c) -> int {
@@ -806,7 +815,7 @@ int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const 
     bsq_timing& T = h->timing;
     T.launches = 0; T.h2d_bytes = T.d2h_bytes = 0; T.h2d = T.d2h = 0;
     int rc = BSQ_OK;
-    bool chunked = n >= 2 * CHUNK_READS && h->meta.built && !getenv("BSQ_NO_CHUNKS");
+    bool chunked = n >= 2 * chunk_reads(n) && h->meta.built && !getenv("BSQ_NO_CHUNKS");
     cudaEventRecord(e0, h->stream);
     if (chunked) {
         // two lanes, copies overlapped with compute; the stage times are sums over chunks of each lane's stream time

@@ -199,6 +199,26 @@ __device__ __forceinline__ int narrow_class(const DevOpts& o, const RegRec& ar, 
     return 2 * gen_cigar_band(o, lq, (int)rl, w2) + 1 <= NARROW_NC ? 1 : 0;
 }
 
+// the register-band kernel derives scores from the three values bwa_fill_scmat produces (match, mismatch, ambiguous)
+__device__ __forceinline__ bool mat_is_simple(const int* smat) {
+    bool ok = true;
+    for (int a = 0; a < 5; ++a)
+        for (int b = 0; b < 5; ++b) ok = ok && smat[a * 5 + b] == ((a == 4 || b == 4) ? smat[4] : (a == b ? smat[0] : smat[1]));
+    return ok;
+}
+
+// A job list holds both classes of thread-per-region work so that the lanes of a warp do similar work: regions whose band
+// fits the register window (w <= REG_WT) grow from the front, wider ones (shared-memory kernel) from the back.
+constexpr int REG_WT = 16;
+__device__ __forceinline__ bool narrow_is_big(const DevOpts& o, int lq, int rlen, int w2, bool simple_mat) {
+    w2 = w2 < o.w << 2 ? w2 : o.w << 2;
+    return !simple_mat || gen_cigar_band(o, lq, rlen, w2) > REG_WT;
+}
+__device__ __forceinline__ void push_narrow(NarrowJob* list, uint32_t cap, uint32_t* cnt_reg, uint32_t* cnt_big, const NarrowJob& jb, bool big) {
+    if (big) list[cap - 1u - atomicAdd(cnt_big, 1u)] = jb;
+    else list[atomicAdd(cnt_reg, 1u)] = jb;
+}
+
 // mem_reg2aln for one region on the whole warp; completes *out (NM, pos, is_rev, CIGAR)
 __device__ void reg2aln_warp(const FinalizeParams& P, const DevIndex& ix, const DevOpts& o, const int* smat, const FScratch& S, uint32_t cig_cap,
                              uint32_t rseq_cap, int l_query, const RegRec& ar, RowDev* out, unsigned long long& cells, unsigned long long& calls) {
@@ -255,6 +275,7 @@ __global__ void __launch_bounds__(FIN_THREADS) regs_finalize(FinalizeParams P, D
     __shared__ int smat[25];
     if (threadIdx.x < 25) smat[threadIdx.x] = o.mat[threadIdx.x];
     __syncthreads();
+    const bool simple_mat = mat_is_simple(smat);
     const int lane = lane_id();
     const uint32_t gwarp = (blockIdx.x * FIN_THREADS + threadIdx.x) >> 5;
     FScratch S;
@@ -393,9 +414,10 @@ __global__ void __launch_bounds__(FIN_THREADS) regs_finalize(FinalizeParams P, D
                 rows[i] = row;
                 if (narrow) {
                     // DP regions and no-DP regions go to separate lists so that the lanes of a warp do similar work
-                    const uint32_t k = ncls == 1 ? atomicAdd(P.narrow_cnt, 1u) : 2u * P.narrow_cap + atomicAdd(P.narrow_cnt + 3, 1u);
                     NarrowJob jb; jb.r = r; jb.slot = blk.base + i; jb.w2 = reg2aln_w2(o, ar); jb.last_sc = -(1 << 30); jb.it = 0; jb.score = 0;
-                    reinterpret_cast<NarrowJob*>(P.narrow_jobs)[k] = jb;
+                    NarrowJob* lists = reinterpret_cast<NarrowJob*>(P.narrow_jobs);
+                    if (ncls == 1) push_narrow(lists, P.narrow_cap, P.narrow_cnt, P.narrow_cnt + 5, jb, narrow_is_big(o, ar.qe - ar.qb, (int)(ar.re - ar.rb), jb.w2, simple_mat));
+                    else lists[2u * P.narrow_cap + atomicAdd(P.narrow_cnt + 3, 1u)] = jb;
                 }
             }
             __syncwarp();
@@ -407,6 +429,96 @@ __global__ void __launch_bounds__(FIN_THREADS) regs_finalize(FinalizeParams P, D
 }
 
 // ---------------------------------------------------------------------------------------------------
+// ksw_global2 on ONE thread with the band in registers.  In diagonal coordinates kk = j - i + WT a cell's three
+// inputs are: the diagonal H(i-1, j-1) at the SAME kk, E from (i-1, j) at kk + 1, F from (i, j-1) at kk - 1 -- so
+// with the kk loop fully unrolled the whole band state (Hd[], Ep[]) is a register file, nothing is indexed
+// dynamically and no shared memory is needed.  A region's own band [i - w, i + w] (w <= WT) is a sub-range of the
+// window: cells outside [beg, end) are computed but masked where it matters (their E and F outputs are -inf, as
+// ksw_global2 has it for cells it never computes; their H is never consumed).  The query travels in a nibble
+// window that slides one base per row; scores come from the three distinct values of bwa_fill_scmat.
+// Z (traceback): one byte per cell, [row][kk / 4][lane] words.  Returns eh[qlen].h.
+template <int WT>
+__device__ __forceinline__ int global_dp_reg(const uint8_t* __restrict__ qg, int lq, bool rev, const uint8_t* __restrict__ pac, int64_t tbase,
+                                             int rlen, int w, int sA, int sB, int sN, int o_del, int e_del, int o_ins, int e_ins,
+                                             uint32_t* __restrict__ Z, unsigned long long& cells) {
+    constexpr int W = 2 * WT + 1, NW = (W + 7) / 8, ZW = (W + 3) / 4;
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    int Hd[W], Ep[W + 1];
+    uint32_t win[NW];
+#pragma unroll
+    for (int kk = 0; kk < W; ++kk) {
+        const int j = kk - WT;                     // row 0: eh[j].h = H(-1, j-1) = -(o_ins + e_ins j) for 1 <= j <= w
+        Hd[kk] = (j >= 1 && j <= w) ? -(o_ins + e_ins * j) : KSW_NEG_INF;
+        Ep[kk] = KSW_NEG_INF;
+    }
+    Ep[W] = KSW_NEG_INF;
+#pragma unroll
+    for (int x = 0; x < NW; ++x) win[x] = 0xffffffffu;
+#pragma unroll
+    for (int kk = WT; kk < W; ++kk) {
+        const int j = kk - WT;
+        if (j < lq) {
+            const uint32_t b = rev ? qg[lq - 1 - j] : qg[j];
+            win[kk >> 3] = (win[kk >> 3] & ~(15u << ((kk & 7) * 4))) | (b << ((kk & 7) * 4));
+        }
+    }
+    int tb = rev ? 3 - (int)pac_get(pac, tbase) : (int)pac_get(pac, tbase);
+    for (int i = 0; i < rlen; ++i) {
+        const int beg = i > w ? i - w : 0;
+        const int end = i + w + 1 < lq ? i + w + 1 : lq;
+        const int ioff = i - WT - beg;                  // kk + ioff = j - beg
+        const unsigned span = (unsigned)(end - beg);
+        const int tz = beg == 0 ? 0 : 0x7fffffff;      // j == 0 (first column): the diagonal input is H(i-1, -1)
+        const int colm1 = i == 0 ? 0 : -(o_del + e_del * i);
+        cells += span;
+        // next row's inputs: reference base, query base entering the window
+        int tb_next = 0; uint32_t nb = 15u;
+        if (i + 1 < rlen) tb_next = rev ? 3 - (int)pac_get(pac, tbase + i + 1) : (int)pac_get(pac, tbase + i + 1);
+        { const int jn = i + 1 + WT; if (jn < lq) nb = rev ? qg[lq - 1 - jn] : qg[jn]; }
+        int f = KSW_NEG_INF;
+        uint32_t zpack = 0;
+        uint32_t* zi = Z + (size_t)i * ZW * 32;
+#pragma unroll
+        for (int kk = 0; kk < W; ++kk) {
+            const int t = ioff + kk;
+            const bool valid = (unsigned)t < span;
+            const int qb = (int)((win[kk >> 3] >> ((kk & 7) * 4)) & 15u);
+            const int sc = qb == tb ? sA : (qb < 4 ? sB : sN);
+            int m = (t == tz ? colm1 : Hd[kk]) + sc;
+            int e = Ep[kk + 1];
+            int d = m >= e ? 0 : 1;
+            int h = m >= e ? m : e;
+            d = h >= f ? d : 2;
+            h = h >= f ? h : f;
+            Hd[kk] = h;
+            int tt = m - oe_del;
+            e -= e_del;
+            d |= e > tt ? 1 << 2 : 0;
+            e = e > tt ? e : tt;
+            Ep[kk] = valid ? e : KSW_NEG_INF;
+            tt = m - oe_ins;
+            int f2 = f - e_ins;
+            d |= f2 > tt ? 2 << 4 : 0;
+            f2 = f2 > tt ? f2 : tt;
+            f = valid ? f2 : f;
+            zpack |= (uint32_t)d << ((kk & 3) * 8);
+            if ((kk & 3) == 3 || kk == W - 1) { zi[(kk >> 2) * 32] = zpack; zpack = 0; }
+        }
+        // slide the query window by one base
+#pragma unroll
+        for (int x = 0; x + 1 < NW; ++x) win[x] = __funnelshift_r(win[x], win[x + 1], 4);
+        win[NW - 1] = ((win[NW - 1] >> 4) & ~(15u << (((W - 1) & 7) * 4))) | (nb << (((W - 1) & 7) * 4));
+        tb = tb_next;
+    }
+    // eh[qlen].h after the last row = H(rlen-1, lq-1): diagonal offset lq - rlen + WT
+    const int ks = lq - rlen + WT;
+    int score = KSW_NEG_INF;
+#pragma unroll
+    for (int kk = 0; kk < W; ++kk) if (kk == ks) score = Hd[kk];
+    return score;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Thread-per-region mem_reg2aln for narrow bands (the common case for 150 bp reads: w = 6..31).
 // One thread runs the scalar ksw_global2 recurrence; the row buffer is a 64-entry circular window in
 // shared memory laid out [column][thread] (bank = thread, conflict-free for any column), the query is
@@ -415,13 +527,17 @@ __global__ void __launch_bounds__(FIN_THREADS) regs_finalize(FinalizeParams P, D
 // A region whose retry needs a wider band is handed to regs_cigar_wide (warp-cooperative rows).
 struct NarrowParams {
     const uint8_t* seqs; const uint64_t* offs; const RegRec* regs; RowDev* rows;
-    const NarrowJob* jobs; const uint32_t* n_jobs; NarrowJob* requeue; uint32_t* requeue_cnt; uint64_t* wide_jobs; uint32_t* wide_cnt;
+    const NarrowJob* jobs; int job_stride; const uint32_t* n_jobs;      // jobs[k * job_stride]: a list's front (+1) or back (-1) section
+    NarrowJob* requeue; uint32_t requeue_cap; uint32_t* requeue_cnt; uint32_t* requeue_big_cnt; uint64_t* wide_jobs; uint32_t* wide_cnt;
     uint32_t* cigar_pool; uint32_t cigar_cap; uint32_t* cigar_top;
     uint8_t* zbuf; uint32_t* ticket; uint32_t* overflow; unsigned long long* counters;
     int diag_pass;   // 1: equal-length regions -- finish the ones whose diagonal is provably optimal, hand the rest to the DP list
 };
 
-__global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams P, DevIndex ix, DevOpts o) {
+// MODE 0: circular row window in shared memory (bands up to NARROW_NC columns); MODE 1: the band in registers
+// (global_dp_reg, w <= REG_WT), no shared memory, regions with a wider band are passed on to a MODE 0 launch.
+template <int MODE>
+__global__ void __launch_bounds__(NARROW_THREADS, MODE == 1 ? 4 : 1) regs_cigar_narrow(NarrowParams P, DevIndex ix, DevOpts o) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ int smat[25];
     if (threadIdx.x < 25) smat[threadIdx.x] = o.mat[threadIdx.x];
@@ -432,7 +548,10 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
     uint8_t* Q = dyn_smem + 2 * NARROW_NC * NARROW_THREADS * 4 + tid;               // Q[j * NARROW_THREADS]
     const uint32_t gwarp = (blockIdx.x * NARROW_THREADS + tid) >> 5;
     // traceback bytes, 4 cells per 32-bit store, laid out [row][4-cell group][lane]: a warp store is 128 contiguous bytes
-    uint32_t* Z = reinterpret_cast<uint32_t*>(P.zbuf + (size_t)gwarp * ((size_t)NARROW_TMAX * NARROW_NC * 32)) + lane;
+    constexpr size_t Z_PER_WARP = MODE == 1 ? (size_t)NARROW_TMAX * ((2 * REG_WT + 1 + 3) / 4) * 4 * 32 : (size_t)NARROW_TMAX * NARROW_NC * 32;
+    constexpr int ZROW = MODE == 1 ? (2 * REG_WT + 1 + 3) / 4 : NARROW_NC / 4;      // words per row and lane
+    uint32_t* Z = reinterpret_cast<uint32_t*>(P.zbuf + (size_t)gwarp * Z_PER_WARP) + lane;
+    const bool simple_mat = mat_is_simple(smat);
     int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins, e_del = o.e_del, e_ins = o.e_ins;
     // keep the four gap constants in registers: left to itself the compiler re-reads them from the constant bank per cell
     asm volatile("" : "+r"(oe_del), "+r"(oe_ins), "+r"(e_del), "+r"(e_ins));
@@ -444,7 +563,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
         if ((uint64_t)t * 32 >= n_jobs) break;
         const uint32_t j_id = t * 32 + lane;
         if (j_id < n_jobs) {
-            const NarrowJob jb = P.jobs[j_id];
+            const NarrowJob jb = P.jobs[(long)j_id * P.job_stride];
             const uint32_t r = jb.r, slot = jb.slot;
             const uint64_t job = (uint64_t)r << 32 | slot;
             const RegRec ar = P.regs[slot];
@@ -456,10 +575,9 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
             const bool reject = lq <= 0 || rb >= re || (rb < l_pac && re > l_pac) || rb < 0 || re > (l_pac << 1);
             // libbwa reverses query and reference on the reverse strand; both then read pac ascending
             const int64_t tbase = rev ? (l_pac << 1) - re : rb;
-            {
-                const uint8_t* qg = P.seqs + P.offs[r] + qb;
-                for (int j = 0; j < lq; ++j) Q[j * NARROW_THREADS] = rev ? qg[lq - 1 - j] : qg[j];
-            }
+            const uint8_t* qg = P.seqs + P.offs[r] + qb;
+            if (MODE == 0) for (int j = 0; j < lq; ++j) Q[j * NARROW_THREADS] = rev ? qg[lq - 1 - j] : qg[j];
+            auto qat = [&](int j) -> int { return MODE == 0 ? (int)Q[j * NARROW_THREADS] : (int)(rev ? qg[lq - 1 - j] : qg[j]); };
             uint32_t cg[NARROW_CIG];
             // ONE try of the band-doubling loop per pass; a region that needs another try is re-queued so that the
             // lanes of a warp stay balanced (the loop state travels in the job record)
@@ -478,23 +596,26 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                         int sc = 0;
                         for (int i = 0; i < lq; ++i) {
                             const int tb = rev ? 3 - (int)pac_get(ix.pac, tbase + i) : (int)pac_get(ix.pac, tbase + i);
-                            sc += smat[tb * 5 + Q[i * NARROW_THREADS]];
+                            sc += smat[tb * 5 + qat(i)];
                         }
                         if (diagonal || sc > (lq - 1) * o.mat_max - oe_ins - oe_del) { score = sc; cg[0] = (uint32_t)lq << 4; n_cigar = 1; diagonal = true; }
-                        else { P.requeue[atomicAdd(P.requeue_cnt, 1u)] = jb; again = true; break; }   // needs the DP: over to the DP list, same try
+                        else { push_narrow(P.requeue, P.requeue_cap, P.requeue_cnt, P.requeue_big_cnt, jb, narrow_is_big(o, lq, rlen, jb.w2, simple_mat)); again = true; break; }   // needs the DP: over to the DP list, same try
                     } else if (diagonal) {
                         int sc = 0;
                         for (int i = 0; i < lq; ++i) {
                             const int tb = rev ? 3 - (int)pac_get(ix.pac, tbase + i) : (int)pac_get(ix.pac, tbase + i);
-                            sc += smat[tb * 5 + Q[i * NARROW_THREADS]];
+                            sc += smat[tb * 5 + qat(i)];
                         }
                         score = sc; cg[0] = (uint32_t)lq << 4; n_cigar = 1;
                     }
                     if (!diagonal) {
                         const int w = gen_cigar_band(o, lq, rlen, w2);
                         const int n_col = lq < 2 * w + 1 ? lq : 2 * w + 1;
-                        if (2 * w + 1 > NARROW_NC || rlen > NARROW_TMAX) { go_wide = true; break; }
+                        if ((MODE == 1 ? (w > REG_WT || !simple_mat) : 2 * w + 1 > NARROW_NC) || rlen > NARROW_TMAX) { go_wide = true; break; }
                         ++calls;
+                        if (MODE == 1) {
+                            score = global_dp_reg<REG_WT>(qg, lq, rev, ix.pac, tbase, rlen, w, smat[0], smat[1], smat[4], o.o_del, e_del, o.o_ins, e_ins, Z, cells);
+                        } else {
                         // first row of the band
                         H[0] = 0; E[0] = KSW_NEG_INF;
                         for (int j = 1; j <= lq && j <= w; ++j) { H[(j & (NARROW_NC - 1)) * NARROW_THREADS] = -(o.o_ins + e_ins * j); E[(j & (NARROW_NC - 1)) * NARROW_THREADS] = KSW_NEG_INF; }
@@ -506,7 +627,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                             int f = KSW_NEG_INF;
                             const int tb = rev ? 3 - (int)pac_get(ix.pac, tbase + i) : (int)pac_get(ix.pac, tbase + i);
                             const int* mrow = smat + tb * 5;
-                            uint32_t* zi = Z + (size_t)i * (NARROW_NC / 4) * 32;
+                            uint32_t* zi = Z + (size_t)i * ZROW * 32;
                             cells += (unsigned long long)(end - beg);
                             uint32_t zpack = 0; int zsh = 0;
                             // walking pointers: circular row window (wraps after NARROW_NC columns), staged query column
@@ -542,6 +663,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                             H[ce] = h1; E[ce] = KSW_NEG_INF;
                         }
                         score = H[(lq & (NARROW_NC - 1)) * NARROW_THREADS];
+                        }
                         // traceback
                         {
                             int which = 0, i = rlen - 1, k = (i + w + 1 < lq ? i + w + 1 : lq) - 1;
@@ -551,8 +673,8 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                                 else cg[n_cigar - 1] += len << 4;
                             };
                             while (i >= 0 && k >= 0) {
-                                const int jj = k - (i > w ? i - w : 0);
-                                which = (int)(Z[((size_t)i * (NARROW_NC / 4) + (jj >> 2)) * 32] >> ((jj & 3) << 3) & 0xff) >> (which << 1) & 3;
+                                const int jj = MODE == 1 ? k - i + REG_WT : k - (i > w ? i - w : 0);
+                                which = (int)(Z[((size_t)i * ZROW + (jj >> 2)) * 32] >> ((jj & 3) << 3) & 0xff) >> (which << 1) & 3;
                                 if (which == 0) { push(0, 1); --i; --k; }
                                 else if (which == 1) { push(2, 1); --i; }
                                 else { push(1, 1); --k; }
@@ -571,7 +693,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                         if (op == 0) {
                             for (int i = 0; i < len; ++i) {
                                 const int tb = rev ? 3 - (int)pac_get(ix.pac, tbase + y + i) : (int)pac_get(ix.pac, tbase + y + i);
-                                n_mm += (int)Q[(x + i) * NARROW_THREADS] != tb;
+                                n_mm += qat(x + i) != tb;
                             }
                             x += len; y += len;
                         } else if (op == 2) { if (k > 0 && k < n_cigar - 1) n_gap += len; y += len; }
@@ -584,7 +706,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) regs_cigar_narrow(NarrowParams
                 if (jb.it + 1 < 3 && score < ar.truesc - o.a) {
                     again = true;
                     NarrowJob nx; nx.r = r; nx.slot = slot; nx.w2 = w2 << 1; nx.last_sc = score; nx.it = jb.it + 1; nx.score = score;
-                    P.requeue[atomicAdd(P.requeue_cnt, 1u)] = nx;
+                    push_narrow(P.requeue, P.requeue_cap, P.requeue_cnt, P.requeue_big_cnt, nx, narrow_is_big(o, lq, rlen, nx.w2, simple_mat));
                 }
             } while (false);
             if (go_wide) {
@@ -690,17 +812,29 @@ int finalize_resident_warps() {
     return nb * sms * FIN_WARPS;
 }
 
-size_t narrow_zbuf_bytes(int* n_warps_out) {
-    int nb = 0, dev = 0, sms = 148;
+// resident warps of the two thread-per-region kernels and the traceback buffer that serves both
+static void narrow_geometry(int* warps_smem, int* warps_reg, size_t* zbytes) {
+    int nb = 0, nr = 0, dev = 0, sms = 148;
     const size_t smem = (size_t)NARROW_THREADS * (2 * NARROW_NC * 4 + NARROW_QMAX);
-    cudaFuncSetAttribute(regs_cigar_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, regs_cigar_narrow, NARROW_THREADS, smem);
+    cudaFuncSetAttribute(regs_cigar_narrow<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, regs_cigar_narrow<0>, NARROW_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nr, regs_cigar_narrow<1>, NARROW_THREADS, 0);
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (nb < 1) nb = 1;
-    const int warps = nb * sms * (NARROW_THREADS / 32);
-    if (n_warps_out) *n_warps_out = warps;
-    return (size_t)warps * NARROW_TMAX * NARROW_NC * 32;
+    if (nr < 1) nr = 1;
+    const int ws = nb * sms * (NARROW_THREADS / 32), wr = nr * sms * (NARROW_THREADS / 32);
+    if (warps_smem) *warps_smem = ws;
+    if (warps_reg) *warps_reg = wr;
+    const size_t zs = (size_t)ws * NARROW_TMAX * NARROW_NC * 32, zr = (size_t)wr * NARROW_TMAX * ((2 * REG_WT + 1 + 3) / 4) * 4 * 32;
+    if (zbytes) *zbytes = zs > zr ? zs : zr;
+}
+
+size_t narrow_zbuf_bytes(int* n_warps_out) {
+    int ws = 0; size_t z = 0;
+    narrow_geometry(&ws, nullptr, &z);
+    if (n_warps_out) *n_warps_out = ws;
+    return z;
 }
 
 void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint32_t rseq_cap, int n_warps, uint64_t* launches) {
@@ -716,25 +850,38 @@ void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts&
     if (!p.narrow_jobs) return;
     // phase 2: thread-per-region narrow-band mem_reg2aln, one try of the band-doubling loop per pass (<= 3 tries)
     {
-        int warps = 0;
-        narrow_zbuf_bytes(&warps);
-        if (warps > p.narrow_warps) warps = p.narrow_warps;
+        int warps = 0, warps_reg = 0;
+        narrow_geometry(&warps, &warps_reg, nullptr);
+        if (warps > p.narrow_warps) { warps_reg = (int)((long long)warps_reg * p.narrow_warps / warps); warps = p.narrow_warps; }
         NarrowJob* listA = reinterpret_cast<NarrowJob*>(p.narrow_jobs);
         NarrowJob* listB = listA + p.narrow_cap;
+        NarrowJob* listS = listA + 2 * (size_t)p.narrow_cap;
         const size_t nsmem = (size_t)NARROW_THREADS * (2 * NARROW_NC * 4 + NARROW_QMAX);
         for (int pass = 0; pass < 4; ++pass) {
             // pass 0: equal-length regions (list S): diagonal proof, the rest joins list A; pass 1: DP regions (A -> re-queue B);
-            // pass 2: second tries (B -> A); pass 3: third tries (A)
+            // pass 2: second tries (B -> A); pass 3: third tries (A).  A DP pass is two launches: the register-band kernel on
+            // the front section of the list, the shared-memory kernel on the back section (bands wider than the register window).
+            // counters: 0 A front, 1 B front, 2 A front (third tries), 3 S, 4 sink, 5 A back, 6 B back, 7 A back (third tries)
             NarrowParams q;
             q.seqs = p.seqs; q.offs = p.offs; q.regs = p.regs; q.rows = p.rows;
-            q.jobs = pass == 0 ? listA + 2 * (size_t)p.narrow_cap : (pass == 2 ? listB : listA);
-            q.n_jobs = p.narrow_cnt + (pass == 0 ? 3 : (pass == 1 ? 0 : (pass == 2 ? 1 : 2)));
-            q.requeue = (pass == 0 || pass == 2) ? listA : listB;
+            NarrowJob* in = pass == 0 ? listS : (pass == 2 ? listB : listA);
+            q.requeue = (pass == 0 || pass == 2) ? listA : listB; q.requeue_cap = p.narrow_cap;
             q.requeue_cnt = p.narrow_cnt + (pass == 0 ? 0 : (pass == 1 ? 1 : (pass == 2 ? 2 : 4)));   // pass 3 never re-queues
+            q.requeue_big_cnt = p.narrow_cnt + (pass == 0 ? 5 : (pass == 1 ? 6 : (pass == 2 ? 7 : 4)));
             q.wide_jobs = p.wide_jobs; q.wide_cnt = p.wide_cnt; q.cigar_pool = p.cigar_pool; q.cigar_cap = p.cigar_cap; q.cigar_top = p.cigar_top;
-            q.zbuf = p.narrow_z; q.ticket = p.ticket + 1 + pass; q.overflow = p.overflow; q.counters = p.counters; q.diag_pass = pass == 0;
-            regs_cigar_narrow<<<warps / (NARROW_THREADS / 32), NARROW_THREADS, nsmem, st>>>(q, ix, o);
-            if (launches) ++*launches;
+            q.zbuf = p.narrow_z; q.overflow = p.overflow; q.counters = p.counters; q.diag_pass = pass == 0;
+            q.jobs = in; q.job_stride = 1; q.ticket = p.ticket + 1 + pass;
+            q.n_jobs = p.narrow_cnt + (pass == 0 ? 3 : (pass == 1 ? 0 : (pass == 2 ? 1 : 2)));
+            if (pass == 0) {
+                regs_cigar_narrow<0><<<warps / (NARROW_THREADS / 32), NARROW_THREADS, nsmem, st>>>(q, ix, o);
+                if (launches) ++*launches;
+            } else {
+                regs_cigar_narrow<1><<<warps_reg / (NARROW_THREADS / 32), NARROW_THREADS, 0, st>>>(q, ix, o);
+                q.jobs = in + p.narrow_cap - 1; q.job_stride = -1; q.ticket = p.ticket + 5 + pass;      // tickets 6..8
+                q.n_jobs = p.narrow_cnt + (pass == 1 ? 5 : (pass == 2 ? 6 : 7));
+                regs_cigar_narrow<0><<<warps / (NARROW_THREADS / 32), NARROW_THREADS, nsmem, st>>>(q, ix, o);
+                if (launches) *launches += 2;
+            }
         }
     }
     // phase 3: whatever needed a wider band on a retry

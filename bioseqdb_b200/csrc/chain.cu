@@ -145,9 +145,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS) chain_build(ChainParams P, DevI
             int b = 0, e = 0;
             for (int i = 0; i < n_iv; ++i) {   // uniform across lanes (broadcast loads)
                 uint64_t x2 = iv[i].x2;
-                uint64_t step = x2 > (uint64_t)o.max_occ ? x2 / (uint64_t)o.max_occ : 1;
-                uint64_t cnt = (x2 + step - 1) / step;
-                if (cnt > (uint64_t)o.max_occ) cnt = (uint64_t)o.max_occ;
+                uint64_t cnt = x2;                       // step == 1 unless the interval is larger than max_occ
+                if (x2 > (uint64_t)o.max_occ) {
+                    const uint64_t step = x2 / (uint64_t)o.max_occ;
+                    cnt = (x2 + step - 1) / step;
+                    if (cnt > (uint64_t)o.max_occ) cnt = (uint64_t)o.max_occ;
+                }
                 total += (uint32_t)cnt;
                 if (x2 > (uint64_t)o.max_occ) {
                     int sb = (int)(iv[i].info >> 32), se = (int)(uint32_t)iv[i].info;
@@ -168,23 +171,48 @@ __global__ void __launch_bounds__(CHAIN_THREADS) chain_build(ChainParams P, DevI
             continue;
         }
         SeedRec* raw = P.raw + base; ChainTmp* ct = P.ctmp + base; uint32_t* ord = P.ord + base;
-        // ---- SA lookups, all lanes (one HBM read each)
+        // ---- SA lookups (one HBM read each).  The occurrences of up to 32 intervals are flattened over the lanes: lane i
+        // holds interval i's (x0, step, count, query span), a warp scan gives each interval its slot range, and every lane
+        // then looks up the owner of its slot -- a read's handful of mostly unique seeds is fetched in one pass.
         {
             uint32_t t0 = 0;
-            for (int i = 0; i < n_iv; ++i) {
-                Intv p = iv[i];
-                uint64_t step = p.x2 > (uint64_t)o.max_occ ? p.x2 / (uint64_t)o.max_occ : 1;
-                uint64_t cnt = (p.x2 + step - 1) / step;
-                if (cnt > (uint64_t)o.max_occ) cnt = (uint64_t)o.max_occ;
-                int qbeg = (int)(p.info >> 32), slen = (int)((uint32_t)p.info - (uint32_t)(p.info >> 32));
-                for (uint64_t c = lane; c < cnt; c += 32) {
-                    int64_t rbeg = (int64_t)sa_at(ix, p.x0 + c * step);
-                    SeedRec s; s.rbeg = rbeg; s.qbeg = qbeg; s.len = slen; s.next = -1;
-                    s.score = bns_intv2rid(ix, rbeg, rbeg + slen);   // rid parked in `score` until chaining
-                    raw[t0 + c] = s;
+            for (int i0 = 0; i0 < n_iv; i0 += 32) {
+                const int i = i0 + lane;
+                uint64_t x0 = 0, step = 1; uint32_t cnt = 0, info_lo = 0, info_hi = 0;
+                if (i < n_iv) {
+                    const Intv p = iv[i];
+                    x0 = p.x0; info_lo = (uint32_t)p.info; info_hi = (uint32_t)(p.info >> 32);
+                    uint64_t c64 = p.x2;
+                    if (p.x2 > (uint64_t)o.max_occ) {
+                        step = p.x2 / (uint64_t)o.max_occ;
+                        c64 = (p.x2 + step - 1) / step;
+                        if (c64 > (uint64_t)o.max_occ) c64 = (uint64_t)o.max_occ;
+                    }
+                    cnt = (uint32_t)c64;
                 }
-                t0 += (uint32_t)cnt;
-                n_sa += cnt;
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+                const uint32_t chunk_total = __shfl_sync(FULL, incl, 31);
+                for (uint32_t tb = 0; tb < chunk_total; tb += 32) {
+                    const uint32_t t = tb + (uint32_t)lane;
+                    // owner = number of intervals whose range ends at or before t (binary search over the inclusive sums)
+                    int own = 0;
+#pragma unroll
+                    for (int b = 16; b > 0; b >>= 1) { const uint32_t v = __shfl_sync(FULL, incl, own + b - 1); if (v <= t) own += b; }
+                    const uint32_t o_incl = __shfl_sync(FULL, incl, own), o_cnt = __shfl_sync(FULL, cnt, own);
+                    const uint64_t o_x0 = __shfl_sync(FULL, x0, own), o_step = __shfl_sync(FULL, step, own);
+                    const uint32_t o_lo = __shfl_sync(FULL, info_lo, own), o_hi = __shfl_sync(FULL, info_hi, own);
+                    if (t < chunk_total) {
+                        const uint32_t c = t - (o_incl - o_cnt);
+                        const int64_t rbeg = (int64_t)sa_at(ix, o_x0 + (uint64_t)c * o_step);
+                        SeedRec sd; sd.rbeg = rbeg; sd.qbeg = (int)o_hi; sd.len = (int)(o_lo - o_hi); sd.next = -1;
+                        sd.score = bns_intv2rid(ix, rbeg, rbeg + sd.len);   // rid parked in `score` until chaining
+                        raw[t0 + t] = sd;
+                    }
+                }
+                t0 += chunk_total;
+                n_sa += chunk_total;
             }
         }
         __syncwarp();

@@ -66,9 +66,12 @@ __device__ __forceinline__ int bns_pos2rid(const DevIndex& ix, int64_t pos_f) {
 __device__ __forceinline__ int bns_intv2rid(const DevIndex& ix, int64_t rb, int64_t re) {
     int is_rev;
     if (rb < ix.l_pac && re > ix.l_pac) return -2;
-    int rid_b = bns_pos2rid(ix, bns_depos(ix, rb, &is_rev));
-    int rid_e = rb < re ? bns_pos2rid(ix, bns_depos(ix, re - 1, &is_rev)) : rid_b;
-    return rid_b == rid_e ? rid_b : -1;
+    const int rid_b = bns_pos2rid(ix, bns_depos(ix, rb, &is_rev));
+    if (rb >= re) return rid_b;
+    // the other end lies in the same sequence iff it is inside rid_b's [offset, next offset): no second search
+    const int64_t pe = bns_depos(ix, re - 1, &is_rev);
+    const bool same = pe >= ix.ann_offset[rid_b] && (rid_b == ix.n_anns - 1 || pe < ix.ann_offset[rid_b + 1]);
+    return same ? rid_b : -1;
 }
 __device__ __forceinline__ uint64_t sa_at(const DevIndex& ix, uint64_t k) {
     return ix.sa_bytes == 4 ? (uint64_t)((const uint32_t*)ix.sa)[k] : ((const uint64_t*)ix.sa)[k];

@@ -21,8 +21,8 @@ __global__ void __launch_bounds__(128) k_dbg_extend(DevOpts o, uint32_t n_jobs, 
     for (;;) {
         uint32_t j = next_ticket(ticket);
         if (j >= n_jobs) break;
-        ExtOut e = ksw_extend_warp(o, (int)(q_off[j + 1] - q_off[j]), q + q_off[j], 1, (int)(t_off[j + 1] - t_off[j]), t + t_off[j], 1,
-                                   w[j], end_bonus[j], h0[j], ehh, ehe, smat, cells, rows);
+        ExtOut e = ksw_extend_warp_t<false>(o, (int)(q_off[j + 1] - q_off[j]), q + q_off[j], 1, (int)(t_off[j + 1] - t_off[j]), t + t_off[j], 1,
+                                          w[j], end_bonus[j], h0[j], ehh, smat, cells, rows);
         if (lane_id() == 0) {
             int* d = out + (size_t)j * 6;
             d[0] = e.score; d[1] = e.qle; d[2] = e.tle; d[3] = e.gtle; d[4] = e.gscore; d[5] = e.max_off;

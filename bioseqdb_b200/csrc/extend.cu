@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(EXT_THREADS, SMEM ? 8 : 4) sw_extend(ExtendPar
                     for (i = 0; i < MAX_BAND_TRY; ++i) {
                         int prev = a.score;
                         aw0 = o.w << i;
-                        e = ksw_extend_warp(o, s.qbeg, query + s.qbeg - 1, -1, tl, S.rseq + tmp - 1, -1, aw0, o.pen_clip5, s.len * o.a,
-                                            S.ehh, S.ehe, smat, cells, rows);
+                        e = ksw_extend_warp_t<SMEM>(o, s.qbeg, query + s.qbeg - 1, -1, tl, S.rseq + tmp - 1, -1, aw0, o.pen_clip5, s.len * o.a,
+                                                  S.ehh, smat, cells, rows);
                         ++calls;
                         a.score = e.score;
                         if (a.score == prev || e.max_off < (aw0 >> 1) + (aw0 >> 2)) break;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(EXT_THREADS, SMEM ? 8 : 4) sw_extend(ExtendPar
                     for (i = 0; i < MAX_BAND_TRY; ++i) {
                         int prev = a.score;
                         aw1 = o.w << i;
-                        e = ksw_extend_warp(o, l_query - qe, query + qe, 1, tl, S.rseq + re, 1, aw1, o.pen_clip3, sc0, S.ehh, S.ehe, smat, cells, rows);
+                        e = ksw_extend_warp_t<SMEM>(o, l_query - qe, query + qe, 1, tl, S.rseq + re, 1, aw1, o.pen_clip3, sc0, S.ehh, smat, cells, rows);
                         ++calls;
                         a.score = e.score;
                         if (a.score == prev || e.max_off < (aw1 >> 1) + (aw1 >> 2)) break;

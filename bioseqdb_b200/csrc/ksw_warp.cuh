@@ -13,18 +13,37 @@
 
 struct ExtOut { int score, qle, tle, gtle, gscore, max_off; };
 
-// ksw_extend2.  q[j*qs], t[i*ts]; ehh/ehe: qlen+1 ints each (warp-private scratch); smat: 25 ints.
-static __device__ __noinline__ ExtOut ksw_extend_warp(const DevOpts& o, int qlen, const uint8_t* q, int qs, int tlen, const uint8_t* t, int ts,
-                                               int w, int end_bonus, int h0, int* ehh, int* ehe, const int* smat,
-                                               unsigned long long& cells, unsigned long long& rows) {
-    const int lane = lane_id();
+// ---- address-space helpers: the row sweeps run on warp-private scratch that lives either in shared memory (short reads)
+// or in global memory (long reads).  With SH the 32-bit shared-window address is used directly (ld/st.shared, 32-bit
+// address arithmetic); otherwise plain generic pointers.
+__device__ __forceinline__ int2 sp_ld2(uint32_t a) { int2 v; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ int2 sp_ld2(const uint8_t* a) { return *reinterpret_cast<const int2*>(a); }
+__device__ __forceinline__ void sp_st2(uint32_t a, int x, int y) { asm volatile("st.shared.v2.s32 [%0], {%1, %2};" :: "r"(a), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ void sp_st2(const uint8_t* a, int x, int y) { *reinterpret_cast<int2*>(const_cast<uint8_t*>(a)) = make_int2(x, y); }
+__device__ __forceinline__ int sp_ldb(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return (int)v; }
+__device__ __forceinline__ int sp_ldb(const uint8_t* a) { return (int)*a; }
+template <bool SH> struct SpBase;
+template <> struct SpBase<true> { typedef uint32_t type; static __device__ __forceinline__ type of(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); } };
+template <> struct SpBase<false> { typedef const uint8_t* type; static __device__ __forceinline__ type of(const void* p) { return reinterpret_cast<const uint8_t*>(p); } };
+
+// ksw_extend2.  q[j*qs], t[i*ts]; ehh: 2 (qlen + 1) ints of warp-private scratch, used as one {h, e} pair per column
+// (both callers carve ehe right behind ehh); smat: 25 ints.  SH: q, t and ehh are in shared memory.
+template <bool SH>
+static __device__ __noinline__ ExtOut ksw_extend_warp_t(const DevOpts& o, int qlen, const uint8_t* q, int qs, int tlen, const uint8_t* t, int ts,
+                                                 int w, int end_bonus, int h0, int* ehh, const int* smat,
+                                                 unsigned long long& cells, unsigned long long& rows) {
+    const int lane = threadIdx.x & 31;
     const int o_del = o.o_del, e_del = o.e_del, o_ins = o.o_ins, e_ins = o.e_ins;
     const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    const typename SpBase<SH>::type eh = SpBase<SH>::of(ehh), qa = SpBase<SH>::of(q), ta = SpBase<SH>::of(t);
+    // bwa_fill_scmat matrices have three distinct values (match, mismatch, ambiguous): scores by comparison, no table walk
+    const int sA = smat[0], sB = smat[1], sN = smat[4];
+    bool simple;
+    { const int a = lane / 5, b = lane - a * 5; simple = __all_sync(FULL, lane >= 25 || smat[lane] == ((a == 4 || b == 4) ? sN : (a == b ? sA : sB))); }
     // first row (closed form of the scalar fill loop): eh[0].h = h0, eh[j].h = max(h0 - o_ins - j e_ins, 0)
     for (int j = lane; j <= qlen; j += 32) {
         int v = j == 0 ? h0 : h0 - o_ins - j * e_ins;
-        ehh[j] = v > 0 ? v : 0;
-        ehe[j] = 0;
+        sp_st2(eh + j * 8, v > 0 ? v : 0, 0);
     }
     {
         int max_ins = (int)((double)(qlen * o.mat_max + end_bonus - o_ins) / e_ins + 1.);
@@ -36,6 +55,7 @@ static __device__ __noinline__ ExtOut ksw_extend_warp(const DevOpts& o, int qlen
     }
     int max = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;
     int beg = 0, end = qlen;
+    uint32_t ncell = 0, nrow = 0;
     __syncwarp();
     for (int i = 0; i < tlen; ++i) {
         if (beg < i - w) beg = i - w;
@@ -43,15 +63,20 @@ static __device__ __noinline__ ExtOut ksw_extend_warp(const DevOpts& o, int qlen
         if (end > qlen) end = qlen;
         int h1_init = 0;
         if (beg == 0) { h1_init = h0 - (o_del + e_del * (i + 1)); if (h1_init < 0) h1_init = 0; }
-        const int* mrow = smat + (int)t[(long)i * ts] * 5;
+        const int tb = sp_ldb(ta + i * ts);
         int carryU = (beg - 1) * e_ins, carryH = h1_init;
         int best_h = -1, best_j = -1, first_nz = -1, last_nz = -1;
-        cells += (unsigned long long)(end > beg ? end - beg : 0); ++rows;
+        ncell += (uint32_t)(end > beg ? end - beg : 0); ++nrow;
         for (int j0 = beg; j0 < end; j0 += 32) {
             const int j = j0 + lane;
             const bool act = j < end;
             int M = 0, e = 0;
-            if (act) { M = ehh[j]; e = ehe[j]; int s = mrow[q[(long)j * qs]]; M = M ? M + s : 0; }
+            if (act) {
+                const int2 v = sp_ld2(eh + j * 8);
+                const int qb = sp_ldb(qa + j * qs);
+                const int sc = simple ? ((qb | tb) > 3 ? sN : (qb == tb ? sA : sB)) : smat[tb * 5 + qb];
+                e = v.y; M = v.x ? v.x + sc : 0;
+            }
             int u = act ? __viaddmax_s32(M, -oe_ins, 0) + j * e_ins : KSW_NEG_INF;
             int inc = u;
 #pragma unroll
@@ -64,9 +89,8 @@ static __device__ __noinline__ ExtOut ksw_extend_warp(const DevOpts& o, int qlen
             if (lane == 0) hl = carryH;
             bool nz = false;
             if (act) {
-                ehh[j] = hl;
                 const int e2 = __viaddmax_s32_relu(e, -e_del, M - oe_del);
-                ehe[j] = e2;
+                sp_st2(eh + j * 8, hl, e2);
                 if (h >= best_h) { best_h = h; best_j = j; }
                 nz = (hl | e2) != 0;
             }
@@ -77,7 +101,7 @@ static __device__ __noinline__ ExtOut ksw_extend_warp(const DevOpts& o, int qlen
             carryH = __shfl_sync(FULL, h, last);
         }
         const int h1 = carryH;  // H(i, end-1), or the first-column value when the row is empty
-        if (lane == 0) { ehh[end] = h1; ehe[end] = 0; }
+        if (lane == 0) sp_st2(eh + end * 8, h1, 0);
         __syncwarp();
         const int jfin = beg < end ? end : beg;
         if (jfin == qlen) {
@@ -108,6 +132,7 @@ static __device__ __noinline__ ExtOut ksw_extend_warp(const DevOpts& o, int qlen
         beg = nbeg;
         end = jj + 2 < qlen ? jj + 2 : qlen;
     }
+    cells += ncell; rows += nrow;
     ExtOut r;
     r.score = max; r.qle = max_j + 1; r.tle = max_i + 1; r.gtle = max_ie + 1; r.gscore = gscore; r.max_off = max_off;
     return r;

@@ -279,6 +279,7 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
         const uint32_t lt = (1u << lane) - 1u;
         const bool can_uq = sizeof(IdxT) == 4 && C.isa != nullptr && min_intv == 1;
         const bool tab_ok = sizeof(IdxT) == 4 && pk != nullptr;
+        const bool fast_ok = tab_ok && !has_n && o.min_seed_len > KK;
         // unique first entry: its walk is one text comparison (uq_stop = the index i at which it dies, uq_x0 = its row then)
         bool uq = false; int uq_stop = 0; IdxT uq_x0 = 0;
         uint32_t ne = 0;
@@ -294,12 +295,44 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
                 }
             }
             if (uq && (present & (present - 1)) == 0 && i > uq_stop) { ne += (uint32_t)(i - uq_stop); i = uq_stop; }   // alone: jump
+            // Fast steps: while every entry other than a unique first one is short enough for the prefix table (and the read
+            // has no ambiguous base, and no entry that dies here can be long enough to be emitted) a step is one table read
+            // plus the two masks -- no base test, no Occ hand-off, no emission logic.
+            if (fast_ok && (uq || !can_uq)) {
+                bool done = false;
+                while (i >= 0 && !(uq && i <= uq_stop)) {
+                    const int fst = __ffs(present) - 1;
+                    const bool actf = (present >> lane) & 1u;
+                    const bool is_uqf = uq && lane == fst;
+                    const int lq = (int)p.info - i;
+                    if (__any_sync(FULL, actf && !is_uqf && lq > KK)) break;
+                    if (!uq && can_uq && __shfl_sync(FULL, p.x2, fst) == 1) break;            // a new unique first entry: general step converts it
+                    uint4 e = make_uint4((uint32_t)p.x0, (uint32_t)p.x1, 1u, 0u);
+                    if (actf && !is_uqf) {
+                        const uint32_t w = __funnelshift_l(pk[(i >> 4) + 1], pk[i >> 4], (i & 15) << 1);
+                        e = __ldg(C.kmer_tab + kmer_level_off(lq) + (w >> (32 - 2 * lq)));
+                    }
+                    const bool alivef = actf && e.z >= min_intv;
+                    const uint32_t amask = __ballot_sync(FULL, alivef);
+                    const uint32_t bef = amask & lt;
+                    const uint32_t psz = __shfl_sync(FULL, e.z, 31 - __clz(bef));
+                    const bool keepf = alivef && (bef == 0 || e.z != psz);
+                    ne += (uint32_t)__popc(present);
+                    present = __ballot_sync(FULL, keepf);
+                    if (keepf) { p.x0 = (IdxT)e.x; p.x1 = (IdxT)e.y; p.x2 = e.z; }
+                    if (!present) { done = true; break; }
+                    --i;
+                }
+                if (done) break;
+                if (uq && (present & (present - 1)) == 0 && i > uq_stop) { ne += (uint32_t)(i - uq_stop); i = uq_stop; }
+            }
+            const int first2 = __ffs(present) - 1;
             int c = -1;
             if (i >= 0) { c = q[i]; if (c > 3) c = -1; }
             const bool act = (present >> lane) & 1u;
             IdxT nx0 = p.x0, nx1 = p.x1; uint32_t sz = 0;
             if (c >= 0) {
-                const bool is_uq = uq && lane == first;
+                const bool is_uq = uq && lane == first2;
                 if (is_uq) sz = i > uq_stop ? 1u : 0u;
                 const int lq = (int)p.info - i;                      // length of the match after prepending q[i]
                 // a match of at most KK bases needs no Occ access: its bi-interval is in the prefix table
@@ -332,11 +365,11 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
             }
             const bool alive = act && sz >= min_intv;
             const uint32_t alive_mask = __ballot_sync(FULL, alive);
-            if (!((alive_mask >> first) & 1u)) {
-                const uint32_t pinfo = __shfl_sync(FULL, p.info, first);
+            if (!((alive_mask >> first2) & 1u)) {
+                const uint32_t pinfo = __shfl_sync(FULL, p.info, first2);
                 if ((int)pinfo - (i + 1) >= o.min_seed_len) {
                     if (O.n < O.cap) {
-                        if (lane == first) { Intv v; v.x0 = uq ? uq_x0 : p.x0; v.x1 = p.x1; v.x2 = p.x2; v.info = (uint64_t)(uint32_t)(i + 1) << 32 | p.info; O.out[O.n] = v; }
+                        if (lane == first2) { Intv v; v.x0 = uq ? uq_x0 : p.x0; v.x1 = p.x1; v.x2 = p.x2; v.info = (uint64_t)(uint32_t)(i + 1) << 32 | p.info; O.out[O.n] = v; }
                     } else O.ovf = true;
                     ++O.n;
                 }
@@ -449,17 +482,30 @@ __device__ __forceinline__ int seed_strategy1(const Ctx<IdxT>& C, int len, const
 template <class IdxT>
 __device__ __forceinline__ void collect_intv(const Ctx<IdxT>& C, const DevOpts& o, int len, const uint8_t* q, IvT<IdxT>* la, IvT<IdxT>* lb,
                                              uint32_t list_cap, Out& O, unsigned long long& n_ext, const uint32_t* pk, bool has_n, IvT<IdxT>* hand) {
+    // passes 1 and 2 share ONE inlined copy of smem1 (the kernel's largest function): a two-state loop feeds it
+    // first every SMEM start (pass 1), then the middle of each long, rare SMEM of pass 1 (pass 2: re-seeding)
     int x = 0;
-    while (x < len) {      // pass 1: all SMEMs
-        if (q[x] < 4) x = smem1(C, o, len, q, x, 1, la, lb, list_cap, O, n_ext, pk, has_n, hand);
-        else ++x;
-    }
-    const uint32_t old_n = O.n < O.cap ? O.n : O.cap;
-    for (uint32_t k = 0; k < old_n; ++k) {   // pass 2: re-seeding inside long, rare SMEMs
-        const Intv p = O.out[k];
-        const int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
-        if (end - start < o.split_len || p.x2 > (uint64_t)o.split_width) continue;
-        smem1(C, o, len, q, (start + end) >> 1, (uint32_t)p.x2 + 1, la, lb, list_cap, O, n_ext, pk, has_n, hand);
+    uint32_t old_n = 0, k = 0;
+    bool pass2 = false;
+    for (;;) {
+        int sx; uint32_t mi;
+        if (!pass2) {
+            while (x < len && q[x] > 3) ++x;
+            if (x >= len) { pass2 = true; old_n = O.n < O.cap ? O.n : O.cap; k = 0; continue; }
+            sx = x; mi = 1;
+        } else {
+            bool found = false;
+            for (; k < old_n; ++k) {
+                const Intv p = O.out[k];
+                const int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
+                if (end - start < o.split_len || p.x2 > (uint64_t)o.split_width) continue;
+                sx = (start + end) >> 1; mi = (uint32_t)p.x2 + 1; found = true; ++k;
+                break;
+            }
+            if (!found) break;
+        }
+        const int r = smem1(C, o, len, q, sx, mi, la, lb, list_cap, O, n_ext, pk, has_n, hand);
+        if (!pass2) x = r;
     }
     if (o.max_mem_intv > 0) {                // pass 3: LAST-like
         x = 0;

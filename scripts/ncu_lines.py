@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Rank source lines of one kernel in an .ncu-rep by executed instructions and stall samples.
-usage: ncu_lines.py report.ncu-rep [n_top]   (needs the report to be captured with --import-source on)"""
+usage: ncu_lines.py report.ncu-rep [n_top] [regions] [kernel-regex]   (report captured with --import-source on)"""
 import csv, collections, subprocess, sys, os, io
 rep = sys.argv[1]; ntop = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-txt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass'], capture_output=True, text=True).stdout
+cmd = ['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass']
+if len(sys.argv) > 4: cmd += ['--kernel-name', 'regex:' + sys.argv[4]]
+txt = subprocess.run(cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 cur = None; hdr = None; agg = collections.defaultdict(lambda: [0, 0, 0]); tot = [0, 0]
 for r in rows:
@@ -25,7 +27,7 @@ for key in (1, 0):
     print('--- by', 'instructions' if key == 1 else 'stall samples')
     for (f, ln), (s, i, l) in sorted(agg.items(), key=lambda kv: -kv[1][key])[:ntop]:
         print(f"{os.path.basename(f)}:{ln:4d} inst {i/tot[1]*100:5.2f}% samp {s/tot[0]*100:5.2f}% (long_sb {l/tot[0]*100:5.2f}%)  {line(f, ln)}")
-if len(sys.argv) > 3:   # region summary: "start:name,start:name,..." for the main .cu file
+if len(sys.argv) > 3 and sys.argv[3]:   # region summary: "start:name,start:name,..." for the main .cu file
     regs = sorted((int(a.split(':')[0]), a.split(':')[1]) for a in sys.argv[3].split(','))
     out = collections.defaultdict(lambda: [0, 0])
     for (f, ln), (s, i, l) in agg.items():

@@ -298,7 +298,7 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
             // Fast steps: while every entry other than a unique first one is short enough for the prefix table (and the read
             // has no ambiguous base, and no entry that dies here can be long enough to be emitted) a step is one table read
             // plus the two masks -- no base test, no Occ hand-off, no emission logic.
-            if (fast_ok && (uq || !can_uq)) {
+            if (fast_ok) {
                 bool done = false;
                 while (i >= 0 && !(uq && i <= uq_stop)) {
                     const int fst = __ffs(present) - 1;

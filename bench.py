@@ -115,6 +115,21 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
 
 
+def seed_traffic(args):
+    """dram__bytes_read + dram__bytes_write of one seed_smem launch from the committed ncu --set full capture of THIS workload
+    (profiles/r01_seed_traffic.json); None when the run is a different workload."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_seed_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+    except (OSError, ValueError):
+        return None
+    w = t.get("workload", {})
+    if w.get("reads") == args.reads and w.get("read_len") == args.read_len and w.get("ref_mbp") == args.ref_mbp and w.get("opts") == args.opts:
+        return t
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -301,7 +316,14 @@ def run_ours(args, rank, world, local_rank):
                 "frac": seed_bytes / seed_s / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": seed_bytes, "random_gather_peak_gbs": gather.value,
                 "frac_of_random_gather": seed_bytes / seed_s / 1e9 / max(gather.value, 1e-9),
-                "dominant_kernel_by_time": dom}
+                "dominant_kernel_by_time": dom,
+                "note": "algorithmic bytes = 2 Occ blocks x the reference's bwt_extend count (SURVEY 8d); the kernel resolves most of "
+                        "those extends from the prefix table / by text comparison, so measured DRAM traffic is below the algorithmic figure"}
+        tr = seed_traffic(args)
+        if tr is not None:
+            roof["traffic"] = tr["dram_bytes_per_launch"]
+            roof["traffic_source"] = tr["source"]
+            roof["traffic_gbs"] = tr["dram_bytes_per_launch"] / seed_s / 1e9
         ext_s = stage["extend"] / args.steps * 1e-3
         fin_s = stage["finalize"] / args.steps * 1e-3
         sw = {"ksw_extend2_gcups": ctr["ext_cells"] / ext_s / 1e9, "ksw_global2_gcups_incl_finalize": ctr["glb_cells"] / fin_s / 1e9,

@@ -67,6 +67,33 @@ static __device__ __noinline__ ExtOut ksw_extend_warp_t(const DevOpts& o, int ql
         int carryU = (beg - 1) * e_ins, carryH = h1_init;
         int best_h = -1, best_j = -1, first_nz = -1, last_nz = -1;
         ncell += (uint32_t)(end > beg ? end - beg : 0); ++nrow;
+        if (end - beg <= 32 && end > beg) {
+            // the common case: the whole row is one chunk -- same arithmetic as the loop below with its carries folded in
+            const int j = beg + lane;
+            const bool act = j < end;
+            int M = 0, e = 0;
+            if (act) {
+                const int2 v = sp_ld2(eh + j * 8);
+                const int qb = sp_ldb(qa + j * qs);
+                const int sc = simple ? ((qb | tb) > 3 ? sN : (qb == tb ? sA : sB)) : smat[tb * 5 + qb];
+                e = v.y; M = v.x ? v.x + sc : 0;
+            }
+            int inc = act ? __viaddmax_s32(M, -oe_ins, 0) + j * e_ins : KSW_NEG_INF;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int ov = __shfl_up_sync(FULL, inc, d); inc = lane >= d ? ::max(inc, ov) : inc; }
+            int ex = __shfl_up_sync(FULL, inc, 1);
+            ex = lane == 0 ? carryU : ::max(ex, carryU);
+            const int f = ex - (j - 1) * e_ins;
+            const int h = __vimax3_s32(M, e, f);
+            int hl = __shfl_up_sync(FULL, h, 1);
+            if (lane == 0) hl = h1_init;
+            const int e2 = __viaddmax_s32_relu(e, -e_del, M - oe_del);
+            if (act) sp_st2(eh + j * 8, hl, e2);
+            const unsigned bal = __ballot_sync(FULL, act && (hl | e2) != 0);
+            if (bal) { first_nz = beg + __ffs(bal) - 1; last_nz = beg + 31 - __clz(bal); }
+            carryH = __shfl_sync(FULL, h, end - beg - 1);
+            best_h = act ? h : -1; best_j = act ? j : -1;
+        } else
         for (int j0 = beg; j0 < end; j0 += 32) {
             const int j = j0 + lane;
             const bool act = j < end;

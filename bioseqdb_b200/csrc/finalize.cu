@@ -270,7 +270,7 @@ __device__ void reg2aln_warp(const FinalizeParams& P, const DevIndex& ix, const 
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(FIN_THREADS) regs_finalize(FinalizeParams P, DevIndex ix, DevOpts o, uint32_t cig_cap, uint32_t rseq_cap) {
+__global__ void __launch_bounds__(FIN_THREADS, 6) regs_finalize(FinalizeParams P, DevIndex ix, DevOpts o, uint32_t cig_cap, uint32_t rseq_cap) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ int smat[25];
     if (threadIdx.x < 25) smat[threadIdx.x] = o.mat[threadIdx.x];

@@ -84,6 +84,7 @@ def lib():
     L.bsq_align_resident.argtypes = [vp]
     L.bsq_result_download.argtypes = [vp, C.POINTER(C.POINTER(BsqResult))]
     L.bsq_index_get_meta.argtypes = [vp, C.POINTER(BsqMeta)]
+    L.bsq_index_device_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.bsq_index_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.bsq_index_download.argtypes = [vp, C.c_int, vp, u64]
     L.bsq_index_alloc_replica.argtypes = [vp, C.POINTER(BsqMeta)]
@@ -103,7 +104,7 @@ def lib():
 ABI_SYMBOLS = [
     "bsq_last_error", "bsq_device_count", "bsq_opts_init", "bsq_index_new", "bsq_index_set_opts", "bsq_index_add_ref", "bsq_index_build",
     "bsq_index_free", "bsq_align_batch", "bsq_result_free", "bsq_last_timing", "bsq_reads_upload", "bsq_align_resident", "bsq_result_download",
-    "bsq_index_get_meta", "bsq_index_device_ptr", "bsq_index_download", "bsq_index_alloc_replica", "bsq_index_bwt_plain", "bsq_index_sa_sampled",
+    "bsq_index_get_meta", "bsq_index_device_bytes", "bsq_index_device_ptr", "bsq_index_download", "bsq_index_alloc_replica", "bsq_index_bwt_plain", "bsq_index_sa_sampled",
     "bsq_debug_seed", "bsq_debug_ksw_extend", "bsq_debug_ksw_global", "bsq_bench_gather", "bsq_bench_dpx", "bsq_set_counters", "bsq_get_counters",
 ]
 

@@ -126,6 +126,11 @@ class BwaIndex:
         check(self.L.bsq_index_get_meta(self.h, C.byref(m)))
         return m
 
+    def device_bytes(self) -> int:
+        b = C.c_uint64(0)
+        check(self.L.bsq_index_device_bytes(self.h, C.byref(b)))
+        return int(b.value)
+
     def download(self, what: int) -> np.ndarray:
         m = self.meta()
         n = int(m.arr_bytes[what])

@@ -40,6 +40,7 @@ template <class T> struct DevBuf {
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    size_t bytes() const { return cap * sizeof(T); }
 };
 
 struct Batch {
@@ -54,6 +55,12 @@ struct Batch {
     DevBuf<double> read_logtab; uint32_t read_logtab_n = 0; uint32_t rseq_cap = 0;
     DevBuf<uint8_t> ext_scratch, fin_scratch, narrow_z, narrow_jobs; DevBuf<uint64_t> wide_jobs;
     DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..23] counters (u64 x 8), [24] narrow_cnt, [25] wide_cnt, [26..27] tickets
+    size_t device_bytes() const {
+        return seqs.bytes() + offs.bytes() + ids.bytes() + intv.bytes() + intv_cnt.bytes() + seed_scratch.bytes() + raw.bytes() + seeds.bytes() + ctmp.bytes() +
+               ord.bytes() + chains.bytes() + srt.bytes() + regs.bytes() + rows.bytes() + rows_compact.bytes() + reg_cnt.bytes() + row_cnt.bytes() + row_off.bytes() +
+               scan_tmp.bytes() + blocks.bytes() + cigar.bytes() + read_logtab.bytes() + ext_scratch.bytes() + fin_scratch.bytes() + narrow_z.bytes() +
+               narrow_jobs.bytes() + wide_jobs.bytes() + ctl.bytes();
+    }
     bool resident = false, aligned = false;
     // one batch = one lane of the host pipeline: its stream, the host staging that must outlive the async copies,
     // and the state of the attempt in flight (pipeline_enqueue -> pipeline_check)
@@ -220,6 +227,19 @@ void bsq_index_free(bsq_index* h) {
 int bsq_index_get_meta(const bsq_index* h, bsq_index_meta* m) {
     if (!h || !m) { bsq_set_error("null argument"); return BSQ_ERR; }
     *m = h->meta;
+    return BSQ_OK;
+}
+
+int bsq_index_device_bytes(const bsq_index* h, uint64_t* bytes) {
+    if (!h || !bytes) { bsq_set_error("null argument"); return BSQ_ERR; }
+    uint64_t b = h->batch.device_bytes() + h->batch2.device_bytes();
+    if (h->meta.built) {
+        const uint64_t n = h->meta.seq_len;
+        b += (h->meta.l_pac + 3) / 4 + ((n + 127) / 128 + 1) * 64 + (n + 1) * h->meta.sa_bytes + h->meta.n_anns * 20;
+        if (h->d_isa) b += (n + 1) * 4 + 64;
+        if (h->d_kmer) b += kmer_table_bytes(h->kmer_k);
+    }
+    *bytes = b;
     return BSQ_OK;
 }
 

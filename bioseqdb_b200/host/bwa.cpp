@@ -1,6 +1,7 @@
 // bwa.cpp -- see bwa.h.  Mirrors reference bioseqdb/bwa.cpp:55-181 with libbwa replaced by the C ABI.
 #include "bwa.h"
 #include <algorithm>
+#include <cstring>
 #include <stdexcept>
 
 namespace bioseqdb {
@@ -35,6 +36,73 @@ void BwaIndex::build() {
     if (pac_forward.empty()) return;
     if (bsq_index_set_opts(index, &options) != BSQ_OK) fail();
     if (bsq_index_build(index) != BSQ_OK) fail();
+}
+
+uint64_t BwaIndex::device_bytes() const {
+    uint64_t b = 0;
+    if (bsq_index_device_bytes(index, &b) != BSQ_OK) fail();
+    return b;
+}
+
+// ---- BwaIndexCache
+static inline uint64_t mix64(uint64_t h, uint64_t v) {          // splitmix-style accumulate
+    h ^= v + 0x9E3779B97F4A7C15ULL + (h << 6) + (h >> 2);
+    h *= 0xBF58476D1CE4E5B9ULL; h ^= h >> 31;
+    return h;
+}
+static void digest_bytes(uint64_t& a, uint64_t& b, const void* p, size_t n) {
+    const uint8_t* s = static_cast<const uint8_t*>(p);
+    for (size_t i = 0; i < n; ++i) { a = (a ^ s[i]) * 0x100000001B3ULL; }                  // FNV-1a
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t w; memcpy(&w, s + i, 8); b = mix64(b, w); }
+    uint64_t tail = 0; memcpy(&tail, s + i, n - i); b = mix64(b, tail ^ ((uint64_t)(n - i) << 56));
+}
+
+std::pair<uint64_t, uint64_t> BwaIndexCache::digest(const Rows& rows) {
+    uint64_t a = 0xCBF29CE484222325ULL, b = 0x243F6A8885A308D3ULL;
+    for (const auto& r : rows) {
+        const int64_t hdr[3] = {r.first, (int64_t)r.second->len, (int64_t)r.second->holes_num()};
+        digest_bytes(a, b, hdr, sizeof(hdr));
+        digest_bytes(a, b, r.second->pac(), pac_byte_size(r.second->len));
+        digest_bytes(a, b, r.second->holes(), (size_t)r.second->holes_num() * sizeof(bsq_hole));
+    }
+    return {a, b};
+}
+
+BwaIndexCache::BwaIndexCache(int device_, uint64_t max_bytes_) : device(device_), max_bytes(max_bytes_) {}
+
+BwaIndex& BwaIndexCache::get(const Rows& rows, const bsq_opts& opts) {
+    const auto key = digest(rows);
+    for (auto it = lru.begin(); it != lru.end(); ++it)
+        if (it->key == key) {
+            ++hits;
+            lru.splice(lru.begin(), lru, it);
+            BwaIndex& ix = *lru.front().index;
+            ix.options = opts;
+            if (ix.ref_count() && bsq_index_set_opts(ix.index, &ix.options) != BSQ_OK) fail();
+            return ix;
+        }
+    ++misses;
+    std::unique_ptr<BwaIndex> ix(new BwaIndex(device));
+    for (const auto& r : rows) ix->add_ref_sequence(r.first, *r.second);
+    ix->options = opts;
+    ix->build();
+    lru.push_front(Entry{key, std::move(ix)});
+    uint64_t total = 0;
+    for (const Entry& e : lru) total += e.index->device_bytes();
+    while (lru.size() > 1 && total > max_bytes) {
+        total -= lru.back().index->device_bytes();
+        lru.pop_back();
+        ++evictions;
+    }
+    return *lru.front().index;
+}
+
+std::vector<std::vector<BwaMatch>> BwaIndexCache::align_sequences(BwaIndex& ix, const std::vector<const NucleotideSequence*>& seqs) {
+    ix.session_lrand_state() = lrand_state;
+    auto out = ix.align_sequences(seqs);
+    lrand_state = ix.session_lrand_state();
+    return out;
 }
 
 std::string BwaIndex::extract_reference_subseq(int64_t rb, int64_t re) const {

@@ -5,7 +5,10 @@
 // turns them into ereport(ERROR).
 #pragma once
 #include <cstdint>
+#include <list>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 #include "sequence.h"
 #include "../../include/bioseqdb_gpu.h"
@@ -40,14 +43,37 @@ public:
 
     bsq_opts options;            // written by bwa_index_from_query before build()
     size_t ref_count() const { return offsets.size(); }
+    uint64_t device_bytes() const;           // bsq_index_device_bytes
+    uint64_t& session_lrand_state() { return lrand_state; }
 
 private:
+    friend class BwaIndexCache;
     std::vector<uint8_t> pac_forward;      // kept on the host for extract_reference_subseq (bwa.cpp:55-68)
     std::vector<bsq_hole> holes;           // not rebased, as in the reference (bwa.cpp:100-104)
     std::vector<int64_t> offsets;
     bsq_index* index;
     uint64_t lrand_state;                  // glibc lrand48 state: one draw per aligned read
     std::string extract_reference_subseq(int64_t ref_begin, int64_t ref_end) const;
+};
+
+// Index cache keyed by the content of the reference rows.  The reference rebuilds a BwaIndex inside
+// every SQL call (bwa_index_from_query, extension.cpp:211-236, called at :326 and :359); the cache keeps built indexes
+// resident in HBM, finds them again by a 128-bit digest of (id, length, payload, holes) of every row in cursor order,
+// applies the call's options to the cached handle, and evicts least-recently-used indexes beyond `max_bytes`.  It also
+// owns the session's lrand48 state (process-wide in the reference), lending it to the index that serves a call.
+class BwaIndexCache {
+public:
+    using Rows = std::vector<std::pair<int64_t, const NucleotideSequence*>>;
+    explicit BwaIndexCache(int device = 0, uint64_t max_bytes = 96ull << 30);
+    BwaIndex& get(const Rows& rows, const bsq_opts& opts);     // built, options applied; owned by the cache
+    // align through a cached index with the session's id stream
+    std::vector<std::vector<BwaMatch>> align_sequences(BwaIndex& ix, const std::vector<const NucleotideSequence*>& seqs);
+    uint64_t hits = 0, misses = 0, evictions = 0;
+    static std::pair<uint64_t, uint64_t> digest(const Rows& rows);
+private:
+    struct Entry { std::pair<uint64_t, uint64_t> key; std::unique_ptr<BwaIndex> index; };
+    std::list<Entry> lru;                  // front = most recently used
+    int device; uint64_t max_bytes; uint64_t lrand_state = 0;
 };
 
 std::string cigar_compressed_to_string(const uint32_t* raw, int len);   // htslib letters on bwa op codes (bwa.cpp:70-77)

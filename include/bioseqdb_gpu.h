@@ -96,6 +96,10 @@ typedef struct bsq_index_meta {
     uint64_t sort_pass_bytes; /* algorithmic bytes moved by the radix passes of the build */
 } bsq_index_meta;
 int bsq_index_get_meta(const bsq_index* h, bsq_index_meta* m);
+/* Device memory held by the index right now: pac / occ / sa / ann, the derived arrays of the seeding kernel (inverse SA,
+ * prefix table) and the batch pools.  What an index cache budgets against (the reference rebuilds its
+ * index on every call, extension.cpp:326,359; a cached handle keeps it resident instead). */
+int bsq_index_device_bytes(const bsq_index* h, uint64_t* bytes);
 int bsq_index_device_ptr(const bsq_index* h, int what, void** dptr);       /* device pointer of an index array */
 int bsq_index_download(const bsq_index* h, int what, void* host_dst, uint64_t bytes);
 int bsq_index_alloc_replica(bsq_index* h, const bsq_index_meta* m);        /* allocate arrays to receive a broadcast */

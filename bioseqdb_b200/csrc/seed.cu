@@ -509,8 +509,49 @@ __device__ __forceinline__ void collect_intv(const Ctx<IdxT>& C, const DevOpts& 
     }
     if (o.max_mem_intv > 0) {                // pass 3: LAST-like
         x = 0;
+        const int min_len = o.min_seed_len, L = min_len + 1;    // a seed of this pass is the first L-mer with < max_mem_intv occurrences
+        // The walk x -> f(x) is sequential, but f is a pure function of x and almost always returns x + L.  Lane t therefore
+        // evaluates f(x + t L) on its own -- K-mer from the prefix table, then (unique K-mer) one text comparison of the
+        // remaining L - K bases -- so the dependent loads of up to 32 starts are in flight together; the chain then consumes
+        // the results in order for as long as each start is the predicted one and was decidable without Occ.
+        const bool spec_ok = sizeof(IdxT) == 4 && C.kmer_tab != nullptr && C.isa != nullptr && pk != nullptr && !has_n &&
+                             min_len >= C.kk && o.max_mem_intv > 1 && L <= 32;
+        const int lane = lane_id();
         while (x < len) {
-            if (q[x] < 4) x = seed_strategy1(C, len, q, x, o.min_seed_len, (uint32_t)o.max_mem_intv, O, n_ext, pk, has_n);
+            if (spec_ok) {
+                if (x + L > len) { n_ext += (unsigned long long)(len - 1 - x); break; }   // too short to emit: only the extension count remains
+                const int xs = x + L * lane;
+                int state = 0;                     // 0 undecided (needs Occ) or out of range, 1 no seed, 2 seed
+                uint32_t r0 = 0, r1 = 0;
+                if (xs + L <= len) {
+                    const uint32_t w = __funnelshift_l(pk[(xs >> 4) + 1], pk[xs >> 4], (xs & 15) << 1);
+                    const uint4 e = __ldg(C.kmer_tab + kmer_level_off(C.kk) + (w >> (32 - 2 * C.kk)));
+                    if (e.z == 0) state = 1;
+                    else if (e.z == 1) {
+                        const uint32_t pos = C.sa[e.x];
+                        bool ok = pos + (uint32_t)L <= C.n;
+                        for (int k = C.kk; ok && k < L; ++k) ok = text_base(C, pos + (uint32_t)k) == (uint32_t)q[xs + k];
+                        state = ok ? 2 : 1;
+                        if (ok) { r0 = e.x; r1 = C.isa[C.n - pos - (uint32_t)L]; }
+                    }
+                }
+                const uint32_t decided = __ballot_sync(FULL, state != 0);
+                const int run = decided == 0xffffffffu ? 32 : __ffs(~decided) - 1;   // leading starts that are decided (0 => lane 0 needs the general walk)
+                if (run > 0) {
+                    const uint32_t runmask = run >= 32 ? 0xffffffffu : ((1u << run) - 1u);
+                    const uint32_t em = __ballot_sync(FULL, state == 2) & runmask;
+                    if (state == 2 && lane < run) {
+                        const uint32_t k = O.n + (uint32_t)__popc(em & ((1u << lane) - 1u));
+                        if (k < O.cap) { Intv v; v.x0 = r0; v.x1 = r1; v.x2 = 1; v.info = (uint64_t)(uint32_t)xs << 32 | (uint32_t)(xs + L); O.out[k] = v; }
+                    }
+                    if (O.n + (uint32_t)__popc(em) > O.cap) O.ovf = true;
+                    O.n += (uint32_t)__popc(em);
+                    n_ext += (unsigned long long)run * (unsigned long long)min_len;
+                    x += run * L;
+                    continue;
+                }
+            }
+            if (q[x] < 4) x = seed_strategy1(C, len, q, x, min_len, (uint32_t)o.max_mem_intv, O, n_ext, pk, has_n);
             else ++x;
         }
     }

@@ -199,3 +199,22 @@ def test_align_batch_chunked_pipeline(gpu_lib):
     oo, on = o["rows"]["cigar_off"].astype(np.int64), o["rows"]["n_cigar"].astype(np.int64)
     oc = np.concatenate([o["cigar"][int(a):int(a + b)] for a, b in zip(oo, on)]) if on.sum() else np.zeros(0, dtype=np.uint32)
     assert np.array_equal(gc, oc)
+
+
+def test_align_batch_chunked_fallback(gpu_lib, monkeypatch):
+    """When the rows outgrow the result block extrapolated from the first chunk, the call drains both lanes and runs one
+    plain pass: same rows as the resident path."""
+    from helpers import PARITY_FIELDS
+    monkeypatch.setenv("BSQ_TEST_TIGHT_RESULT", "1")
+    rows = synth.reference_rows([300_001, 200_003], seed=81)
+    _, gpu = build_pair(rows, O.sql_default_opts(2))
+    n = 2 * (1 << 16) + 4321
+    seqs, offs, _ = synth.simulate_reads(rows, n, 80, seed=82)
+    ids = synth.lrand48_ids_fast(n)
+    g = gpu.align_batch(seqs, offs, ids)
+    assert b"re-run in one pass" in gpu.L.bsq_last_error()      # the fallback really ran (the call itself succeeded)
+    gpu.upload(seqs, offs, ids); gpu.align_resident(); r = gpu.download_result()
+    assert np.array_equal(g.row_off, r.row_off)
+    for f in PARITY_FIELDS:
+        assert np.array_equal(g.rows[f], r.rows[f]), f
+    assert np.array_equal(_flat_cigars(g), _flat_cigars(r))

@@ -33,6 +33,7 @@ template <class IdxT> struct Ctx {
     const IdxT* sL2;         // shared memory: L2[0..4]
     const uint4* kmer_tab;   // prefix table (x0, x1, x2, -) of all t-mers, t <= kk; nullptr when absent
     int kk;                  // depth of the prefix table
+    int lane;                // the thread's lane, read from the special register ONCE (the compiler otherwise re-issues S2R in hot loops)
     // unique-match shortcut (32-bit rows): full SA, inverse SA and the 2-bit text; isa == nullptr disables it
     const uint32_t* sa; const uint32_t* isa; const uint8_t* pac; uint32_t l_pac, n;
     IdxT primary;
@@ -48,7 +49,7 @@ __device__ __forceinline__ IvT<IdxT> extend1(const Ctx<IdxT>& C, const IvT<IdxT>
     const IdxT xo = IS_BACK ? ik.x0 : ik.x1, xb = IS_BACK ? ik.x1 : ik.x0;
     IdxT pos = xo - 1 + (C.lhalf ? (IdxT)ik.x2 : (IdxT)0);
     pos -= (pos >= C.primary);
-    const uint32_t word = __ldg(C.occ + ((size_t)(pos >> 7) << 4) + (lane_id() & 15));
+    const uint32_t word = __ldg(C.occ + ((size_t)(pos >> 7) << 4) + (C.lane & 15));
     // symbol lanes: count symbols == c and > c among the first nsym symbols of the word (branch-free)
     int nsym = (int)(pos & 127) + 1 - (int)C.sym_base;
     nsym = nsym < 0 ? 0 : (nsym > 16 ? 16 : nsym);
@@ -84,7 +85,7 @@ __device__ __forceinline__ IvT<IdxT> extend1(const Ctx<IdxT>& C, const IvT<IdxT>
 // the group.  Every lane of a group returns the group's child interval.
 template <class IdxT>
 __device__ __forceinline__ IvT<IdxT> extend4_back(const Ctx<IdxT>& C, const IvT<IdxT>& ik, int c, bool valid) {
-    const int t = lane_id() & 7;
+    const int t = C.lane & 7;
     const bool lside = (t & 4) != 0;
     const IdxT xo = ik.x0, xb = ik.x1;
     IdxT pos = xo - 1 + (lside ? (IdxT)ik.x2 : (IdxT)0);
@@ -141,7 +142,7 @@ template <class IdxT> __device__ __forceinline__ uint32_t text_base(const Ctx<Id
 }
 // number of consecutive k in [0, maxlen) with q[qpos + k] an ACGT base equal to T[tpos + k]
 template <class IdxT> __device__ __forceinline__ int match_run_fwd(const Ctx<IdxT>& C, uint32_t tpos, const uint8_t* q, int qpos, int maxlen) {
-    const int lane = lane_id();
+    const int lane = C.lane;
     for (int base = 0; base < maxlen; base += 32) {
         const int k = base + lane;
         bool ok = k < maxlen;
@@ -153,7 +154,7 @@ template <class IdxT> __device__ __forceinline__ int match_run_fwd(const Ctx<Idx
 }
 // backwards: number of consecutive k in [0, maxlen) with q[qpos - k] == T[tpos - 1 - k]
 template <class IdxT> __device__ __forceinline__ int match_run_bwd(const Ctx<IdxT>& C, uint32_t tpos, const uint8_t* q, int qpos, int maxlen) {
-    const int lane = lane_id();
+    const int lane = C.lane;
     for (int base = 0; base < maxlen; base += 32) {
         const int k = base + lane;
         bool ok = k < maxlen;
@@ -180,11 +181,11 @@ template <class IdxT> __device__ __forceinline__ IvT<IdxT> set_intv(const Ctx<Id
     return ik;
 }
 
-struct Out { Intv* out; uint32_t n, cap; bool ovf; };
+struct Out { Intv* out; uint32_t n, cap; bool ovf; int lane; };
 
 template <class IdxT> __device__ __forceinline__ void emit(Out& O, const IvT<IdxT>& p, uint32_t start, uint32_t end) {
     if (O.n < O.cap) {
-        if (lane_id() == 0) { Intv v; v.x0 = p.x0; v.x1 = p.x1; v.x2 = p.x2; v.info = (uint64_t)start << 32 | end; O.out[O.n] = v; }
+        if (O.lane == 0) { Intv v; v.x0 = p.x0; v.x1 = p.x1; v.x2 = p.x2; v.info = (uint64_t)start << 32 | end; O.out[O.n] = v; }
     } else O.ovf = true;
     ++O.n;
 }
@@ -196,7 +197,7 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
     if (q[x] > 3) return x + 1;
     if (min_intv < 1) min_intv = 1;
     const int KK = C.kk;
-    const int lane = lane_id();
+    const int lane = C.lane;
     IvT<IdxT> ik = set_intv(C, q[x]);
     ik.info = (uint32_t)(x + 1);
     IvT<IdxT>* curr = la; IvT<IdxT>* prev = lb;
@@ -449,7 +450,7 @@ __device__ __forceinline__ int seed_strategy1(const Ctx<IdxT>& C, int len, const
             // (nothing emitted), or at the end of the read
             const int stop = x + min_len;                       // index of the base whose extension triggers the emission test
             const int lim = (stop < len ? stop + 1 : len) - i;  // bases q[i .. i + lim) are looked at
-            const int lane = lane_id();
+            const int lane = C.lane;
             bool isn = false;
             if (lane < lim) isn = q[i + lane] > 3;              // lim <= min_len + 1 - (i - x) <= 32 for min_seed_len <= 31
             const uint32_t nmask = __ballot_sync(FULL, isn);
@@ -516,7 +517,7 @@ __device__ __forceinline__ void collect_intv(const Ctx<IdxT>& C, const DevOpts& 
         // the results in order for as long as each start is the predicted one and was decidable without Occ.
         const bool spec_ok = sizeof(IdxT) == 4 && C.kmer_tab != nullptr && C.isa != nullptr && pk != nullptr && !has_n &&
                              min_len >= C.kk && o.max_mem_intv > 1 && L <= 32;
-        const int lane = lane_id();
+        const int lane = C.lane;
         while (x < len) {
             if (spec_ok) {
                 if (x + L > len) { n_ext += (unsigned long long)(len - 1 - x); break; }   // too short to emit: only the extension count remains
@@ -649,16 +650,23 @@ __global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 4 
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ IdxT sL2[8];
     __shared__ IvT<IdxT> s_hand[SEED_WARPS][4];   // hand-off slots of the grouped backward extensions
-    IvT<IdxT>* hand = s_hand[threadIdx.x >> 5];
-    if (threadIdx.x < 5) sL2[threadIdx.x] = (IdxT)ix.L2[threadIdx.x];
+    // lane / warp index: read the special register once and make the values opaque, otherwise the compiler re-issues S2R
+    // (a long-scoreboard instruction) wherever they are used inside the hot loops
+    int tid = threadIdx.x;
+    asm volatile("" : "+r"(tid));
+    const int warp_in_cta = tid >> 5;
+    IvT<IdxT>* hand = s_hand[warp_in_cta];
+    const IdxT* sL2p = sL2;
+    asm volatile("" : "+l"(hand), "+l"(sL2p));      // formed once: re-deriving a generic address of shared memory costs an S2UR each time
+    if (tid < 5) sL2[tid] = (IdxT)ix.L2[tid];
     __syncthreads();
     using Iv = IvT<IdxT>;
-    const int lane = lane_id();
-    const uint32_t gwarp = (blockIdx.x * SEED_THREADS + threadIdx.x) >> 5;
+    const int lane = tid & 31;
+    const uint32_t gwarp = (blockIdx.x * SEED_THREADS + (uint32_t)tid) >> 5;
     Intv* gl = P.scratch + (size_t)gwarp * 3 * P.list_cap;     // global scratch: lists of long reads, big-sort buffer
     unsigned long long n_ext = 0;
     Ctx<IdxT> C;
-    C.occ = ix.occ; C.sL2 = sL2; C.primary = (IdxT)ix.primary; C.kmer_tab = P.kmer_tab; C.kk = P.kmer_k;
+    C.occ = ix.occ; C.sL2 = sL2p; C.primary = (IdxT)ix.primary; C.kmer_tab = P.kmer_tab; C.kk = P.kmer_k; C.lane = lane;
     C.sa = reinterpret_cast<const uint32_t*>(ix.sa); C.isa = sizeof(IdxT) == 4 ? P.isa : nullptr; C.pac = ix.pac; C.l_pac = (uint32_t)ix.l_pac; C.n = (uint32_t)ix.seq_len;
     {
         const int idx = lane & 15;
@@ -670,15 +678,15 @@ __global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 4 
     }
     Iv* la; Iv* lb; uint8_t* sq = nullptr;
     if (SMEM) {
-        la = reinterpret_cast<Iv*>(dyn_smem) + (size_t)(threadIdx.x >> 5) * 2 * P.list_cap; lb = la + P.list_cap;
-        sq = dyn_smem + (size_t)SEED_WARPS * 2 * P.list_cap * sizeof(Iv) + (size_t)(threadIdx.x >> 5) * P.read_cap;
+        la = reinterpret_cast<Iv*>(dyn_smem) + (size_t)warp_in_cta * 2 * P.list_cap; lb = la + P.list_cap;
+        sq = dyn_smem + (size_t)SEED_WARPS * 2 * P.list_cap * sizeof(Iv) + (size_t)warp_in_cta * P.read_cap;
     } else { la = reinterpret_cast<Iv*>(gl); lb = la + P.list_cap; }
     for (;;) {
         uint32_t r = next_ticket(P.ticket);
         if (r >= P.n_reads) break;
         const uint8_t* q = P.seqs + P.offs[r];
         const int len = (int)(P.offs[r + 1] - P.offs[r]);
-        Out O; O.out = P.out + (size_t)r * P.cap; O.n = 0; O.cap = P.cap; O.ovf = false;
+        Out O; O.out = P.out + (size_t)r * P.cap; O.n = 0; O.cap = P.cap; O.ovf = false; O.lane = lane;
         if (len >= o.min_seed_len) {   // mem_chain returns before seeding otherwise
             if (SMEM) {
                 __syncwarp();

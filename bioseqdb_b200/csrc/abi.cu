@@ -77,7 +77,8 @@ struct Batch {
         if (evx_ok) { for (auto& e : ev_x) cudaEventDestroy(e); evx_ok = false; }
         seqs.release(); offs.release(); ids.release(); intv.release(); intv_cnt.release(); seed_scratch.release(); raw.release(); seeds.release();
         ctmp.release(); ord.release(); chains.release(); srt.release(); regs.release(); rows.release(); rows_compact.release(); reg_cnt.release();
-        row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release(); ctl.release(); narrow_z.release(); narrow_jobs.release(); wide_jobs.release(); read_logtab.release();
+        row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release();
+        ctl.release(); narrow_z.release(); narrow_jobs.release(); wide_jobs.release(); read_logtab.release();
     }
 };
 
@@ -435,6 +436,19 @@ int ensure_kmer_table(bsq_index* h, const DevIndex& ix) {
     return BSQ_OK;
 }
 
+// the seeding kernel's view of a batch: inputs, per-read interval slots, the index's derived arrays, control words
+SeedParams seed_params(const bsq_index* h, const Batch& b, const DevIndex& ix, uint32_t n, uint32_t cap, uint32_t* ticket, unsigned long long* n_extend) {
+    SeedParams P;
+    P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = cap;
+    P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.kmer_k = h->kmer_k; P.isa = h->d_isa;
+    P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap;
+    // shared-memory bytes per warp for the read: the bases (padded to 16) and their 2-bit packed copy
+    P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u;
+    P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes);
+    P.ticket = ticket; P.overflow = b.ctl.p + 4; P.n_extend = n_extend;
+    return P;
+}
+
 // One attempt of the kernel pipeline on the batch's stream: size the pools, launch every stage, read the control
 // words back asynchronously.  Nothing here waits for the device.
 int pipeline_enqueue(bsq_index* h, Batch& b) {
@@ -485,9 +499,7 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
     unsigned long long* ctr = h->collect_counters ? reinterpret_cast<unsigned long long*>(b.ctl.p + 8) : nullptr;
     cudaEventRecord(ev[0], st);
     {
-        SeedParams P;
-        P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = b.intv_cap;
-        P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.kmer_k = h->kmer_k; P.isa = h->d_isa; P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p + 0; P.overflow = b.ctl.p + 4; P.n_extend = ctr ? ctr + 0 : nullptr;
+        const SeedParams P = seed_params(h, b, ix, n, b.intv_cap, b.ctl.p + 0, ctr ? ctr + 0 : nullptr);
         launch_seed(P, ix, o, st, nullptr); ++T.launches;
     }
     cudaEventRecord(ev[1], st);
@@ -513,7 +525,8 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
         P.seqs = b.seqs.p; P.offs = b.offs.p; P.ids = b.ids.p; P.n_reads = n; P.blocks = b.blocks.p; P.regs = b.regs.p; P.reg_cnt = b.reg_cnt.p;
         P.rows = b.rows.p; P.row_cnt = b.row_cnt.p; P.cigar_pool = b.cigar.p; P.cigar_cap = b.cigar_cap; P.cigar_top = b.ctl.p + 6;
         P.scratch = b.fin_scratch.p; P.scratch_per_warp = fin_per_warp; P.max_len = max_len; P.z_cap = z_cap; P.ann_id = h->d_ann_id;
-        P.narrow_jobs = b.narrow_jobs.p; P.narrow_cap = b.pool_cap; P.narrow_cnt = b.ctl.p + 32; P.wide_jobs = b.wide_jobs.p; P.wide_cnt = b.ctl.p + 25; P.narrow_z = b.narrow_z.p; P.narrow_warps = narrow_warps;
+        P.narrow_jobs = b.narrow_jobs.p; P.narrow_cap = b.pool_cap; P.narrow_cnt = b.ctl.p + 32; P.wide_jobs = b.wide_jobs.p; P.wide_cnt = b.ctl.p + 25;
+        P.narrow_z = b.narrow_z.p; P.narrow_warps = narrow_warps;
         P.ticket = b.ctl.p + 40; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 6 : nullptr;
         launch_finalize(P, ix, o, st, rseq_cap, fin_warps, &T.launches);
     }
@@ -844,7 +857,10 @@ int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const 
         memset(h->counters, 0, sizeof(h->counters));
         bool fell_back = false;
         rc = align_chunked(h, seqs, offs, ids, n, out, &fell_back);
-        if (fell_back) { bsq_set_error("note: result outgrew the chunk pipeline's estimate; batch re-run in one pass"); chunked = false; T.h2d_bytes = T.d2h_bytes = 0; T.h2d = T.d2h = 0; }   // the result outgrew the estimate: one plain pass
+        if (fell_back) {   // the result outgrew the estimate: one plain pass (the note is visible through bsq_last_error; the call succeeds)
+            bsq_set_error("note: result outgrew the chunk pipeline's estimate; batch re-run in one pass");
+            chunked = false; T.h2d_bytes = T.d2h_bytes = 0; T.h2d = T.d2h = 0;
+        }
         else { cudaEventRecord(e3, h->stream); cudaEventSynchronize(e3); cudaEventElapsedTime(&T.total, e0, e3); }
     }
     if (!chunked) {
@@ -891,9 +907,7 @@ int bsq_debug_seed(bsq_index* h, const char* seqs, const uint64_t* offs, uint64_
     CUDA_CHECK(b.intv.ensure((size_t)n * cap)); CUDA_CHECK(b.intv_cnt.ensure(n)); CUDA_CHECK(b.seed_scratch.ensure((size_t)seed_warps * 3 * b.list_cap));
     CUDA_CHECK(b.ctl.ensure(64));
     CUDA_CHECK(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, h->stream));
-    SeedParams P;
-    P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = (uint32_t)n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = cap;
-    P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.kmer_k = h->kmer_k; P.isa = h->d_isa; P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap; P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u; P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes); P.ticket = b.ctl.p; P.overflow = b.ctl.p + 4; P.n_extend = reinterpret_cast<unsigned long long*>(b.ctl.p + 8);
+    const SeedParams P = seed_params(h, b, ix, (uint32_t)n, cap, b.ctl.p, reinterpret_cast<unsigned long long*>(b.ctl.p + 8));
     launch_seed(P, ix, h->dopts, h->stream, nullptr);
     uint32_t ctl[8];
     CUDA_CHECK(cudaMemcpyAsync(ctl, b.ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));

@@ -599,7 +599,10 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE == 1 ? 4 : 1) regs_cigar_
                             sc += smat[tb * 5 + qat(i)];
                         }
                         if (diagonal || sc > (lq - 1) * o.mat_max - oe_ins - oe_del) { score = sc; cg[0] = (uint32_t)lq << 4; n_cigar = 1; diagonal = true; }
-                        else { push_narrow(P.requeue, P.requeue_cap, P.requeue_cnt, P.requeue_big_cnt, jb, narrow_is_big(o, lq, rlen, jb.w2, simple_mat)); again = true; break; }   // needs the DP: over to the DP list, same try
+                        else {   // needs the DP: over to the DP list, same try
+                            push_narrow(P.requeue, P.requeue_cap, P.requeue_cnt, P.requeue_big_cnt, jb, narrow_is_big(o, lq, rlen, jb.w2, simple_mat));
+                            again = true; break;
+                        }
                     } else if (diagonal) {
                         int sc = 0;
                         for (int i = 0; i < lq; ++i) {

@@ -92,6 +92,7 @@ def lib():
     L.bsq_index_sa_sampled.argtypes = [vp, vp, u64]
     L.bsq_debug_seed.argtypes = [vp, vp, vp, u64, vp, u32, vp]
     L.bsq_debug_ksw_extend.argtypes = [C.POINTER(BsqOpts), C.c_int, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.bsq_debug_ksw_extend_thread.argtypes = [C.POINTER(BsqOpts), C.c_int, u64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
     L.bsq_debug_ksw_global.argtypes = [C.POINTER(BsqOpts), C.c_int, u64, vp, vp, vp, vp, vp, vp, vp, u32, vp]
     L.bsq_bench_gather.argtypes = [vp, u64, C.c_int, C.POINTER(C.c_double)]
     L.bsq_bench_dpx.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
@@ -105,7 +106,7 @@ ABI_SYMBOLS = [
     "bsq_last_error", "bsq_device_count", "bsq_opts_init", "bsq_index_new", "bsq_index_set_opts", "bsq_index_add_ref", "bsq_index_build",
     "bsq_index_free", "bsq_align_batch", "bsq_result_free", "bsq_last_timing", "bsq_reads_upload", "bsq_align_resident", "bsq_result_download",
     "bsq_index_get_meta", "bsq_index_device_bytes", "bsq_index_device_ptr", "bsq_index_download", "bsq_index_alloc_replica", "bsq_index_bwt_plain", "bsq_index_sa_sampled",
-    "bsq_debug_seed", "bsq_debug_ksw_extend", "bsq_debug_ksw_global", "bsq_bench_gather", "bsq_bench_dpx", "bsq_set_counters", "bsq_get_counters",
+    "bsq_debug_seed", "bsq_debug_ksw_extend", "bsq_debug_ksw_extend_thread", "bsq_debug_ksw_global", "bsq_bench_gather", "bsq_bench_dpx", "bsq_set_counters", "bsq_get_counters",
 ]
 
 

@@ -54,12 +54,13 @@ struct Batch {
     DevBuf<uint32_t> cigar; uint32_t cigar_cap = 0;
     DevBuf<double> read_logtab; uint32_t read_logtab_n = 0; uint32_t rseq_cap = 0;
     DevBuf<uint8_t> ext_scratch, fin_scratch, narrow_z, narrow_jobs; DevBuf<uint64_t> wide_jobs;
+    DevBuf<ExtMemo> ext_memo; DevBuf<uint8_t> ext_memo_key; DevBuf<uint32_t> ext_memo_perm, ext_memo_hist;   // thread-per-extension pre-pass (extend_plan.cu)
     DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..23] counters (u64 x 8), [24] narrow_cnt, [25] wide_cnt, [26..27] tickets
     size_t device_bytes() const {
         return seqs.bytes() + offs.bytes() + ids.bytes() + intv.bytes() + intv_cnt.bytes() + seed_scratch.bytes() + raw.bytes() + seeds.bytes() + ctmp.bytes() +
                ord.bytes() + chains.bytes() + srt.bytes() + regs.bytes() + rows.bytes() + rows_compact.bytes() + reg_cnt.bytes() + row_cnt.bytes() + row_off.bytes() +
                scan_tmp.bytes() + blocks.bytes() + cigar.bytes() + read_logtab.bytes() + ext_scratch.bytes() + fin_scratch.bytes() + narrow_z.bytes() +
-               narrow_jobs.bytes() + wide_jobs.bytes() + ctl.bytes();
+               narrow_jobs.bytes() + wide_jobs.bytes() + ctl.bytes() + ext_memo.bytes() + ext_memo_key.bytes() + ext_memo_perm.bytes() + ext_memo_hist.bytes();
     }
     bool resident = false, aligned = false;
     // one batch = one lane of the host pipeline: its stream, the host staging that must outlive the async copies,
@@ -79,6 +80,7 @@ struct Batch {
         ctmp.release(); ord.release(); chains.release(); srt.release(); regs.release(); rows.release(); rows_compact.release(); reg_cnt.release();
         row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release();
         ctl.release(); narrow_z.release(); narrow_jobs.release(); wide_jobs.release(); read_logtab.release();
+        ext_memo.release(); ext_memo_key.release(); ext_memo_perm.release(); ext_memo_hist.release();
     }
 };
 
@@ -495,6 +497,13 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
     const size_t narrow_bytes = narrow_zbuf_bytes(&narrow_warps);
     ENS(b.narrow_z.ensure(narrow_bytes)); ENS(b.narrow_jobs.ensure((size_t)b.pool_cap * 3 * 24)); ENS(b.wide_jobs.ensure(b.pool_cap));
     ENS(b.ctl.ensure(64));
+    // the thread-per-extension pre-pass packs column scores in 16 bits: every value it stores is <= l_query * (a + 1)
+    static const bool no_memo = getenv("BSQ_NO_EXT_MEMO") != nullptr;
+    const bool use_memo = !no_memo && max_len <= 512 && (uint64_t)max_len * (uint64_t)(o.a + 1) < 32000;
+    if (use_memo) {
+        ENS(b.ext_memo.ensure((size_t)n * 2)); ENS(b.ext_memo_key.ensure((size_t)n * 2)); ENS(b.ext_memo_perm.ensure((size_t)n * 2));
+        ENS(b.ext_memo_hist.ensure(6 * EXT_MEMO_BINS));
+    }
     ENS(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, st));
     unsigned long long* ctr = h->collect_counters ? reinterpret_cast<unsigned long long*>(b.ctl.p + 8) : nullptr;
     cudaEventRecord(ev[0], st);
@@ -517,6 +526,8 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
         P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.blocks = b.blocks.p; P.chains = b.chains.p; P.seeds = b.seeds.p; P.srt = b.srt.p;
         P.regs = b.regs.p; P.reg_cnt = b.reg_cnt.p; P.scratch = b.ext_scratch.p; P.scratch_per_warp = ext_per_warp; P.max_len = max_len; P.rseq_cap = rseq_cap;
         P.ticket = b.ctl.p + 2; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 3 : nullptr;
+        P.memo = use_memo ? b.ext_memo.p : nullptr; P.memo_key = b.ext_memo_key.p; P.memo_perm = b.ext_memo_perm.p; P.memo_hist = b.ext_memo_hist.p;
+        launch_extend_memo(P, ix, o, st, &T.launches);
         launch_extend(P, ix, o, st); ++T.launches;
     }
     cudaEventRecord(ev[3], st);
@@ -926,8 +937,24 @@ static int dbg_common(const bsq_opts* o, int device, bsq_index** tmp) {
     return *tmp ? BSQ_OK : BSQ_ERR;
 }
 
+static int dbg_ksw_extend(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
+                          const uint64_t* t_off, const int32_t* w, const int32_t* end_bonus, const int32_t* h0, int32_t* out, int mode);
+
 int bsq_debug_ksw_extend(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
                          const uint64_t* t_off, const int32_t* w, const int32_t* end_bonus, const int32_t* h0, int32_t* out) {
+    return dbg_ksw_extend(o, device, n_jobs, q, q_off, t, t_off, w, end_bonus, h0, out, 0);
+}
+
+int bsq_debug_ksw_extend_thread(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
+                                const uint64_t* t_off, const int32_t* w, const int32_t* end_bonus, const int32_t* h0, int32_t* out, int reversed) {
+    return dbg_ksw_extend(o, device, n_jobs, q, q_off, t, t_off, w, end_bonus, h0, out, reversed ? 2 : 1);
+}
+
+}  // extern "C"
+
+// mode 0: warp-cooperative kernel; 1 / 2: thread-per-extension kernel, query stored forward / back to front
+static int dbg_ksw_extend(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
+                          const uint64_t* t_off, const int32_t* w, const int32_t* end_bonus, const int32_t* h0, int32_t* out, int mode) {
     bsq_index* h;
     if (dbg_common(o, device, &h) != BSQ_OK) return BSQ_ERR;
     int rc = BSQ_ERR;
@@ -947,7 +974,11 @@ int bsq_debug_ksw_extend(const bsq_opts* o, int device, uint64_t n_jobs, const u
         DC(cudaMemcpy(dqo, q_off, (n_jobs + 1) * 8, cudaMemcpyHostToDevice)); DC(cudaMemcpy(dto, t_off, (n_jobs + 1) * 8, cudaMemcpyHostToDevice));
         DC(cudaMemcpy(dw, w, n_jobs * 4, cudaMemcpyHostToDevice)); DC(cudaMemcpy(deb, end_bonus, n_jobs * 4, cudaMemcpyHostToDevice));
         DC(cudaMemcpy(dh0, h0, n_jobs * 4, cudaMemcpyHostToDevice));
-        launch_dbg_extend(h->dopts, (uint32_t)n_jobs, dq, dqo, dt, dto, dw, deb, dh0, dout, deh, max_q, dtk, nullptr, blocks, h->stream);
+        if (mode == 0) launch_dbg_extend(h->dopts, (uint32_t)n_jobs, dq, dqo, dt, dto, dw, deb, dh0, dout, deh, max_q, dtk, nullptr, blocks, h->stream);
+        else {
+            if (max_q > (uint32_t)EXT_MEMO_MAXQ) { bsq_set_error("debug extend (thread kernel): query longer than %d", EXT_MEMO_MAXQ); break; }
+            launch_dbg_extend_thread(h->dopts, (uint32_t)n_jobs, dq, dqo, dt, dto, dw, deb, dh0, dout, mode == 2, h->stream);
+        }
         DC(cudaStreamSynchronize(h->stream)); DC(cudaGetLastError());
         DC(cudaMemcpy(out, dout, n_jobs * 24, cudaMemcpyDeviceToHost));
         rc = BSQ_OK;
@@ -956,6 +987,8 @@ int bsq_debug_ksw_extend(const bsq_opts* o, int device, uint64_t n_jobs, const u
     bsq_index_free(h);
     return rc;
 }
+
+extern "C" {
 
 int bsq_debug_ksw_global(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
                          const uint64_t* t_off, const int32_t* w, int32_t* out_score, uint32_t* cigar, uint32_t cig_cap, int32_t* n_cigar) {

@@ -4,6 +4,7 @@
 // microbenchmark that gives the SW roofline denominator.
 #include "pipeline.cuh"
 #include "ksw_warp.cuh"
+#include "ksw_thread.cuh"
 #include "debug_kernels.cuh"
 
 namespace {
@@ -29,6 +30,27 @@ __global__ void __launch_bounds__(128) k_dbg_extend(DevOpts o, uint32_t n_jobs, 
         }
     }
     if (cells_out && lane_id() == 0) atomicAdd(cells_out, cells);
+}
+
+// the thread-per-extension kernel of the production pre-pass (ksw_thread.cuh) on an explicit job list: one job per thread
+struct ByteRows { const uint8_t* t; __device__ __forceinline__ int operator()(int i) const { return (int)t[i]; } };
+constexpr int DBG_NCOL = EXT_MEMO_MAXQ + 1;
+__global__ void __launch_bounds__(128) k_dbg_extend_thread(DevOpts o, uint32_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
+                                                           const uint64_t* t_off, const int* w, const int* end_bonus, const int* h0, int* out, int reversed) {
+    extern __shared__ uint32_t dbg_smem[];
+    uint32_t* eh = dbg_smem + threadIdx.x;
+    uint32_t* qn = dbg_smem + DBG_NCOL * 128 + threadIdx.x;
+    const uint32_t j = blockIdx.x * 128 + threadIdx.x;
+    if (j >= n_jobs) return;
+    const int qlen = (int)(q_off[j + 1] - q_off[j]);
+    // reversed: the caller stored the query back to front, the loader's left-extension path puts it in order again
+    if (reversed) ksw_thread_load_query<128>(qn, q + q_off[j] + qlen, qlen, -1);
+    else ksw_thread_load_query<128>(qn, q + q_off[j], qlen, 1);
+    ByteRows T; T.t = t + t_off[j];
+    uint32_t cells = 0, rows = 0;
+    const ExtOut e = ksw_extend_thread<128>(o, eh, qn, qlen, (int)(t_off[j + 1] - t_off[j]), T, w[j], end_bonus[j], h0[j], cells, rows);
+    int* d = out + (size_t)j * 6;
+    d[0] = e.score; d[1] = e.qle; d[2] = e.tle; d[3] = e.gtle; d[4] = e.gscore; d[5] = e.max_off;
 }
 
 __global__ void __launch_bounds__(128) k_dbg_global(DevOpts o, uint32_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
@@ -114,6 +136,12 @@ void launch_dbg_extend(const DevOpts& o, uint32_t n_jobs, const uint8_t* q, cons
                        const int* end_bonus, const int* h0, int* out, int* eh, uint32_t max_q, uint32_t* ticket, unsigned long long* cells,
                        int blocks, cudaStream_t st) {
     k_dbg_extend<<<blocks, 128, 0, st>>>(o, n_jobs, q, q_off, t, t_off, w, end_bonus, h0, out, eh, max_q, ticket, cells);
+}
+void launch_dbg_extend_thread(const DevOpts& o, uint32_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t, const uint64_t* t_off, const int* w,
+                              const int* end_bonus, const int* h0, int* out, int reversed, cudaStream_t st) {
+    const size_t smem = (size_t)(DBG_NCOL + (DBG_NCOL + 6) / 8) * 128 * 4;
+    cudaFuncSetAttribute(k_dbg_extend_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_dbg_extend_thread<<<(n_jobs + 127) / 128, 128, smem, st>>>(o, n_jobs, q, q_off, t, t_off, w, end_bonus, h0, out, reversed);
 }
 void launch_dbg_global(const DevOpts& o, uint32_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t, const uint64_t* t_off, const int* w,
                        int* out_score, uint32_t* cigar, uint32_t cig_cap, int* n_cigar, int* eh, uint32_t max_q, uint8_t* z, size_t z_per_warp,

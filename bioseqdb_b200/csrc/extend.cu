@@ -83,7 +83,15 @@ __global__ void __launch_bounds__(EXT_THREADS, SMEM ? 8 : 4) sw_extend(ExtendPar
             }
             const int64_t rlen = rmax1 - rmax0;
             if (rlen > (int64_t)P.rseq_cap) { if (lane == 0) atomicMax(P.need_rseq, (uint32_t)(rlen < 0x7fffffff ? rlen : 0x7fffffff)); continue; }
-            for (int64_t i = lane; i < rlen; i += 32) S.rseq[i] = (uint8_t)ref_base(ix, rmax0 + i);
+            // the reference window is decoded only when a ksw_extend2 call really runs here (most calls of a short-read batch
+            // were answered ahead of time by the thread-per-extension pass, extend_plan.cu)
+            bool rseq_ready = false;
+            auto need_rseq = [&]() {
+                if (rseq_ready) return;
+                for (int64_t i = lane; i < rlen; i += 32) S.rseq[i] = (uint8_t)ref_base(ix, rmax0 + i);
+                __syncwarp();
+                rseq_ready = true;
+            };
             // ---- seed order: by (score, index) ascending, processed from the top (keys are unique)
             if (lane == 0) {
                 for (int i = 0; i < n; ++i) srt[i] = (uint64_t)(uint32_t)seeds[i].score << 32 | (uint64_t)i;
@@ -133,8 +141,19 @@ __global__ void __launch_bounds__(EXT_THREADS, SMEM ? 8 : 4) sw_extend(ExtendPar
                     for (i = 0; i < MAX_BAND_TRY; ++i) {
                         int prev = a.score;
                         aw0 = o.w << i;
-                        e = ksw_extend_warp_t<SMEM>(o, s.qbeg, query + s.qbeg - 1, -1, tl, S.rseq + tmp - 1, -1, aw0, o.pen_clip5, s.len * o.a,
-                                                  S.ehh, smat, cells, rows);
+                        bool hit = false;
+                        if (i == 0 && P.memo && n_reg == 0) {
+                            const ExtMemo* M = P.memo + r;
+                            if (M->state == 2 && M->qlen == s.qbeg && M->tlen == tl && M->h0 == s.len * o.a && M->tpos == s.rbeg - 1) {
+                                e.score = M->out[0]; e.qle = M->out[1]; e.tle = M->out[2]; e.gtle = M->out[3]; e.gscore = M->out[4]; e.max_off = M->out[5];
+                                hit = true;
+                            }
+                        }
+                        if (!hit) {
+                            need_rseq();
+                            e = ksw_extend_warp_t<SMEM>(o, s.qbeg, query + s.qbeg - 1, -1, tl, S.rseq + tmp - 1, -1, aw0, o.pen_clip5, s.len * o.a,
+                                                      S.ehh, smat, cells, rows);
+                        }
                         ++calls;
                         a.score = e.score;
                         if (a.score == prev || e.max_off < (aw0 >> 1) + (aw0 >> 2)) break;
@@ -151,7 +170,18 @@ __global__ void __launch_bounds__(EXT_THREADS, SMEM ? 8 : 4) sw_extend(ExtendPar
                     for (i = 0; i < MAX_BAND_TRY; ++i) {
                         int prev = a.score;
                         aw1 = o.w << i;
-                        e = ksw_extend_warp_t<SMEM>(o, l_query - qe, query + qe, 1, tl, S.rseq + re, 1, aw1, o.pen_clip3, sc0, S.ehh, smat, cells, rows);
+                        bool hit = false;
+                        if (i == 0 && P.memo && n_reg == 0) {
+                            const ExtMemo* M = P.memo + (size_t)P.n_reads + r;
+                            if (M->state == 2 && M->qlen == l_query - qe && M->tlen == tl && M->h0 == sc0 && M->tpos == rmax0 + re) {
+                                e.score = M->out[0]; e.qle = M->out[1]; e.tle = M->out[2]; e.gtle = M->out[3]; e.gscore = M->out[4]; e.max_off = M->out[5];
+                                hit = true;
+                            }
+                        }
+                        if (!hit) {
+                            need_rseq();
+                            e = ksw_extend_warp_t<SMEM>(o, l_query - qe, query + qe, 1, tl, S.rseq + re, 1, aw1, o.pen_clip3, sc0, S.ehh, smat, cells, rows);
+                        }
                         ++calls;
                         a.score = e.score;
                         if (a.score == prev || e.max_off < (aw1 >> 1) + (aw1 >> 2)) break;

@@ -32,8 +32,24 @@ struct ChainParams {
 };
 void launch_chain(const ChainParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st);
 
+// Result of one ksw_extend2 call computed ahead of sw_extend by the thread-per-extension kernels (extend_plan.cu).  sw_extend
+// uses `out` only when the parameters of the call it is about to make equal the recorded ones (the call is a pure function
+// of them), so a plan that guessed wrong costs time, never correctness.
+struct ExtMemo {
+    int64_t tpos;                      // doubled-coordinate position of target row 0 (rows walk down from it on the left side, up on the right)
+    int32_t qlen, tlen, h0, state;     // state: 0 none, 1 planned, 3 planned but h0 waits for the left side's score, 2 done (out valid)
+    int32_t out[6];                    // score, qle, tle, gtle, gscore, max_off
+};
+static_assert(sizeof(ExtMemo) == 48, "ExtMemo layout");
+constexpr int EXT_MEMO_MAXQ = 136;     // longest query side the thread kernels take
+constexpr int EXT_MEMO_CLASSES = 4;    // job classes by query length (<= 32, 64, 96, 136 columns): shared memory per thread differs
+
 struct ExtendParams {
     const uint8_t* seqs; const uint64_t* offs; uint32_t n_reads;
+    // thread-per-extension pre-pass (nullptr = off): memo[0 .. n) left sides, memo[n .. 2n) right sides; key[side * n + r] = query
+    // length of the planned job (0 = none); perm[side * n + ...] = reads sorted by key; hist = 2 x 160 bin counts, then 2 x 160
+    // bin starts, then 2 x 160 scatter cursors (zeroed by the host before the launch)
+    ExtMemo* memo; uint8_t* memo_key; uint32_t* memo_perm; uint32_t* memo_hist;
     const ReadBlock* blocks; const ChainRec* chains; const SeedRec* seeds; uint64_t* srt;  // srt: one u64 per pooled seed
     RegRec* regs; uint32_t* reg_cnt;       // a read's regions live at regs[blocks[r].base ...], at most n_seeds of them
     uint8_t* scratch; size_t scratch_per_warp; uint32_t max_len, rseq_cap;
@@ -42,6 +58,8 @@ struct ExtendParams {
     unsigned long long* counters;  // optional: [0] = ksw_extend2 cells, [1] = calls, [2] = rows
 };
 void launch_extend(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st);
+void launch_extend_memo(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint64_t* launches);
+constexpr int EXT_MEMO_BINS = 160;
 size_t extend_scratch_per_warp(uint32_t max_len, uint32_t rseq_cap);
 int extend_resident_warps();
 

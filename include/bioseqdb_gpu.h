@@ -113,6 +113,10 @@ int bsq_debug_seed(bsq_index* h, const char* seqs, const uint64_t* offs, uint64_
  * ext jobs: query/target are nt4 bytes; out = 6 x int32 per job {score,qle,tle,gtle,gscore,max_off}. */
 int bsq_debug_ksw_extend(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
                          const uint64_t* t_off, const int32_t* w, const int32_t* end_bonus, const int32_t* h0, int32_t* out);
+/* the same jobs through the thread-per-extension kernel (one job per thread, query side <= 136 bases); reversed != 0: q holds every
+ * query back to front and the kernel's left-extension loader turns it round */
+int bsq_debug_ksw_extend_thread(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
+                                const uint64_t* t_off, const int32_t* w, const int32_t* end_bonus, const int32_t* h0, int32_t* out, int reversed);
 /* global jobs: out_score[n]; cigar words written at cigar + cig_cap*i with counts in n_cigar[i] */
 int bsq_debug_ksw_global(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
                          const uint64_t* t_off, const int32_t* w, int32_t* out_score, uint32_t* cigar, uint32_t cig_cap, int32_t* n_cigar);

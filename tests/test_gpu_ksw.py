@@ -59,6 +59,32 @@ def test_ksw_extend_parity(gpu_lib, opts_fn, qmax, err):
         assert [sc] + o5.tolist() == out[i].tolist(), (i, len(qs[i]), len(ts[i]), int(w[i]), int(h0[i]))
 
 
+@pytest.mark.parametrize("opts_fn,qmax,err,reversed_q", [(O.sql_default_opts, 136, 0.03, 0), (O.canonical_opts, 136, 0.03, 1), (O.canonical_opts, 136, 0.12, 0),
+                                                         (O.sql_default_opts, 40, 0.3, 1), (O.sql_default_opts, 9, 0.1, 1)])
+def test_ksw_extend_thread_parity(gpu_lib, opts_fn, qmax, err, reversed_q):
+    """The thread-per-extension kernel of the production pre-pass (ksw_thread.cuh) against the scalar oracle, through both of
+    its query loaders (forward = right extension, back to front = left extension)."""
+    rng = np.random.default_rng(qmax * 11 + int(err * 100) + reversed_q)
+    opts = opts_fn(1)
+    n = 3000
+    qs, ts, qcat, tcat, q_off, t_off = _jobs(rng, n, qmax, err, n_frac=0.02)
+    w = rng.choice([100, 200, 5, 30], size=n).astype(np.int32)
+    eb = rng.choice([5, 0], size=n).astype(np.int32)
+    h0 = rng.integers(1, 150, size=n).astype(np.int32)
+    out = np.zeros((n, 6), dtype=np.int32)
+    b = to_bsq(opts)
+    qdev = np.concatenate([x[::-1] for x in qs]) if reversed_q else qcat
+    qdev = np.ascontiguousarray(qdev)
+    _lib.check(gpu_lib.bsq_debug_ksw_extend_thread(C.byref(b), 0, n, _lib.ptr(qdev), _lib.ptr(q_off), _lib.ptr(tcat), _lib.ptr(t_off),
+                                                   _lib.ptr(w), _lib.ptr(eb), _lib.ptr(h0), _lib.ptr(out), reversed_q))
+    L = O.lib()
+    for i in range(n):
+        o5 = np.zeros(5, dtype=np.int32)
+        q = np.ascontiguousarray(qs[i]); t = np.ascontiguousarray(ts[i]) if len(ts[i]) else np.zeros(1, np.uint8)
+        sc = L.orc_ksw_extend2(len(qs[i]), O._ptr(q), len(ts[i]), O._ptr(t), C.byref(opts), int(w[i]), int(eb[i]), int(h0[i]), O._ptr(o5))
+        assert [sc] + o5.tolist() == out[i].tolist(), (i, len(qs[i]), len(ts[i]), int(w[i]), int(h0[i]))
+
+
 @pytest.mark.parametrize("opts_fn,qmax,err", [(O.sql_default_opts, 150, 0.03), (O.canonical_opts, 150, 0.05), (O.canonical_opts, 500, 0.1)])
 def test_ksw_global_parity(gpu_lib, opts_fn, qmax, err):
     rng = np.random.default_rng(qmax + int(err * 1000))

@@ -54,13 +54,13 @@ struct Batch {
     DevBuf<uint32_t> cigar; uint32_t cigar_cap = 0;
     DevBuf<double> read_logtab; uint32_t read_logtab_n = 0; uint32_t rseq_cap = 0;
     DevBuf<uint8_t> ext_scratch, fin_scratch, narrow_z, narrow_jobs; DevBuf<uint64_t> wide_jobs;
-    DevBuf<ExtMemo> ext_memo; DevBuf<uint8_t> ext_memo_key; DevBuf<uint32_t> ext_memo_perm, ext_memo_hist;   // thread-per-extension pre-pass (extend_plan.cu)
-    DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..23] counters (u64 x 8), [24] narrow_cnt, [25] wide_cnt, [26..27] tickets
+    DevBuf<ExtMemo> ext_memo; DevBuf<uint8_t> ext_memo_key; DevBuf<uint32_t> ext_memo_perm, ext_memo_hist, ext_todo;   // thread-per-extension pre-pass (extend_plan.cu)
+    DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..23] counters (u64 x 8), [24] narrow_cnt, [25] wide_cnt, [26..27] tickets, [56] reads left for sw_extend
     size_t device_bytes() const {
         return seqs.bytes() + offs.bytes() + ids.bytes() + intv.bytes() + intv_cnt.bytes() + seed_scratch.bytes() + raw.bytes() + seeds.bytes() + ctmp.bytes() +
                ord.bytes() + chains.bytes() + srt.bytes() + regs.bytes() + rows.bytes() + rows_compact.bytes() + reg_cnt.bytes() + row_cnt.bytes() + row_off.bytes() +
                scan_tmp.bytes() + blocks.bytes() + cigar.bytes() + read_logtab.bytes() + ext_scratch.bytes() + fin_scratch.bytes() + narrow_z.bytes() +
-               narrow_jobs.bytes() + wide_jobs.bytes() + ctl.bytes() + ext_memo.bytes() + ext_memo_key.bytes() + ext_memo_perm.bytes() + ext_memo_hist.bytes();
+               narrow_jobs.bytes() + wide_jobs.bytes() + ctl.bytes() + ext_memo.bytes() + ext_memo_key.bytes() + ext_memo_perm.bytes() + ext_memo_hist.bytes() + ext_todo.bytes();
     }
     bool resident = false, aligned = false;
     // one batch = one lane of the host pipeline: its stream, the host staging that must outlive the async copies,
@@ -80,7 +80,7 @@ struct Batch {
         ctmp.release(); ord.release(); chains.release(); srt.release(); regs.release(); rows.release(); rows_compact.release(); reg_cnt.release();
         row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release();
         ctl.release(); narrow_z.release(); narrow_jobs.release(); wide_jobs.release(); read_logtab.release();
-        ext_memo.release(); ext_memo_key.release(); ext_memo_perm.release(); ext_memo_hist.release();
+        ext_memo.release(); ext_memo_key.release(); ext_memo_perm.release(); ext_memo_hist.release(); ext_todo.release();
     }
 };
 
@@ -502,7 +502,7 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
     const bool use_memo = !no_memo && max_len <= 512 && (uint64_t)max_len * (uint64_t)(o.a + 1) < 32000;
     if (use_memo) {
         ENS(b.ext_memo.ensure((size_t)n * 2)); ENS(b.ext_memo_key.ensure((size_t)n * 2)); ENS(b.ext_memo_perm.ensure((size_t)n * 2));
-        ENS(b.ext_memo_hist.ensure(6 * EXT_MEMO_BINS));
+        ENS(b.ext_memo_hist.ensure(6 * EXT_MEMO_BINS)); ENS(b.ext_todo.ensure(n));
     }
     ENS(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, st));
     unsigned long long* ctr = h->collect_counters ? reinterpret_cast<unsigned long long*>(b.ctl.p + 8) : nullptr;
@@ -527,7 +527,9 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
         P.regs = b.regs.p; P.reg_cnt = b.reg_cnt.p; P.scratch = b.ext_scratch.p; P.scratch_per_warp = ext_per_warp; P.max_len = max_len; P.rseq_cap = rseq_cap;
         P.ticket = b.ctl.p + 2; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 3 : nullptr;
         P.memo = use_memo ? b.ext_memo.p : nullptr; P.memo_key = b.ext_memo_key.p; P.memo_perm = b.ext_memo_perm.p; P.memo_hist = b.ext_memo_hist.p;
+        P.todo = use_memo ? b.ext_todo.p : nullptr; P.todo_cnt = b.ctl.p + 56;
         launch_extend_memo(P, ix, o, st, &T.launches);
+        if (use_memo) { launch_extend_finish(P, ix, o, st); ++T.launches; }
         launch_extend(P, ix, o, st); ++T.launches;
     }
     cudaEventRecord(ev[3], st);

@@ -24,32 +24,27 @@ __device__ __forceinline__ Scratch carve(uint8_t* base, uint32_t max_len, uint32
     return s;
 }
 
-template <bool SMEM>
-__global__ void __launch_bounds__(EXT_THREADS, SMEM ? 8 : 4) sw_extend(ExtendParams P, DevIndex ix, DevOpts o) {
-    extern __shared__ __align__(16) uint8_t dyn_smem[];
-    __shared__ int smat[25];
-    if (threadIdx.x < 25) smat[threadIdx.x] = o.mat[threadIdx.x];
-    __syncthreads();
-    const int lane = lane_id();
-    const uint32_t gwarp = (blockIdx.x * EXT_THREADS + threadIdx.x) >> 5;
-    uint8_t* sbase = SMEM ? dyn_smem + (size_t)(threadIdx.x >> 5) * P.scratch_per_warp : P.scratch + (size_t)gwarp * P.scratch_per_warp;
-    const Scratch S = carve(sbase, P.max_len, P.rseq_cap);
-    unsigned long long cells = 0, calls = 0, rows = 0;
+// mem_chain2aln for one read.  WARPMODE: the 32 lanes of a warp work on the read together (scalar decisions are taken
+// redundantly by every lane, lane 0 writes) and run the ksw_extend2 calls the pre-pass did not answer.  !WARPMODE: ONE thread
+// walks the read with the same code; a ksw_extend2 call without a memo makes it give up (returns false) and the read is
+// queued for the warp kernel, which starts it again from scratch.
+template <bool WARPMODE, bool SMEM>
+__device__ __forceinline__ bool extend_read(const ExtendParams& P, const DevIndex& ix, const DevOpts& o, const uint32_t r, const Scratch& S, const int* smat,
+                                            unsigned long long& cells, unsigned long long& calls, unsigned long long& rows) {
+    const int lane = WARPMODE ? lane_id() : 0;
     const int64_t l_pac = ix.l_pac;
-    for (;;) {
-        uint32_t r = next_ticket(P.ticket);
-        if (r >= P.n_reads) break;
+    {
         const ReadBlock blk = P.blocks[r];
         int n_reg = 0;
-        if (blk.n_chains == 0) { if (lane == 0) P.reg_cnt[r] = 0; continue; }
+        if (blk.n_chains == 0) { if (lane == 0) P.reg_cnt[r] = 0; return true; }
         const int l_query = (int)(P.offs[r + 1] - P.offs[r]);
-        {
+        if (WARPMODE) {
             const uint8_t* qg = P.seqs + P.offs[r];
             for (int i = lane; i < l_query; i += 32) S.query[i] = qg[i];
         }
         const uint8_t* query = S.query;
         RegRec* av = P.regs + blk.base;
-        __syncwarp();
+        if (WARPMODE) __syncwarp();
         for (uint32_t ci = 0; ci < blk.n_chains; ++ci) {
             const ChainRec c = P.chains[blk.base + ci];
             const SeedRec* seeds = P.seeds + blk.base + c.seed_off;
@@ -82,12 +77,16 @@ __global__ void __launch_bounds__(EXT_THREADS, SMEM ? 8 : 4) sw_extend(ExtendPar
                 if (rmax1 < rmax0) rmax1 = rmax0;   // seed lying wholly in inter-row filler: empty fetch
             }
             const int64_t rlen = rmax1 - rmax0;
-            if (rlen > (int64_t)P.rseq_cap) { if (lane == 0) atomicMax(P.need_rseq, (uint32_t)(rlen < 0x7fffffff ? rlen : 0x7fffffff)); continue; }
+            if (rlen > (int64_t)P.rseq_cap) {
+                if (!WARPMODE) return false;
+                if (lane == 0) atomicMax(P.need_rseq, (uint32_t)(rlen < 0x7fffffff ? rlen : 0x7fffffff));
+                continue;
+            }
             // the reference window is decoded only when a ksw_extend2 call really runs here (most calls of a short-read batch
             // were answered ahead of time by the thread-per-extension pass, extend_plan.cu)
             bool rseq_ready = false;
             auto need_rseq = [&]() {
-                if (rseq_ready) return;
+                if (rseq_ready || !WARPMODE) return;
                 for (int64_t i = lane; i < rlen; i += 32) S.rseq[i] = (uint8_t)ref_base(ix, rmax0 + i);
                 __syncwarp();
                 rseq_ready = true;
@@ -97,7 +96,7 @@ __global__ void __launch_bounds__(EXT_THREADS, SMEM ? 8 : 4) sw_extend(ExtendPar
                 for (int i = 0; i < n; ++i) srt[i] = (uint64_t)(uint32_t)seeds[i].score << 32 | (uint64_t)i;
                 ks_introsort_dev(n, srt, [](uint64_t a, uint64_t b) { return a < b; });
             }
-            __syncwarp();
+            if (WARPMODE) __syncwarp();
             for (int k = n - 1; k >= 0; --k) {
                 const SeedRec s = seeds[(uint32_t)srt[k]];
                 int i;
@@ -125,7 +124,7 @@ __global__ void __launch_bounds__(EXT_THREADS, SMEM ? 8 : 4) sw_extend(ExtendPar
                     }
                     if (i == n) {
                         if (lane == 0) srt[k] = 0;
-                        __syncwarp();
+                        if (WARPMODE) __syncwarp();
                         continue;
                     }
                 }
@@ -150,9 +149,11 @@ __global__ void __launch_bounds__(EXT_THREADS, SMEM ? 8 : 4) sw_extend(ExtendPar
                             }
                         }
                         if (!hit) {
-                            need_rseq();
-                            e = ksw_extend_warp_t<SMEM>(o, s.qbeg, query + s.qbeg - 1, -1, tl, S.rseq + tmp - 1, -1, aw0, o.pen_clip5, s.len * o.a,
-                                                      S.ehh, smat, cells, rows);
+                            if constexpr (WARPMODE) {
+                                need_rseq();
+                                e = ksw_extend_warp_t<SMEM>(o, s.qbeg, query + s.qbeg - 1, -1, tl, S.rseq + tmp - 1, -1, aw0, o.pen_clip5, s.len * o.a,
+                                                          S.ehh, smat, cells, rows);
+                            } else return false;
                         }
                         ++calls;
                         a.score = e.score;
@@ -179,8 +180,10 @@ __global__ void __launch_bounds__(EXT_THREADS, SMEM ? 8 : 4) sw_extend(ExtendPar
                             }
                         }
                         if (!hit) {
-                            need_rseq();
-                            e = ksw_extend_warp_t<SMEM>(o, l_query - qe, query + qe, 1, tl, S.rseq + re, 1, aw1, o.pen_clip3, sc0, S.ehh, smat, cells, rows);
+                            if constexpr (WARPMODE) {
+                                need_rseq();
+                                e = ksw_extend_warp_t<SMEM>(o, l_query - qe, query + qe, 1, tl, S.rseq + re, 1, aw1, o.pen_clip3, sc0, S.ehh, smat, cells, rows);
+                            } else return false;
                         }
                         ++calls;
                         a.score = e.score;
@@ -199,12 +202,51 @@ __global__ void __launch_bounds__(EXT_THREADS, SMEM ? 8 : 4) sw_extend(ExtendPar
                 a.frac_rep = c.frac_rep;
                 if (lane == 0) av[n_reg] = a;   // n_reg < n_seeds of the read <= n_alloc
                 ++n_reg;
-                __syncwarp();
+                if (WARPMODE) __syncwarp();
             }
         }
         if (lane == 0) P.reg_cnt[r] = (uint32_t)n_reg;
     }
+    return true;
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(EXT_THREADS, SMEM ? 8 : 4) sw_extend(ExtendParams P, DevIndex ix, DevOpts o) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    __shared__ int smat[25];
+    if (threadIdx.x < 25) smat[threadIdx.x] = o.mat[threadIdx.x];
+    __syncthreads();
+    const int lane = lane_id();
+    const uint32_t gwarp = (blockIdx.x * EXT_THREADS + threadIdx.x) >> 5;
+    uint8_t* sbase = SMEM ? dyn_smem + (size_t)(threadIdx.x >> 5) * P.scratch_per_warp : P.scratch + (size_t)gwarp * P.scratch_per_warp;
+    const Scratch S = carve(sbase, P.max_len, P.rseq_cap);
+    unsigned long long cells = 0, calls = 0, rows = 0;
+    // with the pre-pass on, only the reads ext_finish could not complete are left (P.todo); otherwise every read
+    const uint32_t n_todo = P.todo ? *P.todo_cnt : P.n_reads;
+    for (;;) {
+        const uint32_t t = next_ticket(P.ticket);
+        if (t >= n_todo) break;
+        extend_read<true, SMEM>(P, ix, o, P.todo ? P.todo[t] : t, S, smat, cells, calls, rows);
+    }
     if (P.counters && lane == 0) { atomicAdd(&P.counters[0], cells); atomicAdd(&P.counters[1], calls); atomicAdd(&P.counters[2], rows); }
+}
+
+// Thread per read: completes every read whose ksw_extend2 calls were all answered by the pre-pass; the others go to P.todo.
+__global__ void __launch_bounds__(128) ext_finish(ExtendParams P, DevIndex ix, DevOpts o) {
+    const uint32_t r = blockIdx.x * 128 + threadIdx.x;
+    unsigned long long cells = 0, calls = 0, rows = 0;
+    if (r < P.n_reads) {
+        Scratch S; S.rseq = nullptr; S.query = nullptr; S.ehh = nullptr; S.ehe = nullptr;
+        if (!extend_read<false, false>(P, ix, o, r, S, nullptr, cells, calls, rows)) {
+            calls = 0;
+            P.todo[atomicAdd(P.todo_cnt, 1u)] = r;
+        }
+    }
+    if (P.counters) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) calls += __shfl_xor_sync(FULL, calls, d);
+        if (lane_id() == 0 && calls) atomicAdd(&P.counters[1], calls);
+    }
 }
 
 }  // namespace
@@ -223,6 +265,11 @@ int extend_resident_warps() {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (nb < 1) nb = 1;
     return nb * sms * EXT_WARPS;
+}
+
+void launch_extend_finish(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st) {
+    if (!p.todo || p.n_reads == 0) return;
+    ext_finish<<<(p.n_reads + 127) / 128, 128, 0, st>>>(p, ix, o);
 }
 
 void launch_extend(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st) {

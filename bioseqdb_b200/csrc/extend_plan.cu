@@ -151,9 +151,9 @@ __global__ void __launch_bounds__(DP_THREADS) ext_thread_dp(ExtendParams P, DevI
     ExtMemo* memo = P.memo + (size_t)side * n;
     uint32_t cells = 0, rows = 0;
     for (uint32_t tile = blockIdx.x; lo + tile * NT < hi; tile += gridDim.x) {
-        const uint32_t idx = lo + tile * NT + threadIdx.x;
-        if (idx >= hi) continue;
-        const uint32_t r = perm[idx];
+        const uint32_t k = tile * NT + threadIdx.x;     // longest jobs of the class first: the short ones fill the tail
+        if (k >= hi - lo) continue;
+        const uint32_t r = perm[hi - 1 - k];
         ExtMemo m = memo[r];
         if (m.state == 3) {   // right side behind a left side: starts from the left side's score, unless the left side needs its band retry
             const ExtMemo& l = P.memo[r];

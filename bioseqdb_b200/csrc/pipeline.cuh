@@ -50,6 +50,8 @@ struct ExtendParams {
     // length of the planned job (0 = none); perm[side * n + ...] = reads sorted by key; hist = 2 x 160 bin counts, then 2 x 160
     // bin starts, then 2 x 160 scatter cursors (zeroed by the host before the launch)
     ExtMemo* memo; uint8_t* memo_key; uint32_t* memo_perm; uint32_t* memo_hist;
+    // reads the thread-per-read pass (ext_finish) could not complete, for sw_extend (nullptr = sw_extend takes every read)
+    uint32_t* todo; uint32_t* todo_cnt;
     const ReadBlock* blocks; const ChainRec* chains; const SeedRec* seeds; uint64_t* srt;  // srt: one u64 per pooled seed
     RegRec* regs; uint32_t* reg_cnt;       // a read's regions live at regs[blocks[r].base ...], at most n_seeds of them
     uint8_t* scratch; size_t scratch_per_warp; uint32_t max_len, rseq_cap;
@@ -58,6 +60,7 @@ struct ExtendParams {
     unsigned long long* counters;  // optional: [0] = ksw_extend2 cells, [1] = calls, [2] = rows
 };
 void launch_extend(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st);
+void launch_extend_finish(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st);
 void launch_extend_memo(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint64_t* launches);
 constexpr int EXT_MEMO_BINS = 160;
 size_t extend_scratch_per_warp(uint32_t max_len, uint32_t rseq_cap);

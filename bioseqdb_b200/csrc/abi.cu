@@ -70,12 +70,14 @@ struct Batch {
     uint32_t* ctl_host = nullptr;       // pinned, 16 words: ctl[0..7], total rows (2 words), host-MAPQ flag
     cudaEvent_t ev[5]; bool ev_ok = false;
     cudaEvent_t ev_x[4]; bool evx_ok = false;   // chunked mode: upload begin/end, download begin/end
+    ExtAux ext_aux; bool ext_aux_ok = false;    // side streams of the extension pre-pass
     uint32_t att_rseq_cap = 0; bool idle = true;
     uint64_t out_rows = 0; uint32_t out_cig = 0;
     void release() {
         if (ctl_host) { cudaFreeHost(ctl_host); ctl_host = nullptr; }
         if (ev_ok) { for (auto& e : ev) cudaEventDestroy(e); ev_ok = false; }
         if (evx_ok) { for (auto& e : ev_x) cudaEventDestroy(e); evx_ok = false; }
+        if (ext_aux_ok) { for (auto& s_ : ext_aux.st) cudaStreamDestroy(s_); for (auto& e : ext_aux.ev) cudaEventDestroy(e); ext_aux_ok = false; }
         seqs.release(); offs.release(); ids.release(); intv.release(); intv_cnt.release(); seed_scratch.release(); raw.release(); seeds.release();
         ctmp.release(); ord.release(); chains.release(); srt.release(); regs.release(); rows.release(); rows_compact.release(); reg_cnt.release();
         row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release();
@@ -503,6 +505,11 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
     if (use_memo) {
         ENS(b.ext_memo.ensure((size_t)n * 2)); ENS(b.ext_memo_key.ensure((size_t)n * 2)); ENS(b.ext_memo_perm.ensure((size_t)n * 2));
         ENS(b.ext_memo_hist.ensure(6 * EXT_MEMO_BINS)); ENS(b.ext_todo.ensure(n));
+        if (!b.ext_aux_ok) {
+            for (auto& s_ : b.ext_aux.st) ENS(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
+            for (auto& e : b.ext_aux.ev) ENS(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            b.ext_aux_ok = true;
+        }
     }
     ENS(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, st));
     unsigned long long* ctr = h->collect_counters ? reinterpret_cast<unsigned long long*>(b.ctl.p + 8) : nullptr;
@@ -528,7 +535,8 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
         P.ticket = b.ctl.p + 2; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 3 : nullptr;
         P.memo = use_memo ? b.ext_memo.p : nullptr; P.memo_key = b.ext_memo_key.p; P.memo_perm = b.ext_memo_perm.p; P.memo_hist = b.ext_memo_hist.p;
         P.todo = use_memo ? b.ext_todo.p : nullptr; P.todo_cnt = b.ctl.p + 56;
-        launch_extend_memo(P, ix, o, st, &T.launches);
+        static const bool one_stream = getenv("BSQ_EXT_ONE_STREAM") != nullptr;
+        launch_extend_memo(P, ix, o, st, &T.launches, one_stream ? nullptr : &b.ext_aux);
         if (use_memo) { launch_extend_finish(P, ix, o, st); ++T.launches; }
         launch_extend(P, ix, o, st); ++T.launches;
     }

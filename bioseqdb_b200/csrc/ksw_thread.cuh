@@ -63,7 +63,11 @@ __device__ __forceinline__ ExtOut ksw_extend_thread(const DevOpts& o, uint32_t* 
                                                     int w, int end_bonus, int h0, uint32_t& cells, uint32_t& rows) {
     const int e_del = o.e_del, e_ins = o.e_ins, o_del = o.o_del, o_ins = o.o_ins;
     const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
-    const int sA = o.mat[0], sB = o.mat[1], sN = o.mat[4];   // bwa_fill_scmat: match / mismatch / ambiguous (host checks the matrix has this form)
+    // bwa_fill_scmat: match / mismatch / ambiguous.  The score of a column is ONE byte-permute: the row's five scores (biased to be
+    // non-negative) sit in the bytes of a 64-bit register pair and the query code selects one (bytes 5..7 are zero).
+    const int sA = o.mat[0], sB = o.mat[1], sN = o.mat[4];
+    const int bias = -::min(::min(sA, sB), ::min(sN, 0));
+    const uint32_t lut_mis = (uint32_t)(sB + bias) * 0x01010101u, lut_amb = (uint32_t)(sN + bias) * 0x01010101u, lut_hi = (uint32_t)(sN + bias);
     // first row in closed form: eh[0].h = h0, eh[j].h = max(h0 - o_ins - j e_ins, 0), e = 0
     eh[0] = (uint32_t)h0;
     for (int j = 1; j <= qlen; ++j) { const int v = h0 - o_ins - j * e_ins; eh[j * NT] = (uint32_t)(v > 0 ? v : 0); }
@@ -84,6 +88,7 @@ __device__ __forceinline__ ExtOut ksw_extend_thread(const DevOpts& o, uint32_t* 
         int h1 = 0;
         if (beg == 0) { h1 = h0 - (o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; }
         const int tb = tbase(i);
+        const uint32_t lut_lo = tb > 3 ? lut_amb : lut_mis + ((uint32_t)(sA - sB) << (tb << 3));
         int f = 0, m = 0, mj = -1, first_nz = 0x7fffffff, last_nz = -1;
         cells += (uint32_t)(end > beg ? end - beg : 0); ++rows;
         int j = beg;
@@ -92,12 +97,11 @@ __device__ __forceinline__ ExtOut ksw_extend_thread(const DevOpts& o, uint32_t* 
             uint32_t* p = eh + beg * NT;
             for (; j < end; ++j, p += NT) {
                 if ((j & 7) == 0) qw = qn[(j >> 3) * NT];
-                const int qb = (int)(qw & 15u);
+                const int sc = (int)__byte_perm(lut_lo, lut_hi, (qw & 7u) | 0x7770u) - bias;
                 qw >>= 4;
                 const uint32_t v = *p;
                 int M = (int)(v & 0xffffu);
                 const int e = (int)(v >> 16);
-                const int sc = (qb | tb) > 3 ? sN : (qb == tb ? sA : sB);
                 M = M ? M + sc : 0;
                 const int h = __vimax3_s32(M, e, f);
                 const int e2 = __viaddmax_s32_relu(e, -e_del, M - oe_del);

@@ -61,7 +61,8 @@ struct ExtendParams {
 };
 void launch_extend(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st);
 void launch_extend_finish(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st);
-void launch_extend_memo(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint64_t* launches);
+struct ExtAux { cudaStream_t st[3]; cudaEvent_t ev[4]; };
+void launch_extend_memo(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint64_t* launches, const ExtAux* aux);
 constexpr int EXT_MEMO_BINS = 160;
 size_t extend_scratch_per_warp(uint32_t max_len, uint32_t rseq_cap);
 int extend_resident_warps();

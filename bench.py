@@ -260,6 +260,19 @@ def run_ours(args, rank, world, local_rank):
     pr = res.rows[np.minimum(first, max(total_rows - 1, 0))]
     okk = has & (pr["rid"] == truth[0]) & (pr["is_rev"] == truth[2].astype(np.int32)) & (np.abs(pr["pos"] - truth[1]) <= 16 + args.read_len // 8)
     truth_frac = float(okk.mean())
+    # digest of everything the step produced (row records, CIGAR words, row offsets): two builds / code paths can be compared run to run
+    import hashlib
+    dg = hashlib.sha1()
+    dg.update(np.ascontiguousarray(res.row_off).tobytes())
+    rr = res.rows[:total_rows]
+    for name in rr.dtype.names:
+        if name != "cigar_off":            # pool positions depend on the order warps allocate in; the words they point at do not
+            dg.update(np.ascontiguousarray(rr[name]).tobytes())
+    if total_rows:
+        nc = rr["n_cigar"].astype(np.int64)
+        starts = np.repeat(rr["cigar_off"].astype(np.int64) - np.concatenate(([0], np.cumsum(nc)[:-1])), nc)
+        dg.update(np.ascontiguousarray(res.cigar[starts + np.arange(int(nc.sum()), dtype=np.int64)]).tobytes())
+    rows_digest = dg.hexdigest()
 
     # ---------------- e2e: host buffers through bsq_align_batch
     resp = C.POINTER(_lib.BsqResult)()
@@ -340,7 +353,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roof, "sw": sw,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "wall_ms_per_step": 1e3 * wall_max / args.steps,
-            "rows_per_step_rank0": total_rows, "truth_match_frac_rank0": truth_frac,
+            "rows_per_step_rank0": total_rows, "truth_match_frac_rank0": truth_frac, "rows_sha1_rank0": rows_digest,
             "index": {"build_ms_device": meta.build_ms, "build_wall_s": build_wall, "build_launches": int(meta.build_launches),
                       "sort_pass_gbs": (meta.sort_pass_bytes / (meta.build_ms * 1e-3) / 1e9) if meta.build_ms else None,
                       "seq_len": int(meta.seq_len), "broadcast_bytes": bcast_bytes},

@@ -100,7 +100,7 @@ struct bsq_index {
     cudaStream_t stream2 = nullptr;
     bsq_timing timing;
     double* d_logtab = nullptr;
-    uint32_t* d_isa = nullptr;       // inverse SA for the unique-match shortcut of the seeding kernel (built lazily, 32-bit rows)
+    void* d_isa = nullptr;           // inverse SA for the unique-match shortcut of the seeding kernel (built lazily, rows as wide as the SA's)
     void* d_kmer = nullptr; int kmer_k = 0;          // k-mer table of the LAST-like seeding pass (built lazily per device index)
     bool collect_counters = false;
     uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -241,7 +241,7 @@ int bsq_index_device_bytes(const bsq_index* h, uint64_t* bytes) {
     if (h->meta.built) {
         const uint64_t n = h->meta.seq_len;
         b += (h->meta.l_pac + 3) / 4 + ((n + 127) / 128 + 1) * 64 + (n + 1) * h->meta.sa_bytes + h->meta.n_anns * 20;
-        if (h->d_isa) b += (n + 1) * 4 + 64;
+        if (h->d_isa) b += (n + 1) * (uint64_t)h->meta.sa_bytes + 64;
         if (h->d_kmer) b += kmer_table_bytes(h->kmer_k);
     }
     *bytes = b;
@@ -425,13 +425,13 @@ int upload_reads(bsq_index* h, Batch& b, const char* seqs, const uint64_t* offs,
 
 // k-mer table of the LAST-like seeding pass: built once per device index (also after a broadcast replica)
 int ensure_kmer_table(bsq_index* h, const DevIndex& ix) {
-    if (ix.sa_bytes != 4) return BSQ_OK;
+    if (ix.seq_len >= (1ull << 40)) return BSQ_OK;   // the table packs rows in 40 bits
     if (!h->d_isa && !getenv("BSQ_NO_ISA")) {
-        CUDA_CHECK(cudaMalloc(&h->d_isa, (ix.seq_len + 1) * 4 + 64));
+        CUDA_CHECK(cudaMalloc(&h->d_isa, (ix.seq_len + 1) * (uint64_t)ix.sa_bytes + 64));
         build_isa(ix, h->d_isa, h->stream, &h->timing.launches);
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
     }
-    if (h->d_kmer || ix.seq_len < (1u << 16)) return BSQ_OK;
+    if (h->d_kmer || ix.seq_len < (1u << 16) || getenv("BSQ_NO_KMER")) return BSQ_OK;
     h->kmer_k = kmer_table_depth(ix.seq_len);
     if (const char* e = getenv("BSQ_KMER_K")) { const int k = atoi(e); if (k >= 8 && k <= 14) h->kmer_k = k; }
     CUDA_CHECK(cudaMalloc(&h->d_kmer, kmer_table_bytes(h->kmer_k)));

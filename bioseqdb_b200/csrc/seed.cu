@@ -24,6 +24,16 @@ constexpr int KMER_K_MAX = 14;
 __host__ __device__ constexpr uint32_t kmer_level_off(int t) { return ((1u << (2 * t)) - 4u) / 3u; }   // first entry of level t
 
 template <class IdxT> struct IvT { IdxT x0, x1; uint32_t x2, info; };   // info = end of the match on the query
+// prefix-table entry {x0 low word, x1 low word, x2, hi}: hi = bits 32..39 of x0 | bits 32..39 of x1 << 8 (zero while rows fit 32 bits)
+template <class IdxT> __device__ __forceinline__ IdxT tab_x0(const uint4& e) {
+    return sizeof(IdxT) == 4 ? (IdxT)e.x : (IdxT)((unsigned long long)(e.w & 0xffu) << 32 | e.x);
+}
+template <class IdxT> __device__ __forceinline__ IdxT tab_x1(const uint4& e) {
+    return sizeof(IdxT) == 4 ? (IdxT)e.y : (IdxT)((unsigned long long)((e.w >> 8) & 0xffu) << 32 | e.y);
+}
+__host__ __device__ __forceinline__ uint4 tab_entry(unsigned long long x0, unsigned long long x1, uint32_t x2) {
+    return make_uint4((uint32_t)x0, (uint32_t)x1, x2, (uint32_t)((x0 >> 32) & 0xffu) | (uint32_t)((x1 >> 32) & 0xffu) << 8);
+}
 template <> struct __align__(16) IvT<uint32_t> { uint32_t x0, x1, x2, info; };
 
 // warp-private context: everything the extend needs without indexing the kernel parameter block dynamically
@@ -34,8 +44,8 @@ template <class IdxT> struct Ctx {
     const uint4* kmer_tab;   // prefix table (x0, x1, x2, -) of all t-mers, t <= kk; nullptr when absent
     int kk;                  // depth of the prefix table
     int lane;                // the thread's lane, read from the special register ONCE (the compiler otherwise re-issues S2R in hot loops)
-    // unique-match shortcut (32-bit rows): full SA, inverse SA and the 2-bit text; isa == nullptr disables it
-    const uint32_t* sa; const uint32_t* isa; const uint8_t* pac; uint32_t l_pac, n;
+    // unique-match shortcut: full SA, inverse SA and the 2-bit text; isa == nullptr disables it
+    const IdxT* sa; const IdxT* isa; const uint8_t* pac; IdxT l_pac, n;
     IdxT primary;
     uint32_t sym_base;       // first symbol covered by this lane's word (symbol lanes), 1 << 20 for checkpoint lanes
     int cnt_sym;             // symbol whose checkpoint LOW word this lane holds, -1 otherwise
@@ -137,28 +147,28 @@ __device__ __forceinline__ IvT<IdxT> extend4_back(const Ctx<IdxT>& C, const IvT<
 // compares read and text directly, 32 bases per step, and the rows of the extended match come from the inverse
 // suffix array -- x0 = ISA[start], x1 = ISA[n - start - length] (T is its own reverse complement).  The result
 // is the bi-interval bwt_extend would have produced, because the bi-interval of a string is unique.
-template <class IdxT> __device__ __forceinline__ uint32_t text_base(const Ctx<IdxT>& C, uint32_t p) {
-    return p < C.l_pac ? pac_get(C.pac, p) : 3u - pac_get(C.pac, (int64_t)2 * C.l_pac - 1 - p);
+template <class IdxT> __device__ __forceinline__ uint32_t text_base(const Ctx<IdxT>& C, IdxT p) {
+    return p < C.l_pac ? pac_get(C.pac, (int64_t)p) : 3u - pac_get(C.pac, (int64_t)2 * (int64_t)C.l_pac - 1 - (int64_t)p);
 }
 // number of consecutive k in [0, maxlen) with q[qpos + k] an ACGT base equal to T[tpos + k]
-template <class IdxT> __device__ __forceinline__ int match_run_fwd(const Ctx<IdxT>& C, uint32_t tpos, const uint8_t* q, int qpos, int maxlen) {
+template <class IdxT> __device__ __forceinline__ int match_run_fwd(const Ctx<IdxT>& C, IdxT tpos, const uint8_t* q, int qpos, int maxlen) {
     const int lane = C.lane;
     for (int base = 0; base < maxlen; base += 32) {
         const int k = base + lane;
         bool ok = k < maxlen;
-        if (ok) { const uint32_t p = tpos + (uint32_t)k; const uint32_t b = q[qpos + k]; ok = p < C.n && b < 4 && text_base(C, p) == b; }
+        if (ok) { const IdxT p = tpos + (IdxT)k; const uint32_t b = q[qpos + k]; ok = p < C.n && b < 4 && text_base(C, p) == b; }
         const uint32_t bad = __ballot_sync(FULL, !ok);
         if (bad) { const int r = base + __ffs(bad) - 1; return r < maxlen ? r : maxlen; }
     }
     return maxlen;
 }
 // backwards: number of consecutive k in [0, maxlen) with q[qpos - k] == T[tpos - 1 - k]
-template <class IdxT> __device__ __forceinline__ int match_run_bwd(const Ctx<IdxT>& C, uint32_t tpos, const uint8_t* q, int qpos, int maxlen) {
+template <class IdxT> __device__ __forceinline__ int match_run_bwd(const Ctx<IdxT>& C, IdxT tpos, const uint8_t* q, int qpos, int maxlen) {
     const int lane = C.lane;
     for (int base = 0; base < maxlen; base += 32) {
         const int k = base + lane;
         bool ok = k < maxlen;
-        if (ok) { const uint32_t b = q[qpos - k]; ok = (uint32_t)k < tpos && b < 4 && text_base(C, tpos - 1 - (uint32_t)k) == b; }
+        if (ok) { const uint32_t b = q[qpos - k]; ok = (IdxT)k < tpos && b < 4 && text_base(C, (IdxT)(tpos - 1 - (IdxT)k)) == b; }
         const uint32_t bad = __ballot_sync(FULL, !ok);
         if (bad) { const int r = base + __ffs(bad) - 1; return r < maxlen ? r : maxlen; }
     }
@@ -204,7 +214,7 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
     uint32_t n_curr = 0;
     int i = x + 1;
     bool fwd_done = false;
-    if (sizeof(IdxT) == 4 && C.kmer_tab && x + KK <= len) {
+    if (C.kmer_tab && x + KK <= len) {
         // The first KK - 1 forward steps from the prefix table: lane t fetches the interval of q[x .. x+t]; the step
         // that appends base t+1 records lane t's interval when the size changes and stops the walk when it falls below
         // min_intv -- the same decisions the scalar loop takes, evaluated for all steps at once.
@@ -218,24 +228,26 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
             const int steps = brk ? __ffs(brk) : KK - 1;
             const bool push = change && lane < steps;
             const uint32_t pmask = __ballot_sync(FULL, push);
-            if (push) { IvT<IdxT> pv; pv.x0 = (IdxT)e.x; pv.x1 = (IdxT)e.y; pv.x2 = e.z; pv.info = (uint32_t)(x + lane + 1); curr[__popc(pmask & ((1u << lane) - 1u))] = pv; }
+            if (push) { IvT<IdxT> pv; pv.x0 = tab_x0<IdxT>(e); pv.x1 = tab_x1<IdxT>(e); pv.x2 = e.z; pv.info = (uint32_t)(x + lane + 1); curr[__popc(pmask & ((1u << lane) - 1u))] = pv; }
             n_curr = (uint32_t)__popc(pmask);
             n_ext += (unsigned long long)steps;
             if (brk) { fwd_done = true; i = x + steps; }
             else {
-                ik.x0 = (IdxT)__shfl_sync(FULL, e.x, KK - 1); ik.x1 = (IdxT)__shfl_sync(FULL, e.y, KK - 1);
-                ik.x2 = __shfl_sync(FULL, e.z, KK - 1); ik.info = (uint32_t)(x + KK);
+                uint4 ek;
+                ek.x = __shfl_sync(FULL, e.x, KK - 1); ek.y = __shfl_sync(FULL, e.y, KK - 1); ek.z = __shfl_sync(FULL, e.z, KK - 1);
+                ek.w = sizeof(IdxT) == 8 ? __shfl_sync(FULL, e.w, KK - 1) : 0u;
+                ik.x0 = tab_x0<IdxT>(ek); ik.x1 = tab_x1<IdxT>(ek); ik.x2 = ek.z; ik.info = (uint32_t)(x + KK);
                 i = x + KK;
             }
         }
     }
     if (!fwd_done)
     for (; i < len; ++i) {
-        if (sizeof(IdxT) == 4 && C.isa && ik.x2 == 1 && min_intv == 1) {
+        if (C.isa && ik.x2 == 1 && min_intv == 1) {
             // unique match q[x .. i): walk to the first base that does not match (or the end of the read) in one go
-            const uint32_t pos = C.sa[ik.x0];
-            const int run = match_run_fwd(C, pos + (uint32_t)(i - x), q, i, len - i);
-            if (run > 0) { i += run; ik.x1 = (IdxT)C.isa[C.n - pos - (uint32_t)(i - x)]; ik.info = (uint32_t)i; n_ext += (unsigned long long)run; }
+            const IdxT pos = C.sa[ik.x0];
+            const int run = match_run_fwd(C, (IdxT)(pos + (IdxT)(i - x)), q, i, len - i);
+            if (run > 0) { i += run; ik.x1 = C.isa[C.n - pos - (IdxT)(i - x)]; ik.info = (uint32_t)i; n_ext += (unsigned long long)run; }
             if (i == len) break;                               // matched to the end: recorded after the loop
             if (q[i] < 4) ++n_ext;                             // the extension the scalar code tries next: it empties the interval
             if (n_curr < list_cap) { if (lane == 0) curr[n_curr] = ik; } else O.ovf = true;
@@ -278,8 +290,8 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
         if (own) p = prev[n_prev - 1 - (uint32_t)lane];
         uint32_t present = __ballot_sync(FULL, own);
         const uint32_t lt = (1u << lane) - 1u;
-        const bool can_uq = sizeof(IdxT) == 4 && C.isa != nullptr && min_intv == 1;
-        const bool tab_ok = sizeof(IdxT) == 4 && pk != nullptr;
+        const bool can_uq = C.isa != nullptr && min_intv == 1;
+        const bool tab_ok = pk != nullptr;
         const bool fast_ok = tab_ok && !has_n && o.min_seed_len > KK;
         // unique first entry: its walk is one text comparison (uq_stop = the index i at which it dies, uq_x0 = its row then)
         bool uq = false; int uq_stop = 0; IdxT uq_x0 = 0;
@@ -289,10 +301,10 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
             if (can_uq && !uq) {
                 const uint32_t fx2 = __shfl_sync(FULL, p.x2, first);
                 if (fx2 == 1) {
-                    const uint32_t fx0 = (uint32_t)__shfl_sync(FULL, p.x0, first);
-                    const uint32_t pos = C.sa[fx0];
+                    const IdxT fx0 = __shfl_sync(FULL, p.x0, first);
+                    const IdxT pos = C.sa[fx0];
                     const int run = match_run_bwd(C, pos, q, i, i + 1);
-                    uq = true; uq_stop = i - run; uq_x0 = run > 0 ? (IdxT)C.isa[pos - (uint32_t)run] : (IdxT)fx0;
+                    uq = true; uq_stop = i - run; uq_x0 = run > 0 ? C.isa[pos - (IdxT)run] : fx0;
                 }
             }
             if (uq && (present & (present - 1)) == 0 && i > uq_stop) { ne += (uint32_t)(i - uq_stop); i = uq_stop; }   // alone: jump
@@ -308,7 +320,7 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
                     const int lq = (int)p.info - i;
                     if (__any_sync(FULL, actf && !is_uqf && lq > KK)) break;
                     if (!uq && can_uq && __shfl_sync(FULL, p.x2, fst) == 1) break;            // a new unique first entry: general step converts it
-                    uint4 e = make_uint4((uint32_t)p.x0, (uint32_t)p.x1, 1u, 0u);
+                    uint4 e = make_uint4(0u, 0u, 1u, 0u);      // a unique first entry keeps its interval (size 1)
                     if (actf && !is_uqf) {
                         const uint32_t w = __funnelshift_l(pk[(i >> 4) + 1], pk[i >> 4], (i & 15) << 1);
                         e = __ldg(C.kmer_tab + kmer_level_off(lq) + (w >> (32 - 2 * lq)));
@@ -320,7 +332,7 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
                     const bool keepf = alivef && (bef == 0 || e.z != psz);
                     ne += (uint32_t)__popc(present);
                     present = __ballot_sync(FULL, keepf);
-                    if (keepf) { p.x0 = (IdxT)e.x; p.x1 = (IdxT)e.y; p.x2 = e.z; }
+                    if (keepf && !is_uqf) { p.x0 = tab_x0<IdxT>(e); p.x1 = tab_x1<IdxT>(e); p.x2 = e.z; }
                     if (!present) { done = true; break; }
                     --i;
                 }
@@ -341,7 +353,7 @@ __device__ __forceinline__ int smem1(const Ctx<IdxT>& C, const DevOpts& o, int l
                 if (by_table) {
                     const uint32_t w = __funnelshift_l(pk[(i >> 4) + 1], pk[i >> 4], (i & 15) << 1);
                     const uint4 e = __ldg(C.kmer_tab + kmer_level_off(lq) + (w >> (32 - 2 * lq)));
-                    nx0 = (IdxT)e.x; nx1 = (IdxT)e.y; sz = e.z;
+                    nx0 = tab_x0<IdxT>(e); nx1 = tab_x1<IdxT>(e); sz = e.z;
                 }
                 uint32_t todo = __ballot_sync(FULL, act && !is_uq && !by_table);
                 ne += (uint32_t)__popc(present);
@@ -436,16 +448,16 @@ __device__ __forceinline__ int seed_strategy1(const Ctx<IdxT>& C, int len, const
     int i = x + 1;
     // The first kk - 1 extensions can neither emit (i - x < min_len) nor be observed: take their result from the
     // k-mer table when the next kk bases are all ACGT (an ambiguous base ends the walk, which the plain loop handles)
-    if (sizeof(IdxT) == 4 && C.kmer_tab && min_len >= C.kk && x + C.kk <= len) {
+    if (C.kmer_tab && min_len >= C.kk && x + C.kk <= len) {
         uint32_t w;
         if (kmer_word(q, pk, has_n, x, C.kk, w)) {
             const uint4 e = __ldg(C.kmer_tab + kmer_level_off(C.kk) + (w >> (32 - 2 * C.kk)));
-            ik.x0 = (IdxT)e.x; ik.x1 = (IdxT)e.y; ik.x2 = e.z;
+            ik.x0 = tab_x0<IdxT>(e); ik.x1 = tab_x1<IdxT>(e); ik.x2 = e.z;
             i = x + C.kk; n_ext += C.kk - 1;   // the roofline unit stays the reference's count of bwt_extend calls
         }
     }
     for (; i < len; ++i) {
-        if (sizeof(IdxT) == 4 && C.isa && ik.x2 == 1 && max_intv > 1 && i - x <= min_len) {
+        if (C.isa && ik.x2 == 1 && max_intv > 1 && i - x <= min_len) {
             // unique match q[x .. i): the walk ends at j = x + min_len (emit iff still matching), at an ambiguous base
             // (nothing emitted), or at the end of the read
             const int stop = x + min_len;                       // index of the base whose extension triggers the emission test
@@ -454,14 +466,14 @@ __device__ __forceinline__ int seed_strategy1(const Ctx<IdxT>& C, int len, const
             bool isn = false;
             if (lane < lim) isn = q[i + lane] > 3;              // lim <= min_len + 1 - (i - x) <= 32 for min_seed_len <= 31
             const uint32_t nmask = __ballot_sync(FULL, isn);
-            const uint32_t pos = C.sa[ik.x0];
-            const int run = match_run_fwd(C, pos + (uint32_t)(i - x), q, i, lim);
+            const IdxT pos = C.sa[ik.x0];
+            const int run = match_run_fwd(C, (IdxT)(pos + (IdxT)(i - x)), q, i, lim);
             if (nmask) { const int jn = i + __ffs(nmask) - 1; n_ext += (unsigned long long)(jn - i); return jn + 1; }
             n_ext += (unsigned long long)lim;
             if (stop >= len) return len;
             if (run == lim) {
                 IvT<IdxT> ok = ik;
-                ok.x1 = (IdxT)C.isa[C.n - pos - (uint32_t)(stop + 1 - x)]; ok.x2 = 1;
+                ok.x1 = C.isa[C.n - pos - (IdxT)(stop + 1 - x)]; ok.x2 = 1;
                 emit(O, ok, (uint32_t)x, (uint32_t)(stop + 1));
             }
             return stop + 1;
@@ -515,7 +527,7 @@ __device__ __forceinline__ void collect_intv(const Ctx<IdxT>& C, const DevOpts& 
         // evaluates f(x + t L) on its own -- K-mer from the prefix table, then (unique K-mer) one text comparison of the
         // remaining L - K bases -- so the dependent loads of up to 32 starts are in flight together; the chain then consumes
         // the results in order for as long as each start is the predicted one and was decidable without Occ.
-        const bool spec_ok = sizeof(IdxT) == 4 && C.kmer_tab != nullptr && C.isa != nullptr && pk != nullptr && !has_n &&
+        const bool spec_ok = C.kmer_tab != nullptr && C.isa != nullptr && pk != nullptr && !has_n &&
                              min_len >= C.kk && o.max_mem_intv > 1 && L <= 32;
         const int lane = C.lane;
         while (x < len) {
@@ -523,17 +535,17 @@ __device__ __forceinline__ void collect_intv(const Ctx<IdxT>& C, const DevOpts& 
                 if (x + L > len) { n_ext += (unsigned long long)(len - 1 - x); break; }   // too short to emit: only the extension count remains
                 const int xs = x + L * lane;
                 int state = 0;                     // 0 undecided (needs Occ) or out of range, 1 no seed, 2 seed
-                uint32_t r0 = 0, r1 = 0;
+                IdxT r0 = 0, r1 = 0;
                 if (xs + L <= len) {
                     const uint32_t w = __funnelshift_l(pk[(xs >> 4) + 1], pk[xs >> 4], (xs & 15) << 1);
                     const uint4 e = __ldg(C.kmer_tab + kmer_level_off(C.kk) + (w >> (32 - 2 * C.kk)));
                     if (e.z == 0) state = 1;
                     else if (e.z == 1) {
-                        const uint32_t pos = C.sa[e.x];
-                        bool ok = pos + (uint32_t)L <= C.n;
-                        for (int k = C.kk; ok && k < L; ++k) ok = text_base(C, pos + (uint32_t)k) == (uint32_t)q[xs + k];
+                        const IdxT pos = C.sa[tab_x0<IdxT>(e)];
+                        bool ok = pos + (IdxT)L <= C.n;
+                        for (int k = C.kk; ok && k < L; ++k) ok = text_base(C, (IdxT)(pos + (IdxT)k)) == (uint32_t)q[xs + k];
                         state = ok ? 2 : 1;
-                        if (ok) { r0 = e.x; r1 = C.isa[C.n - pos - (uint32_t)L]; }
+                        if (ok) { r0 = tab_x0<IdxT>(e); r1 = C.isa[C.n - pos - (IdxT)L]; }
                     }
                 }
                 const uint32_t decided = __ballot_sync(FULL, state != 0);
@@ -561,11 +573,16 @@ __device__ __forceinline__ void collect_intv(const Ctx<IdxT>& C, const DevOpts& 
 // ---------------------------------------------------------------- k-mer table of the LAST-like pass
 // Level-by-level: the 4^t intervals of level t come from one forward bwt_extend of each level t-1 interval
 // (all four children at once, scalar Occ4 per thread).  Entry of k-mer b0 b1 .. b_{K-1} sits at index sum b_t 4^{K-1-t}.
-__device__ __forceinline__ void occ4_scalar(const uint32_t* occ, uint32_t primary, uint32_t k, uint32_t cnt[4]) {
+template <class IdxT>
+__device__ __forceinline__ void occ4_scalar(const uint32_t* occ, IdxT primary, IdxT k, IdxT cnt[4]) {
     k -= (k >= primary);
     const uint4* blk = reinterpret_cast<const uint4*>(occ + ((size_t)(k >> 7) << 4));
     const uint4 ca = __ldg(blk), cb = __ldg(blk + 1), s0 = __ldg(blk + 2), s1 = __ldg(blk + 3);
-    cnt[0] = ca.x; cnt[1] = ca.z; cnt[2] = cb.x; cnt[3] = cb.z;
+    if (sizeof(IdxT) == 4) { cnt[0] = (IdxT)ca.x; cnt[1] = (IdxT)ca.z; cnt[2] = (IdxT)cb.x; cnt[3] = (IdxT)cb.z; }
+    else {
+        cnt[0] = (IdxT)((unsigned long long)ca.y << 32 | ca.x); cnt[1] = (IdxT)((unsigned long long)ca.w << 32 | ca.z);
+        cnt[2] = (IdxT)((unsigned long long)cb.y << 32 | cb.x); cnt[3] = (IdxT)((unsigned long long)cb.w << 32 | cb.z);
+    }
     const int within = (int)(k & 127) + 1;
     const uint32_t w8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
@@ -578,34 +595,38 @@ __device__ __forceinline__ void occ4_scalar(const uint32_t* occ, uint32_t primar
     }
 }
 
+template <class IdxT> struct L2Vals { IdxT v[5]; };
+
+template <class IdxT>
 __global__ void k_kmer_level(const uint4* __restrict__ parent, uint4* __restrict__ child, uint32_t n_parent, const uint32_t* __restrict__ occ,
-                             uint32_t primary, uint32_t L2a, uint32_t L2c, uint32_t L2g, uint32_t L2t) {
+                             IdxT primary, L2Vals<IdxT> L2) {
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_parent; p += gridDim.x * blockDim.x) {
         const uint4 ik = parent[p];   // x0, x1, x2
-        uint32_t tk[4], tl[4];
-        occ4_scalar(occ, primary, ik.y - 1, tk);
-        occ4_scalar(occ, primary, ik.y - 1 + ik.z, tl);
-        const uint32_t L2[4] = {L2a, L2c, L2g, L2t};
-        uint32_t x1[4], sz[4], x0[4];
+        const IdxT ix0 = tab_x0<IdxT>(ik), ix1 = tab_x1<IdxT>(ik);
+        IdxT tk[4], tl[4];
+        occ4_scalar<IdxT>(occ, primary, ix1 - 1, tk);
+        occ4_scalar<IdxT>(occ, primary, ix1 - 1 + ik.z, tl);
+        IdxT x1[4], x0[4]; uint32_t sz[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { x1[c] = L2[c] + 1 + tk[c]; sz[c] = tl[c] - tk[c]; }
-        x0[3] = ik.x + (uint32_t)(ik.y <= primary && ik.y + ik.z - 1 >= primary);
+        for (int c = 0; c < 4; ++c) { x1[c] = L2.v[c] + 1 + tk[c]; sz[c] = (uint32_t)(tl[c] - tk[c]); }
+        x0[3] = ix0 + (IdxT)(ix1 <= primary && ix1 + ik.z - 1 >= primary);
         x0[2] = x0[3] + sz[3]; x0[1] = x0[2] + sz[2]; x0[0] = x0[1] + sz[1];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {   // appending base b = taking ok[3 - b] of a forward extension
             const int c = 3 - b;
-            child[(size_t)p * 4 + b] = make_uint4(x0[c], x1[c], ik.z ? sz[c] : 0u, 0u);
+            child[(size_t)p * 4 + b] = tab_entry(x0[c], x1[c], ik.z ? sz[c] : 0u);
         }
     }
 }
-__global__ void k_kmer_level0(uint4* out, uint32_t L2a, uint32_t L2c, uint32_t L2g, uint32_t L2t, uint32_t L2n) {
-    const uint32_t L2[5] = {L2a, L2c, L2g, L2t, L2n};
+template <class IdxT>
+__global__ void k_kmer_level0(uint4* out, L2Vals<IdxT> L2) {
     const int c = threadIdx.x;
-    if (c < 4) out[c] = make_uint4(L2[c] + 1, L2[3 - c] + 1, L2[c + 1] - L2[c], 0u);
+    if (c < 4) out[c] = tab_entry(L2.v[c] + 1, L2.v[3 - c] + 1, (uint32_t)(L2.v[c + 1] - L2.v[c]));
 }
 
-__global__ void k_build_isa(const uint32_t* __restrict__ sa, uint64_t rows, uint32_t* __restrict__ isa) {
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (uint64_t)gridDim.x * blockDim.x) isa[sa[r]] = (uint32_t)r;
+template <class IdxT>
+__global__ void k_build_isa(const IdxT* __restrict__ sa, uint64_t rows, IdxT* __restrict__ isa) {
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (uint64_t)gridDim.x * blockDim.x) isa[sa[r]] = (IdxT)r;
 }
 
 // sort a read's intervals by info (ties are bit-identical records, so any correct sort equals ks_introsort's result)
@@ -667,7 +688,7 @@ __global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 4 
     unsigned long long n_ext = 0;
     Ctx<IdxT> C;
     C.occ = ix.occ; C.sL2 = sL2p; C.primary = (IdxT)ix.primary; C.kmer_tab = P.kmer_tab; C.kk = P.kmer_k; C.lane = lane;
-    C.sa = reinterpret_cast<const uint32_t*>(ix.sa); C.isa = sizeof(IdxT) == 4 ? P.isa : nullptr; C.pac = ix.pac; C.l_pac = (uint32_t)ix.l_pac; C.n = (uint32_t)ix.seq_len;
+    C.sa = reinterpret_cast<const IdxT*>(ix.sa); C.isa = reinterpret_cast<const IdxT*>(P.isa); C.pac = ix.pac; C.l_pac = (IdxT)ix.l_pac; C.n = (IdxT)ix.seq_len;
     {
         const int idx = lane & 15;
         C.sym_base = idx >= 8 ? (uint32_t)((idx - 8) << 4) : (1u << 20);
@@ -696,7 +717,7 @@ __global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 4 
                 __syncwarp();
                 // 2-bit packed copy of the read (16 bases per word, MSB first) for k-mer indices of arbitrary substrings
                 uint32_t* pk = nullptr;
-                if (sizeof(IdxT) == 4 && C.kmer_tab) {
+                if (C.kmer_tab) {
                     pk = reinterpret_cast<uint32_t*>(sq + ((len + 15) & ~15));
                     for (int w = lane; w <= (len >> 4) + 1; w += 32) {
                         uint32_t v = 0;
@@ -744,26 +765,33 @@ int kmer_table_depth(uint64_t n) {
     return k;
 }
 
-// builds levels 1..k of the prefix table into `tab` (kmer_table_bytes(k)).  32-bit indices only.
-void build_kmer_table(const DevIndex& ix, void* tab, int k, cudaStream_t st, uint64_t* launches) {
+// builds levels 1..k of the prefix table into `tab` (kmer_table_bytes(k)); rows of up to 40 bits
+template <class IdxT>
+static void build_kmer_table_t(const DevIndex& ix, void* tab, int k, cudaStream_t st, uint64_t* launches) {
     uint4* base = reinterpret_cast<uint4*>(tab);
-    const uint32_t L2a = (uint32_t)ix.L2[0], L2c = (uint32_t)ix.L2[1], L2g = (uint32_t)ix.L2[2], L2t = (uint32_t)ix.L2[3], L2n = (uint32_t)ix.L2[4];
-    k_kmer_level0<<<1, 32, 0, st>>>(base + kmer_level_off(1), L2a, L2c, L2g, L2t, L2n);
+    L2Vals<IdxT> L2;
+    for (int c = 0; c < 5; ++c) L2.v[c] = (IdxT)ix.L2[c];
+    k_kmer_level0<IdxT><<<1, 32, 0, st>>>(base + kmer_level_off(1), L2);
     if (launches) ++*launches;
     uint32_t n = 4;
     for (int t = 2; t <= k; ++t) {
         const unsigned blocks = (unsigned)std::min<uint32_t>((n + 255) / 256, 148u * 16u);
-        k_kmer_level<<<blocks ? blocks : 1, 256, 0, st>>>(base + kmer_level_off(t - 1), base + kmer_level_off(t), n, ix.occ, (uint32_t)ix.primary, L2a, L2c, L2g, L2t);
+        k_kmer_level<IdxT><<<blocks ? blocks : 1, 256, 0, st>>>(base + kmer_level_off(t - 1), base + kmer_level_off(t), n, ix.occ, (IdxT)ix.primary, L2);
         if (launches) ++*launches;
         n *= 4;
     }
 }
+void build_kmer_table(const DevIndex& ix, void* tab, int k, cudaStream_t st, uint64_t* launches) {
+    if (ix.sa_bytes == 8) build_kmer_table_t<uint64_t>(ix, tab, k, st, launches);
+    else build_kmer_table_t<uint32_t>(ix, tab, k, st, launches);
+}
 
-// inverse suffix array (32-bit rows): isa[SA[r]] = r for the n + 1 rows; `isa` holds n + 1 entries
-void build_isa(const DevIndex& ix, uint32_t* isa, cudaStream_t st, uint64_t* launches) {
+// inverse suffix array: isa[SA[r]] = r for the n + 1 rows; `isa` holds n + 1 entries of ix.sa_bytes bytes
+void build_isa(const DevIndex& ix, void* isa, cudaStream_t st, uint64_t* launches) {
     const uint64_t rows = ix.seq_len + 1;
     const unsigned blocks = (unsigned)std::min<uint64_t>((rows + 255) / 256, 148ull * 16);
-    k_build_isa<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(ix.sa), rows, isa);
+    if (ix.sa_bytes == 8) k_build_isa<uint64_t><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint64_t*>(ix.sa), rows, reinterpret_cast<uint64_t*>(isa));
+    else k_build_isa<uint32_t><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(ix.sa), rows, reinterpret_cast<uint32_t*>(isa));
     if (launches) ++*launches;
 }
 

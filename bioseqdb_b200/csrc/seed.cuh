@@ -17,9 +17,9 @@ struct SeedParams {
     uint32_t list_cap;
     int lists_in_smem;        // narrow path: the two interval lists of a warp and the read live in shared memory
     uint32_t read_cap;        // bytes reserved per warp for the staged read (>= longest read, multiple of 16)
-    const uint4* kmer_tab;    // prefix table: bi-intervals of all t-mers, t <= kmer_k (32-bit indices only), or nullptr
+    const uint4* kmer_tab;    // prefix table: bi-intervals of all t-mers, t <= kmer_k (rows of up to 40 bits), or nullptr
     int kmer_k;
-    const uint32_t* isa;      // inverse suffix array for the unique-match shortcut (32-bit rows), or nullptr
+    const void* isa;          // inverse suffix array for the unique-match shortcut (rows as wide as the SA's), or nullptr
     uint32_t* ticket;
     uint32_t* overflow;       // set to 1 when a read needs more than cap intervals
     unsigned long long* n_extend;  // optional counter (roofline units); nullptr in production
@@ -28,6 +28,6 @@ void launch_seed(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cuda
 int seed_resident_warps();
 size_t kmer_table_bytes(int k);
 int kmer_table_depth(uint64_t n);
-void build_isa(const DevIndex& ix, uint32_t* isa, cudaStream_t st, uint64_t* launches);
+void build_isa(const DevIndex& ix, void* isa, cudaStream_t st, uint64_t* launches);
 void build_kmer_table(const DevIndex& ix, void* tab, int k, cudaStream_t st, uint64_t* launches);
 bool seed_lists_fit_smem(uint32_t list_cap, uint32_t read_cap, int sa_bytes);

@@ -433,7 +433,7 @@ int ensure_kmer_table(bsq_index* h, const DevIndex& ix) {
     }
     if (h->d_kmer || ix.seq_len < (1u << 16) || getenv("BSQ_NO_KMER")) return BSQ_OK;
     h->kmer_k = kmer_table_depth(ix.seq_len);
-    if (const char* e = getenv("BSQ_KMER_K")) { const int k = atoi(e); if (k >= 8 && k <= 14) h->kmer_k = k; }
+    if (const char* e = getenv("BSQ_KMER_K")) { const int k = atoi(e); if (k >= 8 && k <= 15) h->kmer_k = k; }
     CUDA_CHECK(cudaMalloc(&h->d_kmer, kmer_table_bytes(h->kmer_k)));
     build_kmer_table(ix, h->d_kmer, h->kmer_k, h->stream, &h->timing.launches);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
@@ -501,9 +501,10 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
     ENS(b.ctl.ensure(64));
     // the thread-per-extension pre-pass packs column scores in 16 bits: every value it stores is <= l_query * (a + 1)
     static const bool no_memo = getenv("BSQ_NO_EXT_MEMO") != nullptr;
-    const bool use_memo = !no_memo && max_len <= 512 && (uint64_t)max_len * (uint64_t)(o.a + 1) < 32000;
+    const bool use_memo = !no_memo && max_len <= 512 && (uint64_t)max_len * (uint64_t)(o.a + 1) < 32000 && (uint64_t)n * EXT_MEMO_CHAINS < (1ull << 31);
     if (use_memo) {
-        ENS(b.ext_memo.ensure((size_t)n * 2)); ENS(b.ext_memo_key.ensure((size_t)n * 2)); ENS(b.ext_memo_perm.ensure((size_t)n * 2));
+        const size_t jobs2 = (size_t)n * EXT_MEMO_CHAINS * 2;
+        ENS(b.ext_memo.ensure(jobs2)); ENS(b.ext_memo_key.ensure(jobs2)); ENS(b.ext_memo_perm.ensure(jobs2));
         ENS(b.ext_memo_hist.ensure(6 * EXT_MEMO_BINS)); ENS(b.ext_todo.ensure(n));
         if (!b.ext_aux_ok) {
             for (auto& s_ : b.ext_aux.st) ENS(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));

@@ -141,8 +141,8 @@ __device__ __forceinline__ bool extend_read(const ExtendParams& P, const DevInde
                         int prev = a.score;
                         aw0 = o.w << i;
                         bool hit = false;
-                        if (i == 0 && P.memo && n_reg == 0) {
-                            const ExtMemo* M = P.memo + r;
+                        if (i == 0 && P.memo && k == n - 1 && ci < (uint32_t)EXT_MEMO_CHAINS) {
+                            const ExtMemo* M = P.memo + (size_t)r * EXT_MEMO_CHAINS + ci;
                             if (M->state == 2 && M->qlen == s.qbeg && M->tlen == tl && M->h0 == s.len * o.a && M->tpos == s.rbeg - 1) {
                                 e.score = M->out[0]; e.qle = M->out[1]; e.tle = M->out[2]; e.gtle = M->out[3]; e.gscore = M->out[4]; e.max_off = M->out[5];
                                 hit = true;
@@ -172,8 +172,8 @@ __device__ __forceinline__ bool extend_read(const ExtendParams& P, const DevInde
                         int prev = a.score;
                         aw1 = o.w << i;
                         bool hit = false;
-                        if (i == 0 && P.memo && n_reg == 0) {
-                            const ExtMemo* M = P.memo + (size_t)P.n_reads + r;
+                        if (i == 0 && P.memo && k == n - 1 && ci < (uint32_t)EXT_MEMO_CHAINS) {
+                            const ExtMemo* M = P.memo + ((size_t)P.n_reads + r) * EXT_MEMO_CHAINS + ci;
                             if (M->state == 2 && M->qlen == l_query - qe && M->tlen == tl && M->h0 == sc0 && M->tpos == rmax0 + re) {
                                 e.score = M->out[0]; e.qle = M->out[1]; e.tle = M->out[2]; e.gtle = M->out[3]; e.gscore = M->out[4]; e.max_off = M->out[5];
                                 hit = true;

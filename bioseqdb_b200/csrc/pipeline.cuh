@@ -42,12 +42,13 @@ struct ExtMemo {
 };
 static_assert(sizeof(ExtMemo) == 48, "ExtMemo layout");
 constexpr int EXT_MEMO_MAXQ = 136;     // longest query side the thread kernels take
+constexpr int EXT_MEMO_CHAINS = 4;     // chains per read whose first extension is planned; job id = read * EXT_MEMO_CHAINS + chain
 constexpr int EXT_MEMO_CLASSES = 4;    // job classes by query length (<= 32, 64, 96, 136 columns): shared memory per thread differs
 
 struct ExtendParams {
     const uint8_t* seqs; const uint64_t* offs; uint32_t n_reads;
-    // thread-per-extension pre-pass (nullptr = off): memo[0 .. n) left sides, memo[n .. 2n) right sides; key[side * n + r] = query
-    // length of the planned job (0 = none); perm[side * n + ...] = reads sorted by key; hist = 2 x 160 bin counts, then 2 x 160
+    // thread-per-extension pre-pass (nullptr = off), J = n_reads * EXT_MEMO_CHAINS jobs: memo[0 .. J) left sides, memo[J .. 2J) right
+    // sides; key[side * J + job] = query length of the planned job (0 = none); perm[side * J + ...] = jobs sorted by key; hist = 2 x 160 bin counts, then 2 x 160
     // bin starts, then 2 x 160 scatter cursors (zeroed by the host before the launch)
     ExtMemo* memo; uint8_t* memo_key; uint32_t* memo_perm; uint32_t* memo_hist;
     // reads the thread-per-read pass (ext_finish) could not complete, for sw_extend (nullptr = sw_extend takes every read)

@@ -13,6 +13,7 @@
 // halves, i.e. two more single-contributor reductions.  Interval lists and the read live in shared memory.
 #include "seed.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -20,8 +21,8 @@ constexpr int SEED_THREADS = 256;
 constexpr int SEED_WARPS = SEED_THREADS / 32;
 // prefix table: bi-intervals of every t-mer, t = 1..K, levels back to back.  K is chosen per index, about log4 of the text
 // length, so that a K-mer has a handful of occurrences at most: 12 -> 358 MB, 13 -> 1.4 GB, 14 -> 5.7 GB (of 180 GB HBM)
-constexpr int KMER_K_MAX = 14;
-__host__ __device__ constexpr uint32_t kmer_level_off(int t) { return ((1u << (2 * t)) - 4u) / 3u; }   // first entry of level t
+constexpr int KMER_K_MAX = 14;      // automatic choice; BSQ_KMER_K may ask for 15 (23 GB)
+__host__ __device__ constexpr uint32_t kmer_level_off(int t) { return (uint32_t)(((1ull << (2 * t)) - 4ull) / 3ull); }   // first entry of level t
 
 template <class IdxT> struct IvT { IdxT x0, x1; uint32_t x2, info; };   // info = end of the match on the query
 // prefix-table entry {x0 low word, x1 low word, x2, hi}: hi = bits 32..39 of x0 | bits 32..39 of x1 << 8 (zero while rows fit 32 bits)
@@ -666,8 +667,8 @@ __device__ void sort_by_info(Intv* out, uint32_t n_out, Intv* tmp, uint32_t tmp_
 
 // IdxT = uint32_t while the text has fewer than 2^32 rows; SMEM: interval lists and the read staged in shared
 // memory (otherwise in the per-warp global scratch: reads too long for shared memory)
-template <class IdxT, bool SMEM>
-__global__ void __launch_bounds__(SEED_THREADS, (sizeof(IdxT) == 4 && SMEM) ? 4 : 1) seed_smem(SeedParams P, DevIndex ix, DevOpts o) {
+template <class IdxT, bool SMEM, int MINB>
+__global__ void __launch_bounds__(SEED_THREADS, MINB) seed_smem(SeedParams P, DevIndex ix, DevOpts o) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ IdxT sL2[8];
     __shared__ IvT<IdxT> s_hand[SEED_WARPS][4];   // hand-off slots of the grouped backward extensions
@@ -742,16 +743,16 @@ template <class IdxT> size_t lists_bytes(uint32_t list_cap, uint32_t read_cap) {
     return (size_t)SEED_WARPS * (2 * (size_t)list_cap * sizeof(IvT<IdxT>) + read_cap);
 }
 
-template <class IdxT, bool SMEM> void launch_mode(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, size_t smem, int* n_warps_out) {
+template <class IdxT, bool SMEM, int MINB> void launch_mode(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, size_t smem, int* n_warps_out) {
     int dev = 0, sms = 148, nb = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(seed_smem<IdxT, SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seed_smem<IdxT, SMEM>, SEED_THREADS, smem);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(seed_smem<IdxT, SMEM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seed_smem<IdxT, SMEM, MINB>, SEED_THREADS, smem);
     if (nb < 1) nb = 1;
     if (nb * SEED_WARPS > 64) nb = 64 / SEED_WARPS;
     if (n_warps_out) *n_warps_out = nb * sms * SEED_WARPS;
-    seed_smem<IdxT, SMEM><<<nb * sms, SEED_THREADS, smem, st>>>(p, ix, o);
+    seed_smem<IdxT, SMEM, MINB><<<nb * sms, SEED_THREADS, smem, st>>>(p, ix, o);
 }
 
 }  // namespace
@@ -811,10 +812,13 @@ bool seed_lists_fit_smem(uint32_t list_cap, uint32_t read_cap, int sa_bytes) {
 void launch_seed(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, int* n_warps_out) {
     const bool wide = ix.sa_bytes == 8;   // 64-bit row indices
     if (wide) {
-        if (p.lists_in_smem) launch_mode<uint64_t, true>(p, ix, o, st, lists_bytes<uint64_t>(p.list_cap, p.read_cap), n_warps_out);
-        else launch_mode<uint64_t, false>(p, ix, o, st, 0, n_warps_out);
+        static const int ctas = getenv("BSQ_SEED_WIDE_CTAS") ? atoi(getenv("BSQ_SEED_WIDE_CTAS")) : 3;
+        if (p.lists_in_smem) {
+            if (ctas >= 3) launch_mode<uint64_t, true, 3>(p, ix, o, st, lists_bytes<uint64_t>(p.list_cap, p.read_cap), n_warps_out);
+            else launch_mode<uint64_t, true, 2>(p, ix, o, st, lists_bytes<uint64_t>(p.list_cap, p.read_cap), n_warps_out);
+        } else launch_mode<uint64_t, false, 1>(p, ix, o, st, 0, n_warps_out);
     } else {
-        if (p.lists_in_smem) launch_mode<uint32_t, true>(p, ix, o, st, lists_bytes<uint32_t>(p.list_cap, p.read_cap), n_warps_out);
-        else launch_mode<uint32_t, false>(p, ix, o, st, 0, n_warps_out);
+        if (p.lists_in_smem) launch_mode<uint32_t, true, 4>(p, ix, o, st, lists_bytes<uint32_t>(p.list_cap, p.read_cap), n_warps_out);
+        else launch_mode<uint32_t, false, 1>(p, ix, o, st, 0, n_warps_out);
     }
 }

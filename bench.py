@@ -340,7 +340,16 @@ def run_ours(args, rank, world, local_rank):
         ext_s = stage["extend"] / args.steps * 1e-3
         fin_s = stage["finalize"] / args.steps * 1e-3
         sw = {"ksw_extend2_gcups": ctr["ext_cells"] / ext_s / 1e9, "ksw_global2_gcups_incl_finalize": ctr["glb_cells"] / fin_s / 1e9,
-              "ext_cells_per_launch": ctr["ext_cells"], "glb_cells_per_launch": ctr["glb_cells"], "dpx_peak_ginstr_s": dpx.value}
+              "ext_cells_per_launch": ctr["ext_cells"], "glb_cells_per_launch": ctr["glb_cells"], "dpx_peak_ginstr_s": dpx.value,
+              # DPX fraction = DPX instructions per cell of the shipped kernel (ksw_thread.cuh: one __vimax3_s32 and two
+              # __viaddmax_s32_relu) x cells/s over the whole extension stage, against the measured DPX issue peak
+              "ksw_extend2_dpx_per_cell": 3, "ksw_extend2_dpx_frac_of_peak": 3 * ctr["ext_cells"] / ext_s / 1e9 / dpx.value}
+        # row materialisation: NUCLSEQ images of ref_subseq / query_subseq + CIGAR strings of rank 0's rows, on the GPU
+        t0 = time.time()
+        tup = ix.tuples(res, seqs, offs)
+        tup_wall = time.time() - t0
+        tuples = {"rows": total_rows, "bytes": int(len(tup.data)), "device_ms_incl_copies": tup.device_ms, "wall_ms_python": 1e3 * tup_wall,
+                  "rows_per_s_device": total_rows / max(tup.device_ms * 1e-3, 1e-9)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
@@ -350,7 +359,7 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_ms_per_step": e2e_h2d_ms / args.steps, "d2h_ms_per_step": e2e_d2h_ms / args.steps},
             "gpu_launches": launches_all,
             "clocks": clocks,
-            "roofline": roof, "sw": sw,
+            "roofline": roof, "sw": sw, "tuples": tuples,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "wall_ms_per_step": 1e3 * wall_max / args.steps,
             "rows_per_step_rank0": total_rows, "truth_match_frac_rank0": truth_frac, "rows_sha1_rank0": rows_digest,

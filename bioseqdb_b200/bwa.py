@@ -63,6 +63,34 @@ class AlignResult:
         return cigar_to_string(self.cigar[int(row["cigar_off"]):int(row["cigar_off"]) + int(row["n_cigar"])])
 
 
+def nuclseq_image(s) -> bytes:
+    """The NUCLSEQ datum as PostgreSQL stores it (sequence.h:18-38, alloc_raw_nucls sequence.cpp:59-69): varlena length word of an
+    uncompressed 4-byte header, holes_num, len, the hole records, the packed codes."""
+    import struct
+    body = s.holes.tobytes() + s.pac.tobytes()
+    return struct.pack("<III", (12 + len(body)) << 2, len(s.holes), s.len) + body
+
+
+class Tuples:
+    """Result of BwaIndex.tuples: per row: images at off[3i] and off[3i+1], NUL-terminated CIGAR string at off[3i+2]."""
+
+    def __init__(self, off, ref_match, data, device_ms):
+        self.off, self.ref_match, self.data, self.device_ms = off, ref_match, data, device_ms
+
+    def _image(self, at: int) -> bytes:
+        size = int(np.frombuffer(self.data[at:at + 4].tobytes(), dtype="<u4")[0]) >> 2
+        return self.data[at:at + size].tobytes()
+
+    def ref_subseq(self, i: int) -> bytes:
+        return self._image(int(self.off[3 * i]))
+
+    def query_subseq(self, i: int) -> bytes:
+        return self._image(int(self.off[3 * i + 1]))
+
+    def cigar(self, i: int) -> str:
+        return self.data[int(self.off[3 * i + 2]):int(self.off[3 * i + 3])].tobytes().split(b"\0", 1)[0].decode()
+
+
 class BwaIndex:
     """BwaIndex of bioseqdb/bwa.h:32-48 over libbioseqdb_gpu.so."""
 
@@ -214,6 +242,33 @@ class BwaIndex:
         res = C.POINTER(BsqResult)()
         check(self.L.bsq_result_download(self.h, C.byref(res)))
         return self._collect(res)
+
+    def tuples(self, res: AlignResult, seqs: np.ndarray, offs: np.ndarray) -> "Tuples":
+        """Row materialisation on the GPU: for every row of `res` the NUCLSEQ datum images of ref_subseq and
+        query_subseq, the CIGAR string and ref_match_* -- what build_tuple_bwa (extension.cpp:282-305) assembles from a BwaMatch."""
+        from ._lib import BsqTuples
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        row_off = np.ascontiguousarray(res.row_off, dtype=np.uint64)
+        rows = np.ascontiguousarray(res.rows)
+        cigar = np.ascontiguousarray(res.cigar, dtype=np.uint32)
+        r = BsqResult()
+        r.n_reads = len(row_off) - 1
+        r.row_off = row_off.ctypes.data_as(C.POINTER(C.c_uint64))
+        r.rows = rows.ctypes.data
+        r.cigar = cigar.ctypes.data_as(C.POINTER(C.c_uint32))
+        r.n_cigar_words = len(cigar)
+        tp = C.POINTER(BsqTuples)()
+        check(self.L.bsq_result_tuples(self.h, C.byref(r), ptr(seqs), ptr(offs), C.byref(tp)))
+        t = tp.contents
+        n = int(t.n_rows)
+        off = np.ctypeslib.as_array(t.off, shape=(3 * n + 1,)).copy()
+        ref_match = np.ctypeslib.as_array(t.ref_match, shape=(max(3 * n, 1),))[:3 * n].copy().reshape(n, 3)
+        nb = int(t.n_bytes)
+        data = np.ctypeslib.as_array(t.bytes, shape=(max(nb, 1),))[:nb].copy()
+        ms = float(t.device_ms)
+        self.L.bsq_tuples_free(tp)
+        return Tuples(off, ref_match, data, ms)
 
     def timing(self) -> BsqTiming:
         t = BsqTiming()

@@ -15,6 +15,7 @@
 #include "index_build.cuh"
 #include "seed.cuh"
 #include "pipeline.cuh"
+#include "tuples.cuh"
 #include "primitives.cuh"
 #include "debug_kernels.cuh"
 
@@ -897,6 +898,105 @@ int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const 
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
     return rc;
+}
+
+// ---- row materialisation
+struct TuplesImpl { bsq_tuples pub; void* host = nullptr; size_t host_bytes = 0; };
+
+int bsq_result_tuples(bsq_index* h, const bsq_result* res, const char* seqs, const uint64_t* offs, bsq_tuples** out) {
+    if (!h || !res || !offs || !out) { bsq_set_error("null argument"); return BSQ_ERR; }
+    if (!h->meta.built && res->n_reads && res->row_off[res->n_reads]) { bsq_set_error("index not built"); return BSQ_ERR; }
+    CUDA_CHECK(cudaSetDevice(h->device));
+    const uint64_t n_reads = res->n_reads, n_rows = n_reads ? res->row_off[n_reads] : 0;
+    TuplesImpl* T = new TuplesImpl();
+    T->pub.n_rows = n_rows; T->pub.n_bytes = 0; T->pub.device_ms = 0.f; T->pub.off = nullptr; T->pub.ref_match = nullptr; T->pub.bytes = nullptr;
+    if (n_rows == 0) {
+        T->host_bytes = 64;
+        if (cudaHostAlloc(&T->host, T->host_bytes, cudaHostAllocDefault) != cudaSuccess) { delete T; bsq_set_error("pinned allocation failed"); return BSQ_ERR; }
+        T->pub.off = reinterpret_cast<uint64_t*>(T->host); T->pub.off[0] = 0;
+        T->pub.ref_match = reinterpret_cast<int32_t*>(T->pub.off + 1); T->pub.bytes = reinterpret_cast<uint8_t*>(T->pub.off + 2);
+        *out = &T->pub;
+        return BSQ_OK;
+    }
+    if (!seqs) { delete T; bsq_set_error("null argument"); return BSQ_ERR; }
+    cudaStream_t st = h->stream;
+    // host-side preparation: read index of every row; the index's holes sorted by offset with the running maximum of their ends
+    std::vector<uint32_t> row_read(n_rows);
+    for (uint64_t r = 0; r < n_reads; ++r) for (uint64_t k = res->row_off[r]; k < res->row_off[r + 1]; ++k) row_read[k] = (uint32_t)r;
+    std::vector<TupleHole> holes(h->holes.size());
+    for (size_t i = 0; i < holes.size(); ++i) { holes[i].offset = h->holes[i].offset; holes[i].end = h->holes[i].offset + h->holes[i].len; holes[i].idx = (uint32_t)i; holes[i].amb = (uint8_t)h->holes[i].amb; }
+    std::stable_sort(holes.begin(), holes.end(), [](const TupleHole& a, const TupleHole& b) { return a.offset < b.offset; });
+    std::vector<int64_t> maxend(holes.size());
+    for (size_t i = 0; i < holes.size(); ++i) maxend[i] = i ? std::max(maxend[i - 1], holes[i].end) : holes[i].end;
+    const uint64_t total = offs[n_reads] - offs[0];
+    RowDev* d_rows = nullptr; uint32_t *d_row_read = nullptr, *d_cigar = nullptr, *d_nholes = nullptr; uint8_t *d_seqs = nullptr, *d_bytes = nullptr;
+    uint64_t *d_offs = nullptr, *d_off = nullptr, *d_tmp = nullptr; TupleHole* d_holes = nullptr; int64_t* d_maxend = nullptr; int32_t* d_rm = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = BSQ_ERR;
+    do {
+#define TC(x) if ((x) != cudaSuccess) { bsq_set_error("bsq_result_tuples: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        TC(cudaEventCreate(&e0)); TC(cudaEventCreate(&e1));
+        TC(cudaMalloc(&d_rows, n_rows * sizeof(RowDev))); TC(cudaMalloc(&d_row_read, n_rows * 4)); TC(cudaMalloc(&d_cigar, (res->n_cigar_words + 1) * 4));
+        TC(cudaMalloc(&d_seqs, total + 64)); TC(cudaMalloc(&d_offs, (n_reads + 1) * 8)); TC(cudaMalloc(&d_nholes, n_rows * 8));
+        TC(cudaMalloc(&d_off, (3 * n_rows + 1) * 8)); TC(cudaMalloc(&d_tmp, tuple_scan_tmp_elems(n_rows) * 8)); TC(cudaMalloc(&d_rm, n_rows * 12));
+        TC(cudaMalloc(&d_holes, (holes.size() + 1) * sizeof(TupleHole))); TC(cudaMalloc(&d_maxend, (holes.size() + 1) * 8));
+        std::vector<uint64_t> rel(n_reads + 1);
+        for (uint64_t i = 0; i <= n_reads; ++i) rel[i] = offs[i] - offs[0];
+        cudaEventRecord(e0, st);
+        TC(cudaMemcpyAsync(d_rows, res->rows, n_rows * sizeof(RowDev), cudaMemcpyHostToDevice, st));
+        TC(cudaMemcpyAsync(d_row_read, row_read.data(), n_rows * 4, cudaMemcpyHostToDevice, st));
+        if (res->n_cigar_words) TC(cudaMemcpyAsync(d_cigar, res->cigar, res->n_cigar_words * 4, cudaMemcpyHostToDevice, st));
+        if (total) TC(cudaMemcpyAsync(d_seqs, seqs + offs[0], total, cudaMemcpyHostToDevice, st));
+        TC(cudaMemcpyAsync(d_offs, rel.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (!holes.empty()) {
+            TC(cudaMemcpyAsync(d_holes, holes.data(), holes.size() * sizeof(TupleHole), cudaMemcpyHostToDevice, st));
+            TC(cudaMemcpyAsync(d_maxend, maxend.data(), holes.size() * 8, cudaMemcpyHostToDevice, st));
+        }
+        TC(cudaMemsetAsync(d_off, 0, (3 * n_rows + 1) * 8, st));
+        TupleParams P;
+        P.rows = d_rows; P.n_rows = n_rows; P.row_read = d_row_read; P.cigar = d_cigar; P.seqs = d_seqs; P.offs = d_offs;
+        P.pac = h->d_pac; P.l_pac = h->meta.l_pac; P.ann_offset = h->d_ann_offset;
+        P.holes = d_holes; P.hole_maxend = d_maxend; P.n_holes = (uint32_t)holes.size();
+        P.nholes = d_nholes; P.off = d_off; P.ref_match = d_rm; P.bytes = nullptr;
+        launch_tuple_sizes(P, d_tmp, st, &h->timing.launches);
+        uint64_t n_bytes = 0;
+        TC(cudaMemcpyAsync(&n_bytes, d_off + 3 * n_rows, 8, cudaMemcpyDeviceToHost, st));
+        TC(cudaStreamSynchronize(st));
+        TC(cudaMalloc(&d_bytes, n_bytes + 64));
+        TC(cudaMemsetAsync(d_bytes, 0, n_bytes + 64, st));
+        P.bytes = d_bytes;
+        launch_tuple_fill(P, st, &h->timing.launches);
+        // one pinned block: off | ref_match | bytes
+        const size_t off_b = (3 * n_rows + 1) * 8, rm_b = (n_rows * 12 + 7) & ~(size_t)7;
+        T->host_bytes = off_b + rm_b + n_bytes + 64;
+        TC(cudaHostAlloc(&T->host, T->host_bytes, cudaHostAllocDefault));
+        T->pub.off = reinterpret_cast<uint64_t*>(T->host);
+        T->pub.ref_match = reinterpret_cast<int32_t*>(static_cast<char*>(T->host) + off_b);
+        T->pub.bytes = reinterpret_cast<uint8_t*>(static_cast<char*>(T->host) + off_b + rm_b);
+        T->pub.n_bytes = n_bytes;
+        TC(cudaMemcpyAsync(T->pub.off, d_off, off_b, cudaMemcpyDeviceToHost, st));
+        TC(cudaMemcpyAsync(T->pub.ref_match, d_rm, n_rows * 12, cudaMemcpyDeviceToHost, st));
+        if (n_bytes) TC(cudaMemcpyAsync(T->pub.bytes, d_bytes, n_bytes, cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(e1, st);
+        TC(cudaStreamSynchronize(st)); TC(cudaGetLastError());
+        cudaEventElapsedTime(&T->pub.device_ms, e0, e1);
+        rc = BSQ_OK;
+#undef TC
+    } while (0);
+    cudaFree(d_rows); cudaFree(d_row_read); cudaFree(d_cigar); cudaFree(d_seqs); cudaFree(d_offs); cudaFree(d_nholes); cudaFree(d_off); cudaFree(d_tmp);
+    cudaFree(d_rm); cudaFree(d_holes); cudaFree(d_maxend); cudaFree(d_bytes);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (rc != BSQ_OK) { if (T->host) cudaFreeHost(T->host); delete T; return BSQ_ERR; }
+    *out = &T->pub;
+    return BSQ_OK;
+}
+
+void bsq_tuples_free(bsq_tuples* t) {
+    if (!t) return;
+    TuplesImpl* T = reinterpret_cast<TuplesImpl*>(t);
+    if (T->host) cudaFreeHost(T->host);
+    delete T;
 }
 
 void bsq_result_free(bsq_result* r) {

@@ -81,6 +81,24 @@ int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const 
 void bsq_result_free(bsq_result* r);
 int bsq_last_timing(const bsq_index* h, bsq_timing* t);
 
+/* Row materialisation: the variable-length columns of the bwa_result tuple for every row of `res`, built on the
+ * GPU.  Replaces, per row, extract_reference_subseq (bwa.cpp:55-68), cigar_compressed_to_string (bwa.cpp:70-77), the int32
+ * ref_match_* arithmetic (bwa.cpp:171-173) and the two nuclseq_from_text calls of build_tuple_bwa (extension.cpp:285,290).
+ * For row i: bytes + off[3i] = NUCLSEQ datum image of ref_subseq (varlena length word, holes_num, len, hole records, 2-bit codes;
+ * 8-byte aligned, its true size is in the length word), bytes + off[3i+1] = image of query_subseq, bytes + off[3i+2] = the
+ * NUL-terminated CIGAR string; ref_match[3i .. 3i+2] = ref_match_begin, ref_match_end, ref_match_len.
+ * seqs/offs: the reads `res` was computed from (ASCII, as given to bsq_align_batch). */
+typedef struct bsq_tuples {
+    uint64_t n_rows;
+    uint64_t* off;       /* 3 n_rows + 1 */
+    int32_t* ref_match;  /* 3 n_rows */
+    uint8_t* bytes;
+    uint64_t n_bytes;
+    float device_ms;     /* kernels + copies of this call */
+} bsq_tuples;
+int bsq_result_tuples(bsq_index* h, const bsq_result* res, const char* seqs, const uint64_t* offs, bsq_tuples** out);
+void bsq_tuples_free(bsq_tuples* t);
+
 /* Resident-input variant used by bench.py's `value` leg: upload once, run the kernels with inputs and
  * outputs resident in HBM, download on request. */
 int bsq_reads_upload(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n);

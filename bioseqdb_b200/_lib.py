@@ -85,7 +85,7 @@ def lib():
     L.bsq_align_batch.argtypes = [vp, vp, vp, vp, u64, C.POINTER(C.POINTER(BsqResult))]
     L.bsq_result_free.argtypes = [C.POINTER(BsqResult)]
     L.bsq_last_timing.argtypes = [vp, C.POINTER(BsqTiming)]
-    L.bsq_result_tuples.argtypes = [vp, C.POINTER(BsqResult), vp, vp, C.POINTER(C.POINTER(BsqTuples))]
+    L.bsq_result_tuples.argtypes = [vp, C.POINTER(BsqResult), vp, vp, u32, C.POINTER(C.POINTER(BsqTuples))]
     L.bsq_tuples_free.argtypes = [C.POINTER(BsqTuples)]
     L.bsq_reads_upload.argtypes = [vp, vp, vp, vp, u64]
     L.bsq_align_resident.argtypes = [vp]

@@ -71,6 +71,9 @@ def nuclseq_image(s) -> bytes:
     return struct.pack("<III", (12 + len(body)) << 2, len(s.holes), s.len) + body
 
 
+TUPLES_FIX_HOLE_OFFSETS, TUPLES_FIX_REVERSE = 1, 2   # opt-in fix-ups of bsq_result_tuples
+
+
 class Tuples:
     """Result of BwaIndex.tuples: per row: images at off[3i] and off[3i+1], NUL-terminated CIGAR string at off[3i+2]."""
 
@@ -243,7 +246,7 @@ class BwaIndex:
         check(self.L.bsq_result_download(self.h, C.byref(res)))
         return self._collect(res)
 
-    def tuples(self, res: AlignResult, seqs: np.ndarray, offs: np.ndarray) -> "Tuples":
+    def tuples(self, res: AlignResult, seqs: np.ndarray, offs: np.ndarray, flags: int = 0) -> "Tuples":
         """Row materialisation on the GPU: for every row of `res` the NUCLSEQ datum images of ref_subseq and
         query_subseq, the CIGAR string and ref_match_* -- what build_tuple_bwa (extension.cpp:282-305) assembles from a BwaMatch."""
         from ._lib import BsqTuples
@@ -259,7 +262,7 @@ class BwaIndex:
         r.cigar = cigar.ctypes.data_as(C.POINTER(C.c_uint32))
         r.n_cigar_words = len(cigar)
         tp = C.POINTER(BsqTuples)()
-        check(self.L.bsq_result_tuples(self.h, C.byref(r), ptr(seqs), ptr(offs), C.byref(tp)))
+        check(self.L.bsq_result_tuples(self.h, C.byref(r), ptr(seqs), ptr(offs), int(flags), C.byref(tp)))
         t = tp.contents
         n = int(t.n_rows)
         off = np.ctypeslib.as_array(t.off, shape=(3 * n + 1,)).copy()

@@ -93,7 +93,7 @@ struct bsq_index {
     int device = 0;
     bsq_opts opts; DevOpts dopts;
     float mapQ_coef_len = 50.f, mapQ_coef_fac = 0.f;
-    std::vector<uint8_t> pac; std::vector<int64_t> ann_offset, ann_id; std::vector<int32_t> ann_len; std::vector<bsq_hole> holes;
+    std::vector<uint8_t> pac; std::vector<int64_t> ann_offset, ann_id; std::vector<int32_t> ann_len; std::vector<bsq_hole> holes; std::vector<uint32_t> hole_ann;   // hole_ann: reference row of every hole
     uint8_t* d_pac = nullptr; uint32_t* d_occ = nullptr; void* d_sa = nullptr; int64_t* d_ann_offset = nullptr; int32_t* d_ann_len = nullptr; int64_t* d_ann_id = nullptr;
     bsq_index_meta meta;
     cudaStream_t stream = nullptr;
@@ -175,7 +175,7 @@ int bsq_index_add_ref(bsq_index* h, int64_t id, const uint8_t* pac, uint32_t len
     h->ann_id.push_back(id);
     size_t nb = (size_t)len / 4 + (len % 4 != 0);
     h->pac.insert(h->pac.end(), pac, pac + nb);
-    for (uint32_t i = 0; i < n_holes; ++i) h->holes.push_back(holes[i]);
+    for (uint32_t i = 0; i < n_holes; ++i) { h->holes.push_back(holes[i]); h->hole_ann.push_back((uint32_t)h->ann_offset.size() - 1); }
     return BSQ_OK;
 }
 
@@ -903,7 +903,7 @@ int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const 
 // ---- row materialisation
 struct TuplesImpl { bsq_tuples pub; void* host = nullptr; size_t host_bytes = 0; };
 
-int bsq_result_tuples(bsq_index* h, const bsq_result* res, const char* seqs, const uint64_t* offs, bsq_tuples** out) {
+int bsq_result_tuples(bsq_index* h, const bsq_result* res, const char* seqs, const uint64_t* offs, uint32_t flags, bsq_tuples** out) {
     if (!h || !res || !offs || !out) { bsq_set_error("null argument"); return BSQ_ERR; }
     if (!h->meta.built && res->n_reads && res->row_off[res->n_reads]) { bsq_set_error("index not built"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
@@ -924,7 +924,11 @@ int bsq_result_tuples(bsq_index* h, const bsq_result* res, const char* seqs, con
     std::vector<uint32_t> row_read(n_rows);
     for (uint64_t r = 0; r < n_reads; ++r) for (uint64_t k = res->row_off[r]; k < res->row_off[r + 1]; ++k) row_read[k] = (uint32_t)r;
     std::vector<TupleHole> holes(h->holes.size());
-    for (size_t i = 0; i < holes.size(); ++i) { holes[i].offset = h->holes[i].offset; holes[i].end = h->holes[i].offset + h->holes[i].len; holes[i].idx = (uint32_t)i; holes[i].amb = (uint8_t)h->holes[i].amb; }
+    for (size_t i = 0; i < holes.size(); ++i) {
+        // reference behaviour: offsets as stored in the row's datum, i.e. relative to its own row (bwa.cpp:100-104); the fix-up rebases them
+        const int64_t base = (flags & BSQ_TUPLES_FIX_HOLE_OFFSETS) ? h->ann_offset[h->hole_ann[i]] : 0;
+        holes[i].offset = h->holes[i].offset + base; holes[i].end = holes[i].offset + h->holes[i].len; holes[i].idx = (uint32_t)i; holes[i].amb = (uint8_t)h->holes[i].amb;
+    }
     std::stable_sort(holes.begin(), holes.end(), [](const TupleHole& a, const TupleHole& b) { return a.offset < b.offset; });
     std::vector<int64_t> maxend(holes.size());
     for (size_t i = 0; i < holes.size(); ++i) maxend[i] = i ? std::max(maxend[i - 1], holes[i].end) : holes[i].end;
@@ -957,7 +961,7 @@ int bsq_result_tuples(bsq_index* h, const bsq_result* res, const char* seqs, con
         P.rows = d_rows; P.n_rows = n_rows; P.row_read = d_row_read; P.cigar = d_cigar; P.seqs = d_seqs; P.offs = d_offs;
         P.pac = h->d_pac; P.l_pac = h->meta.l_pac; P.ann_offset = h->d_ann_offset;
         P.holes = d_holes; P.hole_maxend = d_maxend; P.n_holes = (uint32_t)holes.size();
-        P.nholes = d_nholes; P.off = d_off; P.ref_match = d_rm; P.bytes = nullptr;
+        P.nholes = d_nholes; P.off = d_off; P.ref_match = d_rm; P.bytes = nullptr; P.fix_reverse = (flags & BSQ_TUPLES_FIX_REVERSE) != 0;
         launch_tuple_sizes(P, d_tmp, st, &h->timing.launches);
         uint64_t n_bytes = 0;
         TC(cudaMemcpyAsync(&n_bytes, d_off + 3 * n_rows, 8, cudaMemcpyDeviceToHost, st));

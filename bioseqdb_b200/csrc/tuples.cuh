@@ -18,6 +18,7 @@ struct TupleParams {
     uint64_t* off;                 // 3 per row + 1: sizes, then (after the scan) byte offsets of ref image / query image / CIGAR string
     int32_t* ref_match;            // 3 per row: ref_match_begin, ref_match_end, ref_match_len
     uint8_t* bytes;
+    bool fix_reverse;              // opt-in fix-up: reverse-strand hits are reported in forward-strand coordinates and text
 };
 size_t tuple_scan_tmp_elems(uint64_t n_rows);
 void launch_tuple_sizes(const TupleParams& P, uint64_t* scan_tmp, cudaStream_t st, uint64_t* launches);

@@ -96,7 +96,16 @@ typedef struct bsq_tuples {
     uint64_t n_bytes;
     float device_ms;     /* kernels + copies of this call */
 } bsq_tuples;
-int bsq_result_tuples(bsq_index* h, const bsq_result* res, const char* seqs, const uint64_t* offs, bsq_tuples** out);
+/* flags = 0 reproduces the reference bit for bit, quirks included.  Opt-in fix-ups for what the reference leaves as
+ * TODO: BSQ_TUPLES_FIX_HOLE_OFFSETS rebases the ambiguity holes of reference row k by that row's offset in the concatenated text
+ * (bwa.cpp:100-104 copies them un-rebased, so a hole of any row shadows the same offsets of row 1); BSQ_TUPLES_FIX_REVERSE reports a
+ * reverse-strand hit in forward-strand coordinates -- ref_subseq is the forward text it covers, ref_match_begin/end are relative to
+ * its row (bwa.cpp:156,172 use the doubled coordinate and read out of bounds).  With both flags ref_subseq is exactly the slice
+ * [ref_match_begin, ref_match_end) of the reference row as it was inserted.  MAPQ and NM, computed but never exported by the
+ * reference (bwa.cpp:158), are fields of bsq_row. */
+#define BSQ_TUPLES_FIX_HOLE_OFFSETS 1u
+#define BSQ_TUPLES_FIX_REVERSE 2u
+int bsq_result_tuples(bsq_index* h, const bsq_result* res, const char* seqs, const uint64_t* offs, uint32_t flags, bsq_tuples** out);
 void bsq_tuples_free(bsq_tuples* t);
 
 /* Resident-input variant used by bench.py's `value` leg: upload once, run the kernels with inputs and

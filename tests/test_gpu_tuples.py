@@ -66,6 +66,36 @@ def test_tuples_holes_and_ambiguity_codes(gpu_lib):
     assert n_hole_rows > 20
 
 
+def test_tuples_fixups(gpu_lib):
+    """SURVEY.md 8f-3, opt-in: with hole offsets rebased and reverse-strand hits turned to forward coordinates, ref_subseq is the
+    slice [ref_match_begin, ref_match_end) of the reference row exactly as it was inserted -- ambiguity letters included, both strands."""
+    from bioseqdb_b200.bwa import TUPLES_FIX_HOLE_OFFSETS, TUPLES_FIX_REVERSE
+    rng = np.random.default_rng(17)
+    rows = []
+    for n in (30_001, 20_002, 9_999):
+        t = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)].copy()
+        for _ in range(25):
+            a = int(rng.integers(0, n - 40)); l = int(rng.integers(1, 12))
+            t[a:a + l] = ord(rng.choice(list("NNRYKM")))
+        rows.append(t)
+    orc, gpu = build_pair(rows, O.sql_default_opts(3))
+    seqs, offs, _ = synth.simulate_reads(rows, 600, 150, seed=95)
+    res = gpu.align_batch(seqs, offs, synth.lrand48_ids_fast(600))
+    tup = gpu.tuples(res, seqs, offs, TUPLES_FIX_HOLE_OFFSETS | TUPLES_FIX_REVERSE)
+    plain = gpu.tuples(res, seqs, offs)
+    n_rev = n_amb = 0
+    for k, row in enumerate(res.rows):
+        b, e, l = tup.ref_match[k].tolist()
+        assert l == e - b == int(row["re"] - row["rb"])
+        want = rows[int(row["rid"])][b:e].tobytes()
+        assert len(want) == l, (k, b, e)
+        assert tup.ref_subseq(k) == nuclseq_image(nuclseq_from_text(want)), (k, want)
+        assert tup.query_subseq(k) == plain.query_subseq(k) and tup.cigar(k) == plain.cigar(k)
+        n_rev += int(row["is_rev"]); n_amb += any(c not in b"ACGT" for c in want)
+        assert b == int(row["pos"])          # mem_aln_t.pos: row-relative, forward strand, leftmost base
+    assert n_rev > 100 and n_amb > 10
+
+
 def test_tuples_empty(gpu_lib):
     rows = synth.reference_rows([20_001], seed=94)
     orc, gpu = build_pair(rows, O.sql_default_opts(1))

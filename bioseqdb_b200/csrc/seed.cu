@@ -22,7 +22,7 @@ constexpr int SEED_WARPS = SEED_THREADS / 32;
 // prefix table: bi-intervals of every t-mer, t = 1..K, levels back to back.  K is chosen per index, about log4 of the text
 // length, so that a K-mer has a handful of occurrences at most: 12 -> 358 MB, 13 -> 1.4 GB, 14 -> 5.7 GB (of 180 GB HBM)
 constexpr int KMER_K_MAX = 14;      // automatic choice; BSQ_KMER_K may ask for 15 (23 GB)
-__host__ __device__ constexpr uint32_t kmer_level_off(int t) { return (uint32_t)(((1ull << (2 * t)) - 4ull) / 3ull); }   // first entry of level t
+__host__ __device__ constexpr uint32_t kmer_level_off(int t) { return (0x55555555u >> (32 - 2 * t)) - 1u; }   // first entry of level t = (4^t - 4) / 3, 1 <= t <= 16
 
 template <class IdxT> struct IvT { IdxT x0, x1; uint32_t x2, info; };   // info = end of the match on the query
 // prefix-table entry {x0 low word, x1 low word, x2, hi}: hi = bits 32..39 of x0 | bits 32..39 of x1 << 8 (zero while rows fit 32 bits)

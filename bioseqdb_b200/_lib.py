@@ -42,6 +42,10 @@ class BsqTuples(C.Structure):
                 ("n_bytes", C.c_uint64), ("device_ms", C.c_float)]
 
 
+class BsqNuclseqs(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("off", C.POINTER(C.c_uint64)), ("bytes", C.POINTER(C.c_uint8)), ("n_bytes", C.c_uint64), ("device_ms", C.c_float)]
+
+
 class BsqTiming(C.Structure):
     _fields_ = [("h2d", C.c_float), ("seed", C.c_float), ("chain", C.c_float), ("extend", C.c_float), ("finalize", C.c_float),
                 ("d2h", C.c_float), ("total", C.c_float), ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
@@ -87,6 +91,8 @@ def lib():
     L.bsq_last_timing.argtypes = [vp, C.POINTER(BsqTiming)]
     L.bsq_result_tuples.argtypes = [vp, C.POINTER(BsqResult), vp, vp, u32, C.POINTER(C.POINTER(BsqTuples))]
     L.bsq_tuples_free.argtypes = [C.POINTER(BsqTuples)]
+    L.bsq_nuclseq_from_text_batch.argtypes = [C.c_int, vp, vp, u64, C.POINTER(C.POINTER(BsqNuclseqs))]
+    L.bsq_nuclseqs_free.argtypes = [C.POINTER(BsqNuclseqs)]
     L.bsq_reads_upload.argtypes = [vp, vp, vp, vp, u64]
     L.bsq_align_resident.argtypes = [vp]
     L.bsq_result_download.argtypes = [vp, C.POINTER(C.POINTER(BsqResult))]
@@ -111,7 +117,7 @@ def lib():
 
 ABI_SYMBOLS = [
     "bsq_last_error", "bsq_device_count", "bsq_opts_init", "bsq_index_new", "bsq_index_set_opts", "bsq_index_add_ref", "bsq_index_build",
-    "bsq_index_free", "bsq_align_batch", "bsq_result_free", "bsq_last_timing", "bsq_result_tuples", "bsq_tuples_free", "bsq_reads_upload", "bsq_align_resident", "bsq_result_download",
+    "bsq_index_free", "bsq_align_batch", "bsq_result_free", "bsq_last_timing", "bsq_result_tuples", "bsq_tuples_free", "bsq_nuclseq_from_text_batch", "bsq_nuclseqs_free", "bsq_reads_upload", "bsq_align_resident", "bsq_result_download",
     "bsq_index_get_meta", "bsq_index_device_bytes", "bsq_index_device_ptr", "bsq_index_download", "bsq_index_alloc_replica", "bsq_index_bwt_plain", "bsq_index_sa_sampled",
     "bsq_debug_seed", "bsq_debug_ksw_extend", "bsq_debug_ksw_extend_thread", "bsq_debug_ksw_global", "bsq_bench_gather", "bsq_bench_dpx", "bsq_set_counters", "bsq_get_counters",
 ]

@@ -16,6 +16,7 @@
 #include "seed.cuh"
 #include "pipeline.cuh"
 #include "tuples.cuh"
+#include "loader.cuh"
 #include "primitives.cuh"
 #include "debug_kernels.cuh"
 
@@ -1001,6 +1002,87 @@ void bsq_tuples_free(bsq_tuples* t) {
     TuplesImpl* T = reinterpret_cast<TuplesImpl*>(t);
     if (T->host) cudaFreeHost(T->host);
     delete T;
+}
+
+// ---- bulk text -> NUCLSEQ
+struct NuclseqsImpl { bsq_nuclseqs pub; void* host = nullptr; };
+
+int bsq_nuclseq_from_text_batch(int device, const char* text, const uint64_t* offs, uint64_t n, bsq_nuclseqs** out) {
+    if (!offs || !out || (n && !text && offs[n] != offs[0])) { bsq_set_error("null argument"); return BSQ_ERR; }
+    if (cudaSetDevice(device) != cudaSuccess) { bsq_set_error("no CUDA device %d (there is no CPU fallback)", device); return BSQ_ERR; }
+    std::vector<uint64_t> rel(n + 1), chunk_off(n + 1);
+    uint64_t chunks = 0;
+    for (uint64_t i = 0; i <= n; ++i) {
+        rel[i] = offs[i] - offs[0];
+        chunk_off[i] = chunks;
+        if (i < n) {
+            const uint64_t len = offs[i + 1] - offs[i];
+            if (len > (uint64_t)(INT32_MAX / 4)) { bsq_set_error("provided sequence is too long"); return BSQ_ERR; }   // extension.cpp:50
+            chunks += (len + 15) >> 4;
+        }
+    }
+    const uint64_t total = rel[n];
+    if (chunks >= (1ull << 32) - 2) { bsq_set_error("batch too large for one call (more than 64 G bases)"); return BSQ_ERR; }
+    NuclseqsImpl* S = new NuclseqsImpl();
+    S->pub.n = n; S->pub.off = nullptr; S->pub.bytes = nullptr; S->pub.n_bytes = 0; S->pub.device_ms = 0.f;
+    uint8_t *d_text = nullptr, *d_bytes = nullptr; uint64_t *d_offs = nullptr, *d_chunk_off = nullptr, *d_img = nullptr, *d_tmp64 = nullptr;
+    uint32_t *d_amb = nullptr, *d_start = nullptr, *d_holes = nullptr, *d_tmp32 = nullptr; unsigned long long* d_bad = nullptr;
+    cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = BSQ_ERR;
+    do {
+#define LC(x) if ((x) != cudaSuccess) { bsq_set_error("bsq_nuclseq_from_text_batch: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        LC(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); LC(cudaEventCreate(&e0)); LC(cudaEventCreate(&e1));
+        LC(cudaMalloc(&d_text, total + 64)); LC(cudaMalloc(&d_offs, (n + 1) * 8)); LC(cudaMalloc(&d_chunk_off, (n + 1) * 8)); LC(cudaMalloc(&d_img, (n + 2) * 8));
+        LC(cudaMalloc(&d_amb, (chunks + 2) * 4)); LC(cudaMalloc(&d_start, (chunks + 2) * 4)); LC(cudaMalloc(&d_holes, (n + 1) * 4));
+        LC(cudaMalloc(&d_tmp32, loader_scan_tmp_elems(chunks) * 4)); LC(cudaMalloc(&d_tmp64, loader_scan_tmp_elems(n) * 8)); LC(cudaMalloc(&d_bad, 8));
+        cudaEventRecord(e0, st);
+        if (total) LC(cudaMemcpyAsync(d_text, text + offs[0], total, cudaMemcpyHostToDevice, st));
+        LC(cudaMemcpyAsync(d_offs, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        LC(cudaMemcpyAsync(d_chunk_off, chunk_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        LC(cudaMemsetAsync(d_amb, 0, (chunks + 2) * 4, st)); LC(cudaMemsetAsync(d_start, 0, (chunks + 2) * 4, st)); LC(cudaMemsetAsync(d_img, 0, (n + 2) * 8, st));
+        LC(cudaMemsetAsync(d_bad, 0xff, 8, st));
+        LoaderParams P;
+        P.text = d_text; P.offs = d_offs; P.n_seqs = n; P.chunk_off = d_chunk_off; P.n_chunks = chunks; P.cnt_amb = d_amb; P.cnt_start = d_start;
+        P.holes_num = d_holes; P.img_off = d_img; P.first_invalid = d_bad; P.bytes = nullptr;
+        uint64_t launches = 0;
+        if (n) launch_loader_scan(P, d_tmp32, d_tmp64, st, &launches);
+        uint64_t n_bytes = 0; unsigned long long bad = ~0ull;
+        LC(cudaMemcpyAsync(&n_bytes, d_img + n, 8, cudaMemcpyDeviceToHost, st));
+        LC(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, st));
+        LC(cudaStreamSynchronize(st)); LC(cudaGetLastError());
+        if (bad != ~0ull) { bsq_set_error("invalid nucleotide in nuclseq_in: '%c'", text[offs[0] + bad]); break; }   // extension.cpp:53-58
+        LC(cudaMalloc(&d_bytes, n_bytes + 64));
+        LC(cudaMemsetAsync(d_bytes, 0, n_bytes + 64, st));
+        P.bytes = d_bytes;
+        if (n) launch_loader_fill(P, st, &launches);
+        const size_t off_b = (n + 1) * 8;
+        LC(cudaHostAlloc(&S->host, off_b + n_bytes + 64, cudaHostAllocDefault));
+        S->pub.off = reinterpret_cast<uint64_t*>(S->host);
+        S->pub.bytes = reinterpret_cast<uint8_t*>(static_cast<char*>(S->host) + off_b);
+        S->pub.n_bytes = n_bytes;
+        LC(cudaMemcpyAsync(S->pub.off, d_img, off_b, cudaMemcpyDeviceToHost, st));
+        if (n_bytes) LC(cudaMemcpyAsync(S->pub.bytes, d_bytes, n_bytes, cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(e1, st);
+        LC(cudaStreamSynchronize(st)); LC(cudaGetLastError());
+        cudaEventElapsedTime(&S->pub.device_ms, e0, e1);
+        rc = BSQ_OK;
+#undef LC
+    } while (0);
+    cudaFree(d_text); cudaFree(d_bytes); cudaFree(d_offs); cudaFree(d_chunk_off); cudaFree(d_img); cudaFree(d_tmp64); cudaFree(d_amb); cudaFree(d_start);
+    cudaFree(d_holes); cudaFree(d_tmp32); cudaFree(d_bad);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    if (rc != BSQ_OK) { if (S->host) cudaFreeHost(S->host); delete S; return BSQ_ERR; }
+    *out = &S->pub;
+    return BSQ_OK;
+}
+
+void bsq_nuclseqs_free(bsq_nuclseqs* s) {
+    if (!s) return;
+    NuclseqsImpl* S = reinterpret_cast<NuclseqsImpl*>(s);
+    if (S->host) cudaFreeHost(S->host);
+    delete S;
 }
 
 void bsq_result_free(bsq_result* r) {

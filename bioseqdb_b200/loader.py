@@ -1,0 +1,67 @@
+"""Bulk loader: the FASTA walk of reference bioseqdb-import/main.cpp:52-72 on the host, then ONE call that turns
+every record's text into a finished NUCLSEQ datum on the GPU (bsq_nuclseq_from_text_batch = nuclseq_in + nuclseq_from_text,
+extension.cpp:46-60, sequence.cpp:209-245) -- instead of one INSERT and one server-side conversion per record."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import BsqNuclseqs, check, ptr
+
+
+def fasta_records(data: bytes):
+    """(name, sequence) pairs exactly as bioseqdb-import submits them (main.cpp:52-72): std::getline lines, a line starting with
+    '>' opens a record named by the rest of the line, other lines are upper-cased and appended, records without sequence are dropped."""
+    name, seq, out = b"", [], []
+
+    def submit():
+        nonlocal name, seq
+        s = b"".join(seq)
+        if s:
+            out.append((name, s))
+        name, seq = b"", []
+
+    lines = data.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()                       # getline does not produce an empty line after the final newline
+    for line in lines:
+        if line[:1] == b">":
+            submit()
+            name = line[1:]
+        else:
+            seq.append(line.upper())
+    submit()
+    return out
+
+
+def nuclseq_images(texts, device: int = 0):
+    """texts: list of bytes. Returns (list of datum images, device_ms). Raises BsqError like nuclseq_in on an invalid letter."""
+    L = _lib.lib()
+    n = len(texts)
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    if n:
+        offs[1:] = np.cumsum([len(t) for t in texts])
+    cat = np.frombuffer(b"".join(texts), dtype=np.uint8) if n and offs[-1] else np.zeros(1, dtype=np.uint8)
+    res = C.POINTER(BsqNuclseqs)()
+    check(L.bsq_nuclseq_from_text_batch(device, ptr(cat), ptr(offs), n, C.byref(res)))
+    r = res.contents
+    off = np.ctypeslib.as_array(r.off, shape=(n + 1,)).copy()
+    nb = int(r.n_bytes)
+    data = np.ctypeslib.as_array(r.bytes, shape=(max(nb, 1),))[:nb].copy()
+    ms = float(r.device_ms)
+    L.bsq_nuclseqs_free(res)
+    images = []
+    for i in range(n):
+        at = int(off[i])
+        size = int(np.frombuffer(data[at:at + 4].tobytes(), dtype="<u4")[0]) >> 2
+        images.append(data[at:at + size].tobytes())
+    return images, ms
+
+
+def load_fasta(data: bytes, device: int = 0):
+    """[(name, NUCLSEQ datum image)] for a FASTA file's bytes -- the rows a COPY ... BINARY into (name, seq) would carry."""
+    recs = fasta_records(data)
+    images, ms = nuclseq_images([s for _, s in recs], device)
+    return [(nm, img) for (nm, _), img in zip(recs, images)], ms

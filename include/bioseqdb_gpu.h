@@ -108,6 +108,21 @@ typedef struct bsq_tuples {
 int bsq_result_tuples(bsq_index* h, const bsq_result* res, const char* seqs, const uint64_t* offs, uint32_t flags, bsq_tuples** out);
 void bsq_tuples_free(bsq_tuples* t);
 
+/* Bulk text -> NUCLSEQ conversion: nuclseq_in + nuclseq_from_text (extension.cpp:46-60, sequence.cpp:209-245) for n
+ * sequences in one call -- what a bulk loader needs in place of bioseqdb-import's one INSERT (and one server-side nuclseq_in) per
+ * FASTA record (bioseqdb-import/main.cpp:52-72).  text: the sequences back to back (upper case, as the importer sends them),
+ * offs[n + 1].  Result: image i (datum bytes as in bsq_tuples) at bytes + off[i].  Fails like nuclseq_in: a letter outside
+ * "ACGTNWSMKRYBDHV" ("invalid nucleotide in nuclseq_in: 'x'") or a sequence longer than INT32_MAX / 4. */
+typedef struct bsq_nuclseqs {
+    uint64_t n;
+    uint64_t* off;      /* n + 1 */
+    uint8_t* bytes;
+    uint64_t n_bytes;
+    float device_ms;    /* kernels + copies of this call */
+} bsq_nuclseqs;
+int bsq_nuclseq_from_text_batch(int device, const char* text, const uint64_t* offs, uint64_t n, bsq_nuclseqs** out);
+void bsq_nuclseqs_free(bsq_nuclseqs* s);
+
 /* Resident-input variant used by bench.py's `value` leg: upload once, run the kernels with inputs and
  * outputs resident in HBM, download on request. */
 int bsq_reads_upload(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n);

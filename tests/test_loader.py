@@ -1,0 +1,63 @@
+"""the bulk loader.  CPU: the FASTA walk of bioseqdb-import/main.cpp:52-72.  GPU: batch nuclseq_in + nuclseq_from_text
+(bsq_nuclseq_from_text_batch) against the host-side codec (bioseqdb_b200/sequence.py, pinned by the payload goldens of SURVEY 8c)."""
+import numpy as np
+import pytest
+
+from bioseqdb_b200.loader import fasta_records
+
+
+def test_fasta_records_follow_the_importer():
+    data = b">chr1 first\nacgtn\nACGT\n>empty\n>chr2\n\nNNNN\nacgu\n\n>tail"
+    assert fasta_records(data) == [(b"chr1 first", b"ACGTNACGT"), (b"chr2", b"NNNNACGU")]
+    assert fasta_records(b"ACGT\n>x\nAC\n") == [(b"", b"ACGT"), (b"x", b"AC")]      # sequence before any header: empty name
+    assert fasta_records(b"") == []
+
+
+def _texts(rng, n, max_len):
+    out = []
+    for i in range(n):
+        ln = int(rng.integers(0, max_len + 1)) if i % 7 else int(rng.choice([0, 1, 3, 4, 5, 15, 16, 17, 31, 32, 33, 64]))
+        t = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=ln)].copy()
+        for _ in range(int(rng.integers(0, 6))):
+            if ln == 0:
+                break
+            a = int(rng.integers(0, ln)); l = int(rng.integers(1, 40))
+            t[a:a + l] = ord(rng.choice(list("NNNWSMKRYBDHV")))
+        out.append(t.tobytes())
+    return out
+
+
+@pytest.mark.gpu
+def test_nuclseq_batch_matches_host_codec(gpu_lib):
+    from bioseqdb_b200.bwa import nuclseq_image
+    from bioseqdb_b200.loader import nuclseq_images
+    from bioseqdb_b200.sequence import nuclseq_from_text
+    rng = np.random.default_rng(404)
+    texts = _texts(rng, 700, 3000)
+    texts += [b"N" * 100_000, b"ACGT" * 25_000 + b"NNR", b"R" * 17 + b"Y" * 16 + b"A" + b"Y" * 15, b"", b"A"]
+    images, ms = nuclseq_images(texts)
+    assert len(images) == len(texts)
+    for i, t in enumerate(texts):
+        assert images[i] == nuclseq_image(nuclseq_from_text(t)), (i, len(t))
+
+
+@pytest.mark.gpu
+def test_nuclseq_batch_rejects_what_nuclseq_in_rejects(gpu_lib):
+    from bioseqdb_b200._lib import BsqError
+    from bioseqdb_b200.loader import nuclseq_images
+    with pytest.raises(BsqError, match="invalid nucleotide in nuclseq_in: 'U'"):
+        nuclseq_images([b"ACGT", b"ACGUACGT"])
+    with pytest.raises(BsqError, match="invalid nucleotide in nuclseq_in: 'a'"):      # lower case is not stored (extension.cpp:40-44)
+        nuclseq_images([b"ACGTaCGT"])
+    assert nuclseq_images([])[0] == []
+
+
+@pytest.mark.gpu
+def test_load_fasta_end_to_end(gpu_lib):
+    from bioseqdb_b200.bwa import nuclseq_image
+    from bioseqdb_b200.loader import load_fasta
+    from bioseqdb_b200.sequence import nuclseq_from_text
+    rows, ms = load_fasta(b">a desc\nacgtnnnn\nACGT\n>b\nNNNNRRYY\nAC\n")
+    assert [n for n, _ in rows] == [b"a desc", b"b"]
+    assert rows[0][1] == nuclseq_image(nuclseq_from_text(b"ACGTNNNNACGT"))
+    assert rows[1][1] == nuclseq_image(nuclseq_from_text(b"NNNNRRYYAC"))

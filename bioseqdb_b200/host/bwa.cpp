@@ -160,6 +160,39 @@ std::vector<std::vector<BwaMatch>> BwaIndex::align_sequences(const std::vector<c
     return out;
 }
 
+BwaTupleBatch BwaIndex::align_sequences_tuples(const std::vector<const NucleotideSequence*>& seqs, uint32_t flags) {
+    if (pac_forward.empty() || seqs.empty()) return BwaTupleBatch();
+    std::string cat;
+    std::vector<uint64_t> offs(seqs.size() + 1, 0);
+    std::vector<int64_t> ids(seqs.size());
+    for (size_t i = 0; i < seqs.size(); ++i) {
+        cat += seqs[i]->to_text();
+        offs[i + 1] = cat.size();
+        lrand_state = (lrand_state * 0x5DEECE66DULL + 0xBULL) & 0xFFFFFFFFFFFFULL;   // id = lrand48()
+        ids[i] = (int64_t)(lrand_state >> 17);
+    }
+    bsq_result* res = nullptr;
+    if (bsq_align_batch(index, cat.data(), offs.data(), ids.data(), seqs.size(), &res) != BSQ_OK) fail();
+    bsq_tuples* tup = nullptr;
+    if (bsq_result_tuples(index, res, cat.data(), offs.data(), flags, &tup) != BSQ_OK) { bsq_result_free(res); fail(); }
+    return BwaTupleBatch(res, tup);
+}
+
+std::vector<std::vector<uint8_t>> nuclseq_datums_from_texts(const std::vector<std::string>& texts, int device) {
+    std::string cat;
+    std::vector<uint64_t> offs(texts.size() + 1, 0);
+    for (size_t i = 0; i < texts.size(); ++i) { cat += texts[i]; offs[i + 1] = cat.size(); }
+    bsq_nuclseqs* r = nullptr;
+    if (bsq_nuclseq_from_text_batch(device, cat.data(), offs.data(), texts.size(), &r) != BSQ_OK) fail();
+    std::vector<std::vector<uint8_t>> out(texts.size());
+    for (size_t i = 0; i < texts.size(); ++i) {
+        const uint8_t* d = r->bytes + r->off[i];
+        out[i].assign(d, d + BwaTupleBatch::datum_size(d));
+    }
+    bsq_nuclseqs_free(r);
+    return out;
+}
+
 std::vector<BwaMatch> BwaIndex::align_sequence(const NucleotideSequence& seq) {
     if (pac_forward.empty()) return {};
     return std::move(align_sequences({&seq})[0]);

@@ -28,6 +28,36 @@ struct BwaMatch {
     int mapq, nm;
 };
 
+// A batch's rows with their variable-length columns already in PostgreSQL's binary form: what build_tuple_bwa
+// (extension.cpp:282-305) hands to heap_form_tuple, built on the GPU by bsq_result_tuples.  Row k of read i: k in
+// [row_begin(i), row_begin(i + 1)).  The datum pointers are 8-byte aligned NUCLSEQ images (the varlena length word is set).
+class BwaTupleBatch {
+public:
+    BwaTupleBatch() = default;
+    BwaTupleBatch(bsq_result* r, bsq_tuples* t) : res(r), tup(t) {}
+    BwaTupleBatch(BwaTupleBatch&& o) noexcept : res(o.res), tup(o.tup) { o.res = nullptr; o.tup = nullptr; }
+    BwaTupleBatch& operator=(BwaTupleBatch&& o) noexcept { release(); res = o.res; tup = o.tup; o.res = nullptr; o.tup = nullptr; return *this; }
+    BwaTupleBatch(const BwaTupleBatch&) = delete;
+    BwaTupleBatch& operator=(const BwaTupleBatch&) = delete;
+    ~BwaTupleBatch() { release(); }
+    uint64_t reads() const { return res ? res->n_reads : 0; }
+    uint64_t row_begin(uint64_t read) const { return res ? res->row_off[read] : 0; }
+    const bsq_row& row(uint64_t k) const { return res->rows[k]; }
+    const uint8_t* ref_subseq_datum(uint64_t k) const { return tup->bytes + tup->off[3 * k]; }
+    const uint8_t* query_subseq_datum(uint64_t k) const { return tup->bytes + tup->off[3 * k + 1]; }
+    const char* cigar(uint64_t k) const { return reinterpret_cast<const char*>(tup->bytes + tup->off[3 * k + 2]); }
+    int32_t ref_match_begin(uint64_t k) const { return tup->ref_match[3 * k]; }
+    int32_t ref_match_end(uint64_t k) const { return tup->ref_match[3 * k + 1]; }
+    int32_t ref_match_len(uint64_t k) const { return tup->ref_match[3 * k + 2]; }
+    static size_t datum_size(const uint8_t* datum) { uint32_t w; __builtin_memcpy(&w, datum, 4); return w >> 2; }   // VARSIZE of a 4-byte header
+private:
+    void release() { if (tup) bsq_tuples_free(tup); if (res) bsq_result_free(res); tup = nullptr; res = nullptr; }
+    bsq_result* res = nullptr; bsq_tuples* tup = nullptr;
+};
+
+// Bulk text -> NUCLSEQ: nuclseq_in for a whole batch on the GPU; datum i = bytes of image i.
+std::vector<std::vector<uint8_t>> nuclseq_datums_from_texts(const std::vector<std::string>& texts, int device = 0);
+
 class BwaIndex {
 public:
     explicit BwaIndex(int device = 0);
@@ -38,6 +68,8 @@ public:
     std::vector<BwaMatch> align_sequence(const NucleotideSequence& seq);
     // batched form of the per-read loop at extension.cpp:362-370: one GPU pass for all reads
     std::vector<std::vector<BwaMatch>> align_sequences(const std::vector<const NucleotideSequence*>& seqs);
+    // the same pass, rows left in binary tuple form (flags: BSQ_TUPLES_FIX_*, 0 = the reference's behaviour)
+    BwaTupleBatch align_sequences_tuples(const std::vector<const NucleotideSequence*>& seqs, uint32_t flags = 0);
     void build();
     void add_ref_sequence(int64_t id, const NucleotideSequence& seq);
 

@@ -56,13 +56,13 @@ struct Batch {
     DevBuf<uint32_t> cigar; uint32_t cigar_cap = 0;
     DevBuf<double> read_logtab; uint32_t read_logtab_n = 0; uint32_t rseq_cap = 0;
     DevBuf<uint8_t> ext_scratch, fin_scratch, narrow_z, narrow_jobs; DevBuf<uint64_t> wide_jobs;
-    DevBuf<ExtMemo> ext_memo; DevBuf<uint8_t> ext_memo_key; DevBuf<uint32_t> ext_memo_perm, ext_memo_hist, ext_todo;   // thread-per-extension pre-pass (extend_plan.cu)
-    DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..23] counters (u64 x 8), [24] narrow_cnt, [25] wide_cnt, [26..27] tickets, [56] reads left for sw_extend
+    DevBuf<ExtMemo> ext_memo; DevBuf<uint8_t> ext_memo_key; DevBuf<uint32_t> ext_memo_perm, ext_memo_hist, ext_todo, chain_todo;   // thread-per-extension pre-pass (extend_plan.cu)
+    DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..23] counters (u64 x 8), [24] narrow_cnt, [25] wide_cnt, [26..27] tickets, [56] reads left for sw_extend, [57] reads left for the warp chain kernel
     size_t device_bytes() const {
         return seqs.bytes() + offs.bytes() + ids.bytes() + intv.bytes() + intv_cnt.bytes() + seed_scratch.bytes() + raw.bytes() + seeds.bytes() + ctmp.bytes() +
                ord.bytes() + chains.bytes() + srt.bytes() + regs.bytes() + rows.bytes() + rows_compact.bytes() + reg_cnt.bytes() + row_cnt.bytes() + row_off.bytes() +
                scan_tmp.bytes() + blocks.bytes() + cigar.bytes() + read_logtab.bytes() + ext_scratch.bytes() + fin_scratch.bytes() + narrow_z.bytes() +
-               narrow_jobs.bytes() + wide_jobs.bytes() + ctl.bytes() + ext_memo.bytes() + ext_memo_key.bytes() + ext_memo_perm.bytes() + ext_memo_hist.bytes() + ext_todo.bytes();
+               narrow_jobs.bytes() + wide_jobs.bytes() + ctl.bytes() + ext_memo.bytes() + ext_memo_key.bytes() + ext_memo_perm.bytes() + ext_memo_hist.bytes() + ext_todo.bytes() + chain_todo.bytes();
     }
     bool resident = false, aligned = false;
     // one batch = one lane of the host pipeline: its stream, the host staging that must outlive the async copies,
@@ -84,7 +84,7 @@ struct Batch {
         ctmp.release(); ord.release(); chains.release(); srt.release(); regs.release(); rows.release(); rows_compact.release(); reg_cnt.release();
         row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release();
         ctl.release(); narrow_z.release(); narrow_jobs.release(); wide_jobs.release(); read_logtab.release();
-        ext_memo.release(); ext_memo_key.release(); ext_memo_perm.release(); ext_memo_hist.release(); ext_todo.release();
+        ext_memo.release(); ext_memo_key.release(); ext_memo_perm.release(); ext_memo_hist.release(); ext_todo.release(); chain_todo.release();
     }
 };
 
@@ -500,7 +500,7 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
     int narrow_warps = 0;
     const size_t narrow_bytes = narrow_zbuf_bytes(&narrow_warps);
     ENS(b.narrow_z.ensure(narrow_bytes)); ENS(b.narrow_jobs.ensure((size_t)b.pool_cap * 3 * 24)); ENS(b.wide_jobs.ensure(b.pool_cap));
-    ENS(b.ctl.ensure(64));
+    ENS(b.ctl.ensure(64)); ENS(b.chain_todo.ensure(n));
     // the thread-per-extension pre-pass packs column scores in 16 bits: every value it stores is <= l_query * (a + 1)
     static const bool no_memo = getenv("BSQ_NO_EXT_MEMO") != nullptr;
     const bool use_memo = !no_memo && max_len <= 512 && (uint64_t)max_len * (uint64_t)(o.a + 1) < 32000 && (uint64_t)n * EXT_MEMO_CHAINS < (1ull << 31);
@@ -528,6 +528,11 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
         P.raw = b.raw.p; P.ctmp = b.ctmp.p; P.ord = b.ord.p; P.chains = b.chains.p; P.seeds = b.seeds.p; P.pool_cap = b.pool_cap; P.pool_top = b.ctl.p + 5;
         P.blocks = b.blocks.p; P.ticket = b.ctl.p + 1; P.overflow = b.ctl.p + 4; P.counters = ctr ? ctr + 1 : nullptr;
         P.logtab = needs_seed_sw(b.max_len) ? b.read_logtab.p : nullptr; P.sw_cells = nullptr;
+        // short reads: a thread-per-read pass takes every read with a handful of seed occurrences, the warp kernel the rest
+        static const bool no_thread_chain = getenv("BSQ_NO_CHAIN_THREAD") != nullptr;
+        const bool thread_chain = !no_thread_chain && !P.logtab;
+        P.todo = thread_chain ? b.chain_todo.p : nullptr; P.todo_cnt = b.ctl.p + 57;
+        if (thread_chain) { launch_chain_thread(P, ix, o, st); ++T.launches; }
         launch_chain(P, ix, o, st); ++T.launches;
     }
     cudaEventRecord(ev[2], st);

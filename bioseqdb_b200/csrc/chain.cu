@@ -124,6 +124,199 @@ __device__ int mem_seed_sw(const DevIndex& ix, const DevOpts& o, const int* smat
     return ksw_local_warp(o, smat, qlen, query + qb, tlen, tw, bH, bF);
 }
 
+// occurrences an interval contributes (the k/step loop of mem_chain) and the stride between them
+__device__ __forceinline__ uint32_t occ_count(const DevOpts& o, uint64_t x2, uint64_t* step_out) {
+    uint64_t step = 1, cnt = x2;
+    if (x2 > (uint64_t)o.max_occ) {
+        step = x2 / (uint64_t)o.max_occ;
+        cnt = (x2 + step - 1) / step;
+        if (cnt > (uint64_t)o.max_occ) cnt = (uint64_t)o.max_occ;
+    }
+    if (step_out) *step_out = step;
+    return (uint32_t)cnt;
+}
+
+// ordered-insert chaining of a read's `total` seeds (raw[t].score holds the seed's rid on entry, its length on exit): returns the
+// number of chains in ct[], ord[] = chain indices sorted by pos
+__device__ __forceinline__ int chain_seeds(SeedRec* raw, ChainTmp* ct, uint32_t* ord, uint32_t total, const DevIndex& ix, const DevOpts& o, unsigned long long& n_dup) {
+    int n_ch = 0;
+    for (uint32_t t = 0; t < total; ++t) {
+        SeedRec s = raw[t];
+        int rid = s.score;
+        if (rid < 0) continue;
+        raw[t].score = s.len;
+        bool to_add = true;
+        int lo = 0;
+        if (n_ch) {
+            lo = find_lower(ct, ord, n_ch, s.rbeg);
+            if (lo > 0) {
+                ChainTmp& c = ct[ord[lo - 1]];
+                // test_and_merge
+                int64_t qend = c.l_qbeg + c.l_len, rend = c.l_rbeg + c.l_len;
+                int res = 0;
+                if (rid != c.rid) res = 0;
+                else if (s.qbeg >= c.f_qbeg && s.qbeg + s.len <= qend && s.rbeg >= c.f_rbeg && s.rbeg + s.len <= rend) res = 1;
+                else if ((c.l_rbeg < ix.l_pac || c.f_rbeg < ix.l_pac) && s.rbeg >= ix.l_pac) res = 0;
+                else {
+                    int64_t x = s.qbeg - c.l_qbeg, y = s.rbeg - c.l_rbeg;
+                    if (y >= 0 && x - y <= o.w && y - x <= o.w && x - c.l_len < o.max_chain_gap && y - c.l_len < o.max_chain_gap) {
+                        raw[c.tail].next = (int32_t)t; c.tail = (int32_t)t; ++c.n;
+                        c.l_rbeg = s.rbeg; c.l_qbeg = s.qbeg; c.l_len = s.len;
+                        res = 1;
+                    }
+                }
+                if (res) to_add = false;
+                else if (c.pos == s.rbeg) ++n_dup;
+            }
+        }
+        if (to_add) {
+            ChainTmp c;
+            c.pos = s.rbeg; c.f_rbeg = c.l_rbeg = s.rbeg; c.f_qbeg = c.l_qbeg = s.qbeg; c.f_len = c.l_len = s.len;
+            c.head = c.tail = (int32_t)t; c.n = 1; c.rid = rid; c.first = -1; c.kept = 0; c.w = 0; c.pad = 0;
+            ct[n_ch] = c;
+            for (int k = n_ch; k > lo; --k) ord[k] = ord[k - 1];
+            ord[lo] = (uint32_t)n_ch;
+            ++n_ch;
+        }
+    }
+    return n_ch;
+}
+
+// mem_chain_flt: ord[] is the chain array `a` in pos order on entry; returns the number of chains that passed
+// min_chain_weight, ord[0 .. n) sorted by weight with ct[].kept set
+__device__ __forceinline__ int chain_filter(ChainTmp* ct, uint32_t* ord, int n_ch, const DevOpts& o) {
+    int n = 0;
+    for (int i = 0; i < n_ch; ++i) { uint32_t c = ord[i]; if ((int)ct[c].w >= o.min_chain_weight) ord[n++] = c; }
+    if (n == 0) return 0;
+    const ChainTmp* ctc = ct;
+    ks_introsort_dev(n, ord, [ctc](uint32_t x, uint32_t y) { return ctc[x].w > ctc[y].w; });
+    // the kept list lives in ChainTmp.pad (P.ord is n_alloc wide, chains <= seeds, so [n, 2n) may not exist)
+    int n_kept = 0;
+    ct[ord[0]].kept = 3; ct[n_kept++].pad = 0;
+    for (int i = 1; i < n; ++i) {
+        ChainTmp& ci = ct[ord[i]];
+        int large_ovlp = 0, k;
+        int bi = ci.f_qbeg, ei = ci.l_qbeg + ci.l_len;
+        for (k = 0; k < n_kept; ++k) {
+            int j = (int)ct[k].pad;
+            ChainTmp& cj = ct[ord[j]];
+            int bj = cj.f_qbeg, ej = cj.l_qbeg + cj.l_len;
+            int b_max = bj > bi ? bj : bi, e_min = ej < ei ? ej : ei;
+            if (e_min > b_max) {   // is_alt is always 0 on this path (reference bwa.cpp:84-91)
+                int li = ei - bi, lj = ej - bj, min_l = li < lj ? li : lj;
+                if ((float)(e_min - b_max) >= __fmul_rn((float)min_l, o.mask_level) && min_l < o.max_chain_gap) {
+                    large_ovlp = 1;
+                    if (cj.first < 0) cj.first = i;
+                    if ((float)(int)ci.w < __fmul_rn((float)(int)cj.w, o.drop_ratio) && (int)cj.w - (int)ci.w >= o.min_seed_len << 1) break;
+                }
+            }
+        }
+        if (k == n_kept) { ct[n_kept++].pad = (uint32_t)i; ci.kept = large_ovlp ? 2 : 3; }
+    }
+    for (int k = 0; k < n_kept; ++k) { ChainTmp& c = ct[ord[ct[k].pad]]; if (c.first >= 0) ct[ord[c.first]].kept = 1; }
+    int i, k;
+    for (i = k = 0; i < n; ++i) {
+        int kp = ct[ord[i]].kept;
+        if (kp == 0 || kp == 3) continue;
+        if (++k >= o.max_chain_extend) break;
+    }
+    for (; i < n; ++i) if (ct[ord[i]].kept < 3) ct[ord[i]].kept = 0;
+    return n;
+}
+
+// Thread per read (short reads, no seed filter): the whole of mem_chain + mem_chain_flt for a read whose intervals have at most
+// CHAIN_THREAD_MAX_OCC occurrences in total -- a handful of SA reads and a few dozen records of bookkeeping, which a warp would do
+// on one lane anyway.  Reads with more occurrences (repeats) are queued for the warp kernel.
+constexpr uint32_t CHAIN_THREAD_MAX_OCC = 48;
+__global__ void __launch_bounds__(CHAIN_THREADS) chain_build_thread(ChainParams P, DevIndex ix, DevOpts o) {
+    const uint32_t r = blockIdx.x * CHAIN_THREADS + threadIdx.x;
+    const int lane = lane_id();
+    const bool active = r < P.n_reads;
+    unsigned long long n_sa = 0, n_dup = 0;
+    uint32_t total = 0; int l_rep = 0, n_iv = 0, len = 0;
+    const Intv* iv = nullptr;
+    if (active) {
+        len = (int)(P.offs[r + 1] - P.offs[r]);
+        iv = P.intv + (size_t)r * P.intv_cap;
+        n_iv = (int)P.intv_cnt[r];
+        int b = 0, e = 0;
+        for (int i = 0; i < n_iv; ++i) {
+            const uint64_t x2 = iv[i].x2;
+            total += occ_count(o, x2, nullptr);
+            if (x2 > (uint64_t)o.max_occ) {
+                const uint64_t info = iv[i].info;
+                int sb = (int)(info >> 32), se = (int)(uint32_t)info;
+                if (sb > e) { l_rep += e - b; b = sb; e = se; }
+                else e = e > se ? e : se;
+            }
+            if (total > CHAIN_THREAD_MAX_OCC) break;
+        }
+        l_rep += e - b;
+    }
+    const bool fast = active && total <= CHAIN_THREAD_MAX_OCC;
+    if (active && !fast) P.todo[atomicAdd(P.todo_cnt, 1u)] = r;
+    // one pool allocation per warp
+    const uint32_t need = fast ? total : 0;
+    uint32_t incl = need;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+    const uint32_t warp_total = __shfl_sync(FULL, incl, 31);
+    uint32_t wbase = 0;
+    if (lane == 31 && warp_total) wbase = atomicAdd(P.pool_top, warp_total);
+    wbase = __shfl_sync(FULL, wbase, 31);
+    if (fast) {
+        const uint32_t base = wbase + incl - need;
+        ReadBlock blk; blk.base = base; blk.n_alloc = total; blk.n_chains = 0; blk.n_seeds = 0;
+        if (total == 0 || (uint64_t)base + total > (uint64_t)P.pool_cap) {
+            if (total) atomicExch(P.overflow, 1u);
+            blk.n_alloc = 0;
+            P.blocks[r] = blk;
+        } else {
+            SeedRec* raw = P.raw + base; ChainTmp* ct = P.ctmp + base; uint32_t* ord = P.ord + base;
+            uint32_t t = 0;
+            for (int i = 0; i < n_iv; ++i) {
+                const Intv p = iv[i];
+                uint64_t step;
+                const uint32_t cnt = occ_count(o, p.x2, &step);
+                const int qb = (int)(p.info >> 32), ql = (int)((uint32_t)p.info - (uint32_t)(p.info >> 32));
+                for (uint32_t c = 0; c < cnt; ++c, ++t) {
+                    const int64_t rbeg = (int64_t)sa_at(ix, p.x0 + (uint64_t)c * step);
+                    SeedRec sd; sd.rbeg = rbeg; sd.qbeg = qb; sd.len = ql; sd.next = -1;
+                    sd.score = bns_intv2rid(ix, rbeg, rbeg + ql);
+                    raw[t] = sd;
+                }
+            }
+            n_sa += total;
+            const int n_ch = chain_seeds(raw, ct, ord, total, ix, o, n_dup);
+            for (int k = 0; k < n_ch; ++k) ct[k].w = (uint32_t)chain_weight(raw, ct[k]);
+            const int n_flt = n_ch ? chain_filter(ct, ord, n_ch, o) : 0;
+            int n_out = 0; uint32_t seed_out = 0;
+            if (n_flt) {
+                ChainRec* co = P.chains + base; SeedRec* so = P.seeds + base;
+                const float frac_rep = (float)l_rep / len;
+                for (int i = 0; i < n_flt; ++i) {
+                    const ChainTmp c = ct[ord[i]];
+                    if (c.kept == 0) continue;
+                    ChainRec rec; rec.pos = c.pos; rec.rid = c.rid; rec.seed_off = (int32_t)seed_out; rec.kept = c.kept;
+                    rec.w = c.w; rec.frac_rep = frac_rep;
+                    int kept_seeds = 0;
+                    for (int s = c.head; s >= 0; s = raw[s].next) { SeedRec q = raw[s]; q.next = -1; so[seed_out] = q; ++seed_out; ++kept_seeds; }
+                    rec.n_seeds = kept_seeds;
+                    co[n_out] = rec;
+                    ++n_out;
+                }
+            }
+            blk.n_chains = (uint32_t)n_out; blk.n_seeds = seed_out;
+            P.blocks[r] = blk;
+        }
+    }
+    if (P.counters) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) { n_sa += __shfl_xor_sync(FULL, n_sa, d); n_dup += __shfl_xor_sync(FULL, n_dup, d); }
+        if (lane == 0) { if (n_sa) atomicAdd(&P.counters[0], n_sa); if (n_dup) atomicAdd(&P.counters[1], n_dup); }
+    }
+}
+
 __global__ void __launch_bounds__(CHAIN_THREADS) chain_build(ChainParams P, DevIndex ix, DevOpts o) {
     __shared__ int smat[25];
     __shared__ int sw_smem[CHAIN_THREADS / 32][SW_BUF_INTS];
@@ -132,9 +325,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS) chain_build(ChainParams P, DevI
     const int lane = lane_id();
     int* swbuf = sw_smem[threadIdx.x >> 5];
     unsigned long long n_sa = 0, n_dup = 0, n_swcells = 0;
+    const uint32_t n_todo = P.todo ? *P.todo_cnt : P.n_reads;     // with the thread pass on: only the reads it queued
     for (;;) {
-        uint32_t r = next_ticket(P.ticket);
-        if (r >= P.n_reads) break;
+        const uint32_t tk = next_ticket(P.ticket);
+        if (tk >= n_todo) break;
+        const uint32_t r = P.todo ? P.todo[tk] : tk;
         const int len = (int)(P.offs[r + 1] - P.offs[r]);
         const Intv* iv = P.intv + (size_t)r * P.intv_cap;
         const int n_iv = (int)P.intv_cnt[r];
@@ -218,95 +413,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS) chain_build(ChainParams P, DevI
         __syncwarp();
         // ---- ordered-insert chaining (lane 0)
         int n_ch = 0;
-        if (lane == 0) {
-            for (uint32_t t = 0; t < total; ++t) {
-                SeedRec s = raw[t];
-                int rid = s.score;
-                if (rid < 0) continue;
-                raw[t].score = s.len;
-                bool to_add = true;
-                int lo = 0;
-                if (n_ch) {
-                    lo = find_lower(ct, ord, n_ch, s.rbeg);
-                    if (lo > 0) {
-                        ChainTmp& c = ct[ord[lo - 1]];
-                        // test_and_merge
-                        int64_t qend = c.l_qbeg + c.l_len, rend = c.l_rbeg + c.l_len;
-                        int res = 0;
-                        if (rid != c.rid) res = 0;
-                        else if (s.qbeg >= c.f_qbeg && s.qbeg + s.len <= qend && s.rbeg >= c.f_rbeg && s.rbeg + s.len <= rend) res = 1;
-                        else if ((c.l_rbeg < ix.l_pac || c.f_rbeg < ix.l_pac) && s.rbeg >= ix.l_pac) res = 0;
-                        else {
-                            int64_t x = s.qbeg - c.l_qbeg, y = s.rbeg - c.l_rbeg;
-                            if (y >= 0 && x - y <= o.w && y - x <= o.w && x - c.l_len < o.max_chain_gap && y - c.l_len < o.max_chain_gap) {
-                                raw[c.tail].next = (int32_t)t; c.tail = (int32_t)t; ++c.n;
-                                c.l_rbeg = s.rbeg; c.l_qbeg = s.qbeg; c.l_len = s.len;
-                                res = 1;
-                            }
-                        }
-                        if (res) to_add = false;
-                        else if (c.pos == s.rbeg) ++n_dup;
-                    }
-                }
-                if (to_add) {
-                    ChainTmp c;
-                    c.pos = s.rbeg; c.f_rbeg = c.l_rbeg = s.rbeg; c.f_qbeg = c.l_qbeg = s.qbeg; c.f_len = c.l_len = s.len;
-                    c.head = c.tail = (int32_t)t; c.n = 1; c.rid = rid; c.first = -1; c.kept = 0; c.w = 0; c.pad = 0;
-                    ct[n_ch] = c;
-                    for (int k = n_ch; k > lo; --k) ord[k] = ord[k - 1];
-                    ord[lo] = (uint32_t)n_ch;
-                    ++n_ch;
-                }
-            }
-        }
+        if (lane == 0) n_ch = chain_seeds(raw, ct, ord, total, ix, o, n_dup);
         n_ch = __shfl_sync(FULL, n_ch, 0);
         __syncwarp();
         // ---- weights (lanes over chains), min_chain_weight drop
         for (int k = lane; k < n_ch; k += 32) ct[k].w = (uint32_t)chain_weight(raw, ct[k]);
         __syncwarp();
         int n_out = 0, n_flt = 0; uint32_t seed_out = 0;
-        if (lane == 0 && n_ch) {
-            // mem_chain_flt: ord[] is the chain array `a` in pos order
-            int n = 0;
-            for (int i = 0; i < n_ch; ++i) { uint32_t c = ord[i]; if ((int)ct[c].w >= o.min_chain_weight) ord[n++] = c; }
-            if (n) {
-                const ChainTmp* ctc = ct;
-                ks_introsort_dev(n, ord, [ctc](uint32_t x, uint32_t y) { return ctc[x].w > ctc[y].w; });
-                // `kept_idx` list lives in the tail of ord (n_alloc >= n_ch >= n ... use a second region: P.ord is
-                // n_alloc wide, chains <= seeds, so [n, 2n) may not exist; keep the list in ChainTmp.pad instead)
-                int n_kept = 0;
-                ct[ord[0]].kept = 3; ct[n_kept++].pad = 0;
-                for (int i = 1; i < n; ++i) {
-                    ChainTmp& ci = ct[ord[i]];
-                    int large_ovlp = 0, k;
-                    int bi = ci.f_qbeg, ei = ci.l_qbeg + ci.l_len;
-                    for (k = 0; k < n_kept; ++k) {
-                        int j = (int)ct[k].pad;
-                        ChainTmp& cj = ct[ord[j]];
-                        int bj = cj.f_qbeg, ej = cj.l_qbeg + cj.l_len;
-                        int b_max = bj > bi ? bj : bi, e_min = ej < ei ? ej : ei;
-                        if (e_min > b_max) {   // is_alt is always 0 on this path (reference bwa.cpp:84-91)
-                            int li = ei - bi, lj = ej - bj, min_l = li < lj ? li : lj;
-                            if ((float)(e_min - b_max) >= __fmul_rn((float)min_l, o.mask_level) && min_l < o.max_chain_gap) {
-                                large_ovlp = 1;
-                                if (cj.first < 0) cj.first = i;
-                                if ((float)(int)ci.w < __fmul_rn((float)(int)cj.w, o.drop_ratio) && (int)cj.w - (int)ci.w >= o.min_seed_len << 1) break;
-                            }
-                        }
-                    }
-                    if (k == n_kept) { ct[n_kept++].pad = (uint32_t)i; ci.kept = large_ovlp ? 2 : 3; }
-                }
-                for (int k = 0; k < n_kept; ++k) { ChainTmp& c = ct[ord[ct[k].pad]]; if (c.first >= 0) ct[ord[c.first]].kept = 1; }
-                int i, k;
-                for (i = k = 0; i < n; ++i) {
-                    int kp = ct[ord[i]].kept;
-                    if (kp == 0 || kp == 3) continue;
-                    if (++k >= o.max_chain_extend) break;
-                }
-                for (; i < n; ++i) if (ct[ord[i]].kept < 3) ct[ord[i]].kept = 0;
-                n_flt = n;
-            }
-        }
+        if (lane == 0 && n_ch) n_flt = chain_filter(ct, ord, n_ch, o);
         n_flt = __shfl_sync(FULL, n_flt, 0);
         __syncwarp();
         // ---- emit kept chains in order with contiguous seeds; long reads first pass every short seed through
@@ -349,6 +463,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS) chain_build(ChainParams P, DevI
 }
 
 }  // namespace
+
+void launch_chain_thread(const ChainParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st) {
+    if (!p.todo || p.n_reads == 0) return;
+    chain_build_thread<<<(p.n_reads + CHAIN_THREADS - 1) / CHAIN_THREADS, CHAIN_THREADS, 0, st>>>(p, ix, o);
+}
 
 void launch_chain(const ChainParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st) {
     int nb = 0, dev = 0, sms = 148;

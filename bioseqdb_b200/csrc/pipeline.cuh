@@ -29,7 +29,9 @@ struct ChainParams {
     unsigned long long* counters;  // optional: [0] = SA lookups, [1] = equal-pos chain events (SURVEY A.5 corner)
     const double* logtab;          // host-libm log(l) for l <= longest read; nullptr when no read is long enough for mem_flt_chained_seeds
     unsigned long long* sw_cells;  // optional: cells of the seed-filter local SW
+    uint32_t* todo; uint32_t* todo_cnt;   // reads the thread-per-read pass left for the warp kernel (nullptr = the warp kernel takes every read)
 };
+void launch_chain_thread(const ChainParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st);
 void launch_chain(const ChainParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st);
 
 // Result of one ksw_extend2 call computed ahead of sw_extend by the thread-per-extension kernels (extend_plan.cu).  sw_extend

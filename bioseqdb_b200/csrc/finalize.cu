@@ -269,6 +269,53 @@ __device__ void reg2aln_warp(const FinalizeParams& P, const DevIndex& ix, const 
     __syncwarp();
 }
 
+// Thread per read: the phase-1 work of a read with ONE region that the thread-per-region kernels can align (no dedup / patch to
+// do; mem_mark_primary_se of a single region is three assignments) -- the common case of a short-read batch.  Every other read
+// is queued for regs_finalize.  Job-list slots are claimed once per warp and list.
+__global__ void __launch_bounds__(128) regs_finalize_thread(FinalizeParams P, DevIndex ix, DevOpts o) {
+    const uint32_t r = blockIdx.x * 128 + threadIdx.x;
+    const int lane = lane_id();
+    int cat = 0;      // 0 nothing to push, 1 register-band DP job, 2 wide-band DP job, 3 no-DP job
+    NarrowJob jb; jb.r = r; jb.slot = 0; jb.w2 = 0; jb.last_sc = -(1 << 30); jb.it = 0; jb.score = 0;
+    if (r < P.n_reads) {
+        const ReadBlock blk = P.blocks[r];
+        const int n = blk.n_alloc ? (int)P.reg_cnt[r] : 0;
+        bool done = false;
+        if (n == 0) { P.row_cnt[r] = 0; done = true; }
+        else if (n == 1) {
+            RegRec ar = P.regs[blk.base];
+            const int ncls = narrow_class(o, ar, P.max_len);
+            if (ncls != 0) {
+                ar.sub = 0; ar.secondary = -1; ar.hash = hash_64((uint64_t)P.ids[r]);      // mem_mark_primary_se, n == 1
+                P.regs[blk.base] = ar;
+                P.rows[blk.base] = row_from_reg(ar, P.ann_id);
+                jb.slot = blk.base; jb.w2 = reg2aln_w2(o, ar);
+                if (ncls == 1) cat = narrow_is_big(o, ar.qe - ar.qb, (int)(ar.re - ar.rb), jb.w2, mat_is_simple(o.mat)) ? 2 : 1;
+                else cat = 3;
+                P.row_cnt[r] = 1;
+                done = true;
+            }
+        }
+        if (!done) P.todo[atomicAdd(P.todo_cnt, 1u)] = r;
+    }
+    NarrowJob* lists = reinterpret_cast<NarrowJob*>(P.narrow_jobs);
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int c = 1; c <= 3; ++c) {
+        const uint32_t mask = __ballot_sync(FULL, cat == c);
+        if (!mask) continue;
+        uint32_t base = 0;
+        if (lane == __ffs(mask) - 1) base = atomicAdd(P.narrow_cnt + (c == 1 ? 0 : (c == 2 ? 5 : 3)), (uint32_t)__popc(mask));
+        base = __shfl_sync(FULL, base, __ffs(mask) - 1);
+        if (cat == c) {
+            const uint32_t k = base + (uint32_t)__popc(mask & lt);
+            if (c == 1) lists[k] = jb;
+            else if (c == 2) lists[P.narrow_cap - 1u - k] = jb;
+            else lists[2u * P.narrow_cap + k] = jb;
+        }
+    }
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(FIN_THREADS, 6) regs_finalize(FinalizeParams P, DevIndex ix, DevOpts o, uint32_t cig_cap, uint32_t rseq_cap) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -292,9 +339,11 @@ __global__ void __launch_bounds__(FIN_THREADS, 6) regs_finalize(FinalizeParams P
         S.z = reinterpret_cast<uint8_t*>(S.cig + cig_cap);
     }
     unsigned long long cells = 0, calls = 0;
+    const uint32_t n_todo = P.todo ? *P.todo_cnt : P.n_reads;     // with the thread pass on: only the reads it queued
     for (;;) {
-        uint32_t r = next_ticket(P.ticket);
-        if (r >= P.n_reads) break;
+        const uint32_t tk = next_ticket(P.ticket);
+        if (tk >= n_todo) break;
+        const uint32_t r = P.todo ? P.todo[tk] : tk;
         const ReadBlock blk = P.blocks[r];
         int n = blk.n_alloc ? (int)P.reg_cnt[r] : 0;
         if (n == 0) { if (lane == 0) P.row_cnt[r] = 0; continue; }
@@ -846,7 +895,11 @@ void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts&
     if (blocks < 1) blocks = 1;
     const bool smem_ok = fin_use_smem(p.max_len, rseq_cap);
     const size_t smem = smem_ok ? fin_fast_bytes(p.max_len, rseq_cap) * FIN_WARPS : 0;
-    // phase 1: dedup / patch / primary marking; wide regions aligned inline, narrow ones queued
+    // phase 1: dedup / patch / primary marking; wide regions aligned inline, narrow ones queued.  Single-region reads first, thread per read.
+    if (p.todo && p.narrow_jobs && p.n_reads) {
+        regs_finalize_thread<<<(p.n_reads + 127) / 128, 128, 0, st>>>(p, ix, o);
+        if (launches) ++*launches;
+    }
     if (smem_ok) regs_finalize<true><<<blocks, FIN_THREADS, smem, st>>>(p, ix, o, cig_cap, rseq_cap);
     else regs_finalize<false><<<blocks, FIN_THREADS, 0, st>>>(p, ix, o, cig_cap, rseq_cap);
     if (launches) ++*launches;

@@ -97,6 +97,7 @@ struct FinalizeParams {
     uint32_t* overflow;
     uint32_t* need_rseq;           // see ExtendParams
     unsigned long long* counters;  // optional: [0] = ksw_global2 cells, [1] = calls
+    uint32_t* todo; uint32_t* todo_cnt;   // reads the thread-per-read pass left for regs_finalize (nullptr = no thread pass)
 };
 void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint32_t rseq_cap, int n_warps, uint64_t* launches);
 size_t narrow_zbuf_bytes(int* n_warps_out);

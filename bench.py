@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000)
     ap.add_argument("--ref-mbp", type=int, default=100)
+    ap.add_argument("--contigs", action="store_true", help="BASELINE configs[4] reference: 500 k contigs of 500-1500 bp (synth.config_row_lengths('C5')) instead of 10 rows")
     ap.add_argument("--opts", default="sql", choices=["sql", "canonical"])
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--err", default="0.008,0.001,0.001", help="substitution,insertion,deletion rates per base")
@@ -59,9 +60,14 @@ def parse():
 
 
 def workload(args, rank):
-    rows_n = 10
-    per = args.ref_mbp * 1_000_000 // rows_n
-    rows = synth.reference_rows([per] * rows_n)
+    if args.contigs:
+        lens = synth.config_row_lengths("C5")
+        rows = synth.reference_rows(lens)
+        args.ref_mbp = int(sum(lens) // 1_000_000)
+    else:
+        rows_n = 10
+        per = args.ref_mbp * 1_000_000 // rows_n
+        rows = synth.reference_rows([per] * rows_n)
     sub, ins, dele = [float(x) for x in args.err.split(",")]
     seqs, offs, truth = synth.simulate_reads(rows, args.reads, args.read_len, sub=sub, ins=ins, dele=dele, seed=synth.SEED_READS + rank,
                                              chunk=max(1, min(200_000, 40_000_000 // max(args.read_len, 1))))
@@ -175,7 +181,7 @@ def run_reference(args, rank, world):
 
 
 def config_dict(args, n_gpus, **extra):
-    d = {"workload": ("BASELINE configs[1]: " if (args.read_len == 150 and args.ref_mbp == 100) else "") + "%d simulated %dbp reads (error sub/ins/del %s) per GPU vs %d Mbp synthetic reference (10 rows), index resident" % (args.reads, args.read_len, args.err, args.ref_mbp),
+    d = {"workload": ("BASELINE configs[1]: " if (args.read_len == 150 and args.ref_mbp == 100 and not args.contigs) else "") + "%d simulated %dbp reads (error sub/ins/del %s) per GPU vs %d Mbp synthetic reference (%s), index resident" % (args.reads, args.read_len, args.err, args.ref_mbp, "500 k contigs of 500-1500 bp, BASELINE configs[4]" if args.contigs else "10 rows"),
          "options": "SQL default (o_del 6, e_del 6, o_ins 1, e_ins 1)" if args.opts == "sql" else "canonical bwa (6/1/6/1)",
          "reads_per_gpu": args.reads, "read_len": args.read_len, "ref_mbp": args.ref_mbp,
          "l2_policy": "per-step working set (index %d MB + batch pools > 1 GB) exceeds the 126 MB L2; no explicit flush" % (args.ref_mbp * 2 + args.ref_mbp * 8 + args.ref_mbp // 4),

@@ -783,9 +783,23 @@ int align_chunked(bsq_index* h, const char* seqs, const uint64_t* offs, const in
     }
     Batch* lane[2] = {&h->batch, &h->batch2};
     for (Batch* b : lane) if (!b->evx_ok) { for (auto& e : b->ev_x) cudaEventCreate(&e); b->evx_ok = true; }
-    const uint64_t CHUNK_READS = chunk_reads(n);
-    const uint64_t n_chunks = (n + CHUNK_READS - 1) / CHUNK_READS;
-    auto start_of = [&](uint64_t c) { return std::min<uint64_t>(c * CHUNK_READS, n); };
+    // chunk boundaries: uniform chunks, or (BSQ_CHUNK_FRACS="f0,f1,...") fractions of the batch -- the first chunk's upload and the
+    // last chunk's download are the only copies nothing hides, while every chunk pays the fixed cost of ~40 kernel tails
+    std::vector<uint64_t> starts;
+    {
+        static const char* fr = getenv("BSQ_CHUNK_FRACS");
+        if (fr) {
+            double acc = 0; starts.push_back(0);
+            for (const char* q = fr; *q;) { char* e; const double f = strtod(q, &e); if (e == q) break; acc += f; starts.push_back(std::min<uint64_t>(n, (uint64_t)(acc * (double)n))); q = *e ? e + 1 : e; }
+            if (starts.back() != n) starts.push_back(n);
+        } else {
+            const uint64_t CHUNK_READS = chunk_reads(n);
+            for (uint64_t s0 = 0; s0 < n; s0 += CHUNK_READS) starts.push_back(s0);
+            starts.push_back(n);
+        }
+    }
+    const uint64_t n_chunks = starts.size() - 1;
+    auto start_of = [&](uint64_t c) { return starts[std::min<uint64_t>(c, n_chunks)]; };
     auto launch = [&](uint64_t c) -> int {
         Batch& b = *lane[c & 1];
         const uint64_t s0 = start_of(c), cnt = start_of(c + 1) - s0;

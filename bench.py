@@ -123,16 +123,18 @@ class ClockSampler:
 
 def seed_traffic(args):
     """dram__bytes_read + dram__bytes_write of one seed_smem launch from the committed ncu --set full capture of THIS workload
-    (profiles/r01_seed_traffic.json); None when the run is a different workload."""
+    (profiles/r01_seed_traffic.json: one record per profiled workload); None when the run is a different workload."""
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_seed_traffic.json")
     try:
         with open(path) as f:
             t = json.load(f)
     except (OSError, ValueError):
         return None
-    w = t.get("workload", {})
-    if w.get("reads") == args.reads and w.get("read_len") == args.read_len and w.get("ref_mbp") == args.ref_mbp and w.get("opts") == args.opts:
-        return t
+    for rec in (t if isinstance(t, list) else [t]):
+        w = rec.get("workload", {})
+        if w.get("reads") == args.reads and w.get("read_len") == args.read_len and w.get("ref_mbp") == args.ref_mbp and w.get("opts") == args.opts \
+                and not getattr(args, "contigs", False):
+            return rec
     return None
 
 

@@ -45,7 +45,6 @@ struct ExtMemo {
 static_assert(sizeof(ExtMemo) == 48, "ExtMemo layout");
 constexpr int EXT_MEMO_MAXQ = 136;     // longest query side the thread kernels take
 constexpr int EXT_MEMO_CHAINS = 4;     // chains per read whose first extension is planned; job id = read * EXT_MEMO_CHAINS + chain
-constexpr int EXT_MEMO_CLASSES = 4;    // job classes by query length (<= 32, 64, 96, 136 columns): shared memory per thread differs
 
 struct ExtendParams {
     const uint8_t* seqs; const uint64_t* offs; uint32_t n_reads;

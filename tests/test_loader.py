@@ -13,6 +13,21 @@ def test_fasta_records_follow_the_importer():
     assert fasta_records(b"") == []
 
 
+def test_datum_image_layout_matches_the_payload_goldens():
+    """SURVEY.md 8c payload goldens (rule of sequence.cpp:209-245) through the datum image the GPU paths are compared with:
+    varlena length word << 2, holes_num, len, hole records {i64 offset, i32 len, char amb, 3 pad}, packed codes."""
+    import struct
+    from bioseqdb_b200.bwa import nuclseq_image
+    from bioseqdb_b200.sequence import nuclseq_from_text
+    assert nuclseq_image(nuclseq_from_text(b"ACGT")) == struct.pack("<III", 13 << 2, 0, 4) + bytes([0x1b])
+    assert nuclseq_image(nuclseq_from_text(b"ACGTA")) == struct.pack("<III", 14 << 2, 0, 5) + bytes([0x1b, 0x39])
+    img = nuclseq_image(nuclseq_from_text(b"ACNNGT"))
+    assert img == struct.pack("<III", (12 + 16 + 2) << 2, 1, 6) + struct.pack("<qi", 2, 2) + b"N\0\0\0" + bytes([0x16, 0xb9])
+    img = nuclseq_image(nuclseq_from_text(b"NNRRA"))
+    assert img[:12] == struct.pack("<III", (12 + 32 + 2) << 2, 2, 5)
+    assert img[12:44] == struct.pack("<qi", 0, 2) + b"N\0\0\0" + struct.pack("<qi", 2, 2) + b"R\0\0\0" and img[44:] == bytes([0x69, 0x1a])
+
+
 def _texts(rng, n, max_len):
     out = []
     for i in range(n):

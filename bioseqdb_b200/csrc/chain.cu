@@ -5,6 +5,7 @@
 // all lanes in parallel; the ordered-insert chaining itself is sequential bookkeeping on a few records.
 #include "pipeline.cuh"
 #include "ksort_dev.cuh"
+#include "launch_cache.cuh"
 
 namespace {
 
@@ -470,10 +471,6 @@ void launch_chain_thread(const ChainParams& p, const DevIndex& ix, const DevOpts
 }
 
 void launch_chain(const ChainParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st) {
-    int nb = 0, dev = 0, sms = 148;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_build, CHAIN_THREADS, 0);
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (nb < 1) nb = 1;
+    const int nb = cached_blocks_per_sm(chain_build, CHAIN_THREADS, 0), sms = cached_sm_count();
     chain_build<<<nb * sms, CHAIN_THREADS, 0, st>>>(p, ix, o);
 }

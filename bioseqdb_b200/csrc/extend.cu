@@ -6,6 +6,7 @@
 #include "pipeline.cuh"
 #include "ksw_warp.cuh"
 #include "ksort_dev.cuh"
+#include "launch_cache.cuh"
 
 namespace {
 
@@ -259,12 +260,7 @@ size_t extend_scratch_per_warp(uint32_t max_len, uint32_t rseq_cap) {
 static bool ext_use_smem(size_t per_warp) { return per_warp * EXT_WARPS <= 40 * 1024; }
 
 int extend_resident_warps() {
-    int nb = 0, dev = 0, sms = 148;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sw_extend<false>, EXT_THREADS, 0);
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (nb < 1) nb = 1;
-    return nb * sms * EXT_WARPS;
+    return cached_blocks_per_sm(sw_extend<false>, EXT_THREADS, 0) * cached_sm_count() * EXT_WARPS;
 }
 
 void launch_extend_finish(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st) {
@@ -273,19 +269,13 @@ void launch_extend_finish(const ExtendParams& p, const DevIndex& ix, const DevOp
 }
 
 void launch_extend(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = cached_sm_count();
     if (ext_use_smem(p.scratch_per_warp)) {
-        size_t smem = p.scratch_per_warp * EXT_WARPS;
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sw_extend<true>, EXT_THREADS, smem);
-        if (nb < 1) nb = 1;
+        const size_t smem = p.scratch_per_warp * EXT_WARPS;
+        const int nb = cached_blocks_per_sm(sw_extend<true>, EXT_THREADS, smem);
         sw_extend<true><<<nb * sms, EXT_THREADS, smem, st>>>(p, ix, o);
     } else {
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sw_extend<false>, EXT_THREADS, 0);
-        if (nb < 1) nb = 1;
+        const int nb = cached_blocks_per_sm(sw_extend<false>, EXT_THREADS, 0);
         sw_extend<false><<<nb * sms, EXT_THREADS, 0, st>>>(p, ix, o);
     }
 }

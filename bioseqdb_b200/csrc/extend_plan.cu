@@ -12,6 +12,7 @@
 // the recorded parameters, and computes everything else (further seeds, band retries, long sides) itself.
 #include "pipeline.cuh"
 #include "ksw_thread.cuh"
+#include "launch_cache.cuh"
 #include <algorithm>
 
 namespace {
@@ -193,10 +194,7 @@ __global__ void __launch_bounds__(DP_THREADS) ext_thread_dp(ExtendParams P, DevI
 template <int NCOL>
 void launch_dp(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, int side, int key_lo, int key_hi, int sms) {
     constexpr size_t smem = (size_t)(NCOL + (NCOL + 6) / 8) * DP_THREADS * 4;
-    cudaFuncSetAttribute(ext_thread_dp<NCOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ext_thread_dp<NCOL>, DP_THREADS, smem);
-    if (nb < 1) nb = 1;
+    const int nb = cached_blocks_per_sm(ext_thread_dp<NCOL>, DP_THREADS, smem);
     const unsigned tiles = (p.n_reads * EXT_MEMO_CHAINS + DP_THREADS - 1) / DP_THREADS;
     const unsigned grid = std::min<unsigned>(tiles, (unsigned)(nb * sms));
     ext_thread_dp<NCOL><<<grid, DP_THREADS, smem, st>>>(p, ix, o, side, key_lo, key_hi);
@@ -208,9 +206,7 @@ void launch_dp(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cuda
 // concurrently -- each class alone leaves most of the chip idle in its tail; nullptr = everything on st.
 void launch_extend_memo(const ExtendParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint64_t* launches, const ExtAux* aux) {
     if (!p.memo || p.n_reads == 0) return;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = cached_sm_count();
     const unsigned blocks = (p.n_reads + PLAN_THREADS - 1) / PLAN_THREADS;
     cudaMemsetAsync(p.memo_hist, 0, 6 * EXT_MEMO_BINS * sizeof(uint32_t), st);
     ext_plan<<<blocks, PLAN_THREADS, 0, st>>>(p, ix, o);

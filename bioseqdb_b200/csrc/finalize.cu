@@ -8,6 +8,7 @@
 #include "pipeline.cuh"
 #include "ksw_warp.cuh"
 #include "ksort_dev.cuh"
+#include "launch_cache.cuh"
 
 namespace {
 
@@ -856,25 +857,14 @@ size_t finalize_scratch_per_warp(uint32_t max_len, uint32_t rseq_cap, uint32_t* 
 static bool fin_use_smem(uint32_t max_len, uint32_t rseq_cap) { return fin_fast_bytes(max_len, rseq_cap) * FIN_WARPS <= 40 * 1024; }
 
 int finalize_resident_warps() {
-    int nb = 0, dev = 0, sms = 148;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, regs_finalize<false>, FIN_THREADS, 0);
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (nb < 1) nb = 1;
-    return nb * sms * FIN_WARPS;
+    return cached_blocks_per_sm(regs_finalize<false>, FIN_THREADS, 0) * cached_sm_count() * FIN_WARPS;
 }
 
 // resident warps of the two thread-per-region kernels and the traceback buffer that serves both
 static void narrow_geometry(int* warps_smem, int* warps_reg, size_t* zbytes) {
-    int nb = 0, nr = 0, dev = 0, sms = 148;
     const size_t smem = (size_t)NARROW_THREADS * (2 * NARROW_NC * 4 + NARROW_QMAX);
-    cudaFuncSetAttribute(regs_cigar_narrow<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, regs_cigar_narrow<0>, NARROW_THREADS, smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nr, regs_cigar_narrow<1>, NARROW_THREADS, 0);
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (nb < 1) nb = 1;
-    if (nr < 1) nr = 1;
+    const int nb = cached_blocks_per_sm(regs_cigar_narrow<0>, NARROW_THREADS, smem), nr = cached_blocks_per_sm(regs_cigar_narrow<1>, NARROW_THREADS, 0);
+    const int sms = cached_sm_count();
     const int ws = nb * sms * (NARROW_THREADS / 32), wr = nr * sms * (NARROW_THREADS / 32);
     if (warps_smem) *warps_smem = ws;
     if (warps_reg) *warps_reg = wr;

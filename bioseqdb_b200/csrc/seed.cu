@@ -12,6 +12,7 @@
 // and S still fit 32 bits (they are bounded by the parent interval), only tk[c] needs its checkpoint's two
 // halves, i.e. two more single-contributor reductions.  Interval lists and the read live in shared memory.
 #include "seed.cuh"
+#include "launch_cache.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -744,12 +745,8 @@ template <class IdxT> size_t lists_bytes(uint32_t list_cap, uint32_t read_cap) {
 }
 
 template <class IdxT, bool SMEM, int MINB> void launch_mode(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, size_t smem, int* n_warps_out) {
-    int dev = 0, sms = 148, nb = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(seed_smem<IdxT, SMEM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seed_smem<IdxT, SMEM, MINB>, SEED_THREADS, smem);
-    if (nb < 1) nb = 1;
+    const int sms = cached_sm_count();
+    int nb = cached_blocks_per_sm(seed_smem<IdxT, SMEM, MINB>, SEED_THREADS, smem);
     if (nb * SEED_WARPS > 64) nb = 64 / SEED_WARPS;
     if (n_warps_out) *n_warps_out = nb * sms * SEED_WARPS;
     seed_smem<IdxT, SMEM, MINB><<<nb * sms, SEED_THREADS, smem, st>>>(p, ix, o);
@@ -798,10 +795,7 @@ void build_isa(const DevIndex& ix, void* isa, cudaStream_t st, uint64_t* launche
 
 int seed_resident_warps() {
     // upper bound used to size the per-warp global scratch: 64 warps per SM
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return 64 * sms;
+    return 64 * cached_sm_count();
 }
 
 bool seed_lists_fit_smem(uint32_t list_cap, uint32_t read_cap, int sa_bytes) {

@@ -503,7 +503,12 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
     ENS(b.ctl.ensure(64)); ENS(b.chain_todo.ensure(n)); ENS(b.fin_todo.ensure(n));
     // the thread-per-extension pre-pass packs column scores in 16 bits: every value it stores is <= l_query * (a + 1)
     static const bool no_memo = getenv("BSQ_NO_EXT_MEMO") != nullptr;
-    const bool use_memo = !no_memo && max_len <= 512 && (uint64_t)max_len * (uint64_t)(o.a + 1) < 32000 && (uint64_t)n * EXT_MEMO_CHAINS < (1ull << 31);
+    // Small batches take the warp-cooperative kernels for the DP stages: the thread-per-extension / thread-per-region kernels are built for
+    // throughput (one thread runs a whole DP, ~0.5 ms of latency whatever the batch size), which is what a one-read call of
+    // nuclseq_search_bwa would wait for.  BSQ_SMALL_BATCH_READS moves the threshold (0 = thread kernels always; the parity tests use that).
+    static const long small_n = getenv("BSQ_SMALL_BATCH_READS") ? atol(getenv("BSQ_SMALL_BATCH_READS")) : 40000;   // measured crossover ~50 k reads (scripts/latency.py)
+    const bool small_batch = (long)n < small_n;
+    const bool use_memo = !no_memo && !small_batch && max_len <= 512 && (uint64_t)max_len * (uint64_t)(o.a + 1) < 32000 && (uint64_t)n * EXT_MEMO_CHAINS < (1ull << 31);
     if (use_memo) {
         const size_t jobs2 = (size_t)n * EXT_MEMO_CHAINS * 2;
         ENS(b.ext_memo.ensure(jobs2)); ENS(b.ext_memo_key.ensure(jobs2)); ENS(b.ext_memo_perm.ensure(jobs2));
@@ -554,11 +559,11 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
         P.seqs = b.seqs.p; P.offs = b.offs.p; P.ids = b.ids.p; P.n_reads = n; P.blocks = b.blocks.p; P.regs = b.regs.p; P.reg_cnt = b.reg_cnt.p;
         P.rows = b.rows.p; P.row_cnt = b.row_cnt.p; P.cigar_pool = b.cigar.p; P.cigar_cap = b.cigar_cap; P.cigar_top = b.ctl.p + 6;
         P.scratch = b.fin_scratch.p; P.scratch_per_warp = fin_per_warp; P.max_len = max_len; P.z_cap = z_cap; P.ann_id = h->d_ann_id;
-        P.narrow_jobs = b.narrow_jobs.p; P.narrow_cap = b.pool_cap; P.narrow_cnt = b.ctl.p + 32; P.wide_jobs = b.wide_jobs.p; P.wide_cnt = b.ctl.p + 25;
+        P.narrow_jobs = small_batch ? nullptr : b.narrow_jobs.p; P.narrow_cap = b.pool_cap; P.narrow_cnt = b.ctl.p + 32; P.wide_jobs = b.wide_jobs.p; P.wide_cnt = b.ctl.p + 25;
         P.narrow_z = b.narrow_z.p; P.narrow_warps = narrow_warps;
         P.ticket = b.ctl.p + 40; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 6 : nullptr;
         static const bool no_thread_fin = getenv("BSQ_NO_FIN_THREAD") != nullptr;
-        P.todo = no_thread_fin ? nullptr : b.fin_todo.p; P.todo_cnt = b.ctl.p + 58;
+        P.todo = (no_thread_fin || small_batch) ? nullptr : b.fin_todo.p; P.todo_cnt = b.ctl.p + 58;
         launch_finalize(P, ix, o, st, rseq_cap, fin_warps, &T.launches);
     }
     // compact rows: exclusive scan of row_cnt (n + 1 entries, the last one is a zero pad) -> row_off

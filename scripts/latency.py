@@ -14,13 +14,14 @@ ix = BwaIndex(0, to_bsq(O.sql_default_opts(5)))
 for i, r in enumerate(rows):
     ix.add_ref_sequence(i + 1, r.tobytes())
 ix.build()
-seqs, offs, _ = synth.simulate_reads(rows, 10000, 150, seed=5)
-ids = synth.lrand48_ids_fast(10000)
-for n in (1, 10, 100, 1000, 10000):
+sizes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1, 10, 100, 1000, 10000]
+seqs, offs, _ = synth.simulate_reads(rows, max(sizes), 150, seed=5)
+ids = synth.lrand48_ids_fast(max(sizes))
+for n in sizes:
     s, o, d = seqs[:int(offs[n])], offs[:n + 1], ids[:n]
     for _ in range(5):
         ix.align_batch(s, o, d)
-    reps = 40
+    reps = 40 if n <= 10000 else 10
     t0 = time.perf_counter()
     for _ in range(reps):
         res = ix.align_batch(s, o, d)

@@ -9,6 +9,12 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+# The library routes batches below BSQ_SMALL_BATCH_READS (default 40000) to its warp-cooperative DP kernels (call latency); the parity
+# tests use small batches but are there to check the throughput path (thread-per-extension / thread-per-region kernels), so they switch the
+# routing off.  tests/test_gpu_align.py::test_small_batch_routing covers the default routing in a process of its own.
+os.environ.setdefault("BSQ_SMALL_BATCH_READS", "0")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -218,3 +218,16 @@ def test_align_batch_chunked_fallback(gpu_lib, monkeypatch):
     for f in PARITY_FIELDS:
         assert np.array_equal(g.rows[f], r.rows[f]), f
     assert np.array_equal(_flat_cigars(g), _flat_cigars(r))
+
+
+def test_small_batch_routing(gpu_lib):
+    """Default routing of a small batch (warp-cooperative DP kernels instead of the thread-per-extension / thread-per-region ones):
+    the smoke check -- 2000 reads against the oracle, bit for bit -- in a fresh process without this suite's BSQ_SMALL_BATCH_READS=0."""
+    import os
+    import subprocess
+    import sys
+    env = {k: v for k, v in os.environ.items() if k != "BSQ_SMALL_BATCH_READS"}
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=env, capture_output=True, timeout=600)
+    assert p.returncode == 0, (p.stdout.decode()[-1500:], p.stderr.decode()[-1500:])
+    assert b"smoke ok" in p.stdout

@@ -37,3 +37,21 @@ def test_fails_loudly_without_gpu():
     from bioseqdb_b200 import BwaIndex, BsqError
     with pytest.raises(BsqError):
         BwaIndex()
+
+
+def test_bulk_loader_fails_loudly_without_gpu():
+    """bsq_nuclseq_from_text_batch needs no index handle: without a CUDA device it must report that, not convert on the host."""
+    import pytest
+    L = _lib.lib()
+    if L.bsq_device_count() > 0:
+        pytest.skip("a GPU is present")
+    from bioseqdb_b200 import BsqError
+    from bioseqdb_b200.loader import nuclseq_images
+    with pytest.raises(BsqError, match="no CUDA device"):
+        nuclseq_images([b"ACGT"])
+
+
+def test_new_struct_layouts():
+    import ctypes as C
+    assert C.sizeof(_lib.BsqTuples) == 48      # n_rows, off, ref_match, bytes, n_bytes, device_ms (+ padding)
+    assert C.sizeof(_lib.BsqNuclseqs) == 40    # n, off, bytes, n_bytes, device_ms (+ padding)

@@ -36,6 +36,39 @@ def fasta_records(data: bytes):
     return out
 
 
+def fasta_record_stream(lines):
+    """The same walk as fasta_records over an iterable of lines (bytes, with or without the trailing newline): yields (name, sequence)
+    one record at a time, so that a file of any size is read in bounded memory."""
+    name, seq = b"", []
+    for line in lines:
+        if line.endswith(b"\n"):
+            line = line[:-1]
+        if line[:1] == b">":
+            s = b"".join(seq)
+            if s:
+                yield name, s
+            name, seq = line[1:], []
+        else:
+            seq.append(line.upper())
+    s = b"".join(seq)
+    if s:
+        yield name, s
+
+
+def fasta_batches(lines, batch_bases: int = 1 << 30):
+    """Groups the records of fasta_record_stream into batches of at most batch_bases bases (a record longer than that is a batch of its
+    own): one bsq_nuclseq_from_text_batch call per batch keeps the device buffers bounded (text + images ~ 1.3 bytes per base)."""
+    batch, n = [], 0
+    for rec in fasta_record_stream(lines):
+        if batch and n + len(rec[1]) > batch_bases:
+            yield batch
+            batch, n = [], 0
+        batch.append(rec)
+        n += len(rec[1])
+    if batch:
+        yield batch
+
+
 def nuclseq_images(texts, device: int = 0):
     """texts: list of bytes. Returns (list of datum images, device_ms). Raises BsqError like nuclseq_in on an invalid letter."""
     L = _lib.lib()
@@ -58,6 +91,15 @@ def nuclseq_images(texts, device: int = 0):
         size = int(np.frombuffer(data[at:at + 4].tobytes(), dtype="<u4")[0]) >> 2
         images.append(data[at:at + size].tobytes())
     return images, ms
+
+
+def load_fasta_file(path: str, device: int = 0, batch_bases: int = 1 << 30):
+    """Yields (name, NUCLSEQ datum image) for every record of a FASTA file, converting batch_bases bases per GPU call."""
+    with open(path, "rb") as f:
+        for batch in fasta_batches(f, batch_bases):
+            images, _ = nuclseq_images([s for _, s in batch], device)
+            for (nm, _), img in zip(batch, images):
+                yield nm, img
 
 
 def load_fasta(data: bytes, device: int = 0):

@@ -13,6 +13,21 @@ def test_fasta_records_follow_the_importer():
     assert fasta_records(b"") == []
 
 
+def test_fasta_stream_and_batches():
+    import io
+    from bioseqdb_b200.loader import fasta_batches, fasta_record_stream
+    data = b">chr1 first\nacgtn\nACGT\n>empty\n>chr2\n\nNNNN\nacgu\n\n>tail"
+    assert list(fasta_record_stream(io.BytesIO(data))) == fasta_records(data)
+    assert list(fasta_record_stream(io.BytesIO(b"ACGT\n>x\nAC"))) == fasta_records(b"ACGT\n>x\nAC")
+    recs = [(b"r%d" % i, b"ACGT" * n) for i, n in enumerate([1, 2, 10, 1, 1, 30, 2])]
+    fa = b"".join(b">" + nm + b"\n" + s + b"\n" for nm, s in recs)
+    batches = list(fasta_batches(io.BytesIO(fa), batch_bases=40))
+    assert [r for b in batches for r in b] == recs                      # order and content kept
+    assert all(sum(len(s) for _, s in b) <= 40 or len(b) == 1 for b in batches)
+    assert [len(b) for b in batches] == [2, 1, 2, 1, 1]                 # greedy: 4+8 | 40 | 4+4 | 120 (over the cap: alone) | 8
+    assert list(fasta_batches(io.BytesIO(b""), 10)) == []
+
+
 def test_datum_image_layout_matches_the_payload_goldens():
     """SURVEY.md 8c payload goldens (rule of sequence.cpp:209-245) through the datum image the GPU paths are compared with:
     varlena length word << 2, holes_num, len, hole records {i64 offset, i32 len, char amb, 3 pad}, packed codes."""

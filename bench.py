@@ -1,23 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- 150 bp reads aligned per second through the bwa hot path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads R] [--ref-mbp M]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3|c4|c5]
 
-A step = one pass of the hot path (seed_smem -> chain_build -> sw_extend -> regs_finalize) over one batch
-of simulated reads against the resident FM-index.  Default workload = BASELINE.json configs[1]:
-1 M simulated 150 bp reads (1 % error) vs a 100 Mbp synthetic reference (10 rows x 10 Mbp) on one B200,
-"SQL default" options (what bwa_opts() really delivers).
+A step = one pass of the hot path (seed -> chain -> extend -> finalize -> rows in read order with MAPQ) over one batch of
+simulated reads against the resident FM-index.  --config picks a BASELINE.json configuration with BASELINE.md's exact row layout
+(default c2 = configs[1]: 1 M simulated 150 bp reads, 1 % error, vs 10 rows x 10 Mbp on one B200; "SQL default" options, i.e. what
+bwa_opts() really delivers):
 
-  value   whole-job reads/s with the reads already resident in HBM (device time, CUDA events on the
-          library's launching stream, max over ranks)
-  e2e     the same metric through the C-ABI call bsq_align_batch with HOST buffers: pinned host reads in,
-          host rows out, H2D and D2H inside the timed region
-  roofline  for the dominant kernel; cpu_baseline = the CPU oracle on this box's host cores (bounded sample)
+  c1  configs[0]  10 k x 150 bp reads vs 5 x 1 Mbp
+  c2  configs[1]  1 M x 150 bp reads vs 10 x 10 Mbp                                   <- the line the driver records
+  c3  configs[2]  10 M x 150 bp reads vs 24 human-chromosome-proportional rows, 3.1 Gbp: 1.25 M reads per GPU (10 M at N = 8)
+  c4  configs[3]  100 k x 10 kbp reads (10 % error) vs the c2 reference: 12.5 k reads per GPU (100 k at N = 8)
+  c5  configs[4]  1 M x 150 bp reads vs 500 k contigs of 500-1500 bp (index build reported in `index`)
 
---impl reference times the CPU path only (the reference cannot be compiled here -- no PostgreSQL / libbwa
-sources -- so this is the oracle port, all host threads, bounded sample per step).
-N > 1 (torchrun): the index is built on rank 0 and broadcast over NCCL, reads are sharded per rank
-(weak scaling: every rank aligns its own batch), no collective in the per-read path.
+  value     whole-job reads/s with the reads already resident in HBM (device time, CUDA events on the library's launching stream,
+            max over ranks)
+  e2e       the same metric through the C-ABI call bsq_align_batch with HOST buffers: pinned host reads in, host rows out, H2D and
+            D2H inside the timed region
+  roofline  for the dominant kernel; cpu_baseline = the CPU oracle on this box's host cores (bounded sample), with `parity`: the
+            oracle's rows compared with the GPU's for every read of that sample (all 24 parity fields + CIGAR words)
+
+--impl reference times the CPU path only (the reference cannot be compiled here -- no PostgreSQL / libbwa sources -- so this is the
+oracle port, all host threads, bounded sample per step).  N > 1 (torchrun): the index is built on rank 0 and broadcast over NCCL,
+reads are sharded per rank (weak scaling: every rank aligns its own batch), no collective in the per-read path.
+
+PARITY UNPINNED: the oracle restates lh3/bwa from its published algorithm; no libbwa binary or reference-held vector exists to pin
+it.  Every ratio this file prints is against that oracle.
 """
 from __future__ import annotations
 
@@ -41,6 +50,15 @@ from bioseqdb_b200 import synth  # noqa: E402
 METRIC = "150bp_reads_aligned_per_sec"
 UNIT = "reads/s"
 
+# (rows layout, reads per GPU, read length, error rates sub/ins/del, BASELINE.json configs index)
+CONFIGS = {
+    "c1": ("C1", 10_000, 150, "0.008,0.001,0.001", 0),
+    "c2": ("C2", 1_000_000, 150, "0.008,0.001,0.001", 1),
+    "c3": ("C3", 1_250_000, 150, "0.008,0.001,0.001", 2),
+    "c4": ("C2", 12_500, 10_000, "0.04,0.03,0.03", 3),
+    "c5": ("C5", 1_000_000, 150, "0.008,0.001,0.001", 4),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -48,26 +66,45 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=1_000_000)
-    ap.add_argument("--ref-mbp", type=int, default=100)
-    ap.add_argument("--contigs", action="store_true", help="BASELINE configs[4] reference: 500 k contigs of 500-1500 bp (synth.config_row_lengths('C5')) instead of 10 rows")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--reads", type=int, default=None, help="reads per GPU (default: the configuration's)")
+    ap.add_argument("--ref-mbp", type=int, default=None, help="ad hoc reference of 10 equal rows instead of the configuration's layout")
+    ap.add_argument("--repeats", action="store_true", help="plant repeat families in the reference (SURVEY.md 8d realism knob: 4 families x 8 copies per Mbp, 300-6000 bp, 2 %% divergence)")
     ap.add_argument("--opts", default="sql", choices=["sql", "canonical"])
-    ap.add_argument("--read-len", type=int, default=150)
-    ap.add_argument("--err", default="0.008,0.001,0.001", help="substitution,insertion,deletion rates per base")
+    ap.add_argument("--read-len", type=int, default=None)
+    ap.add_argument("--err", default=None, help="substitution,insertion,deletion rates per base")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU seconds of the cpu_baseline sample")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true", help="skip the tuple / loader / microbenchmark probes after the timed legs")
+    args = ap.parse_args()
+    layout, reads, rlen, err, idx = CONFIGS[args.config]
+    args.layout = layout
+    args.baseline_index = idx
+    if args.reads is None:
+        args.reads = reads
+    if args.read_len is None:
+        args.read_len = rlen
+    if args.err is None:
+        args.err = err
+    return args
+
+
+def reference_rows(args):
+    if args.ref_mbp is not None:
+        lens = [args.ref_mbp * 1_000_000 // 10] * 10
+    else:
+        lens = synth.config_row_lengths(args.layout)
+    rows = synth.reference_rows(lens)
+    if args.repeats:
+        mbp = max(1, int(sum(lens) // 1_000_000))
+        rows = synth.plant_repeats(rows, n_families=max(20, 4 * mbp), copies=8)
+    args.ref_bases = int(sum(lens))
+    args.ref_rows = len(lens)
+    return rows
 
 
 def workload(args, rank):
-    if args.contigs:
-        lens = synth.config_row_lengths("C5")
-        rows = synth.reference_rows(lens)
-        args.ref_mbp = int(sum(lens) // 1_000_000)
-    else:
-        rows_n = 10
-        per = args.ref_mbp * 1_000_000 // rows_n
-        rows = synth.reference_rows([per] * rows_n)
+    rows = reference_rows(args)
     sub, ins, dele = [float(x) for x in args.err.split(",")]
     seqs, offs, truth = synth.simulate_reads(rows, args.reads, args.read_len, sub=sub, ins=ins, dele=dele, seed=synth.SEED_READS + rank,
                                              chunk=max(1, min(200_000, 40_000_000 // max(args.read_len, 1))))
@@ -80,6 +117,24 @@ def opts_tuple(args, n_rows):
     if args.opts == "sql":
         return (19, max(500, 2 * n_rows), 1, 4, 5, 5, 100, 100, 6, 6, 1, 1)
     return (19, max(500, 2 * n_rows), 1, 4, 5, 5, 100, 100, 6, 1, 6, 1)
+
+
+def config_dict(args):
+    """The same dict in both arms (the driver compares them)."""
+    if args.ref_mbp is not None:
+        ref = "%d Mbp synthetic reference (10 equal rows, ad hoc)" % args.ref_mbp
+    else:
+        ref = {"C1": "5 rows x 1 Mbp", "C2": "10 rows x 10 Mbp", "C3": "24 human-chromosome-proportional rows, 3.1 Gbp",
+               "C5": "500 k contigs of 500-1500 bp (lengths not multiples of 4)"}[args.layout]
+    standard = args.ref_mbp is None and (args.reads, args.read_len, args.err) == CONFIGS[args.config][1:4] and not args.repeats
+    return {"workload": ("BASELINE configs[%d]: " % args.baseline_index if standard else "ad hoc: ") +
+                        "%d simulated %d bp reads (error sub/ins/del %s) per GPU vs %s%s, index resident" % (
+                            args.reads, args.read_len, args.err, ref, ", repeat families planted" if args.repeats else ""),
+            "config": args.config,
+            "options": "SQL default (o_del 6, e_del 6, o_ins 1, e_ins 1)" if args.opts == "sql" else "canonical bwa (6/1/6/1)",
+            "reads_per_gpu": args.reads, "read_len": args.read_len, "ref_layout": args.layout if args.ref_mbp is None else "10 equal rows",
+            "l2_policy": "per-step working set (FM-index + full SA + batch pools, > 1 GB) exceeds the 126 MB L2; no explicit flush",
+            "parallelism": "reads sharded over %d GPU(s), index replicated" % args.gpus}
 
 
 class ClockSampler:
@@ -122,9 +177,9 @@ class ClockSampler:
 
 
 def seed_traffic(args):
-    """dram__bytes_read + dram__bytes_write of one seed_smem launch from the committed ncu --set full capture of THIS workload
-    (profiles/r01_seed_traffic.json: one record per profiled workload); None when the run is a different workload."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_seed_traffic.json")
+    """dram__bytes_read + dram__bytes_write of one launch of the dominant seeding kernel from the committed ncu --set full capture of
+    THIS workload (profiles/seed_traffic.json: one record per profiled workload and kernel version); None for any other workload."""
+    path = os.path.join(ROOT, "profiles", "seed_traffic.json")
     try:
         with open(path) as f:
             t = json.load(f)
@@ -132,8 +187,8 @@ def seed_traffic(args):
         return None
     for rec in (t if isinstance(t, list) else [t]):
         w = rec.get("workload", {})
-        if w.get("reads") == args.reads and w.get("read_len") == args.read_len and w.get("ref_mbp") == args.ref_mbp and w.get("opts") == args.opts \
-                and not getattr(args, "contigs", False):
+        if w.get("config") == args.config and w.get("reads") == args.reads and w.get("read_len") == args.read_len and w.get("opts") == args.opts \
+                and args.ref_mbp is None and not args.repeats:
             return rec
     return None
 
@@ -144,6 +199,14 @@ def measured_peaks():
         with open(p) as f:
             return json.load(f), "measured (MEASURED_PEAKS.json)"
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def sized_sample(orc, args, seqs, offs, ids, cores):
+    """Reads of the workload that cost about --cpu-seconds of all-core CPU work (probed), capped at the batch."""
+    probe = max(16, min(20_000, args.reads, 3_000_000 // max(args.read_len, 1)))
+    r = orc.align_batch(seqs[:int(offs[probe])], offs[:probe + 1], ids[:probe], cores)
+    rate = probe / max(r["seconds"], 1e-9)
+    return int(min(args.reads, max(probe, rate * args.cpu_seconds))), probe, rate
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -157,12 +220,20 @@ def run_reference(args, rank, world):
     orc = O.OracleIndex(O.Opts(*ot))
     for i, r in enumerate(rows):
         orc.add_ref_text(i + 1, r.tobytes())
-    build_s = orc.build()
-    # bounded sample per step: size it from a short probe so that K + W steps end within a few minutes
-    probe = max(16, min(20_000, args.reads, 3_000_000 // max(args.read_len, 1)))
-    r = orc.align_batch(seqs[:int(offs[probe])], offs[:probe + 1], ids[:probe], cores)
-    rate = probe / max(r["seconds"], 1e-9)
-    sample = int(min(args.reads, max(probe, rate * args.cpu_seconds)))
+    if args.ref_bases * 2 >= (1 << 31):
+        # the reference itself cannot index this text (is_bwt takes an int length, bwa.cpp:10,26,47) and the oracle's SA-IS would run for
+        # the better part of an hour: the FM-index arrays (mathematically unique) are taken from the GPU build; the timed path is alignment only
+        from bioseqdb_b200 import BwaIndex, BsqOpts
+        ix = BwaIndex(0, BsqOpts(*ot))
+        ix.add_ref_sequences(list(range(1, len(rows) + 1)), rows)
+        ix.build()
+        orc.adopt(ix.bwt_plain(), int(ix.meta().primary), ix.sa_sampled())
+        ix.close()
+        how = "FM-index arrays adopted from the GPU build (the reference's is_bwt(int n) cannot index this text; not in the step)"
+    else:
+        build_s = orc.build()
+        how = "index built once by the oracle's SA-IS in %.1f s (not in the step)" % build_s
+    sample, _probe, _rate = sized_sample(orc, args, seqs, offs, ids, cores)
     times = []
     for s in range(args.warmup + args.steps):
         r = orc.align_batch(seqs[:int(offs[sample])], offs[:sample + 1], ids[:sample], cores)
@@ -173,26 +244,34 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-        "data": "synthetic", "config": config_dict(args, 1, sample_reads=sample),
+        "data": "synthetic", "config": config_dict(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d of %d reads per step, all %d host threads; index built once by the oracle's SA-IS in %.1f s (not in the step)" % (sample, args.reads, cores, build_s)},
+                         "sample": "%d of %d reads per step, all %d host threads; %s" % (sample, args.reads, cores, how)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "parity_pinning": "unpinned (oracle restates lh3/bwa; no libbwa binary or reference vector to pin it)",
         "note": "the reference cannot be compiled in this image (no PostgreSQL, libbwa, htslib sources): this arm is the CPU oracle port of the same path",
     }
     print(json.dumps(line), flush=True)
 
 
-def config_dict(args, n_gpus, **extra):
-    d = {"workload": ("BASELINE configs[1]: " if (args.read_len == 150 and args.ref_mbp == 100 and not args.contigs) else "") + "%d simulated %dbp reads (error sub/ins/del %s) per GPU vs %d Mbp synthetic reference (%s), index resident" % (args.reads, args.read_len, args.err, args.ref_mbp, "500 k contigs of 500-1500 bp, BASELINE configs[4]" if args.contigs else "10 rows"),
-         "options": "SQL default (o_del 6, e_del 6, o_ins 1, e_ins 1)" if args.opts == "sql" else "canonical bwa (6/1/6/1)",
-         "reads_per_gpu": args.reads, "read_len": args.read_len, "ref_mbp": args.ref_mbp,
-         "l2_policy": "per-step working set (index %d MB + batch pools > 1 GB) exceeds the 126 MB L2; no explicit flush" % (args.ref_mbp * 2 + args.ref_mbp * 8 + args.ref_mbp // 4),
-         "parallelism": "reads sharded over %d GPU(s), index replicated" % n_gpus}
-    d.update(extra)
-    return d
-
-
 # ------------------------------------------------------------------------------------------ our arm
+def rows_digest(res):
+    """SHA-1 over everything the step produced (row offsets, row fields, CIGAR words): two builds / code paths compare run to run."""
+    import hashlib
+    total_rows = int(res.row_off[-1])
+    dg = hashlib.sha1()
+    dg.update(np.ascontiguousarray(res.row_off).tobytes())
+    rr = res.rows[:total_rows]
+    for name in rr.dtype.names:
+        if name != "cigar_off":            # pool positions depend on the order warps allocate in; the words they point at do not
+            dg.update(np.ascontiguousarray(rr[name]).tobytes())
+    if total_rows:
+        nc = rr["n_cigar"].astype(np.int64)
+        starts = np.repeat(rr["cigar_off"].astype(np.int64) - np.concatenate(([0], np.cumsum(nc)[:-1])), nc)
+        dg.update(np.ascontiguousarray(res.cigar[starts + np.arange(int(nc.sum()), dtype=np.int64)]).tobytes())
+    return dg.hexdigest()
+
+
 def run_ours(args, rank, world, local_rank):
     import ctypes as C
     import torch
@@ -209,20 +288,24 @@ def run_ours(args, rank, world, local_rank):
     ot = opts_tuple(args, len(rows))
     ix = BwaIndex(dev, BsqOpts(*ot))
     bcast_bytes = 0
+    bcast_s = 0.0
     t0 = time.time()
+    t_add = 0.0
     if world == 1 or rank == 0:
-        for i, r in enumerate(rows):
-            ix.add_ref_sequence(i + 1, r)
+        ix.add_ref_sequences(list(range(1, len(rows) + 1)), rows)
+        t_add = time.time() - t0
         ix.build()
-    else:
-        for i, r in enumerate(rows):
-            ix._refs.append((i + 1, None))
-            ix.n_rows += 1
+    build_wall = time.time() - t0
     if world > 1:
         from bioseqdb_b200.dist import broadcast_index
+        dist.barrier()
+        tb = time.time()
         bcast_bytes = broadcast_index(ix, rank, dist)
+        dist.barrier()
+        bcast_s = time.time() - tb
     meta = ix.meta()
-    build_wall = time.time() - t0
+    prep_ms = C.c_float(0)
+    _lib.check(ix.L.bsq_index_prepare(ix.h, C.byref(prep_ms)))     # per-device derived arrays (inverse SA, prefix table)
     n = args.reads
 
     def barrier():
@@ -261,29 +344,18 @@ def run_ours(args, rank, world, local_rank):
     clocks = clk.summary()
     res = ix.download_result()
     total_rows = int(res.row_off[-1])
-    # sanity against the simulator's truth (parity is GPU vs oracle in tests/; this is a scale check): the first row of a
+    # sanity against the simulator's truth (parity is GPU vs oracle below and in tests/; this is a scale check): the first row of a
     # read is its best hit -- same reference row, same strand, position within the indel slack
     first = res.row_off[:-1].astype(np.int64)
     has = np.diff(res.row_off.astype(np.int64)) > 0
     pr = res.rows[np.minimum(first, max(total_rows - 1, 0))]
     okk = has & (pr["rid"] == truth[0]) & (pr["is_rev"] == truth[2].astype(np.int32)) & (np.abs(pr["pos"] - truth[1]) <= 16 + args.read_len // 8)
     truth_frac = float(okk.mean())
-    # digest of everything the step produced (row records, CIGAR words, row offsets): two builds / code paths can be compared run to run
-    import hashlib
-    dg = hashlib.sha1()
-    dg.update(np.ascontiguousarray(res.row_off).tobytes())
-    rr = res.rows[:total_rows]
-    for name in rr.dtype.names:
-        if name != "cigar_off":            # pool positions depend on the order warps allocate in; the words they point at do not
-            dg.update(np.ascontiguousarray(rr[name]).tobytes())
-    if total_rows:
-        nc = rr["n_cigar"].astype(np.int64)
-        starts = np.repeat(rr["cigar_off"].astype(np.int64) - np.concatenate(([0], np.cumsum(nc)[:-1])), nc)
-        dg.update(np.ascontiguousarray(res.cigar[starts + np.arange(int(nc.sum()), dtype=np.int64)]).tobytes())
-    rows_digest = dg.hexdigest()
+    digest = rows_digest(res)
 
     # ---------------- e2e: host buffers through bsq_align_batch
     resp = C.POINTER(_lib.BsqResult)()
+
     def one_e2e():
         _lib.check(ix.L.bsq_align_batch(ix.h, C.c_void_p(seqs_pin.data_ptr()), C.c_void_p(offs_pin.data_ptr()), C.c_void_p(ids_pin.data_ptr()), n, C.byref(resp)))
         ix.L.bsq_result_free(resp)
@@ -303,6 +375,21 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_wall = time.time() - e0
 
+    # ---------------- e2e_rows: the reference's unit of output (the 15-column tuple, extension.cpp:282-305) through bsq_align_tuples
+    e2e_rows = None
+    if hasattr(ix, "align_tuples_raw"):
+        for _ in range(2):
+            ix.align_tuples_raw(seqs_pin.data_ptr(), offs_pin.data_ptr(), ids_pin.data_ptr(), n)
+        barrier()
+        r0 = time.time()
+        tup_ms = 0.0
+        tb = 0
+        for _ in range(args.steps):
+            tup_ms_i, tb = ix.align_tuples_raw(seqs_pin.data_ptr(), offs_pin.data_ptr(), ids_pin.data_ptr(), n)
+            tup_ms += tup_ms_i
+        barrier()
+        e2e_rows = {"ms": tup_ms, "wall": time.time() - r0, "d2h_bytes": tb}
+
     # ---------------- max over ranks
     def allmax(x):
         if dist is None:
@@ -314,12 +401,26 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms_max = allmax(e2e_dev_ms)
     wall_max = allmax(wall)
     e2e_wall_max = allmax(e2e_wall)
+    prep_ms_max = allmax(float(prep_ms.value))
+    e2e_rows_ms_max = allmax(e2e_rows["ms"]) if e2e_rows else None
     if dist is not None:
         tot = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
         dist.all_reduce(tot)
         launches_all = int(tot.item())
     else:
         launches_all = launches
+
+    # ---------------- results gathered on the host: every rank's rows to rank 0 over a gloo side group, timed
+    gather = None
+    if dist is not None:
+        from bioseqdb_b200.dist import gather_rows_host
+        gg = dist.new_group(backend="gloo")
+        dist.barrier()
+        g0 = time.time()
+        out = gather_rows_host(res.row_off, res.rows, res.cigar, dist, gg, rank, world)
+        dist.barrier()
+        gather = {"seconds": time.time() - g0, "rows_on_rank0": int(out[0][-1]) if out is not None else None,
+                  "how": "gloo gather of row offsets, rows and CIGAR words to rank 0 (host memory to host memory, one process per GPU)"}
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -329,15 +430,9 @@ def run_ours(args, rank, world, local_rank):
         dom = max(stage, key=stage.get)
         seed_bytes = 64.0 * 2.0 * ctr["n_extend"]                 # per launch: two 64-byte Occ blocks per bwt_extend
         seed_s = stage["seed"] / args.steps * 1e-3
-        gather = C.c_double(0)
-        _lib.check(ix.L.bsq_bench_gather(ix.h, 1 << 28, 3, C.byref(gather)))
-        dpx = C.c_double(0)
-        _lib.check(ix.L.bsq_bench_dpx(dev, 3, C.byref(dpx)))
         roof = {"kernel": "seed_smem", "bound": "hbm", "achieved": seed_bytes / seed_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": seed_bytes / seed_s / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": seed_bytes, "random_gather_peak_gbs": gather.value,
-                "frac_of_random_gather": seed_bytes / seed_s / 1e9 / max(gather.value, 1e-9),
-                "dominant_kernel_by_time": dom,
+                "algorithmic_bytes_per_launch": seed_bytes, "dominant_kernel_by_time": dom,
                 "note": "algorithmic bytes = 2 Occ blocks x the reference's bwt_extend count (SURVEY 8d); the kernel resolves most of "
                         "those extends from the prefix table / by text comparison, so measured DRAM traffic is below the algorithmic figure"}
         tr = seed_traffic(args)
@@ -345,79 +440,104 @@ def run_ours(args, rank, world, local_rank):
             roof["traffic"] = tr["dram_bytes_per_launch"]
             roof["traffic_source"] = tr["source"]
             roof["traffic_gbs"] = tr["dram_bytes_per_launch"] / seed_s / 1e9
+            roof["traffic_frac_of_hbm_peak"] = roof["traffic_gbs"] / peaks["hbm_gbs"]
         ext_s = stage["extend"] / args.steps * 1e-3
         fin_s = stage["finalize"] / args.steps * 1e-3
-        sw = {"ksw_extend2_gcups": ctr["ext_cells"] / ext_s / 1e9, "ksw_global2_gcups_incl_finalize": ctr["glb_cells"] / fin_s / 1e9,
-              "ext_cells_per_launch": ctr["ext_cells"], "glb_cells_per_launch": ctr["glb_cells"], "dpx_peak_ginstr_s": dpx.value,
-              # DPX fraction = DPX instructions per cell of the shipped kernel (ksw_thread.cuh: one __vimax3_s32 and two
-              # __viaddmax_s32_relu) x cells/s over the whole extension stage, against the measured DPX issue peak
-              "ksw_extend2_dpx_per_cell": 3, "ksw_extend2_dpx_frac_of_peak": 3 * ctr["ext_cells"] / ext_s / 1e9 / dpx.value}
-        # row materialisation: NUCLSEQ images of ref_subseq / query_subseq + CIGAR strings of rank 0's rows, on the GPU
-        t0 = time.time()
-        tup = ix.tuples(res, seqs, offs)
-        tup_wall = time.time() - t0
-        # bulk loader: the reference rows' texts -> NUCLSEQ datums in one call (capped at 400 Mbp of text per probe)
-        from bioseqdb_b200.loader import nuclseq_images
-        ld_texts, ld_bases = [], 0
-        for r_ in rows:
-            if ld_bases + len(r_) > 400_000_000:
-                break
-            ld_texts.append(r_.tobytes()); ld_bases += len(r_)
-        _, ld_ms = nuclseq_images(ld_texts, local_rank) if ld_texts else ([], 0.0)
-        loader = {"sequences": len(ld_texts), "bases": ld_bases, "device_ms_incl_copies": ld_ms,
-                  "gbases_per_s_device": ld_bases / max(ld_ms * 1e-3, 1e-9) / 1e9}
-        tuples = {"rows": total_rows, "bytes": int(len(tup.data)), "device_ms_incl_copies": tup.device_ms, "wall_ms_python": 1e3 * tup_wall,
-                  "rows_per_s_device": total_rows / max(tup.device_ms * 1e-3, 1e-9)}
+        sw = {"ksw_extend2_gcups": ctr["ext_cells"] / max(ext_s, 1e-12) / 1e9, "ksw_global2_gcups_incl_finalize": ctr["glb_cells"] / max(fin_s, 1e-12) / 1e9,
+              "ext_cells_per_launch": ctr["ext_cells"], "glb_cells_per_launch": ctr["glb_cells"]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic", "config": config_dict(args, world),
+            "data": "synthetic", "config": config_dict(args),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max / args.steps, "wall_ms_per_step": 1e3 * e2e_wall_max / args.steps,
                     "h2d_ms_per_step": e2e_h2d_ms / args.steps, "d2h_ms_per_step": e2e_d2h_ms / args.steps},
             "gpu_launches": launches_all,
             "clocks": clocks,
-            "roofline": roof, "sw": sw, "tuples": tuples, "loader": loader,
+            "roofline": roof, "sw": sw,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "wall_ms_per_step": 1e3 * wall_max / args.steps,
-            "rows_per_step_rank0": total_rows, "truth_match_frac_rank0": truth_frac, "rows_sha1_rank0": rows_digest,
-            "index": {"build_ms_device": meta.build_ms, "build_wall_s": build_wall, "build_launches": int(meta.build_launches),
+            "rows_per_step_rank0": total_rows, "truth_match_frac_rank0": truth_frac, "rows_sha1_rank0": digest,
+            "index": {"build_ms_device": meta.build_ms, "build_wall_s": build_wall, "add_ref_wall_s": t_add, "build_launches": int(meta.build_launches),
                       "sort_pass_gbs": (meta.sort_pass_bytes / (meta.build_ms * 1e-3) / 1e9) if meta.build_ms else None,
-                      "seq_len": int(meta.seq_len), "broadcast_bytes": bcast_bytes},
+                      "seq_len": int(meta.seq_len), "broadcast_bytes": bcast_bytes, "broadcast_s": bcast_s,
+                      "derived_arrays_ms_max_over_ranks": prep_ms_max, "device_bytes": ix.device_bytes()},
             "counters_per_launch": ctr,
+            "parity_pinning": "unpinned (oracle restates lh3/bwa; no libbwa binary or reference vector to pin it)",
         }
+        if e2e_rows:
+            line["e2e_rows"] = {"value": n * world * args.steps / max(e2e_rows_ms_max * 1e-3, 1e-9), "unit": UNIT, "ms_per_step": e2e_rows_ms_max / args.steps,
+                                "d2h_bytes_per_step": e2e_rows["d2h_bytes"], "frac_of_e2e": (e2e_ms_max / max(e2e_rows_ms_max, 1e-9)),
+                                "what": "bsq_align_tuples with host buffers: rows + NUCLSEQ datum images of ref_subseq / query_subseq + CIGAR strings (the bwa_result tuple of extension.cpp:282-305) on the host"}
+        if gather:
+            line["gather"] = gather
+        if not args.no_extras:
+            gather_gbs = C.c_double(0)
+            _lib.check(ix.L.bsq_bench_gather(ix.h, 1 << 28, 3, C.byref(gather_gbs)))
+            dpx = C.c_double(0)
+            _lib.check(ix.L.bsq_bench_dpx(dev, 3, C.byref(dpx)))
+            roof["random_gather_peak_gbs"] = gather_gbs.value
+            roof["frac_of_random_gather"] = seed_bytes / seed_s / 1e9 / max(gather_gbs.value, 1e-9)
+            if roof.get("traffic_gbs"):
+                roof["traffic_frac_of_random_gather"] = roof["traffic_gbs"] / max(gather_gbs.value, 1e-9)
+            sw["dpx_peak_ginstr_s"] = dpx.value
+            # DPX fraction = DPX instructions per cell of the shipped kernel x cells/s over the whole extension stage, against
+            # the measured DPX issue peak
+            sw["ksw_extend2_dpx_per_cell"] = 3
+            sw["ksw_extend2_dpx_frac_of_peak"] = 3 * ctr["ext_cells"] / max(ext_s, 1e-12) / 1e9 / dpx.value
+            # row materialisation from a host result (the re-upload path) and the bulk loader (8f-4)
+            t0 = time.time()
+            tup = ix.tuples(res, seqs, offs)
+            tup_wall = time.time() - t0
+            from bioseqdb_b200.loader import nuclseq_images
+            ld_texts, ld_bases = [], 0
+            for r_ in rows:
+                if ld_bases + len(r_) > 400_000_000:
+                    break
+                ld_texts.append(r_.tobytes()); ld_bases += len(r_)
+            _, ld_ms = nuclseq_images(ld_texts, local_rank) if ld_texts else ([], 0.0)
+            line["loader"] = {"sequences": len(ld_texts), "bases": ld_bases, "device_ms_incl_copies": ld_ms,
+                              "gbases_per_s_device": ld_bases / max(ld_ms * 1e-3, 1e-9) / 1e9}
+            line["tuples"] = {"rows": total_rows, "bytes": int(len(tup.data)), "device_ms_incl_copies": tup.device_ms, "wall_ms_python": 1e3 * tup_wall,
+                              "rows_per_s_device": total_rows / max(tup.device_ms * 1e-3, 1e-9)}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, rows, seqs, offs, ids, ix, ot)
+            line["cpu_baseline"], line["parity"] = cpu_baseline(args, rows, seqs, offs, ids, ix, ot, res)
+            if line["parity"]["mismatching_reads"]:
+                line["PARITY_FAILED"] = "%d of %d reads differ from the oracle" % (line["parity"]["mismatching_reads"], line["parity"]["reads_checked"])
+                print("PARITY FAILED: %s" % line["PARITY_FAILED"], file=sys.stderr, flush=True)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, rows, seqs, offs, ids, ix, ot):
-    """The oracle port on this box's host cores, bounded sample; the index arrays are adopted from the GPU
-    build (they are mathematically unique) so that the sample budget goes to alignment."""
+def cpu_baseline(args, rows, seqs, offs, ids, ix, ot, gres):
+    """The oracle port on this box's host cores, bounded sample; the index arrays are adopted from the GPU build (they are
+    mathematically unique) so that the sample budget goes to alignment.  The oracle's rows for the sample are then compared with
+    the GPU's rows for the same reads: all PARITY_FIELDS and every CIGAR word (tests/helpers.py parity_report)."""
     import oracle_lib as O
+    from helpers import parity_report
     cores = os.cpu_count() or 1
     orc = O.OracleIndex(O.Opts(*ot))
     for i, r in enumerate(rows):
         orc.add_ref_text(i + 1, r.tobytes())
     orc.adopt(ix.bwt_plain(), int(ix.meta().primary), ix.sa_sampled())
-    probe = max(16, min(20_000, args.reads, 3_000_000 // max(args.read_len, 1)))
-    r = orc.align_batch(seqs[:int(offs[probe])], offs[:probe + 1], ids[:probe], cores)
-    rate = probe / max(r["seconds"], 1e-9)
-    sample = int(min(args.reads, max(probe, rate * args.cpu_seconds)))
+    sample, probe, rate = sized_sample(orc, args, seqs, offs, ids, cores)
     r = orc.align_batch(seqs[:int(offs[sample])], offs[:sample + 1], ids[:sample], cores)
+    parity = parity_report(gres, r, sample)
+    parity["against"] = "CPU oracle port (parity unpinned: no libbwa binary or reference vector exists to pin the oracle)"
     probe1 = max(8, min(probe, int(rate / cores * 3.0)))   # ~3 s of single-core work
     r1 = orc.align_batch(seqs[:int(offs[probe1])], offs[:probe1 + 1], ids[:probe1], 1)
     # index build on a bounded 8 Mbp sample, 1 core
     small = O.OracleIndex(O.Opts(*ot))
-    small.add_ref_text(1, rows[0][:8_000_000].tobytes())
+    head = rows[0][:8_000_000] if len(rows[0]) >= 8_000_000 else np.concatenate(rows[:16000])[:8_000_000]
+    small.add_ref_text(1, head.tobytes())
     bs = small.build()
-    return {"value": sample / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
+    base = {"value": sample / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d of %d reads, %d threads, FM-index arrays adopted from the GPU build" % (sample, args.reads, cores),
             "one_core_reads_per_s": probe1 / r1["seconds"], "index_build_s_8Mbp_1core": bs,
             "oracle_counters_per_read": {k: v / sample for k, v in r["counters"].items()}}
+    return base, parity
 
 
 def main():

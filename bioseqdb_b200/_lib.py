@@ -48,7 +48,7 @@ class BsqNuclseqs(C.Structure):
 
 class BsqTiming(C.Structure):
     _fields_ = [("h2d", C.c_float), ("seed", C.c_float), ("chain", C.c_float), ("extend", C.c_float), ("finalize", C.c_float),
-                ("d2h", C.c_float), ("total", C.c_float), ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("d2h", C.c_float), ("total", C.c_float), ("notes", C.c_uint32), ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 class BsqMeta(C.Structure):
@@ -84,6 +84,7 @@ def lib():
     L.bsq_index_new.argtypes = [C.POINTER(BsqOpts), C.c_int]
     L.bsq_index_set_opts.argtypes = [vp, C.POINTER(BsqOpts)]
     L.bsq_index_add_ref.argtypes = [vp, i64, vp, u32, vp, u32]
+    L.bsq_index_add_ref_datums.argtypes = [vp, u64, vp, vp, vp]
     L.bsq_index_build.argtypes = [vp]
     L.bsq_index_free.argtypes = [vp]
     L.bsq_align_batch.argtypes = [vp, vp, vp, vp, u64, C.POINTER(C.POINTER(BsqResult))]
@@ -101,6 +102,10 @@ def lib():
     L.bsq_index_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.bsq_index_download.argtypes = [vp, C.c_int, vp, u64]
     L.bsq_index_alloc_replica.argtypes = [vp, C.POINTER(BsqMeta)]
+    L.bsq_index_host_state_size.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.bsq_index_host_state_get.argtypes = [vp, vp, u64]
+    L.bsq_index_replica_finish.argtypes = [vp, vp, u64]
+    L.bsq_index_prepare.argtypes = [vp, C.POINTER(C.c_float)]
     L.bsq_index_bwt_plain.argtypes = [vp, vp]
     L.bsq_index_sa_sampled.argtypes = [vp, vp, u64]
     L.bsq_debug_seed.argtypes = [vp, vp, vp, u64, vp, u32, vp]
@@ -116,9 +121,9 @@ def lib():
 
 
 ABI_SYMBOLS = [
-    "bsq_last_error", "bsq_device_count", "bsq_opts_init", "bsq_index_new", "bsq_index_set_opts", "bsq_index_add_ref", "bsq_index_build",
+    "bsq_last_error", "bsq_device_count", "bsq_opts_init", "bsq_index_new", "bsq_index_set_opts", "bsq_index_add_ref", "bsq_index_add_ref_datums", "bsq_index_build",
     "bsq_index_free", "bsq_align_batch", "bsq_result_free", "bsq_last_timing", "bsq_result_tuples", "bsq_tuples_free", "bsq_nuclseq_from_text_batch", "bsq_nuclseqs_free", "bsq_reads_upload", "bsq_align_resident", "bsq_result_download",
-    "bsq_index_get_meta", "bsq_index_device_bytes", "bsq_index_device_ptr", "bsq_index_download", "bsq_index_alloc_replica", "bsq_index_bwt_plain", "bsq_index_sa_sampled",
+    "bsq_index_get_meta", "bsq_index_device_bytes", "bsq_index_device_ptr", "bsq_index_download", "bsq_index_alloc_replica", "bsq_index_host_state_size", "bsq_index_host_state_get", "bsq_index_replica_finish", "bsq_index_prepare", "bsq_index_bwt_plain", "bsq_index_sa_sampled",
     "bsq_debug_seed", "bsq_debug_ksw_extend", "bsq_debug_ksw_extend_thread", "bsq_debug_ksw_global", "bsq_bench_gather", "bsq_bench_dpx", "bsq_set_counters", "bsq_get_counters",
 ]
 

@@ -108,7 +108,7 @@ class BwaIndex:
             raise _lib.BsqError(self.L.bsq_last_error().decode())
         self.device = device
         self.n_rows = 0
-        self._refs = []  # (id, NucleotideSequence) kept for ref_subseq extraction (extract_reference_subseq, bwa.cpp:55-68)
+        self._refs = []  # ids of the reference rows added through this object (the rows themselves live in the library)
         self._lrand_state = 0
 
     def close(self):
@@ -146,11 +146,45 @@ class BwaIndex:
         holes = np.ascontiguousarray(seq.holes)
         pac = np.ascontiguousarray(seq.pac)
         check(self.L.bsq_index_add_ref(self.h, int(ref_id), ptr(pac), seq.len, ptr(holes) if len(holes) else None, len(holes)))
-        self._refs.append((int(ref_id), seq))
+        self._refs.append(int(ref_id))
         self.n_rows += 1
+
+    def add_ref_sequences(self, ref_ids, texts):
+        """Many reference rows in two calls: the texts become NUCLSEQ datums on the GPU (bsq_nuclseq_from_text_batch = nuclseq_in of
+        every row) and the datum images go to bsq_index_add_ref_datums -- the batched form of the add_ref_sequence loop of
+        bwa_index_from_query (extension.cpp:211-219).  texts: bytes or uint8 arrays of upper-case letters."""
+        from ._lib import BsqNuclseqs
+        n = len(texts)
+        if n == 0:
+            return
+        arrs = [t if isinstance(t, np.ndarray) else np.frombuffer(bytes(t), dtype=np.uint8) for t in texts]
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(a) for a in arrs])
+        ids = np.ascontiguousarray(ref_ids, dtype=np.int64)
+        # rows are converted in groups of at most ~1 G bases so that the device staging stays bounded
+        lo = 0
+        while lo < n:
+            hi = lo + 1
+            while hi < n and int(offs[hi + 1] - offs[lo]) <= (1 << 30):
+                hi += 1
+            cat = np.concatenate(arrs[lo:hi]) if hi - lo > 1 else np.ascontiguousarray(arrs[lo])
+            if len(cat) == 0:
+                cat = np.zeros(1, dtype=np.uint8)
+            rel = np.ascontiguousarray(offs[lo:hi + 1] - offs[lo])
+            res = C.POINTER(BsqNuclseqs)()
+            check(self.L.bsq_nuclseq_from_text_batch(self.device, ptr(cat), ptr(rel), hi - lo, C.byref(res)))
+            try:
+                r = res.contents
+                check(self.L.bsq_index_add_ref_datums(self.h, hi - lo, ptr(ids[lo:hi]), C.cast(r.bytes, C.c_void_p), C.cast(r.off, C.c_void_p)))
+            finally:
+                self.L.bsq_nuclseqs_free(res)
+            lo = hi
+        self._refs.extend(int(i) for i in ids)
+        self.n_rows += n
 
     def build(self):
         check(self.L.bsq_index_build(self.h))
+        self._view = None
 
     def meta(self) -> BsqMeta:
         m = BsqMeta()
@@ -289,24 +323,59 @@ class BwaIndex:
 
     def align_sequence(self, seq) -> list[BwaMatch]:
         """BwaIndex::align_sequence (bwa.cpp:141-181) for one read."""
-        if not self._refs:
+        if not self.n_rows:
             return []
         text = nuclseq_to_text(seq) if isinstance(seq, NucleotideSequence) else bytes(seq)
         q = np.frombuffer(text, dtype=np.uint8)
         res = self.align_batch(q, np.array([0, len(q)], dtype=np.uint64))
         return self.matches(res, 0, text)
 
+    def host_state(self) -> bytes:
+        """The index's host-only state (ambiguity holes of the reference rows + their row numbers) as bsq_index_host_state_get writes it."""
+        nb = C.c_uint64(0)
+        check(self.L.bsq_index_host_state_size(self.h, C.byref(nb)))
+        buf = np.zeros(int(nb.value), dtype=np.uint8)
+        check(self.L.bsq_index_host_state_get(self.h, ptr(buf), int(nb.value)))
+        return buf.tobytes()
+
+    def replica_finish(self, host_state: bytes | None):
+        """After the device arrays of a replica were filled (dist.broadcast_index): rebuild the library's host mirrors."""
+        if host_state is None:
+            check(self.L.bsq_index_replica_finish(self.h, None, 0))
+        else:
+            buf = np.frombuffer(host_state, dtype=np.uint8)
+            check(self.L.bsq_index_replica_finish(self.h, ptr(buf), len(buf)))
+        self.n_rows = int(self.meta().n_anns)
+        self._view = None
+
+    def _host_view(self):
+        """(forward text as ASCII, row offsets, holes) read back from the library -- the same on the index that was built and on
+        every replica of it, so ref_subseq does not depend on which rank answers."""
+        v = getattr(self, "_view", None)
+        if v is None:
+            from ._lib import ARR_PAC, ARR_ANN_OFFSET, HOLE_DTYPE
+            p = self.download(ARR_PAC)
+            codes = np.empty((len(p), 4), dtype=np.uint8)
+            codes[:, 0] = p >> 6; codes[:, 1] = (p >> 4) & 3; codes[:, 2] = (p >> 2) & 3; codes[:, 3] = p & 3
+            cat = np.frombuffer(b"ACGT", dtype=np.uint8)[codes.reshape(-1)]
+            offsets = self.download(ARR_ANN_OFFSET).view(np.int64)
+            st = self.host_state()
+            nh = int(np.frombuffer(st[:8], dtype="<u8")[0])
+            holes = np.frombuffer(st[8:8 + 16 * nh], dtype=HOLE_DTYPE)
+            v = self._view = (cat, offsets, holes)
+        return v
+
     def matches(self, res: AlignResult, i: int, text: bytes) -> list[BwaMatch]:
         out = []
         m = self.meta()
-        offsets = np.cumsum([0] + [((s.len + 3) // 4) * 4 for _, s in self._refs])
+        cat, offsets, holes = self._host_view()
         for row in res.rows_of(i):
             rid = int(row["rid"])
             ref_offset = int(offsets[rid])
             rb, re_ = int(row["rb"]), int(row["re"])
             out.append(BwaMatch(
                 ref_id=int(row["ref_id"]),
-                ref_subseq=self._ref_subseq(rb, re_, int(m.l_pac), offsets),
+                ref_subseq=self._ref_subseq(rb, re_, int(m.l_pac), cat, holes),
                 ref_match_begin=_i32(rb - ref_offset), ref_match_end=_i32(re_ - ref_offset), ref_match_len=_i32(re_ - rb),
                 query_subseq=text[int(row["qb"]):int(row["qe"])],
                 query_match_begin=int(row["qb"]), query_match_end=int(row["qe"]), query_match_len=int(row["qe"] - row["qb"]),
@@ -314,30 +383,21 @@ class BwaIndex:
                 cigar=res.cigar_of(row), score=int(row["score"])))
         return out
 
-    def _ref_subseq(self, rb, re_, l_pac, offsets) -> bytes:
+    @staticmethod
+    def _ref_subseq(rb, re_, l_pac, cat, holes) -> bytes:
         """extract_reference_subseq (bwa.cpp:55-68). Forward hits: the reference's own arithmetic, holes
         overlaid with their un-rebased offsets. Reverse hits index past the reference's
         vector (UB, B#3): defined here as the reverse-strand text."""
         comp = bytes.maketrans(b"ACGT", b"TGCA")
-        cat = getattr(self, "_cat", None)
-        if cat is None:
-            parts = []
-            for _, s in self._refs:
-                p = s.pac
-                v = np.empty((len(p), 4), dtype=np.uint8)
-                v[:, 0] = p >> 6; v[:, 1] = (p >> 4) & 3; v[:, 2] = (p >> 2) & 3; v[:, 3] = p & 3
-                parts.append(np.frombuffer(b"ACGT", dtype=np.uint8)[v.reshape(-1)])
-            cat = self._cat = np.concatenate(parts)
         if rb >= l_pac:
             fwd = cat[2 * l_pac - re_:2 * l_pac - rb].tobytes()
             out = bytearray(fwd.translate(comp)[::-1])
         else:
             out = bytearray(cat[rb:re_].tobytes())
-        for _, s in self._refs:
-            for h in s.holes:
-                lo, hi = max(int(h["offset"]), rb), min(int(h["offset"]) + int(h["len"]), re_)
-                for k in range(lo, hi):
-                    out[k - rb] = ord(h["amb"])
+        for h in holes:
+            lo, hi = max(int(h["offset"]), rb), min(int(h["offset"]) + int(h["len"]), re_)
+            for k in range(lo, hi):
+                out[k - rb] = ord(h["amb"])
         return bytes(out)
 
 

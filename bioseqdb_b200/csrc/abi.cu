@@ -24,6 +24,8 @@ static thread_local char g_err[1024] = "";
 void bsq_set_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
+// every extern "C" entry point starts with a clean error string: bsq_last_error() after a call describes THAT call
+#define BSQ_ENTRY() do { g_err[0] = 0; } while (0)
 
 static_assert(sizeof(bsq_row) == sizeof(RowDev), "bsq_row / RowDev mismatch");
 static_assert(sizeof(bsq_hole) == 16, "bsq_hole must match bntamb1_t");
@@ -75,6 +77,7 @@ struct Batch {
     ExtAux ext_aux; bool ext_aux_ok = false;    // side streams of the extension pre-pass
     uint32_t att_rseq_cap = 0; bool idle = true;
     uint64_t out_rows = 0; uint32_t out_cig = 0;
+    uint64_t rows_cap = 0;              // capacity of rows_compact (rows of the batch in read order)
     void release() {
         if (ctl_host) { cudaFreeHost(ctl_host); ctl_host = nullptr; }
         if (ev_ok) { for (auto& e : ev) cudaEventDestroy(e); ev_ok = false; }
@@ -93,7 +96,7 @@ struct Batch {
 struct bsq_index {
     int device = 0;
     bsq_opts opts; DevOpts dopts;
-    float mapQ_coef_len = 50.f, mapQ_coef_fac = 0.f;
+    float mapQ_coef_len = 50.f; int mapQ_coef_fac = 0;   // bwamem.h: `float mapQ_coef_len; int mapQ_coef_fac;`
     std::vector<uint8_t> pac; std::vector<int64_t> ann_offset, ann_id; std::vector<int32_t> ann_len; std::vector<bsq_hole> holes; std::vector<uint32_t> hole_ann;   // hole_ann: reference row of every hole
     uint8_t* d_pac = nullptr; uint32_t* d_occ = nullptr; void* d_sa = nullptr; int64_t* d_ann_offset = nullptr; int32_t* d_ann_len = nullptr; int64_t* d_ann_id = nullptr;
     bsq_index_meta meta;
@@ -105,6 +108,7 @@ struct bsq_index {
     void* d_isa = nullptr;           // inverse SA for the unique-match shortcut of the seeding kernel (built lazily, rows as wide as the SA's)
     void* d_kmer = nullptr; int kmer_k = 0;          // k-mer table of the LAST-like seeding pass (built lazily per device index)
     bool collect_counters = false;
+    bool replica_pending = false;    // device arrays allocated by bsq_index_alloc_replica, host mirrors not yet rebuilt (bsq_index_replica_finish)
     uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
@@ -120,7 +124,7 @@ static void fill_dev_opts(bsq_index* h) {
     for (int i = 0; i < 4; ++i) { for (int j = 0; j < 4; ++j) o.mat[i * 5 + j] = i == j ? 1 : -4; o.mat[i * 5 + 4] = -1; }
     for (int j = 0; j < 5; ++j) o.mat[20 + j] = -1;
     o.mat_max = 1;
-    h->mapQ_coef_len = 50.f; h->mapQ_coef_fac = (float)log((double)h->mapQ_coef_len);
+    h->mapQ_coef_len = 50.f; h->mapQ_coef_fac = (int)log((double)h->mapQ_coef_len);   // mem_opt_init stores log(50) = 3.912 in an int field: 3
 }
 
 static int check_opts(const bsq_opts* o) {
@@ -131,6 +135,8 @@ static int check_opts(const bsq_opts* o) {
     if (o->max_occ == 0) { bsq_set_error("bwa_opt max_occ must be positive (libbwa divides by it)"); return BSQ_ERR; }
     return BSQ_OK;
 }
+
+namespace { DevIndex make_dev_index(const bsq_index* h); int ensure_kmer_table(bsq_index* h, const DevIndex& ix); }
 
 extern "C" {
 
@@ -144,6 +150,7 @@ void bsq_opts_init(bsq_opts* o) {
 }
 
 bsq_index* bsq_index_new(const bsq_opts* o, int device) {
+    BSQ_ENTRY();
     bsq_opts d;
     if (!o) { bsq_opts_init(&d); o = &d; }
     if (check_opts(o) != BSQ_OK) return nullptr;
@@ -161,6 +168,7 @@ bsq_index* bsq_index_new(const bsq_opts* o, int device) {
 }
 
 int bsq_index_set_opts(bsq_index* h, const bsq_opts* o) {
+    BSQ_ENTRY();
     if (!h || !o) { bsq_set_error("null argument"); return BSQ_ERR; }
     if (check_opts(o) != BSQ_OK) return BSQ_ERR;
     h->opts = *o; fill_dev_opts(h);
@@ -168,6 +176,7 @@ int bsq_index_set_opts(bsq_index* h, const bsq_opts* o) {
 }
 
 int bsq_index_add_ref(bsq_index* h, int64_t id, const uint8_t* pac, uint32_t len, const bsq_hole* holes, uint32_t n_holes) {
+    BSQ_ENTRY();
     if (!h) { bsq_set_error("null index"); return BSQ_ERR; }
     if (h->meta.built) { bsq_set_error("index already built"); return BSQ_ERR; }
     // BwaIndex::add_ref_sequence (bwa.cpp:82-105): offset = 4 * bytes so far, byte-rounded append, holes not rebased
@@ -177,6 +186,40 @@ int bsq_index_add_ref(bsq_index* h, int64_t id, const uint8_t* pac, uint32_t len
     size_t nb = (size_t)len / 4 + (len % 4 != 0);
     h->pac.insert(h->pac.end(), pac, pac + nb);
     for (uint32_t i = 0; i < n_holes; ++i) { h->holes.push_back(holes[i]); h->hole_ann.push_back((uint32_t)h->ann_offset.size() - 1); }
+    return BSQ_OK;
+}
+
+// Batched form of bsq_index_add_ref: n NUCLSEQ datum images exactly as PostgreSQL hands them to iterate_nuclseq_table after
+// detoasting (extension.cpp:157-195; layout sequence.h:18-38: varlena length word, holes_num, len, hole records, pac bytes),
+// image i at bytes + off[i].  One call instead of one per reference row (500 k rows in BASELINE configs[4]).
+int bsq_index_add_ref_datums(bsq_index* h, uint64_t n, const int64_t* ids, const uint8_t* bytes, const uint64_t* off) {
+    BSQ_ENTRY();
+    if (!h || (n && (!ids || !bytes || !off))) { bsq_set_error("null argument"); return BSQ_ERR; }
+    if (h->meta.built) { bsq_set_error("index already built"); return BSQ_ERR; }
+    size_t pac_total = 0, holes_total = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t hdr[3]; memcpy(hdr, bytes + off[i], 12);
+        const uint64_t need = 12 + (uint64_t)hdr[1] * sizeof(bsq_hole) + ((uint64_t)hdr[2] + 3) / 4;
+        if ((hdr[0] >> 2) < need) { bsq_set_error("datum %llu is truncated: varlena size %u, header needs %llu", (unsigned long long)i, hdr[0] >> 2, (unsigned long long)need); return BSQ_ERR; }
+        pac_total += ((size_t)hdr[2] + 3) / 4; holes_total += hdr[1];
+    }
+    h->pac.reserve(h->pac.size() + pac_total); h->holes.reserve(h->holes.size() + holes_total); h->hole_ann.reserve(h->hole_ann.size() + holes_total);
+    h->ann_offset.reserve(h->ann_offset.size() + n); h->ann_len.reserve(h->ann_len.size() + n); h->ann_id.reserve(h->ann_id.size() + n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint8_t* d = bytes + off[i];
+        uint32_t hdr[3]; memcpy(hdr, d, 12);
+        const uint32_t n_holes = hdr[1], len = hdr[2];
+        const uint8_t* pac = d + 12 + (size_t)n_holes * sizeof(bsq_hole);
+        // BwaIndex::add_ref_sequence (bwa.cpp:82-105), as bsq_index_add_ref
+        h->ann_offset.push_back((int64_t)h->pac.size() * 4);
+        h->ann_len.push_back((int32_t)len);
+        h->ann_id.push_back(ids[i]);
+        h->pac.insert(h->pac.end(), pac, pac + ((size_t)len + 3) / 4);
+        for (uint32_t k = 0; k < n_holes; ++k) {
+            bsq_hole hl; memcpy(&hl, d + 12 + (size_t)k * sizeof(bsq_hole), sizeof(bsq_hole));   // 4-byte aligned only inside a datum (SURVEY B#11)
+            h->holes.push_back(hl); h->hole_ann.push_back((uint32_t)h->ann_offset.size() - 1);
+        }
+    }
     return BSQ_OK;
 }
 
@@ -198,6 +241,7 @@ static int upload_anns(bsq_index* h) {
 }
 
 int bsq_index_build(bsq_index* h) {
+    BSQ_ENTRY();
     if (!h) { bsq_set_error("null index"); return BSQ_ERR; }
     if (h->pac.empty()) return BSQ_OK;   // bwa.cpp:108-109: empty reference => no index, alignments return nothing
     CUDA_CHECK(cudaSetDevice(h->device));
@@ -232,12 +276,14 @@ void bsq_index_free(bsq_index* h) {
 }
 
 int bsq_index_get_meta(const bsq_index* h, bsq_index_meta* m) {
+    BSQ_ENTRY();
     if (!h || !m) { bsq_set_error("null argument"); return BSQ_ERR; }
     *m = h->meta;
     return BSQ_OK;
 }
 
 int bsq_index_device_bytes(const bsq_index* h, uint64_t* bytes) {
+    BSQ_ENTRY();
     if (!h || !bytes) { bsq_set_error("null argument"); return BSQ_ERR; }
     uint64_t b = h->batch.device_bytes() + h->batch2.device_bytes();
     if (h->meta.built) {
@@ -259,12 +305,14 @@ static void* index_array(const bsq_index* h, int what) {
 }
 
 int bsq_index_device_ptr(const bsq_index* h, int what, void** dptr) {
+    BSQ_ENTRY();
     if (!h || !dptr || what < 0 || what >= BSQ_ARR_COUNT) { bsq_set_error("bad argument"); return BSQ_ERR; }
     *dptr = index_array(h, what);
     return BSQ_OK;
 }
 
 int bsq_index_download(const bsq_index* h, int what, void* dst, uint64_t bytes) {
+    BSQ_ENTRY();
     if (!h || !h->meta.built || what < 0 || what >= BSQ_ARR_COUNT) { bsq_set_error("index not built / bad array"); return BSQ_ERR; }
     if (bytes > h->meta.arr_bytes[what]) { bsq_set_error("download of %llu bytes exceeds array size %llu", (unsigned long long)bytes, (unsigned long long)h->meta.arr_bytes[what]); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
@@ -273,10 +321,12 @@ int bsq_index_download(const bsq_index* h, int what, void* dst, uint64_t bytes) 
 }
 
 int bsq_index_alloc_replica(bsq_index* h, const bsq_index_meta* m) {
+    BSQ_ENTRY();
     if (!h || !m || !m->built) { bsq_set_error("bad argument"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
     free_index_arrays(h);
     h->meta = *m;
+    h->replica_pending = true;
     CUDA_CHECK(cudaMalloc(&h->d_pac, m->arr_bytes[BSQ_ARR_PAC] + 64));
     CUDA_CHECK(cudaMalloc(&h->d_occ, m->arr_bytes[BSQ_ARR_OCC] + 64));
     CUDA_CHECK(cudaMalloc(&h->d_sa, m->arr_bytes[BSQ_ARR_SA] + 64));
@@ -286,7 +336,59 @@ int bsq_index_alloc_replica(bsq_index* h, const bsq_index_meta* m) {
     return BSQ_OK;
 }
 
+// Host-side state that has no device copy: the ambiguity holes of the reference rows (copied un-rebased, bwa.cpp:98-104) and the
+// row each one came from.  Blob = u64 n_holes | n_holes x bsq_hole | n_holes x u32 row.
+int bsq_index_host_state_size(const bsq_index* h, uint64_t* bytes) {
+    BSQ_ENTRY();
+    if (!h || !bytes) { bsq_set_error("null argument"); return BSQ_ERR; }
+    *bytes = 8 + h->holes.size() * (sizeof(bsq_hole) + 4);
+    return BSQ_OK;
+}
+
+int bsq_index_host_state_get(const bsq_index* h, void* buf, uint64_t bytes) {
+    BSQ_ENTRY();
+    if (!h || !buf) { bsq_set_error("null argument"); return BSQ_ERR; }
+    const uint64_t nh = h->holes.size();
+    if (bytes < 8 + nh * (sizeof(bsq_hole) + 4)) { bsq_set_error("host-state buffer too small"); return BSQ_ERR; }
+    uint8_t* p = static_cast<uint8_t*>(buf);
+    memcpy(p, &nh, 8);
+    if (nh) { memcpy(p + 8, h->holes.data(), nh * sizeof(bsq_hole)); memcpy(p + 8 + nh * sizeof(bsq_hole), h->hole_ann.data(), nh * 4); }
+    return BSQ_OK;
+}
+
+// After the device arrays of a replica have been filled (broadcast / peer copy): rebuild the host mirrors the row
+// materialisation and the host adapters read -- pac and the annotation vectors from the device copy, the holes from the
+// source's host-state blob -- so that every replica answers exactly like the index it was copied from.
+int bsq_index_replica_finish(bsq_index* h, const void* host_state, uint64_t bytes) {
+    BSQ_ENTRY();
+    if (!h || !h->meta.built) { bsq_set_error("replica not allocated"); return BSQ_ERR; }
+    CUDA_CHECK(cudaSetDevice(h->device));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    const bsq_index_meta& m = h->meta;
+    h->pac.resize(m.arr_bytes[BSQ_ARR_PAC]); h->ann_offset.resize(m.n_anns); h->ann_len.resize(m.n_anns); h->ann_id.resize(m.n_anns);
+    if (!h->pac.empty()) CUDA_CHECK(cudaMemcpy(h->pac.data(), h->d_pac, h->pac.size(), cudaMemcpyDeviceToHost));
+    if (m.n_anns) {
+        CUDA_CHECK(cudaMemcpy(h->ann_offset.data(), h->d_ann_offset, m.n_anns * 8, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(h->ann_len.data(), h->d_ann_len, m.n_anns * 4, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(h->ann_id.data(), h->d_ann_id, m.n_anns * 8, cudaMemcpyDeviceToHost));
+    }
+    h->replica_pending = false;
+    h->holes.clear(); h->hole_ann.clear();
+    if (host_state) {
+        uint64_t nh = 0;
+        if (bytes < 8) { bsq_set_error("host-state blob truncated"); return BSQ_ERR; }
+        const uint8_t* p = static_cast<const uint8_t*>(host_state);
+        memcpy(&nh, p, 8);
+        if (bytes < 8 + nh * (sizeof(bsq_hole) + 4)) { bsq_set_error("host-state blob truncated"); return BSQ_ERR; }
+        h->holes.resize(nh); h->hole_ann.resize(nh);
+        if (nh) { memcpy(h->holes.data(), p + 8, nh * sizeof(bsq_hole)); memcpy(h->hole_ann.data(), p + 8 + nh * sizeof(bsq_hole), nh * 4); }
+        for (uint32_t a : h->hole_ann) if (a >= m.n_anns) { bsq_set_error("host-state blob names a reference row the index does not have"); return BSQ_ERR; }
+    }
+    return BSQ_OK;
+}
+
 int bsq_index_bwt_plain(const bsq_index* h, uint32_t* out) {
+    BSQ_ENTRY();
     if (!h || !h->meta.built) { bsq_set_error("index not built"); return BSQ_ERR; }
     std::vector<uint32_t> occ(h->meta.arr_bytes[BSQ_ARR_OCC] / 4);
     if (bsq_index_download(h, BSQ_ARR_OCC, occ.data(), h->meta.arr_bytes[BSQ_ARR_OCC]) != BSQ_OK) return BSQ_ERR;
@@ -295,18 +397,44 @@ int bsq_index_bwt_plain(const bsq_index* h, uint32_t* out) {
     return BSQ_OK;
 }
 
+static __global__ void k_sa_sample(const void* sa, int sa_bytes, uint64_t n_sa, uint64_t* out) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_sa; k += (uint64_t)gridDim.x * blockDim.x)
+        out[k] = sa_bytes == 4 ? (uint64_t)static_cast<const uint32_t*>(sa)[k * 32] : static_cast<const uint64_t*>(sa)[k * 32];
+}
+
 int bsq_index_sa_sampled(const bsq_index* h, uint64_t* out, uint64_t n_sa) {
+    BSQ_ENTRY();
     if (!h || !h->meta.built) { bsq_set_error("index not built"); return BSQ_ERR; }
     uint64_t n = h->meta.seq_len;
     if (n_sa != (n + 32) / 32) { bsq_set_error("n_sa must be (seq_len + 32) / 32"); return BSQ_ERR; }
-    std::vector<uint8_t> sa(h->meta.arr_bytes[BSQ_ARR_SA]);
-    if (bsq_index_download(h, BSQ_ARR_SA, sa.data(), sa.size()) != BSQ_OK) return BSQ_ERR;
-    for (uint64_t k = 0; k < n_sa; ++k) {
-        uint64_t row = k * 32;
-        out[k] = h->meta.sa_bytes == 4 ? (uint64_t)((uint32_t*)sa.data())[row] : ((uint64_t*)sa.data())[row];
-    }
+    // rows 0, 32, 64, ... of the full SA, gathered on the device (the full array is 50 GB at 3.1 Gbp)
+    CUDA_CHECK(cudaSetDevice(h->device));
+    uint64_t* d = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, n_sa * 8));
+    k_sa_sample<<<148 * 8, 256, 0, h->stream>>>(h->d_sa, (int)h->meta.sa_bytes, n_sa, d);
+    cudaError_t e = cudaMemcpyAsync(out, d, n_sa * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { bsq_set_error("bsq_index_sa_sampled: %s", cudaGetErrorString(e)); return BSQ_ERR; }
     out[0] = (uint64_t)-1;   // bwt_cal_sa: sa[0] = -1
     return BSQ_OK;
+}
+
+// Builds the arrays the seeding kernel derives from the index on this device (inverse SA, prefix table) now rather than inside
+// the first alignment call; *ms = wall time spent (0 when they were already there).  Every replica calls it after the broadcast.
+int bsq_index_prepare(bsq_index* h, float* ms) {
+    BSQ_ENTRY();
+    if (!h || !h->meta.built) { bsq_set_error("index not built"); return BSQ_ERR; }
+    CUDA_CHECK(cudaSetDevice(h->device));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, h->stream);
+    const DevIndex ix = make_dev_index(h);
+    const int rc = ensure_kmer_table(h, ix);
+    cudaEventRecord(e1, h->stream);
+    cudaEventSynchronize(e1);
+    if (ms) cudaEventElapsedTime(ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
 }
 
 }  // extern "C"
@@ -355,14 +483,14 @@ __device__ __forceinline__ int approx_mapq_dev(const MapqParams& M, const RowDev
 }
 
 __global__ void k_compact_rows(const ReadBlock* blocks, const RowDev* rows, const uint32_t* row_cnt, const uint32_t* row_off, uint32_t n_reads,
-                               RowDev* out, MapqParams M, uint32_t cig_base, uint32_t* host_mapq) {
-    // one warp per read; a row is 120 bytes = 30 words.  cig_base rebases the rows' CIGAR offsets when the batch is one
-    // chunk of a larger result; *host_mapq is raised when a row's MAPQ has to be finished on the host.
+                               RowDev* out, uint32_t out_cap, MapqParams M, uint32_t* host_mapq) {
+    // one warp per read; a row is 120 bytes = 30 words.  *host_mapq is raised when a row's MAPQ has to be finished on the host.  Rows
+    // beyond out_cap are dropped: the host sees the total from the scan, grows the buffer and runs the batch again.
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     for (uint32_t r = gw; r < n_reads; r += nw) {
         uint32_t c = row_cnt[r];
-        if (!c) continue;
+        if (!c || row_off[r] + c > out_cap) continue;
         const RowDev* srow = rows + blocks[r].base;
         RowDev* drow = out + row_off[r];
         const uint32_t* src = reinterpret_cast<const uint32_t*>(srow);
@@ -373,7 +501,6 @@ __global__ void k_compact_rows(const ReadBlock* blocks, const RowDev* rows, cons
             const int mq = srow[k].secondary < 0 ? approx_mapq_dev(M, srow[k]) : 0;
             drow[k].mapq = mq;
             if (mq < 0) atomicExch(host_mapq, 1u);
-            if (cig_base && srow[k].n_cigar) drow[k].cigar_off = srow[k].cigar_off + cig_base;
         }
     }
 }
@@ -568,10 +695,26 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
     }
     // compact rows: exclusive scan of row_cnt (n + 1 entries, the last one is a zero pad) -> row_off
     prim::device_scan<uint32_t, prim::OpSum, false>(b.row_cnt.p, b.row_off.p, n, b.scan_tmp.p, prim::OpSum(), st, &T.launches);
+    {   // rows in read order + MAPQ (the tail of mem_reg2aln): part of the step, so inside the timed window
+        if (!h->d_logtab) {
+            std::vector<double> tab(LOGTAB_N);
+            tab[0] = 0.;
+            for (int i = 1; i < LOGTAB_N; ++i) tab[i] = log((double)i);   // host libm: the values the reference's log() returns
+            ENS(cudaMalloc(&h->d_logtab, LOGTAB_N * sizeof(double)));
+            ENS(cudaMemcpy(h->d_logtab, tab.data(), LOGTAB_N * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        b.rows_cap = std::max<uint64_t>(b.rows_cap, (uint64_t)n * 2 + 4096);
+        ENS(b.rows_compact.ensure(b.rows_cap));
+        MapqParams M; M.a = h->opts.a; M.b = h->opts.b; M.min_seed_len = h->opts.min_seed_len; M.coef_len = h->mapQ_coef_len;
+        M.coef_fac = (double)h->mapQ_coef_fac; M.logtab = h->d_logtab;
+        k_compact_rows<<<148 * 8, 256, 0, st>>>(b.blocks.p, b.rows.p, b.row_cnt.p, b.row_off.p, n, b.rows_compact.p,
+                                                (uint32_t)std::min<uint64_t>(b.rows_cap, 0xffffffffull), M, b.ctl.p + 30); ++T.launches;
+    }
     cudaEventRecord(ev[4], st);
     ENS(cudaMemcpyAsync(b.ctl_host, b.ctl.p, 8 * 4, cudaMemcpyDeviceToHost, st));
     ENS(cudaMemcpyAsync(b.ctl_host + 8, b.row_off.p + (n - 1), 4, cudaMemcpyDeviceToHost, st));
     ENS(cudaMemcpyAsync(b.ctl_host + 9, b.row_cnt.p + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    ENS(cudaMemcpyAsync(b.ctl_host + 10, b.ctl.p + 30, 4, cudaMemcpyDeviceToHost, st));
     b.idle = false;
     return BSQ_OK;
 #undef ENS
@@ -606,6 +749,11 @@ int pipeline_check(bsq_index* h, Batch& b, bool* again) {
             for (int i = 0; i < 8; ++i) h->counters[i] += c8[i];
         }
         b.out_rows = (uint64_t)ctl[8] + ctl[9]; b.out_cig = ctl[6];
+        if (b.out_rows > b.rows_cap) {   // more rows than the compacted buffer holds: grow it and run the batch again
+            b.rows_cap = b.out_rows + b.out_rows / 8 + 4096;
+            *again = true;
+            return BSQ_OK;
+        }
         b.aligned = true;
         return BSQ_OK;
     }
@@ -720,23 +868,8 @@ int download_enqueue(bsq_index* h, Batch& b, ResultImpl* R, uint64_t read_base, 
     const uint64_t total_rows = b.out_rows; const uint32_t cig_top = b.out_cig;
     if (row_base + total_rows > R->row_cap || cig_base + cig_top > R->cig_cap || cig_base + cig_top > 0xffffffffull) { bsq_set_error("result block too small"); return BSQ_ERR; }
     cudaStream_t st = b.st;
-    b.ctl_host[10] = 0;
     CUDA_CHECK(cudaMemcpyAsync(R->o32 + read_base, b.row_off.p, n * 4, cudaMemcpyDeviceToHost, st));
-    if (total_rows) {
-        CUDA_CHECK(b.rows_compact.ensure(total_rows));
-        if (!h->d_logtab) {
-            std::vector<double> tab(LOGTAB_N);
-            tab[0] = 0.;
-            for (int i = 1; i < LOGTAB_N; ++i) tab[i] = log((double)i);   // host libm: the values the reference's log() returns
-            CUDA_CHECK(cudaMalloc(&h->d_logtab, LOGTAB_N * sizeof(double)));
-            CUDA_CHECK(cudaMemcpy(h->d_logtab, tab.data(), LOGTAB_N * sizeof(double), cudaMemcpyHostToDevice));
-        }
-        MapqParams M; M.a = h->opts.a; M.b = h->opts.b; M.min_seed_len = h->opts.min_seed_len; M.coef_len = h->mapQ_coef_len;
-        M.coef_fac = (double)h->mapQ_coef_fac; M.logtab = h->d_logtab;
-        k_compact_rows<<<148 * 8, 256, 0, st>>>(b.blocks.p, b.rows.p, b.row_cnt.p, b.row_off.p, (uint32_t)n, b.rows_compact.p, M, (uint32_t)cig_base, b.ctl.p + 30); ++h->timing.launches;
-        CUDA_CHECK(cudaMemcpyAsync(R->pub.rows + row_base, b.rows_compact.p, total_rows * sizeof(bsq_row), cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaMemcpyAsync(b.ctl_host + 10, b.ctl.p + 30, 4, cudaMemcpyDeviceToHost, st));
-    }
+    if (total_rows) CUDA_CHECK(cudaMemcpyAsync(R->pub.rows + row_base, b.rows_compact.p, total_rows * sizeof(bsq_row), cudaMemcpyDeviceToHost, st));
     if (cig_top) CUDA_CHECK(cudaMemcpyAsync(R->pub.cigar + cig_base, b.cigar.p, (size_t)cig_top * 4, cudaMemcpyDeviceToHost, st));
     h->timing.d2h_bytes += n * 4 + 12 + total_rows * sizeof(bsq_row) + (uint64_t)cig_top * 4;
     return BSQ_OK;
@@ -744,9 +877,11 @@ int download_enqueue(bsq_index* h, Batch& b, ResultImpl* R, uint64_t read_base, 
 
 // after the copies have landed: 64-bit row offsets, and MAPQ of the rows outside the device log table (very long
 // alignments).  n reads starting at read_base, n_rows rows starting at row_base.
-void download_finish(bsq_index* h, ResultImpl* R, uint64_t n, uint64_t read_base, uint64_t n_rows, uint64_t row_base, bool host_mapq) {
+void download_finish(bsq_index* h, ResultImpl* R, uint64_t n, uint64_t read_base, uint64_t n_rows, uint64_t row_base, uint64_t cig_base, bool host_mapq) {
     if (!h->meta.built) { for (uint64_t i = 0; i < n; ++i) R->pub.row_off[read_base + i] = row_base; return; }
     for (uint64_t i = 0; i < n; ++i) R->pub.row_off[read_base + i] = row_base + R->o32[read_base + i];
+    if (cig_base)   // the batch is one chunk of a larger result: its CIGAR words follow the earlier chunks'
+        for (uint64_t i = row_base; i < row_base + n_rows; ++i) if (R->pub.rows[i].n_cigar) R->pub.rows[i].cigar_off += (uint32_t)cig_base;
     if (n_rows && host_mapq)
         for (uint64_t i = row_base; i < row_base + n_rows; ++i)
             if (R->pub.rows[i].mapq < 0) R->pub.rows[i].mapq = approx_mapq(h, R->pub.rows[i]);
@@ -758,7 +893,7 @@ int download_result(bsq_index* h, Batch& b, bsq_result** out) {
     ResultImpl* R = result_new(b.n, b.out_rows, b.out_cig);
     if (!R) return BSQ_ERR;
     if (download_enqueue(h, b, R, 0, 0, 0) != BSQ_OK || cudaStreamSynchronize(b.st) != cudaSuccess) { result_delete(R); if (!*bsq_last_error()) bsq_set_error("download failed"); return BSQ_ERR; }
-    download_finish(h, R, b.n, 0, b.out_rows, 0, b.ctl_host && b.ctl_host[10]);
+    download_finish(h, R, b.n, 0, b.out_rows, 0, 0, b.ctl_host && b.ctl_host[10]);
     R->pub.row_off[b.n] = b.out_rows;
     R->pub.n_cigar_words = b.out_cig;
     *out = &R->pub;
@@ -814,14 +949,14 @@ int align_chunked(bsq_index* h, const char* seqs, const uint64_t* offs, const in
         cudaEventRecord(b.ev_x[1], b.st);
         return pipeline_enqueue(h, b);
     };
-    struct Pending { bool on = false; uint64_t c = 0, n = 0, n_rows = 0, row_base = 0; } pend;
+    struct Pending { bool on = false; uint64_t c = 0, n = 0, n_rows = 0, row_base = 0, cig_base = 0; bool host_mapq = false; } pend;
     ResultImpl* R = nullptr;
     auto complete = [&](const Pending& q) -> int {       // host side of chunk q.c's download
         Batch& b = *lane[q.c & 1];
         if (cudaEventSynchronize(b.ev_x[3]) != cudaSuccess) { bsq_set_error("result download failed: %s", cudaGetErrorString(cudaGetLastError())); return BSQ_ERR; }
         float ms;
         if (cudaEventElapsedTime(&ms, b.ev_x[2], b.ev_x[3]) == cudaSuccess) h->timing.d2h += ms;
-        download_finish(h, R, q.n, start_of(q.c), q.n_rows, q.row_base, b.ctl_host[10] != 0);
+        download_finish(h, R, q.n, start_of(q.c), q.n_rows, q.row_base, q.cig_base, q.host_mapq);
         return BSQ_OK;
     };
     uint64_t row_base = 0, cig_base = 0;
@@ -842,7 +977,8 @@ int align_chunked(bsq_index* h, const char* seqs, const uint64_t* offs, const in
         cudaEventRecord(b.ev_x[2], b.st);
         if ((rc = download_enqueue(h, b, R, start_of(c), row_base, cig_base)) != BSQ_OK) break;
         cudaEventRecord(b.ev_x[3], b.st);
-        Pending mine; mine.on = true; mine.c = c; mine.n = b.n; mine.n_rows = b.out_rows; mine.row_base = row_base;
+        Pending mine; mine.on = true; mine.c = c; mine.n = b.n; mine.n_rows = b.out_rows; mine.row_base = row_base; mine.cig_base = cig_base;
+        mine.host_mapq = b.ctl_host[10] != 0;   // read now: the lane's control words are reused by the next chunk it takes
         row_base += b.out_rows; cig_base += b.out_cig;
         if (pend.on) { if ((rc = complete(pend)) != BSQ_OK) break; pend.on = false; }
         // chunk c-1's lane is free on the host side now (its download completed): it already runs chunk c+1.
@@ -869,6 +1005,7 @@ int align_chunked(bsq_index* h, const char* seqs, const uint64_t* offs, const in
 extern "C" {
 
 int bsq_reads_upload(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n) {
+    BSQ_ENTRY();
     if (!h || (n && (!seqs || !offs || !ids))) { bsq_set_error("null argument"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
     h->timing.launches = 0;
@@ -879,6 +1016,7 @@ int bsq_reads_upload(bsq_index* h, const char* seqs, const uint64_t* offs, const
 }
 
 int bsq_align_resident(bsq_index* h) {
+    BSQ_ENTRY();
     if (!h) { bsq_set_error("null index"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
     h->timing.launches = 0;
@@ -886,18 +1024,20 @@ int bsq_align_resident(bsq_index* h) {
 }
 
 int bsq_result_download(bsq_index* h, bsq_result** out) {
+    BSQ_ENTRY();
     if (!h || !out) { bsq_set_error("null argument"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
     return download_result(h, h->batch, out);
 }
 
 int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, bsq_result** out) {
+    BSQ_ENTRY();
     if (!h || !out || (n && (!seqs || !offs || !ids))) { bsq_set_error("null argument"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
     cudaEvent_t e0, e1, e2, e3;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
     bsq_timing& T = h->timing;
-    T.launches = 0; T.h2d_bytes = T.d2h_bytes = 0; T.h2d = T.d2h = 0;
+    T.launches = 0; T.h2d_bytes = T.d2h_bytes = 0; T.h2d = T.d2h = 0; T.notes = 0;
     int rc = BSQ_OK;
     bool chunked = n >= 2 * chunk_reads(n) && h->meta.built && !getenv("BSQ_NO_CHUNKS");
     cudaEventRecord(e0, h->stream);
@@ -907,8 +1047,8 @@ int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const 
         memset(h->counters, 0, sizeof(h->counters));
         bool fell_back = false;
         rc = align_chunked(h, seqs, offs, ids, n, out, &fell_back);
-        if (fell_back) {   // the result outgrew the estimate: one plain pass (the note is visible through bsq_last_error; the call succeeds)
-            bsq_set_error("note: result outgrew the chunk pipeline's estimate; batch re-run in one pass");
+        if (fell_back) {   // the result outgrew the estimate: one plain pass; the call succeeds and says so in bsq_timing.notes
+            T.notes |= BSQ_NOTE_CHUNK_FALLBACK;
             chunked = false; T.h2d_bytes = T.d2h_bytes = 0; T.h2d = T.d2h = 0;
         }
         else { cudaEventRecord(e3, h->stream); cudaEventSynchronize(e3); cudaEventElapsedTime(&T.total, e0, e3); }
@@ -931,8 +1071,10 @@ int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const 
 struct TuplesImpl { bsq_tuples pub; void* host = nullptr; size_t host_bytes = 0; };
 
 int bsq_result_tuples(bsq_index* h, const bsq_result* res, const char* seqs, const uint64_t* offs, uint32_t flags, bsq_tuples** out) {
+    BSQ_ENTRY();
     if (!h || !res || !offs || !out) { bsq_set_error("null argument"); return BSQ_ERR; }
     if (!h->meta.built && res->n_reads && res->row_off[res->n_reads]) { bsq_set_error("index not built"); return BSQ_ERR; }
+    if (h->replica_pending) { bsq_set_error("replica without host state: call bsq_index_replica_finish after filling its arrays (the hole overlay of ref_subseq lives on the host)"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
     const uint64_t n_reads = res->n_reads, n_rows = n_reads ? res->row_off[n_reads] : 0;
     TuplesImpl* T = new TuplesImpl();
@@ -1034,6 +1176,7 @@ void bsq_tuples_free(bsq_tuples* t) {
 struct NuclseqsImpl { bsq_nuclseqs pub; void* host = nullptr; };
 
 int bsq_nuclseq_from_text_batch(int device, const char* text, const uint64_t* offs, uint64_t n, bsq_nuclseqs** out) {
+    BSQ_ENTRY();
     if (!offs || !out || (n && !text && offs[n] != offs[0])) { bsq_set_error("null argument"); return BSQ_ERR; }
     if (cudaSetDevice(device) != cudaSuccess) { bsq_set_error("no CUDA device %d (there is no CPU fallback)", device); return BSQ_ERR; }
     std::vector<uint64_t> rel(n + 1), chunk_off(n + 1);
@@ -1119,6 +1262,7 @@ void bsq_result_free(bsq_result* r) {
 }
 
 int bsq_last_timing(const bsq_index* h, bsq_timing* t) {
+    BSQ_ENTRY();
     if (!h || !t) { bsq_set_error("null argument"); return BSQ_ERR; }
     *t = h->timing;
     return BSQ_OK;
@@ -1128,6 +1272,7 @@ int bsq_set_counters(bsq_index* h, int on) { if (!h) return BSQ_ERR; h->collect_
 int bsq_get_counters(const bsq_index* h, uint64_t* out8) { if (!h || !out8) return BSQ_ERR; memcpy(out8, h->counters, sizeof(h->counters)); return BSQ_OK; }
 
 int bsq_debug_seed(bsq_index* h, const char* seqs, const uint64_t* offs, uint64_t n, uint64_t* out, uint32_t cap, uint32_t* cnt) {
+    BSQ_ENTRY();
     if (!h || !h->meta.built) { bsq_set_error("index not built"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
     std::vector<int64_t> ids(n, 0);
@@ -1165,11 +1310,13 @@ static int dbg_ksw_extend(const bsq_opts* o, int device, uint64_t n_jobs, const 
 
 int bsq_debug_ksw_extend(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
                          const uint64_t* t_off, const int32_t* w, const int32_t* end_bonus, const int32_t* h0, int32_t* out) {
+    BSQ_ENTRY();
     return dbg_ksw_extend(o, device, n_jobs, q, q_off, t, t_off, w, end_bonus, h0, out, 0);
 }
 
 int bsq_debug_ksw_extend_thread(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
                                 const uint64_t* t_off, const int32_t* w, const int32_t* end_bonus, const int32_t* h0, int32_t* out, int reversed) {
+    BSQ_ENTRY();
     return dbg_ksw_extend(o, device, n_jobs, q, q_off, t, t_off, w, end_bonus, h0, out, reversed ? 2 : 1);
 }
 
@@ -1215,6 +1362,7 @@ extern "C" {
 
 int bsq_debug_ksw_global(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
                          const uint64_t* t_off, const int32_t* w, int32_t* out_score, uint32_t* cigar, uint32_t cig_cap, int32_t* n_cigar) {
+    BSQ_ENTRY();
     bsq_index* h;
     if (dbg_common(o, device, &h) != BSQ_OK) return BSQ_ERR;
     int rc = BSQ_ERR;
@@ -1251,6 +1399,7 @@ int bsq_debug_ksw_global(const bsq_opts* o, int device, uint64_t n_jobs, const u
 }
 
 int bsq_bench_gather(bsq_index* h, uint64_t n_loads, int reps, double* gbs) {
+    BSQ_ENTRY();
     if (!h || !h->meta.built || !gbs) { bsq_set_error("index not built"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
     const uint64_t n_blocks = h->meta.arr_bytes[BSQ_ARR_OCC] / 64;
@@ -1276,6 +1425,7 @@ int bsq_bench_gather(bsq_index* h, uint64_t n_loads, int reps, double* gbs) {
 }
 
 int bsq_bench_dpx(int device, int reps, double* gops) {
+    BSQ_ENTRY();
     if (!gops) { bsq_set_error("null argument"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(device));
     int* sink = nullptr;

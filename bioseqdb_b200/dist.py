@@ -57,7 +57,14 @@ def broadcast_index(ix, rank: int, dist, src: int = 0) -> int:
         dist.broadcast(t, src)
         total += n
     torch.cuda.synchronize()
-    return total
+    # host-only state (the reference rows' ambiguity holes): every replica must overlay the same holes on ref_subseq
+    st = ix.host_state() if rank == src else None
+    nb = torch.tensor([len(st) if st is not None else 0], dtype=torch.int64, device="cuda")
+    dist.broadcast(nb, src)
+    st = broadcast_meta(st, int(nb.item()), dist, "cuda", src)
+    if rank != src:
+        ix.replica_finish(st)
+    return total + int(nb.item())
 
 
 def broadcast_host_arrays(arrays: dict | None, names, dist, src: int = 0) -> dict:
@@ -95,6 +102,41 @@ def gather_rows(row_off: np.ndarray, rows: np.ndarray, cigar: np.ndarray, dist, 
     for ro, rw, cg in gathered:
         offs.append(ro[1:].astype(np.uint64) + np.uint64(base_rows))
         rw = rw.copy()
+        rw["cigar_off"] += np.uint32(base_cig)
+        all_rows.append(rw)
+        all_cig.append(cg)
+        base_rows += len(rw)
+        base_cig += len(cg)
+    return np.concatenate(offs), np.concatenate(all_rows), np.concatenate(all_cig)
+
+
+def gather_rows_host(row_off: np.ndarray, rows: np.ndarray, cigar: np.ndarray, dist, group, rank: int, world: int, dst: int = 0):
+    """gather_rows over a CPU (gloo) group with plain byte tensors instead of pickled objects: the results are already in host
+    memory (one process per GPU), so this is a host-to-host copy of every rank's row offsets, rows and CIGAR words to `dst`."""
+    import torch
+    sizes = torch.tensor([row_off.nbytes, rows.nbytes, cigar.nbytes], dtype=torch.int64)
+    all_sizes = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    parts = []
+    for k, arr in enumerate((row_off, rows, cigar)):
+        mine = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()) if arr.nbytes else torch.zeros(0, dtype=torch.uint8)
+        cap = int(max(int(s[k]) for s in all_sizes))
+        buf = torch.zeros(cap, dtype=torch.uint8)
+        buf[:mine.numel()] = mine
+        got = [torch.zeros(cap, dtype=torch.uint8) for _ in range(world)] if rank == dst else None
+        dist.gather(buf, got, dst=dst, group=group)
+        if rank == dst:
+            parts.append([g[:int(all_sizes[r][k])].numpy() for r, g in enumerate(got)])
+    if rank != dst:
+        return None
+    offs = [np.zeros(1, dtype=np.uint64)]
+    all_rows, all_cig = [], []
+    base_rows = base_cig = 0
+    for r in range(world):
+        ro = parts[0][r].view(np.uint64)
+        rw = parts[1][r].view(rows.dtype).copy()
+        cg = parts[2][r].view(np.uint32)
+        offs.append(ro[1:] + np.uint64(base_rows))
         rw["cigar_off"] += np.uint32(base_cig)
         all_rows.append(rw)
         all_cig.append(cg)

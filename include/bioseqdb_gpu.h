@@ -57,8 +57,10 @@ typedef struct bsq_result {
 } bsq_result;
 
 /* per-stage device timings of the last bsq_align_batch / bsq_align_resident call, milliseconds */
+#define BSQ_NOTE_CHUNK_FALLBACK 1u /* bsq_align_batch: the result outgrew the chunk pipeline's estimate, the batch was re-run in one pass */
 typedef struct bsq_timing {
     float h2d, seed, chain, extend, finalize, d2h, total;
+    uint32_t notes;    /* BSQ_NOTE_* bits: things a successful call wants its caller to know (never an error; see bsq_last_error for those) */
     uint64_t launches; /* kernels launched by the call */
     uint64_t h2d_bytes, d2h_bytes;
 } bsq_timing;
@@ -72,6 +74,9 @@ void bsq_opts_init(bsq_opts* o);
 bsq_index* bsq_index_new(const bsq_opts* o, int device);
 int bsq_index_set_opts(bsq_index* h, const bsq_opts* o);
 int bsq_index_add_ref(bsq_index* h, int64_t id, const uint8_t* pac, uint32_t len, const bsq_hole* holes, uint32_t n_holes);
+/* n reference rows in one call: NUCLSEQ datum images as PostgreSQL stores them (sequence.h:18-38), image i at bytes + off[i] --
+ * what iterate_nuclseq_table (extension.cpp:157-195) holds after detoasting each row; same semantics as n calls of bsq_index_add_ref */
+int bsq_index_add_ref_datums(bsq_index* h, uint64_t n, const int64_t* ids, const uint8_t* bytes, const uint64_t* off);
 int bsq_index_build(bsq_index* h);
 void bsq_index_free(bsq_index* h);
 
@@ -145,6 +150,14 @@ int bsq_index_device_bytes(const bsq_index* h, uint64_t* bytes);
 int bsq_index_device_ptr(const bsq_index* h, int what, void** dptr);       /* device pointer of an index array */
 int bsq_index_download(const bsq_index* h, int what, void* host_dst, uint64_t bytes);
 int bsq_index_alloc_replica(bsq_index* h, const bsq_index_meta* m);        /* allocate arrays to receive a broadcast */
+/* Completing a replica: the index also has HOST-side state (the reference rows' ambiguity holes, un-rebased as bwa.cpp:98-104
+ * copies them; pac and annotation mirrors).  The source serialises it (size / get), the replica passes the blob to
+ * bsq_index_replica_finish once its device arrays have been filled; from then on the replica answers every call -- alignment,
+ * bsq_result_tuples with its hole overlay, the adapters' ref_subseq -- exactly like the source. */
+int bsq_index_host_state_size(const bsq_index* h, uint64_t* bytes);
+int bsq_index_host_state_get(const bsq_index* h, void* buf, uint64_t bytes);
+int bsq_index_replica_finish(bsq_index* h, const void* host_state, uint64_t bytes);
+int bsq_index_prepare(bsq_index* h, float* ms);   /* build the per-device derived arrays (inverse SA, prefix table) now; *ms = time spent */
 int bsq_index_bwt_plain(const bsq_index* h, uint32_t* out);               /* the u32 stream of bwa.cpp:48-50 */
 int bsq_index_sa_sampled(const bsq_index* h, uint64_t* out, uint64_t n_sa); /* bwt_cal_sa(bwt, 32) view */
 

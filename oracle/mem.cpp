@@ -11,7 +11,7 @@ namespace orc {
 
 void opts_init(Opts& o) {
     o = Opts();
-    o.mapQ_coef_fac = (float)log((double)o.mapQ_coef_len);
+    o.mapQ_coef_fac = (int)log((double)o.mapQ_coef_len);   // bwamem.h declares `int mapQ_coef_fac`: mem_opt_init's log(50) = 3.912 is truncated to 3
     for (int i = 0; i < 4; ++i) {
         for (int j = 0; j < 4; ++j) o.mat[i * 5 + j] = i == j ? o.a : -o.b;
         o.mat[i * 5 + 4] = -1;

@@ -29,7 +29,7 @@ struct Opts {
     int max_mem_intv = 20, split_width = 10;
     int max_chain_gap = 10000, max_chain_extend = 1 << 30, min_chain_weight = 0;
     float split_factor = 1.5f, mask_level = 0.50f, drop_ratio = 0.50f, mask_level_redun = 0.95f;
-    float mapQ_coef_len = 50.f, mapQ_coef_fac = 0.f;  // fac = log(len), filled by opts_init()
+    float mapQ_coef_len = 50.f; int mapQ_coef_fac = 0;  // fac = (int)log(len) = 3 (an int field in bwamem.h), filled by opts_init()
     int8_t mat[25];
 };
 void opts_init(Opts& o);  // mem_opt_init() defaults incl. bwa_fill_scmat(a=1,b=4)

@@ -60,3 +60,47 @@ def read_arrays(reads):
     offs[1:] = np.cumsum([len(r) for r in reads])
     seqs = np.frombuffer(b"".join(reads), dtype=np.uint8) if reads else np.zeros(0, dtype=np.uint8)
     return seqs, offs
+
+
+def _flat_cigars(rows, cigar):
+    nc = rows["n_cigar"].astype(np.int64)
+    tot = int(nc.sum())
+    if tot == 0:
+        return np.zeros(0, dtype=np.uint32), nc
+    starts = np.repeat(rows["cigar_off"].astype(np.int64) - np.concatenate(([0], np.cumsum(nc)[:-1])), nc)
+    return cigar[starts + np.arange(tot, dtype=np.int64)], nc
+
+
+def parity_report(gres, ores, n_reads=None):
+    """Vectorised read-level comparison of GPU rows with oracle rows over the first n_reads reads: every PARITY_FIELDS column and the
+    CIGAR words.  A read mismatches when its row count, any field of any of its rows, or any CIGAR word differs.
+    Returns {"reads_checked", "mismatching_reads", "rows_checked", "fields", "first_mismatching_reads"}."""
+    g_off = gres.row_off.astype(np.int64)
+    o_off = ores["row_off"].astype(np.int64)
+    n = int(n_reads if n_reads is not None else min(len(g_off), len(o_off)) - 1)
+    g_cnt, o_cnt = np.diff(g_off[:n + 1]), np.diff(o_off[:n + 1])
+    bad = g_cnt != o_cnt
+    same = ~bad
+    g_rows = gres.rows[int(g_off[0]):int(g_off[n])][np.repeat(same, g_cnt)]
+    o_rows = ores["rows"][int(o_off[0]):int(o_off[n])][np.repeat(same, o_cnt)]
+    read_of_row = np.repeat(np.arange(n)[same], g_cnt[same])
+    row_bad = np.zeros(len(g_rows), dtype=bool)
+    for f in PARITY_FIELDS:
+        row_bad |= g_rows[f] != o_rows[f]
+    gc, gn = _flat_cigars(g_rows, gres.cigar)
+    oc, on = _flat_cigars(o_rows, ores["cigar"])
+    if len(gc) == len(oc) and np.array_equal(gn, on):
+        if len(gc):
+            word_bad = gc != oc
+            if word_bad.any():
+                row_bad[np.unique(np.repeat(np.arange(len(g_rows)), gn)[word_bad])] = True
+    else:   # n_cigar differs somewhere: those rows are already flagged by the n_cigar field; compare the rest row by row
+        eq = gn == on
+        for i in np.flatnonzero(eq & ~row_bad):
+            a = gres.cigar[int(g_rows["cigar_off"][i]):int(g_rows["cigar_off"][i]) + int(gn[i])]
+            b = ores["cigar"][int(o_rows["cigar_off"][i]):int(o_rows["cigar_off"][i]) + int(on[i])]
+            if not np.array_equal(a, b):
+                row_bad[i] = True
+    bad[np.unique(read_of_row[row_bad])] = True
+    return {"reads_checked": n, "mismatching_reads": int(bad.sum()), "rows_checked": int(len(g_rows)), "fields": len(PARITY_FIELDS),
+            "cigars_compared": True, "first_mismatching_reads": np.flatnonzero(bad)[:8].tolist()}

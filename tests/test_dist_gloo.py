@@ -20,7 +20,7 @@ def _worker(rank, world, port, q):
     import torch.distributed as dist
     import oracle_lib as O
     from bioseqdb_b200 import synth
-    from bioseqdb_b200.dist import broadcast_host_arrays, gather_rows, shard_reads
+    from bioseqdb_b200.dist import broadcast_host_arrays, gather_rows, gather_rows_host, shard_reads
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rows = synth.reference_rows([60_001, 40_003], seed=91)
@@ -40,7 +40,9 @@ def _worker(rank, world, port, q):
     s, o, i_, (lo, hi) = shard_reads(seqs, offs, ids, rank, world)
     res = ix.align_batch(s, o, i_, 1)
     merged = gather_rows(res["row_off"], res["rows"], res["cigar"], dist, rank, world)
+    merged2 = gather_rows_host(res["row_off"], res["rows"], res["cigar"], dist, None, rank, world)   # byte-tensor gather used by bench.py
     if rank == 0:
+        assert all(np.array_equal(a, b) for a, b in zip(merged, merged2))
         full = O.OracleIndex(opts)
         for i, r in enumerate(rows):
             full.add_ref_text(i + 1, r.tobytes())

@@ -58,13 +58,13 @@ struct Batch {
     DevBuf<uint32_t> cigar; uint32_t cigar_cap = 0;
     DevBuf<double> read_logtab; uint32_t read_logtab_n = 0; uint32_t rseq_cap = 0;
     DevBuf<uint8_t> ext_scratch, fin_scratch, narrow_z, narrow_jobs; DevBuf<uint64_t> wide_jobs;
-    DevBuf<ExtMemo> ext_memo; DevBuf<uint8_t> ext_memo_key; DevBuf<uint32_t> ext_memo_perm, ext_memo_hist, ext_todo, chain_todo, fin_todo;   // thread-per-extension pre-pass (extend_plan.cu)
+    DevBuf<ExtMemo> ext_memo; DevBuf<uint8_t> ext_memo_key; DevBuf<uint32_t> ext_memo_perm, ext_memo_hist, ext_todo, chain_todo, fin_todo, seed_todo;   // thread-per-extension pre-pass (extend_plan.cu)
     DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..23] counters (u64 x 8), [24] narrow_cnt, [25] wide_cnt, [26..27] tickets, [56] reads left for sw_extend, [57] reads left for the warp chain kernel, [58] for regs_finalize
     size_t device_bytes() const {
         return seqs.bytes() + offs.bytes() + ids.bytes() + intv.bytes() + intv_cnt.bytes() + seed_scratch.bytes() + raw.bytes() + seeds.bytes() + ctmp.bytes() +
                ord.bytes() + chains.bytes() + srt.bytes() + regs.bytes() + rows.bytes() + rows_compact.bytes() + reg_cnt.bytes() + row_cnt.bytes() + row_off.bytes() +
                scan_tmp.bytes() + blocks.bytes() + cigar.bytes() + read_logtab.bytes() + ext_scratch.bytes() + fin_scratch.bytes() + narrow_z.bytes() +
-               narrow_jobs.bytes() + wide_jobs.bytes() + ctl.bytes() + ext_memo.bytes() + ext_memo_key.bytes() + ext_memo_perm.bytes() + ext_memo_hist.bytes() + ext_todo.bytes() + chain_todo.bytes() + fin_todo.bytes();
+               narrow_jobs.bytes() + wide_jobs.bytes() + ctl.bytes() + ext_memo.bytes() + ext_memo_key.bytes() + ext_memo_perm.bytes() + ext_memo_hist.bytes() + ext_todo.bytes() + chain_todo.bytes() + fin_todo.bytes() + seed_todo.bytes();
     }
     bool resident = false, aligned = false;
     // one batch = one lane of the host pipeline: its stream, the host staging that must outlive the async copies,
@@ -87,7 +87,7 @@ struct Batch {
         ctmp.release(); ord.release(); chains.release(); srt.release(); regs.release(); rows.release(); rows_compact.release(); reg_cnt.release();
         row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release();
         ctl.release(); narrow_z.release(); narrow_jobs.release(); wide_jobs.release(); read_logtab.release();
-        ext_memo.release(); ext_memo_key.release(); ext_memo_perm.release(); ext_memo_hist.release(); ext_todo.release(); chain_todo.release(); fin_todo.release();
+        ext_memo.release(); ext_memo_key.release(); ext_memo_perm.release(); ext_memo_hist.release(); ext_todo.release(); chain_todo.release(); fin_todo.release(); seed_todo.release();
     }
 };
 
@@ -579,6 +579,7 @@ SeedParams seed_params(const bsq_index* h, const Batch& b, const DevIndex& ix, u
     P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u;
     P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes);
     P.ticket = ticket; P.overflow = b.ctl.p + 4; P.n_extend = n_extend;
+    P.todo = b.seed_todo.p; P.todo_cnt = b.ctl.p + 59;    // reads the thread-per-read pass leaves for seed_smem
     return P;
 }
 
@@ -627,7 +628,7 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
     int narrow_warps = 0;
     const size_t narrow_bytes = narrow_zbuf_bytes(&narrow_warps);
     ENS(b.narrow_z.ensure(narrow_bytes)); ENS(b.narrow_jobs.ensure((size_t)b.pool_cap * 3 * 24)); ENS(b.wide_jobs.ensure(b.pool_cap));
-    ENS(b.ctl.ensure(64)); ENS(b.chain_todo.ensure(n)); ENS(b.fin_todo.ensure(n));
+    ENS(b.ctl.ensure(64)); ENS(b.chain_todo.ensure(n)); ENS(b.fin_todo.ensure(n)); ENS(b.seed_todo.ensure(n + 1));
     // the thread-per-extension pre-pass packs column scores in 16 bits: every value it stores is <= l_query * (a + 1)
     static const bool no_memo = getenv("BSQ_NO_EXT_MEMO") != nullptr;
     // Small batches take the warp-cooperative kernels for the DP stages: the thread-per-extension / thread-per-region kernels are built for
@@ -650,7 +651,10 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
     unsigned long long* ctr = h->collect_counters ? reinterpret_cast<unsigned long long*>(b.ctl.p + 8) : nullptr;
     cudaEventRecord(ev[0], st);
     {
-        const SeedParams P = seed_params(h, b, ix, n, b.intv_cap, b.ctl.p + 0, ctr ? ctr + 0 : nullptr);
+        SeedParams P = seed_params(h, b, ix, n, b.intv_cap, b.ctl.p + 0, ctr ? ctr + 0 : nullptr);
+        // thread per read first (almost every short read); seed_smem, warp per read, takes what it declined
+        if (seed_thread_usable(P, o, b.max_len)) { launch_seed_thread(P, ix, o, b.max_len, b.ctl.p + 60, st); ++T.launches; }
+        else P.todo = nullptr;
         launch_seed(P, ix, o, st, nullptr); ++T.launches;
     }
     cudaEventRecord(ev[1], st);
@@ -1286,7 +1290,10 @@ int bsq_debug_seed(bsq_index* h, const char* seqs, const uint64_t* offs, uint64_
     CUDA_CHECK(b.intv.ensure((size_t)n * cap)); CUDA_CHECK(b.intv_cnt.ensure(n)); CUDA_CHECK(b.seed_scratch.ensure((size_t)seed_warps * 3 * b.list_cap));
     CUDA_CHECK(b.ctl.ensure(64));
     CUDA_CHECK(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, h->stream));
-    const SeedParams P = seed_params(h, b, ix, (uint32_t)n, cap, b.ctl.p, reinterpret_cast<unsigned long long*>(b.ctl.p + 8));
+    CUDA_CHECK(b.seed_todo.ensure(n + 1));
+    SeedParams P = seed_params(h, b, ix, (uint32_t)n, cap, b.ctl.p, reinterpret_cast<unsigned long long*>(b.ctl.p + 8));
+    if (seed_thread_usable(P, h->dopts, b.max_len)) launch_seed_thread(P, ix, h->dopts, b.max_len, b.ctl.p + 60, h->stream);
+    else P.todo = nullptr;
     launch_seed(P, ix, h->dopts, h->stream, nullptr);
     uint32_t ctl[8];
     CUDA_CHECK(cudaMemcpyAsync(ctl, b.ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));

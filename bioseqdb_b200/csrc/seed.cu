@@ -12,6 +12,7 @@
 // and S still fit 32 bits (they are bounded by the parent interval), only tk[c] needs its checkpoint's two
 // halves, i.e. two more single-contributor reductions.  Interval lists and the read live in shared memory.
 #include "seed.cuh"
+#include "seed_thread.cuh"
 #include "launch_cache.cuh"
 #include <algorithm>
 #include <cstdlib>
@@ -704,9 +705,11 @@ __global__ void __launch_bounds__(SEED_THREADS, MINB) seed_smem(SeedParams P, De
         la = reinterpret_cast<Iv*>(dyn_smem) + (size_t)warp_in_cta * 2 * P.list_cap; lb = la + P.list_cap;
         sq = dyn_smem + (size_t)SEED_WARPS * 2 * P.list_cap * sizeof(Iv) + (size_t)warp_in_cta * P.read_cap;
     } else { la = reinterpret_cast<Iv*>(gl); lb = la + P.list_cap; }
+    const uint32_t n_todo = P.todo ? *P.todo_cnt : P.n_reads;     // with the thread pass on: only the reads it queued
     for (;;) {
-        uint32_t r = next_ticket(P.ticket);
-        if (r >= P.n_reads) break;
+        const uint32_t tk = next_ticket(P.ticket);
+        if (tk >= n_todo) break;
+        const uint32_t r = P.todo ? P.todo[tk] : tk;
         const uint8_t* q = P.seqs + P.offs[r];
         const int len = (int)(P.offs[r + 1] - P.offs[r]);
         Out O; O.out = P.out + (size_t)r * P.cap; O.n = 0; O.cap = P.cap; O.ovf = false; O.lane = lane;
@@ -738,6 +741,105 @@ __global__ void __launch_bounds__(SEED_THREADS, MINB) seed_smem(SeedParams P, De
         if (lane == 0) P.out_cnt[r] = n_out;
     }
     if (P.n_extend && lane == 0 && n_ext) atomicAdd(P.n_extend, n_ext);
+}
+
+// ---------------------------------------------------------------- thread-per-read pass (seed_thread.cuh)
+// One thread runs mem_collect_intv for one read; a warp takes 32 consecutive reads per ticket.  The reads' 2-bit packed copies
+// live in shared memory laid out [word][thread] (bank = lane).  Intervals are staged unsorted in the upper half of the read's
+// output slots, ranked by `info` with a 32-bit key per record, and written in order to the lower half.  Reads the thread
+// declines are appended to `todo` for seed_smem.
+constexpr int ST_THREADS = 128;
+template <class IdxT>
+__global__ void __launch_bounds__(ST_THREADS) seed_thread(SeedParams P, DevIndex ix, DevOpts o, uint32_t* ticket, int words) {
+    extern __shared__ __align__(16) uint32_t st_pk[];      // [words][ST_THREADS] packed reads, then [PCAP][ST_THREADS] P(b) arrays
+    uint32_t* st_pc = st_pk + (size_t)words * ST_THREADS;
+    const int tid = threadIdx.x, lane = tid & 31;
+    seedt::Index<IdxT> X;
+    X.occ = ix.occ; X.tab = reinterpret_cast<const seedt::U4*>(P.kmer_tab); X.kk = P.kmer_k;
+    X.sa = reinterpret_cast<const IdxT*>(ix.sa); X.isa = reinterpret_cast<const IdxT*>(P.isa); X.pac = ix.pac;
+    X.l_pac = (IdxT)ix.l_pac; X.n = (IdxT)ix.seq_len; X.primary = (IdxT)ix.primary;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) X.L2[c] = (IdxT)ix.L2[c];
+    seedt::Opts so; so.min_seed_len = o.min_seed_len; so.split_len = o.split_len; so.split_width = o.split_width; so.max_mem_intv = o.max_mem_intv;
+    const uint32_t half = P.cap / 2;                 // sorted records go to slots [0, half), the staging is [cap - half, cap)
+    unsigned long long n_ext_sum = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(ticket, 32u);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= P.n_reads) break;
+        const uint32_t r = base + (uint32_t)lane;
+        bool active = r < P.n_reads, fail = false;
+        if (active) {
+            const uint64_t off = P.offs[r];
+            const int len = (int)(P.offs[r + 1] - off);
+            if (len < o.min_seed_len) { P.out_cnt[r] = 0; active = false; }       // mem_chain returns before seeding
+            else if ((len >> 4) + 3 > words) fail = true;
+            else {
+                const uint8_t* q = P.seqs + off;
+                uint32_t amb = 0;
+                for (int w = 0; w < words; ++w) {
+                    uint32_t v = 0;
+                    const int b0 = w << 4;
+                    if (b0 < len) {
+                        const int nb = len - b0 < 16 ? len - b0 : 16;
+                        for (int k = 0; k < nb; ++k) { const uint32_t c = q[b0 + k]; amb |= c; v |= (c & 3u) << (30 - 2 * k); }
+                    }
+                    st_pk[w * ST_THREADS + tid] = v;
+                }
+                if (amb > 3) fail = true;          // an ambiguous base: the warp kernel's general path
+            }
+        }
+        // ---- the 32 reads of the warp advance together (seed_thread.cuh), call by call and, inside a call, list entry by list
+        // entry: the loop counters are warp votes, so the lanes meet again at every call and every column
+        seedt::Read R; R.pk = st_pk + tid; R.stride = ST_THREADS; R.len = 0;
+        seedt::Work<IdxT> W;
+        Intv* slots = P.out + (size_t)(active ? r : 0) * P.cap;
+        seedt::work_init(W, reinterpret_cast<seedt::IntvOut*>(slots + (P.cap - half)), half, st_pc + tid, ST_THREADS);
+        const bool run = active && !fail;
+        if (run) R.len = (int)(P.offs[r + 1] - P.offs[r]);
+        seedt::Calls C; seedt::calls_init(C);
+        for (;;) {
+            int x = 0; uint32_t mi = 1;
+            const bool has = run && seedt::next_call(C, so, R, W, &x, &mi);
+            if (!__any_sync(FULL, has)) break;
+            if (has) seedt::smem_forward(X, R, x, mi, W);
+            const int ncol = has && !W.fail ? W.n : 0;
+            for (int k = 0; __any_sync(FULL, k < ncol); ++k) seedt::smem_column(X, so, R, k, W, k < ncol && !W.fail);
+            if (has && C.pass == 1) C.next_x = W.ret;
+        }
+        if (run && !W.fail) seedt::last_like_pass(X, so, R, W);
+        if (active && !fail) {
+            fail = W.fail;
+            if (!fail) {
+                // rank by info: key = start | end | staging index (9 + 9 + 6 bits; reads of at most 496 bases, at most 64 records)
+                uint32_t key[64];
+                const uint32_t n = W.n_out;
+                for (uint32_t k = 0; k < n; ++k) {
+                    const uint64_t info = W.out[k].info;
+                    uint32_t kk = (uint32_t)(info >> 32) << 15 | ((uint32_t)info & 0x1ffu) << 6 | k;
+                    uint32_t j = k;
+                    while (j > 0 && key[j - 1] > kk) { key[j] = key[j - 1]; --j; }
+                    key[j] = kk;
+                }
+                for (uint32_t k = 0; k < n; ++k) slots[k] = reinterpret_cast<const Intv*>(W.out)[key[k] & 63u];
+                P.out_cnt[r] = n;
+                n_ext_sum += W.n_ext;
+            }
+        }
+        const uint32_t fm = __ballot_sync(FULL, active && fail);
+        if (fm) {
+            uint32_t at = 0;
+            if (lane == 0) at = atomicAdd(const_cast<uint32_t*>(P.todo_cnt), (uint32_t)__popc(fm));
+            at = __shfl_sync(FULL, at, 0);
+            if (active && fail) const_cast<uint32_t*>(P.todo)[at + (uint32_t)__popc(fm & ((1u << lane) - 1u))] = r;
+        }
+    }
+    if (P.n_extend) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) n_ext_sum += __shfl_xor_sync(FULL, n_ext_sum, d);
+        if (lane == 0 && n_ext_sum) atomicAdd(P.n_extend, n_ext_sum);
+    }
 }
 
 template <class IdxT> size_t lists_bytes(uint32_t list_cap, uint32_t read_cap) {
@@ -814,5 +916,25 @@ void launch_seed(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cuda
     } else {
         if (p.lists_in_smem) launch_mode<uint32_t, true, 4>(p, ix, o, st, lists_bytes<uint32_t>(p.list_cap, p.read_cap), n_warps_out);
         else launch_mode<uint32_t, false, 1>(p, ix, o, st, 0, n_warps_out);
+    }
+}
+
+// The thread-per-read pass takes a batch when the prefix table and the inverse SA exist, seeds are longer than the table is deep
+// (so that an emitted match always carries its rows) and the reads fit its packed shared-memory copy and 9-bit sort key.
+bool seed_thread_usable(const SeedParams& p, const DevOpts& o, uint32_t max_len) {
+    static const bool off = getenv("BSQ_NO_SEED_THREAD") != nullptr;
+    return !off && p.kmer_tab && p.isa && p.todo && o.min_seed_len > p.kmer_k && o.max_mem_intv > 1 && max_len <= 496 && p.cap / 2 >= 16 && p.cap / 2 <= 64;
+}
+
+void launch_seed_thread(const SeedParams& p, const DevIndex& ix, const DevOpts& o, uint32_t max_len, uint32_t* ticket, cudaStream_t st) {
+    const int words = (int)(max_len >> 4) + 3;
+    const size_t smem = (size_t)(words + seedt::PCAP) * ST_THREADS * 4;
+    const int sms = cached_sm_count();
+    if (ix.sa_bytes == 8) {
+        const int nb = cached_blocks_per_sm(seed_thread<uint64_t>, ST_THREADS, smem);
+        seed_thread<uint64_t><<<nb * sms, ST_THREADS, smem, st>>>(p, ix, o, ticket, words);
+    } else {
+        const int nb = cached_blocks_per_sm(seed_thread<uint32_t>, ST_THREADS, smem);
+        seed_thread<uint32_t><<<nb * sms, ST_THREADS, smem, st>>>(p, ix, o, ticket, words);
     }
 }

@@ -442,6 +442,10 @@ int bsq_index_prepare(bsq_index* h, float* ms) {
 // ------------------------------------------------------------------------------------------------ batch
 namespace {
 
+__global__ void k_rebase_offs(uint64_t* offs, uint64_t n, uint64_t base) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) offs[i] -= base;
+}
+
 __global__ void k_to_nt4(uint8_t* s, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint8_t c = s[i], v;
@@ -541,12 +545,15 @@ int upload_reads(bsq_index* h, Batch& b, const char* seqs, const uint64_t* offs,
         b.read_logtab_n = max_len + 1;
     }
     CUDA_CHECK(b.seqs.ensure(total + 64)); CUDA_CHECK(b.offs.ensure(n + 1)); CUDA_CHECK(b.ids.ensure(n + 1));
-    b.rel.resize(n + 1);                    // staging owned by the batch: it outlives the asynchronous copy
-    for (uint64_t i = 0; i <= n; ++i) b.rel[i] = offs[i] - (n ? offs[0] : 0);
+    // the caller's buffers go to the device as they are (pinned buffers make these copies truly asynchronous; pageable ones are staged
+    // by the runtime); the offsets are rebased to the batch's first read on the device
     if (total) CUDA_CHECK(cudaMemcpyAsync(b.seqs.p, seqs + offs[0], total, cudaMemcpyHostToDevice, b.st));
-    CUDA_CHECK(cudaMemcpyAsync(b.offs.p, b.rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, b.st));
-    if (n) CUDA_CHECK(cudaMemcpyAsync(b.ids.p, ids, n * 8, cudaMemcpyHostToDevice, b.st));
+    if (n) {
+        CUDA_CHECK(cudaMemcpyAsync(b.offs.p, offs, (n + 1) * 8, cudaMemcpyHostToDevice, b.st));
+        CUDA_CHECK(cudaMemcpyAsync(b.ids.p, ids, n * 8, cudaMemcpyHostToDevice, b.st));
+    } else CUDA_CHECK(cudaMemsetAsync(b.offs.p, 0, 8, b.st));
     if (total) { k_to_nt4<<<(unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 16), 256, 0, b.st>>>(b.seqs.p, total); ++h->timing.launches; }
+    if (n && offs[0]) { k_rebase_offs<<<(unsigned)std::min<uint64_t>((n + 256) / 256, 148 * 8), 256, 0, b.st>>>(b.offs.p, n + 1, offs[0]); ++h->timing.launches; }
     h->timing.h2d_bytes += total + (n + 1) * 8 + n * 8;
     b.resident = true;
     return BSQ_OK;

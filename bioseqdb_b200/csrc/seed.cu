@@ -795,7 +795,7 @@ __global__ void __launch_bounds__(ST_THREADS) seed_thread(SeedParams P, DevIndex
         seedt::Read R; R.pk = st_pk + tid; R.stride = ST_THREADS; R.len = 0;
         seedt::Work<IdxT> W;
         Intv* slots = P.out + (size_t)(active ? r : 0) * P.cap;
-        seedt::work_init(W, reinterpret_cast<seedt::IntvOut*>(slots + (P.cap - half)), half, st_pc + tid, ST_THREADS);
+        seedt::work_init(W, reinterpret_cast<seedt::IntvOut*>(slots + (P.cap - half)), half < (uint32_t)seedt::PCAP ? half : (uint32_t)seedt::PCAP, st_pc + tid, ST_THREADS);
         const bool run = active && !fail;
         if (run) R.len = (int)(P.offs[r + 1] - P.offs[r]);
         seedt::Calls C; seedt::calls_init(C);
@@ -813,16 +813,17 @@ __global__ void __launch_bounds__(ST_THREADS) seed_thread(SeedParams P, DevIndex
             fail = W.fail;
             if (!fail) {
                 // rank by info: key = start | end | staging index (9 + 9 + 6 bits; reads of at most 496 bases, at most 64 records)
-                uint32_t key[64];
+                // (the keys live in the lane's P(b) array, which is free once the calls are over)
+                uint32_t* key = st_pc + tid;
                 const uint32_t n = W.n_out;
                 for (uint32_t k = 0; k < n; ++k) {
                     const uint64_t info = W.out[k].info;
                     uint32_t kk = (uint32_t)(info >> 32) << 15 | ((uint32_t)info & 0x1ffu) << 6 | k;
                     uint32_t j = k;
-                    while (j > 0 && key[j - 1] > kk) { key[j] = key[j - 1]; --j; }
-                    key[j] = kk;
+                    while (j > 0 && key[(j - 1) * ST_THREADS] > kk) { key[j * ST_THREADS] = key[(j - 1) * ST_THREADS]; --j; }
+                    key[j * ST_THREADS] = kk;
                 }
-                for (uint32_t k = 0; k < n; ++k) slots[k] = reinterpret_cast<const Intv*>(W.out)[key[k] & 63u];
+                for (uint32_t k = 0; k < n; ++k) slots[k] = reinterpret_cast<const Intv*>(W.out)[key[k * ST_THREADS] & 63u];
                 P.out_cnt[r] = n;
                 n_ext_sum += W.n_ext;
             }

@@ -214,17 +214,20 @@ template <class IdxT, int IS_BACK> ST_HD Iv<IdxT> extend_one(const Index<IdxT>& 
 // followed, when the match outgrows the table, by a tail of real extensions or (one occurrence) a text comparison.
 // P lives in a small per-thread array pc[] (steps a non-unique entry was kept) plus one implicit range (the steps the unique
 // entry is alive).
-constexpr int LCAP = 32;                      // forward entries of one call
+constexpr int RCAP = 8;                       // forward entries longer than the table (they carry their rows)
+constexpr int TAB_UNROLL = 4;                 // prefix-table lookups a thread keeps in flight in a column walk
 constexpr int PCAP = 32;                      // steps a non-unique entry may be kept (table depth + a few real extensions)
-enum { K_TAB = 0, K_ROWS = 1 };              // K_TAB: match of at most kk bases, rows not stored; K_ROWS: x0 / x1 valid
-template <class IdxT> struct Ent { IdxT x0, x1; uint32_t x2; int16_t end; int16_t kind; };
+template <class IdxT> struct RowsEnt { IdxT x0, x1; uint32_t x2; int end; };
 
+// The forward entries of a call need no array: an entry of at most K bases is fully described by its length (its size is a table
+// entry), so the table part of the list is a BIT MASK over lengths 1..K; only the few entries longer than the table are stored.
 template <class IdxT> struct Work {
     // the call in flight: bwt_smem1a(x, min_intv)
-    int x, ret, n; uint32_t min_intv;
+    int x, ret, n, n_rows; uint32_t min_intv;
+    uint32_t mask, top_z;                     // bit L set: the match q[x .. x+L) is a list entry; top_z = size of the longest of them
     int nvalid, uq_lo, uq_hi, last_mem_start; bool have_mem;
     uint32_t* pc; int pc_stride;             // pc[b * pc_stride], b < PCAP
-    Ent<IdxT> ent[LCAP];
+    RowsEnt<IdxT> re[RCAP];
     // results
     IntvOut* out; uint32_t n_out, cap; bool fail; unsigned long long n_ext;
 };
@@ -234,33 +237,40 @@ template <class IdxT> ST_HD void emit(Work<IdxT>& W, IdxT x0, IdxT x1, uint32_t 
     IntvOut v; v.x0 = x0; v.x1 = x1; v.x2 = x2; v.info = (uint64_t)(uint32_t)start << 32 | (uint32_t)end;
     W.out[W.n_out++] = v;
 }
-template <class IdxT> ST_HD bool push(Work<IdxT>& W, IdxT x0, IdxT x1, uint32_t x2, int end, int kind) {
-    if (W.n >= LCAP) { W.fail = true; return false; }
-    Ent<IdxT>& d = W.ent[W.n++]; d.x0 = x0; d.x1 = x1; d.x2 = x2; d.end = (int16_t)end; d.kind = (int16_t)kind;
+template <class IdxT> ST_HD bool push_rows(Work<IdxT>& W, IdxT x0, IdxT x1, uint32_t x2, int end) {
+    if (W.n_rows >= RCAP) { W.fail = true; return false; }
+    RowsEnt<IdxT>& d = W.re[W.n_rows++]; d.x0 = x0; d.x1 = x1; d.x2 = x2; d.end = end;
     return true;
 }
 
-// forward walk of bwt_smem1a(x, min_intv): pushes the list entries, shortest match first; W.ret = end of the longest match
+// forward walk of bwt_smem1a(x, min_intv): records the list entries (mask + rows entries); W.ret = end of the longest match
 template <class IdxT>
 ST_HD void smem_forward(const Index<IdxT>& X, const Read& R, int x, uint32_t min_intv, Work<IdxT>& W) {
     const int len = R.len, K = X.kk;
     if (min_intv < 1) min_intv = 1;
-    W.x = x; W.min_intv = min_intv; W.n = 0; W.ret = len;
+    W.x = x; W.min_intv = min_intv; W.n = 0; W.n_rows = 0; W.mask = 0; W.top_z = 0; W.ret = len;
     W.nvalid = 0; W.uq_lo = W.uq_hi = 0; W.have_mem = false; W.last_mem_start = 0;
-    // matches of up to K bases: the prefix table
+    // matches of up to K bases: the prefix table.  The K lookups are independent: all in flight together.
     const int maxt = len - x < K ? len - x : K;
     const uint32_t w0 = rd_window(R, x);
-    uint32_t cur_x2 = ld_u4(X.tab + level_off(1) + (w0 >> 30)).z;
+    uint32_t zs[16];
+#pragma unroll
+    for (int t = 1; t <= 15; ++t) zs[t] = t <= maxt ? ld_u32(reinterpret_cast<const uint32_t*>(X.tab + (level_off(t) + (w0 >> (32 - 2 * t)))) + 2) : 0u;
+    uint32_t cur_x2 = zs[1], n_ext = 0, mask = 0, top_z = 0;
     int i = x + 1; bool stopped = false;
-    for (int t = 2; t <= maxt; ++t, ++i) {       // appending q[i], i = x + t - 1
-        const uint32_t sz = ld_u4(X.tab + level_off(t) + (w0 >> (32 - 2 * t))).z;
-        ++W.n_ext;
-        if (sz != cur_x2) {
-            if (!push(W, (IdxT)0, (IdxT)0, cur_x2, i, K_TAB)) return;
-            if (sz < min_intv) { stopped = true; break; }
+#pragma unroll
+    for (int t = 2; t <= 15; ++t) {              // appending q[i], i = x + t - 1
+        if (t <= maxt && !stopped) {
+            const uint32_t sz = zs[t];
+            ++n_ext;
+            if (sz != cur_x2) {
+                mask |= 1u << (t - 1); top_z = cur_x2;
+                if (sz < min_intv) stopped = true;
+            }
+            if (!stopped) { cur_x2 = sz; ++i; }
         }
-        cur_x2 = sz;
     }
+    W.n_ext += n_ext;
     if (!stopped) {
         const U4 e = ld_u4(X.tab + level_off(maxt) + (w0 >> (32 - 2 * maxt)));
         Iv<IdxT> ik; ik.x0 = tab_x0<IdxT>(e); ik.x1 = tab_x1<IdxT>(e); ik.x2 = cur_x2;
@@ -272,21 +282,28 @@ ST_HD void smem_forward(const Index<IdxT>& X, const Read& R, int x, uint32_t min
                 if (run > 0) { i += run; ik.x1 = ld_idx(X.isa + (X.n - pos - (IdxT)(i - x))); W.n_ext += (unsigned long long)run; }
                 if (i == len) break;
                 ++W.n_ext;                       // the extension the scalar code tries next empties the interval
-                if (!push(W, ik.x0, ik.x1, 1u, i, K_ROWS)) return;
+                if (i - x <= K) { mask |= 1u << (i - x); top_z = 1; }
+                else if (!push_rows(W, ik.x0, ik.x1, 1u, i)) return;
                 stopped = true;
                 break;
             }
             const Iv<IdxT> ok = extend_one<IdxT, 0>(X, ik, 3 - rd_base(R, i));
             ++W.n_ext;
             if (ok.x2 != ik.x2) {
-                if (!push(W, ik.x0, ik.x1, ik.x2, i, i - x <= K ? K_TAB : K_ROWS)) return;
+                if (i - x <= K) { mask |= 1u << (i - x); top_z = ik.x2; }
+                else if (!push_rows(W, ik.x0, ik.x1, ik.x2, i)) return;
                 if (ok.x2 < min_intv) { stopped = true; break; }
             }
             ik = ok;
         }
-        if (!stopped && !push(W, ik.x0, ik.x1, ik.x2, len, len - x <= K ? K_TAB : K_ROWS)) return;   // reached the end of the read
+        if (!stopped) {                          // reached the end of the read: the last interval is recorded too
+            if (len - x <= K) { mask |= 1u << (len - x); top_z = ik.x2; }
+            else if (!push_rows(W, ik.x0, ik.x1, ik.x2, len)) return;
+        }
     }
-    W.ret = W.ent[W.n - 1].end;
+    W.mask = mask; W.top_z = top_z;
+    W.n = W.n_rows + popc32(mask);
+    W.ret = W.n_rows ? W.re[W.n_rows - 1].end : x + (31 - clz32(mask));
 }
 
 // the entry with rows (x0, x1, x2) dies at step i (it is the match q[i+1 .. end)): bwt_smem1a's emission rule
@@ -314,26 +331,54 @@ ST_HD void smem_column(const Index<IdxT>& X, const Opts& o, const Read& R, int k
     int end = 0, b = 0, i = x - 1, nb = 0;
     uint32_t cur = 0; IdxT x0 = 0, x1 = 0; bool rows = false;
     if (live) {
-        const Ent<IdxT>& p = W.ent[W.n - 1 - k];
-        end = p.end; cur = p.x2; x0 = p.x0; x1 = p.x1; rows = p.kind == K_ROWS;
+        if (k < W.n_rows) { const RowsEnt<IdxT>& p = W.re[W.n_rows - 1 - k]; end = p.end; cur = p.x2; x0 = p.x0; x1 = p.x1; rows = true; }
+        else {
+            // the longest table entry not walked yet; its size is only needed when it is 1 (the longest entry of the list) --
+            // every other entry has at least 2 occurrences, and the exact number is read again if the walk outgrows the table
+            const int L = 31 - clz32(W.mask);
+            cur = (k == W.n_rows) ? W.top_z : 2u;
+            W.mask ^= 1u << L; end = x + L;
+        }
         if (!(can_uq && cur == 1)) nb = i + 1 < K - (end - x) ? i + 1 : K - (end - x);     // steps with i >= 0 and end - i <= K
+        if (nb < 0) nb = 0;
     }
-    // ---- steps inside the prefix table: one lookup and one comparison with P(b) each
+    // ---- steps inside the prefix table: one lookup and one comparison with P(b) each.  The address of a step's lookup does not
+    // depend on the previous step's result (only whether the walk goes on does), so TAB_UNROLL lookups are issued together
+    // (loads in flight per thread), then consumed in order; the lookups past the end of the walk are simply not used.
+    uint32_t n_ext = 0;
     while (ST_ANY(live && b < nb)) {
         if (live && b < nb) {
-            const int lq = end - i;
-            const uint32_t s = ld_u4(X.tab + level_off(lq) + (rd_window(R, i) >> (32 - 2 * lq))).z;
-            ++W.n_ext;
-            const uint32_t P = b < W.nvalid ? W.pc[b * W.pc_stride] : (b >= W.uq_lo && b < W.uq_hi ? 1u : 0u);
-            if (s < min_intv) { entry_dies(o, W, P != 0, i, end, x0, x1, cur); live = false; }
-            else if (s == P) live = false;                                // same occurrences as a longer entry from here on
-            else {
-                W.pc[b * W.pc_stride] = s; if (W.nvalid <= b) W.nvalid = b + 1;
-                cur = s; rows = false; ++b; --i;
-                if (can_uq && s == 1) nb = b;                             // one occurrence left: the tail takes it
+            const int w = i >> 4;
+            const uint32_t wc = rd_word(R, w > 0 ? w - 1 : 0), wa = rd_word(R, w), wb = rd_word(R, w + 1);
+            uint32_t sv[TAB_UNROLL];
+#pragma unroll
+            for (int u = 0; u < TAB_UNROLL; ++u) {
+                sv[u] = 0;
+                const int iu = i - u;
+                if (b + u < nb) {
+                    const int sh = (iu & 15) << 1, lq = end - iu;
+                    const uint32_t win = (iu >> 4) == w ? fsl(wb, wa, sh) : fsl(wa, wc, sh);
+                    sv[u] = ld_u32(reinterpret_cast<const uint32_t*>(X.tab + (level_off(lq) + (win >> (32 - 2 * lq)))) + 2);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < TAB_UNROLL; ++u) {
+                if (live && b < nb) {
+                    const uint32_t s = sv[u];
+                    ++n_ext;
+                    const uint32_t P = b < W.nvalid ? W.pc[b * W.pc_stride] : (b >= W.uq_lo && b < W.uq_hi ? 1u : 0u);
+                    if (s < min_intv) { entry_dies(o, W, P != 0, i, end, x0, x1, cur); live = false; }
+                    else if (s == P) live = false;                        // same occurrences as a longer entry from here on
+                    else {
+                        W.pc[b * W.pc_stride] = s; if (W.nvalid <= b) W.nvalid = b + 1;
+                        cur = s; rows = false; ++b; --i;
+                        if (can_uq && s == 1) nb = b;                     // one occurrence left: the tail takes it
+                    }
+                }
             }
         }
     }
+    W.n_ext += n_ext;
     // ---- tail: one occurrence => text comparison; otherwise real extensions
     while (ST_ANY(live)) {
         if (live) {
@@ -355,7 +400,7 @@ ST_HD void smem_column(const Index<IdxT>& X, const Opts& o, const Read& R, int k
                     uint32_t s; IdxT nx0 = x0, nx1 = x1; bool nrows = false;
                     if (lq <= K) s = tab_get(X, R, i, lq).z;
                     else {
-                        if (!rows) { const U4 f = tab_get(X, R, i + 1, lq - 1); x0 = tab_x0<IdxT>(f); x1 = tab_x1<IdxT>(f); }
+                        if (!rows) { const U4 f = tab_get(X, R, i + 1, lq - 1); x0 = tab_x0<IdxT>(f); x1 = tab_x1<IdxT>(f); cur = f.z; }
                         Iv<IdxT> pi; pi.x0 = x0; pi.x1 = x1; pi.x2 = cur;
                         const Iv<IdxT> ok = extend_one<IdxT, 1>(X, pi, rd_base(R, i));
                         s = ok.x2; nx0 = ok.x0; nx1 = ok.x1; nrows = true;

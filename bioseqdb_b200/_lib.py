@@ -13,6 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbioseqdb_gpu.so")
 CSRC = os.path.join(_HERE, "csrc")
 
+# rows as the parity tests and the oracle binding see them: every mem_alnreg_t / mem_aln_t field side by side.  The library returns
+# them as two records per row -- bsq_row (64 bytes, always) and bsq_row_ext (48 bytes, with BSQ_FLAG_ROWS_EXT) -- which
+# BwaIndex._collect joins into this dtype (extension fields are zero when they were not requested).
 ROW_DTYPE = np.dtype([
     ("rb", "<i8"), ("re", "<i8"), ("pos", "<i8"), ("hash", "<u8"),
     ("qb", "<i4"), ("qe", "<i4"), ("rid", "<i4"), ("score", "<i4"), ("truesc", "<i4"), ("sub", "<i4"),
@@ -22,6 +25,18 @@ ROW_DTYPE = np.dtype([
     ("cigar_off", "<u4"), ("n_cigar", "<u4"), ("ref_id", "<i8"),
 ])
 assert ROW_DTYPE.itemsize == 120
+PUB_ROW_DTYPE = np.dtype([   # bsq_row
+    ("rb", "<i8"), ("re", "<i8"), ("pos", "<i8"), ("ref_id", "<i8"),
+    ("qb", "<i4"), ("qe", "<i4"), ("rid", "<i4"), ("score", "<i4"), ("NM", "<i4"),
+    ("cigar_off", "<u4"), ("n_cigar", "<u4"), ("flag", "<u2"), ("mapq", "u1"), ("is_rev", "u1"),
+])
+assert PUB_ROW_DTYPE.itemsize == 64
+EXT_ROW_DTYPE = np.dtype([   # bsq_row_ext
+    ("hash", "<u8"), ("truesc", "<i4"), ("sub", "<i4"), ("csub", "<i4"), ("sub_n", "<i4"), ("w", "<i4"), ("seedcov", "<i4"),
+    ("secondary", "<i4"), ("seedlen0", "<i4"), ("n_comp", "<i4"), ("frac_rep", "<f4"),
+])
+assert EXT_ROW_DTYPE.itemsize == 48
+FLAG_ROWS_EXT = 1
 HOLE_DTYPE = np.dtype([("offset", "<i8"), ("len", "<i4"), ("amb", "S1"), ("_pad", "V3")])
 
 ARR_PAC, ARR_OCC, ARR_SA, ARR_ANN_OFFSET, ARR_ANN_LEN, ARR_ANN_ID, ARR_COUNT = range(7)
@@ -34,7 +49,7 @@ class BsqOpts(C.Structure):
 
 class BsqResult(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("row_off", C.POINTER(C.c_uint64)), ("rows", C.c_void_p),
-                ("cigar", C.POINTER(C.c_uint32)), ("n_cigar_words", C.c_uint64)]
+                ("cigar", C.POINTER(C.c_uint32)), ("n_cigar_words", C.c_uint64), ("rows_ext", C.c_void_p)]
 
 
 class BsqTuples(C.Structure):
@@ -83,11 +98,14 @@ def lib():
     L.bsq_index_new.restype = vp
     L.bsq_index_new.argtypes = [C.POINTER(BsqOpts), C.c_int]
     L.bsq_index_set_opts.argtypes = [vp, C.POINTER(BsqOpts)]
+    L.bsq_index_set_flags.argtypes = [vp, u32]
     L.bsq_index_add_ref.argtypes = [vp, i64, vp, u32, vp, u32]
     L.bsq_index_add_ref_datums.argtypes = [vp, u64, vp, vp, vp]
     L.bsq_index_build.argtypes = [vp]
     L.bsq_index_free.argtypes = [vp]
     L.bsq_align_batch.argtypes = [vp, vp, vp, vp, u64, C.POINTER(C.POINTER(BsqResult))]
+    L.bsq_align_batch_datums.argtypes = [vp, vp, vp, vp, u64, C.POINTER(C.POINTER(BsqResult))]
+    L.bsq_session_lrand48.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
     L.bsq_result_free.argtypes = [C.POINTER(BsqResult)]
     L.bsq_last_timing.argtypes = [vp, C.POINTER(BsqTiming)]
     L.bsq_result_tuples.argtypes = [vp, C.POINTER(BsqResult), vp, vp, u32, C.POINTER(C.POINTER(BsqTuples))]
@@ -121,8 +139,8 @@ def lib():
 
 
 ABI_SYMBOLS = [
-    "bsq_last_error", "bsq_device_count", "bsq_opts_init", "bsq_index_new", "bsq_index_set_opts", "bsq_index_add_ref", "bsq_index_add_ref_datums", "bsq_index_build",
-    "bsq_index_free", "bsq_align_batch", "bsq_result_free", "bsq_last_timing", "bsq_result_tuples", "bsq_tuples_free", "bsq_nuclseq_from_text_batch", "bsq_nuclseqs_free", "bsq_reads_upload", "bsq_align_resident", "bsq_result_download",
+    "bsq_last_error", "bsq_device_count", "bsq_opts_init", "bsq_index_new", "bsq_index_set_opts", "bsq_index_set_flags", "bsq_index_add_ref", "bsq_index_add_ref_datums", "bsq_index_build",
+    "bsq_index_free", "bsq_align_batch", "bsq_align_batch_datums", "bsq_session_lrand48", "bsq_result_free", "bsq_last_timing", "bsq_result_tuples", "bsq_tuples_free", "bsq_nuclseq_from_text_batch", "bsq_nuclseqs_free", "bsq_reads_upload", "bsq_align_resident", "bsq_result_download",
     "bsq_index_get_meta", "bsq_index_device_bytes", "bsq_index_device_ptr", "bsq_index_download", "bsq_index_alloc_replica", "bsq_index_host_state_size", "bsq_index_host_state_get", "bsq_index_replica_finish", "bsq_index_prepare", "bsq_index_bwt_plain", "bsq_index_sa_sampled",
     "bsq_debug_seed", "bsq_debug_ksw_extend", "bsq_debug_ksw_extend_thread", "bsq_debug_ksw_global", "bsq_bench_gather", "bsq_bench_dpx", "bsq_set_counters", "bsq_get_counters",
 ]

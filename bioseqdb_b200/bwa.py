@@ -10,7 +10,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import BsqMeta, BsqOpts, BsqResult, BsqTiming, ROW_DTYPE, check, ptr
+from ._lib import BsqMeta, BsqOpts, BsqResult, BsqTiming, EXT_ROW_DTYPE, PUB_ROW_DTYPE, ROW_DTYPE, check, ptr
 from .sequence import NucleotideSequence, nuclseq_from_text, nuclseq_to_text
 
 _CIGAR_CHR = "MIDNSHP=XB"  # htslib's table applied to bwa op codes (bwa.cpp:70-77): soft clip prints as 'N'
@@ -107,9 +107,9 @@ class BwaIndex:
         if not self.h:
             raise _lib.BsqError(self.L.bsq_last_error().decode())
         self.device = device
+        self.set_rows_ext(True)      # the Python mirror drives the parity tests: it asks for every field (bench's e2e leg switches it off)
         self.n_rows = 0
         self._refs = []  # ids of the reference rows added through this object (the rows themselves live in the library)
-        self._lrand_state = 0
 
     def close(self):
         if getattr(self, "h", None):
@@ -216,33 +216,23 @@ class BwaIndex:
         check(self.L.bsq_index_sa_sampled(self.h, ptr(out), n_sa))
         return out
 
-    # ---- lrand48 ids: mem_align1 draws one per read; the host keeps the generator
-    def next_ids(self, n: int) -> np.ndarray:
-        from .synth import lrand48_ids
-        ids, self._lrand_state = lrand48_ids(n, self._lrand_state) if n <= 4096 else self._ids_big(n)
-        return ids
+    # ---- lrand48 ids: mem_align1 draws one per read.  The library keeps the session's generator state in the handle
+    # and draws the ids on the device whenever a call passes none; _lrand_state is a view of that state (the index cache moves it
+    # from one cached index to the next, bioseqdb_b200/cache.py).
+    @property
+    def _lrand_state(self) -> int:
+        return self.session_lrand48()
 
-    def _ids_big(self, n):
-        from .synth import lrand48_ids_fast
-        if self._lrand_state == 0:
-            ids = lrand48_ids_fast(n)
-            # recover the state after n draws: one more scalar pass over the last block is cheap
-            a, c, m = 0x5DEECE66D, 0xB, (1 << 48) - 1
-            x = 0
-            # jump: x_n = A^n x_0 + C (A^n - 1)/(A - 1); computed by square-and-multiply on the affine map
-            A, Cc, k = 1, 0, n
-            ba, bc = a, c
-            while k:
-                if k & 1:
-                    A, Cc = (A * ba) & m, (Cc * ba + bc) & m
-                ba, bc = (ba * ba) & m, (bc * ba + bc) & m
-                k >>= 1
-            x = (A * x + Cc) & m
-            return ids, x
-        from .synth import lrand48_ids
-        return lrand48_ids(n, self._lrand_state)
+    @_lrand_state.setter
+    def _lrand_state(self, v: int):
+        self.session_lrand48(int(v))
 
     # ---- alignment
+    def set_rows_ext(self, on: bool):
+        """Ask for (or drop) the bsq_row_ext records: the mem_alnreg_t fields only parity checks read (hash, truesc, sub, ...)."""
+        check(self.L.bsq_index_set_flags(self.h, _lib.FLAG_ROWS_EXT if on else 0))
+        self.rows_ext = bool(on)
+
     def _collect(self, res_p) -> AlignResult:
         r = res_p.contents
         n = int(r.n_reads)
@@ -250,7 +240,13 @@ class BwaIndex:
         total = int(row_off[n])
         rows = np.zeros(total, dtype=ROW_DTYPE)
         if total:
-            C.memmove(ptr(rows), r.rows, total * ROW_DTYPE.itemsize)
+            pub = np.frombuffer((C.c_uint8 * (total * PUB_ROW_DTYPE.itemsize)).from_address(r.rows), dtype=PUB_ROW_DTYPE)
+            for f in PUB_ROW_DTYPE.names:
+                rows[f] = pub[f]
+            if r.rows_ext:
+                ext = np.frombuffer((C.c_uint8 * (total * EXT_ROW_DTYPE.itemsize)).from_address(r.rows_ext), dtype=EXT_ROW_DTYPE)
+                for f in EXT_ROW_DTYPE.names:
+                    rows[f] = ext[f]
         ncw = int(r.n_cigar_words)
         cigar = np.ctypeslib.as_array(r.cigar, shape=(max(ncw, 1),))[:ncw].copy()
         self.L.bsq_result_free(res_p)
@@ -261,10 +257,29 @@ class BwaIndex:
         seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
         offs = np.ascontiguousarray(offs, dtype=np.uint64)
         n = len(offs) - 1
-        ids = self.next_ids(n) if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
         res = C.POINTER(BsqResult)()
-        check(self.L.bsq_align_batch(self.h, ptr(seqs), ptr(offs), ptr(ids), n, C.byref(res)))
+        check(self.L.bsq_align_batch(self.h, ptr(seqs), ptr(offs), ptr(ids) if ids is not None else None, n, C.byref(res)))
         return self._collect(res)
+
+    def align_batch_datums(self, data: np.ndarray, off: np.ndarray, ids: np.ndarray | None = None) -> AlignResult:
+        """The same call with the reads as NUCLSEQ datum images (image i at data[off[i]:], off has n + 1 entries): what the PG glue holds
+        for the query rows (extension.cpp:362) before to_text_palloc.  ids=None: the library continues the session's lrand48 stream."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = len(off) - 1
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+        res = C.POINTER(BsqResult)()
+        check(self.L.bsq_align_batch_datums(self.h, ptr(data), ptr(off), ptr(ids) if ids is not None else None, n, C.byref(res)))
+        return self._collect(res)
+
+    def session_lrand48(self, state: int | None = None) -> int:
+        """Read (state=None) or set the lrand48 state the library draws read ids from when a call passes none."""
+        v = C.c_uint64(0 if state is None else state)
+        check(self.L.bsq_session_lrand48(self.h, 0 if state is None else 1, C.byref(v)))
+        return int(v.value)
 
     def upload(self, seqs, offs, ids):
         seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
@@ -287,7 +302,9 @@ class BwaIndex:
         seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
         offs = np.ascontiguousarray(offs, dtype=np.uint64)
         row_off = np.ascontiguousarray(res.row_off, dtype=np.uint64)
-        rows = np.ascontiguousarray(res.rows)
+        rows = np.zeros(len(res.rows), dtype=PUB_ROW_DTYPE)
+        for f in PUB_ROW_DTYPE.names:
+            rows[f] = res.rows[f]
         cigar = np.ascontiguousarray(res.cigar, dtype=np.uint32)
         r = BsqResult()
         r.n_reads = len(row_off) - 1

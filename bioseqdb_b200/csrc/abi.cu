@@ -27,7 +27,7 @@ void bsq_set_error(const char* fmt, ...) {
 // every extern "C" entry point starts with a clean error string: bsq_last_error() after a call describes THAT call
 #define BSQ_ENTRY() do { g_err[0] = 0; } while (0)
 
-static_assert(sizeof(bsq_row) == sizeof(RowDev), "bsq_row / RowDev mismatch");
+static_assert(sizeof(bsq_row) == sizeof(RowPub) && sizeof(bsq_row_ext) == sizeof(RowExt), "bsq_row / RowPub mismatch");
 static_assert(sizeof(bsq_hole) == 16, "bsq_hole must match bntamb1_t");
 
 namespace {
@@ -50,10 +50,11 @@ template <class T> struct DevBuf {
 struct Batch {
     uint64_t n = 0; uint32_t max_len = 0; uint64_t total_bases = 0;
     DevBuf<uint8_t> seqs; DevBuf<uint64_t> offs; DevBuf<int64_t> ids;
+    DevBuf<uint8_t> datums; DevBuf<uint64_t> datum_off, scan_tmp64;   // reads handed over as NUCLSEQ datum images (upload_datums)
     DevBuf<Intv> intv; DevBuf<uint32_t> intv_cnt; uint32_t intv_cap = 0;
     DevBuf<Intv> seed_scratch; uint32_t list_cap = 0;
     DevBuf<SeedRec> raw, seeds; DevBuf<ChainTmp> ctmp; DevBuf<uint32_t> ord; DevBuf<ChainRec> chains; DevBuf<uint64_t> srt;
-    DevBuf<RegRec> regs; DevBuf<RowDev> rows, rows_compact; DevBuf<uint32_t> reg_cnt, row_cnt, row_off, scan_tmp;
+    DevBuf<RegRec> regs; DevBuf<RowDev> rows; DevBuf<RowPub> rows_compact; DevBuf<RowExt> rows_ext; DevBuf<uint32_t> reg_cnt, row_cnt, row_off, scan_tmp;
     DevBuf<ReadBlock> blocks; uint32_t pool_cap = 0;
     DevBuf<uint32_t> cigar; uint32_t cigar_cap = 0;
     DevBuf<double> read_logtab; uint32_t read_logtab_n = 0; uint32_t rseq_cap = 0;
@@ -61,8 +62,8 @@ struct Batch {
     DevBuf<ExtMemo> ext_memo; DevBuf<uint8_t> ext_memo_key; DevBuf<uint32_t> ext_memo_perm, ext_memo_hist, ext_todo, chain_todo, fin_todo, seed_todo;   // thread-per-extension pre-pass (extend_plan.cu)
     DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..23] counters (u64 x 8), [24] narrow_cnt, [25] wide_cnt, [26..27] tickets, [56] reads left for sw_extend, [57] reads left for the warp chain kernel, [58] for regs_finalize
     size_t device_bytes() const {
-        return seqs.bytes() + offs.bytes() + ids.bytes() + intv.bytes() + intv_cnt.bytes() + seed_scratch.bytes() + raw.bytes() + seeds.bytes() + ctmp.bytes() +
-               ord.bytes() + chains.bytes() + srt.bytes() + regs.bytes() + rows.bytes() + rows_compact.bytes() + reg_cnt.bytes() + row_cnt.bytes() + row_off.bytes() +
+        return seqs.bytes() + offs.bytes() + ids.bytes() + datums.bytes() + datum_off.bytes() + scan_tmp64.bytes() + intv.bytes() + intv_cnt.bytes() + seed_scratch.bytes() + raw.bytes() + seeds.bytes() + ctmp.bytes() +
+               ord.bytes() + chains.bytes() + srt.bytes() + regs.bytes() + rows.bytes() + rows_compact.bytes() + rows_ext.bytes() + reg_cnt.bytes() + row_cnt.bytes() + row_off.bytes() +
                scan_tmp.bytes() + blocks.bytes() + cigar.bytes() + read_logtab.bytes() + ext_scratch.bytes() + fin_scratch.bytes() + narrow_z.bytes() +
                narrow_jobs.bytes() + wide_jobs.bytes() + ctl.bytes() + ext_memo.bytes() + ext_memo_key.bytes() + ext_memo_perm.bytes() + ext_memo_hist.bytes() + ext_todo.bytes() + chain_todo.bytes() + fin_todo.bytes() + seed_todo.bytes();
     }
@@ -70,7 +71,7 @@ struct Batch {
     // one batch = one lane of the host pipeline: its stream, the host staging that must outlive the async copies,
     // and the state of the attempt in flight (pipeline_enqueue -> pipeline_check)
     cudaStream_t st = nullptr;
-    std::vector<uint64_t> rel;
+    std::vector<bsq_row_ext> ext_tmp;   // extension records fetched only to finish a MAPQ on the host
     uint32_t* ctl_host = nullptr;       // pinned, 16 words: ctl[0..7], total rows (2 words), host-MAPQ flag
     cudaEvent_t ev[5]; bool ev_ok = false;
     cudaEvent_t ev_x[4]; bool evx_ok = false;   // chunked mode: upload begin/end, download begin/end
@@ -83,8 +84,8 @@ struct Batch {
         if (ev_ok) { for (auto& e : ev) cudaEventDestroy(e); ev_ok = false; }
         if (evx_ok) { for (auto& e : ev_x) cudaEventDestroy(e); evx_ok = false; }
         if (ext_aux_ok) { for (auto& s_ : ext_aux.st) cudaStreamDestroy(s_); for (auto& e : ext_aux.ev) cudaEventDestroy(e); ext_aux_ok = false; }
-        seqs.release(); offs.release(); ids.release(); intv.release(); intv_cnt.release(); seed_scratch.release(); raw.release(); seeds.release();
-        ctmp.release(); ord.release(); chains.release(); srt.release(); regs.release(); rows.release(); rows_compact.release(); reg_cnt.release();
+        seqs.release(); offs.release(); ids.release(); datums.release(); datum_off.release(); scan_tmp64.release(); intv.release(); intv_cnt.release(); seed_scratch.release(); raw.release(); seeds.release();
+        ctmp.release(); ord.release(); chains.release(); srt.release(); regs.release(); rows.release(); rows_compact.release(); rows_ext.release(); reg_cnt.release();
         row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release();
         ctl.release(); narrow_z.release(); narrow_jobs.release(); wide_jobs.release(); read_logtab.release();
         ext_memo.release(); ext_memo_key.release(); ext_memo_perm.release(); ext_memo_hist.release(); ext_todo.release(); chain_todo.release(); fin_todo.release(); seed_todo.release();
@@ -108,6 +109,8 @@ struct bsq_index {
     void* d_isa = nullptr;           // inverse SA for the unique-match shortcut of the seeding kernel (built lazily, rows as wide as the SA's)
     void* d_kmer = nullptr; int kmer_k = 0;          // k-mer table of the LAST-like seeding pass (built lazily per device index)
     bool collect_counters = false;
+    uint32_t flags = 0;              // BSQ_FLAG_*
+    uint64_t lrand_state = 0;        // glibc lrand48 state of the session (one draw per aligned read when the caller passes no ids)
     bool replica_pending = false;    // device arrays allocated by bsq_index_alloc_replica, host mirrors not yet rebuilt (bsq_index_replica_finish)
     uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -172,6 +175,14 @@ int bsq_index_set_opts(bsq_index* h, const bsq_opts* o) {
     if (!h || !o) { bsq_set_error("null argument"); return BSQ_ERR; }
     if (check_opts(o) != BSQ_OK) return BSQ_ERR;
     h->opts = *o; fill_dev_opts(h);
+    return BSQ_OK;
+}
+
+int bsq_index_set_flags(bsq_index* h, uint32_t flags) {
+    BSQ_ENTRY();
+    if (!h) { bsq_set_error("null index"); return BSQ_ERR; }
+    if (flags & ~BSQ_FLAG_ROWS_EXT) { bsq_set_error("unknown flag bits %#x", flags & ~BSQ_FLAG_ROWS_EXT); return BSQ_ERR; }
+    h->flags = flags;
     return BSQ_OK;
 }
 
@@ -442,6 +453,66 @@ int bsq_index_prepare(bsq_index* h, float* ms) {
 // ------------------------------------------------------------------------------------------------ batch
 namespace {
 
+// ids[i] = the (first + i + 1)-th value glibc lrand48() returns from state x0 (mem_align1 draws one per read):
+// x_k = A^k x0 + C (A^k - 1) / (A - 1) mod 2^48 by square-and-multiply on the affine map, id = x_k >> 17
+__global__ void k_lrand48_ids(uint64_t x0, uint64_t first, uint64_t n, int64_t* ids) {
+    const uint64_t M = (1ull << 48) - 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t k = first + i + 1, A = 1, C = 0, ba = 0x5DEECE66DULL, bc = 0xBULL;
+        while (k) {
+            if (k & 1) { A = (A * ba) & M; C = (C * ba + bc) & M; }
+            bc = (bc * ba + bc) & M; ba = (ba * ba) & M;
+            k >>= 1;
+        }
+        ids[i] = (int64_t)(((A * x0 + C) & M) >> 17);
+    }
+}
+uint64_t lrand48_advance(uint64_t x, uint64_t k) {
+    const uint64_t M = (1ull << 48) - 1;
+    uint64_t A = 1, C = 0, ba = 0x5DEECE66DULL, bc = 0xBULL;
+    while (k) {
+        if (k & 1) { A = (A * ba) & M; C = (C * ba + bc) & M; }
+        bc = (bc * ba + bc) & M; ba = (ba * ba) & M;
+        k >>= 1;
+    }
+    return (A * x + C) & M;
+}
+
+// NUCLSEQ datum images -> what mem_align1 sees after to_text_palloc + nst_nt4_table (bwa.cpp:146-149): codes 0..3 from the packed
+// bases, 4 wherever a hole (an ambiguous letter) covers the base.  Pass 1: lengths; pass 2 (after the scan): one warp per read.
+// stats[0] = longest read, stats[1] = index + 1 of a truncated / oversized image (0 = all fine)
+__global__ void k_datum_lens(const uint8_t* bytes, const uint64_t* doff, uint64_t base, uint64_t n, uint64_t* lens, uint32_t* stats) {
+    uint32_t mx = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint8_t* d = bytes + (doff[i] - base);
+        uint32_t hdr[3]; memcpy(hdr, d, 12);
+        const uint64_t need = 12 + (uint64_t)hdr[1] * 16 + ((uint64_t)hdr[2] + 3) / 4;
+        if ((hdr[0] >> 2) < need || doff[i + 1] < doff[i] + need || hdr[2] > 0x3fffffffu) { atomicMax(stats + 1, (uint32_t)(i + 1)); hdr[2] = 0; }
+        lens[i] = hdr[2];
+        mx = mx > hdr[2] ? mx : hdr[2];
+    }
+    mx = __reduce_max_sync(FULL, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(stats, mx);
+    if (blockIdx.x == 0 && threadIdx.x == 0) lens[n] = 0;
+}
+__global__ void k_datum_unpack(const uint8_t* bytes, const uint64_t* doff, uint64_t base, uint64_t n, const uint64_t* offs, uint8_t* seqs) {
+    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t r = gw; r < n; r += nw) {
+        const uint8_t* d = bytes + (doff[r] - base);
+        uint32_t n_holes, len; memcpy(&n_holes, d + 4, 4); memcpy(&len, d + 8, 4);
+        const uint8_t* pac = d + 12 + (size_t)n_holes * 16;
+        uint8_t* q = seqs + offs[r];
+        for (uint32_t i = lane; i < len; i += 32) q[i] = (pac[i >> 2] >> ((~i & 3u) << 1)) & 3u;
+        __syncwarp();
+        for (uint32_t k = 0; k < n_holes; ++k) {
+            int64_t ho; int32_t hl; memcpy(&ho, d + 12 + (size_t)k * 16, 8); memcpy(&hl, d + 12 + (size_t)k * 16 + 8, 4);
+            for (int64_t i = ho + lane; i < ho + hl && i < (int64_t)len; i += 32) if (i >= 0) q[i] = 4;
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void k_rebase_offs(uint64_t* offs, uint64_t n, uint64_t base) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) offs[i] -= base;
 }
@@ -463,7 +534,7 @@ __global__ void k_to_nt4(uint8_t* s, uint64_t n) {
 // (alignment length l and sub_n + 1): both come from a table filled by the HOST libm, so every double
 // operation here is an IEEE +,-,*,/ evaluated in the reference's order (the library is compiled with
 // --fmad=false).  Rows whose l or sub_n fall outside the table get mapq = -1 and are finished on the host.
-constexpr int LOGTAB_N = 4096;
+constexpr int LOGTAB_N = 65536;   // alignments of up to 65535 bases get their MAPQ on the device
 struct MapqParams { int a, b, min_seed_len; float coef_len; double coef_fac; const double* logtab; };
 
 __device__ __forceinline__ int approx_mapq_dev(const MapqParams& M, const RowDev& r) {
@@ -486,25 +557,32 @@ __device__ __forceinline__ int approx_mapq_dev(const MapqParams& M, const RowDev
     return mapq;
 }
 
+constexpr int MAPQ_HOST = 255;   // mapq value of a row whose MAPQ the host finishes (l or sub_n outside the device log table)
 __global__ void k_compact_rows(const ReadBlock* blocks, const RowDev* rows, const uint32_t* row_cnt, const uint32_t* row_off, uint32_t n_reads,
-                               RowDev* out, uint32_t out_cap, MapqParams M, uint32_t* host_mapq) {
-    // one warp per read; a row is 120 bytes = 30 words.  *host_mapq is raised when a row's MAPQ has to be finished on the host.  Rows
-    // beyond out_cap are dropped: the host sees the total from the scan, grows the buffer and runs the batch again.
+                               RowPub* out, RowExt* ext, uint32_t out_cap, MapqParams M, uint32_t* host_mapq) {
+    // thread per row slot of a read: the 120-byte working record becomes the 64-byte public row (+ the 48-byte extension when asked
+    // for).  *host_mapq is raised when a row's MAPQ has to be finished on the host.  Rows beyond out_cap are dropped: the host sees
+    // the total from the scan, grows the buffer and runs the batch again.
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     for (uint32_t r = gw; r < n_reads; r += nw) {
-        uint32_t c = row_cnt[r];
+        const uint32_t c = row_cnt[r];
         if (!c || row_off[r] + c > out_cap) continue;
         const RowDev* srow = rows + blocks[r].base;
-        RowDev* drow = out + row_off[r];
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(srow);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(drow);
-        for (uint32_t w = lane; w < c * 30; w += 32) dst[w] = src[w];
-        __syncwarp();
         for (uint32_t k = lane; k < c; k += 32) {
-            const int mq = srow[k].secondary < 0 ? approx_mapq_dev(M, srow[k]) : 0;
-            drow[k].mapq = mq;
+            const RowDev a = srow[k];
+            const int mq = a.secondary < 0 ? approx_mapq_dev(M, a) : 0;
             if (mq < 0) atomicExch(host_mapq, 1u);
+            RowPub d;
+            d.rb = a.rb; d.re = a.re; d.pos = a.pos; d.ref_id = a.ref_id; d.qb = a.qb; d.qe = a.qe; d.rid = a.rid; d.score = a.score; d.NM = a.NM;
+            d.cigar_off = a.cigar_off; d.n_cigar = a.n_cigar; d.flag = (uint16_t)a.flag; d.mapq = (uint8_t)(mq < 0 ? MAPQ_HOST : mq); d.is_rev = (uint8_t)a.is_rev;
+            out[row_off[r] + k] = d;
+            if (ext) {
+                RowExt e;
+                e.hash = a.hash; e.truesc = a.truesc; e.sub = a.sub; e.csub = a.csub; e.sub_n = a.sub_n; e.w = a.w; e.seedcov = a.seedcov;
+                e.secondary = a.secondary; e.seedlen0 = a.seedlen0; e.n_comp = a.n_comp; e.frac_rep = a.frac_rep;
+                ext[row_off[r] + k] = e;
+            }
         }
     }
 }
@@ -523,7 +601,7 @@ uint32_t rseq_cap_for(const bsq_index* h, uint32_t max_len) { return max_len + 4
 // reads longer than this would need mem_flt_chained_seeds' local SW (runs when 5.5 ln L <= 0.05 L)
 bool needs_seed_sw(uint32_t len) { return len > 0 && 5.5f * log((double)len) <= 0.05f * (double)len; }
 
-int upload_reads(bsq_index* h, Batch& b, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n) {
+int upload_reads(bsq_index* h, Batch& b, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, uint64_t id_first = 0) {
     b.resident = false; b.aligned = false;
     if (n >= 0x7fffffffull) { bsq_set_error("batch too large"); return BSQ_ERR; }
     uint32_t max_len = 0;
@@ -550,11 +628,57 @@ int upload_reads(bsq_index* h, Batch& b, const char* seqs, const uint64_t* offs,
     if (total) CUDA_CHECK(cudaMemcpyAsync(b.seqs.p, seqs + offs[0], total, cudaMemcpyHostToDevice, b.st));
     if (n) {
         CUDA_CHECK(cudaMemcpyAsync(b.offs.p, offs, (n + 1) * 8, cudaMemcpyHostToDevice, b.st));
-        CUDA_CHECK(cudaMemcpyAsync(b.ids.p, ids, n * 8, cudaMemcpyHostToDevice, b.st));
+        if (ids) CUDA_CHECK(cudaMemcpyAsync(b.ids.p, ids, n * 8, cudaMemcpyHostToDevice, b.st));
+        else { k_lrand48_ids<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8), 256, 0, b.st>>>(h->lrand_state, id_first, n, b.ids.p); ++h->timing.launches; }
     } else CUDA_CHECK(cudaMemsetAsync(b.offs.p, 0, 8, b.st));
     if (total) { k_to_nt4<<<(unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 16), 256, 0, b.st>>>(b.seqs.p, total); ++h->timing.launches; }
     if (n && offs[0]) { k_rebase_offs<<<(unsigned)std::min<uint64_t>((n + 256) / 256, 148 * 8), 256, 0, b.st>>>(b.offs.p, n + 1, offs[0]); ++h->timing.launches; }
-    h->timing.h2d_bytes += total + (n + 1) * 8 + n * 8;
+    h->timing.h2d_bytes += total + (n + 1) * 8 + (ids ? n * 8 : 0);
+    b.resident = true;
+    return BSQ_OK;
+}
+
+// The same batch handed over as NUCLSEQ datum images (image i at bytes + doff[i], as PostgreSQL stores the query rows): 2 bits per
+// base on the wire instead of 8.  The host reads the headers once (longest read, total bases: the pools are sized from them); the
+// images are unpacked on the device.
+int upload_datums(bsq_index* h, Batch& b, const uint8_t* bytes, const uint64_t* doff, const int64_t* ids, uint64_t n, uint64_t id_first = 0) {
+    b.resident = false; b.aligned = false;
+    if (n >= 0x7fffffffull) { bsq_set_error("batch too large"); return BSQ_ERR; }
+    if (n && doff[n] < doff[0]) { bsq_set_error("datum offsets must be non-decreasing"); return BSQ_ERR; }
+    const uint64_t nbytes = n ? doff[n] - doff[0] : 0;
+    b.n = n; b.max_len = 0; b.total_bases = 0;
+    CUDA_CHECK(b.offs.ensure(n + 2)); CUDA_CHECK(b.ids.ensure(n + 1)); CUDA_CHECK(b.ctl.ensure(64));
+    CUDA_CHECK(b.datums.ensure(nbytes + 64)); CUDA_CHECK(b.datum_off.ensure(n + 1)); CUDA_CHECK(b.scan_tmp64.ensure(prim::scan_tmp_elems(n + 1) + 16));
+    if (!b.ctl_host) CUDA_CHECK(cudaHostAlloc(&b.ctl_host, 16 * 4, cudaHostAllocDefault));
+    uint64_t total = 0; uint32_t max_len = 0;
+    if (n) {
+        // images, their offsets and the ids go down as they are; the headers are read ON THE DEVICE (longest read, total bases, validity:
+        // four bytes come back) -- walking a million headers in host memory costs more than the whole copy
+        CUDA_CHECK(cudaMemcpyAsync(b.datums.p, bytes + doff[0], nbytes, cudaMemcpyHostToDevice, b.st));
+        CUDA_CHECK(cudaMemcpyAsync(b.datum_off.p, doff, (n + 1) * 8, cudaMemcpyHostToDevice, b.st));
+        if (ids) CUDA_CHECK(cudaMemcpyAsync(b.ids.p, ids, n * 8, cudaMemcpyHostToDevice, b.st));
+        else { k_lrand48_ids<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8), 256, 0, b.st>>>(h->lrand_state, id_first, n, b.ids.p); ++h->timing.launches; }
+        CUDA_CHECK(cudaMemsetAsync(b.ctl.p + 61, 0, 8, b.st));
+        k_datum_lens<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8), 256, 0, b.st>>>(b.datums.p, b.datum_off.p, doff[0], n, b.offs.p, b.ctl.p + 61); ++h->timing.launches;
+        prim::device_scan<uint64_t, prim::OpSum, false>(b.offs.p, b.offs.p, n + 1, b.scan_tmp64.p, prim::OpSum(), b.st, &h->timing.launches);
+        CUDA_CHECK(cudaMemcpyAsync(b.ctl_host + 12, b.ctl.p + 61, 8, cudaMemcpyDeviceToHost, b.st));
+        CUDA_CHECK(cudaMemcpyAsync(b.ctl_host + 14, b.offs.p + n, 8, cudaMemcpyDeviceToHost, b.st));
+        CUDA_CHECK(cudaStreamSynchronize(b.st));
+        if (b.ctl_host[13]) { bsq_set_error("datum %u is truncated or longer than a read may be", b.ctl_host[13] - 1); return BSQ_ERR; }
+        max_len = b.ctl_host[12]; memcpy(&total, b.ctl_host + 14, 8);
+    } else CUDA_CHECK(cudaMemsetAsync(b.offs.p, 0, 8, b.st));
+    b.max_len = max_len; b.total_bases = total;
+    if (needs_seed_sw(max_len) && b.read_logtab_n < max_len + 1) {
+        std::vector<double> tab(max_len + 1);
+        tab[0] = 0.;
+        for (uint32_t i = 1; i <= max_len; ++i) tab[i] = log((double)i);
+        CUDA_CHECK(b.read_logtab.ensure(max_len + 1));
+        CUDA_CHECK(cudaMemcpy(b.read_logtab.p, tab.data(), (max_len + 1) * sizeof(double), cudaMemcpyHostToDevice));
+        b.read_logtab_n = max_len + 1;
+    }
+    CUDA_CHECK(b.seqs.ensure(total + 64));
+    if (n) { k_datum_unpack<<<(unsigned)std::min<uint64_t>((n + 7) / 8, 148 * 16), 256, 0, b.st>>>(b.datums.p, b.datum_off.p, doff[0], n, b.offs.p, b.seqs.p); ++h->timing.launches; }
+    h->timing.h2d_bytes += nbytes + (n + 1) * 8 + (ids ? n * 8 : 0);
     b.resident = true;
     return BSQ_OK;
 }
@@ -716,9 +840,11 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
         }
         b.rows_cap = std::max<uint64_t>(b.rows_cap, (uint64_t)n * 2 + 4096);
         ENS(b.rows_compact.ensure(b.rows_cap));
+        // the extension records are always produced on the device: a row the host must finish (MAPQ outside the log table) needs them
+        ENS(b.rows_ext.ensure(b.rows_cap));
         MapqParams M; M.a = h->opts.a; M.b = h->opts.b; M.min_seed_len = h->opts.min_seed_len; M.coef_len = h->mapQ_coef_len;
         M.coef_fac = (double)h->mapQ_coef_fac; M.logtab = h->d_logtab;
-        k_compact_rows<<<148 * 8, 256, 0, st>>>(b.blocks.p, b.rows.p, b.row_cnt.p, b.row_off.p, n, b.rows_compact.p,
+        k_compact_rows<<<148 * 8, 256, 0, st>>>(b.blocks.p, b.rows.p, b.row_cnt.p, b.row_off.p, n, b.rows_compact.p, b.rows_ext.p,
                                                 (uint32_t)std::min<uint64_t>(b.rows_cap, 0xffffffffull), M, b.ctl.p + 30); ++T.launches;
     }
     cudaEventRecord(ev[4], st);
@@ -798,11 +924,11 @@ int run_pipeline(bsq_index* h, Batch& b) {
 }
 
 // mem_approx_mapq_se on the host: double math with libm log
-int approx_mapq(const bsq_index* h, const bsq_row& a) {
+int approx_mapq(const bsq_index* h, const bsq_row& a, const bsq_row_ext& x) {
     const bsq_opts& o = h->opts;
-    int mapq, l, sub = a.sub ? a.sub : o.min_seed_len * o.a;
+    int mapq, l, sub = x.sub ? x.sub : o.min_seed_len * o.a;
     double identity;
-    sub = a.csub > sub ? a.csub : sub;
+    sub = x.csub > sub ? x.csub : sub;
     if (sub >= a.score) return 0;
     l = a.qe - a.qb > a.re - a.rb ? a.qe - a.qb : (int)(a.re - a.rb);
     identity = 1. - (double)(l * o.a - a.score) / (o.a + o.b) / l;
@@ -813,17 +939,17 @@ int approx_mapq(const bsq_index* h, const bsq_row& a) {
         tmp *= identity * identity;
         mapq = (int)(6.02 * (a.score - sub) / o.a * tmp * tmp + .499);
     }
-    if (a.sub_n > 0) mapq -= (int)(4.343 * log(a.sub_n + 1) + .499);
+    if (x.sub_n > 0) mapq -= (int)(4.343 * log(x.sub_n + 1) + .499);
     if (mapq > 60) mapq = 60;
     if (mapq < 0) mapq = 0;
-    mapq = (int)(mapq * (1. - a.frac_rep) + .499);
+    mapq = (int)(mapq * (1. - x.frac_rep) + .499);
     return mapq;
 }
 
 // A result lives in ONE pinned host block, laid out by capacity: row_off (u64 x (n+1)) | rows (row_cap + 1) |
 // cigar (cig_cap + 1) | the device's u32 row offsets (n + 1).  Freed blocks are cached process-wide so that
 // steady-state calls do not pay cudaHostAlloc.
-struct ResultImpl { bsq_result pub; void* block; size_t bytes; uint64_t row_cap, cig_cap; uint32_t* o32; };
+struct ResultImpl { bsq_result pub; void* block; size_t bytes; uint64_t row_cap, cig_cap; uint32_t* o32; bsq_row_ext* ext; };
 struct PinnedCache { void* ptr[4]; size_t bytes[4]; };
 PinnedCache g_pinned = {{nullptr, nullptr, nullptr, nullptr}, {0, 0, 0, 0}};
 std::mutex g_pinned_mu;
@@ -850,11 +976,14 @@ void pinned_put(void* p, size_t bytes) {
     cudaFreeHost(p);
 }
 
-ResultImpl* result_new(uint64_t n, uint64_t row_cap, uint64_t cig_cap) {
+// layout by capacity: row_off (u64 x (n+1)) | rows (row_cap + 1) | cigar (cig_cap + 1) | the device's u32 row offsets (n + 1) |
+// extension rows (row_cap + 1; only with BSQ_FLAG_ROWS_EXT or when a row's MAPQ was finished on the host)
+ResultImpl* result_new(uint64_t n, uint64_t row_cap, uint64_t cig_cap, bool with_ext) {
     const size_t off_rows = ((n + 1) * 8 + 63) & ~(size_t)63;
     const size_t off_cig = (off_rows + (row_cap + 1) * sizeof(bsq_row) + 63) & ~(size_t)63;
     const size_t off_o32 = (off_cig + (cig_cap + 1) * 4 + 63) & ~(size_t)63;
-    const size_t need = off_o32 + (n + 1) * 4;
+    const size_t off_ext = (off_o32 + (n + 1) * 4 + 63) & ~(size_t)63;
+    const size_t need = off_ext + (with_ext ? (row_cap + 1) * sizeof(bsq_row_ext) : 0);
     size_t got = 0;
     void* block = pinned_get(need, &got);
     if (!block) { bsq_set_error("cannot allocate %zu bytes of pinned host memory for the result", need); return nullptr; }
@@ -866,6 +995,8 @@ ResultImpl* result_new(uint64_t n, uint64_t row_cap, uint64_t cig_cap) {
     R->pub.cigar = reinterpret_cast<uint32_t*>(static_cast<char*>(block) + off_cig);
     R->pub.n_cigar_words = 0;
     R->o32 = reinterpret_cast<uint32_t*>(static_cast<char*>(block) + off_o32);
+    R->ext = with_ext ? reinterpret_cast<bsq_row_ext*>(static_cast<char*>(block) + off_ext) : nullptr;
+    R->pub.rows_ext = R->ext;
     return R;
 }
 
@@ -881,30 +1012,39 @@ int download_enqueue(bsq_index* h, Batch& b, ResultImpl* R, uint64_t read_base, 
     cudaStream_t st = b.st;
     CUDA_CHECK(cudaMemcpyAsync(R->o32 + read_base, b.row_off.p, n * 4, cudaMemcpyDeviceToHost, st));
     if (total_rows) CUDA_CHECK(cudaMemcpyAsync(R->pub.rows + row_base, b.rows_compact.p, total_rows * sizeof(bsq_row), cudaMemcpyDeviceToHost, st));
+    if (total_rows && R->ext) CUDA_CHECK(cudaMemcpyAsync(R->ext + row_base, b.rows_ext.p, total_rows * sizeof(bsq_row_ext), cudaMemcpyDeviceToHost, st));
+    else if (total_rows && b.ctl_host[10]) {   // rare: a MAPQ to finish on the host although the caller did not ask for the extension records
+        b.ext_tmp.resize(total_rows);
+        CUDA_CHECK(cudaMemcpyAsync(b.ext_tmp.data(), b.rows_ext.p, total_rows * sizeof(bsq_row_ext), cudaMemcpyDeviceToHost, st));
+    }
     if (cig_top) CUDA_CHECK(cudaMemcpyAsync(R->pub.cigar + cig_base, b.cigar.p, (size_t)cig_top * 4, cudaMemcpyDeviceToHost, st));
-    h->timing.d2h_bytes += n * 4 + 12 + total_rows * sizeof(bsq_row) + (uint64_t)cig_top * 4;
+    h->timing.d2h_bytes += n * 4 + 12 + total_rows * (sizeof(bsq_row) + (R->ext ? sizeof(bsq_row_ext) : 0)) + (uint64_t)cig_top * 4;
     return BSQ_OK;
 }
 
 // after the copies have landed: 64-bit row offsets, and MAPQ of the rows outside the device log table (very long
 // alignments).  n reads starting at read_base, n_rows rows starting at row_base.
-void download_finish(bsq_index* h, ResultImpl* R, uint64_t n, uint64_t read_base, uint64_t n_rows, uint64_t row_base, uint64_t cig_base, bool host_mapq) {
+void download_finish(bsq_index* h, ResultImpl* R, uint64_t n, uint64_t read_base, uint64_t n_rows, uint64_t row_base, uint64_t cig_base, bool host_mapq,
+                     const bsq_row_ext* ext_tmp) {
     if (!h->meta.built) { for (uint64_t i = 0; i < n; ++i) R->pub.row_off[read_base + i] = row_base; return; }
     for (uint64_t i = 0; i < n; ++i) R->pub.row_off[read_base + i] = row_base + R->o32[read_base + i];
     if (cig_base)   // the batch is one chunk of a larger result: its CIGAR words follow the earlier chunks'
         for (uint64_t i = row_base; i < row_base + n_rows; ++i) if (R->pub.rows[i].n_cigar) R->pub.rows[i].cigar_off += (uint32_t)cig_base;
-    if (n_rows && host_mapq)
-        for (uint64_t i = row_base; i < row_base + n_rows; ++i)
-            if (R->pub.rows[i].mapq < 0) R->pub.rows[i].mapq = approx_mapq(h, R->pub.rows[i]);
+    if (n_rows && host_mapq) {
+        // alignments longer than the device's log table: mem_approx_mapq_se with libm on the host, from the extension records
+        const bsq_row_ext* ext = R->ext ? R->ext + row_base : ext_tmp;
+        for (uint64_t i = 0; i < n_rows && ext; ++i)
+            if (R->pub.rows[row_base + i].mapq == MAPQ_HOST) R->pub.rows[row_base + i].mapq = (uint8_t)approx_mapq(h, R->pub.rows[row_base + i], ext[i]);
+    }
 }
 
 int download_result(bsq_index* h, Batch& b, bsq_result** out) {
     if (!b.aligned) { bsq_set_error("no aligned batch to download"); return BSQ_ERR; }
     h->timing.d2h_bytes = 0;
-    ResultImpl* R = result_new(b.n, b.out_rows, b.out_cig);
+    ResultImpl* R = result_new(b.n, b.out_rows, b.out_cig, (h->flags & BSQ_FLAG_ROWS_EXT) != 0);
     if (!R) return BSQ_ERR;
     if (download_enqueue(h, b, R, 0, 0, 0) != BSQ_OK || cudaStreamSynchronize(b.st) != cudaSuccess) { result_delete(R); if (!*bsq_last_error()) bsq_set_error("download failed"); return BSQ_ERR; }
-    download_finish(h, R, b.n, 0, b.out_rows, 0, 0, b.ctl_host && b.ctl_host[10]);
+    download_finish(h, R, b.n, 0, b.out_rows, 0, 0, b.ctl_host && b.ctl_host[10], b.ext_tmp.data());
     R->pub.row_off[b.n] = b.out_rows;
     R->pub.n_cigar_words = b.out_cig;
     *out = &R->pub;
@@ -916,17 +1056,26 @@ int download_result(bsq_index* h, Batch& b, bsq_result** out) {
 // Chunk c's rows follow chunk c-1's in the result, so downloads are issued in chunk order; a lane takes chunk c+2 as
 // soon as chunk c's download has been queued (stream order protects the device buffers), and the host-side completion
 // of a download is deferred until the next chunk's work is in the queue.
-// chunk size: a quarter of the batch, within [64 K, 256 K] reads (measured on B200, 1 M x 150 bp: 64 K 66.7 ms,
-// 128 K 65.7, 256 K 64.5, 512 K 68.2, 32 K 78.8 per step).  BSQ_CHUNK_READS overrides it.
-constexpr uint64_t CHUNK_MIN = 1u << 16, CHUNK_MAX = 1u << 18;
+// chunk size: half of the batch, within [64 K, 1 M] reads.  Measured on B200, 1 M x 150 bp with the slim wire format (64 MB in, 77 MB
+// out): one pass 35.2 ms, 2 chunks 31.8, 4 chunks 35.9 (a chunk pays ~40 kernel tails and runs on half-empty persistent grids, so few
+// large chunks win once the copies are small).  BSQ_CHUNK_READS overrides it.
+constexpr uint64_t CHUNK_MIN = 1u << 16, CHUNK_MAX = 1u << 20;
 uint64_t chunk_reads(uint64_t n) {
     static long long env = -1;
     if (env < 0) { env = 0; if (const char* e = getenv("BSQ_CHUNK_READS")) { const long long x = atoll(e); if (x >= 1024) env = x; } }
     if (env > 0) return (uint64_t)env;
-    return std::min(std::max((n + 3) / 4, CHUNK_MIN), CHUNK_MAX);
+    const uint64_t k = std::max<uint64_t>(2, (n + CHUNK_MAX - 1) / CHUNK_MAX);     // as few chunks as the cap allows, at least two
+    return std::max((n + k - 1) / k, CHUNK_MIN);
 }
 
-int align_chunked(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, bsq_result** out, bool* fell_back) {
+// where a batch's reads come from: ASCII + offsets (bsq_align_batch) or NUCLSEQ datum images (bsq_align_batch_datums)
+struct ReadSrc { const char* seqs; const uint64_t* offs; const uint8_t* dbytes; const uint64_t* doff; const int64_t* ids; };
+int upload_src(bsq_index* h, Batch& b, const ReadSrc& S, uint64_t s0, uint64_t cnt) {
+    const int64_t* ids = S.ids ? S.ids + s0 : nullptr;
+    return S.dbytes ? upload_datums(h, b, S.dbytes, S.doff + s0, ids, cnt, s0) : upload_reads(h, b, S.seqs, S.offs + s0, ids, cnt, s0);
+}
+
+int align_chunked(bsq_index* h, const ReadSrc& S, uint64_t n, bsq_result** out, bool* fell_back) {
     *fell_back = false;
     if (!h->stream2) {
         CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
@@ -956,7 +1105,7 @@ int align_chunked(bsq_index* h, const char* seqs, const uint64_t* offs, const in
         const uint64_t s0 = start_of(c), cnt = start_of(c + 1) - s0;
         b.intv_cap = std::max(b.intv_cap, lane[(c & 1) ^ 1]->intv_cap);      // capacities learnt by one lane serve the other
         cudaEventRecord(b.ev_x[0], b.st);
-        if (upload_reads(h, b, seqs, offs + s0, ids + s0, cnt) != BSQ_OK) return BSQ_ERR;
+        if (upload_src(h, b, S, s0, cnt) != BSQ_OK) return BSQ_ERR;
         cudaEventRecord(b.ev_x[1], b.st);
         return pipeline_enqueue(h, b);
     };
@@ -967,7 +1116,7 @@ int align_chunked(bsq_index* h, const char* seqs, const uint64_t* offs, const in
         if (cudaEventSynchronize(b.ev_x[3]) != cudaSuccess) { bsq_set_error("result download failed: %s", cudaGetErrorString(cudaGetLastError())); return BSQ_ERR; }
         float ms;
         if (cudaEventElapsedTime(&ms, b.ev_x[2], b.ev_x[3]) == cudaSuccess) h->timing.d2h += ms;
-        download_finish(h, R, q.n, start_of(q.c), q.n_rows, q.row_base, q.cig_base, q.host_mapq);
+        download_finish(h, R, q.n, start_of(q.c), q.n_rows, q.row_base, q.cig_base, q.host_mapq, b.ext_tmp.data());
         return BSQ_OK;
     };
     uint64_t row_base = 0, cig_base = 0;
@@ -981,7 +1130,7 @@ int align_chunked(bsq_index* h, const char* seqs, const uint64_t* offs, const in
             // capacity of the result from the first chunk's yield
             // (BSQ_TEST_TIGHT_RESULT makes the estimate too small on purpose so that tests reach the one-plain-pass fallback)
             const double scale = (double)n / (double)b.n * (getenv("BSQ_TEST_TIGHT_RESULT") ? 0.4 : 1.2);
-            R = result_new(n, (uint64_t)(b.out_rows * scale) + (getenv("BSQ_TEST_TIGHT_RESULT") ? 16 : 65536), (uint64_t)(b.out_cig * scale) + (getenv("BSQ_TEST_TIGHT_RESULT") ? 16 : 65536));
+            R = result_new(n, (uint64_t)(b.out_rows * scale) + (getenv("BSQ_TEST_TIGHT_RESULT") ? 16 : 65536), (uint64_t)(b.out_cig * scale) + (getenv("BSQ_TEST_TIGHT_RESULT") ? 16 : 65536), (h->flags & BSQ_FLAG_ROWS_EXT) != 0);
             if (!R) { rc = BSQ_ERR; break; }
         }
         if (row_base + b.out_rows > R->row_cap || cig_base + b.out_cig > R->cig_cap) { *fell_back = true; break; }
@@ -1017,7 +1166,7 @@ extern "C" {
 
 int bsq_reads_upload(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n) {
     BSQ_ENTRY();
-    if (!h || (n && (!seqs || !offs || !ids))) { bsq_set_error("null argument"); return BSQ_ERR; }
+    if (!h || (n && (!seqs || !offs))) { bsq_set_error("null argument"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
     h->timing.launches = 0;
     h->timing.h2d_bytes = 0;
@@ -1041,23 +1190,21 @@ int bsq_result_download(bsq_index* h, bsq_result** out) {
     return download_result(h, h->batch, out);
 }
 
-int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, bsq_result** out) {
-    BSQ_ENTRY();
-    if (!h || !out || (n && (!seqs || !offs || !ids))) { bsq_set_error("null argument"); return BSQ_ERR; }
+static int align_batch_src(bsq_index* h, const ReadSrc& S, uint64_t n, bsq_result** out) {
     CUDA_CHECK(cudaSetDevice(h->device));
     cudaEvent_t e0, e1, e2, e3;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
     bsq_timing& T = h->timing;
     T.launches = 0; T.h2d_bytes = T.d2h_bytes = 0; T.h2d = T.d2h = 0; T.notes = 0;
     int rc = BSQ_OK;
-    bool chunked = n >= 2 * chunk_reads(n) && h->meta.built && !getenv("BSQ_NO_CHUNKS");
+    bool chunked = n >= 2 * CHUNK_MIN && n > chunk_reads(n) && h->meta.built && !getenv("BSQ_NO_CHUNKS");
     cudaEventRecord(e0, h->stream);
     if (chunked) {
         // two lanes, copies overlapped with compute; the stage times are sums over chunks of each lane's stream time
         T.seed = T.chain = T.extend = T.finalize = T.total = 0;
         memset(h->counters, 0, sizeof(h->counters));
         bool fell_back = false;
-        rc = align_chunked(h, seqs, offs, ids, n, out, &fell_back);
+        rc = align_chunked(h, S, n, out, &fell_back);
         if (fell_back) {   // the result outgrew the estimate: one plain pass; the call succeeds and says so in bsq_timing.notes
             T.notes |= BSQ_NOTE_CHUNK_FALLBACK;
             chunked = false; T.h2d_bytes = T.d2h_bytes = 0; T.h2d = T.d2h = 0;
@@ -1065,7 +1212,7 @@ int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const 
         else { cudaEventRecord(e3, h->stream); cudaEventSynchronize(e3); cudaEventElapsedTime(&T.total, e0, e3); }
     }
     if (!chunked) {
-        rc = upload_reads(h, h->batch, seqs, offs, ids, n);
+        rc = upload_src(h, h->batch, S, 0, n);
         cudaEventRecord(e1, h->stream);
         if (rc == BSQ_OK) rc = run_pipeline(h, h->batch);
         cudaEventRecord(e2, h->stream);
@@ -1075,7 +1222,29 @@ int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const 
         cudaEventElapsedTime(&T.h2d, e0, e1); cudaEventElapsedTime(&T.d2h, e2, e3); cudaEventElapsedTime(&T.total, e0, e3);
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    if (rc == BSQ_OK && !S.ids) h->lrand_state = lrand48_advance(h->lrand_state, n);   // the session's stream moved on by one draw per read
     return rc;
+}
+
+int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, bsq_result** out) {
+    BSQ_ENTRY();
+    if (!h || !out || (n && (!seqs || !offs))) { bsq_set_error("null argument"); return BSQ_ERR; }
+    const ReadSrc S{seqs, offs, nullptr, nullptr, ids};
+    return align_batch_src(h, S, n, out);
+}
+
+int bsq_align_batch_datums(bsq_index* h, const uint8_t* bytes, const uint64_t* off, const int64_t* ids, uint64_t n, bsq_result** out) {
+    BSQ_ENTRY();
+    if (!h || !out || (n && (!bytes || !off))) { bsq_set_error("null argument"); return BSQ_ERR; }
+    const ReadSrc S{nullptr, nullptr, bytes, off, ids};
+    return align_batch_src(h, S, n, out);
+}
+
+int bsq_session_lrand48(bsq_index* h, int set, uint64_t* state) {
+    BSQ_ENTRY();
+    if (!h || !state) { bsq_set_error("null argument"); return BSQ_ERR; }
+    if (set) h->lrand_state = *state & 0xFFFFFFFFFFFFULL; else *state = h->lrand_state;
+    return BSQ_OK;
 }
 
 // ---- row materialisation
@@ -1113,21 +1282,21 @@ int bsq_result_tuples(bsq_index* h, const bsq_result* res, const char* seqs, con
     std::vector<int64_t> maxend(holes.size());
     for (size_t i = 0; i < holes.size(); ++i) maxend[i] = i ? std::max(maxend[i - 1], holes[i].end) : holes[i].end;
     const uint64_t total = offs[n_reads] - offs[0];
-    RowDev* d_rows = nullptr; uint32_t *d_row_read = nullptr, *d_cigar = nullptr, *d_nholes = nullptr; uint8_t *d_seqs = nullptr, *d_bytes = nullptr;
+    RowPub* d_rows = nullptr; uint32_t *d_row_read = nullptr, *d_cigar = nullptr, *d_nholes = nullptr; uint8_t *d_seqs = nullptr, *d_bytes = nullptr;
     uint64_t *d_offs = nullptr, *d_off = nullptr, *d_tmp = nullptr; TupleHole* d_holes = nullptr; int64_t* d_maxend = nullptr; int32_t* d_rm = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int rc = BSQ_ERR;
     do {
 #define TC(x) if ((x) != cudaSuccess) { bsq_set_error("bsq_result_tuples: %s", cudaGetErrorString(cudaGetLastError())); break; }
         TC(cudaEventCreate(&e0)); TC(cudaEventCreate(&e1));
-        TC(cudaMalloc(&d_rows, n_rows * sizeof(RowDev))); TC(cudaMalloc(&d_row_read, n_rows * 4)); TC(cudaMalloc(&d_cigar, (res->n_cigar_words + 1) * 4));
+        TC(cudaMalloc(&d_rows, n_rows * sizeof(RowPub))); TC(cudaMalloc(&d_row_read, n_rows * 4)); TC(cudaMalloc(&d_cigar, (res->n_cigar_words + 1) * 4));
         TC(cudaMalloc(&d_seqs, total + 64)); TC(cudaMalloc(&d_offs, (n_reads + 1) * 8)); TC(cudaMalloc(&d_nholes, n_rows * 8));
         TC(cudaMalloc(&d_off, (3 * n_rows + 1) * 8)); TC(cudaMalloc(&d_tmp, tuple_scan_tmp_elems(n_rows) * 8)); TC(cudaMalloc(&d_rm, n_rows * 12));
         TC(cudaMalloc(&d_holes, (holes.size() + 1) * sizeof(TupleHole))); TC(cudaMalloc(&d_maxend, (holes.size() + 1) * 8));
         std::vector<uint64_t> rel(n_reads + 1);
         for (uint64_t i = 0; i <= n_reads; ++i) rel[i] = offs[i] - offs[0];
         cudaEventRecord(e0, st);
-        TC(cudaMemcpyAsync(d_rows, res->rows, n_rows * sizeof(RowDev), cudaMemcpyHostToDevice, st));
+        TC(cudaMemcpyAsync(d_rows, res->rows, n_rows * sizeof(RowPub), cudaMemcpyHostToDevice, st));
         TC(cudaMemcpyAsync(d_row_read, row_read.data(), n_rows * 4, cudaMemcpyHostToDevice, st));
         if (res->n_cigar_words) TC(cudaMemcpyAsync(d_cigar, res->cigar, res->n_cigar_words * 4, cudaMemcpyHostToDevice, st));
         if (total) TC(cudaMemcpyAsync(d_seqs, seqs + offs[0], total, cudaMemcpyHostToDevice, st));

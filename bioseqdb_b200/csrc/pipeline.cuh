@@ -69,7 +69,7 @@ constexpr int EXT_MEMO_BINS = 160;
 size_t extend_scratch_per_warp(uint32_t max_len, uint32_t rseq_cap);
 int extend_resident_warps();
 
-struct RowDev {  // device image of bsq_row (include/bioseqdb_gpu.h)
+struct RowDev {  // a row as the finalisation kernels build it (one record per region)
     int64_t rb, re, pos; uint64_t hash;
     int32_t qb, qe, rid, score, truesc, sub, csub, sub_n, w, seedcov, secondary, seedlen0, n_comp;
     float frac_rep;
@@ -77,7 +77,20 @@ struct RowDev {  // device image of bsq_row (include/bioseqdb_gpu.h)
     uint32_t cigar_off, n_cigar;
     int64_t ref_id;
 };
-static_assert(sizeof(RowDev) == 120, "RowDev must match bsq_row");
+static_assert(sizeof(RowDev) == 120, "RowDev layout");
+struct RowPub {  // device image of bsq_row (include/bioseqdb_gpu.h): rows in read order, as they leave the device
+    int64_t rb, re, pos, ref_id;
+    int32_t qb, qe, rid, score, NM;
+    uint32_t cigar_off, n_cigar;
+    uint16_t flag; uint8_t mapq, is_rev;
+};
+static_assert(sizeof(RowPub) == 64, "RowPub must match bsq_row");
+struct RowExt {  // device image of bsq_row_ext
+    uint64_t hash;
+    int32_t truesc, sub, csub, sub_n, w, seedcov, secondary, seedlen0, n_comp;
+    float frac_rep;
+};
+static_assert(sizeof(RowExt) == 48, "RowExt must match bsq_row_ext");
 
 struct FinalizeParams {
     const uint8_t* seqs; const uint64_t* offs; const int64_t* ids; uint32_t n_reads;

@@ -76,7 +76,7 @@ __device__ __forceinline__ int dec_digits(uint32_t v) { int d = 1; while (v >= 1
 
 // The reference interval of a row.  Reference behaviour: [rb, re) of the doubled coordinate as it is.  With the reverse-strand
 // fix-up a hit on the reverse strand becomes the forward-strand interval it covers, [2 l_pac - re, 2 l_pac - rb).
-__device__ __forceinline__ RowDev row_for_text(const TupleParams& P, RowDev a) {
+__device__ __forceinline__ RowPub row_for_text(const TupleParams& P, RowPub a) {
     if (P.fix_reverse && a.rb >= P.l_pac) { const int64_t b = (P.l_pac << 1) - a.re, e = (P.l_pac << 1) - a.rb; a.rb = b; a.re = e; }
     return a;
 }
@@ -85,7 +85,7 @@ __device__ __forceinline__ RowDev row_for_text(const TupleParams& P, RowDev a) {
 __global__ void __launch_bounds__(TUP_THREADS) k_tuple_sizes(TupleParams P) {
     const uint64_t row = (uint64_t)blockIdx.x * TUP_THREADS + threadIdx.x;
     if (row >= P.n_rows) return;
-    const RowDev a = row_for_text(P, P.rows[row]);
+    const RowPub a = row_for_text(P, P.rows[row]);
     const int64_t rlen = a.re > a.rb ? a.re - a.rb : 0;
     const bool overlay = range_has_holes(P, a.rb, a.re);
     uint32_t nh_ref = 0;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(TUP_THREADS) k_tuple_fill(TupleParams P) {
     const uint64_t t = (uint64_t)blockIdx.x * TUP_THREADS + threadIdx.x;
     if (t >= 3 * P.n_rows) return;
     const uint64_t row = t / 3; const int col = (int)(t - row * 3);
-    const RowDev a = row_for_text(P, P.rows[row]);
+    const RowPub a = row_for_text(P, P.rows[row]);
     uint8_t* dst = P.bytes + P.off[t];
     if (col == 0) {
         const uint32_t nh = P.nholes[2 * row];

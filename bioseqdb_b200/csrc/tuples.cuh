@@ -7,7 +7,7 @@
 struct TupleHole { int64_t offset, end; uint32_t idx; int32_t amb; };   // a hole of the index: [offset, end), position in the hole list, letter
 
 struct TupleParams {
-    const RowDev* rows; uint64_t n_rows;
+    const RowPub* rows; uint64_t n_rows;
     const uint32_t* row_read;      // read index of every row
     const uint32_t* cigar;         // the result's CIGAR words
     const uint8_t* seqs;           // the reads as ASCII (the text BwaIndex::align_sequence works on), offs[n_reads + 1]

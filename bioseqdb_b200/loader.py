@@ -69,6 +69,25 @@ def fasta_batches(lines, batch_bases: int = 1 << 30):
         yield batch
 
 
+def nuclseq_image_block(cat: np.ndarray, offs: np.ndarray, device: int = 0):
+    """n sequences (concatenated upper-case text `cat`, offs[n + 1]) -> (bytes, off[n + 1], device_ms): the datum images back to back as
+    the library wrote them (8-byte aligned; the true size of an image is in its length word), ready for bsq_align_batch_datums /
+    bsq_index_add_ref_datums.  off[n] = total bytes."""
+    L = _lib.lib()
+    cat = np.ascontiguousarray(cat, dtype=np.uint8)
+    offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    n = len(offs) - 1
+    res = C.POINTER(BsqNuclseqs)()
+    check(L.bsq_nuclseq_from_text_batch(device, ptr(cat if len(cat) else np.zeros(1, dtype=np.uint8)), ptr(offs), n, C.byref(res)))
+    r = res.contents
+    off = np.ctypeslib.as_array(r.off, shape=(n + 1,)).copy()
+    nb = int(r.n_bytes)
+    data = np.ctypeslib.as_array(r.bytes, shape=(max(nb, 1),))[:nb].copy()
+    ms = float(r.device_ms)
+    L.bsq_nuclseqs_free(res)
+    return data, off, ms
+
+
 def nuclseq_images(texts, device: int = 0):
     """texts: list of bytes. Returns (list of datum images, device_ms). Raises BsqError like nuclseq_in on an invalid letter."""
     L = _lib.lib()

@@ -37,16 +37,25 @@ typedef struct bsq_opts {
 /* == bntamb1_t (16 bytes), the hole record inside a NUCLSEQ datum (bioseqdb/sequence.h:13-14) */
 typedef struct bsq_hole { int64_t offset; int32_t len; char amb; } bsq_hole;
 
-/* One output row = one mem_alnreg_t plus the mem_aln_t fields of its mem_reg2aln (bwa.cpp:151-177).
- * rb/re are positions in the doubled (forward+reverse) coordinate; pos is row-relative forward. */
+/* One output row (64 bytes) = what BwaMatch is built from (bwa.cpp:151-177: rb, re, qb, qe, rid of the mem_alnreg_t; flag, is_rev, cigar,
+ * score of its mem_aln_t) plus MAPQ and NM, which the path computes and the reference never exports (bwa.cpp:158).  rb/re are
+ * positions in the doubled (forward+reverse) coordinate; pos is row-relative forward. */
 typedef struct bsq_row {
-    int64_t rb, re, pos; uint64_t hash;
-    int32_t qb, qe, rid, score, truesc, sub, csub, sub_n, w, seedcov, secondary, seedlen0, n_comp;
-    float frac_rep;
-    int32_t is_rev, mapq, NM, flag;
-    uint32_t cigar_off, n_cigar; /* bwa cigar words (len<<4|op, op: M0 I1 D2 S3) in bsq_result.cigar */
+    int64_t rb, re, pos;
     int64_t ref_id;              /* the id column of the reference row (bwa.cpp:160) */
+    int32_t qb, qe, rid, score;
+    int32_t NM;
+    uint32_t cigar_off, n_cigar; /* bwa cigar words (len<<4|op, op: M0 I1 D2 S3) in bsq_result.cigar */
+    uint16_t flag;               /* 0x100 = secondary */
+    uint8_t mapq, is_rev;
 } bsq_row;
+/* The remaining mem_alnreg_t fields of a row (48 bytes): only the parity tests and debugging read them, so they travel only when
+ * the index carries BSQ_FLAG_ROWS_EXT (bsq_index_set_flags); bsq_result.rows_ext is NULL otherwise. */
+typedef struct bsq_row_ext {
+    uint64_t hash;
+    int32_t truesc, sub, csub, sub_n, w, seedcov, secondary, seedlen0, n_comp;
+    float frac_rep;
+} bsq_row_ext;
 
 typedef struct bsq_result {
     uint64_t n_reads;
@@ -54,6 +63,7 @@ typedef struct bsq_result {
     bsq_row* rows;     /* row_off[n_reads] rows, per read in reference order (score desc, hash) */
     uint32_t* cigar;
     uint64_t n_cigar_words;
+    bsq_row_ext* rows_ext; /* parallel to rows, or NULL */
 } bsq_result;
 
 /* per-stage device timings of the last bsq_align_batch / bsq_align_resident call, milliseconds */
@@ -73,6 +83,8 @@ int bsq_device_count(void);
 void bsq_opts_init(bsq_opts* o);
 bsq_index* bsq_index_new(const bsq_opts* o, int device);
 int bsq_index_set_opts(bsq_index* h, const bsq_opts* o);
+#define BSQ_FLAG_ROWS_EXT 1u   /* results also carry bsq_row_ext records */
+int bsq_index_set_flags(bsq_index* h, uint32_t flags);
 int bsq_index_add_ref(bsq_index* h, int64_t id, const uint8_t* pac, uint32_t len, const bsq_hole* holes, uint32_t n_holes);
 /* n reference rows in one call: NUCLSEQ datum images as PostgreSQL stores them (sequence.h:18-38), image i at bytes + off[i] --
  * what iterate_nuclseq_table (extension.cpp:157-195) holds after detoasting each row; same semantics as n calls of bsq_index_add_ref */
@@ -83,6 +95,13 @@ void bsq_index_free(bsq_index* h);
 /* reads: concatenated ASCII (what BwaIndex::align_sequence hands to mem_align1 after to_text_palloc,
  * bwa.cpp:146-149), offs[n+1], ids[n] = the values lrand48() would have returned. */
 int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, bsq_result** out);
+/* The same call with the reads as they sit in the database: n NUCLSEQ datum images (sequence.h:18-38), image i at bytes + off[i],
+ * off[n + 1] -- what iterate_nuclseq_table holds for every query row (extension.cpp:362) BEFORE to_text_palloc expands it to one
+ * byte per base.  2 bits per base cross the bus; the images are unpacked (holes -> ambiguous code 4) on the device.
+ * In both calls ids may be NULL: the library then draws the ids itself, continuing the session's lrand48 stream kept in the handle
+ * (one draw per read in call order, starting from glibc's fresh-process state; bsq_session_lrand48 reads / sets it). */
+int bsq_align_batch_datums(bsq_index* h, const uint8_t* bytes, const uint64_t* off, const int64_t* ids, uint64_t n, bsq_result** out);
+int bsq_session_lrand48(bsq_index* h, int set, uint64_t* state);
 void bsq_result_free(bsq_result* r);
 int bsq_last_timing(const bsq_index* h, bsq_timing* t);
 

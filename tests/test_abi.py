@@ -23,7 +23,8 @@ def test_header_symbols_exported():
 
 def test_struct_layouts():
     import ctypes as C
-    assert _lib.ROW_DTYPE.itemsize == 120
+    assert _lib.ROW_DTYPE.itemsize == 120 and _lib.PUB_ROW_DTYPE.itemsize == 64 and _lib.EXT_ROW_DTYPE.itemsize == 48
+    assert C.sizeof(_lib.BsqResult) == 48
     assert C.sizeof(_lib.BsqOpts) == 48
     assert _lib.HOLE_DTYPE.itemsize == 16
 

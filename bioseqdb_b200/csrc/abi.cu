@@ -772,11 +772,11 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
         const size_t jobs2 = (size_t)n * EXT_MEMO_CHAINS * 2;
         ENS(b.ext_memo.ensure(jobs2)); ENS(b.ext_memo_key.ensure(jobs2)); ENS(b.ext_memo_perm.ensure(jobs2));
         ENS(b.ext_memo_hist.ensure(6 * EXT_MEMO_BINS)); ENS(b.ext_todo.ensure(n));
-        if (!b.ext_aux_ok) {
-            for (auto& s_ : b.ext_aux.st) ENS(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
-            for (auto& e : b.ext_aux.ev) ENS(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            b.ext_aux_ok = true;
-        }
+    }
+    if (!b.ext_aux_ok && !small_batch) {
+        for (auto& s_ : b.ext_aux.st) ENS(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
+        for (auto& e : b.ext_aux.ev) ENS(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        b.ext_aux_ok = true;
     }
     ENS(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, st));
     unsigned long long* ctr = h->collect_counters ? reinterpret_cast<unsigned long long*>(b.ctl.p + 8) : nullptr;
@@ -826,7 +826,7 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
         P.ticket = b.ctl.p + 40; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 6 : nullptr;
         static const bool no_thread_fin = getenv("BSQ_NO_FIN_THREAD") != nullptr;
         P.todo = (no_thread_fin || small_batch) ? nullptr : b.fin_todo.p; P.todo_cnt = b.ctl.p + 58;
-        launch_finalize(P, ix, o, st, rseq_cap, fin_warps, &T.launches);
+        launch_finalize(P, ix, o, st, rseq_cap, fin_warps, &T.launches, b.ext_aux_ok ? &b.ext_aux : nullptr);
     }
     // compact rows: exclusive scan of row_cnt (n + 1 entries, the last one is a zero pad) -> row_off
     prim::device_scan<uint32_t, prim::OpSum, false>(b.row_cnt.p, b.row_off.p, n, b.scan_tmp.p, prim::OpSum(), st, &T.launches);

@@ -6,6 +6,7 @@
 // The DP rows run on the whole warp (ksw_global_warp).  MAPQ needs libm's log() and is finished on the
 // host from the fields written here (A.12).
 #include "pipeline.cuh"
+#include <cstdlib>
 #include "ksw_warp.cuh"
 #include "ksort_dev.cuh"
 #include "launch_cache.cuh"
@@ -211,6 +212,7 @@ __device__ __forceinline__ bool mat_is_simple(const int* smat) {
 // A job list holds both classes of thread-per-region work so that the lanes of a warp do similar work: regions whose band
 // fits the register window (w <= REG_WT) grow from the front, wider ones (shared-memory kernel) from the back.
 constexpr int REG_WT = 16;
+constexpr int REG_WT2 = 32;   // second register kernel: bands of half-width 17..32 (65 columns of H and E in registers, 2 CTAs per SM)
 __device__ __forceinline__ bool narrow_is_big(const DevOpts& o, int lq, int rlen, int w2, bool simple_mat) {
     w2 = w2 < o.w << 2 ? w2 : o.w << 2;
     return !simple_mat || gen_cigar_band(o, lq, rlen, w2) > REG_WT;
@@ -581,13 +583,14 @@ struct NarrowParams {
     NarrowJob* requeue; uint32_t requeue_cap; uint32_t* requeue_cnt; uint32_t* requeue_big_cnt; uint64_t* wide_jobs; uint32_t* wide_cnt;
     uint32_t* cigar_pool; uint32_t cigar_cap; uint32_t* cigar_top;
     uint8_t* zbuf; uint32_t* ticket; uint32_t* overflow; unsigned long long* counters;
+    int big_go_wide; // experiment (BSQ_FIN_BIG_TO_WIDE): bands wider than the register window go to the warp-cooperative kernel
     int diag_pass;   // 1: equal-length regions -- finish the ones whose diagonal is provably optimal, hand the rest to the DP list
 };
 
 // MODE 0: circular row window in shared memory (bands up to NARROW_NC columns); MODE 1: the band in registers
 // (global_dp_reg, w <= REG_WT), no shared memory, regions with a wider band are passed on to a MODE 0 launch.
 template <int MODE>
-__global__ void __launch_bounds__(NARROW_THREADS, MODE == 1 ? 4 : 1) regs_cigar_narrow(NarrowParams P, DevIndex ix, DevOpts o) {
+__global__ void __launch_bounds__(NARROW_THREADS, MODE == 1 ? 4 : (MODE == 2 ? 2 : 1)) regs_cigar_narrow(NarrowParams P, DevIndex ix, DevOpts o) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ int smat[25];
     if (threadIdx.x < 25) smat[threadIdx.x] = o.mat[threadIdx.x];
@@ -598,8 +601,9 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE == 1 ? 4 : 1) regs_cigar_
     uint8_t* Q = dyn_smem + 2 * NARROW_NC * NARROW_THREADS * 4 + tid;               // Q[j * NARROW_THREADS]
     const uint32_t gwarp = (blockIdx.x * NARROW_THREADS + tid) >> 5;
     // traceback bytes, 4 cells per 32-bit store, laid out [row][4-cell group][lane]: a warp store is 128 contiguous bytes
-    constexpr size_t Z_PER_WARP = MODE == 1 ? (size_t)NARROW_TMAX * ((2 * REG_WT + 1 + 3) / 4) * 4 * 32 : (size_t)NARROW_TMAX * NARROW_NC * 32;
-    constexpr int ZROW = MODE == 1 ? (2 * REG_WT + 1 + 3) / 4 : NARROW_NC / 4;      // words per row and lane
+    constexpr int WTM = MODE == 2 ? REG_WT2 : REG_WT;                                // half-width of the register window (MODE 1 / 2)
+    constexpr size_t Z_PER_WARP = MODE != 0 ? (size_t)NARROW_TMAX * ((2 * WTM + 1 + 3) / 4) * 4 * 32 : (size_t)NARROW_TMAX * NARROW_NC * 32;
+    constexpr int ZROW = MODE != 0 ? (2 * WTM + 1 + 3) / 4 : NARROW_NC / 4;         // words per row and lane
     uint32_t* Z = reinterpret_cast<uint32_t*>(P.zbuf + (size_t)gwarp * Z_PER_WARP) + lane;
     const bool simple_mat = mat_is_simple(smat);
     int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins, e_del = o.e_del, e_ins = o.e_ins;
@@ -664,10 +668,10 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE == 1 ? 4 : 1) regs_cigar_
                     if (!diagonal) {
                         const int w = gen_cigar_band(o, lq, rlen, w2);
                         const int n_col = lq < 2 * w + 1 ? lq : 2 * w + 1;
-                        if ((MODE == 1 ? (w > REG_WT || !simple_mat) : 2 * w + 1 > NARROW_NC) || rlen > NARROW_TMAX) { go_wide = true; break; }
+                        if ((MODE != 0 ? (w > WTM || !simple_mat) : (2 * w + 1 > NARROW_NC || P.big_go_wide)) || rlen > NARROW_TMAX) { go_wide = true; break; }
                         ++calls;
-                        if (MODE == 1) {
-                            score = global_dp_reg<REG_WT>(qg, lq, rev, ix.pac, tbase, rlen, w, smat[0], smat[1], smat[4], o.o_del, e_del, o.o_ins, e_ins, Z, cells);
+                        if (MODE != 0) {
+                            score = global_dp_reg<WTM>(qg, lq, rev, ix.pac, tbase, rlen, w, smat[0], smat[1], smat[4], o.o_del, e_del, o.o_ins, e_ins, Z, cells);
                         } else {
                         // first row of the band
                         H[0] = 0; E[0] = KSW_NEG_INF;
@@ -726,7 +730,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE == 1 ? 4 : 1) regs_cigar_
                                 else cg[n_cigar - 1] += len << 4;
                             };
                             while (i >= 0 && k >= 0) {
-                                const int jj = MODE == 1 ? k - i + REG_WT : k - (i > w ? i - w : 0);
+                                const int jj = MODE != 0 ? k - i + WTM : k - (i > w ? i - w : 0);
                                 which = (int)(Z[((size_t)i * ZROW + (jj >> 2)) * 32] >> ((jj & 3) << 3) & 0xff) >> (which << 1) & 3;
                                 if (which == 0) { push(0, 1); --i; --k; }
                                 else if (which == 1) { push(2, 1); --i; }
@@ -860,26 +864,31 @@ int finalize_resident_warps() {
     return cached_blocks_per_sm(regs_finalize<false>, FIN_THREADS, 0) * cached_sm_count() * FIN_WARPS;
 }
 
-// resident warps of the two thread-per-region kernels and the traceback buffer that serves both
-static void narrow_geometry(int* warps_smem, int* warps_reg, size_t* zbytes) {
+// resident warps of the two thread-per-region kernels and their traceback buffers (the kernels of a DP pass run side by side, so
+// each has its own: the register kernel's first, the shared-memory kernel's behind it)
+static void narrow_geometry(int* warps_smem, int* warps_reg, int* warps_reg2, size_t* zbytes_reg, size_t* zbytes_smem) {
     const size_t smem = (size_t)NARROW_THREADS * (2 * NARROW_NC * 4 + NARROW_QMAX);
     const int nb = cached_blocks_per_sm(regs_cigar_narrow<0>, NARROW_THREADS, smem), nr = cached_blocks_per_sm(regs_cigar_narrow<1>, NARROW_THREADS, 0);
+    const int nr2 = cached_blocks_per_sm(regs_cigar_narrow<2>, NARROW_THREADS, 0);
     const int sms = cached_sm_count();
-    const int ws = nb * sms * (NARROW_THREADS / 32), wr = nr * sms * (NARROW_THREADS / 32);
+    const int ws = nb * sms * (NARROW_THREADS / 32), wr = nr * sms * (NARROW_THREADS / 32), wr2 = nr2 * sms * (NARROW_THREADS / 32);
     if (warps_smem) *warps_smem = ws;
     if (warps_reg) *warps_reg = wr;
-    const size_t zs = (size_t)ws * NARROW_TMAX * NARROW_NC * 32, zr = (size_t)wr * NARROW_TMAX * ((2 * REG_WT + 1 + 3) / 4) * 4 * 32;
-    if (zbytes) *zbytes = zs > zr ? zs : zr;
+    if (warps_reg2) *warps_reg2 = wr2;
+    // the back-section kernel is either the shared-memory one or the wide register one: one buffer, sized for the larger
+    const size_t zs = (size_t)ws * NARROW_TMAX * NARROW_NC * 32, z2 = (size_t)wr2 * NARROW_TMAX * ((2 * REG_WT2 + 1 + 3) / 4) * 4 * 32;
+    if (zbytes_smem) *zbytes_smem = zs > z2 ? zs : z2;
+    if (zbytes_reg) *zbytes_reg = (size_t)wr * NARROW_TMAX * ((2 * REG_WT + 1 + 3) / 4) * 4 * 32;
 }
 
 size_t narrow_zbuf_bytes(int* n_warps_out) {
-    int ws = 0; size_t z = 0;
-    narrow_geometry(&ws, nullptr, &z);
+    int ws = 0; size_t zr = 0, zs = 0;
+    narrow_geometry(&ws, nullptr, nullptr, &zr, &zs);
     if (n_warps_out) *n_warps_out = ws;
-    return z;
+    return zr + zs;
 }
 
-void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint32_t rseq_cap, int n_warps, uint64_t* launches) {
+void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint32_t rseq_cap, int n_warps, uint64_t* launches, const ExtAux* aux) {
     const uint32_t cig_cap = fin_cig_cap(p.max_len, rseq_cap);
     int blocks = n_warps / FIN_WARPS;
     if (blocks < 1) blocks = 1;
@@ -896,9 +905,16 @@ void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts&
     if (!p.narrow_jobs) return;
     // phase 2: thread-per-region narrow-band mem_reg2aln, one try of the band-doubling loop per pass (<= 3 tries)
     {
-        int warps = 0, warps_reg = 0;
-        narrow_geometry(&warps, &warps_reg, nullptr);
-        if (warps > p.narrow_warps) { warps_reg = (int)((long long)warps_reg * p.narrow_warps / warps); warps = p.narrow_warps; }
+        int warps = 0, warps_reg = 0, warps_reg2 = 0; size_t z_reg = 0;
+        narrow_geometry(&warps, &warps_reg, &warps_reg2, &z_reg, nullptr);
+        // the scoring matrix of this path is mem_opt_init's and never changes (SURVEY B#5): match / mismatch / N, which is what the
+        // register kernels assume; any other matrix takes the shared-memory kernel
+        bool simple = true;
+        for (int a = 0; a < 5 && simple; ++a) for (int c = 0; c < 5; ++c) {
+            const int want = (a == 4 || c == 4) ? o.mat[4] : (a == c ? o.mat[0] : o.mat[1]);
+            if (o.mat[a * 5 + c] != want) { simple = false; break; }
+        }
+        static const bool no_reg2 = getenv("BSQ_FIN_NO_REG2") != nullptr;
         NarrowJob* listA = reinterpret_cast<NarrowJob*>(p.narrow_jobs);
         NarrowJob* listB = listA + p.narrow_cap;
         NarrowJob* listS = listA + 2 * (size_t)p.narrow_cap;
@@ -916,16 +932,24 @@ void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts&
             q.requeue_big_cnt = p.narrow_cnt + (pass == 0 ? 5 : (pass == 1 ? 6 : (pass == 2 ? 7 : 4)));
             q.wide_jobs = p.wide_jobs; q.wide_cnt = p.wide_cnt; q.cigar_pool = p.cigar_pool; q.cigar_cap = p.cigar_cap; q.cigar_top = p.cigar_top;
             q.zbuf = p.narrow_z; q.overflow = p.overflow; q.counters = p.counters; q.diag_pass = pass == 0;
+            { static const bool btw = getenv("BSQ_FIN_BIG_TO_WIDE") != nullptr; q.big_go_wide = btw; }
             q.jobs = in; q.job_stride = 1; q.ticket = p.ticket + 1 + pass;
             q.n_jobs = p.narrow_cnt + (pass == 0 ? 3 : (pass == 1 ? 0 : (pass == 2 ? 1 : 2)));
             if (pass == 0) {
-                regs_cigar_narrow<0><<<warps / (NARROW_THREADS / 32), NARROW_THREADS, nsmem, st>>>(q, ix, o);
+                // the diagonal proof needs no band state: the register kernel's geometry (no shared memory, 4 CTAs per SM)
+                regs_cigar_narrow<1><<<warps_reg / (NARROW_THREADS / 32), NARROW_THREADS, 0, st>>>(q, ix, o);
                 if (launches) ++*launches;
             } else {
+                // the two kernels of a DP pass work on disjoint sections of the list: side by side when a side stream is there
+                cudaStream_t s2 = aux ? aux->st[0] : st;
+                if (aux) { cudaEventRecord(aux->ev[0], st); cudaStreamWaitEvent(s2, aux->ev[0], 0); }
                 regs_cigar_narrow<1><<<warps_reg / (NARROW_THREADS / 32), NARROW_THREADS, 0, st>>>(q, ix, o);
                 q.jobs = in + p.narrow_cap - 1; q.job_stride = -1; q.ticket = p.ticket + 5 + pass;      // tickets 6..8
                 q.n_jobs = p.narrow_cnt + (pass == 1 ? 5 : (pass == 2 ? 6 : 7));
-                regs_cigar_narrow<0><<<warps / (NARROW_THREADS / 32), NARROW_THREADS, nsmem, st>>>(q, ix, o);
+                q.zbuf = p.narrow_z + z_reg;
+                if (simple && !no_reg2) regs_cigar_narrow<2><<<warps_reg2 / (NARROW_THREADS / 32), NARROW_THREADS, 0, s2>>>(q, ix, o);
+                else regs_cigar_narrow<0><<<warps / (NARROW_THREADS / 32), NARROW_THREADS, nsmem, s2>>>(q, ix, o);
+                if (aux) { cudaEventRecord(aux->ev[1], s2); cudaStreamWaitEvent(st, aux->ev[1], 0); }
                 if (launches) *launches += 2;
             }
         }

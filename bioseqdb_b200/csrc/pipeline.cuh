@@ -111,7 +111,9 @@ struct FinalizeParams {
     unsigned long long* counters;  // optional: [0] = ksw_global2 cells, [1] = calls
     uint32_t* todo; uint32_t* todo_cnt;   // reads the thread-per-read pass left for regs_finalize (nullptr = no thread pass)
 };
-void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint32_t rseq_cap, int n_warps, uint64_t* launches);
+struct ExtAux;
+// aux (optional): side streams + events; the two kernels of a DP pass (register band / shared-memory band) then run side by side
+void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, uint32_t rseq_cap, int n_warps, uint64_t* launches, const ExtAux* aux);
 size_t narrow_zbuf_bytes(int* n_warps_out);
 size_t finalize_scratch_per_warp(uint32_t max_len, uint32_t rseq_cap, uint32_t* z_cap_out);
 int finalize_resident_warps();

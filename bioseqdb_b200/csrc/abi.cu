@@ -59,13 +59,13 @@ struct Batch {
     DevBuf<uint32_t> cigar; uint32_t cigar_cap = 0;
     DevBuf<double> read_logtab; uint32_t read_logtab_n = 0; uint32_t rseq_cap = 0;
     DevBuf<uint8_t> ext_scratch, fin_scratch, narrow_z, narrow_jobs; DevBuf<uint64_t> wide_jobs;
-    DevBuf<ExtMemo> ext_memo; DevBuf<uint8_t> ext_memo_key; DevBuf<uint32_t> ext_memo_perm, ext_memo_hist, ext_todo, chain_todo, fin_todo, seed_todo;   // thread-per-extension pre-pass (extend_plan.cu)
+    DevBuf<ExtMemo> ext_memo; DevBuf<uint8_t> ext_memo_key; DevBuf<uint32_t> ext_memo_perm, ext_memo_hist, ext_todo, chain_todo, fin_todo, seed_todo, seed_pk, seed_u32;   // thread-per-extension pre-pass (extend_plan.cu)
     DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..23] counters (u64 x 8), [24] narrow_cnt, [25] wide_cnt, [26..27] tickets, [56] reads left for sw_extend, [57] reads left for the warp chain kernel, [58] for regs_finalize
     size_t device_bytes() const {
         return seqs.bytes() + offs.bytes() + ids.bytes() + datums.bytes() + datum_off.bytes() + scan_tmp64.bytes() + intv.bytes() + intv_cnt.bytes() + seed_scratch.bytes() + raw.bytes() + seeds.bytes() + ctmp.bytes() +
                ord.bytes() + chains.bytes() + srt.bytes() + regs.bytes() + rows.bytes() + rows_compact.bytes() + rows_ext.bytes() + reg_cnt.bytes() + row_cnt.bytes() + row_off.bytes() +
                scan_tmp.bytes() + blocks.bytes() + cigar.bytes() + read_logtab.bytes() + ext_scratch.bytes() + fin_scratch.bytes() + narrow_z.bytes() +
-               narrow_jobs.bytes() + wide_jobs.bytes() + ctl.bytes() + ext_memo.bytes() + ext_memo_key.bytes() + ext_memo_perm.bytes() + ext_memo_hist.bytes() + ext_todo.bytes() + chain_todo.bytes() + fin_todo.bytes() + seed_todo.bytes();
+               narrow_jobs.bytes() + wide_jobs.bytes() + ctl.bytes() + ext_memo.bytes() + ext_memo_key.bytes() + ext_memo_perm.bytes() + ext_memo_hist.bytes() + ext_todo.bytes() + chain_todo.bytes() + fin_todo.bytes() + seed_todo.bytes() + seed_pk.bytes() + seed_u32.bytes();
     }
     bool resident = false, aligned = false;
     // one batch = one lane of the host pipeline: its stream, the host staging that must outlive the async copies,
@@ -88,7 +88,7 @@ struct Batch {
         ctmp.release(); ord.release(); chains.release(); srt.release(); regs.release(); rows.release(); rows_compact.release(); rows_ext.release(); reg_cnt.release();
         row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release();
         ctl.release(); narrow_z.release(); narrow_jobs.release(); wide_jobs.release(); read_logtab.release();
-        ext_memo.release(); ext_memo_key.release(); ext_memo_perm.release(); ext_memo_hist.release(); ext_todo.release(); chain_todo.release(); fin_todo.release(); seed_todo.release();
+        ext_memo.release(); ext_memo_key.release(); ext_memo_perm.release(); ext_memo_hist.release(); ext_todo.release(); chain_todo.release(); fin_todo.release(); seed_todo.release(); seed_pk.release(); seed_u32.release();
     }
 };
 
@@ -693,6 +693,13 @@ int ensure_kmer_table(bsq_index* h, const DevIndex& ix) {
     }
     if (h->d_kmer || ix.seq_len < (1u << 16) || getenv("BSQ_NO_KMER")) return BSQ_OK;
     h->kmer_k = kmer_table_depth(ix.seq_len);
+    // One level more than ceil(log4 n) where HBM allows it (23 GB at K = 15): a K-mer of the read's own locus then has a second,
+    // chance occurrence three times less often, and every such occurrence costs the seeding kernels real bwt_extend steps
+    // (measured at 200 M symbols: 13.6 -> 12.3 ms per 1 M reads).  Only for 32-bit indexes; the 64-bit ones keep their HBM for SA + ISA.
+    if (h->kmer_k == 14 && ix.sa_bytes == 4 && ix.seq_len > (1ull << 27)) {
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && fr > 4 * kmer_table_bytes(15)) h->kmer_k = 15;
+    }
     if (const char* e = getenv("BSQ_KMER_K")) { const int k = atoi(e); if (k >= 8 && k <= 15) h->kmer_k = k; }
     CUDA_CHECK(cudaMalloc(&h->d_kmer, kmer_table_bytes(h->kmer_k)));
     build_kmer_table(ix, h->d_kmer, h->kmer_k, h->stream, &h->timing.launches);
@@ -710,7 +717,8 @@ SeedParams seed_params(const bsq_index* h, const Batch& b, const DevIndex& ix, u
     P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u;
     P.lists_in_smem = seed_lists_fit_smem(b.list_cap, P.read_cap, ix.sa_bytes);
     P.ticket = ticket; P.overflow = b.ctl.p + 4; P.n_extend = n_extend;
-    P.todo = b.seed_todo.p; P.todo_cnt = b.ctl.p + 59;    // reads the thread-per-read pass leaves for seed_smem
+    P.todo = b.seed_todo.p; P.todo_cnt = b.ctl.p + 59;    // reads the thread-per-read passes leave for seed_smem
+    P.pk = b.seed_pk.p; P.rflag = b.seed_u32.p; P.cnt12 = b.seed_u32.p ? b.seed_u32.p + n : nullptr; P.ext12 = b.seed_u32.p ? b.seed_u32.p + 2 * (size_t)n : nullptr;
     return P;
 }
 
@@ -760,6 +768,7 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
     const size_t narrow_bytes = narrow_zbuf_bytes(&narrow_warps);
     ENS(b.narrow_z.ensure(narrow_bytes)); ENS(b.narrow_jobs.ensure((size_t)b.pool_cap * 3 * 24)); ENS(b.wide_jobs.ensure(b.pool_cap));
     ENS(b.ctl.ensure(64)); ENS(b.chain_todo.ensure(n)); ENS(b.fin_todo.ensure(n)); ENS(b.seed_todo.ensure(n + 1));
+    if (max_len <= 496) { ENS(b.seed_pk.ensure((size_t)n * seed_thread_words(max_len))); ENS(b.seed_u32.ensure(3 * (size_t)n)); }
     // the thread-per-extension pre-pass packs column scores in 16 bits: every value it stores is <= l_query * (a + 1)
     static const bool no_memo = getenv("BSQ_NO_EXT_MEMO") != nullptr;
     // Small batches take the warp-cooperative kernels for the DP stages: the thread-per-extension / thread-per-region kernels are built for
@@ -784,7 +793,7 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
     {
         SeedParams P = seed_params(h, b, ix, n, b.intv_cap, b.ctl.p + 0, ctr ? ctr + 0 : nullptr);
         // thread per read first (almost every short read); seed_smem, warp per read, takes what it declined
-        if (seed_thread_usable(P, o, b.max_len)) { launch_seed_thread(P, ix, o, b.max_len, b.ctl.p + 60, st); ++T.launches; }
+        if (seed_thread_usable(P, o, b.max_len)) T.launches += launch_seed_thread(P, ix, o, b.max_len, b.ctl.p + 60, st);
         else P.todo = nullptr;
         launch_seed(P, ix, o, st, nullptr); ++T.launches;
     }
@@ -1467,6 +1476,7 @@ int bsq_debug_seed(bsq_index* h, const char* seqs, const uint64_t* offs, uint64_
     CUDA_CHECK(b.ctl.ensure(64));
     CUDA_CHECK(cudaMemsetAsync(b.ctl.p, 0, 64 * 4, h->stream));
     CUDA_CHECK(b.seed_todo.ensure(n + 1));
+    if (b.max_len <= 496) { CUDA_CHECK(b.seed_pk.ensure((size_t)n * seed_thread_words(b.max_len))); CUDA_CHECK(b.seed_u32.ensure(3 * (size_t)n)); }
     SeedParams P = seed_params(h, b, ix, (uint32_t)n, cap, b.ctl.p, reinterpret_cast<unsigned long long*>(b.ctl.p + 8));
     if (seed_thread_usable(P, h->dopts, b.max_len)) launch_seed_thread(P, ix, h->dopts, b.max_len, b.ctl.p + 60, h->stream);
     else P.todo = nullptr;

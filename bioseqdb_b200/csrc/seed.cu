@@ -743,97 +743,154 @@ __global__ void __launch_bounds__(SEED_THREADS, MINB) seed_smem(SeedParams P, De
     if (P.n_extend && lane == 0 && n_ext) atomicAdd(P.n_extend, n_ext);
 }
 
-// ---------------------------------------------------------------- thread-per-read pass (seed_thread.cuh)
-// One thread runs mem_collect_intv for one read; a warp takes 32 consecutive reads per ticket.  The reads' 2-bit packed copies
-// live in shared memory laid out [word][thread] (bank = lane).  Intervals are staged unsorted in the upper half of the read's
-// output slots, ranked by `info` with a 32-bit key per record, and written in order to the lower half.  Reads the thread
-// declines are appended to `todo` for seed_smem.
+// ---------------------------------------------------------------- thread-per-read passes (seed_thread.cuh)
+// Three kernels.  seed_pack turns every read into its 2-bit packed copy (16 bases per word) and flags the reads the thread code does
+// not take.  seed_calls runs passes 1 and 2 of mem_collect_intv -- every bwt_smem1a call -- with PERSISTENT LANES: a lane works
+// through the calls of its read and fetches the next read as soon as it has none left, so that in every round all 32 lanes of a
+// warp carry a call (reads differ a lot in how many calls they need: one per sequencing error); inside a round the lanes walk the
+// list entry by list entry, loop counters being warp votes (seed_thread.cuh).  seed_last, thread per read, runs the LAST-like
+// pass, ranks the read's intervals by `info` and writes them in order; reads the thread code declined go to `todo` for seed_smem.
+// The reads' packed copies and the P(b) arrays live in shared memory laid out [word][thread] (bank = lane); intervals are staged
+// unsorted in the upper half of the read's output slots.
 constexpr int ST_THREADS = 128;
-template <class IdxT>
-__global__ void __launch_bounds__(ST_THREADS) seed_thread(SeedParams P, DevIndex ix, DevOpts o, uint32_t* ticket, int words) {
-    extern __shared__ __align__(16) uint32_t st_pk[];      // [words][ST_THREADS] packed reads, then [PCAP][ST_THREADS] P(b) arrays
-    uint32_t* st_pc = st_pk + (size_t)words * ST_THREADS;
-    const int tid = threadIdx.x, lane = tid & 31;
+constexpr uint32_t ST_FAIL = 0xffffffffu;
+enum { STF_FALLBACK = 1, STF_EMPTY = 2 };      // read flags: not for the thread code (ambiguous base / too long); shorter than a seed
+
+__global__ void seed_pack(SeedParams P, int min_seed_len, int words) {
+    const uint64_t total = (uint64_t)P.n_reads * (uint32_t)words;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(t / (uint32_t)words); const int w = (int)(t % (uint32_t)words);
+        const uint64_t off = P.offs[r];
+        const int len = (int)(P.offs[r + 1] - off);
+        uint32_t v = 0, amb = 0;
+        const int b0 = w << 4;
+        if ((len >> 4) + 3 <= words && b0 < len) {
+            const uint8_t* q = P.seqs + off + b0;
+            const int nb = len - b0 < 16 ? len - b0 : 16;
+            for (int k = 0; k < nb; ++k) { const uint32_t c = q[k]; amb |= c; v |= (c & 3u) << (30 - 2 * k); }
+        }
+        P.pk[t] = v;
+        uint32_t f = amb > 3 ? (uint32_t)STF_FALLBACK : 0u;
+        if (w == 0) { if (len < min_seed_len) f |= STF_EMPTY; else if ((len >> 4) + 3 > words) f |= STF_FALLBACK; }
+        if (f) atomicOr(P.rflag + r, f);
+    }
+}
+
+template <class IdxT> __device__ __forceinline__ seedt::Index<IdxT> st_index(const SeedParams& P, const DevIndex& ix) {
     seedt::Index<IdxT> X;
     X.occ = ix.occ; X.tab = reinterpret_cast<const seedt::U4*>(P.kmer_tab); X.kk = P.kmer_k;
     X.sa = reinterpret_cast<const IdxT*>(ix.sa); X.isa = reinterpret_cast<const IdxT*>(P.isa); X.pac = ix.pac;
     X.l_pac = (IdxT)ix.l_pac; X.n = (IdxT)ix.seq_len; X.primary = (IdxT)ix.primary;
 #pragma unroll
     for (int c = 0; c < 5; ++c) X.L2[c] = (IdxT)ix.L2[c];
+    return X;
+}
+
+template <class IdxT>
+__global__ void __launch_bounds__(ST_THREADS) seed_calls(SeedParams P, DevIndex ix, DevOpts o, uint32_t* ticket, int words) {
+    extern __shared__ __align__(16) uint32_t st_pk[];      // [words][ST_THREADS] packed reads, then [PCAP][ST_THREADS] P(b) arrays
+    uint32_t* st_pc = st_pk + (size_t)words * ST_THREADS;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const seedt::Index<IdxT> X = st_index<IdxT>(P, ix);
     seedt::Opts so; so.min_seed_len = o.min_seed_len; so.split_len = o.split_len; so.split_width = o.split_width; so.max_mem_intv = o.max_mem_intv;
     const uint32_t half = P.cap / 2;                 // sorted records go to slots [0, half), the staging is [cap - half, cap)
-    unsigned long long n_ext_sum = 0;
+    const uint32_t stage_cap = half < (uint32_t)seedt::PCAP ? half : (uint32_t)seedt::PCAP;
+    seedt::Read R; R.pk = st_pk + tid; R.stride = ST_THREADS; R.len = 0;
+    seedt::Work<IdxT> W;
+    seedt::work_init(W, (seedt::IntvOut*)nullptr, stage_cap, st_pc + tid, ST_THREADS);
+    seedt::Calls C; seedt::calls_init(C);
+    uint32_t r = ST_FAIL;                            // the lane's read (ST_FAIL = none)
+    bool dry = false;                                // the queue of reads is exhausted
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(ticket, 32u);
-        base = __shfl_sync(FULL, base, 0);
-        if (base >= P.n_reads) break;
-        const uint32_t r = base + (uint32_t)lane;
-        bool active = r < P.n_reads, fail = false;
-        if (active) {
-            const uint64_t off = P.offs[r];
-            const int len = (int)(P.offs[r + 1] - off);
-            if (len < o.min_seed_len) { P.out_cnt[r] = 0; active = false; }       // mem_chain returns before seeding
-            else if ((len >> 4) + 3 > words) fail = true;
-            else {
-                const uint8_t* q = P.seqs + off;
-                uint32_t amb = 0;
-                for (int w = 0; w < words; ++w) {
-                    uint32_t v = 0;
-                    const int b0 = w << 4;
-                    if (b0 < len) {
-                        const int nb = len - b0 < 16 ? len - b0 : 16;
-                        for (int k = 0; k < nb; ++k) { const uint32_t c = q[b0 + k]; amb |= c; v |= (c & 3u) << (30 - 2 * k); }
-                    }
-                    st_pk[w * ST_THREADS + tid] = v;
-                }
-                if (amb > 3) fail = true;          // an ambiguous base: the warp kernel's general path
-            }
-        }
-        // ---- the 32 reads of the warp advance together (seed_thread.cuh), call by call and, inside a call, list entry by list
-        // entry: the loop counters are warp votes, so the lanes meet again at every call and every column
-        seedt::Read R; R.pk = st_pk + tid; R.stride = ST_THREADS; R.len = 0;
-        seedt::Work<IdxT> W;
-        Intv* slots = P.out + (size_t)(active ? r : 0) * P.cap;
-        seedt::work_init(W, reinterpret_cast<seedt::IntvOut*>(slots + (P.cap - half)), half < (uint32_t)seedt::PCAP ? half : (uint32_t)seedt::PCAP, st_pc + tid, ST_THREADS);
-        const bool run = active && !fail;
-        if (run) R.len = (int)(P.offs[r + 1] - P.offs[r]);
-        seedt::Calls C; seedt::calls_init(C);
+        // ---- every lane gets a call: the next one of its read, or the first one of a new read
+        int x = 0; uint32_t mi = 1; bool has = false;
         for (;;) {
-            int x = 0; uint32_t mi = 1;
-            const bool has = run && seedt::next_call(C, so, R, W, &x, &mi);
-            if (!__any_sync(FULL, has)) break;
-            if (has) seedt::smem_forward(X, R, x, mi, W);
-            const int ncol = has && !W.fail ? W.n : 0;
-            for (int k = 0; __any_sync(FULL, k < ncol); ++k) seedt::smem_column(X, so, R, k, W, k < ncol && !W.fail);
-            if (has && C.pass == 1) C.next_x = W.ret;
-        }
-        if (run && !W.fail) seedt::last_like_pass(X, so, R, W);
-        if (active && !fail) {
-            fail = W.fail;
-            if (!fail) {
-                // rank by info: key = start | end | staging index (9 + 9 + 6 bits; reads of at most 496 bases, at most 64 records)
-                // (the keys live in the lane's P(b) array, which is free once the calls are over)
-                uint32_t* key = st_pc + tid;
-                const uint32_t n = W.n_out;
-                for (uint32_t k = 0; k < n; ++k) {
-                    const uint64_t info = W.out[k].info;
-                    uint32_t kk = (uint32_t)(info >> 32) << 15 | ((uint32_t)info & 0x1ffu) << 6 | k;
-                    uint32_t j = k;
-                    while (j > 0 && key[(j - 1) * ST_THREADS] > kk) { key[j * ST_THREADS] = key[(j - 1) * ST_THREADS]; --j; }
-                    key[j * ST_THREADS] = kk;
+            if (r != ST_FAIL && !has) {
+                has = seedt::next_call(C, so, R, W, &x, &mi);
+                if (!has) {                           // passes 1 and 2 of this read are done
+                    P.cnt12[r] = W.fail ? ST_FAIL : W.n_out; P.ext12[r] = (uint32_t)W.n_ext;
+                    r = ST_FAIL;
                 }
-                for (uint32_t k = 0; k < n; ++k) slots[k] = reinterpret_cast<const Intv*>(W.out)[key[k * ST_THREADS] & 63u];
-                P.out_cnt[r] = n;
-                n_ext_sum += W.n_ext;
+            }
+            const bool need = r == ST_FAIL && !dry;
+            const uint32_t nm = __ballot_sync(FULL, need);
+            if (!nm) break;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(ticket, (uint32_t)__popc(nm));
+            base = __shfl_sync(FULL, base, 0);
+            if (need) {
+                const uint32_t rr = base + (uint32_t)__popc(nm & ((1u << lane) - 1u));
+                if (rr >= P.n_reads) dry = true;
+                else if (P.rflag[rr] == 0) {
+                    r = rr;
+                    const uint32_t* src = P.pk + (size_t)rr * (uint32_t)words;
+                    for (int w = 0; w < words; ++w) st_pk[w * ST_THREADS + tid] = src[w];
+                    R.len = (int)(P.offs[rr + 1] - P.offs[rr]);
+                    seedt::work_init(W, reinterpret_cast<seedt::IntvOut*>(P.out + (size_t)rr * P.cap + (P.cap - half)), stage_cap, st_pc + tid, ST_THREADS);
+                    seedt::calls_init(C);
+                }
             }
         }
-        const uint32_t fm = __ballot_sync(FULL, active && fail);
+        if (!__any_sync(FULL, has)) break;
+        // ---- one bwt_smem1a call per lane: forward walk, then the backward walk entry by entry
+        if (has) seedt::smem_forward(X, R, x, mi, W);
+        const int ncol = has && !W.fail ? W.n : 0;
+        for (int k = 0; __any_sync(FULL, k < ncol); ++k) seedt::smem_column(X, so, R, k, W, k < ncol && !W.fail);
+        if (has && C.pass == 1) C.next_x = W.ret;
+    }
+}
+
+template <class IdxT>
+__global__ void __launch_bounds__(ST_THREADS) seed_last(SeedParams P, DevIndex ix, DevOpts o, int words) {
+    extern __shared__ __align__(16) uint32_t st_pk[];
+    uint32_t* st_pc = st_pk + (size_t)words * ST_THREADS;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const seedt::Index<IdxT> X = st_index<IdxT>(P, ix);
+    seedt::Opts so; so.min_seed_len = o.min_seed_len; so.split_len = o.split_len; so.split_width = o.split_width; so.max_mem_intv = o.max_mem_intv;
+    const uint32_t half = P.cap / 2;
+    const uint32_t stage_cap = half < (uint32_t)seedt::PCAP ? half : (uint32_t)seedt::PCAP;
+    unsigned long long n_ext_sum = 0;
+    for (uint32_t base = blockIdx.x * ST_THREADS; base < P.n_reads; base += gridDim.x * ST_THREADS) {
+        const uint32_t r = base + (uint32_t)tid;
+        bool fail = false;
+        if (r < P.n_reads) {
+            const uint32_t fl = P.rflag[r], c12 = P.cnt12[r];
+            if (fl & STF_EMPTY) P.out_cnt[r] = 0;                                   // mem_chain returns before seeding
+            else if (fl || c12 == ST_FAIL) fail = true;
+            else {
+                const uint32_t* src = P.pk + (size_t)r * (uint32_t)words;
+                for (int w = 0; w < words; ++w) st_pk[w * ST_THREADS + tid] = src[w];
+                seedt::Read R; R.pk = st_pk + tid; R.stride = ST_THREADS; R.len = (int)(P.offs[r + 1] - P.offs[r]);
+                Intv* slots = P.out + (size_t)r * P.cap;
+                seedt::Work<IdxT> W;
+                seedt::work_init(W, reinterpret_cast<seedt::IntvOut*>(slots + (P.cap - half)), stage_cap, st_pc + tid, ST_THREADS);
+                W.n_out = c12;
+                seedt::last_like_pass(X, so, R, W);
+                fail = W.fail;
+                if (!fail) {
+                    // rank by info: key = start | end | staging index (9 + 9 + 6 bits; reads of at most 496 bases, at most 64 records);
+                    // the keys live in the lane's P(b) array, which is free here
+                    uint32_t* key = st_pc + tid;
+                    const uint32_t n = W.n_out;
+                    for (uint32_t k = 0; k < n; ++k) {
+                        const uint64_t info = W.out[k].info;
+                        uint32_t kk = (uint32_t)(info >> 32) << 15 | ((uint32_t)info & 0x1ffu) << 6 | k;
+                        uint32_t j = k;
+                        while (j > 0 && key[(j - 1) * ST_THREADS] > kk) { key[j * ST_THREADS] = key[(j - 1) * ST_THREADS]; --j; }
+                        key[j * ST_THREADS] = kk;
+                    }
+                    for (uint32_t k = 0; k < n; ++k) slots[k] = reinterpret_cast<const Intv*>(W.out)[key[k * ST_THREADS] & 63u];
+                    P.out_cnt[r] = n;
+                    n_ext_sum += W.n_ext + P.ext12[r];
+                }
+            }
+        }
+        const uint32_t fm = __ballot_sync(FULL, fail);
         if (fm) {
             uint32_t at = 0;
             if (lane == 0) at = atomicAdd(const_cast<uint32_t*>(P.todo_cnt), (uint32_t)__popc(fm));
             at = __shfl_sync(FULL, at, 0);
-            if (active && fail) const_cast<uint32_t*>(P.todo)[at + (uint32_t)__popc(fm & ((1u << lane) - 1u))] = r;
+            if (fail) const_cast<uint32_t*>(P.todo)[at + (uint32_t)__popc(fm & ((1u << lane) - 1u))] = r;
         }
     }
     if (P.n_extend) {
@@ -924,18 +981,28 @@ void launch_seed(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cuda
 // (so that an emitted match always carries its rows) and the reads fit its packed shared-memory copy and 9-bit sort key.
 bool seed_thread_usable(const SeedParams& p, const DevOpts& o, uint32_t max_len) {
     static const bool off = getenv("BSQ_NO_SEED_THREAD") != nullptr;
-    return !off && p.kmer_tab && p.isa && p.todo && o.min_seed_len > p.kmer_k && o.max_mem_intv > 1 && max_len <= 496 && p.cap / 2 >= 16 && p.cap / 2 <= 64;
+    return !off && p.kmer_tab && p.isa && p.todo && p.pk && o.min_seed_len > p.kmer_k && o.max_mem_intv > 1 && max_len <= 496 && p.cap / 2 >= 16 && p.cap / 2 <= 64;
 }
 
-void launch_seed_thread(const SeedParams& p, const DevIndex& ix, const DevOpts& o, uint32_t max_len, uint32_t* ticket, cudaStream_t st) {
-    const int words = (int)(max_len >> 4) + 3;
+int seed_thread_words(uint32_t max_len) { return (int)(max_len >> 4) + 3; }
+
+// seed_pack -> seed_calls -> seed_last on `st`; returns the number of launches
+int launch_seed_thread(const SeedParams& p, const DevIndex& ix, const DevOpts& o, uint32_t max_len, uint32_t* ticket, cudaStream_t st) {
+    const int words = seed_thread_words(max_len);
     const size_t smem = (size_t)(words + seedt::PCAP) * ST_THREADS * 4;
     const int sms = cached_sm_count();
+    cudaMemsetAsync(p.rflag, 0, (size_t)p.n_reads * 4, st);
+    const uint64_t total = (uint64_t)p.n_reads * (uint32_t)words;
+    seed_pack<<<(unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)sms * 16), 256, 0, st>>>(p, o.min_seed_len, words);
+    const unsigned last_blocks = (unsigned)std::min<uint64_t>(((uint64_t)p.n_reads + ST_THREADS - 1) / ST_THREADS, (uint64_t)sms * 8);
     if (ix.sa_bytes == 8) {
-        const int nb = cached_blocks_per_sm(seed_thread<uint64_t>, ST_THREADS, smem);
-        seed_thread<uint64_t><<<nb * sms, ST_THREADS, smem, st>>>(p, ix, o, ticket, words);
+        const int nb = cached_blocks_per_sm(seed_calls<uint64_t>, ST_THREADS, smem);
+        seed_calls<uint64_t><<<nb * sms, ST_THREADS, smem, st>>>(p, ix, o, ticket, words);
+        seed_last<uint64_t><<<last_blocks, ST_THREADS, smem, st>>>(p, ix, o, words);
     } else {
-        const int nb = cached_blocks_per_sm(seed_thread<uint32_t>, ST_THREADS, smem);
-        seed_thread<uint32_t><<<nb * sms, ST_THREADS, smem, st>>>(p, ix, o, ticket, words);
+        const int nb = cached_blocks_per_sm(seed_calls<uint32_t>, ST_THREADS, smem);
+        seed_calls<uint32_t><<<nb * sms, ST_THREADS, smem, st>>>(p, ix, o, ticket, words);
+        seed_last<uint32_t><<<last_blocks, ST_THREADS, smem, st>>>(p, ix, o, words);
     }
+    return 3;
 }

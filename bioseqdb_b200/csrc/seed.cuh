@@ -25,10 +25,14 @@ struct SeedParams {
     unsigned long long* n_extend;  // optional counter (roofline units); nullptr in production
     // reads the thread-per-read pass (seed_thread) left for seed_smem; nullptr = seed_smem takes every read
     const uint32_t* todo; const uint32_t* todo_cnt;
+    // working arrays of the thread-per-read passes: packed reads (n_reads x seed_thread_words), per-read flags, records / logical
+    // extensions after passes 1 and 2
+    uint32_t* pk; uint32_t* rflag; uint32_t* cnt12; uint32_t* ext12;
 };
 // thread-per-read pass: runs before launch_seed when seed_thread_usable(); appends the reads it declines to p.todo
 bool seed_thread_usable(const SeedParams& p, const DevOpts& o, uint32_t max_len);
-void launch_seed_thread(const SeedParams& p, const DevIndex& ix, const DevOpts& o, uint32_t max_len, uint32_t* ticket, cudaStream_t st);
+int seed_thread_words(uint32_t max_len);
+int launch_seed_thread(const SeedParams& p, const DevIndex& ix, const DevOpts& o, uint32_t max_len, uint32_t* ticket, cudaStream_t st);
 void launch_seed(const SeedParams& p, const DevIndex& ix, const DevOpts& o, cudaStream_t st, int* n_warps_out);
 int seed_resident_warps();
 size_t kmer_table_bytes(int k);

@@ -37,6 +37,7 @@ EXT_ROW_DTYPE = np.dtype([   # bsq_row_ext
 ])
 assert EXT_ROW_DTYPE.itemsize == 48
 FLAG_ROWS_EXT = 1
+FLAG_TWO_CHUNKS = 2
 HOLE_DTYPE = np.dtype([("offset", "<i8"), ("len", "<i4"), ("amb", "S1"), ("_pad", "V3")])
 
 ARR_PAC, ARR_OCC, ARR_SA, ARR_ANN_OFFSET, ARR_ANN_LEN, ARR_ANN_ID, ARR_COUNT = range(7)

@@ -230,8 +230,11 @@ class BwaIndex:
     # ---- alignment
     def set_rows_ext(self, on: bool):
         """Ask for (or drop) the bsq_row_ext records: the mem_alnreg_t fields only parity checks read (hash, truesc, sub, ...)."""
-        check(self.L.bsq_index_set_flags(self.h, _lib.FLAG_ROWS_EXT if on else 0))
         self.rows_ext = bool(on)
+        self._apply_flags()
+
+    def _apply_flags(self):
+        check(self.L.bsq_index_set_flags(self.h, (_lib.FLAG_ROWS_EXT if self.rows_ext else 0) | (_lib.FLAG_TWO_CHUNKS if getattr(self, "two_chunks", False) else 0)))
 
     def _collect(self, res_p) -> AlignResult:
         r = res_p.contents
@@ -274,6 +277,56 @@ class BwaIndex:
         res = C.POINTER(BsqResult)()
         check(self.L.bsq_align_batch_datums(self.h, ptr(data), ptr(off), ptr(ids) if ids is not None else None, n, C.byref(res)))
         return self._collect(res)
+
+    def align_tuples_raw(self, data_ptr: int, off_ptr: int, ids_ptr: int | None, n: int, flags: int = 0):
+        """bench helper: one bsq_align_batch_datums call on raw (pinned) host pointers followed by bsq_result_tuples on its result, which
+        the library serves from the still-resident batch.  Returns (device ms of both calls, bytes that came back)."""
+        from ._lib import BsqTuples
+        if not getattr(self, "two_chunks", False):
+            self.two_chunks = True
+            self._apply_flags()
+        res = C.POINTER(BsqResult)()
+        check(self.L.bsq_align_batch_datums(self.h, C.c_void_p(data_ptr), C.c_void_p(off_ptr), C.c_void_p(ids_ptr) if ids_ptr else None, n, C.byref(res)))
+        t = self.timing()
+        tp = C.POINTER(BsqTuples)()
+        try:
+            check(self.L.bsq_result_tuples(self.h, res, None, None, int(flags), C.byref(tp)))
+            ms = float(t.total) + float(tp.contents.device_ms)
+            nbytes = int(t.d2h_bytes) + int(tp.contents.n_bytes) + int(tp.contents.n_rows) * 36 + 8
+            self.L.bsq_tuples_free(tp)
+        finally:
+            self.L.bsq_result_free(res)
+        return ms, nbytes
+
+    def align_tuples_datums(self, data: np.ndarray, off: np.ndarray, ids: np.ndarray | None = None, flags: int = 0):
+        """Rows and their materialised columns in one go: bsq_align_batch_datums, then bsq_result_tuples served from the resident batch
+        (no re-upload).  Returns (AlignResult, Tuples)."""
+        from ._lib import BsqTuples
+        if not getattr(self, "two_chunks", False):
+            self.two_chunks = True
+            self._apply_flags()
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = len(off) - 1
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+        res = C.POINTER(BsqResult)()
+        check(self.L.bsq_align_batch_datums(self.h, ptr(data), ptr(off), ptr(ids) if ids is not None else None, n, C.byref(res)))
+        tp = C.POINTER(BsqTuples)()
+        try:
+            check(self.L.bsq_result_tuples(self.h, res, None, None, int(flags), C.byref(tp)))
+            t = tp.contents
+            nr = int(t.n_rows)
+            toff = np.ctypeslib.as_array(t.off, shape=(3 * nr + 1,)).copy()
+            ref_match = np.ctypeslib.as_array(t.ref_match, shape=(max(3 * nr, 1),))[:3 * nr].copy().reshape(nr, 3)
+            nb = int(t.n_bytes)
+            tdata = np.ctypeslib.as_array(t.bytes, shape=(max(nb, 1),))[:nb].copy()
+            tup = Tuples(toff, ref_match, tdata, float(t.device_ms))
+            self.L.bsq_tuples_free(tp)
+        except Exception:
+            self.L.bsq_result_free(res)
+            raise
+        return self._collect(res), tup
 
     def session_lrand48(self, state: int | None = None) -> int:
         """Read (state=None) or set the lrand48 state the library draws read ids from when a call passes none."""

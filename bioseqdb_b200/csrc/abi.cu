@@ -50,7 +50,10 @@ template <class T> struct DevBuf {
 struct Batch {
     uint64_t n = 0; uint32_t max_len = 0; uint64_t total_bases = 0;
     DevBuf<uint8_t> seqs; DevBuf<uint64_t> offs; DevBuf<int64_t> ids;
-    DevBuf<uint8_t> datums; DevBuf<uint64_t> datum_off, scan_tmp64;   // reads handed over as NUCLSEQ datum images (upload_datums)
+    DevBuf<uint8_t> datums; DevBuf<uint64_t> datum_off, scan_tmp64;
+    DevBuf<uint8_t> ascii;              // the reads as text (what to_text_palloc yields): the row materialisation reads query_subseq from it
+    uint64_t res_serial = 0, res_read_base = 0, res_row_base = 0, res_cig_base = 0;
+    DevBuf<uint64_t> tup_off, tup_tmp; DevBuf<uint32_t> tup_row_read, tup_nholes; DevBuf<int32_t> tup_rm; DevBuf<uint8_t> tup_bytes;   // row materialisation from the resident batch   // the result (and the place in it) this batch's rows went to   // reads handed over as NUCLSEQ datum images (upload_datums)
     DevBuf<Intv> intv; DevBuf<uint32_t> intv_cnt; uint32_t intv_cap = 0;
     DevBuf<Intv> seed_scratch; uint32_t list_cap = 0;
     DevBuf<SeedRec> raw, seeds; DevBuf<ChainTmp> ctmp; DevBuf<uint32_t> ord; DevBuf<ChainRec> chains; DevBuf<uint64_t> srt;
@@ -62,7 +65,7 @@ struct Batch {
     DevBuf<ExtMemo> ext_memo; DevBuf<uint8_t> ext_memo_key; DevBuf<uint32_t> ext_memo_perm, ext_memo_hist, ext_todo, chain_todo, fin_todo, seed_todo, seed_pk, seed_u32;   // thread-per-extension pre-pass (extend_plan.cu)
     DevBuf<uint32_t> ctl;  // [0..3] tickets, [4] overflow, [5] pool_top, [6] cigar_top, [8..23] counters (u64 x 8), [24] narrow_cnt, [25] wide_cnt, [26..27] tickets, [56] reads left for sw_extend, [57] reads left for the warp chain kernel, [58] for regs_finalize
     size_t device_bytes() const {
-        return seqs.bytes() + offs.bytes() + ids.bytes() + datums.bytes() + datum_off.bytes() + scan_tmp64.bytes() + intv.bytes() + intv_cnt.bytes() + seed_scratch.bytes() + raw.bytes() + seeds.bytes() + ctmp.bytes() +
+        return seqs.bytes() + offs.bytes() + ids.bytes() + ascii.bytes() + datums.bytes() + datum_off.bytes() + scan_tmp64.bytes() + intv.bytes() + intv_cnt.bytes() + seed_scratch.bytes() + raw.bytes() + seeds.bytes() + ctmp.bytes() +
                ord.bytes() + chains.bytes() + srt.bytes() + regs.bytes() + rows.bytes() + rows_compact.bytes() + rows_ext.bytes() + reg_cnt.bytes() + row_cnt.bytes() + row_off.bytes() +
                scan_tmp.bytes() + blocks.bytes() + cigar.bytes() + read_logtab.bytes() + ext_scratch.bytes() + fin_scratch.bytes() + narrow_z.bytes() +
                narrow_jobs.bytes() + wide_jobs.bytes() + ctl.bytes() + ext_memo.bytes() + ext_memo_key.bytes() + ext_memo_perm.bytes() + ext_memo_hist.bytes() + ext_todo.bytes() + chain_todo.bytes() + fin_todo.bytes() + seed_todo.bytes() + seed_pk.bytes() + seed_u32.bytes();
@@ -84,7 +87,7 @@ struct Batch {
         if (ev_ok) { for (auto& e : ev) cudaEventDestroy(e); ev_ok = false; }
         if (evx_ok) { for (auto& e : ev_x) cudaEventDestroy(e); evx_ok = false; }
         if (ext_aux_ok) { for (auto& s_ : ext_aux.st) cudaStreamDestroy(s_); for (auto& e : ext_aux.ev) cudaEventDestroy(e); ext_aux_ok = false; }
-        seqs.release(); offs.release(); ids.release(); datums.release(); datum_off.release(); scan_tmp64.release(); intv.release(); intv_cnt.release(); seed_scratch.release(); raw.release(); seeds.release();
+        seqs.release(); offs.release(); ids.release(); ascii.release(); tup_off.release(); tup_tmp.release(); tup_row_read.release(); tup_nholes.release(); tup_rm.release(); tup_bytes.release(); datums.release(); datum_off.release(); scan_tmp64.release(); intv.release(); intv_cnt.release(); seed_scratch.release(); raw.release(); seeds.release();
         ctmp.release(); ord.release(); chains.release(); srt.release(); regs.release(); rows.release(); rows_compact.release(); rows_ext.release(); reg_cnt.release();
         row_cnt.release(); row_off.release(); scan_tmp.release(); blocks.release(); cigar.release(); ext_scratch.release(); fin_scratch.release();
         ctl.release(); narrow_z.release(); narrow_jobs.release(); wide_jobs.release(); read_logtab.release();
@@ -181,7 +184,7 @@ int bsq_index_set_opts(bsq_index* h, const bsq_opts* o) {
 int bsq_index_set_flags(bsq_index* h, uint32_t flags) {
     BSQ_ENTRY();
     if (!h) { bsq_set_error("null index"); return BSQ_ERR; }
-    if (flags & ~BSQ_FLAG_ROWS_EXT) { bsq_set_error("unknown flag bits %#x", flags & ~BSQ_FLAG_ROWS_EXT); return BSQ_ERR; }
+    if (flags & ~(BSQ_FLAG_ROWS_EXT | BSQ_FLAG_TWO_CHUNKS)) { bsq_set_error("unknown flag bits %#x", flags & ~(BSQ_FLAG_ROWS_EXT | BSQ_FLAG_TWO_CHUNKS)); return BSQ_ERR; }
     h->flags = flags;
     return BSQ_OK;
 }
@@ -495,21 +498,22 @@ __global__ void k_datum_lens(const uint8_t* bytes, const uint64_t* doff, uint64_
     if ((threadIdx.x & 31) == 0 && mx) atomicMax(stats, mx);
     if (blockIdx.x == 0 && threadIdx.x == 0) lens[n] = 0;
 }
-__global__ void k_datum_unpack(const uint8_t* bytes, const uint64_t* doff, uint64_t base, uint64_t n, const uint64_t* offs, uint8_t* seqs) {
+__global__ void k_datum_unpack(const uint8_t* bytes, const uint64_t* doff, uint64_t base, uint64_t n, const uint64_t* offs, uint8_t* seqs, uint8_t* ascii) {
     const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     for (uint64_t r = gw; r < n; r += nw) {
         const uint8_t* d = bytes + (doff[r] - base);
         uint32_t n_holes, len; memcpy(&n_holes, d + 4, 4); memcpy(&len, d + 8, 4);
         const uint8_t* pac = d + 12 + (size_t)n_holes * 16;
-        uint8_t* q = seqs + offs[r];
-        for (uint32_t i = lane; i < len; i += 32) q[i] = (pac[i >> 2] >> ((~i & 3u) << 1)) & 3u;
+        uint8_t* q = seqs + offs[r]; uint8_t* a = ascii + offs[r];
+        for (uint32_t i = lane; i < len; i += 32) { const uint32_t c = (pac[i >> 2] >> ((~i & 3u) << 1)) & 3u; q[i] = (uint8_t)c; a[i] = (uint8_t)"ACGT"[c]; }
         __syncwarp();
-        for (uint32_t k = 0; k < n_holes; ++k) {
+        for (uint32_t k = 0; k < n_holes; ++k) {   // inplace_to_text (sequence.cpp:71-81): holes in order, later ones overwrite
             int64_t ho; int32_t hl; memcpy(&ho, d + 12 + (size_t)k * 16, 8); memcpy(&hl, d + 12 + (size_t)k * 16 + 8, 4);
-            for (int64_t i = ho + lane; i < ho + hl && i < (int64_t)len; i += 32) if (i >= 0) q[i] = 4;
+            const uint8_t amb = d[12 + (size_t)k * 16 + 12];
+            for (int64_t i = ho + lane; i < ho + hl && i < (int64_t)len; i += 32) if (i >= 0) { q[i] = 4; a[i] = amb; }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
@@ -602,7 +606,7 @@ uint32_t rseq_cap_for(const bsq_index* h, uint32_t max_len) { return max_len + 4
 bool needs_seed_sw(uint32_t len) { return len > 0 && 5.5f * log((double)len) <= 0.05f * (double)len; }
 
 int upload_reads(bsq_index* h, Batch& b, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, uint64_t id_first = 0) {
-    b.resident = false; b.aligned = false;
+    b.resident = false; b.aligned = false; b.res_serial = 0;
     if (n >= 0x7fffffffull) { bsq_set_error("batch too large"); return BSQ_ERR; }
     uint32_t max_len = 0;
     for (uint64_t i = 0; i < n; ++i) {
@@ -631,7 +635,11 @@ int upload_reads(bsq_index* h, Batch& b, const char* seqs, const uint64_t* offs,
         if (ids) CUDA_CHECK(cudaMemcpyAsync(b.ids.p, ids, n * 8, cudaMemcpyHostToDevice, b.st));
         else { k_lrand48_ids<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8), 256, 0, b.st>>>(h->lrand_state, id_first, n, b.ids.p); ++h->timing.launches; }
     } else CUDA_CHECK(cudaMemsetAsync(b.offs.p, 0, 8, b.st));
-    if (total) { k_to_nt4<<<(unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 16), 256, 0, b.st>>>(b.seqs.p, total); ++h->timing.launches; }
+    if (total) {
+        CUDA_CHECK(b.ascii.ensure(total + 64));
+        CUDA_CHECK(cudaMemcpyAsync(b.ascii.p, b.seqs.p, total, cudaMemcpyDeviceToDevice, b.st));   // the text stays for the row materialisation
+        k_to_nt4<<<(unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 16), 256, 0, b.st>>>(b.seqs.p, total); ++h->timing.launches;
+    }
     if (n && offs[0]) { k_rebase_offs<<<(unsigned)std::min<uint64_t>((n + 256) / 256, 148 * 8), 256, 0, b.st>>>(b.offs.p, n + 1, offs[0]); ++h->timing.launches; }
     h->timing.h2d_bytes += total + (n + 1) * 8 + (ids ? n * 8 : 0);
     b.resident = true;
@@ -642,7 +650,7 @@ int upload_reads(bsq_index* h, Batch& b, const char* seqs, const uint64_t* offs,
 // base on the wire instead of 8.  The host reads the headers once (longest read, total bases: the pools are sized from them); the
 // images are unpacked on the device.
 int upload_datums(bsq_index* h, Batch& b, const uint8_t* bytes, const uint64_t* doff, const int64_t* ids, uint64_t n, uint64_t id_first = 0) {
-    b.resident = false; b.aligned = false;
+    b.resident = false; b.aligned = false; b.res_serial = 0;
     if (n >= 0x7fffffffull) { bsq_set_error("batch too large"); return BSQ_ERR; }
     if (n && doff[n] < doff[0]) { bsq_set_error("datum offsets must be non-decreasing"); return BSQ_ERR; }
     const uint64_t nbytes = n ? doff[n] - doff[0] : 0;
@@ -676,8 +684,8 @@ int upload_datums(bsq_index* h, Batch& b, const uint8_t* bytes, const uint64_t* 
         CUDA_CHECK(cudaMemcpy(b.read_logtab.p, tab.data(), (max_len + 1) * sizeof(double), cudaMemcpyHostToDevice));
         b.read_logtab_n = max_len + 1;
     }
-    CUDA_CHECK(b.seqs.ensure(total + 64));
-    if (n) { k_datum_unpack<<<(unsigned)std::min<uint64_t>((n + 7) / 8, 148 * 16), 256, 0, b.st>>>(b.datums.p, b.datum_off.p, doff[0], n, b.offs.p, b.seqs.p); ++h->timing.launches; }
+    CUDA_CHECK(b.seqs.ensure(total + 64)); CUDA_CHECK(b.ascii.ensure(total + 64));
+    if (n) { k_datum_unpack<<<(unsigned)std::min<uint64_t>((n + 7) / 8, 148 * 16), 256, 0, b.st>>>(b.datums.p, b.datum_off.p, doff[0], n, b.offs.p, b.seqs.p, b.ascii.p); ++h->timing.launches; }
     h->timing.h2d_bytes += nbytes + (n + 1) * 8 + (ids ? n * 8 : 0);
     b.resident = true;
     return BSQ_OK;
@@ -958,7 +966,9 @@ int approx_mapq(const bsq_index* h, const bsq_row& a, const bsq_row_ext& x) {
 // A result lives in ONE pinned host block, laid out by capacity: row_off (u64 x (n+1)) | rows (row_cap + 1) |
 // cigar (cig_cap + 1) | the device's u32 row offsets (n + 1).  Freed blocks are cached process-wide so that
 // steady-state calls do not pay cudaHostAlloc.
-struct ResultImpl { bsq_result pub; void* block; size_t bytes; uint64_t row_cap, cig_cap; uint32_t* o32; bsq_row_ext* ext; };
+struct ResultImpl { bsq_result pub; void* block; size_t bytes; uint64_t row_cap, cig_cap; uint32_t* o32; bsq_row_ext* ext; uint64_t serial; };
+// results handed out and not yet freed: bsq_result_tuples recognises its own results (a caller may also pass a bsq_result it assembled)
+std::mutex g_live_mu; std::vector<const ResultImpl*> g_live; uint64_t g_result_serial = 0;
 struct PinnedCache { void* ptr[4]; size_t bytes[4]; };
 PinnedCache g_pinned = {{nullptr, nullptr, nullptr, nullptr}, {0, 0, 0, 0}};
 std::mutex g_pinned_mu;
@@ -1006,10 +1016,15 @@ ResultImpl* result_new(uint64_t n, uint64_t row_cap, uint64_t cig_cap, bool with
     R->o32 = reinterpret_cast<uint32_t*>(static_cast<char*>(block) + off_o32);
     R->ext = with_ext ? reinterpret_cast<bsq_row_ext*>(static_cast<char*>(block) + off_ext) : nullptr;
     R->pub.rows_ext = R->ext;
+    { std::lock_guard<std::mutex> lk(g_live_mu); R->serial = ++g_result_serial; g_live.push_back(R); }
     return R;
 }
 
-void result_delete(ResultImpl* R) { if (R) { pinned_put(R->block, R->bytes); delete R; } }
+void result_delete(ResultImpl* R) {
+    if (!R) return;
+    { std::lock_guard<std::mutex> lk(g_live_mu); for (size_t i = 0; i < g_live.size(); ++i) if (g_live[i] == R) { g_live[i] = g_live.back(); g_live.pop_back(); break; } }
+    pinned_put(R->block, R->bytes); delete R;
+}
 
 // Compacts the aligned batch's rows on the device (+ MAPQ) and starts the copies into the result: the batch's reads are
 // reads [read_base, read_base + b.n) of the result, its rows go to row_base, its CIGAR words to cig_base.
@@ -1019,6 +1034,7 @@ int download_enqueue(bsq_index* h, Batch& b, ResultImpl* R, uint64_t read_base, 
     const uint64_t total_rows = b.out_rows; const uint32_t cig_top = b.out_cig;
     if (row_base + total_rows > R->row_cap || cig_base + cig_top > R->cig_cap || cig_base + cig_top > 0xffffffffull) { bsq_set_error("result block too small"); return BSQ_ERR; }
     cudaStream_t st = b.st;
+    b.res_serial = R->serial; b.res_read_base = read_base; b.res_row_base = row_base; b.res_cig_base = cig_base;
     CUDA_CHECK(cudaMemcpyAsync(R->o32 + read_base, b.row_off.p, n * 4, cudaMemcpyDeviceToHost, st));
     if (total_rows) CUDA_CHECK(cudaMemcpyAsync(R->pub.rows + row_base, b.rows_compact.p, total_rows * sizeof(bsq_row), cudaMemcpyDeviceToHost, st));
     if (total_rows && R->ext) CUDA_CHECK(cudaMemcpyAsync(R->ext + row_base, b.rows_ext.p, total_rows * sizeof(bsq_row_ext), cudaMemcpyDeviceToHost, st));
@@ -1069,7 +1085,8 @@ int download_result(bsq_index* h, Batch& b, bsq_result** out) {
 // out): one pass 35.2 ms, 2 chunks 31.8, 4 chunks 35.9 (a chunk pays ~40 kernel tails and runs on half-empty persistent grids, so few
 // large chunks win once the copies are small).  BSQ_CHUNK_READS overrides it.
 constexpr uint64_t CHUNK_MIN = 1u << 16, CHUNK_MAX = 1u << 20;
-uint64_t chunk_reads(uint64_t n) {
+uint64_t chunk_reads(uint64_t n, bool two = false) {
+    if (two) return std::max((n + 1) / 2, CHUNK_MIN);
     static long long env = -1;
     if (env < 0) { env = 0; if (const char* e = getenv("BSQ_CHUNK_READS")) { const long long x = atoll(e); if (x >= 1024) env = x; } }
     if (env > 0) return (uint64_t)env;
@@ -1102,7 +1119,7 @@ int align_chunked(bsq_index* h, const ReadSrc& S, uint64_t n, bsq_result** out, 
             for (const char* q = fr; *q;) { char* e; const double f = strtod(q, &e); if (e == q) break; acc += f; starts.push_back(std::min<uint64_t>(n, (uint64_t)(acc * (double)n))); q = *e ? e + 1 : e; }
             if (starts.back() != n) starts.push_back(n);
         } else {
-            const uint64_t CHUNK_READS = chunk_reads(n);
+            const uint64_t CHUNK_READS = chunk_reads(n, (h->flags & BSQ_FLAG_TWO_CHUNKS) != 0);
             for (uint64_t s0 = 0; s0 < n; s0 += CHUNK_READS) starts.push_back(s0);
             starts.push_back(n);
         }
@@ -1206,7 +1223,7 @@ static int align_batch_src(bsq_index* h, const ReadSrc& S, uint64_t n, bsq_resul
     bsq_timing& T = h->timing;
     T.launches = 0; T.h2d_bytes = T.d2h_bytes = 0; T.h2d = T.d2h = 0; T.notes = 0;
     int rc = BSQ_OK;
-    bool chunked = n >= 2 * CHUNK_MIN && n > chunk_reads(n) && h->meta.built && !getenv("BSQ_NO_CHUNKS");
+    bool chunked = n >= 2 * CHUNK_MIN && n > chunk_reads(n, (h->flags & BSQ_FLAG_TWO_CHUNKS) != 0) && h->meta.built && !getenv("BSQ_NO_CHUNKS");
     cudaEventRecord(e0, h->stream);
     if (chunked) {
         // two lanes, copies overlapped with compute; the stage times are sums over chunks of each lane's stream time
@@ -1257,13 +1274,139 @@ int bsq_session_lrand48(bsq_index* h, int set, uint64_t* state) {
 }
 
 // ---- row materialisation
-struct TuplesImpl { bsq_tuples pub; void* host = nullptr; size_t host_bytes = 0; };
+
+// row -> read index of a batch from its exclusive row offsets (thread per read)
+static __global__ void k_row_read(const uint32_t* row_off, const uint32_t* row_cnt, uint32_t n_reads, uint32_t* row_read) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x)
+        for (uint32_t k = 0; k < row_cnt[r]; ++k) row_read[row_off[r] + k] = r;
+}
+static __global__ void k_add_u64(uint64_t* v, uint64_t n, uint64_t add) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) v[i] += add;
+}
+
+static void index_holes_sorted(const bsq_index* h, uint32_t flags, std::vector<TupleHole>& holes, std::vector<int64_t>& maxend) {
+    holes.resize(h->holes.size());
+    for (size_t i = 0; i < holes.size(); ++i) {
+        // reference behaviour: offsets as stored in the row's datum, i.e. relative to its own row (bwa.cpp:100-104); the fix-up rebases them
+        const int64_t base = (flags & BSQ_TUPLES_FIX_HOLE_OFFSETS) ? h->ann_offset[h->hole_ann[i]] : 0;
+        holes[i].offset = h->holes[i].offset + base; holes[i].end = holes[i].offset + h->holes[i].len; holes[i].idx = (uint32_t)i; holes[i].amb = (uint8_t)h->holes[i].amb;
+    }
+    std::stable_sort(holes.begin(), holes.end(), [](const TupleHole& a, const TupleHole& b) { return a.offset < b.offset; });
+    maxend.resize(holes.size());
+    for (size_t i = 0; i < holes.size(); ++i) maxend[i] = i ? std::max(maxend[i - 1], holes[i].end) : holes[i].end;
+}
+
+struct TuplesImpl { bsq_tuples pub; void* host = nullptr; size_t host_bytes = 0; bool cached = false; };
+
+// Row materialisation straight from the batch(es) that produced `R` and still sit in HBM: rows in read order (rows_compact), CIGAR
+// pool, the reads' text -- nothing is uploaded again.  Returns 1 when the result is not (or no longer) resident: the caller then
+// takes the general path that uploads rows, CIGARs and reads.
+static int tuples_resident(bsq_index* h, const ResultImpl* R, uint32_t flags, bsq_tuples** out) {
+    Batch* lanes[2] = {&h->batch, &h->batch2};
+    Batch* piece[2]; int np = 0;
+    uint64_t covered = 0;
+    for (Batch* b : lanes) if (b->aligned && b->res_serial == R->serial && b->n) piece[np++] = b;
+    if (np == 2 && piece[0]->res_read_base > piece[1]->res_read_base) std::swap(piece[0], piece[1]);
+    for (int k = 0; k < np; ++k) { if (piece[k]->res_read_base != covered) return 1; covered += piece[k]->n; }
+    if (np == 0 || covered != R->pub.n_reads) return 1;
+    const uint64_t n_rows = R->pub.row_off[R->pub.n_reads];
+    if (n_rows == 0) return 1;
+    std::vector<TupleHole> holes; std::vector<int64_t> maxend;
+    index_holes_sorted(h, flags, holes, maxend);
+    TupleHole* d_holes = nullptr; int64_t* d_maxend = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    TuplesImpl* T = new TuplesImpl();
+    T->pub.n_rows = n_rows; T->pub.n_bytes = 0; T->pub.device_ms = 0.f;
+    int rc = BSQ_ERR;
+    do {
+#define TR(x) if ((x) != cudaSuccess) { bsq_set_error("bsq_result_tuples: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        TR(cudaEventCreate(&e0)); TR(cudaEventCreate(&e1));
+        TR(cudaMalloc(&d_holes, (holes.size() + 1) * sizeof(TupleHole))); TR(cudaMalloc(&d_maxend, (holes.size() + 1) * 8));
+        cudaStream_t s0 = piece[0]->st;
+        cudaEventRecord(e0, s0);
+        if (!holes.empty()) {
+            TR(cudaMemcpyAsync(d_holes, holes.data(), holes.size() * sizeof(TupleHole), cudaMemcpyHostToDevice, s0));
+            TR(cudaMemcpyAsync(d_maxend, maxend.data(), holes.size() * 8, cudaMemcpyHostToDevice, s0));
+        }
+        TR(cudaStreamSynchronize(s0));
+        TupleParams P[2]; uint64_t nb[2] = {0, 0}; bool bad = false;
+        for (int k = 0; k < np && !bad; ++k) {       // sizes of every piece (the pieces run on their own lanes' streams)
+            Batch& b = *piece[k]; const uint64_t nr = b.out_rows;
+            if (cudaSuccess != b.tup_off.ensure(3 * nr + 2) || cudaSuccess != b.tup_tmp.ensure(tuple_scan_tmp_elems(nr)) || cudaSuccess != b.tup_row_read.ensure(nr + 1) ||
+                cudaSuccess != b.tup_nholes.ensure(2 * nr + 2) || cudaSuccess != b.tup_rm.ensure(3 * nr + 3)) { bsq_set_error("bsq_result_tuples: out of device memory"); bad = true; break; }
+            TupleParams& q = P[k];
+            q.rows = b.rows_compact.p; q.n_rows = nr; q.row_read = b.tup_row_read.p; q.cigar = b.cigar.p; q.seqs = b.ascii.p; q.offs = b.offs.p;
+            q.pac = h->d_pac; q.l_pac = h->meta.l_pac; q.ann_offset = h->d_ann_offset;
+            q.holes = d_holes; q.hole_maxend = d_maxend; q.n_holes = (uint32_t)holes.size();
+            q.nholes = b.tup_nholes.p; q.off = b.tup_off.p; q.ref_match = b.tup_rm.p; q.bytes = nullptr; q.fix_reverse = (flags & BSQ_TUPLES_FIX_REVERSE) != 0;
+            if (nr) {
+                k_row_read<<<(unsigned)std::min<uint64_t>((b.n + 255) / 256, 148 * 8), 256, 0, b.st>>>(b.row_off.p, b.row_cnt.p, (uint32_t)b.n, b.tup_row_read.p); ++h->timing.launches;
+                cudaMemsetAsync(b.tup_off.p, 0, (3 * nr + 1) * 8, b.st);
+                launch_tuple_sizes(q, b.tup_tmp.p, b.st, &h->timing.launches);
+                cudaMemcpyAsync(b.ctl_host + 14, b.tup_off.p + 3 * nr, 8, cudaMemcpyDeviceToHost, b.st);
+            }
+        }
+        if (bad) break;
+        for (int k = 0; k < np; ++k) { TR(cudaStreamSynchronize(piece[k]->st)); if (piece[k]->out_rows) memcpy(&nb[k], piece[k]->ctl_host + 14, 8); }
+        const uint64_t n_bytes = nb[0] + nb[1];
+        // one pinned block (from the library's cache): off | ref_match | bytes
+        const size_t off_b = (3 * n_rows + 1) * 8, rm_b = (n_rows * 12 + 7) & ~(size_t)7;
+        size_t got = 0;
+        T->host = pinned_get(off_b + rm_b + n_bytes + 64, &got);
+        if (!T->host) { bsq_set_error("cannot allocate pinned host memory for the tuples"); break; }
+        T->host_bytes = got; T->cached = true;
+        T->pub.off = reinterpret_cast<uint64_t*>(T->host);
+        T->pub.ref_match = reinterpret_cast<int32_t*>(static_cast<char*>(T->host) + off_b);
+        T->pub.bytes = reinterpret_cast<uint8_t*>(static_cast<char*>(T->host) + off_b + rm_b);
+        T->pub.n_bytes = n_bytes;
+        uint64_t row_base = 0, byte_base = 0;
+        for (int k = 0; k < np && !bad; ++k) {
+            Batch& b = *piece[k]; const uint64_t nr = b.out_rows;
+            if (nr) {
+                if (cudaSuccess != b.tup_bytes.ensure(nb[k] + 64)) { bsq_set_error("bsq_result_tuples: out of device memory"); bad = true; break; }
+                cudaMemsetAsync(b.tup_bytes.p, 0, nb[k] + 64, b.st);
+                P[k].bytes = b.tup_bytes.p;
+                launch_tuple_fill(P[k], b.st, &h->timing.launches);
+                if (byte_base) { k_add_u64<<<(unsigned)std::min<uint64_t>((3 * nr + 256) / 256, 148 * 8), 256, 0, b.st>>>(b.tup_off.p, 3 * nr + 1, byte_base); ++h->timing.launches; }
+                cudaMemcpyAsync(T->pub.off + 3 * row_base, b.tup_off.p, (3 * nr + 1) * 8, cudaMemcpyDeviceToHost, b.st);
+                cudaMemcpyAsync(T->pub.ref_match + 3 * row_base, b.tup_rm.p, nr * 12, cudaMemcpyDeviceToHost, b.st);
+                cudaMemcpyAsync(T->pub.bytes + byte_base, b.tup_bytes.p, nb[k], cudaMemcpyDeviceToHost, b.st);
+            }
+            row_base += nr; byte_base += nb[k];
+        }
+        if (bad) break;
+        for (int k = 1; k < np; ++k) TR(cudaStreamSynchronize(piece[k]->st));
+        cudaEventRecord(e1, s0);
+        TR(cudaStreamSynchronize(s0)); TR(cudaGetLastError());
+        T->pub.off[3 * n_rows] = n_bytes;
+        cudaEventElapsedTime(&T->pub.device_ms, e0, e1);
+        rc = BSQ_OK;
+#undef TR
+    } while (0);
+    cudaFree(d_holes); cudaFree(d_maxend);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (rc != BSQ_OK) { if (T->host) pinned_put(T->host, T->host_bytes); delete T; return BSQ_ERR; }
+    *out = &T->pub;
+    return BSQ_OK;
+}
 
 int bsq_result_tuples(bsq_index* h, const bsq_result* res, const char* seqs, const uint64_t* offs, uint32_t flags, bsq_tuples** out) {
     BSQ_ENTRY();
-    if (!h || !res || !offs || !out) { bsq_set_error("null argument"); return BSQ_ERR; }
-    if (!h->meta.built && res->n_reads && res->row_off[res->n_reads]) { bsq_set_error("index not built"); return BSQ_ERR; }
+    if (!h || !res || !out) { bsq_set_error("null argument"); return BSQ_ERR; }
     if (h->replica_pending) { bsq_set_error("replica without host state: call bsq_index_replica_finish after filling its arrays (the hole overlay of ref_subseq lives on the host)"); return BSQ_ERR; }
+    {   // a result of this library whose batch is still in HBM needs no upload at all
+        const ResultImpl* mine = nullptr;
+        { std::lock_guard<std::mutex> lk(g_live_mu); for (const ResultImpl* r : g_live) if (&r->pub == res) { mine = r; break; } }
+        static const bool no_res = getenv("BSQ_TUPLES_NO_RESIDENT") != nullptr;
+        if (mine && h->meta.built && !no_res) {
+            if (cudaSetDevice(h->device) != cudaSuccess) { bsq_set_error("cudaSetDevice failed"); return BSQ_ERR; }
+            const int rc = tuples_resident(h, mine, flags, out);
+            if (rc != 1) return rc;
+        }
+    }
+    if (!offs) { bsq_set_error("null argument"); return BSQ_ERR; }
+    if (!h->meta.built && res->n_reads && res->row_off[res->n_reads]) { bsq_set_error("index not built"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
     const uint64_t n_reads = res->n_reads, n_rows = n_reads ? res->row_off[n_reads] : 0;
     TuplesImpl* T = new TuplesImpl();
@@ -1281,15 +1424,8 @@ int bsq_result_tuples(bsq_index* h, const bsq_result* res, const char* seqs, con
     // host-side preparation: read index of every row; the index's holes sorted by offset with the running maximum of their ends
     std::vector<uint32_t> row_read(n_rows);
     for (uint64_t r = 0; r < n_reads; ++r) for (uint64_t k = res->row_off[r]; k < res->row_off[r + 1]; ++k) row_read[k] = (uint32_t)r;
-    std::vector<TupleHole> holes(h->holes.size());
-    for (size_t i = 0; i < holes.size(); ++i) {
-        // reference behaviour: offsets as stored in the row's datum, i.e. relative to its own row (bwa.cpp:100-104); the fix-up rebases them
-        const int64_t base = (flags & BSQ_TUPLES_FIX_HOLE_OFFSETS) ? h->ann_offset[h->hole_ann[i]] : 0;
-        holes[i].offset = h->holes[i].offset + base; holes[i].end = holes[i].offset + h->holes[i].len; holes[i].idx = (uint32_t)i; holes[i].amb = (uint8_t)h->holes[i].amb;
-    }
-    std::stable_sort(holes.begin(), holes.end(), [](const TupleHole& a, const TupleHole& b) { return a.offset < b.offset; });
-    std::vector<int64_t> maxend(holes.size());
-    for (size_t i = 0; i < holes.size(); ++i) maxend[i] = i ? std::max(maxend[i - 1], holes[i].end) : holes[i].end;
+    std::vector<TupleHole> holes; std::vector<int64_t> maxend;
+    index_holes_sorted(h, flags, holes, maxend);
     const uint64_t total = offs[n_reads] - offs[0];
     RowPub* d_rows = nullptr; uint32_t *d_row_read = nullptr, *d_cigar = nullptr, *d_nholes = nullptr; uint8_t *d_seqs = nullptr, *d_bytes = nullptr;
     uint64_t *d_offs = nullptr, *d_off = nullptr, *d_tmp = nullptr; TupleHole* d_holes = nullptr; int64_t* d_maxend = nullptr; int32_t* d_rm = nullptr;
@@ -1357,7 +1493,7 @@ int bsq_result_tuples(bsq_index* h, const bsq_result* res, const char* seqs, con
 void bsq_tuples_free(bsq_tuples* t) {
     if (!t) return;
     TuplesImpl* T = reinterpret_cast<TuplesImpl*>(t);
-    if (T->host) cudaFreeHost(T->host);
+    if (T->host) { if (T->cached) pinned_put(T->host, T->host_bytes); else cudaFreeHost(T->host); }
     delete T;
 }
 
@@ -1445,9 +1581,7 @@ void bsq_nuclseqs_free(bsq_nuclseqs* s) {
 
 void bsq_result_free(bsq_result* r) {
     if (!r) return;
-    ResultImpl* R = reinterpret_cast<ResultImpl*>(r);   // pub is the first member
-    pinned_put(R->block, R->bytes);
-    delete R;
+    result_delete(reinterpret_cast<ResultImpl*>(r));   // pub is the first member
 }
 
 int bsq_last_timing(const bsq_index* h, bsq_timing* t) {

@@ -1000,7 +1000,9 @@ int launch_seed_thread(const SeedParams& p, const DevIndex& ix, const DevOpts& o
         seed_calls<uint64_t><<<nb * sms, ST_THREADS, smem, st>>>(p, ix, o, ticket, words);
         seed_last<uint64_t><<<last_blocks, ST_THREADS, smem, st>>>(p, ix, o, words);
     } else {
-        const int nb = cached_blocks_per_sm(seed_calls<uint32_t>, ST_THREADS, smem);
+        int nb = cached_blocks_per_sm(seed_calls<uint32_t>, ST_THREADS, smem);
+        static const int cap = getenv("BSQ_SEED_CTAS") ? atoi(getenv("BSQ_SEED_CTAS")) : 0;
+        if (cap > 0 && cap < nb) nb = cap;
         seed_calls<uint32_t><<<nb * sms, ST_THREADS, smem, st>>>(p, ix, o, ticket, words);
         seed_last<uint32_t><<<last_blocks, ST_THREADS, smem, st>>>(p, ix, o, words);
     }

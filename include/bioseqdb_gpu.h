@@ -84,6 +84,8 @@ void bsq_opts_init(bsq_opts* o);
 bsq_index* bsq_index_new(const bsq_opts* o, int device);
 int bsq_index_set_opts(bsq_index* h, const bsq_opts* o);
 #define BSQ_FLAG_ROWS_EXT 1u   /* results also carry bsq_row_ext records */
+#define BSQ_FLAG_TWO_CHUNKS 2u /* bsq_align_batch* cuts a batch into at most two chunks, so that the whole batch is still in HBM when
+                                * bsq_result_tuples is called on its result (which then uploads nothing) */
 int bsq_index_set_flags(bsq_index* h, uint32_t flags);
 int bsq_index_add_ref(bsq_index* h, int64_t id, const uint8_t* pac, uint32_t len, const bsq_hole* holes, uint32_t n_holes);
 /* n reference rows in one call: NUCLSEQ datum images as PostgreSQL stores them (sequence.h:18-38), image i at bytes + off[i] --
@@ -111,7 +113,9 @@ int bsq_last_timing(const bsq_index* h, bsq_timing* t);
  * For row i: bytes + off[3i] = NUCLSEQ datum image of ref_subseq (varlena length word, holes_num, len, hole records, 2-bit codes;
  * 8-byte aligned, its true size is in the length word), bytes + off[3i+1] = image of query_subseq, bytes + off[3i+2] = the
  * NUL-terminated CIGAR string; ref_match[3i .. 3i+2] = ref_match_begin, ref_match_end, ref_match_len.
- * seqs/offs: the reads `res` was computed from (ASCII, as given to bsq_align_batch). */
+ * seqs/offs: the reads `res` was computed from (ASCII, as given to bsq_align_batch).  When `res` is the result of the handle's latest
+ * bsq_align_batch* call and that batch is still resident (one or two chunks), rows, CIGARs and reads are taken from HBM: nothing is
+ * uploaded and seqs / offs may be NULL. */
 typedef struct bsq_tuples {
     uint64_t n_rows;
     uint64_t* off;       /* 3 n_rows + 1 */

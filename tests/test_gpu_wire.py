@@ -89,3 +89,29 @@ def test_public_rows_without_extension(gpu_lib):
     _same(full, slim, pub)
     assert not slim.rows["hash"].any() and full.rows["hash"].any()
     assert int(t.d2h_bytes) < 2000 * 4 + 16 + len(slim.rows) * 64 + len(slim.cigar) * 4 + 64
+
+
+def test_tuples_from_resident_batch(gpu_lib):
+    """bsq_result_tuples on the library's own result of a batch that is still in HBM uploads nothing; its datums, CIGAR
+    strings and ref_match_* must equal the general path's (rows, CIGARs and reads uploaded again), for one-pass and two-chunk batches,
+    holes in the reference and in the reads included."""
+    rows = [r.tobytes() for r in synth.reference_rows([250_001, 150_003], seed=141)]
+    rows[0] = rows[0][:5000] + b"N" * 30 + rows[0][5030:90_000] + b"RRY" + rows[0][90_003:]
+    _, gpu = build_pair(rows, O.sql_default_opts(2))
+    clean = [np.frombuffer(r.replace(b"N", b"A").replace(b"R", b"G").replace(b"Y", b"C"), dtype=np.uint8) for r in rows]
+    for n in (3000, 2 * 65536 + 777):
+        seqs, offs, _ = synth.simulate_reads(clean, n, 100, seed=142 + n, n_frac=0.003)
+        extra = [rows[0][4950:5100], rows[0][89_950:90_100]]      # reads over the reference's holes (their own N / R / Y become holes of query_subseq)
+        es, eo = read_arrays(extra)
+        seqs = np.concatenate([seqs, es]); offs = np.concatenate([offs, eo[1:] + offs[-1]])
+        ids = synth.lrand48_ids_fast(len(offs) - 1)
+        data, off, _ = nuclseq_image_block(seqs, offs)
+        res, tup = gpu.align_tuples_datums(data, off, ids)
+        ref = gpu.tuples(res, seqs, offs)                          # general path: host result, everything uploaded
+        assert len(res.rows) > n * 0.9
+        assert np.array_equal(tup.off, ref.off) and np.array_equal(tup.ref_match, ref.ref_match)
+        assert np.array_equal(tup.data, ref.data)
+        for flags in (1, 3):
+            res2, tup2 = gpu.align_tuples_datums(data, off, ids, flags)
+            ref2 = gpu.tuples(res2, seqs, offs, flags)
+            assert np.array_equal(tup2.off, ref2.off) and np.array_equal(tup2.data, ref2.data) and np.array_equal(tup2.ref_match, ref2.ref_match)

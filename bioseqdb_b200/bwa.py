@@ -471,6 +471,51 @@ class BwaIndex:
         return bytes(out)
 
 
+class MultiBwaIndex:
+    """One process, one thread, several GPUs (bsq_multi_*): the built index `ix` replicated to `devices` (devices[0] = ix.device), a
+    batch split into contiguous blocks of reads, one result in read order.  Options / flags / the lrand48 session are those of `ix`."""
+
+    def __init__(self, ix: BwaIndex, devices):
+        self.ix = ix
+        self.L = ix.L
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        self.m = self.L.bsq_multi_new(ix.h, ptr(devs), len(devs))
+        if not self.m:
+            raise _lib.BsqError(self.L.bsq_last_error().decode())
+        self.devices = list(int(d) for d in devs)
+
+    def close(self):
+        if getattr(self, "m", None):
+            self.L.bsq_multi_free(self.m)
+            self.m = None
+
+    def __del__(self):
+        self.close()
+
+    def align_batch(self, seqs, offs, ids=None) -> AlignResult:
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+        res = C.POINTER(BsqResult)()
+        check(self.L.bsq_multi_align_batch(self.m, ptr(seqs), ptr(offs), ptr(ids) if ids is not None else None, len(offs) - 1, C.byref(res)))
+        return self.ix._collect(res)
+
+    def align_batch_datums(self, data, off, ids=None) -> AlignResult:
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+        res = C.POINTER(BsqResult)()
+        check(self.L.bsq_multi_align_batch_datums(self.m, ptr(data), ptr(off), ptr(ids) if ids is not None else None, len(off) - 1, C.byref(res)))
+        return self.ix._collect(res)
+
+    def timing(self) -> BsqTiming:
+        t = BsqTiming()
+        check(self.L.bsq_multi_last_timing(self.m, C.byref(t)))
+        return t
+
+
 def _i32(v: int) -> int:
     v &= 0xFFFFFFFF
     return v - (1 << 32) if v & 0x80000000 else v

@@ -649,7 +649,7 @@ int upload_reads(bsq_index* h, Batch& b, const char* seqs, const uint64_t* offs,
 // The same batch handed over as NUCLSEQ datum images (image i at bytes + doff[i], as PostgreSQL stores the query rows): 2 bits per
 // base on the wire instead of 8.  The host reads the headers once (longest read, total bases: the pools are sized from them); the
 // images are unpacked on the device.
-int upload_datums(bsq_index* h, Batch& b, const uint8_t* bytes, const uint64_t* doff, const int64_t* ids, uint64_t n, uint64_t id_first = 0) {
+int upload_datums_begin(bsq_index* h, Batch& b, const uint8_t* bytes, const uint64_t* doff, const int64_t* ids, uint64_t n, uint64_t id_first) {
     b.resident = false; b.aligned = false; b.res_serial = 0;
     if (n >= 0x7fffffffull) { bsq_set_error("batch too large"); return BSQ_ERR; }
     if (n && doff[n] < doff[0]) { bsq_set_error("datum offsets must be non-decreasing"); return BSQ_ERR; }
@@ -658,7 +658,6 @@ int upload_datums(bsq_index* h, Batch& b, const uint8_t* bytes, const uint64_t* 
     CUDA_CHECK(b.offs.ensure(n + 2)); CUDA_CHECK(b.ids.ensure(n + 1)); CUDA_CHECK(b.ctl.ensure(64));
     CUDA_CHECK(b.datums.ensure(nbytes + 64)); CUDA_CHECK(b.datum_off.ensure(n + 1)); CUDA_CHECK(b.scan_tmp64.ensure(prim::scan_tmp_elems(n + 1) + 16));
     if (!b.ctl_host) CUDA_CHECK(cudaHostAlloc(&b.ctl_host, 16 * 4, cudaHostAllocDefault));
-    uint64_t total = 0; uint32_t max_len = 0;
     if (n) {
         // images, their offsets and the ids go down as they are; the headers are read ON THE DEVICE (longest read, total bases, validity:
         // four bytes come back) -- walking a million headers in host memory costs more than the whole copy
@@ -671,10 +670,19 @@ int upload_datums(bsq_index* h, Batch& b, const uint8_t* bytes, const uint64_t* 
         prim::device_scan<uint64_t, prim::OpSum, false>(b.offs.p, b.offs.p, n + 1, b.scan_tmp64.p, prim::OpSum(), b.st, &h->timing.launches);
         CUDA_CHECK(cudaMemcpyAsync(b.ctl_host + 12, b.ctl.p + 61, 8, cudaMemcpyDeviceToHost, b.st));
         CUDA_CHECK(cudaMemcpyAsync(b.ctl_host + 14, b.offs.p + n, 8, cudaMemcpyDeviceToHost, b.st));
+    } else CUDA_CHECK(cudaMemsetAsync(b.offs.p, 0, 8, b.st));
+    h->timing.h2d_bytes += nbytes + (n + 1) * 8 + (ids ? n * 8 : 0);
+    return BSQ_OK;
+}
+// second half: waits for the header pass, sizes the text buffers, unpacks the images
+int upload_datums_end(bsq_index* h, Batch& b, uint64_t doff0) {
+    const uint64_t n = b.n;
+    uint64_t total = 0; uint32_t max_len = 0;
+    if (n) {
         CUDA_CHECK(cudaStreamSynchronize(b.st));
         if (b.ctl_host[13]) { bsq_set_error("datum %u is truncated or longer than a read may be", b.ctl_host[13] - 1); return BSQ_ERR; }
         max_len = b.ctl_host[12]; memcpy(&total, b.ctl_host + 14, 8);
-    } else CUDA_CHECK(cudaMemsetAsync(b.offs.p, 0, 8, b.st));
+    }
     b.max_len = max_len; b.total_bases = total;
     if (needs_seed_sw(max_len) && b.read_logtab_n < max_len + 1) {
         std::vector<double> tab(max_len + 1);
@@ -685,10 +693,13 @@ int upload_datums(bsq_index* h, Batch& b, const uint8_t* bytes, const uint64_t* 
         b.read_logtab_n = max_len + 1;
     }
     CUDA_CHECK(b.seqs.ensure(total + 64)); CUDA_CHECK(b.ascii.ensure(total + 64));
-    if (n) { k_datum_unpack<<<(unsigned)std::min<uint64_t>((n + 7) / 8, 148 * 16), 256, 0, b.st>>>(b.datums.p, b.datum_off.p, doff[0], n, b.offs.p, b.seqs.p, b.ascii.p); ++h->timing.launches; }
-    h->timing.h2d_bytes += nbytes + (n + 1) * 8 + (ids ? n * 8 : 0);
+    if (n) { k_datum_unpack<<<(unsigned)std::min<uint64_t>((n + 7) / 8, 148 * 16), 256, 0, b.st>>>(b.datums.p, b.datum_off.p, doff0, n, b.offs.p, b.seqs.p, b.ascii.p); ++h->timing.launches; }
     b.resident = true;
     return BSQ_OK;
+}
+int upload_datums(bsq_index* h, Batch& b, const uint8_t* bytes, const uint64_t* doff, const int64_t* ids, uint64_t n, uint64_t id_first = 0) {
+    if (upload_datums_begin(h, b, bytes, doff, ids, n, id_first) != BSQ_OK) return BSQ_ERR;
+    return upload_datums_end(h, b, n ? doff[0] : 0);
 }
 
 // k-mer table of the LAST-like seeding pass: built once per device index (also after a broadcast replica)
@@ -1771,6 +1782,160 @@ int bsq_bench_dpx(int device, int reps, double* gops) {
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
     *gops = (double)blocks * 256 * (double)iters * 8.0 / (best * 1e-3) / 1e9;   // DPX instructions (per thread) per second, in G
+    return BSQ_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------- one process, several GPUs
+// a PostgreSQL backend is one process with one thread.  bsq_multi is that shape: ONE host thread drives every
+// device with streams.  The index built on the first device is copied to the others over NVLink (peer copies of pac / Occ / SA /
+// annotations + the host-side state), every device derives its own inverse SA and prefix table, a batch is cut into contiguous
+// blocks of reads -- read i keeps lrand48 id i -- and the rows of all blocks land in ONE pinned result in read order.
+struct bsq_multi {
+    std::vector<bsq_index*> ix;      // ix[0] is the caller's (built) handle, the others are replicas owned here
+    bsq_timing timing;
+};
+
+bsq_multi* bsq_multi_new(bsq_index* built, const int* devices, int n_devices) {
+    BSQ_ENTRY();
+    if (!built || !built->meta.built || !devices || n_devices < 1) { bsq_set_error("bsq_multi_new: a built index and a device list are needed"); return nullptr; }
+    if (devices[0] != built->device) { bsq_set_error("bsq_multi_new: devices[0] must be the device the index was built on (%d)", built->device); return nullptr; }
+    bsq_multi* m = new bsq_multi;
+    memset(&m->timing, 0, sizeof(m->timing));
+    m->ix.push_back(built);
+    uint64_t hs_bytes = 0;
+    bsq_index_host_state_size(built, &hs_bytes);
+    std::vector<uint8_t> hs(hs_bytes);
+    bsq_index_host_state_get(built, hs.data(), hs_bytes);
+    bool ok = true;
+    for (int k = 1; k < n_devices && ok; ++k) {
+        bsq_index* r = bsq_index_new(&built->opts, devices[k]);
+        if (!r) { ok = false; break; }
+        m->ix.push_back(r);
+        r->flags = built->flags;
+        if (bsq_index_alloc_replica(r, &built->meta) != BSQ_OK) { ok = false; break; }
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, devices[k], built->device);
+        if (can) { cudaSetDevice(devices[k]); cudaDeviceEnablePeerAccess(built->device, 0); cudaGetLastError(); }
+        for (int what = 0; what < BSQ_ARR_COUNT && ok; ++what) {
+            const uint64_t nb = built->meta.arr_bytes[what];
+            if (nb && cudaMemcpyPeerAsync(index_array(r, what), devices[k], index_array(built, what), built->device, nb, r->stream) != cudaSuccess) {
+                bsq_set_error("bsq_multi_new: peer copy to device %d failed: %s", devices[k], cudaGetErrorString(cudaGetLastError())); ok = false;
+            }
+        }
+    }
+    for (size_t k = 1; k < m->ix.size() && ok; ++k) {
+        if (bsq_index_replica_finish(m->ix[k], hs.data(), hs_bytes) != BSQ_OK) { ok = false; break; }
+        if (bsq_index_prepare(m->ix[k], nullptr) != BSQ_OK) ok = false;
+    }
+    if (ok && bsq_index_prepare(built, nullptr) != BSQ_OK) ok = false;
+    if (!ok) { char keep[1024]; snprintf(keep, sizeof(keep), "%s", g_err); for (size_t k = 1; k < m->ix.size(); ++k) bsq_index_free(m->ix[k]); delete m; bsq_set_error("%s", keep); return nullptr; }
+    return m;
+}
+
+void bsq_multi_free(bsq_multi* m) {
+    if (!m) return;
+    for (size_t k = 1; k < m->ix.size(); ++k) bsq_index_free(m->ix[k]);
+    delete m;
+}
+
+int bsq_multi_devices(const bsq_multi* m) { return m ? (int)m->ix.size() : 0; }
+
+static int multi_align(bsq_multi* m, const ReadSrc& S, uint64_t n, bsq_result** out) {
+    const size_t D = m->ix.size();
+    std::vector<uint64_t> lo(D + 1);
+    for (size_t d = 0; d <= D; ++d) lo[d] = n * d / D;                       // contiguous blocks, as the oracle's thread sharding
+    bsq_index* h0 = m->ix[0];
+    const uint64_t session = h0->lrand_state;
+    std::vector<cudaEvent_t> e0(D), e1(D);
+    int rc = BSQ_OK;
+    for (size_t d = 0; d < D; ++d) { cudaSetDevice(m->ix[d]->device); cudaEventCreate(&e0[d]); cudaEventCreate(&e1[d]); }
+    // phase 1: every device's copies are queued before anything is waited for
+    for (size_t d = 0; d < D && rc == BSQ_OK; ++d) {
+        bsq_index* h = m->ix[d]; Batch& b = h->batch;
+        cudaSetDevice(h->device);
+        h->opts = h0->opts; h->dopts = h0->dopts; h->flags = h0->flags; h->lrand_state = session;
+        bsq_timing& T = h->timing;
+        T.launches = 0; T.h2d_bytes = T.d2h_bytes = 0; T.h2d = T.d2h = 0; T.notes = 0; T.seed = T.chain = T.extend = T.finalize = T.total = 0;
+        memset(h->counters, 0, sizeof(h->counters));
+        cudaEventRecord(e0[d], b.st);
+        const uint64_t cnt = lo[d + 1] - lo[d];
+        const int64_t* ids = S.ids ? S.ids + lo[d] : nullptr;
+        rc = S.dbytes ? upload_datums_begin(h, b, S.dbytes, S.doff + lo[d], ids, cnt, lo[d]) : upload_reads(h, b, S.seqs, S.offs + lo[d], ids, cnt, lo[d]);
+    }
+    // phase 2: the kernel pipelines
+    for (size_t d = 0; d < D && rc == BSQ_OK; ++d) {
+        bsq_index* h = m->ix[d];
+        cudaSetDevice(h->device);
+        if (S.dbytes) rc = upload_datums_end(h, h->batch, lo[d + 1] > lo[d] ? S.doff[lo[d]] : 0);
+        if (rc == BSQ_OK) rc = pipeline_enqueue(h, h->batch);
+    }
+    for (size_t d = 0; d < D && rc == BSQ_OK; ++d) { cudaSetDevice(m->ix[d]->device); rc = pipeline_finish(m->ix[d], m->ix[d]->batch); }
+    // phase 3: one result, every device's rows behind the previous device's
+    ResultImpl* R = nullptr;
+    if (rc == BSQ_OK) {
+        uint64_t rows = 0, cig = 0;
+        for (size_t d = 0; d < D; ++d) { rows += m->ix[d]->batch.out_rows; cig += m->ix[d]->batch.out_cig; }
+        if (cig > 0xffffffffull) { bsq_set_error("result has more CIGAR words than a 32-bit offset addresses"); rc = BSQ_ERR; }
+        else { cudaSetDevice(h0->device); R = result_new(n, rows, cig, (h0->flags & BSQ_FLAG_ROWS_EXT) != 0); if (!R) rc = BSQ_ERR; }
+    }
+    if (rc == BSQ_OK) {
+        uint64_t row_base = 0, cig_base = 0;
+        std::vector<uint64_t> rb(D), cb(D);
+        for (size_t d = 0; d < D && rc == BSQ_OK; ++d) {
+            bsq_index* h = m->ix[d]; Batch& b = h->batch;
+            cudaSetDevice(h->device);
+            rb[d] = row_base; cb[d] = cig_base;
+            rc = download_enqueue(h, b, R, lo[d], row_base, cig_base);
+            cudaEventRecord(e1[d], b.st);
+            row_base += b.out_rows; cig_base += b.out_cig;
+        }
+        for (size_t d = 0; d < D && rc == BSQ_OK; ++d) {
+            bsq_index* h = m->ix[d]; Batch& b = h->batch;
+            cudaSetDevice(h->device);
+            if (cudaStreamSynchronize(b.st) != cudaSuccess) { bsq_set_error("device %d: %s", h->device, cudaGetErrorString(cudaGetLastError())); rc = BSQ_ERR; break; }
+            download_finish(h, R, b.n, lo[d], b.out_rows, rb[d], cb[d], b.ctl_host && b.ctl_host[10], b.ext_tmp.data());
+        }
+        if (rc == BSQ_OK) { R->pub.row_off[n] = row_base; R->pub.n_cigar_words = cig_base; }
+    }
+    // timing: a device's time runs from its first copy to the end of its download; the call's time is the slowest device's
+    bsq_timing& MT = m->timing;
+    memset(&MT, 0, sizeof(MT));
+    for (size_t d = 0; d < D; ++d) {
+        bsq_index* h = m->ix[d];
+        cudaSetDevice(h->device);
+        float ms = 0;
+        if (rc == BSQ_OK && cudaEventElapsedTime(&ms, e0[d], e1[d]) == cudaSuccess) MT.total = std::max(MT.total, ms);
+        MT.seed = std::max(MT.seed, h->timing.seed); MT.chain = std::max(MT.chain, h->timing.chain); MT.extend = std::max(MT.extend, h->timing.extend);
+        MT.finalize = std::max(MT.finalize, h->timing.finalize);
+        MT.launches += h->timing.launches; MT.h2d_bytes += h->timing.h2d_bytes; MT.d2h_bytes += h->timing.d2h_bytes;
+        cudaEventDestroy(e0[d]); cudaEventDestroy(e1[d]);
+    }
+    cudaSetDevice(h0->device);
+    if (rc != BSQ_OK) { result_delete(R); return BSQ_ERR; }
+    if (!S.ids) h0->lrand_state = lrand48_advance(session, n);
+    *out = &R->pub;
+    return BSQ_OK;
+}
+
+int bsq_multi_align_batch(bsq_multi* m, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, bsq_result** out) {
+    BSQ_ENTRY();
+    if (!m || !out || (n && (!seqs || !offs))) { bsq_set_error("null argument"); return BSQ_ERR; }
+    const ReadSrc S{seqs, offs, nullptr, nullptr, ids};
+    return multi_align(m, S, n, out);
+}
+
+int bsq_multi_align_batch_datums(bsq_multi* m, const uint8_t* bytes, const uint64_t* off, const int64_t* ids, uint64_t n, bsq_result** out) {
+    BSQ_ENTRY();
+    if (!m || !out || (n && (!bytes || !off))) { bsq_set_error("null argument"); return BSQ_ERR; }
+    const ReadSrc S{nullptr, nullptr, bytes, off, ids};
+    return multi_align(m, S, n, out);
+}
+
+int bsq_multi_last_timing(const bsq_multi* m, bsq_timing* t) {
+    BSQ_ENTRY();
+    if (!m || !t) { bsq_set_error("null argument"); return BSQ_ERR; }
+    *t = m->timing;
     return BSQ_OK;
 }
 

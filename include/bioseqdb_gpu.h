@@ -181,6 +181,18 @@ int bsq_index_host_state_size(const bsq_index* h, uint64_t* bytes);
 int bsq_index_host_state_get(const bsq_index* h, void* buf, uint64_t bytes);
 int bsq_index_replica_finish(bsq_index* h, const void* host_state, uint64_t bytes);
 int bsq_index_prepare(bsq_index* h, float* ms);   /* build the per-device derived arrays (inverse SA, prefix table) now; *ms = time spent */
+/* One process, one host thread, several GPUs (reference extension.cpp:346-377 is one backend, one thread): the
+ * index of `built` is copied to devices[1..] (peer copies over NVLink + the host-side state), every device derives its own inverse SA /
+ * prefix table, and a batch is cut into contiguous blocks of reads, one per device (read i keeps lrand48 id i).  The rows of all
+ * devices come back in ONE result in read order.  devices[0] must be the device `built` lives on; `built` stays the caller's (options
+ * and flags set on it apply to every device; free it after bsq_multi_free). */
+typedef struct bsq_multi bsq_multi;
+bsq_multi* bsq_multi_new(bsq_index* built, const int* devices, int n_devices);
+void bsq_multi_free(bsq_multi* m);
+int bsq_multi_devices(const bsq_multi* m);
+int bsq_multi_align_batch(bsq_multi* m, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, bsq_result** out);
+int bsq_multi_align_batch_datums(bsq_multi* m, const uint8_t* bytes, const uint64_t* off, const int64_t* ids, uint64_t n, bsq_result** out);
+int bsq_multi_last_timing(const bsq_multi* m, bsq_timing* t);   /* total = the slowest device's time from its first copy to the end of its download */
 int bsq_index_bwt_plain(const bsq_index* h, uint32_t* out);               /* the u32 stream of bwa.cpp:48-50 */
 int bsq_index_sa_sampled(const bsq_index* h, uint64_t* out, uint64_t n_sa); /* bwt_cal_sa(bwt, 32) view */
 

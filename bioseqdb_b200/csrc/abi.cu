@@ -567,13 +567,12 @@ __global__ void k_compact_rows(const ReadBlock* blocks, const RowDev* rows, cons
     // thread per row slot of a read: the 120-byte working record becomes the 64-byte public row (+ the 48-byte extension when asked
     // for).  *host_mapq is raised when a row's MAPQ has to be finished on the host.  Rows beyond out_cap are dropped: the host sees
     // the total from the scan, grows the buffer and runs the batch again.
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    for (uint32_t r = gw; r < n_reads; r += nw) {
+    // thread per read (a read has one row, rarely a handful)
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x) {
         const uint32_t c = row_cnt[r];
         if (!c || row_off[r] + c > out_cap) continue;
         const RowDev* srow = rows + blocks[r].base;
-        for (uint32_t k = lane; k < c; k += 32) {
+        for (uint32_t k = 0; k < c; ++k) {
             const RowDev a = srow[k];
             const int mq = a.secondary < 0 ? approx_mapq_dev(M, a) : 0;
             if (mq < 0) atomicExch(host_mapq, 1u);
@@ -872,7 +871,7 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
         ENS(b.rows_ext.ensure(b.rows_cap));
         MapqParams M; M.a = h->opts.a; M.b = h->opts.b; M.min_seed_len = h->opts.min_seed_len; M.coef_len = h->mapQ_coef_len;
         M.coef_fac = (double)h->mapQ_coef_fac; M.logtab = h->d_logtab;
-        k_compact_rows<<<148 * 8, 256, 0, st>>>(b.blocks.p, b.rows.p, b.row_cnt.p, b.row_off.p, n, b.rows_compact.p, b.rows_ext.p,
+        k_compact_rows<<<(unsigned)std::min<uint32_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(b.blocks.p, b.rows.p, b.row_cnt.p, b.row_off.p, n, b.rows_compact.p, b.rows_ext.p,
                                                 (uint32_t)std::min<uint64_t>(b.rows_cap, 0xffffffffull), M, b.ctl.p + 30); ++T.launches;
     }
     cudaEventRecord(ev[4], st);
@@ -1740,18 +1739,23 @@ int bsq_bench_gather(bsq_index* h, uint64_t n_loads, int reps, double* gbs) {
     BSQ_ENTRY();
     if (!h || !h->meta.built || !gbs) { bsq_set_error("index not built"); return BSQ_ERR; }
     CUDA_CHECK(cudaSetDevice(h->device));
-    const uint64_t n_blocks = h->meta.arr_bytes[BSQ_ARR_OCC] / 64;
+    // the table the random 64-byte reads go to: the largest array the seeding kernels gather from (SURVEY 8d asks for a table at least
+    // the size of the index, so that the figure is an HBM number, not an L2 one): prefix table, else the full SA, else Occ
+    const uint32_t* table = h->d_occ; uint64_t table_bytes = h->meta.arr_bytes[BSQ_ARR_OCC];
+    if (h->meta.arr_bytes[BSQ_ARR_SA] > table_bytes) { table = reinterpret_cast<const uint32_t*>(h->d_sa); table_bytes = h->meta.arr_bytes[BSQ_ARR_SA]; }
+    if (h->d_kmer && kmer_table_bytes(h->kmer_k) > table_bytes) { table = reinterpret_cast<const uint32_t*>(h->d_kmer); table_bytes = kmer_table_bytes(h->kmer_k); }
+    const uint64_t n_blocks = table_bytes / 64;
     const int blocks = 148 * 8;                       // 8 CTAs of 256 threads per SM
     const uint64_t groups = (uint64_t)blocks * 256 / 16;
     uint64_t per_group = std::max<uint64_t>(8, (n_loads / groups) / 8 * 8);
     uint32_t* sink = nullptr;
     CUDA_CHECK(cudaMalloc(&sink, 64));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    launch_gather(h->d_occ, n_blocks, per_group, blocks, sink, h->stream);   // warm-up
+    launch_gather(table, n_blocks, per_group, blocks, sink, h->stream);   // warm-up
     float best = 1e30f;
     for (int r = 0; r < reps; ++r) {
         cudaEventRecord(e0, h->stream);
-        launch_gather(h->d_occ, n_blocks, per_group, blocks, sink, h->stream);
+        launch_gather(table, n_blocks, per_group, blocks, sink, h->stream);
         cudaEventRecord(e1, h->stream);
         CUDA_CHECK(cudaEventSynchronize(e1));
         float ms; cudaEventElapsedTime(&ms, e0, e1);

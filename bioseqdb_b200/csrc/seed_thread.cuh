@@ -459,13 +459,44 @@ ST_HD int seed_strategy1(const Index<IdxT>& X, const Opts& o, const Read& R, int
     return len;
 }
 
-// pass 3: the LAST-like pass
+// pass 3: the LAST-like pass.  The walk x -> f(x) is sequential, but f is a pure function of x and almost always returns x + L
+// (L = min_seed_len + 1: the first match with fewer than max_mem_intv occurrences is the L-mer itself).  LAST_BATCH predicted starts are
+// therefore evaluated together -- K-mer entries, then (one occurrence) SA rows, text words, ISA rows: each group of loads in flight at
+// once -- and consumed in order for as long as each start is the predicted one and was decidable without Occ.
+constexpr int LAST_BATCH = 8;
 template <class IdxT> ST_HD void last_like_pass(const Index<IdxT>& X, const Opts& o, const Read& R, Work<IdxT>& W) {
     if (o.max_mem_intv <= 0) return;
-    const int len = R.len;
+    const int len = R.len, K = X.kk, min_len = o.min_seed_len, L = min_len + 1;
+    const bool spec_ok = X.isa != nullptr && o.max_mem_intv > 1 && min_len >= K;
     int x = 0;
     while (x < len && !W.fail) {
-        if (x + X.kk > len) {
+        const int nb = spec_ok ? ((len - x) / L < LAST_BATCH ? (len - x) / L : LAST_BATCH) : 0;   // starts whose whole L-mer lies in the read
+        if (nb > 0) {
+            U4 e[LAST_BATCH]; IdxT pos[LAST_BATCH], r1[LAST_BATCH]; bool hit[LAST_BATCH];
+#pragma unroll
+            for (int k = 0; k < LAST_BATCH; ++k) if (k < nb) e[k] = tab_get(X, R, x + k * L, K);
+#pragma unroll
+            for (int k = 0; k < LAST_BATCH; ++k) { pos[k] = 0; if (k < nb && e[k].z == 1) pos[k] = ld_idx(X.sa + tab_x0<IdxT>(e[k])); }
+#pragma unroll
+            for (int k = 0; k < LAST_BATCH; ++k) {
+                hit[k] = false;
+                if (k < nb && e[k].z == 1) hit[k] = match_run_fwd(X, R, (IdxT)(pos[k] + (IdxT)K), x + k * L + K, L - K) == L - K;
+            }
+#pragma unroll
+            for (int k = 0; k < LAST_BATCH; ++k) { r1[k] = 0; if (hit[k]) r1[k] = ld_idx(X.isa + (X.n - pos[k] - (IdxT)L)); }
+            int done = 0;
+#pragma unroll
+            for (int k = 0; k < LAST_BATCH; ++k) {
+                if (k == done && k < nb && e[k].z <= 1) {            // decided without Occ: no seed, or the unique L-mer
+                    if (hit[k]) emit(W, tab_x0<IdxT>(e[k]), r1[k], 1u, x + k * L, x + k * L + L);
+                    W.n_ext += (unsigned long long)min_len;
+                    ++done;
+                }
+            }
+            x += done * L;
+            if (done == nb || W.fail) continue;
+        }
+        if (x + K > len) {
             // fewer than K bases left: no table entry; the walk cannot emit (i - x < min_len), only its extensions count
             W.n_ext += (unsigned long long)(len - 1 - x);
             break;

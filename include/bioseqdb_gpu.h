@@ -210,7 +210,8 @@ int bsq_debug_ksw_extend_thread(const bsq_opts* o, int device, uint64_t n_jobs, 
 /* global jobs: out_score[n]; cigar words written at cigar + cig_cap*i with counts in n_cigar[i] */
 int bsq_debug_ksw_global(const bsq_opts* o, int device, uint64_t n_jobs, const uint8_t* q, const uint64_t* q_off, const uint8_t* t,
                          const uint64_t* t_off, const int32_t* w, int32_t* out_score, uint32_t* cigar, uint32_t cig_cap, int32_t* n_cigar);
-/* random 64-byte gather microbenchmark over the Occ array (the seeding roofline denominator): GB/s */
+/* random 64-byte gather microbenchmark over the largest array the seeding kernels read (prefix table / full SA / Occ: at least the
+ * size of the index, so that the figure is an HBM number): the seeding roofline denominator, GB/s */
 int bsq_bench_gather(bsq_index* h, uint64_t n_loads, int reps, double* gbs);
 /* DPX issue microbenchmark (independent __vimax3_s32 / __viaddmax_s32_relu): G instructions per second */
 int bsq_bench_dpx(int device, int reps, double* gops);

@@ -110,6 +110,7 @@ struct bsq_index {
     bsq_timing timing;
     double* d_logtab = nullptr;
     void* d_isa = nullptr;           // inverse SA for the unique-match shortcut of the seeding kernel (built lazily, rows as wide as the SA's)
+    uint32_t* d_kmer_z = nullptr;    // sizes-only copy of the prefix table
     void* d_kmer = nullptr; int kmer_k = 0;          // k-mer table of the LAST-like seeding pass (built lazily per device index)
     bool collect_counters = false;
     uint32_t flags = 0;              // BSQ_FLAG_*
@@ -239,6 +240,7 @@ int bsq_index_add_ref_datums(bsq_index* h, uint64_t n, const int64_t* ids, const
 
 static void free_index_arrays(bsq_index* h) {
     if (h->d_kmer) { cudaFree(h->d_kmer); h->d_kmer = nullptr; }
+    if (h->d_kmer_z) { cudaFree(h->d_kmer_z); h->d_kmer_z = nullptr; }
     if (h->d_isa) { cudaFree(h->d_isa); h->d_isa = nullptr; }
     if (h->d_pac) cudaFree(h->d_pac); if (h->d_occ) cudaFree(h->d_occ); if (h->d_sa) cudaFree(h->d_sa);
     if (h->d_ann_offset) cudaFree(h->d_ann_offset); if (h->d_ann_len) cudaFree(h->d_ann_len); if (h->d_ann_id) cudaFree(h->d_ann_id);
@@ -305,6 +307,7 @@ int bsq_index_device_bytes(const bsq_index* h, uint64_t* bytes) {
         b += (h->meta.l_pac + 3) / 4 + ((n + 127) / 128 + 1) * 64 + (n + 1) * h->meta.sa_bytes + h->meta.n_anns * 20;
         if (h->d_isa) b += (n + 1) * (uint64_t)h->meta.sa_bytes + 64;
         if (h->d_kmer) b += kmer_table_bytes(h->kmer_k);
+        if (h->d_kmer_z) b += kmer_table_bytes(h->kmer_k) / 4;
     }
     *bytes = b;
     return BSQ_OK;
@@ -721,6 +724,8 @@ int ensure_kmer_table(bsq_index* h, const DevIndex& ix) {
     if (const char* e = getenv("BSQ_KMER_K")) { const int k = atoi(e); if (k >= 8 && k <= 15) h->kmer_k = k; }
     CUDA_CHECK(cudaMalloc(&h->d_kmer, kmer_table_bytes(h->kmer_k)));
     build_kmer_table(ix, h->d_kmer, h->kmer_k, h->stream, &h->timing.launches);
+    if (!getenv("BSQ_NO_KMER_Z") && cudaMalloc(&h->d_kmer_z, kmer_table_bytes(h->kmer_k) / 4) == cudaSuccess) build_kmer_sizes(h->d_kmer, h->d_kmer_z, h->kmer_k, h->stream, &h->timing.launches);
+    else { h->d_kmer_z = nullptr; cudaGetLastError(); }
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
     return BSQ_OK;
 }
@@ -729,7 +734,7 @@ int ensure_kmer_table(bsq_index* h, const DevIndex& ix) {
 SeedParams seed_params(const bsq_index* h, const Batch& b, const DevIndex& ix, uint32_t n, uint32_t cap, uint32_t* ticket, unsigned long long* n_extend) {
     SeedParams P;
     P.seqs = b.seqs.p; P.offs = b.offs.p; P.n_reads = n; P.out = b.intv.p; P.out_cnt = b.intv_cnt.p; P.cap = cap;
-    P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.kmer_k = h->kmer_k; P.isa = h->d_isa;
+    P.kmer_tab = reinterpret_cast<const uint4*>(h->d_kmer); P.kmer_k = h->kmer_k; P.kmer_ztab = h->d_kmer_z; P.isa = h->d_isa;
     P.scratch = b.seed_scratch.p; P.list_cap = b.list_cap;
     // shared-memory bytes per warp for the read: the bases (padded to 16) and their 2-bit packed copy
     P.read_cap = ((b.max_len + 16) & ~15u) + (((b.max_len >> 4) + 3) << 2) + 16 & ~15u;

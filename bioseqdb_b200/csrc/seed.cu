@@ -778,7 +778,7 @@ __global__ void seed_pack(SeedParams P, int min_seed_len, int words) {
 
 template <class IdxT> __device__ __forceinline__ seedt::Index<IdxT> st_index(const SeedParams& P, const DevIndex& ix) {
     seedt::Index<IdxT> X;
-    X.occ = ix.occ; X.tab = reinterpret_cast<const seedt::U4*>(P.kmer_tab); X.kk = P.kmer_k;
+    X.occ = ix.occ; X.tab = reinterpret_cast<const seedt::U4*>(P.kmer_tab); X.kk = P.kmer_k; X.ztab = P.kmer_ztab;
     X.sa = reinterpret_cast<const IdxT*>(ix.sa); X.isa = reinterpret_cast<const IdxT*>(P.isa); X.pac = ix.pac;
     X.l_pac = (IdxT)ix.l_pac; X.n = (IdxT)ix.seq_len; X.primary = (IdxT)ix.primary;
 #pragma unroll
@@ -915,6 +915,16 @@ template <class IdxT, bool SMEM, int MINB> void launch_mode(const SeedParams& p,
 }  // namespace
 
 size_t kmer_table_bytes(int k) { return (size_t)kmer_level_off(k + 1) * sizeof(uint4); }
+
+static __global__ void k_kmer_sizes(const uint4* __restrict__ tab, uint32_t* __restrict__ ztab, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) ztab[i] = tab[i].z;
+}
+// the sizes-only copy of the prefix table (kmer_table_bytes(k) / 4 bytes)
+void build_kmer_sizes(const void* tab, uint32_t* ztab, int k, cudaStream_t st, uint64_t* launches) {
+    const uint64_t n = kmer_level_off(k + 1);
+    k_kmer_sizes<<<148 * 16, 256, 0, st>>>(reinterpret_cast<const uint4*>(tab), ztab, n);
+    if (launches) ++*launches;
+}
 
 // depth of the prefix table for a text of n symbols: ceil(log4 n), within [8, KMER_K_MAX]
 int kmer_table_depth(uint64_t n) {

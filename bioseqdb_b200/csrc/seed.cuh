@@ -19,6 +19,7 @@ struct SeedParams {
     uint32_t read_cap;        // bytes reserved per warp for the staged read (>= longest read, multiple of 16)
     const uint4* kmer_tab;    // prefix table: bi-intervals of all t-mers, t <= kmer_k (rows of up to 40 bits), or nullptr
     int kmer_k;
+    const uint32_t* kmer_ztab; // sizes-only copy of the prefix table (same indexing), or nullptr
     const void* isa;          // inverse suffix array for the unique-match shortcut (rows as wide as the SA's), or nullptr
     uint32_t* ticket;
     uint32_t* overflow;       // set to 1 when a read needs more than cap intervals
@@ -39,4 +40,5 @@ size_t kmer_table_bytes(int k);
 int kmer_table_depth(uint64_t n);
 void build_isa(const DevIndex& ix, void* isa, cudaStream_t st, uint64_t* launches);
 void build_kmer_table(const DevIndex& ix, void* tab, int k, cudaStream_t st, uint64_t* launches);
+void build_kmer_sizes(const void* tab, uint32_t* ztab, int k, cudaStream_t st, uint64_t* launches);
 bool seed_lists_fit_smem(uint32_t list_cap, uint32_t read_cap, int sa_bytes);

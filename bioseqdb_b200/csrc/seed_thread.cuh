@@ -58,6 +58,8 @@ ST_HD uint32_t fsl(uint32_t lo, uint32_t hi, int s) { return s ? (hi << s) | (lo
 
 template <class IdxT> struct Index {
     const uint32_t* occ; const U4* tab; int kk;
+    const uint32_t* ztab;    // sizes only (the .z of every table entry, same indexing): what the walks compare; 4 bytes per entry, so the
+                             // levels that stay in L2 reach two levels deeper than with the 16-byte entries (nullptr: read tab)
     const IdxT* sa; const IdxT* isa; const uint8_t* pac;
     IdxT l_pac, n, primary; IdxT L2[5];
 };
@@ -143,6 +145,10 @@ template <class IdxT> ST_HD int match_run_bwd(const Index<IdxT>& X, const Read& 
     return maxlen;
 }
 
+// size of table entry `idx` (all levels share one index space)
+template <class IdxT> ST_HD uint32_t tab_size(const Index<IdxT>& X, uint32_t idx) {
+    return X.ztab ? ld_u32(X.ztab + idx) : ld_u32(reinterpret_cast<const uint32_t*>(X.tab + idx) + 2);
+}
 // ---- prefix table: entry of the t-mer starting at read position s (1 <= t <= kk, s + t <= len)
 template <class IdxT> ST_HD U4 tab_get(const Index<IdxT>& X, const Read& R, int s, int t) {
     return ld_u4(X.tab + level_off(t) + (rd_window(R, s) >> (32 - 2 * t)));
@@ -255,7 +261,7 @@ ST_HD void smem_forward(const Index<IdxT>& X, const Read& R, int x, uint32_t min
     const uint32_t w0 = rd_window(R, x);
     uint32_t zs[16];
 #pragma unroll
-    for (int t = 1; t <= 15; ++t) zs[t] = t <= maxt ? ld_u32(reinterpret_cast<const uint32_t*>(X.tab + (level_off(t) + (w0 >> (32 - 2 * t)))) + 2) : 0u;
+    for (int t = 1; t <= 15; ++t) zs[t] = t <= maxt ? tab_size(X, level_off(t) + (w0 >> (32 - 2 * t))) : 0u;
     uint32_t cur_x2 = zs[1], n_ext = 0, mask = 0, top_z = 0;
     int i = x + 1; bool stopped = false;
 #pragma unroll
@@ -358,7 +364,7 @@ ST_HD void smem_column(const Index<IdxT>& X, const Opts& o, const Read& R, int k
                 if (b + u < nb) {
                     const int sh = (iu & 15) << 1, lq = end - iu;
                     const uint32_t win = (iu >> 4) == w ? fsl(wb, wa, sh) : fsl(wa, wc, sh);
-                    sv[u] = ld_u32(reinterpret_cast<const uint32_t*>(X.tab + (level_off(lq) + (win >> (32 - 2 * lq)))) + 2);
+                    sv[u] = tab_size(X, level_off(lq) + (win >> (32 - 2 * lq)));
                 }
             }
 #pragma unroll

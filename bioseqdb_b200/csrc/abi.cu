@@ -1531,7 +1531,7 @@ int bsq_nuclseq_from_text_batch(int device, const char* text, const uint64_t* of
         }
     }
     const uint64_t total = rel[n];
-    if (chunks >= (1ull << 32) - 2) { bsq_set_error("batch too large for one call (more than 64 G bases)"); return BSQ_ERR; }
+    if (chunks >= (1ull << 32) - 2 || total >= (1ull << 32)) { bsq_set_error("batch too large for one call (4 G bases at most: the ranks of ambiguous bases are 32-bit)"); return BSQ_ERR; }
     NuclseqsImpl* S = new NuclseqsImpl();
     S->pub.n = n; S->pub.off = nullptr; S->pub.bytes = nullptr; S->pub.n_bytes = 0; S->pub.device_ms = 0.f;
     uint8_t *d_text = nullptr, *d_bytes = nullptr; uint64_t *d_offs = nullptr, *d_chunk_off = nullptr, *d_img = nullptr, *d_tmp64 = nullptr;
@@ -1559,6 +1559,7 @@ int bsq_nuclseq_from_text_batch(int device, const char* text, const uint64_t* of
         LC(cudaMemcpyAsync(&n_bytes, d_img + n, 8, cudaMemcpyDeviceToHost, st));
         LC(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, st));
         LC(cudaStreamSynchronize(st)); LC(cudaGetLastError());
+        if (bad != ~0ull && (bad >> 63)) { bsq_set_error("sequence at text offset %llu needs a datum of 1 GiB or more (too many ambiguity runs): invalid memory alloc request size", (unsigned long long)(bad & ~(1ull << 63))); break; }
         if (bad != ~0ull) { bsq_set_error("invalid nucleotide in nuclseq_in: '%c'", text[offs[0] + bad]); break; }   // extension.cpp:53-58
         LC(cudaMalloc(&d_bytes, n_bytes + 64));
         LC(cudaMemsetAsync(d_bytes, 0, n_bytes + 64, st));

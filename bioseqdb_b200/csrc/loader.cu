@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(LD_THREADS) k_record_sizes(LoaderParams P) {
     const uint64_t len = P.offs[r + 1] - P.offs[r];
     P.holes_num[r] = (uint32_t)holes;
     const uint64_t size = 12 + 16 * holes + ((len + 3) >> 2);
+    // a varlena length word holds 30 bits: the reference fails such a datum in palloc0 (MaxAllocSize, sequence.cpp:59-69)
+    if (size >= 0x3fffffffull) atomicMin(P.first_invalid, (unsigned long long)P.offs[r] | (1ull << 63));
     P.img_off[r] = (size + 7) & ~7ull;
 }
 

@@ -789,7 +789,7 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
     ENS(b.ext_scratch.ensure((size_t)ext_warps * ext_per_warp)); ENS(b.fin_scratch.ensure((size_t)fin_warps * fin_per_warp));
     int narrow_warps = 0;
     const size_t narrow_bytes = narrow_zbuf_bytes(&narrow_warps);
-    ENS(b.narrow_z.ensure(narrow_bytes)); ENS(b.narrow_jobs.ensure((size_t)b.pool_cap * 3 * 24)); ENS(b.wide_jobs.ensure(b.pool_cap));
+    ENS(b.narrow_z.ensure(narrow_bytes)); ENS(b.narrow_jobs.ensure((size_t)b.pool_cap * 4 * 24)); ENS(b.wide_jobs.ensure(b.pool_cap));
     ENS(b.ctl.ensure(64)); ENS(b.chain_todo.ensure(n)); ENS(b.fin_todo.ensure(n)); ENS(b.seed_todo.ensure(n + 1));
     if (max_len <= 496) { ENS(b.seed_pk.ensure((size_t)n * seed_thread_words(max_len))); ENS(b.seed_u32.ensure(3 * (size_t)n)); }
     // the thread-per-extension pre-pass packs column scores in 16 bits: every value it stores is <= l_query * (a + 1)
@@ -855,6 +855,7 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
         P.scratch = b.fin_scratch.p; P.scratch_per_warp = fin_per_warp; P.max_len = max_len; P.z_cap = z_cap; P.ann_id = h->d_ann_id;
         P.narrow_jobs = small_batch ? nullptr : b.narrow_jobs.p; P.narrow_cap = b.pool_cap; P.narrow_cnt = b.ctl.p + 32; P.wide_jobs = b.wide_jobs.p; P.wide_cnt = b.ctl.p + 25;
         P.narrow_z = b.narrow_z.p; P.narrow_warps = narrow_warps;
+        { static const bool no_tight = getenv("BSQ_FIN_NO_TIGHT") != nullptr; P.narrow_tight = !no_tight; }
         P.ticket = b.ctl.p + 40; P.overflow = b.ctl.p + 4; P.need_rseq = b.ctl.p + 7; P.counters = ctr ? ctr + 6 : nullptr;
         static const bool no_thread_fin = getenv("BSQ_NO_FIN_THREAD") != nullptr;
         P.todo = (no_thread_fin || small_batch) ? nullptr : b.fin_todo.p; P.todo_cnt = b.ctl.p + 58;
@@ -1609,6 +1610,15 @@ int bsq_last_timing(const bsq_index* h, bsq_timing* t) {
 
 int bsq_set_counters(bsq_index* h, int on) { if (!h) return BSQ_ERR; h->collect_counters = on != 0; return BSQ_OK; }
 int bsq_get_counters(const bsq_index* h, uint64_t* out8) { if (!h || !out8) return BSQ_ERR; memcpy(out8, h->counters, sizeof(h->counters)); return BSQ_OK; }
+
+// the control words of the last batch's pipeline (queue sizes, tickets; layout at Batch::ctl): read after a call has ended
+int bsq_debug_ctl(bsq_index* h, uint32_t* out64) {
+    BSQ_ENTRY();
+    if (!h || !out64 || !h->batch.ctl.p) { bsq_set_error("no batch"); return BSQ_ERR; }
+    CUDA_CHECK(cudaSetDevice(h->device));
+    CUDA_CHECK(cudaMemcpy(out64, h->batch.ctl.p, 64 * 4, cudaMemcpyDeviceToHost));
+    return BSQ_OK;
+}
 
 int bsq_debug_seed(bsq_index* h, const char* seqs, const uint64_t* offs, uint64_t n, uint64_t* out, uint32_t cap, uint32_t* cnt) {
     BSQ_ENTRY();

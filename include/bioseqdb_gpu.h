@@ -218,6 +218,7 @@ int bsq_bench_dpx(int device, int reps, double* gops);
 /* Optional work counters of the last batch (the roofline's algorithmic units):
  * out8 = {bwt_extend calls, SA lookups, equal-pos chain events, ksw_extend2 cells, calls, rows, ksw_global2 cells, calls} */
 int bsq_set_counters(bsq_index* h, int on);
+int bsq_debug_ctl(bsq_index* h, uint32_t* out64);   /* control words of the last batch (queue sizes of the finalize passes at [32..39]) */
 int bsq_get_counters(const bsq_index* h, uint64_t* out8);
 
 #ifdef __cplusplus

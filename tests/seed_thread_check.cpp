@@ -64,10 +64,11 @@ template <class IdxT> static int run(int ref_len, int n_reads, int read_len, dou
     }
     std::vector<uint8_t> pac(ix.pac); pac.resize(pac.size() + 16, 0);
     std::vector<uint32_t> occ(ix.bwt); occ.resize(occ.size() + 32, 0);
-    seedt::Index<IdxT> X;
+    seedt::Index<IdxT> X{};
     std::vector<uint32_t> ztab(tab.size());
     for (size_t i = 0; i < tab.size(); ++i) ztab[i] = tab[i].z;
-    X.occ = occ.data(); X.tab = tab.data(); X.kk = K; X.ztab = (K & 1) ? ztab.data() : nullptr;   // odd depths run with the size table, even ones without X.sa = sa.data(); X.isa = isa.data(); X.pac = pac.data();
+    X.occ = occ.data(); X.tab = tab.data(); X.kk = K; X.ztab = (K & 1) ? ztab.data() : nullptr;   // odd depths run with the size table, even ones without
+    X.sa = sa.data(); X.isa = isa.data(); X.pac = pac.data();
     X.l_pac = (IdxT)l_pac; X.n = (IdxT)n; X.primary = (IdxT)ix.primary;
     for (int c = 0; c < 5; ++c) X.L2[c] = (IdxT)ix.L2[c];
     seedt::Opts so; so.min_seed_len = opt.min_seed_len; so.split_len = (int)(opt.min_seed_len * opt.split_factor + .499); so.split_width = opt.split_width; so.max_mem_intv = opt.max_mem_intv;

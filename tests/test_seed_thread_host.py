@@ -13,7 +13,7 @@ EXE = os.path.join(ROOT, "tests", "_build", "seed_thread_check")
 @pytest.fixture(scope="module")
 def checker(oracle):
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-Wno-unknown-pragmas", "-o", EXE, os.path.join(ROOT, "tests", "seed_thread_check.cpp"),
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-ftrivial-auto-var-init=pattern", "-Wno-unknown-pragmas", "-o", EXE, os.path.join(ROOT, "tests", "seed_thread_check.cpp"),
                            "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
     return EXE
 

@@ -212,17 +212,20 @@ __device__ __forceinline__ bool mat_is_simple(const int* smat) {
 // A job list holds both classes of thread-per-region work so that the lanes of a warp do similar work: regions whose band
 // fits the register window (w <= REG_WT) grow from the front, wider ones (shared-memory kernel) from the back.
 constexpr int REG_WT = 16;
-constexpr int REG_WT3 = 8;    // tight first try (MODE 3): 17 columns; accepted only when no path outside the window can reach the score found
-constexpr int NARROW_T_CNT = 18;   // index of list T's counter behind narrow_cnt (ctl word 50)
+// tight first tries: MODE 4 runs a 9-column window, MODE 3 a 17-column one; a result is accepted only when no path that leaves
+// the window can reach the score found inside it (lists T4 -> T8 -> A)
+constexpr int REG_WT3 = 8;
+constexpr int REG_WT4 = 4;
+constexpr int NARROW_T4_CNT = 20, NARROW_T8_CNT = 21;   // counters of lists T4 / T8 behind narrow_cnt (ctl words 52, 53)
 constexpr int REG_WT2 = 32;   // second register kernel: bands of half-width 17..32 (65 columns of H and E in registers, 2 CTAs per SM)
 __device__ __forceinline__ bool narrow_is_big(const DevOpts& o, int lq, int rlen, int w2, bool simple_mat) {
     w2 = w2 < o.w << 2 ? w2 : o.w << 2;
     return !simple_mat || gen_cigar_band(o, lq, rlen, w2) > REG_WT;
 }
 // the tight pass takes a region when the register kernels can score it and the end cell lies inside the tight window
-__device__ __forceinline__ bool narrow_is_tight(const DevOpts& o, int lq, int rlen, bool simple_mat) {
+__device__ __forceinline__ bool narrow_is_tight(const DevOpts& o, int lq, int rlen, bool simple_mat, int wt = REG_WT3) {
     const int dl = lq - rlen;
-    return simple_mat && (dl < 0 ? -dl : dl) <= REG_WT3 && o.o_del >= 0 && o.e_del >= 0 && o.o_ins >= 0 && o.e_ins >= 0 && o.mat_max > 0;
+    return simple_mat && (dl < 0 ? -dl : dl) <= wt && o.o_del >= 0 && o.e_del >= 0 && o.o_ins >= 0 && o.e_ins >= 0 && o.mat_max > 0;
 }
 __device__ __forceinline__ void push_narrow(NarrowJob* list, uint32_t cap, uint32_t* cnt_reg, uint32_t* cnt_big, const NarrowJob& jb, bool big) {
     if (big) list[cap - 1u - atomicAdd(cnt_big, 1u)] = jb;
@@ -285,7 +288,7 @@ __device__ void reg2aln_warp(const FinalizeParams& P, const DevIndex& ix, const 
 __global__ void __launch_bounds__(128) regs_finalize_thread(FinalizeParams P, DevIndex ix, DevOpts o) {
     const uint32_t r = blockIdx.x * 128 + threadIdx.x;
     const int lane = lane_id();
-    int cat = 0;      // 0 nothing to push, 1 register-band DP job, 2 wide-band DP job, 3 no-DP job, 4 tight first try
+    int cat = 0;      // 0 nothing to push, 1 register-band DP job, 2 wide-band DP job, 3 no-DP job, 4 / 5 tight first try (9 / 17 columns)
     NarrowJob jb; jb.r = r; jb.slot = 0; jb.w2 = 0; jb.last_sc = -(1 << 30); jb.it = 0; jb.score = 0;
     if (r < P.n_reads) {
         const ReadBlock blk = P.blocks[r];
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(128) regs_finalize_thread(FinalizeParams P, De
                 jb.slot = blk.base; jb.w2 = reg2aln_w2(o, ar);
                 if (ncls == 1) {
                     const bool sm = mat_is_simple(o.mat);
-                    if (P.narrow_tight && narrow_is_tight(o, ar.qe - ar.qb, (int)(ar.re - ar.rb), sm)) cat = 4;
+                    if (P.narrow_tight && narrow_is_tight(o, ar.qe - ar.qb, (int)(ar.re - ar.rb), sm)) cat = narrow_is_tight(o, ar.qe - ar.qb, (int)(ar.re - ar.rb), sm, REG_WT4) ? 4 : 5;
                     else cat = narrow_is_big(o, ar.qe - ar.qb, (int)(ar.re - ar.rb), jb.w2, sm) ? 2 : 1;
                 } else cat = 3;
                 P.row_cnt[r] = 1;
@@ -314,18 +317,18 @@ __global__ void __launch_bounds__(128) regs_finalize_thread(FinalizeParams P, De
     NarrowJob* lists = reinterpret_cast<NarrowJob*>(P.narrow_jobs);
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int c = 1; c <= 4; ++c) {
+    for (int c = 1; c <= 5; ++c) {
         const uint32_t mask = __ballot_sync(FULL, cat == c);
         if (!mask) continue;
         uint32_t base = 0;
-        if (lane == __ffs(mask) - 1) base = atomicAdd(P.narrow_cnt + (c == 1 ? 0 : (c == 2 ? 5 : (c == 3 ? 3 : NARROW_T_CNT))), (uint32_t)__popc(mask));
+        if (lane == __ffs(mask) - 1) base = atomicAdd(P.narrow_cnt + (c == 1 ? 0 : (c == 2 ? 5 : (c == 3 ? 3 : (c == 4 ? NARROW_T4_CNT : NARROW_T8_CNT)))), (uint32_t)__popc(mask));
         base = __shfl_sync(FULL, base, __ffs(mask) - 1);
         if (cat == c) {
             const uint32_t k = base + (uint32_t)__popc(mask & lt);
             if (c == 1) lists[k] = jb;
             else if (c == 2) lists[P.narrow_cap - 1u - k] = jb;
             else if (c == 3) lists[2u * P.narrow_cap + k] = jb;
-            else lists[3u * P.narrow_cap + k] = jb;
+            else lists[(c == 4 ? 3u : 4u) * P.narrow_cap + k] = jb;
         }
     }
 }
@@ -479,8 +482,10 @@ __global__ void __launch_bounds__(FIN_THREADS, 6) regs_finalize(FinalizeParams P
                     // DP regions and no-DP regions go to separate lists so that the lanes of a warp do similar work
                     NarrowJob jb; jb.r = r; jb.slot = blk.base + i; jb.w2 = reg2aln_w2(o, ar); jb.last_sc = -(1 << 30); jb.it = 0; jb.score = 0;
                     NarrowJob* lists = reinterpret_cast<NarrowJob*>(P.narrow_jobs);
-                    if (ncls == 1 && P.narrow_tight && narrow_is_tight(o, ar.qe - ar.qb, (int)(ar.re - ar.rb), simple_mat))
-                        lists[3u * P.narrow_cap + atomicAdd(P.narrow_cnt + NARROW_T_CNT, 1u)] = jb;
+                    if (ncls == 1 && P.narrow_tight && narrow_is_tight(o, ar.qe - ar.qb, (int)(ar.re - ar.rb), simple_mat)) {
+                        if (narrow_is_tight(o, ar.qe - ar.qb, (int)(ar.re - ar.rb), simple_mat, REG_WT4)) lists[3u * P.narrow_cap + atomicAdd(P.narrow_cnt + NARROW_T4_CNT, 1u)] = jb;
+                        else lists[4u * P.narrow_cap + atomicAdd(P.narrow_cnt + NARROW_T8_CNT, 1u)] = jb;
+                    }
                     else if (ncls == 1) push_narrow(lists, P.narrow_cap, P.narrow_cnt, P.narrow_cnt + 5, jb, narrow_is_big(o, ar.qe - ar.qb, (int)(ar.re - ar.rb), jb.w2, simple_mat));
                     else lists[2u * P.narrow_cap + atomicAdd(P.narrow_cnt + 3, 1u)] = jb;
                 }
@@ -583,6 +588,48 @@ __device__ __forceinline__ int global_dp_reg(const uint8_t* __restrict__ qg, int
     return score;
 }
 
+// 16 bases pac[f .. f+16), first base in the top bits (pac is padded, f >= 0)
+__device__ __forceinline__ uint32_t pac_win16(const uint8_t* pac, int64_t f) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(pac) + (f >> 4);
+    return __funnelshift_l(__byte_perm(w[1], 0, 0x0123), __byte_perm(w[0], 0, 0x0123), (int)(f & 15) << 1);
+}
+// Mismatches on the gap-free diagonal of a region with lq == rlen, 16 bases per step: the query bytes (codes 0..3) are packed to two
+// bits and XORed with a pac window.  Pairs are (q[j], pac[tbase + j]) on the forward strand and (q[j], 3 - pac[tbase + lq - 1 - j])
+// on the reverse one (libbwa reverses both sequences there; a count does not care about the order).  *ok = false when the query
+// holds a code above 3 (the caller then scores base by base with the matrix).
+__device__ __forceinline__ int diag_mismatches(const uint8_t* qg, int lq, bool rev, const uint8_t* pac, int64_t tbase, bool* ok) {
+    const uint32_t* qa = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(qg) & ~(uintptr_t)3);
+    const int sh = (int)(reinterpret_cast<uintptr_t>(qg) & 3) * 8;
+    uint32_t prev = qa[0], amb = 0;
+    int mm = 0, j0 = 0;
+    for (; j0 + 16 <= lq; j0 += 16) {
+        uint32_t Q = 0;                                   // base j0 + k at bits 2k
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t nx = qa[(j0 >> 2) + k + 1];   // the read buffer is padded: the word behind the last base exists
+            const uint32_t x = __funnelshift_r(prev, nx, sh);
+            prev = nx;
+            amb |= x;
+            Q |= ((x | x >> 6 | x >> 12 | x >> 18) & 0xffu) << (8 * k);
+        }
+        uint32_t v;
+        if (rev) v = ~pac_win16(pac, tbase + lq - 16 - j0);   // position tbase + lq - 1 - (j0 + k) sits at bits 2k of the window
+        else {
+            const uint32_t r = __brev(pac_win16(pac, tbase + j0));             // base order reversed, and the two bits of each base
+            v = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+        }
+        const uint32_t d = Q ^ v;
+        mm += __popc((d | d >> 1) & 0x55555555u);
+    }
+    for (int j = j0; j < lq; ++j) {
+        const uint32_t q = qg[j];
+        amb |= q;
+        mm += q != (rev ? 3u - pac_get(pac, tbase + lq - 1 - j) : pac_get(pac, tbase + j));
+    }
+    *ok = (amb & 0xfcfcfcfcu) == 0;
+    return mm;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Thread-per-region mem_reg2aln for narrow bands (the common case for 150 bp reads: w = 6..31).
 // One thread runs the scalar ksw_global2 recurrence; the row buffer is a 64-entry circular window in
@@ -604,7 +651,7 @@ struct NarrowParams {
 // MODE 0: circular row window in shared memory (bands up to NARROW_NC columns); MODE 1: the band in registers
 // (global_dp_reg, w <= REG_WT), no shared memory, regions with a wider band are passed on to a MODE 0 launch.
 template <int MODE>
-__global__ void __launch_bounds__(NARROW_THREADS, MODE == 3 ? 6 : (MODE == 1 ? 4 : (MODE == 2 ? 2 : 1))) regs_cigar_narrow(NarrowParams P, DevIndex ix, DevOpts o) {
+__global__ void __launch_bounds__(NARROW_THREADS, MODE >= 3 ? 6 : (MODE == 1 ? 4 : (MODE == 2 ? 2 : 1))) regs_cigar_narrow(NarrowParams P, DevIndex ix, DevOpts o) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ int smat[25];
     if (threadIdx.x < 25) smat[threadIdx.x] = o.mat[threadIdx.x];
@@ -615,7 +662,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE == 3 ? 6 : (MODE == 1 ? 4
     uint8_t* Q = dyn_smem + 2 * NARROW_NC * NARROW_THREADS * 4 + tid;               // Q[j * NARROW_THREADS]
     const uint32_t gwarp = (blockIdx.x * NARROW_THREADS + tid) >> 5;
     // traceback bytes, 4 cells per 32-bit store, laid out [row][4-cell group][lane]: a warp store is 128 contiguous bytes
-    constexpr int WTM = MODE == 2 ? REG_WT2 : (MODE == 3 ? REG_WT3 : REG_WT);                                // half-width of the register window (MODE 1 / 2)
+    constexpr int WTM = MODE == 2 ? REG_WT2 : (MODE == 3 ? REG_WT3 : (MODE == 4 ? REG_WT4 : REG_WT));                                // half-width of the register window (MODE 1 / 2)
     constexpr size_t Z_PER_WARP = MODE != 0 ? (size_t)NARROW_TMAX * ((2 * WTM + 1 + 3) / 4) * 4 * 32 : (size_t)NARROW_TMAX * NARROW_NC * 32;
     constexpr int ZROW = MODE != 0 ? (2 * WTM + 1 + 3) / 4 : NARROW_NC / 4;         // words per row and lane
     uint32_t* Z = reinterpret_cast<uint32_t*>(P.zbuf + (size_t)gwarp * Z_PER_WARP) + lane;
@@ -654,6 +701,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE == 3 ? 6 : (MODE == 1 ? 4
             bool go_wide = false, again = false;
             do {
                 n_cigar = 0; NM = -1;
+                int nm_known = -1;       // mismatches of a gap-free row, when the packed comparison has counted them already
                 if (!reject) {
                     bool diagonal = lq == rlen && w2 == 0;   // bwa_gen_cigar2's own no-DP case
                     if (P.diag_pass && lq == rlen) {
@@ -662,7 +710,12 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE == 3 ? 6 : (MODE == 1 ? 4
                         // bound it is the UNIQUE optimum of ksw_global2 for every band (the diagonal lies inside any band), so the
                         // traceback is lq M and the score is band-independent: the DP and the band-doubling retries are skipped.
                         int sc = 0;
-                        for (int i = 0; i < lq; ++i) {
+                        bool fast = false;
+                        if (MODE != 0 && simple_mat) {
+                            const int mm = diag_mismatches(qg, lq, rev, ix.pac, tbase, &fast);
+                            if (fast) { sc = smat[0] * (lq - mm) + smat[1] * mm; nm_known = mm; }
+                        }
+                        if (!fast) for (int i = 0; i < lq; ++i) {
                             const int tb = rev ? 3 - (int)pac_get(ix.pac, tbase + i) : (int)pac_get(ix.pac, tbase + i);
                             sc += smat[tb * 5 + qat(i)];
                         }
@@ -682,28 +735,29 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE == 3 ? 6 : (MODE == 1 ? 4
                     }
                     if (!diagonal) {
                         const int wx = gen_cigar_band(o, lq, rlen, w2);
-                        // MODE 3 runs the band min(w, REG_WT3).  A path that leaves that band reaches a diagonal k = wr + 1 away from the
+                        // MODE 3 / 4 run the band min(w, WTM).  A path that leaves that band reaches a diagonal k = wr + 1 away from the
                         // main one and has to come back to the end cell: at least k gap bases on one side and k -+ (lq - rlen) on the other,
                         // so it scores at most ub.  If the score found inside the tight band beats ub, every decision along the traceback
                         // sees the same winner as under the band bwa_gen_cigar2 asks for (an alternative through outside cells, continued
                         // along the same suffix, would be a full path scoring >= the optimum): score and CIGAR are those of band w.
-                        const int w = MODE == 3 ? (wx < WTM ? wx : WTM) : wx;
-                        if (MODE == 3 && (!narrow_is_tight(o, lq, rlen, simple_mat) || rlen > NARROW_TMAX)) {
+                        const int w = MODE >= 3 ? (wx < WTM ? wx : WTM) : wx;
+                        if (MODE >= 3 && (!narrow_is_tight(o, lq, rlen, simple_mat, WTM) || rlen > NARROW_TMAX)) {
                             push_narrow(P.requeue, P.requeue_cap, P.requeue_cnt, P.requeue_big_cnt, jb, narrow_is_big(o, lq, rlen, jb.w2, simple_mat));
                             again = true; break;
                         }
                         const int n_col = lq < 2 * w + 1 ? lq : 2 * w + 1;
-                        if (MODE == 3) {}
+                        if (MODE >= 3) {}
                         else if ((MODE != 0 ? (w > WTM || !simple_mat) : (2 * w + 1 > NARROW_NC || P.big_go_wide)) || rlen > NARROW_TMAX) { go_wide = true; break; }
                         ++calls;
                         if (MODE != 0) {
                             score = global_dp_reg<WTM>(qg, lq, rev, ix.pac, tbase, rlen, w, smat[0], smat[1], smat[4], o.o_del, e_del, o.o_ins, e_ins, Z, cells);
-                            if (MODE == 3 && w < wx) {
+                            if (MODE >= 3 && w < wx) {
                                 const int k = w + 1, dl = lq - rlen;
                                 const int ubp = o.mat_max * (lq - k) - (o.o_ins + e_ins * k) - (o.o_del + e_del * (k - dl));
                                 const int ubm = o.mat_max * (rlen - k) - (o.o_del + e_del * k) - (o.o_ins + e_ins * (k + dl));
-                                if (score <= (ubp > ubm ? ubp : ubm)) {    // not provable: the band bwa asks for, same try
-                                    push_narrow(P.requeue, P.requeue_cap, P.requeue_cnt, P.requeue_big_cnt, jb, narrow_is_big(o, lq, rlen, jb.w2, simple_mat));
+                                if (score <= (ubp > ubm ? ubp : ubm)) {    // not provable: the next wider window, or the band bwa asks for; same try
+                                    if (MODE == 4 && P.tight) P.tight[atomicAdd(P.tight_cnt, 1u)] = jb;
+                                    else push_narrow(P.requeue, P.requeue_cap, P.requeue_cnt, P.requeue_big_cnt, jb, narrow_is_big(o, lq, rlen, jb.w2, simple_mat));
                                     again = true; break;
                                 }
                             }
@@ -780,7 +834,8 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE == 3 ? 6 : (MODE == 1 ? 4
                     }
                     // NM
                     int x = 0, y = 0, n_mm = 0, n_gap = 0;
-                    for (int k = 0; k < n_cigar; ++k) {
+                    if (nm_known >= 0 && n_cigar == 1) n_mm = nm_known;
+                    else for (int k = 0; k < n_cigar; ++k) {
                         const int op = (int)(cg[k] & 0xf), len = (int)(cg[k] >> 4);
                         if (op == 0) {
                             for (int i = 0; i < len; ++i) {
@@ -901,7 +956,7 @@ int finalize_resident_warps() {
 
 // resident warps of the two thread-per-region kernels and their traceback buffers (the kernels of a DP pass run side by side, so
 // each has its own: the register kernel's first, the shared-memory kernel's behind it)
-static void narrow_geometry(int* warps_smem, int* warps_reg, int* warps_reg2, size_t* zbytes_reg, size_t* zbytes_smem, int* warps_reg3 = nullptr) {
+static void narrow_geometry(int* warps_smem, int* warps_reg, int* warps_reg2, size_t* zbytes_reg, size_t* zbytes_smem, int* warps_reg3 = nullptr, int* warps_reg4 = nullptr) {
     const size_t smem = (size_t)NARROW_THREADS * (2 * NARROW_NC * 4 + NARROW_QMAX);
     const int nb = cached_blocks_per_sm(regs_cigar_narrow<0>, NARROW_THREADS, smem), nr = cached_blocks_per_sm(regs_cigar_narrow<1>, NARROW_THREADS, 0);
     const int nr2 = cached_blocks_per_sm(regs_cigar_narrow<2>, NARROW_THREADS, 0);
@@ -914,9 +969,13 @@ static void narrow_geometry(int* warps_smem, int* warps_reg, int* warps_reg2, si
     const size_t zs = (size_t)ws * NARROW_TMAX * NARROW_NC * 32, z2 = (size_t)wr2 * NARROW_TMAX * ((2 * REG_WT2 + 1 + 3) / 4) * 4 * 32;
     if (zbytes_smem) *zbytes_smem = zs > z2 ? zs : z2;
     const int wr3 = cached_blocks_per_sm(regs_cigar_narrow<3>, NARROW_THREADS, 0) * sms * (NARROW_THREADS / 32);
+    const int wr4 = cached_blocks_per_sm(regs_cigar_narrow<4>, NARROW_THREADS, 0) * sms * (NARROW_THREADS / 32);
     if (warps_reg3) *warps_reg3 = wr3;
+    if (warps_reg4) *warps_reg4 = wr4;
     const size_t z1 = (size_t)wr * NARROW_TMAX * ((2 * REG_WT + 1 + 3) / 4) * 4 * 32, z3 = (size_t)wr3 * NARROW_TMAX * ((2 * REG_WT3 + 1 + 3) / 4) * 4 * 32;
-    if (zbytes_reg) *zbytes_reg = z1 > z3 ? z1 : z3;    // the tight pass runs alone and shares the first buffer
+    const size_t z4 = (size_t)wr4 * NARROW_TMAX * ((2 * REG_WT4 + 1 + 3) / 4) * 4 * 32;
+    const size_t zm = z1 > z3 ? z1 : z3;
+    if (zbytes_reg) *zbytes_reg = zm > z4 ? zm : z4;    // the tight passes run alone and share the first buffer
 }
 
 size_t narrow_zbuf_bytes(int* n_warps_out) {
@@ -943,8 +1002,8 @@ void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts&
     if (!p.narrow_jobs) return;
     // phase 2: thread-per-region narrow-band mem_reg2aln, one try of the band-doubling loop per pass (<= 3 tries)
     {
-        int warps = 0, warps_reg = 0, warps_reg2 = 0, warps_reg3 = 0; size_t z_reg = 0;
-        narrow_geometry(&warps, &warps_reg, &warps_reg2, &z_reg, nullptr, &warps_reg3);
+        int warps = 0, warps_reg = 0, warps_reg2 = 0, warps_reg3 = 0, warps_reg4 = 0; size_t z_reg = 0;
+        narrow_geometry(&warps, &warps_reg, &warps_reg2, &z_reg, nullptr, &warps_reg3, &warps_reg4);
         // the scoring matrix of this path is mem_opt_init's and never changes (SURVEY B#5): match / mismatch / N, which is what the
         // register kernels assume; any other matrix takes the shared-memory kernel
         bool simple = true;
@@ -956,7 +1015,8 @@ void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts&
         NarrowJob* listA = reinterpret_cast<NarrowJob*>(p.narrow_jobs);
         NarrowJob* listB = listA + p.narrow_cap;
         NarrowJob* listS = listA + 2 * (size_t)p.narrow_cap;
-        NarrowJob* listT = listA + 3 * (size_t)p.narrow_cap;
+        NarrowJob* listT4 = listA + 3 * (size_t)p.narrow_cap;
+        NarrowJob* listT8 = listA + 4 * (size_t)p.narrow_cap;
         const size_t nsmem = (size_t)NARROW_THREADS * (2 * NARROW_NC * 4 + NARROW_QMAX);
         for (int pass = 0; pass < 4; ++pass) {
             // pass 0: equal-length regions (list S): diagonal proof, the rest joins list A; pass 1: DP regions (A -> re-queue B);
@@ -971,7 +1031,7 @@ void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts&
             q.requeue_big_cnt = p.narrow_cnt + (pass == 0 ? 5 : (pass == 1 ? 6 : (pass == 2 ? 7 : 4)));
             q.wide_jobs = p.wide_jobs; q.wide_cnt = p.wide_cnt; q.cigar_pool = p.cigar_pool; q.cigar_cap = p.cigar_cap; q.cigar_top = p.cigar_top;
             q.zbuf = p.narrow_z; q.overflow = p.overflow; q.counters = p.counters; q.diag_pass = pass == 0;
-            q.tight = p.narrow_tight && simple ? listT : nullptr; q.tight_cnt = p.narrow_cnt + NARROW_T_CNT;
+            q.tight = p.narrow_tight && simple ? listT4 : nullptr; q.tight_cnt = p.narrow_cnt + NARROW_T4_CNT;
             { static const bool btw = getenv("BSQ_FIN_BIG_TO_WIDE") != nullptr; q.big_go_wide = btw; }
             q.jobs = in; q.job_stride = 1; q.ticket = p.ticket + 1 + pass;
             q.n_jobs = p.narrow_cnt + (pass == 0 ? 3 : (pass == 1 ? 0 : (pass == 2 ? 1 : 2)));
@@ -980,10 +1040,14 @@ void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts&
                 regs_cigar_narrow<1><<<warps_reg / (NARROW_THREADS / 32), NARROW_THREADS, 0, st>>>(q, ix, o);
                 if (launches) ++*launches;
                 if (q.tight) {
-                    // pass T: every first try whose end cell fits the tight window; what it cannot prove joins list A, same try
-                    q.diag_pass = 0; q.jobs = listT; q.n_jobs = q.tight_cnt; q.ticket = p.ticket + 9; q.tight = nullptr;
+                    // passes T4, T8: every first try whose end cell fits the tight window; what T4 cannot prove goes to T8, what T8
+                    // cannot prove joins list A -- always the same try
+                    q.diag_pass = 0; q.jobs = listT4; q.n_jobs = p.narrow_cnt + NARROW_T4_CNT; q.ticket = p.ticket + 9;
+                    q.tight = listT8; q.tight_cnt = p.narrow_cnt + NARROW_T8_CNT;
+                    regs_cigar_narrow<4><<<warps_reg4 / (NARROW_THREADS / 32), NARROW_THREADS, 0, st>>>(q, ix, o);
+                    q.jobs = listT8; q.n_jobs = p.narrow_cnt + NARROW_T8_CNT; q.ticket = p.ticket + 10; q.tight = nullptr;
                     regs_cigar_narrow<3><<<warps_reg3 / (NARROW_THREADS / 32), NARROW_THREADS, 0, st>>>(q, ix, o);
-                    if (launches) ++*launches;
+                    if (launches) *launches += 2;
                 }
             } else {
                 // the two kernels of a DP pass work on disjoint sections of the list: side by side when a side stream is there

@@ -102,11 +102,11 @@ struct FinalizeParams {
     const int64_t* ann_id;
     // narrow-band regions are queued (read << 32 | row slot) for the thread-per-region kernel; regions that
     // need a wider band on a retry come back through wide_jobs.  narrow_jobs == nullptr disables the split.
-    bool narrow_tight = true;      // first tries go through the tight-band pass (list T, the fourth list of narrow_jobs)
-    void* narrow_jobs; uint32_t narrow_cap;   // four lists of narrow_cap job records (24 B each): A, B (ping-pong between tries), S (equal-length regions), T (tight first tries)
+    bool narrow_tight = true;      // first tries go through the tight-band pass (lists T4, T8 of narrow_jobs)
+    void* narrow_jobs; uint32_t narrow_cap;   // five lists of narrow_cap job records (24 B each): A, B (ping-pong between tries), S (equal-length regions), T4, T8 (tight first tries)
     uint32_t* narrow_cnt;                     // eight consecutive counters: list A, list B, list A (third tries), list S, sink, wide-band hand-over lists of passes 1..3
     uint64_t* wide_jobs; uint32_t* wide_cnt; uint8_t* narrow_z; int narrow_warps;
-    uint32_t* ticket;              // ten consecutive tickets: finalize, narrow pass 0..3, wide, shared-memory narrow kernel of passes 1..3, tight pass
+    uint32_t* ticket;              // eleven consecutive tickets: finalize, narrow pass 0..3, wide, shared-memory narrow kernel of passes 1..3, the two tight passes
     uint32_t* overflow;
     uint32_t* need_rseq;           // see ExtendParams
     unsigned long long* counters;  // optional: [0] = ksw_global2 cells, [1] = calls

@@ -20,7 +20,8 @@ _lib.check(ix.L.bsq_debug_ctl(ix.h, ctl.ctypes.data_as(C.c_void_p)))
 names = ["A front (DP tries 1)", "B front (tries 2)", "A front (tries 3)", "S (equal-length, diagonal pass)", "sink", "A back", "B back", "A back (tries 3)"]
 for k, nme in enumerate(names):
     print("%-34s %9d" % (nme, ctl[32 + k]))
-print("%-34s %9d" % ("T (tight first tries)", ctl[50]))
+print("%-34s %9d" % ("T4 (tight first tries, 9 columns)", ctl[52]))
+print("%-34s %9d" % ("T8 (17 columns)", ctl[53]))
 print("wide jobs", ctl[25], "cigar words", ctl[6], "counters", ix.counters())
 res = ix.download_result()
 print("rows", int(res.row_off[-1]), "digest", bench.rows_digest(res))

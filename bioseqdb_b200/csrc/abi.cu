@@ -77,7 +77,7 @@ struct Batch {
     std::vector<bsq_row_ext> ext_tmp;   // extension records fetched only to finish a MAPQ on the host
     uint32_t* ctl_host = nullptr;       // pinned, 16 words: ctl[0..7], total rows (2 words), host-MAPQ flag
     cudaEvent_t ev[5]; bool ev_ok = false;
-    cudaEvent_t ev_x[4]; bool evx_ok = false;   // chunked mode: upload begin/end, download begin/end
+    cudaEvent_t ev_x[5]; bool evx_ok = false;   // chunked mode: upload begin/end, download begin/end, pipeline queued
     ExtAux ext_aux; bool ext_aux_ok = false;    // side streams of the extension pre-pass
     uint32_t att_rseq_cap = 0; bool idle = true;
     uint64_t out_rows = 0; uint32_t out_cig = 0;
@@ -1149,7 +1149,13 @@ int align_chunked(bsq_index* h, const ReadSrc& S, uint64_t n, bsq_result** out, 
         cudaEventRecord(b.ev_x[0], b.st);
         if (upload_src(h, b, S, s0, cnt) != BSQ_OK) return BSQ_ERR;
         cudaEventRecord(b.ev_x[1], b.st);
-        return pipeline_enqueue(h, b);
+        // BSQ_CHUNK_SERIAL: chunk c's kernels start behind chunk c-1's (its copies still overlap them), so that an earlier chunk is
+        // finished -- and its download under way -- while the later one computes, instead of both sharing the SMs to the end
+        static const bool serial = getenv("BSQ_CHUNK_SERIAL") != nullptr;
+        if (serial && c > 0) cudaStreamWaitEvent(b.st, lane[(c & 1) ^ 1]->ev_x[4], 0);
+        const int rc2 = pipeline_enqueue(h, b);
+        cudaEventRecord(b.ev_x[4], b.st);
+        return rc2;
     };
     struct Pending { bool on = false; uint64_t c = 0, n = 0, n_rows = 0, row_base = 0, cig_base = 0; bool host_mapq = false; } pend;
     ResultImpl* R = nullptr;

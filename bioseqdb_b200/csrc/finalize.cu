@@ -214,6 +214,7 @@ __device__ __forceinline__ bool mat_is_simple(const int* smat) {
 constexpr int REG_WT = 16;
 // tight first tries: MODE 4 runs a 9-column window, MODE 3 a 17-column one; a result is accepted only when no path that leaves
 // the window can reach the score found inside it (lists T4 -> T8 -> A)
+constexpr uint32_t NARROW_SHORT_LIST = 1024;
 constexpr int REG_WT3 = 8;
 constexpr int REG_WT4 = 4;
 constexpr int NARROW_T4_CNT = 20, NARROW_T8_CNT = 21;   // counters of lists T4 / T8 behind narrow_cnt (ctl words 52, 53)
@@ -507,10 +508,14 @@ __global__ void __launch_bounds__(FIN_THREADS, 6) regs_finalize(FinalizeParams P
 // ksw_global2 has it for cells it never computes; their H is never consumed).  The query travels in a nibble
 // window that slides one base per row; scores come from the three distinct values of bwa_fill_scmat.
 // Z (traceback): one byte per cell, [row][kk / 4][lane] words.  Returns eh[qlen].h.
-template <int WT>
+// TIGHT (the tight passes): rows whose whole window lies inside the matrix and the band (w == WT, WT < i, i + WT < lq) take a leaner
+// cell -- no validity masks, no first-column case, match / mismatch from one XOR of the window with the row's base.  That cell
+// scores an ambiguous query base as a mismatch, so the caller must discard the result when *amb has a bit above the low two.
+template <int WT, bool TIGHT>
 __device__ __forceinline__ int global_dp_reg(const uint8_t* __restrict__ qg, int lq, bool rev, const uint8_t* __restrict__ pac, int64_t tbase,
                                              int rlen, int w, int sA, int sB, int sN, int o_del, int e_del, int o_ins, int e_ins,
-                                             uint32_t* __restrict__ Z, unsigned long long& cells) {
+                                             uint32_t* __restrict__ Z, unsigned long long& cells, uint32_t* amb_out = nullptr) {
+    uint32_t amb = 0;
     constexpr int W = 2 * WT + 1, NW = (W + 7) / 8, ZW = (W + 3) / 4;
     const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
     int Hd[W], Ep[W + 1];
@@ -529,6 +534,7 @@ __device__ __forceinline__ int global_dp_reg(const uint8_t* __restrict__ qg, int
         const int j = kk - WT;
         if (j < lq) {
             const uint32_t b = rev ? qg[lq - 1 - j] : qg[j];
+            amb |= b;
             win[kk >> 3] = (win[kk >> 3] & ~(15u << ((kk & 7) * 4))) | (b << ((kk & 7) * 4));
         }
     }
@@ -544,10 +550,36 @@ __device__ __forceinline__ int global_dp_reg(const uint8_t* __restrict__ qg, int
         // next row's inputs: reference base, query base entering the window
         int tb_next = 0; uint32_t nb = 15u;
         if (i + 1 < rlen) tb_next = rev ? 3 - (int)pac_get(pac, tbase + i + 1) : (int)pac_get(pac, tbase + i + 1);
-        { const int jn = i + 1 + WT; if (jn < lq) nb = rev ? qg[lq - 1 - jn] : qg[jn]; }
+        { const int jn = i + 1 + WT; if (jn < lq) { nb = rev ? qg[lq - 1 - jn] : qg[jn]; amb |= nb; } }
         int f = KSW_NEG_INF;
         uint32_t zpack = 0;
         uint32_t* zi = Z + (size_t)i * ZW * 32;
+        if (TIGHT && w == WT && i > WT && i + WT + 1 <= lq) {
+            uint32_t xw[NW];
+#pragma unroll
+            for (int x = 0; x < NW; ++x) xw[x] = win[x] ^ ((uint32_t)tb * 0x11111111u);
+#pragma unroll
+            for (int kk = 0; kk < W; ++kk) {
+                const bool mis = ((xw[kk >> 3] >> ((kk & 7) * 4)) & 15u) != 0;
+                const int m = Hd[kk] + (mis ? sB : sA);
+                int e = Ep[kk + 1];
+                int d = m >= e ? 0 : 1;
+                int h = m >= e ? m : e;
+                d = h >= f ? d : 2;
+                h = h >= f ? h : f;
+                Hd[kk] = h;
+                int tt = m - oe_del;
+                e -= e_del;
+                d |= e > tt ? 1 << 2 : 0;
+                Ep[kk] = e > tt ? e : tt;
+                tt = m - oe_ins;
+                f -= e_ins;
+                d |= f > tt ? 2 << 4 : 0;
+                f = f > tt ? f : tt;
+                zpack |= (uint32_t)d << ((kk & 3) * 8);
+                if ((kk & 3) == 3 || kk == W - 1) { zi[(kk >> 2) * 32] = zpack; zpack = 0; }
+            }
+        } else
 #pragma unroll
         for (int kk = 0; kk < W; ++kk) {
             const int t = ioff + kk;
@@ -585,6 +617,7 @@ __device__ __forceinline__ int global_dp_reg(const uint8_t* __restrict__ qg, int
     int score = KSW_NEG_INF;
 #pragma unroll
     for (int kk = 0; kk < W; ++kk) if (kk == ks) score = Hd[kk];
+    if (TIGHT && amb_out) *amb_out = amb;
     return score;
 }
 
@@ -645,13 +678,15 @@ struct NarrowParams {
     uint8_t* zbuf; uint32_t* ticket; uint32_t* overflow; unsigned long long* counters;
     int big_go_wide; // experiment (BSQ_FIN_BIG_TO_WIDE): bands wider than the register window go to the warp-cooperative kernel
     NarrowJob* tight; uint32_t* tight_cnt;   // list T: first tries the tight pass (MODE 3) takes; nullptr = no tight pass
+    uint32_t short_list;   // lists of at most this many regions are handed to the warp-cooperative kernel (BSQ_FIN_SHORT_LIST)
     int diag_pass;   // 1: equal-length regions -- finish the ones whose diagonal is provably optimal, hand the rest to the DP list
 };
 
+// MODE 5: the diagonal pass only (no DP code, few registers: the pass is a chain of dependent loads per region and lives on occupancy).
 // MODE 0: circular row window in shared memory (bands up to NARROW_NC columns); MODE 1: the band in registers
 // (global_dp_reg, w <= REG_WT), no shared memory, regions with a wider band are passed on to a MODE 0 launch.
 template <int MODE>
-__global__ void __launch_bounds__(NARROW_THREADS, MODE >= 3 ? 6 : (MODE == 1 ? 4 : (MODE == 2 ? 2 : 1))) regs_cigar_narrow(NarrowParams P, DevIndex ix, DevOpts o) {
+__global__ void __launch_bounds__(NARROW_THREADS, MODE == 5 ? 10 : (MODE >= 3 ? 6 : (MODE == 1 ? 4 : (MODE == 2 ? 2 : 1)))) regs_cigar_narrow(NarrowParams P, DevIndex ix, DevOpts o) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ int smat[25];
     if (threadIdx.x < 25) smat[threadIdx.x] = o.mat[threadIdx.x];
@@ -672,11 +707,18 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE >= 3 ? 6 : (MODE == 1 ? 4
     asm volatile("" : "+r"(oe_del), "+r"(oe_ins), "+r"(e_del), "+r"(e_ins));
     const int64_t l_pac = ix.l_pac;
     const uint32_t n_jobs = *P.n_jobs;
+    // A short list is a latency problem for one thread per region (a launch lasts as long as ONE region's DP, hundreds of
+    // microseconds): its regions go to the warp-cooperative kernel, which runs a row's cells side by side.
+    const bool short_list = MODE != 0 && !P.diag_pass && n_jobs <= P.short_list;
     unsigned long long cells = 0, calls = 0;
     for (;;) {
         uint32_t t = next_ticket(P.ticket);
         if ((uint64_t)t * 32 >= n_jobs) break;
         const uint32_t j_id = t * 32 + lane;
+        uint32_t cg[NARROW_CIG];
+        // what the lane has to write into the CIGAR pool (one allocation per warp, behind the region's work)
+        int e_nc = 0, e_first = 0, e_clip5 = 0, e_clip3 = 0, e_n = 0;
+        uint32_t e_slot = 0; bool e_on = false;
         if (j_id < n_jobs) {
             const NarrowJob jb = P.jobs[(long)j_id * P.job_stride];
             const uint32_t r = jb.r, slot = jb.slot;
@@ -693,7 +735,6 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE >= 3 ? 6 : (MODE == 1 ? 4
             const uint8_t* qg = P.seqs + P.offs[r] + qb;
             if (MODE == 0) for (int j = 0; j < lq; ++j) Q[j * NARROW_THREADS] = rev ? qg[lq - 1 - j] : qg[j];
             auto qat = [&](int j) -> int { return MODE == 0 ? (int)Q[j * NARROW_THREADS] : (int)(rev ? qg[lq - 1 - j] : qg[j]); };
-            uint32_t cg[NARROW_CIG];
             // ONE try of the band-doubling loop per pass; a region that needs another try is re-queued so that the
             // lanes of a warp stay balanced (the loop state travels in the job record)
             int n_cigar = 0, NM = -1, score = jb.score;
@@ -701,6 +742,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE >= 3 ? 6 : (MODE == 1 ? 4
             bool go_wide = false, again = false;
             do {
                 n_cigar = 0; NM = -1;
+                if (short_list && !reject) { go_wide = true; break; }
                 int nm_known = -1;       // mismatches of a gap-free row, when the packed comparison has counted them already
                 if (!reject) {
                     bool diagonal = lq == rlen && w2 == 0;   // bwa_gen_cigar2's own no-DP case
@@ -733,7 +775,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE >= 3 ? 6 : (MODE == 1 ? 4
                         }
                         score = sc; cg[0] = (uint32_t)lq << 4; n_cigar = 1;
                     }
-                    if (!diagonal) {
+                    if (MODE != 5 && !diagonal) {
                         const int wx = gen_cigar_band(o, lq, rlen, w2);
                         // MODE 3 / 4 run the band min(w, WTM).  A path that leaves that band reaches a diagonal k = wr + 1 away from the
                         // main one and has to come back to the end cell: at least k gap bases on one side and k -+ (lq - rlen) on the other,
@@ -750,7 +792,12 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE >= 3 ? 6 : (MODE == 1 ? 4
                         else if ((MODE != 0 ? (w > WTM || !simple_mat) : (2 * w + 1 > NARROW_NC || P.big_go_wide)) || rlen > NARROW_TMAX) { go_wide = true; break; }
                         ++calls;
                         if (MODE != 0) {
-                            score = global_dp_reg<WTM>(qg, lq, rev, ix.pac, tbase, rlen, w, smat[0], smat[1], smat[4], o.o_del, e_del, o.o_ins, e_ins, Z, cells);
+                            uint32_t amb = 0;
+                            score = global_dp_reg<WTM, (MODE >= 3)>(qg, lq, rev, ix.pac, tbase, rlen, w, smat[0], smat[1], smat[4], o.o_del, e_del, o.o_ins, e_ins, Z, cells, &amb);
+                            if (MODE >= 3 && (amb & ~3u)) {            // an ambiguous base in the query: the exact-band kernels score it
+                                push_narrow(P.requeue, P.requeue_cap, P.requeue_cnt, P.requeue_big_cnt, jb, narrow_is_big(o, lq, rlen, jb.w2, simple_mat));
+                                again = true; break;
+                            }
                             if (MODE >= 3 && w < wx) {
                                 const int k = w + 1, dl = lq - rlen;
                                 const int ubp = o.mat_max * (lq - k) - (o.o_ins + e_ins * k) - (o.o_del + e_del * (k - dl));
@@ -838,7 +885,12 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE >= 3 ? 6 : (MODE == 1 ? 4
                     else for (int k = 0; k < n_cigar; ++k) {
                         const int op = (int)(cg[k] & 0xf), len = (int)(cg[k] >> 4);
                         if (op == 0) {
-                            for (int i = 0; i < len; ++i) {
+                            bool fast = false;
+                            int mm = 0;
+                            // a run of M: q[x .. x+len) against the reference from y on -- the packed comparison of the diagonal pass
+                            if (MODE != 0 && len >= 16) mm = diag_mismatches(rev ? qg + (lq - x - len) : qg + x, len, rev, ix.pac, tbase + y, &fast);
+                            if (fast) n_mm += mm;
+                            else for (int i = 0; i < len; ++i) {
                                 const int tb = rev ? 3 - (int)pac_get(ix.pac, tbase + y + i) : (int)pac_get(ix.pac, tbase + y + i);
                                 n_mm += qat(x + i) != tb;
                             }
@@ -869,20 +921,33 @@ __global__ void __launch_bounds__(NARROW_THREADS, MODE >= 3 ? 6 : (MODE == 1 ? 4
                 }
                 int clip5 = 0, clip3 = 0;
                 if (qb != 0 || qe != l_read) { clip5 = is_rev ? l_read - qe : qb; clip3 = is_rev ? qb : l_read - qe; }
-                const int n_out = nc + (clip5 ? 1 : 0) + (clip3 ? 1 : 0);
-                uint32_t coff = n_out ? atomicAdd(P.cigar_top, (uint32_t)n_out) : 0u;
+                e_nc = nc; e_first = first; e_clip5 = clip5; e_clip3 = clip3; e_n = nc + (clip5 ? 1 : 0) + (clip3 ? 1 : 0);
+                e_slot = slot; e_on = true;
                 RowDev* out = P.rows + slot;
-                if ((uint64_t)coff + (uint64_t)n_out > (uint64_t)P.cigar_cap) { atomicExch(P.overflow, 1u); }
+                const int rid = bns_pos2rid(ix, pos);
+                out->NM = NM; out->is_rev = is_rev; out->pos = pos - ix.ann_offset[rid < 0 ? 0 : rid];
+            }
+        }
+        __syncwarp();
+        {   // pool space for the warp's CIGARs: one atomic (a million single-lane atomics on one word are a stage of their own)
+            uint32_t incl = (uint32_t)e_n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t up = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += up; }
+            uint32_t base = 0;
+            if (lane == 31 && incl) base = atomicAdd(P.cigar_top, incl);
+            base = __shfl_sync(FULL, base, 31);
+            if (e_on) {
+                const uint32_t coff = base + incl - (uint32_t)e_n;
+                RowDev* out = P.rows + e_slot;
+                if ((uint64_t)coff + (uint64_t)e_n > (uint64_t)P.cigar_cap) { atomicExch(P.overflow, 1u); }
                 else {
                     uint32_t* dst = P.cigar_pool + coff;
                     int k = 0;
-                    if (clip5) dst[k++] = (uint32_t)clip5 << 4 | 3;
-                    for (int c = 0; c < nc; ++c) dst[k++] = cg[first + c];
-                    if (clip3) dst[k++] = (uint32_t)clip3 << 4 | 3;
-                    out->cigar_off = coff; out->n_cigar = (uint32_t)n_out;
+                    if (e_clip5) dst[k++] = (uint32_t)e_clip5 << 4 | 3;
+                    for (int c = 0; c < e_nc; ++c) dst[k++] = cg[e_first + c];
+                    if (e_clip3) dst[k++] = (uint32_t)e_clip3 << 4 | 3;
+                    out->cigar_off = coff; out->n_cigar = (uint32_t)e_n;
                 }
-                const int rid = bns_pos2rid(ix, pos);
-                out->NM = NM; out->is_rev = is_rev; out->pos = pos - ix.ann_offset[rid < 0 ? 0 : rid];
             }
         }
         __syncwarp();
@@ -1033,11 +1098,13 @@ void launch_finalize(const FinalizeParams& p, const DevIndex& ix, const DevOpts&
             q.zbuf = p.narrow_z; q.overflow = p.overflow; q.counters = p.counters; q.diag_pass = pass == 0;
             q.tight = p.narrow_tight && simple ? listT4 : nullptr; q.tight_cnt = p.narrow_cnt + NARROW_T4_CNT;
             { static const bool btw = getenv("BSQ_FIN_BIG_TO_WIDE") != nullptr; q.big_go_wide = btw; }
+            { static const uint32_t sl = getenv("BSQ_FIN_SHORT_LIST") ? (uint32_t)atoi(getenv("BSQ_FIN_SHORT_LIST")) : NARROW_SHORT_LIST; q.short_list = sl; }
             q.jobs = in; q.job_stride = 1; q.ticket = p.ticket + 1 + pass;
             q.n_jobs = p.narrow_cnt + (pass == 0 ? 3 : (pass == 1 ? 0 : (pass == 2 ? 1 : 2)));
             if (pass == 0) {
-                // the diagonal proof needs no band state: the register kernel's geometry (no shared memory, 4 CTAs per SM)
-                regs_cigar_narrow<1><<<warps_reg / (NARROW_THREADS / 32), NARROW_THREADS, 0, st>>>(q, ix, o);
+                // the diagonal proof needs no band state: a build of the kernel without the DP (12 CTAs per SM)
+                static const int warps_diag = cached_blocks_per_sm(regs_cigar_narrow<5>, NARROW_THREADS, 0) * cached_sm_count() * (NARROW_THREADS / 32);
+                regs_cigar_narrow<5><<<warps_diag / (NARROW_THREADS / 32), NARROW_THREADS, 0, st>>>(q, ix, o);
                 if (launches) ++*launches;
                 if (q.tight) {
                     // passes T4, T8: every first try whose end cell fits the tight window; what T4 cannot prove goes to T8, what T8

@@ -22,6 +22,7 @@ for k, nme in enumerate(names):
     print("%-34s %9d" % (nme, ctl[32 + k]))
 print("%-34s %9d" % ("T4 (tight first tries, 9 columns)", ctl[52]))
 print("%-34s %9d" % ("T8 (17 columns)", ctl[53]))
+print("reads left for regs_finalize (warp per read)", ctl[58])
 print("wide jobs", ctl[25], "cigar words", ctl[6], "counters", ix.counters())
 res = ix.download_result()
 print("rows", int(res.row_off[-1]), "digest", bench.rows_digest(res))

@@ -13,6 +13,9 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 # tests use small batches but are there to check the throughput path (thread-per-extension / thread-per-region kernels), so they switch the
 # routing off.  tests/test_gpu_align.py::test_small_batch_routing covers the default routing in a process of its own.
 os.environ.setdefault("BSQ_SMALL_BATCH_READS", "0")
+# Likewise the finalize stage hands job lists of at most BSQ_FIN_SHORT_LIST (default 1024) regions to its warp-cooperative kernel; the
+# parity tests keep the thread-per-region kernels in play.  test_small_batch_routing runs with the defaults.
+os.environ.setdefault("BSQ_FIN_SHORT_LIST", "0")
 
 
 def pytest_configure(config):

@@ -227,7 +227,7 @@ def test_small_batch_routing(gpu_lib):
     import os
     import subprocess
     import sys
-    env = {k: v for k, v in os.environ.items() if k != "BSQ_SMALL_BATCH_READS"}
+    env = {k: v for k, v in os.environ.items() if k not in ("BSQ_SMALL_BATCH_READS", "BSQ_FIN_SHORT_LIST")}
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=env, capture_output=True, timeout=600)
     assert p.returncode == 0, (p.stdout.decode()[-1500:], p.stderr.decode()[-1500:])

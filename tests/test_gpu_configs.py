@@ -128,3 +128,36 @@ def test_replica_with_host_state(gpu_lib):
     assert np.array_equal(ts.off, tr.off) and np.array_equal(ts.data, tr.data) and np.array_equal(ts.ref_match, tr.ref_match)
     assert [mm.ref_subseq for mm in src.matches(rs, 0, reads[0])] == [mm.ref_subseq for mm in rep.matches(rr, 0, reads[0])]
     assert any(b"N" in mm.ref_subseq for mm in rep.matches(rr, 0, reads[0]))
+
+
+_DEFAULT_ROUTING = r"""
+import sys
+sys.path.insert(0, "tests")
+import oracle_lib as O
+from bioseqdb_b200 import synth
+from helpers import build_pair, parity_report
+rows = synth.plant_repeats(synth.reference_rows(synth.config_row_lengths("C1")), n_families=100, copies=8)
+orc, gpu = build_pair(rows, O.%s(len(rows)))
+# noisy reads with long indels: the 9- and 17-column tight passes leave work for the exact-band lists, which are short
+seqs, offs, _ = synth.simulate_reads(rows, 60_000, 150, sub=0.03, ins=0.004, dele=0.004, seed=synth.SEED_READS + 91)
+ids = synth.lrand48_ids_fast(60_000)
+g = gpu.align_batch(seqs, offs, ids)
+o = orc.align_batch(seqs, offs, ids, 8)
+rep = parity_report(g, o)
+assert rep["reads_checked"] == 60_000 and rep["mismatching_reads"] == 0, rep
+print("routing ok", int(g.row_off[-1]))
+"""
+
+
+@pytest.mark.parametrize("opts_name", ["sql_default_opts", "canonical_opts"])
+def test_default_list_routing(gpu_lib, opts_name):
+    """The suite runs with BSQ_SMALL_BATCH_READS=0 and BSQ_FIN_SHORT_LIST=0 so that small cases reach the thread-per-region kernels; the
+    library's own defaults -- short job lists handed to the warp-cooperative kernel -- get a 60 k-read case in a process of their own."""
+    import os
+    import subprocess
+    import sys
+    env = {k: v for k, v in os.environ.items() if k not in ("BSQ_SMALL_BATCH_READS", "BSQ_FIN_SHORT_LIST")}
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", _DEFAULT_ROUTING % opts_name], cwd=root, env=env, capture_output=True, timeout=900)
+    assert p.returncode == 0, (p.stdout.decode()[-1500:], p.stderr.decode()[-3000:])
+    assert b"routing ok" in p.stdout

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <vector>
+#include <chrono>
 #include <algorithm>
 #include <mutex>
 #include "../../include/bioseqdb_gpu.h"
@@ -53,6 +54,8 @@ struct Batch {
     DevBuf<uint8_t> datums; DevBuf<uint64_t> datum_off, scan_tmp64;
     DevBuf<uint8_t> ascii;              // the reads as text (what to_text_palloc yields): the row materialisation reads query_subseq from it
     uint64_t res_serial = 0, res_read_base = 0, res_row_base = 0, res_cig_base = 0;
+    DevBuf<uint64_t> row_off64;        // the result's view of row_off: 64-bit, counted from the start of the whole result
+    uint64_t cig_rebased = 0;          // what has been added to rows_compact[].cigar_off so far (reset when the rows are written again)
     DevBuf<uint64_t> tup_off, tup_tmp; DevBuf<uint32_t> tup_row_read, tup_nholes; DevBuf<int32_t> tup_rm; DevBuf<uint8_t> tup_bytes;   // row materialisation from the resident batch   // the result (and the place in it) this batch's rows went to   // reads handed over as NUCLSEQ datum images (upload_datums)
     DevBuf<Intv> intv; DevBuf<uint32_t> intv_cnt; uint32_t intv_cap = 0;
     DevBuf<Intv> seed_scratch; uint32_t list_cap = 0;
@@ -113,6 +116,7 @@ struct bsq_index {
     uint32_t* d_kmer_z = nullptr;    // sizes-only copy of the prefix table
     void* d_kmer = nullptr; int kmer_k = 0;          // k-mer table of the LAST-like seeding pass (built lazily per device index)
     bool collect_counters = false;
+    int prio_hi = 0, prio_lo = 0;          // stream priorities of the two lanes of the chunked pipeline
     uint32_t flags = 0;              // BSQ_FLAG_*
     uint64_t lrand_state = 0;        // glibc lrand48 state of the session (one draw per aligned read when the caller passes no ids)
     bool replica_pending = false;    // device arrays allocated by bsq_index_alloc_replica, host mirrors not yet rebuilt (bsq_index_replica_finish)
@@ -169,7 +173,13 @@ bsq_index* bsq_index_new(const bsq_opts* o, int device) {
     h->device = device; h->opts = *o;
     memset(&h->meta, 0, sizeof(h->meta)); memset(&h->timing, 0, sizeof(h->timing));
     fill_dev_opts(h);
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { bsq_set_error("cudaStreamCreate failed"); delete h; return nullptr; }
+    // The main stream (and lane 0 of the chunked pipeline) outranks lane 1: two chunks share the SMs, the earlier one gets free ones
+    // first and is done -- its result on the way to the host -- while the later one still computes.  BSQ_NO_STREAM_PRIO: equal ranks.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (getenv("BSQ_NO_STREAM_PRIO")) prio_hi = prio_lo;
+    h->prio_hi = prio_hi; h->prio_lo = prio_lo;
+    if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { bsq_set_error("cudaStreamCreate failed"); delete h; return nullptr; }
     h->batch.st = h->stream;
     return h;
 }
@@ -806,7 +816,7 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
         ENS(b.ext_memo_hist.ensure(6 * EXT_MEMO_BINS)); ENS(b.ext_todo.ensure(n));
     }
     if (!b.ext_aux_ok && !small_batch) {
-        for (auto& s_ : b.ext_aux.st) ENS(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
+        for (auto& s_ : b.ext_aux.st) ENS(cudaStreamCreateWithPriority(&s_, cudaStreamNonBlocking, &b == &h->batch ? h->prio_hi : h->prio_lo));
         for (auto& e : b.ext_aux.ev) ENS(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         b.ext_aux_ok = true;
     }
@@ -877,6 +887,7 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
         ENS(b.rows_ext.ensure(b.rows_cap));
         MapqParams M; M.a = h->opts.a; M.b = h->opts.b; M.min_seed_len = h->opts.min_seed_len; M.coef_len = h->mapQ_coef_len;
         M.coef_fac = (double)h->mapQ_coef_fac; M.logtab = h->d_logtab;
+        b.cig_rebased = 0;
         k_compact_rows<<<(unsigned)std::min<uint32_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(b.blocks.p, b.rows.p, b.row_cnt.p, b.row_off.p, n, b.rows_compact.p, b.rows_ext.p,
                                                 (uint32_t)std::min<uint64_t>(b.rows_cap, 0xffffffffull), M, b.ctl.p + 30); ++T.launches;
     }
@@ -1044,6 +1055,15 @@ void result_delete(ResultImpl* R) {
 
 // Compacts the aligned batch's rows on the device (+ MAPQ) and starts the copies into the result: the batch's reads are
 // reads [read_base, read_base + b.n) of the result, its rows go to row_base, its CIGAR words to cig_base.
+// A chunk's place in the whole result, applied on the device ahead of the copy: 64-bit row offsets from the chunk's 32-bit ones, CIGAR
+// offsets moved behind the earlier chunks' words (a host loop over a million 64-byte records costs more than the copy itself).
+static __global__ void k_result_rebase(const uint32_t* __restrict__ row_off, uint64_t n, uint64_t row_base, uint64_t* __restrict__ row_off64,
+                                       RowPub* __restrict__ rows, uint64_t n_rows, uint32_t cig_delta) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint64_t i = t0; i < n; i += stride) row_off64[i] = row_base + row_off[i];
+    if (cig_delta) for (uint64_t i = t0; i < n_rows; i += stride) if (rows[i].n_cigar) rows[i].cigar_off += cig_delta;
+}
+
 int download_enqueue(bsq_index* h, Batch& b, ResultImpl* R, uint64_t read_base, uint64_t row_base, uint64_t cig_base) {
     const uint64_t n = b.n;
     if (n == 0 || !h->meta.built || !b.aligned) return BSQ_OK;
@@ -1051,7 +1071,12 @@ int download_enqueue(bsq_index* h, Batch& b, ResultImpl* R, uint64_t read_base, 
     if (row_base + total_rows > R->row_cap || cig_base + cig_top > R->cig_cap || cig_base + cig_top > 0xffffffffull) { bsq_set_error("result block too small"); return BSQ_ERR; }
     cudaStream_t st = b.st;
     b.res_serial = R->serial; b.res_read_base = read_base; b.res_row_base = row_base; b.res_cig_base = cig_base;
-    CUDA_CHECK(cudaMemcpyAsync(R->o32 + read_base, b.row_off.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(b.row_off64.ensure(n + 1));
+    k_result_rebase<<<(unsigned)std::min<uint64_t>((std::max<uint64_t>(n, total_rows) + 255) / 256, 148 * 8), 256, 0, st>>>(
+        b.row_off.p, n, row_base, b.row_off64.p, b.rows_compact.p, total_rows, (uint32_t)(cig_base - b.cig_rebased));
+    ++h->timing.launches;
+    b.cig_rebased = cig_base;
+    CUDA_CHECK(cudaMemcpyAsync(R->pub.row_off + read_base, b.row_off64.p, n * 8, cudaMemcpyDeviceToHost, st));
     if (total_rows) CUDA_CHECK(cudaMemcpyAsync(R->pub.rows + row_base, b.rows_compact.p, total_rows * sizeof(bsq_row), cudaMemcpyDeviceToHost, st));
     if (total_rows && R->ext) CUDA_CHECK(cudaMemcpyAsync(R->ext + row_base, b.rows_ext.p, total_rows * sizeof(bsq_row_ext), cudaMemcpyDeviceToHost, st));
     else if (total_rows && b.ctl_host[10]) {   // rare: a MAPQ to finish on the host although the caller did not ask for the extension records
@@ -1059,7 +1084,7 @@ int download_enqueue(bsq_index* h, Batch& b, ResultImpl* R, uint64_t read_base, 
         CUDA_CHECK(cudaMemcpyAsync(b.ext_tmp.data(), b.rows_ext.p, total_rows * sizeof(bsq_row_ext), cudaMemcpyDeviceToHost, st));
     }
     if (cig_top) CUDA_CHECK(cudaMemcpyAsync(R->pub.cigar + cig_base, b.cigar.p, (size_t)cig_top * 4, cudaMemcpyDeviceToHost, st));
-    h->timing.d2h_bytes += n * 4 + 12 + total_rows * (sizeof(bsq_row) + (R->ext ? sizeof(bsq_row_ext) : 0)) + (uint64_t)cig_top * 4;
+    h->timing.d2h_bytes += n * 8 + 12 + total_rows * (sizeof(bsq_row) + (R->ext ? sizeof(bsq_row_ext) : 0)) + (uint64_t)cig_top * 4;
     return BSQ_OK;
 }
 
@@ -1068,9 +1093,7 @@ int download_enqueue(bsq_index* h, Batch& b, ResultImpl* R, uint64_t read_base, 
 void download_finish(bsq_index* h, ResultImpl* R, uint64_t n, uint64_t read_base, uint64_t n_rows, uint64_t row_base, uint64_t cig_base, bool host_mapq,
                      const bsq_row_ext* ext_tmp) {
     if (!h->meta.built) { for (uint64_t i = 0; i < n; ++i) R->pub.row_off[read_base + i] = row_base; return; }
-    for (uint64_t i = 0; i < n; ++i) R->pub.row_off[read_base + i] = row_base + R->o32[read_base + i];
-    if (cig_base)   // the batch is one chunk of a larger result: its CIGAR words follow the earlier chunks'
-        for (uint64_t i = row_base; i < row_base + n_rows; ++i) if (R->pub.rows[i].n_cigar) R->pub.rows[i].cigar_off += (uint32_t)cig_base;
+    (void)cig_base;     // row offsets and CIGAR offsets were put in place on the device (k_result_rebase)
     if (n_rows && host_mapq) {
         // alignments longer than the device's log table: mem_approx_mapq_se with libm on the host, from the extension records
         const bsq_row_ext* ext = R->ext ? R->ext + row_base : ext_tmp;
@@ -1120,9 +1143,14 @@ int upload_src(bsq_index* h, Batch& b, const ReadSrc& S, uint64_t s0, uint64_t c
 int align_chunked(bsq_index* h, const ReadSrc& S, uint64_t n, bsq_result** out, bool* fell_back) {
     *fell_back = false;
     if (!h->stream2) {
-        CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, h->prio_lo));
         h->batch2.st = h->stream2;
     }
+    static const bool trace = getenv("BSQ_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what, uint64_t c) {
+        if (trace) fprintf(stderr, "[bsq trace] %8.3f ms  %s %llu\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), what, (unsigned long long)c);
+    };
     Batch* lane[2] = {&h->batch, &h->batch2};
     for (Batch* b : lane) if (!b->evx_ok) { for (auto& e : b->ev_x) cudaEventCreate(&e); b->evx_ok = true; }
     // chunk boundaries: uniform chunks, or (BSQ_CHUNK_FRACS="f0,f1,...") fractions of the batch -- the first chunk's upload and the
@@ -1147,7 +1175,9 @@ int align_chunked(bsq_index* h, const ReadSrc& S, uint64_t n, bsq_result** out, 
         const uint64_t s0 = start_of(c), cnt = start_of(c + 1) - s0;
         b.intv_cap = std::max(b.intv_cap, lane[(c & 1) ^ 1]->intv_cap);      // capacities learnt by one lane serve the other
         cudaEventRecord(b.ev_x[0], b.st);
+        mark("upload begin", c);
         if (upload_src(h, b, S, s0, cnt) != BSQ_OK) return BSQ_ERR;
+        mark("upload done (headers back)", c);
         cudaEventRecord(b.ev_x[1], b.st);
         // BSQ_CHUNK_SERIAL: chunk c's kernels start behind chunk c-1's (its copies still overlap them), so that an earlier chunk is
         // finished -- and its download under way -- while the later one computes, instead of both sharing the SMs to the end
@@ -1155,6 +1185,7 @@ int align_chunked(bsq_index* h, const ReadSrc& S, uint64_t n, bsq_result** out, 
         if (serial && c > 0) cudaStreamWaitEvent(b.st, lane[(c & 1) ^ 1]->ev_x[4], 0);
         const int rc2 = pipeline_enqueue(h, b);
         cudaEventRecord(b.ev_x[4], b.st);
+        mark("pipeline queued", c);
         return rc2;
     };
     struct Pending { bool on = false; uint64_t c = 0, n = 0, n_rows = 0, row_base = 0, cig_base = 0; bool host_mapq = false; } pend;
@@ -1164,7 +1195,9 @@ int align_chunked(bsq_index* h, const ReadSrc& S, uint64_t n, bsq_result** out, 
         if (cudaEventSynchronize(b.ev_x[3]) != cudaSuccess) { bsq_set_error("result download failed: %s", cudaGetErrorString(cudaGetLastError())); return BSQ_ERR; }
         float ms;
         if (cudaEventElapsedTime(&ms, b.ev_x[2], b.ev_x[3]) == cudaSuccess) h->timing.d2h += ms;
+        mark("download arrived", q.c);
         download_finish(h, R, q.n, start_of(q.c), q.n_rows, q.row_base, q.cig_base, q.host_mapq, b.ext_tmp.data());
+        mark("download finished on the host", q.c);
         return BSQ_OK;
     };
     uint64_t row_base = 0, cig_base = 0;
@@ -1173,6 +1206,7 @@ int align_chunked(bsq_index* h, const ReadSrc& S, uint64_t n, bsq_result** out, 
     for (uint64_t c = 0; c < n_chunks && rc == BSQ_OK; ++c) {
         Batch& b = *lane[c & 1];
         if ((rc = pipeline_finish(h, b)) != BSQ_OK) break;
+        mark("pipeline finished", c);
         { float ms; if (cudaEventElapsedTime(&ms, b.ev_x[0], b.ev_x[1]) == cudaSuccess) h->timing.h2d += ms; }
         if (!R) {
             // capacity of the result from the first chunk's yield
@@ -1185,6 +1219,7 @@ int align_chunked(bsq_index* h, const ReadSrc& S, uint64_t n, bsq_result** out, 
         cudaEventRecord(b.ev_x[2], b.st);
         if ((rc = download_enqueue(h, b, R, start_of(c), row_base, cig_base)) != BSQ_OK) break;
         cudaEventRecord(b.ev_x[3], b.st);
+        mark("download queued", c);
         Pending mine; mine.on = true; mine.c = c; mine.n = b.n; mine.n_rows = b.out_rows; mine.row_base = row_base; mine.cig_base = cig_base;
         mine.host_mapq = b.ctl_host[10] != 0;   // read now: the lane's control words are reused by the next chunk it takes
         row_base += b.out_rows; cig_base += b.out_cig;
@@ -1357,7 +1392,7 @@ static int tuples_resident(bsq_index* h, const ResultImpl* R, uint32_t flags, bs
             if (cudaSuccess != b.tup_off.ensure(3 * nr + 2) || cudaSuccess != b.tup_tmp.ensure(tuple_scan_tmp_elems(nr)) || cudaSuccess != b.tup_row_read.ensure(nr + 1) ||
                 cudaSuccess != b.tup_nholes.ensure(2 * nr + 2) || cudaSuccess != b.tup_rm.ensure(3 * nr + 3)) { bsq_set_error("bsq_result_tuples: out of device memory"); bad = true; break; }
             TupleParams& q = P[k];
-            q.rows = b.rows_compact.p; q.n_rows = nr; q.row_read = b.tup_row_read.p; q.cigar = b.cigar.p; q.seqs = b.ascii.p; q.offs = b.offs.p;
+            q.rows = b.rows_compact.p; q.n_rows = nr; q.row_read = b.tup_row_read.p; q.cigar = b.cigar.p - b.cig_rebased; q.seqs = b.ascii.p; q.offs = b.offs.p;
             q.pac = h->d_pac; q.l_pac = h->meta.l_pac; q.ann_offset = h->d_ann_offset;
             q.holes = d_holes; q.hole_maxend = d_maxend; q.n_holes = (uint32_t)holes.size();
             q.nholes = b.tup_nholes.p; q.off = b.tup_off.p; q.ref_match = b.tup_rm.p; q.bytes = nullptr; q.fix_reverse = (flags & BSQ_TUPLES_FIX_REVERSE) != 0;

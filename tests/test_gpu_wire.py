@@ -88,7 +88,7 @@ def test_public_rows_without_extension(gpu_lib):
     gpu.set_rows_ext(True)
     _same(full, slim, pub)
     assert not slim.rows["hash"].any() and full.rows["hash"].any()
-    assert int(t.d2h_bytes) < 2000 * 4 + 16 + len(slim.rows) * 64 + len(slim.cigar) * 4 + 64
+    assert int(t.d2h_bytes) < 2000 * 8 + 16 + len(slim.rows) * 64 + len(slim.cigar) * 4 + 64
 
 
 def test_tuples_from_resident_batch(gpu_lib):

@@ -418,6 +418,10 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+    # every rank checks ITS copy of the index (built or received by broadcast) against the text: bsq_index_verify over EVERY row and
+    # block (30 ms at c2, about a second for the 6.2 G rows of c3)
+    verify = ix.verify(1 << 40)
+    verify["unsound_ranks"] = int(allmax(0.0 if verify["sound"] else 1.0) > 0) if dist is not None else int(not verify["sound"])
     dev_ms_max = allmax(dev_ms)
     e2e_ms_max = allmax(e2e_dev_ms)
     asc_ms_max = allmax(asc_dev_ms)
@@ -487,7 +491,8 @@ def run_ours(args, rank, world, local_rank):
             "index": {"build_ms_device": meta.build_ms, "build_wall_s": build_wall, "add_ref_wall_s": t_add, "build_launches": int(meta.build_launches),
                       "sort_pass_gbs": (meta.sort_pass_bytes / (meta.build_ms * 1e-3) / 1e9) if meta.build_ms else None,
                       "seq_len": int(meta.seq_len), "broadcast_bytes": bcast_bytes, "broadcast_s": bcast_s,
-                      "derived_arrays_ms_max_over_ranks": prep_ms_max, "device_bytes": ix.device_bytes()},
+                      "derived_arrays_ms_max_over_ranks": prep_ms_max, "device_bytes": ix.device_bytes(),
+                      "verify": verify},
             "counters_per_launch": ctr,
             "parity_pinning": "unpinned (oracle restates lh3/bwa; no libbwa binary or reference vector to pin it)",
         }

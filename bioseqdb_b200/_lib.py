@@ -73,6 +73,13 @@ class BsqMeta(C.Structure):
                 ("build_launches", C.c_uint64), ("sort_pass_bytes", C.c_uint64)]
 
 
+class BsqIndexCheck(C.Structure):
+    _fields_ = [("rows", C.c_uint64), ("exhaustive", C.c_uint64), ("sa_permutation_ok", C.c_uint64), ("sa_out_of_range", C.c_uint64),
+                ("order_checked", C.c_uint64), ("order_bad", C.c_uint64), ("order_undecided", C.c_uint64),
+                ("rows_checked", C.c_uint64), ("bwt_bad", C.c_uint64), ("lf_bad", C.c_uint64),
+                ("occ_blocks_checked", C.c_uint64), ("occ_bad", C.c_uint64), ("l2_ok", C.c_uint64), ("ms", C.c_double)]
+
+
 def build_library(force: bool = False) -> str:
     """Compile libbioseqdb_gpu.so for sm_100a (nvcc cross-compiles without a GPU)."""
     if force:
@@ -143,6 +150,7 @@ def lib():
     L.bsq_set_counters.argtypes = [vp, C.c_int]
     L.bsq_get_counters.argtypes = [vp, vp]
     L.bsq_debug_ctl.argtypes = [vp, vp]
+    L.bsq_index_verify.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
     _LIB = L
     return L
 
@@ -151,7 +159,7 @@ ABI_SYMBOLS = [
     "bsq_last_error", "bsq_device_count", "bsq_opts_init", "bsq_index_new", "bsq_index_set_opts", "bsq_index_set_flags", "bsq_index_add_ref", "bsq_index_add_ref_datums", "bsq_index_build",
     "bsq_index_free", "bsq_align_batch", "bsq_align_batch_datums", "bsq_session_lrand48", "bsq_result_free", "bsq_last_timing", "bsq_result_tuples", "bsq_tuples_free", "bsq_nuclseq_from_text_batch", "bsq_nuclseqs_free", "bsq_reads_upload", "bsq_align_resident", "bsq_result_download",
     "bsq_index_get_meta", "bsq_index_device_bytes", "bsq_index_device_ptr", "bsq_index_download", "bsq_index_alloc_replica", "bsq_index_host_state_size", "bsq_index_host_state_get", "bsq_index_replica_finish", "bsq_index_prepare", "bsq_multi_new", "bsq_multi_free", "bsq_multi_devices", "bsq_multi_align_batch", "bsq_multi_align_batch_datums", "bsq_multi_last_timing", "bsq_index_bwt_plain", "bsq_index_sa_sampled",
-    "bsq_debug_seed", "bsq_debug_ksw_extend", "bsq_debug_ksw_extend_thread", "bsq_debug_ksw_global", "bsq_bench_gather", "bsq_bench_dpx", "bsq_set_counters", "bsq_get_counters", "bsq_debug_ctl",
+    "bsq_debug_seed", "bsq_debug_ksw_extend", "bsq_debug_ksw_extend_thread", "bsq_debug_ksw_global", "bsq_bench_gather", "bsq_bench_dpx", "bsq_set_counters", "bsq_get_counters", "bsq_debug_ctl", "bsq_index_verify",
 ]
 
 

@@ -191,6 +191,15 @@ class BwaIndex:
         check(self.L.bsq_index_get_meta(self.h, C.byref(m)))
         return m
 
+    def verify(self, n_samples: int = 1 << 22, seed: int = 20261018) -> dict:
+        """Device-side check of the index against its text (bsq_index_verify): every `*_bad` must be 0 and every `*_ok` 1."""
+        from ._lib import BsqIndexCheck
+        c = BsqIndexCheck()
+        check(self.L.bsq_index_verify(self.h, int(n_samples), int(seed), C.byref(c)))
+        d = {k: (float(getattr(c, k)) if k == "ms" else int(getattr(c, k))) for k, _ in BsqIndexCheck._fields_}
+        d["sound"] = bool(d["sa_permutation_ok"] and d["l2_ok"] and not (d["sa_out_of_range"] or d["order_bad"] or d["bwt_bad"] or d["lf_bad"] or d["occ_bad"]))
+        return d
+
     def device_bytes(self) -> int:
         b = C.c_uint64(0)
         check(self.L.bsq_index_device_bytes(self.h, C.byref(b)))

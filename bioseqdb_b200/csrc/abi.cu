@@ -16,6 +16,7 @@
 #include "index_build.cuh"
 #include "seed.cuh"
 #include "pipeline.cuh"
+#include "index_verify.cuh"
 #include "tuples.cuh"
 #include "loader.cuh"
 #include "primitives.cuh"
@@ -1651,6 +1652,42 @@ int bsq_last_timing(const bsq_index* h, bsq_timing* t) {
 
 int bsq_set_counters(bsq_index* h, int on) { if (!h) return BSQ_ERR; h->collect_counters = on != 0; return BSQ_OK; }
 int bsq_get_counters(const bsq_index* h, uint64_t* out8) { if (!h || !out8) return BSQ_ERR; memcpy(out8, h->counters, sizeof(h->counters)); return BSQ_OK; }
+
+int bsq_index_verify(bsq_index* h, uint64_t n_samples, uint64_t seed, bsq_index_check* out) {
+    BSQ_ENTRY();
+    if (!h || !out) { bsq_set_error("null argument"); return BSQ_ERR; }
+    if (!h->meta.built) { bsq_set_error("index not built"); return BSQ_ERR; }
+    CUDA_CHECK(cudaSetDevice(h->device));
+    const DevIndex ix = make_dev_index(h);
+    unsigned long long* d = nullptr; unsigned long long v[IV_WORDS];
+    CUDA_CHECK(cudaMalloc(&d, IV_WORDS * 8));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, h->stream);
+    launch_index_verify(ix, n_samples, seed, 65536, d, h->stream);
+    cudaEventRecord(e1, h->stream);
+    cudaError_t ce = cudaMemcpyAsync(v, d, sizeof(v), cudaMemcpyDeviceToHost, h->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    if (ce != cudaSuccess) { bsq_set_error("bsq_index_verify: %s", cudaGetErrorString(ce)); return BSQ_ERR; }
+    memset(out, 0, sizeof(*out));
+    const uint64_t n = ix.seq_len;
+    const unsigned __int128 N = n;
+    // sum and sum of squares of 0..n, exact in 128 bits (n < 2^41), compared mod 2^64
+    const uint64_t want_sum = (uint64_t)(N * (N + 1) / 2), want_sq = (uint64_t)(N * (N + 1) * (2 * N + 1) / 6);
+    out->rows = n + 1;
+    out->exhaustive = n_samples >= n + 1;
+    out->sa_permutation_ok = v[IV_SA_SUM] == want_sum && v[IV_SA_SUMSQ] == want_sq && v[IV_SA_RANGE_BAD] == 0;
+    out->sa_out_of_range = v[IV_SA_RANGE_BAD];
+    out->order_checked = v[IV_ORDER_CHECKED]; out->order_bad = v[IV_ORDER_BAD]; out->order_undecided = v[IV_ORDER_UNDECIDED];
+    out->rows_checked = v[IV_ROWS_CHECKED]; out->bwt_bad = v[IV_BWT_BAD]; out->lf_bad = v[IV_LF_BAD];
+    out->occ_blocks_checked = v[IV_OCC_CHECKED]; out->occ_bad = v[IV_OCC_BAD];
+    bool l2 = ix.L2[0] == 0;
+    for (int c = 0; c < 4; ++c) l2 = l2 && ix.L2[c + 1] - ix.L2[c] == v[IV_TEXT_CNT + c] + v[IV_TEXT_CNT + 3 - c];
+    out->l2_ok = l2;
+    out->ms = ms;
+    return BSQ_OK;
+}
 
 // the control words of the last batch's pipeline (queue sizes, tickets; layout at Batch::ctl): read after a call has ended
 int bsq_debug_ctl(bsq_index* h, uint32_t* out64) {

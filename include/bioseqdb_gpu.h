@@ -193,6 +193,22 @@ int bsq_multi_devices(const bsq_multi* m);
 int bsq_multi_align_batch(bsq_multi* m, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, bsq_result** out);
 int bsq_multi_align_batch_datums(bsq_multi* m, const uint8_t* bytes, const uint64_t* off, const int64_t* ids, uint64_t n, bsq_result** out);
 int bsq_multi_last_timing(const bsq_multi* m, bsq_timing* t);   /* total = the slowest device's time from its first copy to the end of its download */
+/* Check of the device index against the text it was built from, by kernels that share no code with the builder or the seeding
+ * kernels: SA is a permutation of 0..n (sum / sum of squares over all rows), adjacent suffixes are in order (text comparison), the BWT
+ * string is T[SA[k]-1], bwt_invPsi(k) = L2[c] + occ(k, c) lands on the row of SA[k]-1 (what bwt_sa / bwt_extend rely on, libbwa bwt.c
+ * behind reference bwa.cpp:149), the Occ checkpoints equal a recount of the blocks, L2 equals the symbol counts of the text.  Rows and
+ * blocks are sampled (n_samples draws of each) unless n_samples covers them all.  Every *_bad must be 0 and *_ok 1 for a sound index. */
+typedef struct bsq_index_check {
+    uint64_t rows;                 /* n + 1 */
+    uint64_t exhaustive;           /* 1: every row and block was checked */
+    uint64_t sa_permutation_ok, sa_out_of_range;
+    uint64_t order_checked, order_bad, order_undecided;   /* undecided: equal over the comparison limit (64 Ki symbols) */
+    uint64_t rows_checked, bwt_bad, lf_bad;
+    uint64_t occ_blocks_checked, occ_bad;
+    uint64_t l2_ok;
+    double ms;
+} bsq_index_check;
+int bsq_index_verify(bsq_index* h, uint64_t n_samples, uint64_t seed, bsq_index_check* out);
 int bsq_index_bwt_plain(const bsq_index* h, uint32_t* out);               /* the u32 stream of bwa.cpp:48-50 */
 int bsq_index_sa_sampled(const bsq_index* h, uint64_t* out, uint64_t n_sa); /* bwt_cal_sa(bwt, 32) view */
 

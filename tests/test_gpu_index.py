@@ -35,6 +35,9 @@ def _check_index(orc, gpu):
     rng = np.random.default_rng(5)
     for k in rng.integers(1, oi["seq_len"] + 1, size=300):
         assert int(sa[int(k)]) == orc.bwt_sa(int(k))
+    # the device-side verifier (no code shared with the builder) agrees: every row and block, nothing undecided on these texts
+    chk = gpu.verify(n_samples=1 << 40)
+    assert chk["sound"] and chk["exhaustive"] == 1 and chk["rows_checked"] == oi["seq_len"] + 1 and chk["order_checked"] == oi["seq_len"], chk
 
 
 @pytest.mark.parametrize("lens", [[1000], [997, 1503, 64], [200_003, 150_001, 99_999]])
@@ -80,3 +83,66 @@ def test_index_wide_path_small(gpu_lib, monkeypatch, text):
         ids = synth.lrand48_ids_fast(800)
         bad = compare_results(gpu.align_batch(seqs, offs, ids), orc.align_batch(seqs, offs, ids, 2))
         assert not bad, "\n".join(bad)
+
+
+def _device_view(gpu, what, dtype):
+    """torch view of one of the index's device arrays (the handle the multi-GPU broadcast writes through)."""
+    import ctypes as C
+    import torch
+    from bioseqdb_b200.dist import _CudaArray
+    p = C.c_void_p()
+    _lib.check(gpu.L.bsq_index_device_ptr(gpu.h, what, C.byref(p)))
+    n = int(gpu.meta().arr_bytes[what])
+    return torch.as_tensor(_CudaArray(p.value, n), device="cuda").view(dtype)
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_index_verifier_catches_corruption(gpu_lib, monkeypatch, wide):
+    """bsq_index_verify is the check the 6.2 G-row index gets (nothing else can look at it): here it must pass a sound index and name
+    each kind of damage -- two suffix-array rows swapped, one BWT symbol changed, one Occ checkpoint off by one."""
+    import torch
+    if wide:
+        monkeypatch.setenv("BSQ_FORCE_WIDE", "1")
+    rows = synth.reference_rows([50_001, 30_003], seed=77)
+    _, gpu = build_pair(rows, O.sql_default_opts(2))
+    assert gpu.meta().sa_bytes == (8 if wide else 4)
+    ok = gpu.verify(n_samples=1 << 40)
+    assert ok["sound"] and ok["order_undecided"] == 0, ok
+    sampled = gpu.verify(n_samples=5000)
+    assert sampled["sound"] and sampled["exhaustive"] == 0 and sampled["rows_checked"] == 5000, sampled
+    sa = _device_view(gpu, _lib.ARR_SA, torch.int64 if wide else torch.int32)
+    occ = _device_view(gpu, _lib.ARR_OCC, torch.int32)
+    # (1) two rows of the suffix array swapped: still a permutation, no longer sorted, LF and BWT break at those rows
+    a, b = int(sa[1000]), int(sa[1001])
+    sa[1000], sa[1001] = b, a
+    torch.cuda.synchronize()
+    bad = gpu.verify(n_samples=1 << 40)
+    assert not bad["sound"] and bad["sa_permutation_ok"] == 1 and bad["order_bad"] >= 1 and bad["lf_bad"] >= 1, bad
+    sa[1000], sa[1001] = a, b
+    # (2) a duplicated entry: not a permutation any more
+    sa[2000] = int(sa[2001])
+    torch.cuda.synchronize()
+    bad = gpu.verify(n_samples=1 << 40)
+    assert not bad["sound"] and bad["sa_permutation_ok"] == 0, bad
+    # restore the entry from a second build of the same rows
+    _, fresh = build_pair(rows, O.sql_default_opts(2))
+    good_sa = fresh.download(_lib.ARR_SA).view(np.uint64 if wide else np.uint32)
+    sa[2000] = int(good_sa[2000])
+    torch.cuda.synchronize()
+    assert gpu.verify(n_samples=1 << 40)["sound"]
+    # (3) one BWT symbol changed (block 3, first word): the BWT check, LF and the block recount notice
+    w = int(occ[3 * 16 + 8])
+    occ[3 * 16 + 8] = w ^ (1 << 30)
+    torch.cuda.synchronize()
+    bad = gpu.verify(n_samples=1 << 40)
+    assert not bad["sound"] and bad["bwt_bad"] >= 1 and bad["occ_bad"] >= 1, bad
+    occ[3 * 16 + 8] = w
+    # (4) one checkpoint count off by one
+    c = int(occ[5 * 16])
+    occ[5 * 16] = c + 1
+    torch.cuda.synchronize()
+    bad = gpu.verify(n_samples=1 << 40)
+    assert not bad["sound"] and bad["occ_bad"] >= 1 and bad["lf_bad"] >= 1, bad
+    occ[5 * 16] = c
+    torch.cuda.synchronize()
+    assert gpu.verify(n_samples=1 << 40)["sound"]

@@ -117,6 +117,9 @@ struct bsq_index {
     uint32_t* d_kmer_z = nullptr;    // sizes-only copy of the prefix table
     void* d_kmer = nullptr; int kmer_k = 0;          // k-mer table of the LAST-like seeding pass (built lazily per device index)
     bool collect_counters = false;
+    int kmer_k_cap = 15;                   // lowered when the batch pools did not fit beside the table (kmer_downgrade)
+    bool alloc_failed = false;             // the last pipeline_enqueue stopped on cudaErrorMemoryAllocation
+    int test_pool_oom = getenv("BSQ_TEST_POOL_OOM") ? atoi(getenv("BSQ_TEST_POOL_OOM")) : 0;   // test hook: that many pool allocations "fail"
     int prio_hi = 0, prio_lo = 0;          // stream priorities of the two lanes of the chunked pipeline
     uint32_t flags = 0;              // BSQ_FLAG_*
     uint64_t lrand_state = 0;        // glibc lrand48 state of the session (one draw per aligned read when the caller passes no ids)
@@ -728,17 +731,33 @@ int ensure_kmer_table(bsq_index* h, const DevIndex& ix) {
     // One level more than ceil(log4 n) where HBM allows it (23 GB at K = 15): a K-mer of the read's own locus then has a second,
     // chance occurrence three times less often, and every such occurrence costs the seeding kernels real bwt_extend steps
     // (measured at 200 M symbols: 13.6 -> 12.3 ms per 1 M reads).  Only for 32-bit indexes; the 64-bit ones keep their HBM for SA + ISA.
-    if (h->kmer_k == 14 && ix.sa_bytes == 4 && ix.seq_len > (1ull << 27)) {
+    if (h->kmer_k == 14 && ix.seq_len > (1ull << 27)) {
         size_t fr = 0, tot = 0;
-        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && fr > 4 * kmer_table_bytes(15)) h->kmer_k = 15;
+        const size_t want = kmer_table_bytes(15) + kmer_table_bytes(15) / 4;     // entries + the size table
+        // 32-bit indexes: when the table is a quarter of what is free.  64-bit ones (SA + ISA already hold 16 bytes per symbol): when 40 GB
+        // stay free for the batch pools of two lanes (c3: 77 GB free -> 28.6 GB table; measured 28.5 -> 25.9 ms seeding per 1.25 M reads).
+        // If the pools do not fit after all, the pipeline drops a level and goes on (kmer_downgrade).
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && (ix.sa_bytes == 4 ? fr > 4 * kmer_table_bytes(15) : fr > want + (40ull << 30))) h->kmer_k = 15;
     }
     if (const char* e = getenv("BSQ_KMER_K")) { const int k = atoi(e); if (k >= 8 && k <= 15) h->kmer_k = k; }
+    if (h->kmer_k > h->kmer_k_cap) h->kmer_k = h->kmer_k_cap;
     CUDA_CHECK(cudaMalloc(&h->d_kmer, kmer_table_bytes(h->kmer_k)));
     build_kmer_table(ix, h->d_kmer, h->kmer_k, h->stream, &h->timing.launches);
     if (!getenv("BSQ_NO_KMER_Z") && cudaMalloc(&h->d_kmer_z, kmer_table_bytes(h->kmer_k) / 4) == cudaSuccess) build_kmer_sizes(h->d_kmer, h->d_kmer_z, h->kmer_k, h->stream, &h->timing.launches);
     else { h->d_kmer_z = nullptr; cudaGetLastError(); }
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
     return BSQ_OK;
+}
+
+// Device memory ran out while sizing a batch's pools: give back the deepest level of the prefix table (three quarters of it) and let
+// ensure_kmer_table rebuild the shallower one.  cudaFree waits for everything already queued, so no kernel loses the table under it.
+bool kmer_downgrade(bsq_index* h) {
+    if (!h->d_kmer || h->kmer_k <= 8) return false;
+    cudaFree(h->d_kmer); h->d_kmer = nullptr;
+    if (h->d_kmer_z) { cudaFree(h->d_kmer_z); h->d_kmer_z = nullptr; }
+    h->kmer_k_cap = h->kmer_k - 1;
+    cudaGetLastError();
+    return true;
 }
 
 // the seeding kernel's view of a batch: inputs, per-read interval slots, the index's derived arrays, control words
@@ -758,7 +777,19 @@ SeedParams seed_params(const bsq_index* h, const Batch& b, const DevIndex& ix, u
 
 // One attempt of the kernel pipeline on the batch's stream: size the pools, launch every stage, read the control
 // words back asynchronously.  Nothing here waits for the device.
+static int pipeline_enqueue_once(bsq_index* h, Batch& b);
 int pipeline_enqueue(bsq_index* h, Batch& b) {
+    h->alloc_failed = false;
+    int rc = pipeline_enqueue_once(h, b);
+    for (int tries = 0; rc != BSQ_OK && h->alloc_failed && tries < 2 && kmer_downgrade(h); ++tries) {
+        h->alloc_failed = false;
+        h->timing.notes |= BSQ_NOTE_TABLE_DOWNGRADED;
+        rc = pipeline_enqueue_once(h, b);
+        if (rc == BSQ_OK) bsq_set_error("");
+    }
+    return rc;
+}
+static int pipeline_enqueue_once(bsq_index* h, Batch& b) {
     if (!b.resident) { bsq_set_error("no reads uploaded"); return BSQ_ERR; }
     const uint32_t n = (uint32_t)b.n;
     bsq_timing& T = h->timing;
@@ -789,7 +820,8 @@ int pipeline_enqueue(bsq_index* h, Batch& b) {
         int fit = (int)std::max<size_t>(budget / fin_per_warp, 4 * 148);
         fin_warps = std::min(fin_warps, fit) / 4 * 4;
     }
-#define ENS(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { bsq_set_error("allocating batch pools: %s", cudaGetErrorString(e_)); return BSQ_ERR; } } while (0)
+#define ENS(x) do { cudaError_t e_ = (x); if (e_ == cudaSuccess && h->test_pool_oom > 0) { --h->test_pool_oom; e_ = cudaErrorMemoryAllocation; } \
+    if (e_ != cudaSuccess) { if (e_ == cudaErrorMemoryAllocation) h->alloc_failed = true; cudaGetLastError(); bsq_set_error("allocating batch pools: %s", cudaGetErrorString(e_)); return BSQ_ERR; } } while (0)
     ENS(b.intv.ensure((size_t)n * b.intv_cap)); ENS(b.intv_cnt.ensure(n));
     ENS(b.seed_scratch.ensure((size_t)seed_warps * 3 * b.list_cap));
     ENS(b.raw.ensure(b.pool_cap)); ENS(b.seeds.ensure(b.pool_cap)); ENS(b.ctmp.ensure(b.pool_cap)); ENS(b.ord.ensure(b.pool_cap));

@@ -68,6 +68,7 @@ typedef struct bsq_result {
 
 /* per-stage device timings of the last bsq_align_batch / bsq_align_resident call, milliseconds */
 #define BSQ_NOTE_CHUNK_FALLBACK 1u /* bsq_align_batch: the result outgrew the chunk pipeline's estimate, the batch was re-run in one pass */
+#define BSQ_NOTE_TABLE_DOWNGRADED 2u /* device memory was short for the batch pools: the seeding prefix table gave up its deepest level */
 typedef struct bsq_timing {
     float h2d, seed, chain, extend, finalize, d2h, total;
     uint32_t notes;    /* BSQ_NOTE_* bits: things a successful call wants its caller to know (never an error; see bsq_last_error for those) */

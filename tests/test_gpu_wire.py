@@ -115,3 +115,24 @@ def test_tuples_from_resident_batch(gpu_lib):
             res2, tup2 = gpu.align_tuples_datums(data, off, ids, flags)
             ref2 = gpu.tuples(res2, seqs, offs, flags)
             assert np.array_equal(tup2.off, ref2.off) and np.array_equal(tup2.data, ref2.data) and np.array_equal(tup2.ref_match, ref2.ref_match)
+
+
+def test_pool_oom_drops_a_table_level(gpu_lib, monkeypatch):
+    """Device memory short while sizing the batch pools (simulated: BSQ_TEST_POOL_OOM makes one pool allocation fail): the library gives back
+    the deepest level of the seeding prefix table, rebuilds the shallower one and finishes the call; the rows do not change (the table
+    only shortcuts bwt_extend), the call says so in bsq_timing.notes, and the next call runs without incident."""
+    from helpers import compare_results
+    monkeypatch.setenv("BSQ_TEST_POOL_OOM", "1")
+    rows = synth.reference_rows([150_001, 100_003], seed=151)
+    orc, gpu = build_pair(rows, O.sql_default_opts(2))
+    seqs, offs, _ = synth.simulate_reads(rows, 3000, 150, seed=152)
+    ids = synth.lrand48_ids_fast(3000)
+    g = gpu.align_batch(seqs, offs, ids)
+    assert gpu.timing().notes & 2                       # BSQ_NOTE_TABLE_DOWNGRADED
+    assert gpu.L.bsq_last_error() == b""
+    o = orc.align_batch(seqs, offs, ids, 4)
+    bad = compare_results(g, o)
+    assert not bad, "\n".join(bad)
+    g2 = gpu.align_batch(seqs, offs, ids)
+    assert not (gpu.timing().notes & 2)
+    assert not compare_results(g2, o)

@@ -470,6 +470,7 @@ ST_HD int seed_strategy1(const Index<IdxT>& X, const Opts& o, const Read& R, int
 // therefore evaluated together -- K-mer entries, then (one occurrence) SA rows, text words, ISA rows: each group of loads in flight at
 // once -- and consumed in order for as long as each start is the predicted one and was decidable without Occ.
 constexpr int LAST_BATCH = 8;
+constexpr int MWL = 4;                       // K-mer occurrences the LAST-like pass settles by text comparison
 template <class IdxT> ST_HD void last_like_pass(const Index<IdxT>& X, const Opts& o, const Read& R, Work<IdxT>& W) {
     if (o.max_mem_intv <= 0) return;
     const int len = R.len, K = X.kk, min_len = o.min_seed_len, L = min_len + 1;
@@ -501,6 +502,36 @@ template <class IdxT> ST_HD void last_like_pass(const Index<IdxT>& X, const Opts
             }
             x += done * L;
             if (done == nb || W.fail) continue;
+            // The start at x stopped the batch.  A K-mer with a handful of occurrences (fewer than max_mem_intv) is decided the same way
+            // as the unique one, from the text: the L-mer's occurrences are those of the K-mer whose next L - K bases match the read;
+            // they are consecutive rows of the K-mer's interval (the longer pattern's interval lies inside the shorter one's), and the
+            // reverse-strand row is the smallest row of their reverse-complement occurrences.  No Occ block is touched.
+            U4 em; em.x = em.y = em.z = em.w = 0;
+#pragma unroll
+            for (int k = 0; k < LAST_BATCH; ++k) if (k == done) em = e[k];
+            if (em.z >= 2u && em.z <= (uint32_t)MWL && em.z < (uint32_t)o.max_mem_intv) {
+                const IdxT b0 = tab_x0<IdxT>(em);
+                IdxT pp[MWL]; bool hh[MWL];
+#pragma unroll
+                for (int t = 0; t < MWL; ++t) pp[t] = t < (int)em.z ? ld_idx(X.sa + b0 + (IdxT)t) : (IdxT)0;
+#pragma unroll
+                for (int t = 0; t < MWL; ++t) hh[t] = t < (int)em.z && match_run_fwd(X, R, (IdxT)(pp[t] + (IdxT)K), x + K, L - K) == L - K;
+                uint32_t cnt = 0; int tfirst = 0;
+#pragma unroll
+                for (int t = MWL - 1; t >= 0; --t) if (hh[t]) { ++cnt; tfirst = t; }
+                if (cnt) {
+                    IdxT rr[MWL];
+#pragma unroll
+                    for (int t = 0; t < MWL; ++t) rr[t] = hh[t] ? ld_idx(X.isa + (X.n - pp[t] - (IdxT)L)) : (IdxT)0;
+                    IdxT rmin = 0; bool have = false;
+#pragma unroll
+                    for (int t = 0; t < MWL; ++t) if (hh[t] && (!have || rr[t] < rmin)) { rmin = rr[t]; have = true; }
+                    emit(W, (IdxT)(b0 + (IdxT)tfirst), rmin, cnt, x, x + L);
+                }
+                W.n_ext += (unsigned long long)min_len;
+                x += L;
+                continue;
+            }
         }
         if (x + K > len) {
             // fewer than K bases left: no table entry; the walk cannot emit (i - x < min_len), only its extensions count

@@ -96,7 +96,10 @@ int bsq_index_build(bsq_index* h);
 void bsq_index_free(bsq_index* h);
 
 /* reads: concatenated ASCII (what BwaIndex::align_sequence hands to mem_align1 after to_text_palloc,
- * bwa.cpp:146-149), offs[n+1], ids[n] = the values lrand48() would have returned. */
+ * bwa.cpp:146-149), offs[n+1], ids[n] = the values lrand48() would have returned.
+ * Large batches run as two chunks whose host<->device copies overlap the other chunk's kernels; that overlap needs PAGE-LOCKED host
+ * buffers (cudaHostAlloc / cudaHostRegister).  Pageable buffers are accepted -- the driver then stages every copy synchronously and
+ * the call is correct but slower.  The result block itself is always page-locked (the library's own allocation). */
 int bsq_align_batch(bsq_index* h, const char* seqs, const uint64_t* offs, const int64_t* ids, uint64_t n, bsq_result** out);
 /* The same call with the reads as they sit in the database: n NUCLSEQ datum images (sequence.h:18-38), image i at bytes + off[i],
  * off[n + 1] -- what iterate_nuclseq_table holds for every query row (extension.cpp:362) BEFORE to_text_palloc expands it to one

@@ -191,14 +191,19 @@ __device__ __forceinline__ int gen_cigar_band(const DevOpts& o, int l_query, int
     return w > min_w ? w : min_w;
 }
 
-// 0: align on the warp here; 1: thread-per-region narrow-band DP; 2: thread-per-region, no DP (equal lengths, zero band)
-__device__ __forceinline__ int narrow_class(const DevOpts& o, const RegRec& ar, uint32_t max_len) {
+__device__ __forceinline__ bool narrow_is_tight(const DevOpts& o, int lq, int rlen, bool simple_mat, int wt);
+// 0: align on the warp here; 1: thread-per-region narrow-band DP; 2: thread-per-region, no DP (equal lengths, zero band).
+// tight_ok: the tight passes are on and the matrix is the plain one -- then a region whose band is wider than any thread kernel's
+// still gets its first try there (the proof of the tight passes does not care how wide the band asked for is; a region they cannot
+// settle travels on to the exact-band lists, whose kernels hand a band they do not hold to the warp-cooperative one).
+__device__ __forceinline__ int narrow_class(const DevOpts& o, const RegRec& ar, uint32_t max_len, bool tight_ok) {
     const int lq = ar.qe - ar.qb; const int64_t rl = ar.re - ar.rb;
     if (max_len > NARROW_QMAX || lq <= 0 || rl <= 0 || rl > NARROW_TMAX) return 0;
     int w2 = reg2aln_w2(o, ar);
     w2 = w2 < o.w << 2 ? w2 : o.w << 2;
     if (lq == rl) return 2;   // equal lengths: first a thread checks whether the gap-free diagonal is provably the unique optimum
-    return 2 * gen_cigar_band(o, lq, (int)rl, w2) + 1 <= NARROW_NC ? 1 : 0;
+    if (2 * gen_cigar_band(o, lq, (int)rl, w2) + 1 <= NARROW_NC) return 1;
+    return tight_ok && narrow_is_tight(o, lq, (int)rl, true, 8) ? 1 : 0;
 }
 
 // the register-band kernel derives scores from the three values bwa_fill_scmat produces (match, mismatch, ambiguous)
@@ -225,6 +230,7 @@ __device__ __forceinline__ bool narrow_is_big(const DevOpts& o, int lq, int rlen
 }
 // the tight pass takes a region when the register kernels can score it and the end cell lies inside the tight window
 __device__ __forceinline__ bool narrow_is_tight(const DevOpts& o, int lq, int rlen, bool simple_mat, int wt = REG_WT3) {
+    static_assert(REG_WT3 == 8, "narrow_class passes the literal");
     const int dl = lq - rlen;
     return simple_mat && (dl < 0 ? -dl : dl) <= wt && o.o_del >= 0 && o.e_del >= 0 && o.o_ins >= 0 && o.e_ins >= 0 && o.mat_max > 0;
 }
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(128) regs_finalize_thread(FinalizeParams P, De
         if (n == 0) { P.row_cnt[r] = 0; done = true; }
         else if (n == 1) {
             RegRec ar = P.regs[blk.base];
-            const int ncls = narrow_class(o, ar, P.max_len);
+            const int ncls = narrow_class(o, ar, P.max_len, P.narrow_tight && mat_is_simple(o.mat));
             if (ncls != 0) {
                 ar.sub = 0; ar.secondary = -1; ar.hash = hash_64((uint64_t)P.ids[r]);      // mem_mark_primary_se, n == 1
                 P.regs[blk.base] = ar;
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 6) regs_finalize(FinalizeParams P
         for (int i = 0; i < n; ++i) {
             const RegRec ar = a[i];
             RowDev row = row_from_reg(ar, P.ann_id);
-            const int ncls = P.narrow_jobs != nullptr ? narrow_class(o, ar, P.max_len) : 0;
+            const int ncls = P.narrow_jobs != nullptr ? narrow_class(o, ar, P.max_len, P.narrow_tight && simple_mat) : 0;
             const bool narrow = ncls != 0;
             if (lane == 0) {
                 rows[i] = row;

@@ -77,3 +77,25 @@ def test_tight_band_result_is_the_full_band_result(oracle, opts_fn):
                     held[wt] += 1
     print("tight-band claim: windows tried", tried, "premise held", held)
     assert tried > 4000 and held[4] > 0.3 * tried / 2 and held[8] > held[4] * 0.9, (tried, held)
+
+
+@pytest.mark.parametrize("opts_fn", [O.sql_default_opts, O.canonical_opts])
+def test_diagonal_proof_of_the_equal_length_pass(oracle, opts_fn):
+    """Pass 0 of the finalize stage (regs_cigar_narrow<5>): for a region with lq == rlen, a gap-free diagonal scoring more than
+    (lq - 1) max(mat) - oe_ins - oe_del is the unique optimum of ksw_global2 under EVERY band -- CIGAR lq M, score = the diagonal's."""
+    L = O.lib()
+    opts = opts_fn(1)
+    rng = np.random.default_rng(7)
+    held = 0
+    for it in range(1500):
+        n = int(rng.integers(20, 180))
+        t = rng.integers(0, 4, size=n).astype(np.uint8) if it % 2 else np.repeat(rng.integers(0, 4, size=n // 2 + 1), rng.integers(1, 5, size=n // 2 + 1))[:n].astype(np.uint8)
+        q = np.where(rng.random(n) < rng.choice([0.0, 0.01, 0.03]), rng.integers(0, 4, size=n), t).astype(np.uint8)
+        diag = int(np.sum(np.where(q == t, 1, -4)))
+        if diag <= (n - 1) * 1 - (opts.o_ins + opts.e_ins) - (opts.o_del + opts.e_del):
+            continue
+        held += 1
+        for w in (1, 5, 37, 100):
+            sc, cig = _global(L, q, t, opts, w)
+            assert sc == diag and cig == [n << 4], (it, w, n, diag, sc, cig)
+    assert held > 700, held

@@ -90,6 +90,7 @@ def test_diagonal_proof_of_the_equal_length_pass(oracle, opts_fn):
     for it in range(1500):
         n = int(rng.integers(20, 180))
         t = rng.integers(0, 4, size=n).astype(np.uint8) if it % 2 else np.repeat(rng.integers(0, 4, size=n // 2 + 1), rng.integers(1, 5, size=n // 2 + 1))[:n].astype(np.uint8)
+        n = len(t)
         q = np.where(rng.random(n) < rng.choice([0.0, 0.01, 0.03]), rng.integers(0, 4, size=n), t).astype(np.uint8)
         diag = int(np.sum(np.where(q == t, 1, -4)))
         if diag <= (n - 1) * 1 - (opts.o_ins + opts.e_ins) - (opts.o_del + opts.e_del):
